@@ -1,0 +1,33 @@
+"""CPU oracle for the MR-Flow plane+parallax hot path.
+
+TEST INFRASTRUCTURE ONLY.  Nothing under ``mrflow_b200/`` may import this package; the only
+permitted users are ``tests/``, ``__graft_entry__.smoke()`` and the ``cpu_baseline`` /
+``--impl reference`` legs of ``bench.py`` (as the checker / the timed CPU arm, never as the
+product).
+
+What it is: a numpy + OpenCV restatement of the reference functions on the path named by
+SURVEY.md section 8a, each function citing the reference file:line it follows.  The reference is
+Python, so the restatement calls the very same third-party primitives the reference calls
+(``cv2.remap``, ``cv2.perspectiveTransform``, ``cv2.cvtColor``, ``cv2.GaussianBlur``,
+``cv2.erode``, ``scipy.special.ive``; OpenCV 4.13.0 / scipy 1.18.1 in this image -- the reference
+pins neither, README.md:19 only says "OpenCV >= 3.0").  ``oracle.cvemul`` additionally restates
+those OpenCV primitives in plain numpy, bit-exactly, so the CUDA kernels have an arithmetic
+specification that does not depend on OpenCV's binary.
+
+Parity status
+-------------
+* a1-a8, a10 (flow<->structure maps, sampler, robust functions, rigidity unaries): PINNED.
+  ``tests/golden/make_golden.py`` imports the real reference from ``/root/reference`` (with the
+  import shims of SURVEY.md section 8c, none of which alters arithmetic) and stores its outputs on
+  seeded inputs in ``tests/golden/*.npz``; ``tests/test_oracle_golden.py`` checks this oracle
+  against them.
+* a11 (``computeDataTerm`` residual + energy): PINNED the same way (energy ``E_data`` and the
+  residual image of the reference function on a seeded pair).
+* a12 (the per-label cost volume): the reference's arithmetic for this step lived in a compiled
+  extension that is NOT shipped (``pipeline/build_cost_volume.py:26-27``).  The oracle composes
+  it from shipped reference functions exactly as SURVEY.md section 8c defines; each label plane is
+  pinned against the reference's own ``computeDataTerm`` geometry + ``interpolate_through_H`` +
+  ``robust_functions`` run at that label (golden ``costvol_*.npz``), but the *choice* of
+  composition (rho, sigma0, channels) is ours: for a12 as a whole, "parity unpinned" by the
+  reference's own tests -- it has none.
+"""

@@ -1,0 +1,163 @@
+#!/usr/bin/env python
+"""Generate tests/golden/*.npz by running the REAL reference (/root/reference) on seeded inputs.
+
+Run in the authoring container only (the GPU box has no /root/reference):
+
+    python tests/golden/make_golden.py
+
+Import shims (none alters arithmetic): sys.path entries for the
+reference's Python-2 implicit relative imports, MRFLOW_HOME, a stub ``chumpy`` module (only
+``refine_A`` / the epipole BFGS use it; both are bypassed below), ``np.float`` alias, stub
+matplotlib-free ``utils.plot_debug`` / ``utils.compute_figure`` modules.
+
+The fixtures are small (a 96x72 triplet, crops and checksums); whole volumes are not stored.
+"""
+import os
+import sys
+import types
+import hashlib
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+REF = "/root/reference"
+
+
+def import_reference():
+    os.environ["MRFLOW_HOME"] = REF
+    for p in (REF, REF + "/structure_refinement", REF + "/utils"):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    if not hasattr(np, "float"):
+        np.float = float
+    ch_mod = types.ModuleType("chumpy")
+    ch_mod.ch = types.SimpleNamespace()
+    sys.modules.setdefault("chumpy", ch_mod)
+    for name in ("utils.plot_debug", "utils.compute_figure", "utils.print_exception", "utils.spyder_debug"):
+        m = types.ModuleType(name)
+        m.__dict__["__all__"] = []
+        sys.modules.setdefault(name, m)
+    import utils  # noqa: F401  (reference package)
+    for name in ("plot_debug", "compute_figure", "print_exception", "spyder_debug"):
+        setattr(sys.modules["utils"], name, sys.modules["utils." + name])
+    from utils import flow_homography, robust_functions
+    from pipeline import compute_structure as cs
+    from pipeline import structure2flow as s2f
+    from rigidity import inference
+    import interpolate_through_H as ith
+    import optimize_structure_single_scale as oss
+    return dict(fh=flow_homography, rf=robust_functions, cs=cs, s2f=s2f, inf=inference, ith=ith, oss=oss)
+
+
+def sha(a):
+    return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+
+
+def main():
+    sys.path.insert(0, ROOT)
+    from mrflow_b200 import synth
+    ref = import_reference()
+    fh, rf, cs, s2f, inf, ith, oss = (ref[k] for k in ("fh", "rf", "cs", "s2f", "inf", "ith", "oss"))
+    import cv2
+    import argparse
+
+    for tag, kw in (("outside", dict(shape=(72, 96), seed=7, epipole="outside", flow_noise=0.02)),
+                    ("inside", dict(shape=(72, 96), seed=8, epipole="inside", moving_objects=True))):
+        t = synth.make_triplet(n_waves=8, **kw)
+        h, w = t["shape"]
+        y, x = np.mgrid[:h, :w]
+        out = {}
+        # --- a1 / a2 / a3 ------------------------------------------------------------------
+        par, dists, res = [], [], []
+        for f in range(2):
+            ur, vr = fh.get_residual_flow(x, y, t["flow"][f][0], t["flow"][f][1], t["homographies"][f])
+            p, fv, d = cs.flow2parallax(ur, vr, t["epipoles"][f])
+            out["u_res%d" % f], out["v_res%d" % f] = ur, vr
+            out["parallax%d" % f], out["dists%d" % f] = p, d
+            par.append(p); dists.append(d); res.append((ur, vr))
+        mu = [d.mean() for d in dists]
+        out["mu"] = np.array(mu)
+        for f, B in ((0, -0.37), (1, 0.41)):
+            out["structure%d" % f] = cs.parallax2normedstructure(par[f], t["epipoles"][f], B, mu[f])
+        # --- a6 ----------------------------------------------------------------------------
+        params = argparse.Namespace(debug_compute_figure=0)
+        u, v = s2f.structure_to_flow(out["structure1"], t["epipoles"][1], mu[1], t["homographies"][1], 0.41, params)
+        out["s2f_u"], out["s2f_v"] = u, v
+        rig01 = (t["rigidity"] > 0.5).astype(np.float64)
+        _, cu, cv = s2f.combine_flow(out["structure1"], t["flow"][1], rig01, t["epipoles"], mu,
+                                     t["homographies"], [-0.37, 0.41], t["images"], params)
+        out["combine_u"], out["combine_v"] = cu, cv
+        # --- a7 ----------------------------------------------------------------------------
+        for f in range(2):
+            out["unary%d" % f] = inf.get_unaries_rigid(x, y, res[f][0], res[f][1],
+                                                       t["epipoles"][f][0], t["epipoles"][f][1], sigma=1.0)
+        # --- a8 ----------------------------------------------------------------------------
+        rs = np.random.RandomState(99)
+        I = rs.rand(h, w, 3) * 255
+        xn = x + rs.uniform(-6, 6, (h, w))
+        yn = y + rs.uniform(-6, 6, (h, w))
+        J, m = ith.interpolate_through_H(I, t["homographies"][1], xn, yn, compute_derivs=False)
+        out["ith_I"], out["ith_xn"], out["ith_yn"], out["ith_J"], out["ith_mask"] = I, xn, yn, J, m
+        # --- a10 ---------------------------------------------------------------------------
+        z = (rs.standard_normal(4001) * 3) ** 2
+        out["rho_x"] = z
+        gens = dict(lor_fixed=rf.generate_lorentzian(1.5), lor_auto=rf.generate_lorentzian(),
+                    charb_fixed=rf.generate_charbonnier(1e-3), charb_auto=rf.generate_charbonnier(),
+                    charb_a=rf.generate_charbonnier(0.01, 0.45), gm_fixed=rf.generate_geman_mcclure(2.0),
+                    gm_auto=rf.generate_geman_mcclure(), quad=rf.generate_quadratic())
+        for k, (fn, dfn) in gens.items():
+            out["rho_" + k], out["drho_" + k] = fn(z), dfn(z)
+        # --- a11: channels exactly as optimize_structure_single_scale.py:350-371 builds them ----
+        chans = []
+        for Iim in t["images"]:
+            g = cv2.cvtColor(Iim.astype("float32"), cv2.COLOR_RGB2GRAY).astype("float64") * 255.0
+            gy, gx = np.gradient(g)
+            gy = cv2.GaussianBlur(gy, ksize=(3, 3), sigmaX=-1)
+            gx = cv2.GaussianBlur(gx, ksize=(3, 3), sigmaX=-1)
+            chans.append(np.dstack((g, gy, gx)))
+        cw = np.concatenate((0.01 * np.array([1.0]), [1.0, 1.0]))
+        rig = rig01
+        occ = (rs.rand(h, w) < 0.05).astype(np.float64)
+        robust_ev, robust_deriv = rf.generate_lorentzian(1.0)
+        # computeDataTerm needs scipy.ndimage / sparse names from its module namespace
+        for f, (B, nb) in enumerate(((-0.37, 0), (0.41, 2))):
+            A = out["structure1"] * (mu[0] / mu[1] if f == 0 else 1.0)
+            A = np.nan_to_num(A, posinf=0.0, neginf=0.0)
+            _, _, E = oss.computeDataTerm(A, chans[1], chans[nb], rig, occ, t["homographies"][f], B, mu[f],
+                                          t["epipoles"][f], robust_ev, robust_deriv, 0.0, cw)
+            out["dataterm_A%d" % f] = A
+            out["dataterm_E%d" % f] = np.array(E)
+        out["dataterm_occ"] = occ
+        out["dataterm_rig"] = rig
+        # --- a12: per-label planes from the reference geometry + sampler + rho ----------------
+        labels = np.linspace(-3.0, 4.5, 7)
+        planes = np.zeros((2, len(labels), h, w), np.float32)
+        for f, (B, nb) in enumerate(((-0.37, 0), (0.41, 2))):
+            q = t["epipoles"][f]
+            H = t["homographies"][f]
+            for li, lab in enumerate(labels):
+                a = lab * (mu[0] / mu[1] if f == 0 else 1.0)
+                # geometry lines :210-235 evaluated through the reference function itself is not
+                # separable from its linearisation, so replay them here verbatim in spirit with
+                # the reference's own sampler and rho.
+                vx = q[0] - x; vy = q[1] - y
+                nrm = np.maximum(0.5, np.sqrt(vx ** 2 + vy ** 2))
+                n = np.sqrt(vx ** 2 + vy ** 2) / mu[f]
+                r = a * B * n / (B * a / mu[f] - 1)
+                J, m = ith.interpolate_through_H(chans[nb], H, x + r * (vx / nrm), y + r * (vy / nrm),
+                                                 compute_derivs=False)
+                Iz = ((J - chans[1]) * cw[np.newaxis, np.newaxis, :]).mean(axis=2)
+                Iz[m == 0] = 0; Iz[occ == 1] = 0; Iz[rig == 0] = 0
+                planes[f, li] = robust_ev(Iz ** 2)
+        out["cv_labels"] = labels
+        out["cv_cost_sha"] = np.array(sha(planes))
+        out["cv_cost_crop"] = planes[:, :, 20:36, 30:62].copy()
+        out["cv_argmin"] = planes.argmin(axis=1).astype(np.int32)
+        out["cv_min"] = planes.min(axis=1)
+        np.savez_compressed(os.path.join(HERE, "ref_%s.npz" % tag), **out)
+        print(tag, "written:", len(out), "arrays")
+
+
+if __name__ == "__main__":
+    main()

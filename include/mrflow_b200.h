@@ -1,0 +1,202 @@
+/*
+ * mrflow_b200.h -- C ABI of libmrflow_b200.so: the dense plane+parallax hot path of MR-Flow
+ * (jswulff/mrflow) as hand-written sm_100a CUDA kernels.
+ *
+ * The reference has no FFI for this path: its boundary is the Python function signature, called
+ * in-process with numpy arrays.  The one real FFI in the reference,
+ * extern/eff_trws/eff_trws.pyx:4-58 (caller-owned C-contiguous buffers passed as raw pointers,
+ * results written into caller-provided arrays), is the model followed here.  Each entry point
+ * below names the reference function(s) (file:line under /root/reference) it replaces; the
+ * Python host layer in mrflow_b200/ re-exposes them under the reference's own names/signatures.
+ *
+ * Conventions
+ *  - every pointer is a DEVICE pointer unless the parameter name ends in _host;
+ *  - nothing is allocated inside the library; scratch buffers are caller-provided and their
+ *    sizes come from the mrf_*_scratch_bytes() helpers;
+ *  - every call is asynchronous on `stream` (a cudaStream_t); no global state, thread-safe per
+ *    stream; return value 0 = OK, otherwise a cudaError_t (>0) or an MRF_E_* code (<0); a
+ *    message for the calling thread's last failure is available from mrf_last_error();
+ *  - images are row-major; `rows`/`y0` describe a row band: the buffers hold `rows` rows whose
+ *    first row is global row `y0` of a frame `frame_h` rows tall (y0=0, rows=frame_h for a whole
+ *    frame).  Pixel coordinates used in the arithmetic are always the GLOBAL ones, so a band
+ *    computes bit-identical values to the whole frame;
+ *  - 3x3 matrices are fp64 row-major [9]; epipoles are fp64 [2] = (x, y).
+ */
+#ifndef MRFLOW_B200_H
+#define MRFLOW_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* mrf_stream_t; /* cudaStream_t */
+
+#define MRF_E_BADARG   (-1)
+#define MRF_E_NOTMA    (-2) /* driver entry point for tensor-map encoding unavailable */
+#define MRF_E_SCRATCH  (-3)
+
+/* sampling modes: the reference samples with cv2.remap(INTER_CUBIC, BORDER_REPLICATE) on
+ * 1/32-px quantised coordinates (structure_refinement/interpolation.py:76-80); LINEAR is the
+ * same quantisation with INTER_LINEAR (north_star's "bilinear"; rigidity/occlusions.py). */
+#define MRF_INTERP_CUBIC   0
+#define MRF_INTERP_LINEAR  1
+
+/* robust functions, utils/robust_functions.py:26-70 (argument is x^2), fixed-parameter forms */
+#define MRF_RHO_LORENTZIAN    0  /* log(1 + x/sigma^2)            :52 */
+#define MRF_RHO_CHARBONNIER   1  /* sqrt(x + eps^2)               :33  (param = eps) */
+#define MRF_RHO_GEMAN_MCCLURE 2  /* sigma*x/(x + sigma^2)         :64 */
+#define MRF_RHO_QUADRATIC     3  /* x                             :46 */
+#define MRF_RHO_LORENTZIAN_AUTO 4 /* s*log(1 + 0.5x/s^2), s given :58  (auto-sigma form) */
+#define MRF_RHO_NONE          5  /* the residual Iz itself (for the auto-sigma pre-pass) */
+
+/* cost-volume output layouts */
+#define MRF_LAYOUT_LHW_F32 0  /* [L][rows][w] fp32, coalesced along x */
+#define MRF_LAYOUT_HWL_I32 1  /* [rows][w][L] int32 = (int)(cost*i32_scale), what
+                                 extern/eff_trws/image.cpp:80 consumes */
+
+int         mrf_version(void);
+const char* mrf_last_error(void);
+
+/* ---- a1 + a2: utils/flow_homography.py:4-16 (get_residual_flow) fused with
+ *      pipeline/compute_structure.py:517-537 (flow2parallax).
+ * u,v fp32 [rows,w]; Hinv = inverse homography; q = epipole.  Any output may be NULL. */
+int mrf_flow_to_parallax(const float* u, const float* v, int rows, int w, int y0,
+                         const double* Hinv_host, const double* q_host,
+                         float* u_res, float* v_res, double* parallax, double* dists,
+                         mrf_stream_t stream);
+
+/* ---- mu of pipeline/compute_structure.py:84: sum over the band of ||p - q|| (fp64,
+ * deterministic two-stage reduction); out_sum is ONE double on the device.
+ * scratch: mrf_reduce_scratch_bytes() bytes. */
+size_t mrf_reduce_scratch_bytes(void);
+int mrf_epipole_dist_sum(int rows, int w, int y0, const double* q_host,
+                         double* out_sum, void* scratch, mrf_stream_t stream);
+
+/* ---- a3: pipeline/compute_structure.py:25-33 (parallax2normedstructure). */
+int mrf_parallax_to_structure(const double* parallax, int rows, int w, int y0,
+                              const double* q_host, double B, double mu,
+                              double* structure, mrf_stream_t stream);
+
+/* ---- a6: pipeline/structure2flow.py:14-38 (structure_to_flow) incl. get_full_flow
+ * (utils/flow_homography.py:20-37); if nonrigid != NULL also the paste of
+ * combine_flow_simple (:72-73): where nonrigid[p] != 0 the output is flow_init. */
+int mrf_structure_to_flow(const double* structure, int rows, int w, int y0,
+                          const double* q_host, double mu, const double* H_host, double b,
+                          const uint8_t* nonrigid, const float* init_u, const float* init_v,
+                          float* u, float* v, mrf_stream_t stream);
+
+/* ---- a7: rigidity/inference.py:28-59 (get_unaries_rigid), dtype behaviour included
+ * (fp32 flow magnitude / angle, fp64 elsewhere). */
+int mrf_rigidity_unaries(const float* u_res, const float* v_res, int rows, int w, int y0,
+                         const double* q_host, double sigma, double prior_rigid,
+                         double prior_nonrigid, double* prob, mrf_stream_t stream);
+
+/* ---- a4 (dense part 1): pipeline/compute_structure.py:104-153 -- direction unaries for both
+ * frames (a7), the small-motion (0.6) / occlusion (0.5) overrides, the occlusion-aware merge
+ * and the CNN-weighted threshold.  Inputs: residual flows of both frames, occlusion masks
+ * (uint8, !=0 == occluded), CNN rigidity fp64.  Outputs: p_dir fp64, p_thr uint8. */
+int mrf_rigidity_direction(const float* ures0, const float* vres0, const float* ures1, const float* vres1,
+                           const uint8_t* occ0, const uint8_t* occ1, const double* p_cnn,
+                           int rows, int w, int y0, const double* q0_host, const double* q1_host,
+                           double sigma_direction, double weight_cnn,
+                           double* p_dir, uint8_t* p_thr, mrf_stream_t stream);
+
+/* ---- a4 (dense part 2): pipeline/compute_structure.py:172-221 -- valid-pixel mask
+ * pv = |par0|>0.1 & |par1|>0.1 & p_thr, and the two candidate lists whose medians give
+ * B_fwd (:187-191, structure at B=1 over pv) and B_b (:209-221, template/target over pv).
+ * The lists are written compacted (order unspecified) to cand_s1 / cand_ratio (capacity
+ * rows*w each); *count (device int) receives their length.  B_fwd enters the ratio list, so
+ * call with want=1 for cand_s1 first, take the median, then want=2 with B_fwd for cand_ratio. */
+int mrf_structure_candidates(const double* par0, const double* par1, const uint8_t* p_thr,
+                             int rows, int w, int y0, const double* q0_host, const double* q1_host,
+                             double mu0, double mu1, double B_fwd, int want,
+                             uint8_t* pv, double* cand, int* count, mrf_stream_t stream);
+
+/* ---- a4 (dense part 3): pipeline/compute_structure.py:374-394 -- structure-consistency
+ * rigidity, merge with direction + CNN, unaries for the MRF.  unaries_f64 is [rows,w,2] fp64 =
+ * dstack(1-p, p) (:392); unaries_i32 (optional) is the packing of rigidity/inference.py:113,
+ * int32(-unaries*1000), [rows,w,2]. */
+int mrf_rigidity_structure(const double* S0, const double* S1, const double* p_dir, const double* p_cnn,
+                           const uint8_t* occ0, const uint8_t* occ1, int rows, int w,
+                           double mu0, double mu1, double sigma_structure, double weight_cnn,
+                           double* unaries_f64, int32_t* unaries_i32, mrf_stream_t stream);
+
+/* ---- exact order statistics for the medians of compute_structure.py:190,221 and the
+ * auto-sigma of utils/robust_functions.py:23-29.  keys: n fp64 values (not modified);
+ * out[0] = k-th smallest (0-based), out[1] = (k+1)-th smallest (so the caller forms numpy's
+ * mean-of-two-middles for even n); out[2] = number of NaNs (numpy's median is NaN if any).
+ * scratch: mrf_select_scratch_bytes(n) bytes. */
+size_t mrf_select_scratch_bytes(size_t n);
+int mrf_select_kth_f64(const double* keys, size_t n, size_t k, double* out3,
+                       void* scratch, mrf_stream_t stream);
+/* abs deviation |x - c| in place helper for MAD (utils/robust_functions.py:23,
+ * compute_structure.py:190) */
+int mrf_abs_deviation_f64(const double* x, size_t n, double c, double* out, mrf_stream_t stream);
+
+/* ---- masked min/max for the label range of pipeline/build_cost_volume.py:154-169,190-192:
+ * min/max over the band of S with the pixels zeroed that the reference zeroes (rigidity rule
+ * + the +-10 px box round the epipole).  zero_mask uint8 (!=0 -> value replaced by 0) may be
+ * NULL; box = {x0,x1,y0,y1} half-open in global coords or NULL.  out2 = {min, max} device. */
+int mrf_masked_minmax_f64(const double* S, const uint8_t* zero_mask, int rows, int w, int y0,
+                          const int* box_host, double* out2, void* scratch, mrf_stream_t stream);
+
+/* ---- a11 channel construction, structure_refinement/optimize_structure_single_scale.py:350-371
+ * (variational_dataterm_grayscale=1): gray = cvtColor(fp32 RGB)*255 (fp64), np.gradient,
+ * 3x3 Gaussian blur.  rgb fp32 [h,w,3] interleaved (the reference's I.astype('float32')).
+ * Outputs (either may be NULL): ch64 fp64 [h,w,3] interleaved = dstack(gray, gy, gx);
+ * texels fp32 [h,w,4] = (gray, gy, gx, 0) each rounded to fp32 -- the sampler's input
+ * (interpolation.py:76 casts the image to fp32).  gray_scratch: h*w doubles. */
+int mrf_prepare_channels(const float* rgb, int h, int w, double* ch64, float* texels,
+                         double* gray_scratch, mrf_stream_t stream);
+
+/* ---- a8: structure_refinement/interpolate_through_H.py:7-51 (compute_derivs=False) with
+ * interpolation.py:76-80.  img fp32 [img_h,img_w,C] interleaved, C in 1..4; xn,yn fp64 [n];
+ * J fp32 [n,C]; mask fp64 [n] (1 inside the frame, else 0).  H may be NULL (= identity
+ * without the projective division, i.e. plain interp_lin). */
+int mrf_warp_sample(const float* img, int img_h, int img_w, int C, const double* H_host,
+                    const double* xn, const double* yn, size_t n, int interp,
+                    float* J, double* mask, mrf_stream_t stream);
+
+/* ---- a11 + a12: the per-label data cost (computeDataTerm geometry :210-235, sampling :238,
+ * residual :269-286, energy term :302) for ONE neighbour frame and ALL labels, i.e. the job
+ * of the missing extension at pipeline/build_cost_volume.py:209-219. */
+typedef struct {
+  /* reference frame band */
+  int rows, w, y0, frame_h;
+  /* neighbour-frame texel buffer [nb_rows][w][4] fp32 holding global rows nb_y0.. */
+  int nb_rows, nb_y0;
+  double H[9];          /* homography reference -> neighbour */
+  double q[2];          /* epipole */
+  double mu, B;
+  double label_scale;   /* mu0/mu1 for the backward frame, 1 for the forward one (:435-436) */
+  int    n_labels;      /* <= 256 */
+  int    interp;        /* MRF_INTERP_* */
+  int    rho;           /* MRF_RHO_* */
+  double rho_param;     /* sigma or eps */
+  double cw[3];         /* channel weights (0.01,1,1) :371 */
+  int    layout;        /* MRF_LAYOUT_* */
+  double i32_scale;     /* for MRF_LAYOUT_HWL_I32 */
+  int    variant;       /* 0 = auto; otherwise force a kernel variant (testing/benchmarks) */
+} mrf_costvol_params;
+
+/* ref_ch: fp64 [rows,w,3] channels of the reference frame band; nb_texels as described;
+ * labels: fp64 [n_labels] structure_range (device); nonrigid/occluded: uint8 [rows,w], !=0
+ * zeroes the residual (:285-286), may be NULL.  cost: layout-dependent, may be NULL (then only
+ * min/argmin are produced); min_cost fp32 [rows,w] / argmin int32 [rows,w] (first minimum,
+ * np.argmin semantics) may be NULL. */
+int mrf_cost_volume(const mrf_costvol_params* p_host, const double* ref_ch, const float* nb_texels,
+                    const double* labels, const uint8_t* nonrigid, const uint8_t* occluded,
+                    void* cost, float* min_cost, int32_t* argmin, mrf_stream_t stream);
+
+/* number of kernel launches the library has issued in this process (for bench.py's
+ * gpu_launches); reset with mrf_reset_launch_count(). */
+long long mrf_launch_count(void);
+void      mrf_reset_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MRFLOW_B200_H */

@@ -1,0 +1,431 @@
+// Pointwise plane+parallax geometry kernels (SURVEY.md section 8a rows a1-a7 and the dense parts of
+// a4).  All of them are streaming, one thread per pixel, coalesced along x; they are HBM-bound
+// with a few dozen fp64 flops per pixel.  Arithmetic follows the reference operation by
+// operation (compiled with -fmad=false) so results are bit-identical wherever the reference only
+// uses IEEE +,-,*,/,sqrt; transcendental functions (atan2, sin, exp, I0e) agree to a few ulp.
+#include "common.cuh"
+#include <stdarg.h>
+#include <math.h>
+
+namespace mrf {
+
+thread_local char g_err[512] = {0};
+std::atomic<long long> g_launches{0};
+
+int fail(int code, const char* fmt, ...) {
+  va_list ap; va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+int check_launch(const char* what) {
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return fail((int)e, "%s: %s", what, cudaGetErrorString(e));
+  return 0;
+}
+
+// ------------------------------------------------------------------------------- a1 + a2
+// utils/flow_homography.py:4-16 + pipeline/compute_structure.py:517-537
+__global__ void __launch_bounds__(256)
+k_flow_to_parallax(const float* __restrict__ u, const float* __restrict__ v, int rows, int w, int y0,
+                   Mat3 Hinv, Pt2 q, float* __restrict__ u_res, float* __restrict__ v_res,
+                   double* __restrict__ parallax, double* __restrict__ dists) {
+  const long long n = (long long)rows * w;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int yl = (int)(i / w);
+    const int x = (int)(i - (long long)yl * w);
+    const int y = yl + y0;
+    // x + u: int64 + fp32 -> fp64 in numpy, then .astype('float32')
+    const float x2 = (float)((double)x + (double)u[i]);
+    const float y2 = (float)((double)y + (double)v[i]);
+    float X, Y;
+    persp_f32(x2, y2, Hinv, X, Y);
+    const float ur = X - (float)x;   // fp32 - fp32
+    const float vr = Y - (float)y;
+    if (u_res) u_res[i] = ur;
+    if (v_res) v_res[i] = vr;
+    if (parallax || dists) {
+      const double fx = q.x - (double)x;
+      const double fy = q.y - (double)y;
+      const double d = sqrt(fx * fx + fy * fy);
+      if (dists) dists[i] = d;
+      if (parallax) {
+        const double dn = fmax(d, 1e-3);
+        parallax[i] = (double)ur * (fx / dn) + (double)vr * (fy / dn);
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------- mu
+// pipeline/compute_structure.py:84 -- sum of ||p-q|| over the band; fixed grid, fixed tree ->
+// deterministic.  (numpy's pairwise sum rounds differently by O(1e-16) relative.)
+constexpr int kRedBlocks = 1024;
+constexpr int kRedThreads = 256;
+
+__device__ __forceinline__ double block_sum(double v, double* sh) {
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  if (lane == 0) sh[wid] = v;
+  __syncthreads();
+  const int nw = blockDim.x >> 5;
+  v = (threadIdx.x < nw) ? sh[threadIdx.x] : 0.0;
+  if (wid == 0) for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+  __syncthreads();
+  return v;
+}
+
+__global__ void __launch_bounds__(kRedThreads)
+k_dist_sum_partial(int rows, int w, int y0, Pt2 q, double* __restrict__ partial) {
+  __shared__ double sh[32];
+  const long long n = (long long)rows * w;
+  double acc = 0.0;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int yl = (int)(i / w);
+    const int x = (int)(i - (long long)yl * w);
+    const double fx = q.x - (double)x, fy = q.y - (double)(yl + y0);
+    acc += sqrt(fx * fx + fy * fy);
+  }
+  acc = block_sum(acc, sh);
+  if (threadIdx.x == 0) partial[blockIdx.x] = acc;
+}
+
+__global__ void __launch_bounds__(kRedBlocks)
+k_sum_final(const double* __restrict__ partial, int n, double* __restrict__ out) {
+  __shared__ double sh[32];
+  double v = (threadIdx.x < n) ? partial[threadIdx.x] : 0.0;
+  v = block_sum(v, sh);
+  if (threadIdx.x == 0) out[0] = v;
+}
+
+// ------------------------------------------------------------------------------- a3
+// pipeline/compute_structure.py:25-33
+__global__ void __launch_bounds__(256)
+k_parallax_to_structure(const double* __restrict__ parallax, int rows, int w, int y0, Pt2 q, double B,
+                        double mu, double* __restrict__ structure) {
+  const long long n = (long long)rows * w;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int yl = (int)(i / w);
+    const int x = (int)(i - (long long)yl * w);
+    const double dx = (double)x - q.x, dy = (double)(yl + y0) - q.y;
+    const double dst = sqrt(dx * dx + dy * dy);
+    const double p = parallax[i];
+    structure[i] = p / (B * (p / mu - dst / mu));
+  }
+}
+
+// ------------------------------------------------------------------------------- a6
+// pipeline/structure2flow.py:14-38, :72-73; utils/flow_homography.py:20-37
+__global__ void __launch_bounds__(256)
+k_structure_to_flow(const double* __restrict__ structure, int rows, int w, int y0, Pt2 q, double mu,
+                    Mat3 H, double b, const uint8_t* __restrict__ nonrigid,
+                    const float* __restrict__ init_u, const float* __restrict__ init_v,
+                    float* __restrict__ u, float* __restrict__ v) {
+  const long long n = (long long)rows * w;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n;
+       i += (long long)gridDim.x * blockDim.x) {
+    if (nonrigid && nonrigid[i]) { u[i] = init_u[i]; v[i] = init_v[i]; continue; }
+    const int yl = (int)(i / w);
+    const int x = (int)(i - (long long)yl * w);
+    const int y = yl + y0;
+    const double dx = (double)x - q.x, dy = (double)y - q.y;
+    const double d = sqrt(dx * dx + dy * dy);
+    const double nn = d / mu;
+    const double bs = b * structure[i];
+    const double par = (bs * nn) / (bs / mu - 1.0);
+    const double dm = fmax(1e-3, d);
+    const double ur = ((q.x - (double)x) / dm) * par;
+    const double vr = ((q.y - (double)y) / dm) * par;
+    const float x2 = (float)((double)x + ur);
+    const float y2 = (float)((double)y + vr);
+    float X, Y;
+    persp_f32(x2, y2, H, X, Y);
+    u[i] = X - (float)x;
+    v[i] = Y - (float)y;
+  }
+}
+
+// ------------------------------------------------------------------------------- a7
+// Exponentially scaled modified Bessel function I0e(x) = exp(-|x|) I0(x), fp64.
+// scipy.special.ive(0, x) (the reference's call, rigidity/inference.py:54) is restated by its
+// published definition: ascending series for x <= 30, Hankel asymptotic expansion above.
+__device__ double i0e_f64(double x) {
+  x = fabs(x);
+  if (x <= 30.0) {
+    const double q = 0.25 * x * x;
+    double term = 1.0, sum = 1.0;
+    for (int k = 1; k < 200; ++k) {
+      term *= q / ((double)k * (double)k);
+      sum += term;
+      if (term < 1e-17 * sum) break;
+    }
+    return sum * exp(-x);
+  }
+  const double inv = 1.0 / (8.0 * x);
+  double term = 1.0, sum = 1.0;
+  for (int k = 1; k < 24; ++k) {
+    const double o = (double)(2 * k - 1);
+    term *= o * o * inv / (double)k;
+    sum += term;
+    if (term < 1e-17 * sum) break;
+  }
+  return sum / sqrt(6.283185307179586476925 * x);
+}
+
+// rigidity/inference.py:28-59 with the reference's dtypes (u_res, v_res fp32 => dist, ang_uv and
+// the Bessel argument/result are fp32 quantities; the rest is fp64).
+__device__ __forceinline__ double unary_rigid(float ur, float vr, int x, int y, Pt2 q, double sigma,
+                                              double prior_r, double prior_n) {
+  const float dist = sqrtf(ur * ur + vr * vr);
+  const double ang_foe = atan2(q.y - (double)y, q.x - (double)x);
+  const float ang_uv = atan2f(vr, ur);
+  const double ang = (double)ang_uv - ang_foe;
+  const double dfl = (double)dist * sin(ang);
+  const double p = 1.0 / sqrt(2.0 * 3.141592653589793 * (sigma * sigma)) *
+                   exp(-(dfl * dfl) / (2.0 * (sigma * sigma)));
+  const float arg = (dist * dist) / (float)((sigma * sigma) * 4.0);
+  const float bes = (float)i0e_f64((double)arg);
+  const double c = sqrt(2.0 * 3.141592653589793) / sigma * (double)bes;
+  return prior_r * p / (prior_r * p + prior_n * c / (2.0 * 3.141592653589793));
+}
+
+__global__ void __launch_bounds__(256)
+k_rigidity_unaries(const float* __restrict__ ur, const float* __restrict__ vr, int rows, int w, int y0,
+                   Pt2 q, double sigma, double pr, double pn, double* __restrict__ prob) {
+  const long long n = (long long)rows * w;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int yl = (int)(i / w);
+    const int x = (int)(i - (long long)yl * w);
+    prob[i] = unary_rigid(ur[i], vr[i], x, yl + y0, q, sigma, pr, pn);
+  }
+}
+
+// pipeline/compute_structure.py:104-153
+__global__ void __launch_bounds__(256)
+k_rigidity_direction(const float* __restrict__ ur0, const float* __restrict__ vr0,
+                     const float* __restrict__ ur1, const float* __restrict__ vr1,
+                     const uint8_t* __restrict__ occ0, const uint8_t* __restrict__ occ1,
+                     const double* __restrict__ p_cnn, int rows, int w, int y0, Pt2 q0, Pt2 q1,
+                     double sigma, double wc, double* __restrict__ p_dir, uint8_t* __restrict__ p_thr) {
+  const long long n = (long long)rows * w;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int yl = (int)(i / w);
+    const int x = (int)(i - (long long)yl * w);
+    const int y = yl + y0;
+    const float a0 = ur0[i], b0 = vr0[i], a1 = ur1[i], b1 = vr1[i];
+    double pb = unary_rigid(a0, b0, x, y, q0, sigma, 0.5, 0.5);
+    double pf = unary_rigid(a1, b1, x, y, q1, sigma, 0.5, 0.5);
+    if (sqrtf(a0 * a0 + b0 * b0) < 0.1f) pb = 0.6;      // :112-113,:128 (fp32 compare)
+    if (sqrtf(a1 * a1 + b1 * b1) < 0.1f) pf = 0.6;
+    const bool ob = occ0 && occ0[i], of = occ1 && occ1[i];
+    if (of) pf = 0.5;                                   // :135-136
+    if (ob) pb = 0.5;
+    double pd = (pb + pf) / 2.0;                         // :140
+    if (ob) pd = 0.25 + 0.5 * pf;                        // :142
+    if (of) pd = 0.25 + 0.5 * pb;                        // :144
+    if (ob && of) pd = 0.5;                              // :146
+    if (p_dir) p_dir[i] = pd;
+    if (p_thr) p_thr[i] = (wc * p_cnn[i] + (1.0 - wc) * pd) > 0.5 ? 1 : 0;   // :152-153
+  }
+}
+
+// pipeline/compute_structure.py:172-221
+__global__ void __launch_bounds__(256)
+k_structure_candidates(const double* __restrict__ par0, const double* __restrict__ par1,
+                       const uint8_t* __restrict__ p_thr, int rows, int w, int y0, Pt2 q0, Pt2 q1,
+                       double mu0, double mu1, double B_fwd, int want, uint8_t* __restrict__ pv,
+                       double* __restrict__ cand, int* __restrict__ count) {
+  const long long n = (long long)rows * w;
+  for (long long i0 = blockIdx.x * (long long)blockDim.x; i0 < n; i0 += (long long)gridDim.x * blockDim.x) {
+    const long long i = i0 + threadIdx.x;
+    bool valid = false;
+    double val = 0.0;
+    if (i < n) {
+      const double p0 = par0[i], p1 = par1[i];
+      valid = (fabs(p0) > 0.1) && (fabs(p1) > 0.1) && (p_thr[i] != 0);
+      if (pv) pv[i] = valid ? 1 : 0;
+      if (valid && cand) {
+        const int yl = (int)(i / w);
+        const int x = (int)(i - (long long)yl * w);
+        const int y = yl + y0;
+        const double dx1 = (double)x - q1.x, dy1 = (double)y - q1.y;
+        const double d1 = sqrt(dx1 * dx1 + dy1 * dy1);
+        if (want == 1) {
+          // parallax2normedstructure(par1, q1, 1.0, mu1)  :187
+          val = p1 / (1.0 * (p1 / mu1 - d1 / mu1));
+        } else {
+          // :209-219; dists_normed = foe_dists/mu with foe_dists from flow2parallax (q - x)
+          const double fx0 = q0.x - (double)x, fy0 = q0.y - (double)y;
+          const double dn0 = sqrt(fx0 * fx0 + fy0 * fy0) / mu0;
+          const double fx1 = q1.x - (double)x, fy1 = q1.y - (double)y;
+          const double dn1 = sqrt(fx1 * fx1 + fy1 * fy1) / mu1;
+          const double target = p1 / (B_fwd * (p1 / mu1 - dn1));
+          const double templ = mu1 / mu0 * p0 / (p0 / mu0 - dn0);
+          val = templ / target;
+        }
+      }
+    }
+    if (cand) {
+      // warp-aggregated compaction (order is irrelevant for order statistics)
+      const unsigned m = __ballot_sync(0xffffffffu, valid);
+      const int lane = threadIdx.x & 31;
+      int base = 0;
+      if (lane == 0 && m) base = atomicAdd(count, __popc(m));
+      base = __shfl_sync(0xffffffffu, base, 0);
+      if (valid) cand[base + __popc(m & ((1u << lane) - 1u))] = val;
+    }
+  }
+}
+
+// pipeline/compute_structure.py:374-394, rigidity/inference.py:113
+__global__ void __launch_bounds__(256)
+k_rigidity_structure(const double* __restrict__ S0, const double* __restrict__ S1,
+                     const double* __restrict__ p_dir, const double* __restrict__ p_cnn,
+                     const uint8_t* __restrict__ occ0, const uint8_t* __restrict__ occ1, long long n,
+                     double mu0, double mu1, double ss, double wc, double* __restrict__ un64,
+                     int32_t* __restrict__ un32) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n;
+       i += (long long)gridDim.x * blockDim.x) {
+    const double ad = S0[i] * mu1 / mu0 - S1[i];
+    const double t = ad / ss;
+    double ps = exp(-(t * t));
+    const bool bad = (occ0 && occ0[i]) || (occ1 && occ1[i]);
+    const double pd = p_dir[i];
+    if (bad) ps = 0.5;
+    double pm = pd * ps;
+    if (bad) pm = 0.25 + 0.5 * pd;
+    const double pr = wc * p_cnn[i] + (1.0 - wc) * pm;
+    const double u0 = 1.0 - pr, u1 = pr;
+    if (un64) { un64[2 * i] = u0; un64[2 * i + 1] = u1; }
+    if (un32) { un32[2 * i] = (int32_t)((-u0) * 1000.0); un32[2 * i + 1] = (int32_t)((-u1) * 1000.0); }
+  }
+}
+
+__global__ void __launch_bounds__(256)
+k_abs_dev(const double* __restrict__ x, size_t n, double c, double* __restrict__ out) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+    out[i] = fabs(x[i] - c);
+}
+
+static inline unsigned grid_for(long long n, int threads = 256) {
+  long long b = (n + threads - 1) / threads;
+  const long long cap = (long long)kSMs * 16;
+  if (b > cap) b = cap;
+  if (b < 1) b = 1;
+  return (unsigned)b;
+}
+
+}  // namespace mrf
+
+using namespace mrf;
+
+extern "C" {
+
+int mrf_version(void) { return 100; }
+const char* mrf_last_error(void) { return g_err; }
+long long mrf_launch_count(void) { return g_launches.load(); }
+void mrf_reset_launch_count(void) { g_launches.store(0); }
+
+int mrf_flow_to_parallax(const float* u, const float* v, int rows, int w, int y0, const double* Hinv_host,
+                         const double* q_host, float* u_res, float* v_res, double* parallax, double* dists,
+                         mrf_stream_t stream) {
+  MRF_CHECK_ARG(u && v && rows > 0 && w > 0 && Hinv_host && q_host);
+  const long long n = (long long)rows * w;
+  k_flow_to_parallax<<<grid_for(n), 256, 0, S(stream)>>>(u, v, rows, w, y0, mat3(Hinv_host), pt2(q_host),
+                                                        u_res, v_res, parallax, dists);
+  return check_launch("mrf_flow_to_parallax");
+}
+
+size_t mrf_reduce_scratch_bytes(void) { return sizeof(double) * kRedBlocks * 2; }
+
+int mrf_epipole_dist_sum(int rows, int w, int y0, const double* q_host, double* out_sum, void* scratch,
+                         mrf_stream_t stream) {
+  MRF_CHECK_ARG(rows > 0 && w > 0 && q_host && out_sum && scratch);
+  k_dist_sum_partial<<<kRedBlocks, kRedThreads, 0, S(stream)>>>(rows, w, y0, pt2(q_host), (double*)scratch);
+  int rc = check_launch("mrf_epipole_dist_sum/partial");
+  if (rc) return rc;
+  k_sum_final<<<1, kRedBlocks, 0, S(stream)>>>((const double*)scratch, kRedBlocks, out_sum);
+  return check_launch("mrf_epipole_dist_sum/final");
+}
+
+int mrf_parallax_to_structure(const double* parallax, int rows, int w, int y0, const double* q_host, double B,
+                              double mu, double* structure, mrf_stream_t stream) {
+  MRF_CHECK_ARG(parallax && structure && rows > 0 && w > 0 && q_host);
+  k_parallax_to_structure<<<grid_for((long long)rows * w), 256, 0, S(stream)>>>(parallax, rows, w, y0,
+                                                                               pt2(q_host), B, mu, structure);
+  return check_launch("mrf_parallax_to_structure");
+}
+
+int mrf_structure_to_flow(const double* structure, int rows, int w, int y0, const double* q_host, double mu,
+                          const double* H_host, double b, const uint8_t* nonrigid, const float* init_u,
+                          const float* init_v, float* u, float* v, mrf_stream_t stream) {
+  MRF_CHECK_ARG(structure && u && v && rows > 0 && w > 0 && q_host && H_host);
+  MRF_CHECK_ARG(!nonrigid || (init_u && init_v));
+  k_structure_to_flow<<<grid_for((long long)rows * w), 256, 0, S(stream)>>>(
+      structure, rows, w, y0, pt2(q_host), mu, mat3(H_host), b, nonrigid, init_u, init_v, u, v);
+  return check_launch("mrf_structure_to_flow");
+}
+
+int mrf_rigidity_unaries(const float* u_res, const float* v_res, int rows, int w, int y0, const double* q_host,
+                         double sigma, double prior_rigid, double prior_nonrigid, double* prob,
+                         mrf_stream_t stream) {
+  MRF_CHECK_ARG(u_res && v_res && prob && rows > 0 && w > 0 && q_host && sigma > 0);
+  k_rigidity_unaries<<<grid_for((long long)rows * w), 256, 0, S(stream)>>>(
+      u_res, v_res, rows, w, y0, pt2(q_host), sigma, prior_rigid, prior_nonrigid, prob);
+  return check_launch("mrf_rigidity_unaries");
+}
+
+int mrf_rigidity_direction(const float* ures0, const float* vres0, const float* ures1, const float* vres1,
+                           const uint8_t* occ0, const uint8_t* occ1, const double* p_cnn, int rows, int w,
+                           int y0, const double* q0_host, const double* q1_host, double sigma_direction,
+                           double weight_cnn, double* p_dir, uint8_t* p_thr, mrf_stream_t stream) {
+  MRF_CHECK_ARG(ures0 && vres0 && ures1 && vres1 && rows > 0 && w > 0 && q0_host && q1_host);
+  MRF_CHECK_ARG(!p_thr || p_cnn);
+  k_rigidity_direction<<<grid_for((long long)rows * w), 256, 0, S(stream)>>>(
+      ures0, vres0, ures1, vres1, occ0, occ1, p_cnn, rows, w, y0, pt2(q0_host), pt2(q1_host),
+      sigma_direction, weight_cnn, p_dir, p_thr);
+  return check_launch("mrf_rigidity_direction");
+}
+
+int mrf_structure_candidates(const double* par0, const double* par1, const uint8_t* p_thr, int rows, int w,
+                             int y0, const double* q0_host, const double* q1_host, double mu0, double mu1,
+                             double B_fwd, int want, uint8_t* pv, double* cand, int* count,
+                             mrf_stream_t stream) {
+  MRF_CHECK_ARG(par0 && par1 && p_thr && rows > 0 && w > 0 && q0_host && q1_host);
+  MRF_CHECK_ARG(!cand || (count && (want == 1 || want == 2)));
+  if (count) {
+    cudaError_t e = cudaMemsetAsync(count, 0, sizeof(int), S(stream));
+    if (e != cudaSuccess) return fail((int)e, "mrf_structure_candidates: %s", cudaGetErrorString(e));
+  }
+  k_structure_candidates<<<grid_for((long long)rows * w), 256, 0, S(stream)>>>(
+      par0, par1, p_thr, rows, w, y0, pt2(q0_host), pt2(q1_host), mu0, mu1, B_fwd, want, pv, cand, count);
+  return check_launch("mrf_structure_candidates");
+}
+
+int mrf_rigidity_structure(const double* S0, const double* S1, const double* p_dir, const double* p_cnn,
+                           const uint8_t* occ0, const uint8_t* occ1, int rows, int w, double mu0, double mu1,
+                           double sigma_structure, double weight_cnn, double* unaries_f64,
+                           int32_t* unaries_i32, mrf_stream_t stream) {
+  MRF_CHECK_ARG(S0 && S1 && p_dir && p_cnn && rows > 0 && w > 0 && (unaries_f64 || unaries_i32));
+  const long long n = (long long)rows * w;
+  k_rigidity_structure<<<grid_for(n), 256, 0, S(stream)>>>(S0, S1, p_dir, p_cnn, occ0, occ1, n, mu0, mu1,
+                                                          sigma_structure, weight_cnn, unaries_f64,
+                                                          unaries_i32);
+  return check_launch("mrf_rigidity_structure");
+}
+
+int mrf_abs_deviation_f64(const double* x, size_t n, double c, double* out, mrf_stream_t stream) {
+  MRF_CHECK_ARG(x && out);
+  if (n == 0) return 0;
+  k_abs_dev<<<grid_for((long long)n), 256, 0, S(stream)>>>(x, n, c, out);
+  return check_launch("mrf_abs_deviation_f64");
+}
+
+}  // extern "C"

@@ -126,12 +126,24 @@ int mrf_rigidity_structure(const double* S0, const double* S1, const double* p_d
 
 /* ---- exact order statistics for the medians of compute_structure.py:190,221 and the
  * auto-sigma of utils/robust_functions.py:23-29.  keys: n fp64 values (not modified);
- * out[0] = k-th smallest (0-based), out[1] = (k+1)-th smallest (so the caller forms numpy's
- * mean-of-two-middles for even n); out[2] = number of NaNs (numpy's median is NaN if any).
- * scratch: mrf_select_scratch_bytes(n) bytes. */
+ * out3[0] = k-th smallest (0-based), out3[1] = (k+1)-th smallest (so the caller forms numpy's
+ * mean-of-two-middles for even n; undefined for k = n-1), out3[2] = number of NaNs (numpy's
+ * median is NaN if any; NaNs order last as in numpy's sort).
+ * scratch: mrf_select_scratch_bytes(n) bytes, 8-byte aligned. */
 size_t mrf_select_scratch_bytes(size_t n);
 int mrf_select_kth_f64(const double* keys, size_t n, size_t k, double* out3,
                        void* scratch, mrf_stream_t stream);
+/* The same selection in steps, for keys sharded over several GPUs: every
+ * rank runs begin(k_global); then 8 x { hist on its shard; all-reduce(SUM) the 256 uint64
+ * histogram words at scratch + MRF_SELECT_HIST_OFFSET bytes; pick }; then successor on its
+ * shard; all-reduce words 3,4 (SUM: #NaN, #keys <= kth) and word 5 (MIN, unsigned: smallest
+ * order-key above kth) of the state at scratch; result. */
+#define MRF_SELECT_HIST_OFFSET 64
+int mrf_select_begin(size_t k, void* scratch, mrf_stream_t stream);
+int mrf_select_hist_f64(const double* keys, size_t n, void* scratch, mrf_stream_t stream);
+int mrf_select_pick(void* scratch, mrf_stream_t stream);
+int mrf_select_successor_f64(const double* keys, size_t n, void* scratch, mrf_stream_t stream);
+int mrf_select_result(size_t k, void* scratch, double* out3, mrf_stream_t stream);
 /* abs deviation |x - c| in place helper for MAD (utils/robust_functions.py:23,
  * compute_structure.py:190) */
 int mrf_abs_deviation_f64(const double* x, size_t n, double c, double* out, mrf_stream_t stream);
@@ -139,17 +151,20 @@ int mrf_abs_deviation_f64(const double* x, size_t n, double c, double* out, mrf_
 /* ---- masked min/max for the label range of pipeline/build_cost_volume.py:154-169,190-192:
  * min/max over the band of S with the pixels zeroed that the reference zeroes (rigidity rule
  * + the +-10 px box round the epipole).  zero_mask uint8 (!=0 -> value replaced by 0) may be
- * NULL; box = {x0,x1,y0,y1} half-open in global coords or NULL.  out2 = {min, max} device. */
+ * NULL; box = {x0,x1,y0,y1} half-open in global coords or NULL.  out2 = {min, max} device;
+ * NaN propagates as in numpy.  scratch: mrf_minmax_scratch_bytes() bytes. */
+size_t mrf_minmax_scratch_bytes(void);
 int mrf_masked_minmax_f64(const double* S, const uint8_t* zero_mask, int rows, int w, int y0,
                           const int* box_host, double* out2, void* scratch, mrf_stream_t stream);
 
 /* ---- a11 channel construction, structure_refinement/optimize_structure_single_scale.py:350-371
  * (variational_dataterm_grayscale=1): gray = cvtColor(fp32 RGB)*255 (fp64), np.gradient,
- * 3x3 Gaussian blur.  rgb fp32 [h,w,3] interleaved (the reference's I.astype('float32')).
+ * 3x3 Gaussian blur.  rgb [h,w,3] interleaved, fp32 or (rgb_is_f64 != 0) fp64 as load_data.py:52
+ * produces it; fp64 input is rounded to fp32 first, the reference's I.astype('float32').
  * Outputs (either may be NULL): ch64 fp64 [h,w,3] interleaved = dstack(gray, gy, gx);
  * texels fp32 [h,w,4] = (gray, gy, gx, 0) each rounded to fp32 -- the sampler's input
  * (interpolation.py:76 casts the image to fp32).  gray_scratch: h*w doubles. */
-int mrf_prepare_channels(const float* rgb, int h, int w, double* ch64, float* texels,
+int mrf_prepare_channels(const void* rgb, int rgb_is_f64, int h, int w, double* ch64, float* texels,
                          double* gray_scratch, mrf_stream_t stream);
 
 /* ---- a8: structure_refinement/interpolate_through_H.py:7-51 (compute_derivs=False) with
@@ -179,17 +194,36 @@ typedef struct {
   double cw[3];         /* channel weights (0.01,1,1) :371 */
   int    layout;        /* MRF_LAYOUT_* */
   double i32_scale;     /* for MRF_LAYOUT_HWL_I32 */
-  int    variant;       /* 0 = auto; otherwise force a kernel variant (testing/benchmarks) */
+  int    variant;       /* MRF_VARIANT_* */
 } mrf_costvol_params;
+
+/* kernel variants: STAGED copies the tile's footprint window of the neighbour frame into shared
+ * memory with TMA bulk copies and gathers from there (default); GATHER reads every tap through
+ * L1/L2 from global memory.  Results are bit-identical. */
+#define MRF_VARIANT_STAGED 0
+#define MRF_VARIANT_GATHER 1
 
 /* ref_ch: fp64 [rows,w,3] channels of the reference frame band; nb_texels as described;
  * labels: fp64 [n_labels] structure_range (device); nonrigid/occluded: uint8 [rows,w], !=0
  * zeroes the residual (:285-286), may be NULL.  cost: layout-dependent, may be NULL (then only
  * min/argmin are produced); min_cost fp32 [rows,w] / argmin int32 [rows,w] (first minimum,
- * np.argmin semantics) may be NULL. */
+ * np.argmin semantics) may be NULL.  halo_miss (device int, may be NULL; zero it first) counts
+ * in-frame samples whose taps fall outside the neighbour band nb_y0..nb_y0+nb_rows-1 -- a
+ * non-zero value means the caller's halo was too small and the band must be recomputed. */
 int mrf_cost_volume(const mrf_costvol_params* p_host, const double* ref_ch, const float* nb_texels,
                     const double* labels, const uint8_t* nonrigid, const uint8_t* occluded,
-                    void* cost, float* min_cost, int32_t* argmin, mrf_stream_t stream);
+                    void* cost, float* min_cost, int32_t* argmin, int* halo_miss, mrf_stream_t stream);
+
+/* ---- utils/robust_functions.py:26-70 on a device array: out = rho(x) (deriv = 0) or d rho/dx
+ * (deriv = 1), x = squared residual.  kind = MRF_RHO_*; p1 = sigma / eps; p2 = Charbonnier
+ * exponent a (:26; 0.5 selects the sqrt form) or, for the Geman-McClure derivative, sigma**3 as
+ * the caller's Python evaluates it (:65).  MRF_RHO_NONE writes sqrt(x), the sample of the MAD
+ * auto-sigma (:23-29). */
+int mrf_robust_apply_f64(const double* x, size_t n, int kind, int deriv, double p1, double p2,
+                         double* out, mrf_stream_t stream);
+
+/* ---- pipeline/compute_structure.py:44: cv2.erode(uint8, ones((3,3))) (default border). */
+int mrf_erode3x3_u8(const uint8_t* src, int h, int w, uint8_t* dst, mrf_stream_t stream);
 
 /* number of kernel launches the library has issued in this process (for bench.py's
  * gpu_launches); reset with mrf_reset_launch_count(). */

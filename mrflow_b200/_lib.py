@@ -1,0 +1,98 @@
+"""ctypes binding of libmrflow_b200.so (include/mrflow_b200.h).
+
+There is no fallback: if the library is missing or a call fails, an exception is raised.  Build it
+with ``python -m mrflow_b200._build`` (or ``__graft_entry__.build()``).
+"""
+import ctypes as C
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libmrflow_b200.so")
+
+INTERP = {"cubic": 0, "linear": 1}
+RHO = {"lorentzian": 0, "charbonnier": 1, "geman_mcclure": 2, "quadratic": 3, "lorentzian_auto": 4, "none": 5}
+LAYOUT = {"LHW_F32": 0, "HWL_I32": 1}
+VARIANT = {"staged": 0, "gather": 1}
+SELECT_HIST_OFFSET = 64
+
+
+class CostVolParams(C.Structure):
+    """mrf_costvol_params"""
+    _fields_ = [("rows", C.c_int), ("w", C.c_int), ("y0", C.c_int), ("frame_h", C.c_int),
+                ("nb_rows", C.c_int), ("nb_y0", C.c_int),
+                ("H", C.c_double * 9), ("q", C.c_double * 2),
+                ("mu", C.c_double), ("B", C.c_double), ("label_scale", C.c_double),
+                ("n_labels", C.c_int), ("interp", C.c_int), ("rho", C.c_int),
+                ("rho_param", C.c_double), ("cw", C.c_double * 3),
+                ("layout", C.c_int), ("i32_scale", C.c_double), ("variant", C.c_int)]
+
+
+_P, _I, _D, _Z = C.c_void_p, C.c_int, C.c_double, C.c_size_t
+_DP = C.POINTER(C.c_double)
+_IP = C.POINTER(C.c_int)
+
+# name -> (restype, argtypes); every symbol include/mrflow_b200.h declares
+SIGNATURES = {
+    "mrf_version": (C.c_int, []),
+    "mrf_last_error": (C.c_char_p, []),
+    "mrf_launch_count": (C.c_longlong, []),
+    "mrf_reset_launch_count": (None, []),
+    "mrf_flow_to_parallax": (_I, [_P, _P, _I, _I, _I, _DP, _DP, _P, _P, _P, _P, _P]),
+    "mrf_reduce_scratch_bytes": (_Z, []),
+    "mrf_epipole_dist_sum": (_I, [_I, _I, _I, _DP, _P, _P, _P]),
+    "mrf_parallax_to_structure": (_I, [_P, _I, _I, _I, _DP, _D, _D, _P, _P]),
+    "mrf_structure_to_flow": (_I, [_P, _I, _I, _I, _DP, _D, _DP, _D, _P, _P, _P, _P, _P, _P]),
+    "mrf_rigidity_unaries": (_I, [_P, _P, _I, _I, _I, _DP, _D, _D, _D, _P, _P]),
+    "mrf_rigidity_direction": (_I, [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _DP, _DP, _D, _D, _P, _P, _P]),
+    "mrf_structure_candidates": (_I, [_P, _P, _P, _I, _I, _I, _DP, _DP, _D, _D, _D, _I, _P, _P, _P, _P]),
+    "mrf_rigidity_structure": (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _D, _D, _D, _D, _P, _P, _P]),
+    "mrf_select_scratch_bytes": (_Z, [_Z]),
+    "mrf_select_kth_f64": (_I, [_P, _Z, _Z, _P, _P, _P]),
+    "mrf_select_begin": (_I, [_Z, _P, _P]),
+    "mrf_select_hist_f64": (_I, [_P, _Z, _P, _P]),
+    "mrf_select_pick": (_I, [_P, _P]),
+    "mrf_select_successor_f64": (_I, [_P, _Z, _P, _P]),
+    "mrf_select_result": (_I, [_Z, _P, _P, _P]),
+    "mrf_abs_deviation_f64": (_I, [_P, _Z, _D, _P, _P]),
+    "mrf_minmax_scratch_bytes": (_Z, []),
+    "mrf_masked_minmax_f64": (_I, [_P, _P, _I, _I, _I, _IP, _P, _P, _P]),
+    "mrf_prepare_channels": (_I, [_P, _I, _I, _I, _P, _P, _P, _P]),
+    "mrf_warp_sample": (_I, [_P, _I, _I, _I, _DP, _P, _P, _Z, _I, _P, _P, _P]),
+    "mrf_cost_volume": (_I, [C.POINTER(CostVolParams), _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
+    "mrf_erode3x3_u8": (_I, [_P, _I, _I, _P, _P]),
+    "mrf_robust_apply_f64": (_I, [_P, _Z, _I, _I, _D, _D, _P, _P]),
+}
+
+_lib = None
+
+
+def lib():
+    """The loaded library; raises if it has not been built (no CPU fallback exists)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError("libmrflow_b200.so is not built (%s); run `python -m mrflow_b200._build`. "
+                               "mrflow_b200 has no CPU fallback." % LIB_PATH)
+        L = C.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(L, name)      # AttributeError if the library lacks a declared symbol
+            fn.restype = res
+            fn.argtypes = args
+        _lib = L
+    return _lib
+
+
+class MrfError(RuntimeError):
+    pass
+
+
+def check(rc, what):
+    if rc != 0:
+        msg = lib().mrf_last_error()
+        raise MrfError("%s failed (%d): %s" % (what, rc, msg.decode() if msg else ""))
+
+
+def dvec(values):
+    """host double array argument"""
+    values = [float(v) for v in values]
+    return (C.c_double * len(values))(*values)

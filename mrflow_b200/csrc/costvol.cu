@@ -1,0 +1,341 @@
+// The per-label data cost of the plane+parallax model -- the job of the extension that is missing
+// from the reference (pipeline/build_cost_volume.py:209-219), re-specified as
+// one evaluation of the residual of computeDataTerm
+// (structure_refinement/optimize_structure_single_scale.py:210-286) per label:
+//
+//   geometry :210-235   vx = qx-x, vy = qy-y, nrm = max(0.5, |v|), n = |v|/mu,
+//                       r = (A*B*n)/(B*A/mu - 1), (xn, yn) = (x, y) + r*(v/nrm)          [fp64]
+//   warp     :238       interpolate_through_H.py:30-42: (X, Y) = H(xn, yn) in fp64, inside-frame mask
+//                       on the fp64 coordinates, cv2.remap(fp32 image, fp32 coords, CUBIC, REPLICATE)
+//   residual :269-286   Iz = mean_c((J_c - I1_c) * cw_c); 0 where outside / occluded / non-rigid
+//   cost     :302       rho(Iz^2), utils/robust_functions.py:26-70; stored as fp32
+//
+// One thread owns one reference pixel and walks the labels, so the label-major [L][rows][w] volume
+// is written with fully coalesced 128-byte warp stores and the per-pixel min/argmin is a register
+// reduction.  A block owns a 32x8 pixel tile.  In the staged variant the block first bounds the
+// footprint of its tile over the whole label range (the sample points of one pixel lie on the
+// image of its epipolar segment under H), copies that window of the neighbour frame's packed
+// texels (gray, d/dy, d/dx, 0) into shared memory with one TMA bulk copy per window row
+// (cp.async.bulk global->shared completing on an mbarrier), and gathers the 16 bicubic taps with
+// LDS.128.  Samples whose footprint leaves the staged window (labels near the pole of the
+// parallax formula, very large parallax) take the global-memory gather path, which is also the
+// whole kernel in the unstaged variant -- results are bit-identical either way.
+//
+// Arithmetic is written operation by operation in the reference's order and compiled with
+// -fmad=false, so the fp64 coordinates, the 1/32-px bins, the fp32 tap sums and the fp64 residual
+// are the oracle's bit for bit; only log() (<= 1 ulp fp64 before the fp32 rounding) can differ.
+#include "sampling.cuh"
+
+namespace mrf {
+
+constexpr int kTX = 32, kTY = 8, kThreads = kTX * kTY;
+constexpr int kMaxLabels = 256;
+constexpr int kWinCap = 3072;      // staged window capacity in texels (48 KB)
+constexpr int kWinMaxW = 384;      // widest staged row
+
+struct CVArgs {
+  int rows, w, y0, frame_h;
+  int nb_rows, nb_y0;
+  Mat3 H;
+  Pt2 q;
+  double mu, B, label_scale;
+  int L, rho;
+  double rho_param;
+  double cw0, cw1, cw2;
+  int layout;
+  float i32_scale;
+  const double* ref_ch;
+  const float4* nb;
+  const double* labels;
+  const uint8_t* nonrigid;
+  const uint8_t* occluded;
+  void* cost;
+  float* min_cost;
+  int32_t* argmin;
+  int* halo_miss;
+};
+
+// utils/robust_functions.py:26-70, argument already squared
+__device__ __forceinline__ double rho_eval(int kind, double x, double p) {
+  switch (kind) {
+    case MRF_RHO_LORENTZIAN:      return log(1.0 + x / (p * p));                 // :52
+    case MRF_RHO_CHARBONNIER:     return sqrt(x + p * p);                        // :33 (a = 0.5)
+    case MRF_RHO_GEMAN_MCCLURE:   return (p * x) / (x + p * p);                  // :64
+    case MRF_RHO_QUADRATIC:       return x;                                      // :46
+    case MRF_RHO_LORENTZIAN_AUTO: return p * log(1.0 + (0.5 * x) / (p * p));     // :58
+    default:                      return x;
+  }
+}
+
+struct FetchBand {   // neighbour texels in global memory, band rows nb_y0 .. nb_y0+nb_rows-1
+  const float4* nb; int w; int nb_y0;
+  __device__ __forceinline__ F3 operator()(int yy, int xx) const {
+    const float4 t = __ldg(nb + ((long long)(yy - nb_y0) * w + xx));
+    F3 r; r.x = t.x; r.y = t.y; r.z = t.z; return r;
+  }
+};
+struct FetchWin {    // staged window in shared memory
+  const float4* win; int ww; int wx0; int wy0;
+  __device__ __forceinline__ F3 operator()(int yy, int xx) const {
+    const float4 t = win[(yy - wy0) * ww + (xx - wx0)];
+    F3 r; r.x = t.x; r.y = t.y; r.z = t.z; return r;
+  }
+};
+
+template <int INTERP, class Fetch>
+__device__ __forceinline__ F3 sample(const Fetch& f, int h, int w, float xf, float yf) {
+  if (INTERP == MRF_INTERP_CUBIC) return sample_cubic(f, h, w, xf, yf);
+  return sample_linear(f, h, w, xf, yf);
+}
+
+template <int INTERP>
+__device__ __noinline__ F3 sample_band(const float4* nb, int w, int nb_y0, int frame_h, float xf, float yf) {
+  FetchBand f{nb, w, nb_y0};
+  return sample<INTERP>(f, frame_h, w, xf, yf);
+}
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "WAIT_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra DONE_%=;\n\t"
+      "bra WAIT_%=;\n\t"
+      "DONE_%=:\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+// TMA bulk copy global -> shared, completion counted in bytes on the mbarrier (SASS: UBLKCP)
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
+template <int INTERP, bool STAGED>
+__global__ void __launch_bounds__(kThreads, 3)
+k_cost_volume(const __grid_constant__ CVArgs a) {
+  extern __shared__ __align__(128) unsigned char dyn_smem[];
+  __shared__ double s_ab[kMaxLabels];
+  __shared__ double s_den[kMaxLabels];
+  __shared__ double s_c[2];         // min / max over labels of A*B / (B*A/mu - 1)
+  __shared__ float s_red[kTY][4];
+  __shared__ int s_win[4];          // wx0, wy0, ww, wh
+  __shared__ __align__(8) uint64_t s_bar;
+
+  const int lane = threadIdx.x & 31, wrp = threadIdx.x >> 5;
+  const int x = blockIdx.x * kTX + lane;
+  const int yl = blockIdx.y * kTY + wrp;
+  const bool valid = (x < a.w) && (yl < a.rows);
+  const int y = yl + a.y0;
+  const int L = a.L;
+
+  // per-label scalars: a = label*scale (:435-436), A*B and B*A/mu - 1 (:221)
+  for (int l = threadIdx.x; l < L; l += kThreads) {
+    const double al = a.labels[l] * a.label_scale;
+    const double ab = al * a.B;
+    s_ab[l] = ab;
+    s_den[l] = ab / a.mu - 1.0;
+  }
+  if (STAGED && threadIdx.x == 0) mbar_init(&s_bar, 1);
+  __syncthreads();
+  if (STAGED && wrp == 0) {
+    double cmin = 1.0e300, cmax = -1.0e300;
+    for (int l = lane; l < L; l += 32) {
+      const double c = s_ab[l] / s_den[l];
+      cmin = fmin(cmin, c); cmax = fmax(cmax, c);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      cmin = fmin(cmin, __shfl_xor_sync(0xffffffffu, cmin, o));
+      cmax = fmax(cmax, __shfl_xor_sync(0xffffffffu, cmax, o));
+    }
+    if (lane == 0) { s_c[0] = cmin; s_c[1] = cmax; }
+  }
+
+  // per-pixel geometry :210-218
+  const double xd = (double)x, yd = (double)y;
+  const double vx = a.q.x - xd, vy = a.q.y - yd;
+  const double dist = sqrt(vx * vx + vy * vy);
+  const double nrm = fmax(0.5, dist);
+  const double t1 = vx / nrm, t2 = vy / nrm;
+  const double n = dist / a.mu;
+
+  const long long pix = (long long)yl * a.w + x;
+  bool dead = !valid;
+  double c0 = 0.0, c1 = 0.0, c2 = 0.0;
+  if (valid) {
+    if (a.nonrigid && a.nonrigid[pix]) dead = true;    // Iz[rigidity==0] = 0   :286
+    if (a.occluded && a.occluded[pix]) dead = true;    // Iz[occlusions==1] = 0 :285
+    c0 = a.ref_ch[3 * pix]; c1 = a.ref_ch[3 * pix + 1]; c2 = a.ref_ch[3 * pix + 2];
+  }
+
+  int wx0 = 0, wy0 = 0, ww = 0, wh = 0;
+  if (STAGED) {
+    // Bound the tile's footprint: r ranges over n*[cmin, cmax]; H maps the segment to a segment.
+    float bx0 = 3.0e38f, bx1 = -3.0e38f, by0 = 3.0e38f, by1 = -3.0e38f;
+    __syncthreads();
+    if (!dead) {
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const double r = s_c[e] * n;
+        const double xn = xd + r * t1, yn = yd + r * t2;
+        double X, Y; bool in;
+        through_H(a.H, xn, yn, a.frame_h, a.w, X, Y, in);
+        const float Xf = fminf(fmaxf((float)X, -1.0e6f), 1.0e6f);   // NaN -> -1e6 .. harmless
+        const float Yf = fminf(fmaxf((float)Y, -1.0e6f), 1.0e6f);
+        bx0 = fminf(bx0, Xf); bx1 = fmaxf(bx1, Xf);
+        by0 = fminf(by0, Yf); by1 = fmaxf(by1, Yf);
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      bx0 = fminf(bx0, __shfl_xor_sync(0xffffffffu, bx0, o));
+      bx1 = fmaxf(bx1, __shfl_xor_sync(0xffffffffu, bx1, o));
+      by0 = fminf(by0, __shfl_xor_sync(0xffffffffu, by0, o));
+      by1 = fmaxf(by1, __shfl_xor_sync(0xffffffffu, by1, o));
+    }
+    if (lane == 0) { s_red[wrp][0] = bx0; s_red[wrp][1] = bx1; s_red[wrp][2] = by0; s_red[wrp][3] = by1; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      for (int k = 1; k < kTY; ++k) {
+        s_red[0][0] = fminf(s_red[0][0], s_red[k][0]); s_red[0][1] = fmaxf(s_red[0][1], s_red[k][1]);
+        s_red[0][2] = fminf(s_red[0][2], s_red[k][2]); s_red[0][3] = fmaxf(s_red[0][3], s_red[k][3]);
+      }
+      int X0 = 0, Y0 = 0, W = 0, Hh = 0;
+      if (s_red[0][0] <= s_red[0][1]) {
+        const int ylo = max(0, a.nb_y0), yhi = min(a.frame_h, a.nb_y0 + a.nb_rows) - 1;
+        int x0 = max(0, (int)floorf(s_red[0][0]) - 2), x1 = min(a.w - 1, (int)ceilf(s_red[0][1]) + 3);
+        int y0 = max(ylo, (int)floorf(s_red[0][2]) - 2), y1 = min(yhi, (int)ceilf(s_red[0][3]) + 3);
+        if (x1 >= x0 && y1 >= y0) {
+          W = x1 - x0 + 1; Hh = y1 - y0 + 1;
+          if (W > kWinMaxW) { x0 += (W - kWinMaxW) / 2; W = kWinMaxW; }
+          const int hmax = kWinCap / W;
+          if (Hh > hmax) { y0 += (Hh - hmax) / 2; Hh = hmax; }
+          X0 = x0; Y0 = y0;
+        }
+      }
+      s_win[0] = X0; s_win[1] = Y0; s_win[2] = W; s_win[3] = Hh;
+      if (W > 0) mbar_expect_tx(&s_bar, (uint32_t)(W * Hh) * 16u);
+    }
+    __syncthreads();
+    wx0 = s_win[0]; wy0 = s_win[1]; ww = s_win[2]; wh = s_win[3];
+    if (ww > 0) {
+      for (int j = threadIdx.x; j < wh; j += kThreads)
+        bulk_g2s(dyn_smem + (size_t)j * ww * 16, a.nb + ((long long)(wy0 + j - a.nb_y0) * a.w + wx0),
+                 (uint32_t)ww * 16u, &s_bar);
+      mbar_wait(&s_bar, 0);
+    }
+  }
+  if (!valid) return;
+
+  const float4* win = reinterpret_cast<const float4*>(dyn_smem);
+  const int wx1 = wx0 + ww - 1, wy1 = wy0 + wh - 1;
+  const int band_lo = a.nb_y0, band_hi = a.nb_y0 + a.nb_rows - 1;
+  const double cost_dead = rho_eval(a.rho, 0.0, a.rho_param);
+  float best = 0.f; int best_l = 0;
+  float* cost_f = (a.layout == MRF_LAYOUT_LHW_F32) ? (float*)a.cost : nullptr;
+  int32_t* cost_i = (a.layout == MRF_LAYOUT_HWL_I32) ? (int32_t*)a.cost : nullptr;
+  const size_t plane = (size_t)a.rows * a.w;
+
+  for (int l = 0; l < L; ++l) {
+    double cst = cost_dead;
+    if (!dead) {
+      const double r = (s_ab[l] * n) / s_den[l];            // :221
+      const double xn = xd + r * t1, yn = yd + r * t2;      // :224-235
+      double X, Y; bool inside;
+      through_H(a.H, xn, yn, a.frame_h, a.w, X, Y, inside);
+      if (inside) {
+        const float xf = (float)X, yf = (float)Y;           // interpolation.py:77-78
+        F3 J;
+        bool staged = false;
+        if (STAGED) {
+          int ix, iy, fx, fy;
+          cv_quantise(xf, ix, fx); cv_quantise(yf, iy, fy);
+          const int lo = (INTERP == MRF_INTERP_CUBIC) ? -1 : 0, hi = (INTERP == MRF_INTERP_CUBIC) ? 2 : 1;
+          const int xa = max(0, min(a.w - 1, ix + lo)), xb = max(0, min(a.w - 1, ix + hi));
+          const int ya = max(0, min(a.frame_h - 1, iy + lo)), yb = max(0, min(a.frame_h - 1, iy + hi));
+          staged = (xa >= wx0) && (xb <= wx1) && (ya >= wy0) && (yb <= wy1);
+        }
+        if (staged) {
+          FetchWin f{win, ww, wx0, wy0};
+          J = sample<INTERP>(f, a.frame_h, a.w, xf, yf);
+        } else {
+          // halo check for row-band inputs: taps of an in-frame sample lie in rows iy-1..iy+2
+          int iy, fy; cv_quantise(yf, iy, fy);
+          const int ya = max(0, min(a.frame_h - 1, iy - 1)), yb = max(0, min(a.frame_h - 1, iy + 2));
+          if (ya < band_lo || yb > band_hi) {
+            if (a.halo_miss) atomicAdd(a.halo_miss, 1);
+            J.x = J.y = J.z = 0.f;
+          } else {
+            J = sample_band<INTERP>(a.nb, a.w, a.nb_y0, a.frame_h, xf, yf);
+          }
+        }
+        const double e0 = ((double)J.x - c0) * a.cw0;       // :274
+        const double e1 = ((double)J.y - c1) * a.cw1;
+        const double e2 = ((double)J.z - c2) * a.cw2;
+        const double Iz = ((e0 + e1) + e2) / 3.0;
+        cst = (a.rho == MRF_RHO_NONE) ? Iz : rho_eval(a.rho, Iz * Iz, a.rho_param);   // :302
+
+      }
+    }
+    const float cf = (float)cst;
+    if (cost_f) __stcs(cost_f + (size_t)l * plane + pix, cf);
+    if (cost_i) cost_i[(size_t)pix * L + l] = (int32_t)(cf * a.i32_scale);
+    if (l == 0 || cf < best) { best = cf; best_l = l; }     // np.argmin: first minimum
+  }
+  if (a.min_cost) a.min_cost[pix] = best;
+  if (a.argmin) a.argmin[pix] = best_l;
+}
+
+}  // namespace mrf
+
+using namespace mrf;
+
+extern "C" int mrf_cost_volume(const mrf_costvol_params* p, const double* ref_ch, const float* nb_texels,
+                               const double* labels, const uint8_t* nonrigid, const uint8_t* occluded,
+                               void* cost, float* min_cost, int32_t* argmin, int* halo_miss,
+                               mrf_stream_t stream) {
+  MRF_CHECK_ARG(p && ref_ch && nb_texels && labels);
+  MRF_CHECK_ARG(p->rows > 0 && p->w > 0 && p->frame_h >= p->y0 + p->rows && p->y0 >= 0);
+  MRF_CHECK_ARG(p->nb_rows > 0 && p->nb_y0 >= 0 && p->nb_y0 + p->nb_rows <= p->frame_h);
+  MRF_CHECK_ARG(p->n_labels >= 1 && p->n_labels <= kMaxLabels);
+  MRF_CHECK_ARG(p->interp == MRF_INTERP_CUBIC || p->interp == MRF_INTERP_LINEAR);
+  MRF_CHECK_ARG(p->rho >= MRF_RHO_LORENTZIAN && p->rho <= MRF_RHO_NONE);
+  MRF_CHECK_ARG(p->layout == MRF_LAYOUT_LHW_F32 || p->layout == MRF_LAYOUT_HWL_I32);
+  MRF_CHECK_ARG(cost || min_cost || argmin);
+  MRF_CHECK_ARG(((uintptr_t)nb_texels & 15) == 0);
+  CVArgs a;
+  a.rows = p->rows; a.w = p->w; a.y0 = p->y0; a.frame_h = p->frame_h;
+  a.nb_rows = p->nb_rows; a.nb_y0 = p->nb_y0;
+  a.H = mat3(p->H); a.q = pt2(p->q);
+  a.mu = p->mu; a.B = p->B; a.label_scale = p->label_scale;
+  a.L = p->n_labels; a.rho = p->rho; a.rho_param = p->rho_param;
+  a.cw0 = p->cw[0]; a.cw1 = p->cw[1]; a.cw2 = p->cw[2];
+  a.layout = p->layout; a.i32_scale = (float)p->i32_scale;
+  a.ref_ch = ref_ch; a.nb = (const float4*)nb_texels; a.labels = labels;
+  a.nonrigid = nonrigid; a.occluded = occluded;
+  a.cost = cost; a.min_cost = min_cost; a.argmin = argmin; a.halo_miss = halo_miss;
+
+  const dim3 grid(cdiv(p->w, kTX), cdiv(p->rows, kTY));
+  const bool staged = (p->variant != MRF_VARIANT_GATHER);
+  const size_t smem = staged ? (size_t)kWinCap * 16 : 0;
+  cudaError_t e = cudaSuccess;
+#define MRF_LAUNCH(I, ST)                                                                             \
+  do {                                                                                                \
+    if (smem) e = cudaFuncSetAttribute(k_cost_volume<I, ST>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                       (int)smem);                                                    \
+    if (e == cudaSuccess) k_cost_volume<I, ST><<<grid, kThreads, smem, S(stream)>>>(a);               \
+  } while (0)
+  if (p->interp == MRF_INTERP_CUBIC) { if (staged) MRF_LAUNCH(MRF_INTERP_CUBIC, true); else MRF_LAUNCH(MRF_INTERP_CUBIC, false); }
+  else                               { if (staged) MRF_LAUNCH(MRF_INTERP_LINEAR, true); else MRF_LAUNCH(MRF_INTERP_LINEAR, false); }
+#undef MRF_LAUNCH
+  if (e != cudaSuccess) return fail((int)e, "mrf_cost_volume: %s", cudaGetErrorString(e));
+  return check_launch("mrf_cost_volume");
+}

@@ -1,0 +1,86 @@
+// Element-wise helpers around the path: the robust functions of utils/robust_functions.py:26-70
+// applied to device arrays (for callers such as optimize_structure_single_scale.py:289,302 that hold
+// the generated closures), the square root used by their MAD auto-sigma (:23-29), and the 3x3
+// erosion of the thresholded rigidity at pipeline/compute_structure.py:44.  Streaming, HBM-bound.
+#include "common.cuh"
+#include <math.h>
+
+namespace mrf {
+
+// kind = MRF_RHO_*, deriv = 0 -> rho(x), 1 -> d rho / d x  (x is the squared residual).
+// p1: sigma (or eps); p2: Charbonnier exponent a (0.5 -> sqrt form) / sigma^3 for Geman-McClure'.
+__global__ void __launch_bounds__(256)
+k_robust_apply(const double* __restrict__ x, size_t n, int kind, int deriv, double p1, double p2,
+               double* __restrict__ out) {
+  const double s2 = p1 * p1;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const double v = x[i];
+    double r;
+    switch (kind) {
+      case MRF_RHO_LORENTZIAN:
+        r = deriv ? 1.0 / (s2 + v) : log(1.0 + v / s2); break;                          // :52-53
+      case MRF_RHO_LORENTZIAN_AUTO:
+        r = deriv ? p1 / (v + 2.0 * s2) : p1 * log(1.0 + (0.5 * v) / s2); break;       // :58-59
+      case MRF_RHO_CHARBONNIER:
+        if (p2 == 0.5) r = deriv ? 1.0 / (2.0 * sqrt(v + s2)) : sqrt(v + s2);           // :33-34
+        else           r = deriv ? p2 * pow(v + s2, p2 - 1.0) : pow(v + s2, p2);        // :41-42
+        break;
+      case MRF_RHO_GEMAN_MCCLURE: {
+        const double d = v + s2;
+        r = deriv ? p2 / (d * d) : (p1 * v) / d; break;                                 // :64-65
+      }
+      case MRF_RHO_QUADRATIC:
+        r = deriv ? 1.0 : v; break;                                                     // :46-47
+      default:
+        r = sqrt(v); break;                                                             // MRF_RHO_NONE: sqrt(x) for _mad
+    }
+    out[i] = r;
+  }
+}
+
+// cv2.erode(u8, ones(3,3)) with OpenCV's default border (+inf: outside pixels never lower the min)
+__global__ void __launch_bounds__(256)
+k_erode3(const uint8_t* __restrict__ src, int h, int w, uint8_t* __restrict__ dst) {
+  const int x = blockIdx.x * 32 + (threadIdx.x & 31);
+  const int y = blockIdx.y * 8 + (threadIdx.x >> 5);
+  if (x >= w || y >= h) return;
+  uint8_t m = 255;
+#pragma unroll
+  for (int dy = -1; dy <= 1; ++dy) {
+    const int yy = y + dy;
+    if (yy < 0 || yy >= h) continue;
+#pragma unroll
+    for (int dx = -1; dx <= 1; ++dx) {
+      const int xx = x + dx;
+      if (xx < 0 || xx >= w) continue;
+      const uint8_t v = src[(long long)yy * w + xx];
+      m = v < m ? v : m;
+    }
+  }
+  dst[(long long)y * w + x] = m;
+}
+
+}  // namespace mrf
+
+using namespace mrf;
+
+extern "C" {
+
+int mrf_robust_apply_f64(const double* x, size_t n, int kind, int deriv, double p1, double p2, double* out,
+                         mrf_stream_t stream) {
+  MRF_CHECK_ARG(x && out && kind >= MRF_RHO_LORENTZIAN && kind <= MRF_RHO_NONE);
+  if (n == 0) return 0;
+  long long b = (long long)((n + 255) / 256);
+  if (b > kSMs * 16) b = kSMs * 16;
+  k_robust_apply<<<(unsigned)b, 256, 0, S(stream)>>>(x, n, kind, deriv, p1, p2, out);
+  return check_launch("mrf_robust_apply_f64");
+}
+
+int mrf_erode3x3_u8(const uint8_t* src, int h, int w, uint8_t* dst, mrf_stream_t stream) {
+  MRF_CHECK_ARG(src && dst && h > 0 && w > 0 && src != dst);
+  dim3 grid(cdiv(w, 32), cdiv(h, 8));
+  k_erode3<<<grid, 256, 0, S(stream)>>>(src, h, w, dst);
+  return check_launch("mrf_erode3x3_u8");
+}
+
+}  // extern "C"

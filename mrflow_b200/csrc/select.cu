@@ -1,0 +1,256 @@
+// Exact order statistics and masked min/max -- the global reductions the plane+parallax path needs
+// (SURVEY.md section 0 finding 5):
+//   * medians of pipeline/compute_structure.py:190 (MAD scale B_fwd) and :221 (B_b), and the
+//     auto-sigma of utils/robust_functions.py:23-29: k-th smallest of n fp64 keys, exactly, plus its
+//     successor so the caller can form numpy's mean-of-two-middles;
+//   * label range of pipeline/build_cost_volume.py:154-169,190-192: min / max with the reference's
+//     zeroing rules applied on the fly.
+//
+// Selection is an 8-pass MSD radix select over order-preserving 64-bit keys: each pass histograms one
+// byte of the keys that still match the prefix found so far (shared-memory privatised histogram,
+// one global atomic per bin per block), and a one-thread step picks the byte.  The histogram and the
+// pick are separate entry points so that a multi-GPU caller can all-reduce the 256-bin histogram
+// (2 KB over NCCL) between them -- the exchange step of SURVEY.md section 8e.  NaNs order last
+// (numpy's sort order) and are counted, since numpy's median is NaN when any is present.
+#include "common.cuh"
+
+namespace mrf {
+
+// state layout (uint64 words, device): 0 prefix (high bits found so far), 1 pass (0..8),
+// 2 k remaining inside the prefix class, 3 NaN count, 4 count(keys <= kth), 5 min key > kth
+constexpr int kStWords = 8;
+constexpr int kHistBins = 256;
+
+__device__ __forceinline__ unsigned long long order_key(double v) {
+  if (v != v) return 0xFFFFFFFFFFFFFFFFull;                 // every NaN sorts last
+  const unsigned long long b = (unsigned long long)__double_as_longlong(v);
+  return (b & 0x8000000000000000ull) ? ~b : (b | 0x8000000000000000ull);
+}
+__device__ __forceinline__ double key_value(unsigned long long k) {
+  if (k == 0xFFFFFFFFFFFFFFFFull) return __longlong_as_double(0x7FF8000000000000ll);
+  const unsigned long long b = (k & 0x8000000000000000ull) ? (k & 0x7FFFFFFFFFFFFFFFull) : ~k;
+  return __longlong_as_double((long long)b);
+}
+
+__global__ void __launch_bounds__(256)
+k_select_init(unsigned long long* st, unsigned long long k, unsigned long long* hist) {
+  if (threadIdx.x < kStWords) st[threadIdx.x] = 0;
+  __syncthreads();
+  if (threadIdx.x == 0) { st[2] = k; st[5] = 0xFFFFFFFFFFFFFFFFull; }
+  hist[threadIdx.x] = 0;
+}
+
+__global__ void __launch_bounds__(256)
+k_select_hist(const double* __restrict__ keys, size_t n, const unsigned long long* __restrict__ st,
+              unsigned long long* __restrict__ hist) {
+  __shared__ unsigned int sh[kHistBins];
+  sh[threadIdx.x] = 0;
+  __syncthreads();
+  const int pass = (int)st[1];
+  const unsigned long long prefix = st[0];
+  const int shift = 56 - 8 * pass;
+  const unsigned long long himask = pass == 0 ? 0ull : (~0ull << (shift + 8));
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const unsigned long long k = order_key(keys[i]);
+    if ((k & himask) == prefix) atomicAdd(&sh[(k >> shift) & 0xFF], 1u);
+  }
+  __syncthreads();
+  const unsigned int c = sh[threadIdx.x];
+  if (c) atomicAdd(&hist[threadIdx.x], (unsigned long long)c);
+}
+
+// pick the byte holding the k-th key; clears the histogram for the next pass
+__global__ void __launch_bounds__(32)
+k_select_pick(unsigned long long* st, unsigned long long* hist) {
+  if (threadIdx.x == 0) {
+    const int pass = (int)st[1];
+    const int shift = 56 - 8 * pass;
+    unsigned long long k = st[2];
+    int b = 0;
+    for (; b < kHistBins - 1; ++b) {
+      const unsigned long long c = hist[b];
+      if (k < c) break;
+      k -= c;
+    }
+    st[0] |= ((unsigned long long)b) << shift;
+    st[2] = k;
+    st[1] = (unsigned long long)(pass + 1);
+  }
+  __syncwarp();
+  for (int i = threadIdx.x; i < kHistBins; i += 32) hist[i] = 0;
+}
+
+// after the 8th pass st[0] is the k-th key: count keys <= it, the smallest key above it, and NaNs
+__global__ void __launch_bounds__(256)
+k_select_successor(const double* __restrict__ keys, size_t n, unsigned long long* __restrict__ st) {
+  const unsigned long long kth = st[0];
+  unsigned long long cnt_le = 0, nan = 0, min_gt = 0xFFFFFFFFFFFFFFFFull;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const double v = keys[i];
+    const unsigned long long k = order_key(v);
+    if (v != v) ++nan;
+    if (k <= kth) ++cnt_le; else if (k < min_gt) min_gt = k;
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    cnt_le += __shfl_down_sync(0xffffffffu, cnt_le, o);
+    nan += __shfl_down_sync(0xffffffffu, nan, o);
+    const unsigned long long m = __shfl_down_sync(0xffffffffu, min_gt, o);
+    min_gt = m < min_gt ? m : min_gt;
+  }
+  if ((threadIdx.x & 31) == 0) {
+    if (cnt_le) atomicAdd(&st[4], cnt_le);
+    if (nan) atomicAdd(&st[3], nan);
+    if (min_gt != 0xFFFFFFFFFFFFFFFFull) atomicMin(&st[5], min_gt);
+  }
+}
+
+// out3 = { kth, (k+1)th, #NaN }; k_orig is the rank asked for
+__global__ void k_select_result(const unsigned long long* __restrict__ st, unsigned long long k_orig,
+                                double* __restrict__ out3) {
+  const unsigned long long kth = st[0];
+  out3[0] = key_value(kth);
+  out3[1] = (st[4] >= k_orig + 2) ? key_value(kth) : key_value(st[5]);
+  out3[2] = (double)st[3];
+}
+
+// ------------------------------------------------------------------------------ masked min/max
+// numpy semantics: NaN propagates through min()/max().
+__global__ void __launch_bounds__(256)
+k_masked_minmax(const double* __restrict__ S, const uint8_t* __restrict__ zero_mask, int rows, int w, int y0,
+                int bx0, int bx1, int by0, int by1, bool have_box, double* __restrict__ part) {
+  __shared__ double smin[8], smax[8];
+  __shared__ int snan[8];
+  const long long n = (long long)rows * w;
+  double lo = INFINITY, hi = -INFINITY;
+  int nan = 0;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int yl = (int)(i / w);
+    const int x = (int)(i - (long long)yl * w);
+    const int y = yl + y0;
+    double v = S[i];
+    if (zero_mask && zero_mask[i]) v = 0.0;
+    if (have_box && x >= bx0 && x < bx1 && y >= by0 && y < by1) v = 0.0;
+    if (v != v) nan = 1;
+    lo = fmin(lo, v); hi = fmax(hi, v);
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    lo = fmin(lo, __shfl_down_sync(0xffffffffu, lo, o));
+    hi = fmax(hi, __shfl_down_sync(0xffffffffu, hi, o));
+    nan |= __shfl_down_sync(0xffffffffu, nan, o);
+  }
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  if (lane == 0) { smin[wid] = lo; smax[wid] = hi; snan[wid] = nan; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int k = 1; k < 8; ++k) { lo = fmin(lo, smin[k]); hi = fmax(hi, smax[k]); nan |= snan[k]; }
+    part[3 * blockIdx.x] = lo; part[3 * blockIdx.x + 1] = hi; part[3 * blockIdx.x + 2] = (double)nan;
+  }
+}
+
+__global__ void __launch_bounds__(256)
+k_minmax_final(const double* __restrict__ part, int nblocks, double* __restrict__ out2) {
+  __shared__ double smin[8], smax[8];
+  __shared__ int snan[8];
+  double lo = INFINITY, hi = -INFINITY;
+  int nan = 0;
+  for (int i = threadIdx.x; i < nblocks; i += blockDim.x) {
+    lo = fmin(lo, part[3 * i]); hi = fmax(hi, part[3 * i + 1]);
+    if (part[3 * i + 2] != 0.0) nan = 1;
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    lo = fmin(lo, __shfl_down_sync(0xffffffffu, lo, o));
+    hi = fmax(hi, __shfl_down_sync(0xffffffffu, hi, o));
+    nan |= __shfl_down_sync(0xffffffffu, nan, o);
+  }
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  if (lane == 0) { smin[wid] = lo; smax[wid] = hi; snan[wid] = nan; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int k = 1; k < 8; ++k) { lo = fmin(lo, smin[k]); hi = fmax(hi, smax[k]); nan |= snan[k]; }
+    const double qnan = __longlong_as_double(0x7FF8000000000000ll);
+    out2[0] = nan ? qnan : lo;
+    out2[1] = nan ? qnan : hi;
+  }
+}
+
+constexpr int kSelBlocks = kSMs * 8;
+constexpr int kMMBlocks = 592;
+
+}  // namespace mrf
+
+using namespace mrf;
+
+extern "C" {
+
+size_t mrf_select_scratch_bytes(size_t) { return sizeof(unsigned long long) * (kStWords + kHistBins); }
+
+int mrf_select_begin(size_t k, void* scratch, mrf_stream_t stream) {
+  MRF_CHECK_ARG(scratch);
+  unsigned long long* st = (unsigned long long*)scratch;
+  k_select_init<<<1, 256, 0, S(stream)>>>(st, (unsigned long long)k, st + kStWords);
+  return check_launch("mrf_select_begin");
+}
+
+int mrf_select_hist_f64(const double* keys, size_t n, void* scratch, mrf_stream_t stream) {
+  MRF_CHECK_ARG(scratch && (keys || n == 0));
+  if (n == 0) return 0;
+  unsigned long long* st = (unsigned long long*)scratch;
+  const unsigned blocks = (unsigned)((n + 255) / 256 < (size_t)kSelBlocks ? (n + 255) / 256 : kSelBlocks);
+  k_select_hist<<<blocks, 256, 0, S(stream)>>>(keys, n, st, st + kStWords);
+  return check_launch("mrf_select_hist_f64");
+}
+
+int mrf_select_pick(void* scratch, mrf_stream_t stream) {
+  MRF_CHECK_ARG(scratch);
+  unsigned long long* st = (unsigned long long*)scratch;
+  k_select_pick<<<1, 32, 0, S(stream)>>>(st, st + kStWords);
+  return check_launch("mrf_select_pick");
+}
+
+int mrf_select_successor_f64(const double* keys, size_t n, void* scratch, mrf_stream_t stream) {
+  MRF_CHECK_ARG(scratch && (keys || n == 0));
+  if (n == 0) return 0;
+  const unsigned blocks = (unsigned)((n + 255) / 256 < (size_t)kSelBlocks ? (n + 255) / 256 : kSelBlocks);
+  k_select_successor<<<blocks, 256, 0, S(stream)>>>(keys, n, (unsigned long long*)scratch);
+  return check_launch("mrf_select_successor_f64");
+}
+
+int mrf_select_result(size_t k, void* scratch, double* out3, mrf_stream_t stream) {
+  MRF_CHECK_ARG(scratch && out3);
+  k_select_result<<<1, 1, 0, S(stream)>>>((const unsigned long long*)scratch, (unsigned long long)k, out3);
+  return check_launch("mrf_select_result");
+}
+
+int mrf_select_kth_f64(const double* keys, size_t n, size_t k, double* out3, void* scratch,
+                       mrf_stream_t stream) {
+  MRF_CHECK_ARG(keys && out3 && scratch && n > 0 && k < n);
+  int rc = mrf_select_begin(k, scratch, stream);
+  for (int pass = 0; pass < 8 && !rc; ++pass) {
+    rc = mrf_select_hist_f64(keys, n, scratch, stream);
+    if (!rc) rc = mrf_select_pick(scratch, stream);
+  }
+  if (!rc) rc = mrf_select_successor_f64(keys, n, scratch, stream);
+  if (!rc) rc = mrf_select_result(k, scratch, out3, stream);
+  return rc;
+}
+
+size_t mrf_minmax_scratch_bytes(void) { return sizeof(double) * 3 * kMMBlocks; }
+
+int mrf_masked_minmax_f64(const double* Sv, const uint8_t* zero_mask, int rows, int w, int y0,
+                          const int* box_host, double* out2, void* scratch, mrf_stream_t stream) {
+  MRF_CHECK_ARG(Sv && out2 && scratch && rows > 0 && w > 0);
+  const long long n = (long long)rows * w;
+  long long nb = (n + 255) / 256;
+  if (nb > kMMBlocks) nb = kMMBlocks;
+  k_masked_minmax<<<(unsigned)nb, 256, 0, S(stream)>>>(Sv, zero_mask, rows, w, y0,
+                                                      box_host ? box_host[0] : 0, box_host ? box_host[1] : 0,
+                                                      box_host ? box_host[2] : 0, box_host ? box_host[3] : 0,
+                                                      box_host != nullptr, (double*)scratch);
+  int rc = check_launch("mrf_masked_minmax_f64/partial");
+  if (rc) return rc;
+  k_minmax_final<<<1, 256, 0, S(stream)>>>((const double*)scratch, (int)nb, out2);
+  return check_launch("mrf_masked_minmax_f64/final");
+}
+
+}  // extern "C"

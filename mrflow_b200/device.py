@@ -1,0 +1,287 @@
+"""Device-level wrappers: torch CUDA tensors in, torch CUDA tensors out, one C-ABI call each.
+
+PyTorch is plumbing here (device memory, streams); all arithmetic happens in libmrflow_b200.so.
+Every function runs on the current CUDA stream of the tensors' device and is asynchronous.
+Names follow the reference's domain; each docstring cites the reference lines it replaces
+(paths relative to the reference repository root).
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import CostVolParams, INTERP, LAYOUT, RHO, VARIANT, check, dvec
+
+F32, F64, U8, I32 = torch.float32, torch.float64, torch.uint8, torch.int32
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _p(t):
+    return C.c_void_p(0) if t is None else C.c_void_p(t.data_ptr())
+
+
+def _chk(t, dtype, name):
+    if t is None:
+        return
+    if not (t.is_cuda and t.dtype == dtype and t.is_contiguous()):
+        raise TypeError("%s must be a contiguous CUDA %s tensor" % (name, dtype))
+
+
+def _mat(H):
+    return dvec(np.asarray(H, dtype=np.float64).reshape(9))
+
+
+def _pt(q):
+    return dvec(np.asarray(q, dtype=np.float64).reshape(2))
+
+
+def launch_count():
+    return int(_lib.lib().mrf_launch_count())
+
+
+def reset_launch_count():
+    _lib.lib().mrf_reset_launch_count()
+
+
+# ------------------------------------------------------------------------------------ a1 + a2
+def flow_to_parallax(u, v, Hinv, q, y0=0, want_residual=True, want_parallax=True, want_dists=True):
+    """utils/flow_homography.py:4-16 (get_residual_flow, ``Hinv`` = inv(H)) fused with
+    pipeline/compute_structure.py:517-537 (flow2parallax).  Returns (u_res, v_res, parallax, dists)."""
+    _chk(u, F32, "u"); _chk(v, F32, "v")
+    rows, w = u.shape
+    ur = torch.empty_like(u) if want_residual else None
+    vr = torch.empty_like(u) if want_residual else None
+    par = torch.empty((rows, w), dtype=F64, device=u.device) if want_parallax else None
+    dst = torch.empty((rows, w), dtype=F64, device=u.device) if want_dists else None
+    check(_lib.lib().mrf_flow_to_parallax(_p(u), _p(v), rows, w, y0, _mat(Hinv), _pt(q), _p(ur), _p(vr), _p(par),
+                                          _p(dst), _stream()), "mrf_flow_to_parallax")
+    return ur, vr, par, dst
+
+
+def epipole_dist_sum(rows, w, q, y0=0, device="cuda"):
+    """Sum over the band of ||p - q|| (the numerator of mu, pipeline/compute_structure.py:84).
+    Returns a 1-element fp64 tensor."""
+    L = _lib.lib()
+    out = torch.empty(1, dtype=F64, device=device)
+    scratch = torch.empty(L.mrf_reduce_scratch_bytes(), dtype=U8, device=device)
+    check(L.mrf_epipole_dist_sum(rows, w, y0, _pt(q), _p(out), _p(scratch), _stream()), "mrf_epipole_dist_sum")
+    return out
+
+
+def parallax_to_structure(parallax, q, B, mu, y0=0):
+    """pipeline/compute_structure.py:25-33 (parallax2normedstructure)."""
+    _chk(parallax, F64, "parallax")
+    rows, w = parallax.shape
+    out = torch.empty_like(parallax)
+    check(_lib.lib().mrf_parallax_to_structure(_p(parallax), rows, w, y0, _pt(q), float(B), float(mu), _p(out),
+                                               _stream()), "mrf_parallax_to_structure")
+    return out
+
+
+# ------------------------------------------------------------------------------------ a6
+def structure_to_flow(structure, q, mu, H, b, y0=0, nonrigid=None, init_u=None, init_v=None):
+    """pipeline/structure2flow.py:14-38 incl. utils/flow_homography.py:20-37; with ``nonrigid`` also
+    the paste of combine_flow_simple (:72-73)."""
+    _chk(structure, F64, "structure"); _chk(nonrigid, U8, "nonrigid"); _chk(init_u, F32, "init_u"); _chk(init_v, F32, "init_v")
+    rows, w = structure.shape
+    u = torch.empty((rows, w), dtype=F32, device=structure.device)
+    v = torch.empty_like(u)
+    check(_lib.lib().mrf_structure_to_flow(_p(structure), rows, w, y0, _pt(q), float(mu), _mat(H), float(b),
+                                           _p(nonrigid), _p(init_u), _p(init_v), _p(u), _p(v), _stream()),
+          "mrf_structure_to_flow")
+    return u, v
+
+
+# ------------------------------------------------------------------------------------ a7, a4
+def rigidity_unaries(u_res, v_res, q, sigma=1.0, prior_rigid=0.5, prior_nonrigid=0.5, y0=0):
+    """rigidity/inference.py:28-59 (get_unaries_rigid)."""
+    _chk(u_res, F32, "u_res"); _chk(v_res, F32, "v_res")
+    rows, w = u_res.shape
+    out = torch.empty((rows, w), dtype=F64, device=u_res.device)
+    check(_lib.lib().mrf_rigidity_unaries(_p(u_res), _p(v_res), rows, w, y0, _pt(q), float(sigma), float(prior_rigid),
+                                          float(prior_nonrigid), _p(out), _stream()), "mrf_rigidity_unaries")
+    return out
+
+
+def rigidity_direction(res0, res1, occ0, occ1, p_cnn, q0, q1, sigma_direction, weight_cnn, y0=0):
+    """pipeline/compute_structure.py:104-153.  Returns (p_dir fp64, p_thr uint8)."""
+    for t in (*res0, *res1):
+        _chk(t, F32, "residual flow")
+    _chk(occ0, U8, "occ0"); _chk(occ1, U8, "occ1"); _chk(p_cnn, F64, "p_cnn")
+    rows, w = res0[0].shape
+    p_dir = torch.empty((rows, w), dtype=F64, device=p_cnn.device)
+    p_thr = torch.empty((rows, w), dtype=U8, device=p_cnn.device)
+    check(_lib.lib().mrf_rigidity_direction(_p(res0[0]), _p(res0[1]), _p(res1[0]), _p(res1[1]), _p(occ0), _p(occ1),
+                                            _p(p_cnn), rows, w, y0, _pt(q0), _pt(q1), float(sigma_direction),
+                                            float(weight_cnn), _p(p_dir), _p(p_thr), _stream()),
+          "mrf_rigidity_direction")
+    return p_dir, p_thr
+
+
+def structure_candidates(par0, par1, p_thr, q0, q1, mu0, mu1, B_fwd, want, y0=0, pv_out=True):
+    """pipeline/compute_structure.py:172-221: valid mask ``pv`` and the compacted candidate list whose
+    median gives B_fwd (want=1) or B_b (want=2).  Returns (pv uint8, cand fp64 [capacity], count int32[1])."""
+    _chk(par0, F64, "par0"); _chk(par1, F64, "par1"); _chk(p_thr, U8, "p_thr")
+    rows, w = par0.shape
+    dev = par0.device
+    pv = torch.empty((rows, w), dtype=U8, device=dev) if pv_out else None
+    cand = torch.empty(rows * w, dtype=F64, device=dev) if want else None
+    count = torch.zeros(1, dtype=I32, device=dev)
+    check(_lib.lib().mrf_structure_candidates(_p(par0), _p(par1), _p(p_thr), rows, w, y0, _pt(q0), _pt(q1), float(mu0),
+                                              float(mu1), float(B_fwd), int(want), _p(pv), _p(cand), _p(count),
+                                              _stream()), "mrf_structure_candidates")
+    return pv, cand, count
+
+
+def rigidity_structure(S0, S1, p_dir, p_cnn, occ0, occ1, mu0, mu1, sigma_structure, weight_cnn, want_i32=False):
+    """pipeline/compute_structure.py:374-394 (+ the int32 packing of rigidity/inference.py:113).
+    Returns (unaries fp64 [rows,w,2], unaries int32 [rows,w,2] or None)."""
+    for t in (S0, S1, p_dir, p_cnn):
+        _chk(t, F64, "fp64 plane")
+    _chk(occ0, U8, "occ0"); _chk(occ1, U8, "occ1")
+    rows, w = S0.shape
+    un = torch.empty((rows, w, 2), dtype=F64, device=S0.device)
+    ui = torch.empty((rows, w, 2), dtype=I32, device=S0.device) if want_i32 else None
+    check(_lib.lib().mrf_rigidity_structure(_p(S0), _p(S1), _p(p_dir), _p(p_cnn), _p(occ0), _p(occ1), rows, w,
+                                            float(mu0), float(mu1), float(sigma_structure), float(weight_cnn), _p(un),
+                                            _p(ui), _stream()), "mrf_rigidity_structure")
+    return un, ui
+
+
+def erode3x3(mask_u8):
+    """pipeline/compute_structure.py:44 -- cv2.erode(uint8, ones((3,3)))."""
+    _chk(mask_u8, U8, "mask")
+    h, w = mask_u8.shape
+    out = torch.empty_like(mask_u8)
+    check(_lib.lib().mrf_erode3x3_u8(_p(mask_u8), h, w, _p(out), _stream()), "mrf_erode3x3_u8")
+    return out
+
+
+# ------------------------------------------------------------------------------------ statistics
+def select_kth(keys, k, n=None):
+    """k-th smallest (0-based) of the first ``n`` fp64 keys, its successor and the NaN count, as a
+    3-element fp64 device tensor (no host synchronisation)."""
+    _chk(keys, F64, "keys")
+    L = _lib.lib()
+    n = keys.numel() if n is None else int(n)
+    out = torch.empty(3, dtype=F64, device=keys.device)
+    scratch = torch.empty(L.mrf_select_scratch_bytes(n), dtype=U8, device=keys.device)
+    check(L.mrf_select_kth_f64(_p(keys), n, int(k), _p(out), _p(scratch), _stream()), "mrf_select_kth_f64")
+    return out
+
+
+def median(keys, n=None):
+    """numpy.median of the first ``n`` keys (mean of the two middle order statistics for even n,
+    NaN if any key is NaN).  Synchronises (returns a Python float)."""
+    n = keys.numel() if n is None else int(n)
+    if n == 0:
+        return float("nan")
+    k = (n - 1) // 2
+    r = select_kth(keys, k, n).cpu().numpy()
+    if r[2] > 0:
+        return float("nan")
+    if n % 2 == 1:
+        return float(r[0])
+    return float(np.mean(np.array([r[0], r[1]])))
+
+
+def abs_deviation(x, c, n=None):
+    """|x - c| (MAD, utils/robust_functions.py:23 / pipeline/compute_structure.py:190)."""
+    _chk(x, F64, "x")
+    n = x.numel() if n is None else int(n)
+    out = torch.empty(n, dtype=F64, device=x.device)
+    check(_lib.lib().mrf_abs_deviation_f64(_p(x), n, float(c), _p(out), _stream()), "mrf_abs_deviation_f64")
+    return out
+
+
+def masked_minmax(S, zero_mask=None, box=None, y0=0):
+    """min / max of S with the pixels of ``zero_mask`` and of the half-open global box
+    (x0, x1, y0, y1) replaced by 0 (pipeline/build_cost_volume.py:154-169,190-191).  fp64[2] tensor."""
+    _chk(S, F64, "S"); _chk(zero_mask, U8, "zero_mask")
+    L = _lib.lib()
+    rows, w = S.shape
+    out = torch.empty(2, dtype=F64, device=S.device)
+    scratch = torch.empty(L.mrf_minmax_scratch_bytes(), dtype=U8, device=S.device)
+    bx = (C.c_int * 4)(*[int(b) for b in box]) if box is not None else None
+    check(L.mrf_masked_minmax_f64(_p(S), _p(zero_mask), rows, w, y0, bx, _p(out), _p(scratch), _stream()),
+          "mrf_masked_minmax_f64")
+    return out
+
+
+def robust_apply(x, kind, deriv, p1, p2=0.0):
+    """utils/robust_functions.py:26-70 on a device array (x = squared residual)."""
+    _chk(x, F64, "x")
+    out = torch.empty_like(x)
+    check(_lib.lib().mrf_robust_apply_f64(_p(x), x.numel(), RHO[kind], int(deriv), float(p1), float(p2), _p(out),
+                                          _stream()), "mrf_robust_apply_f64")
+    return out
+
+
+# ------------------------------------------------------------------------------------ a11 / a8 / a12
+def prepare_channels(rgb, want_ch64=True, want_texels=True):
+    """structure_refinement/optimize_structure_single_scale.py:350-371 (grayscale data term):
+    (gray*255, blur3(d/dy), blur3(d/dx)).  ``rgb`` [h,w,3] fp64 or fp32.  Returns
+    (ch64 fp64 [h,w,3] or None, texels fp32 [h,w,4] or None)."""
+    if not (rgb.is_cuda and rgb.is_contiguous() and rgb.dtype in (F32, F64) and rgb.dim() == 3 and rgb.shape[2] == 3):
+        raise TypeError("rgb must be a contiguous CUDA [h,w,3] fp32/fp64 tensor")
+    h, w = rgb.shape[:2]
+    dev = rgb.device
+    ch64 = torch.empty((h, w, 3), dtype=F64, device=dev) if want_ch64 else None
+    tex = torch.empty((h, w, 4), dtype=F32, device=dev) if want_texels else None
+    gray = torch.empty((h, w), dtype=F64, device=dev)
+    check(_lib.lib().mrf_prepare_channels(_p(rgb), int(rgb.dtype == F64), h, w, _p(ch64), _p(tex), _p(gray), _stream()),
+          "mrf_prepare_channels")
+    return ch64, tex
+
+
+def warp_sample(img, H, xn, yn, interp="cubic", want_mask=True):
+    """structure_refinement/interpolate_through_H.py:7-51 (compute_derivs=False).  ``img`` fp32
+    [h,w] or [h,w,C<=4]; xn, yn fp64 of any (equal) shape.  Returns (J fp32 xn.shape(+[C]), mask fp64)."""
+    _chk(img, F32, "img"); _chk(xn, F64, "xn"); _chk(yn, F64, "yn")
+    h, w = img.shape[:2]
+    Cn = 1 if img.dim() == 2 else img.shape[2]
+    n = xn.numel()
+    J = torch.empty(tuple(xn.shape) + ((Cn,) if img.dim() == 3 else ()), dtype=F32, device=img.device)
+    mask = torch.empty(tuple(xn.shape), dtype=F64, device=img.device) if want_mask else None
+    Hh = _mat(H) if H is not None else None
+    check(_lib.lib().mrf_warp_sample(_p(img), h, w, Cn, Hh, _p(xn), _p(yn), n, INTERP[interp], _p(J), _p(mask),
+                                     _stream()), "mrf_warp_sample")
+    return J, mask
+
+
+def cost_volume(ref_ch, nb_texels, labels, H, q, mu, B, label_scale=1.0, nonrigid=None, occluded=None,
+                rho="lorentzian", rho_param=1.0, cw=(0.01, 1.0, 1.0), interp="cubic", layout="LHW_F32",
+                i32_scale=1000.0, variant="staged", y0=0, frame_h=None, nb_y0=0, want_cost=True,
+                want_min=True, want_argmin=True, out=None, halo_miss=None):
+    """Per-label data cost of ONE neighbour frame (the missing extension of
+    pipeline/build_cost_volume.py:209-219, defined per SURVEY.md section 8c from
+    optimize_structure_single_scale.py:210-302).  ``ref_ch`` fp64 [rows,w,3] reference-frame channels
+    (band starting at global row ``y0``), ``nb_texels`` fp32 [nb_rows,w,4] neighbour texels (band starting
+    at ``nb_y0``), ``labels`` fp64 [L].  Returns (cost, min_cost fp32 [rows,w], argmin int32 [rows,w])."""
+    _chk(ref_ch, F64, "ref_ch"); _chk(nb_texels, F32, "nb_texels"); _chk(labels, F64, "labels")
+    _chk(nonrigid, U8, "nonrigid"); _chk(occluded, U8, "occluded")
+    rows, w = ref_ch.shape[:2]
+    nb_rows = nb_texels.shape[0]
+    frame_h = rows if frame_h is None else int(frame_h)
+    Ln = labels.numel()
+    dev = ref_ch.device
+    p = CostVolParams()
+    p.rows, p.w, p.y0, p.frame_h, p.nb_rows, p.nb_y0 = rows, w, int(y0), frame_h, nb_rows, int(nb_y0)
+    p.H = _mat(H); p.q = _pt(q)
+    p.mu, p.B, p.label_scale = float(mu), float(B), float(label_scale)
+    p.n_labels, p.interp, p.rho, p.rho_param = Ln, INTERP[interp], RHO[rho], float(rho_param)
+    p.cw = dvec(cw)
+    p.layout, p.i32_scale, p.variant = LAYOUT[layout], float(i32_scale), VARIANT[variant]
+    cost = out
+    if cost is None and want_cost:
+        cost = (torch.empty((Ln, rows, w), dtype=F32, device=dev) if layout == "LHW_F32"
+                else torch.empty((rows, w, Ln), dtype=I32, device=dev))
+    mn = torch.empty((rows, w), dtype=F32, device=dev) if want_min else None
+    am = torch.empty((rows, w), dtype=I32, device=dev) if want_argmin else None
+    check(_lib.lib().mrf_cost_volume(C.byref(p), _p(ref_ch), _p(nb_texels), _p(labels), _p(nonrigid), _p(occluded),
+                                     _p(cost), _p(mn), _p(am), _p(halo_miss), _stream()), "mrf_cost_volume")
+    return cost, mn, am

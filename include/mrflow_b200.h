@@ -88,6 +88,12 @@ int mrf_structure_to_flow(const double* structure, int rows, int w, int y0,
                           const uint8_t* nonrigid, const float* init_u, const float* init_v,
                           float* u, float* v, mrf_stream_t stream);
 
+/* ---- a6 tail on its own: utils/flow_homography.py:20-37 (get_full_flow) and :41-48
+ * (homography2flow = get_full_flow of a zero residual).  u_res, v_res fp64 (an fp32 residual
+ * promoted to fp64, which is what numpy's int64 + fp32 does at :32-33). */
+int mrf_full_flow(const double* u_res, const double* v_res, int rows, int w, int y0,
+                  const double* H_host, float* u, float* v, mrf_stream_t stream);
+
 /* ---- a7: rigidity/inference.py:28-59 (get_unaries_rigid), dtype behaviour included
  * (fp32 flow magnitude / angle, fp64 elsewhere). */
 int mrf_rigidity_unaries(const float* u_res, const float* v_res, int rows, int w, int y0,
@@ -97,12 +103,13 @@ int mrf_rigidity_unaries(const float* u_res, const float* v_res, int rows, int w
 /* ---- a4 (dense part 1): pipeline/compute_structure.py:104-153 -- direction unaries for both
  * frames (a7), the small-motion (0.6) / occlusion (0.5) overrides, the occlusion-aware merge
  * and the CNN-weighted threshold.  Inputs: residual flows of both frames, occlusion masks
- * (uint8, !=0 == occluded), CNN rigidity fp64.  Outputs: p_dir fp64, p_thr uint8. */
+ * (uint8, !=0 == occluded), CNN rigidity fp64.  Outputs: p_dir fp64, p_thr uint8, and (optional,
+ * device int) thr_count = p_thr.sum() for the TooMuchNonRigid gate (:164). */
 int mrf_rigidity_direction(const float* ures0, const float* vres0, const float* ures1, const float* vres1,
                            const uint8_t* occ0, const uint8_t* occ1, const double* p_cnn,
                            int rows, int w, int y0, const double* q0_host, const double* q1_host,
                            double sigma_direction, double weight_cnn,
-                           double* p_dir, uint8_t* p_thr, mrf_stream_t stream);
+                           double* p_dir, uint8_t* p_thr, int* thr_count, mrf_stream_t stream);
 
 /* ---- a4 (dense part 2): pipeline/compute_structure.py:172-221 -- valid-pixel mask
  * pv = |par0|>0.1 & |par1|>0.1 & p_thr, and the two candidate lists whose medians give

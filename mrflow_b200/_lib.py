@@ -42,8 +42,9 @@ SIGNATURES = {
     "mrf_epipole_dist_sum": (_I, [_I, _I, _I, _DP, _P, _P, _P]),
     "mrf_parallax_to_structure": (_I, [_P, _I, _I, _I, _DP, _D, _D, _P, _P]),
     "mrf_structure_to_flow": (_I, [_P, _I, _I, _I, _DP, _D, _DP, _D, _P, _P, _P, _P, _P, _P]),
+    "mrf_full_flow": (_I, [_P, _P, _I, _I, _I, _DP, _P, _P, _P]),
     "mrf_rigidity_unaries": (_I, [_P, _P, _I, _I, _I, _DP, _D, _D, _D, _P, _P]),
-    "mrf_rigidity_direction": (_I, [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _DP, _DP, _D, _D, _P, _P, _P]),
+    "mrf_rigidity_direction": (_I, [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _DP, _DP, _D, _D, _P, _P, _P, _P]),
     "mrf_structure_candidates": (_I, [_P, _P, _P, _I, _I, _I, _DP, _DP, _D, _D, _D, _I, _P, _P, _P, _P]),
     "mrf_rigidity_structure": (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _D, _D, _D, _D, _P, _P, _P]),
     "mrf_select_scratch_bytes": (_Z, [_Z]),

@@ -150,6 +150,26 @@ k_structure_to_flow(const double* __restrict__ structure, int rows, int w, int y
   }
 }
 
+// utils/flow_homography.py:20-37 on its own (get_full_flow): residual flow fp64 (an fp32 input
+// promoted, as numpy promotes int64 + fp32) -> full flow fp32
+__global__ void __launch_bounds__(256)
+k_full_flow(const double* __restrict__ ur, const double* __restrict__ vr, int rows, int w, int y0, Mat3 H,
+            float* __restrict__ u, float* __restrict__ v) {
+  const long long n = (long long)rows * w;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int yl = (int)(i / w);
+    const int x = (int)(i - (long long)yl * w);
+    const int y = yl + y0;
+    const float x2 = (float)((double)x + ur[i]);
+    const float y2 = (float)((double)y + vr[i]);
+    float X, Y;
+    persp_f32(x2, y2, H, X, Y);
+    u[i] = X - (float)x;
+    v[i] = Y - (float)y;
+  }
+}
+
 // ------------------------------------------------------------------------------- a7
 // Exponentially scaled modified Bessel function I0e(x) = exp(-|x|) I0(x), fp64.
 // scipy.special.ive(0, x) (the reference's call, rigidity/inference.py:54) is restated by its
@@ -183,7 +203,8 @@ __device__ __forceinline__ double unary_rigid(float ur, float vr, int x, int y, 
                                               double prior_r, double prior_n) {
   const float dist = sqrtf(ur * ur + vr * vr);
   const double ang_foe = atan2(q.y - (double)y, q.x - (double)x);
-  const float ang_uv = atan2f(vr, ur);
+  // numpy's fp32 arctan2 is libm/SVML dependent (1-4 ulp); use the correctly rounded value
+  const float ang_uv = (float)atan2((double)vr, (double)ur);
   const double ang = (double)ang_uv - ang_foe;
   const double dfl = (double)dist * sin(ang);
   const double p = 1.0 / sqrt(2.0 * 3.141592653589793 * (sigma * sigma)) *
@@ -212,8 +233,10 @@ k_rigidity_direction(const float* __restrict__ ur0, const float* __restrict__ vr
                      const float* __restrict__ ur1, const float* __restrict__ vr1,
                      const uint8_t* __restrict__ occ0, const uint8_t* __restrict__ occ1,
                      const double* __restrict__ p_cnn, int rows, int w, int y0, Pt2 q0, Pt2 q1,
-                     double sigma, double wc, double* __restrict__ p_dir, uint8_t* __restrict__ p_thr) {
+                     double sigma, double wc, double* __restrict__ p_dir, uint8_t* __restrict__ p_thr,
+                     int* __restrict__ thr_count) {
   const long long n = (long long)rows * w;
+  int mine = 0;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n;
        i += (long long)gridDim.x * blockDim.x) {
     const int yl = (int)(i / w);
@@ -232,7 +255,15 @@ k_rigidity_direction(const float* __restrict__ ur0, const float* __restrict__ vr
     if (of) pd = 0.25 + 0.5 * pb;                        // :144
     if (ob && of) pd = 0.5;                              // :146
     if (p_dir) p_dir[i] = pd;
-    if (p_thr) p_thr[i] = (wc * p_cnn[i] + (1.0 - wc) * pd) > 0.5 ? 1 : 0;   // :152-153
+    if (p_thr) {
+      const bool t = (wc * p_cnn[i] + (1.0 - wc) * pd) > 0.5;                // :152-153
+      p_thr[i] = t ? 1 : 0;
+      mine += t ? 1 : 0;
+    }
+  }
+  if (thr_count) {                                                          // p_thr.sum()  :164
+    for (int o = 16; o > 0; o >>= 1) mine += __shfl_down_sync(0xffffffffu, mine, o);
+    if ((threadIdx.x & 31) == 0 && mine) atomicAdd(thr_count, mine);
   }
 }
 
@@ -373,6 +404,13 @@ int mrf_structure_to_flow(const double* structure, int rows, int w, int y0, cons
   return check_launch("mrf_structure_to_flow");
 }
 
+int mrf_full_flow(const double* u_res, const double* v_res, int rows, int w, int y0, const double* H_host,
+                  float* u, float* v, mrf_stream_t stream) {
+  MRF_CHECK_ARG(u_res && v_res && u && v && rows > 0 && w > 0 && H_host);
+  k_full_flow<<<grid_for((long long)rows * w), 256, 0, S(stream)>>>(u_res, v_res, rows, w, y0, mat3(H_host), u, v);
+  return check_launch("mrf_full_flow");
+}
+
 int mrf_rigidity_unaries(const float* u_res, const float* v_res, int rows, int w, int y0, const double* q_host,
                          double sigma, double prior_rigid, double prior_nonrigid, double* prob,
                          mrf_stream_t stream) {
@@ -385,12 +423,18 @@ int mrf_rigidity_unaries(const float* u_res, const float* v_res, int rows, int w
 int mrf_rigidity_direction(const float* ures0, const float* vres0, const float* ures1, const float* vres1,
                            const uint8_t* occ0, const uint8_t* occ1, const double* p_cnn, int rows, int w,
                            int y0, const double* q0_host, const double* q1_host, double sigma_direction,
-                           double weight_cnn, double* p_dir, uint8_t* p_thr, mrf_stream_t stream) {
+                           double weight_cnn, double* p_dir, uint8_t* p_thr, int* thr_count,
+                           mrf_stream_t stream) {
   MRF_CHECK_ARG(ures0 && vres0 && ures1 && vres1 && rows > 0 && w > 0 && q0_host && q1_host);
   MRF_CHECK_ARG(!p_thr || p_cnn);
+  MRF_CHECK_ARG(!thr_count || p_thr);
+  if (thr_count) {
+    cudaError_t e = cudaMemsetAsync(thr_count, 0, sizeof(int), S(stream));
+    if (e != cudaSuccess) return fail((int)e, "mrf_rigidity_direction: %s", cudaGetErrorString(e));
+  }
   k_rigidity_direction<<<grid_for((long long)rows * w), 256, 0, S(stream)>>>(
       ures0, vres0, ures1, vres1, occ0, occ1, p_cnn, rows, w, y0, pt2(q0_host), pt2(q1_host),
-      sigma_direction, weight_cnn, p_dir, p_thr);
+      sigma_direction, weight_cnn, p_dir, p_thr, thr_count);
   return check_launch("mrf_rigidity_direction");
 }
 

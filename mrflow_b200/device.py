@@ -96,6 +96,16 @@ def structure_to_flow(structure, q, mu, H, b, y0=0, nonrigid=None, init_u=None, 
     return u, v
 
 
+def full_flow(u_res, v_res, H, y0=0):
+    """utils/flow_homography.py:20-37 (get_full_flow); residual fp64 -> full flow fp32."""
+    _chk(u_res, F64, "u_res"); _chk(v_res, F64, "v_res")
+    rows, w = u_res.shape
+    u = torch.empty((rows, w), dtype=F32, device=u_res.device)
+    v = torch.empty_like(u)
+    check(_lib.lib().mrf_full_flow(_p(u_res), _p(v_res), rows, w, y0, _mat(H), _p(u), _p(v), _stream()), "mrf_full_flow")
+    return u, v
+
+
 # ------------------------------------------------------------------------------------ a7, a4
 def rigidity_unaries(u_res, v_res, q, sigma=1.0, prior_rigid=0.5, prior_nonrigid=0.5, y0=0):
     """rigidity/inference.py:28-59 (get_unaries_rigid)."""
@@ -108,18 +118,20 @@ def rigidity_unaries(u_res, v_res, q, sigma=1.0, prior_rigid=0.5, prior_nonrigid
 
 
 def rigidity_direction(res0, res1, occ0, occ1, p_cnn, q0, q1, sigma_direction, weight_cnn, y0=0):
-    """pipeline/compute_structure.py:104-153.  Returns (p_dir fp64, p_thr uint8)."""
+    """pipeline/compute_structure.py:104-153.  Returns (p_dir fp64, p_thr uint8, count int32[1] =
+    p_thr.sum())."""
     for t in (*res0, *res1):
         _chk(t, F32, "residual flow")
     _chk(occ0, U8, "occ0"); _chk(occ1, U8, "occ1"); _chk(p_cnn, F64, "p_cnn")
     rows, w = res0[0].shape
     p_dir = torch.empty((rows, w), dtype=F64, device=p_cnn.device)
     p_thr = torch.empty((rows, w), dtype=U8, device=p_cnn.device)
+    cnt = torch.empty(1, dtype=I32, device=p_cnn.device)
     check(_lib.lib().mrf_rigidity_direction(_p(res0[0]), _p(res0[1]), _p(res1[0]), _p(res1[1]), _p(occ0), _p(occ1),
                                             _p(p_cnn), rows, w, y0, _pt(q0), _pt(q1), float(sigma_direction),
-                                            float(weight_cnn), _p(p_dir), _p(p_thr), _stream()),
+                                            float(weight_cnn), _p(p_dir), _p(p_thr), _p(cnt), _stream()),
           "mrf_rigidity_direction")
-    return p_dir, p_thr
+    return p_dir, p_thr, cnt
 
 
 def structure_candidates(par0, par1, p_thr, q0, q1, mu0, mu1, B_fwd, want, y0=0, pv_out=True):

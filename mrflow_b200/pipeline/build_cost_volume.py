@@ -1,0 +1,75 @@
+"""``pipeline/build_cost_volume.py`` of the reference on the B200.
+
+The reference file is an orphan: it imports a compiled extension (``linesearch``, :26-27) that was
+never shipped, so its per-label cost cannot run.  What it fixes is the interface -- the signature
+(:42), the 6-element return (:226-231), 51 labels (:50) spanning 1.5x the min/max of the normed
+structures (:190-192) -- and this module keeps exactly that.  The cost itself is the data term the
+reference does ship, evaluated once per label:
+``computeDataTerm`` geometry + ``interpolate_through_H`` + ``robust_functions``
+(structure_refinement/optimize_structure_single_scale.py:210-302), with the live conventions of
+``pipeline/compute_structure.py`` for parallax -> structure (B divides, :32).
+"""
+import numpy as np
+import torch
+
+from .. import device, planeparallax as pp
+from .._host import down, flag, require_cuda, up
+
+N_RANGES = pp.N_LABELS     # pipeline/build_cost_volume.py:50
+
+
+def build_cost_volume(images, flow, rigidity, homographies, epipoles, params=None, rho="lorentzian", sigma=1.0,
+                      interp="cubic", range_mask="as_written", layout="LHW_F32", variant="staged",
+                      return_device=False, stats=None):
+    """pipeline/build_cost_volume.py:42-231.
+
+    images: 3 x fp64 [h,w,3] in [0,1]; flow: [[u,v] bwd, [u,v] fwd] fp32; rigidity fp64 [h,w];
+    homographies 2 x 3x3; epipoles 2 x [2].  Returns the reference's 6-list
+    ``[costvol_array, structure_array, mu_array, B_array, epipoles_new_array, structure_range]``:
+    cost volumes fp32 [51,h,w] (or int32 [h,w,51] = int(cost*1000) with ``layout='HWL_I32'``, the layout
+    extern/eff_trws/image.cpp:80 reads), structures fp64 [h,w], ``B_array = [B_b, 1.0]`` (:131).
+
+    ``rho``/``sigma``: robust function of utils/robust_functions.py (fixed-parameter forms);
+    ``interp``: 'cubic' is what the reference samples with (interpolation.py:76-80), 'linear' the
+    bilinear variant; ``range_mask``: 'as_written' zeroes the pixels with rigidity > 0 before taking
+    the label range (:159, sic), 'rigid_only' the others.  ``return_device=True`` keeps everything in HBM
+    (torch CUDA tensors, plus per-pixel min cost / argmin label as a 7th element).
+    """
+    require_cuda()
+    stats = stats or pp.LocalStats()
+    rigidity = np.asarray(rigidity)
+    band = pp.Band.from_host(images, flow, rigidity, None)
+    out = cost_volume_pass(band, homographies, epipoles, rigidity > 0, stats, rho=rho, sigma=sigma, interp=interp,
+                           range_mask=range_mask, layout=layout, variant=variant)
+    cost, S, mu_ar, B_ar, q_new, labels, mins, argmins = out
+    if return_device:
+        return [cost, S, mu_ar, B_ar, q_new, labels, (mins, argmins)]
+    return [[_down_pinned(cost[0]), _down_pinned(cost[1])], [down(S[0]), down(S[1])], mu_ar, B_ar, q_new, labels]
+
+
+def _down_pinned(t):
+    """Device -> host through a pinned staging buffer (the volumes are 91 MB each at Sintel size)."""
+    host = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+    host.copy_(t, non_blocking=True)
+    torch.cuda.current_stream().synchronize()
+    return host.numpy()
+
+
+def cost_volume_pass(band, homographies, epipoles, rigid_host_mask, stats, rho="lorentzian", sigma=1.0, interp="cubic",
+                     range_mask="as_written", layout="LHW_F32", variant="staged", out=(None, None), want_cost=True,
+                     halo_miss=None):
+    """The device-resident body of build_cost_volume for one row band (everything stays in HBM)."""
+    rigid_mask = flag(rigid_host_mask) if not isinstance(rigid_host_mask, torch.Tensor) else rigid_host_mask
+    fp = pp.first_pass(band, homographies, epipoles, rigid_mask, stats)            # :78-106
+    _, B_ar = pp.scales(band, fp, rigid_mask, stats, B_fwd_fixed=1.0)               # :113-131
+    S = pp.structures(band, fp, B_ar)                                              # :145-152
+    nonrigid = (rigid_mask == 0).to(torch.uint8)
+    zero_mask = rigid_mask if range_mask == "as_written" else nonrigid             # :159
+    labels = pp.label_range(band, S, zero_mask, fp["q"], stats)                    # :154-192
+    labels_dev = torch.from_numpy(labels).to(band.device)
+    ref64, tex = pp.channels(band)
+    res = pp.cost_volumes(band, ref64, tex, labels_dev, homographies, fp["q"], fp["mu"], B_ar, nonrigid,
+                          rho=rho, rho_param=sigma, interp=interp, layout=layout, variant=variant, out=out,
+                          want_cost=want_cost, halo_miss=halo_miss)
+    cost = [res[0][0], res[1][0]]
+    return cost, S, fp["mu"], B_ar, fp["q"], labels, [res[0][1], res[1][1]], [res[0][2], res[1][2]]

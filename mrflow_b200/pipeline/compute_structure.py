@@ -1,0 +1,135 @@
+"""``pipeline/compute_structure.py`` of the reference on the B200.
+
+``compute_structure(images, flow, rigidity, occlusions_precomputed, homographies, epipoles, params)``
+keeps the reference signature (:37) and its 7-element return (:443-449); every dense per-pixel step
+runs as a CUDA kernel, the three medians as an exact radix select.  What stays on the host is what
+the reference itself delegates to host solvers: the 441-pixel BFGS of ``correct_epipole`` (:453-511),
+``refine_A`` (chumpy, :259-356) and the MRF inference of ``rigidity/inference.py:99-135`` (C++ TRW-S /
+alpha-expansion in extern/eff_trws) -- the unchanged consumer of the unaries.
+"""
+import numpy as np
+
+from .. import device, planeparallax as pp
+from .._host import down, flag, require_cuda, up
+
+
+def _default_infer_mrf():
+    try:
+        from rigidity import inference          # the reference's own module, when it is on sys.path
+        return inference.infer_mrf
+    except Exception as e:                      # noqa: BLE001
+        raise RuntimeError("rigidity.inference.infer_mrf (reference, needs extern/eff_trws) is not importable; "
+                           "pass infer_mrf= explicitly") from e
+
+
+def _refine_A():
+    try:
+        from initialization import refine_A     # reference module; needs chumpy
+        return refine_A.refine_A
+    except Exception:                           # noqa: BLE001
+        return None
+
+
+def parallax2normedstructure(parallax, q, B, mu):
+    """pipeline/compute_structure.py:25-33"""
+    require_cuda()
+    return down(device.parallax_to_structure(up(parallax, np.float64), q, B, mu))
+
+
+def flow2parallax(u, v, q):
+    """pipeline/compute_structure.py:517-537.  ``u, v`` are residual flows (fp32 as
+    get_residual_flow returns them).  Returns (parallax, foe_vectors, foe_dists)."""
+    require_cuda()
+    u = np.asarray(u); v = np.asarray(v)
+    h, w = u.shape
+    # identity homography: f32(f32(x+u)) - f32(x) == u for fp32 u on the pixel grid only when the sum
+    # is exact, so the parallax kernel is fed through the residual path with H = I and the result is
+    # recomputed from (u, v) directly below.
+    q = np.asarray(q, dtype=np.float64)
+    y, x = np.mgrid[:h, :w]
+    zero = up(np.zeros((h, w), np.float32), np.float32)
+    _, _, _, dists = device.flow_to_parallax(zero, zero, np.eye(3), q, want_residual=False, want_parallax=False)
+    dists = down(dists)
+    nx = (q[0] - x) / np.maximum(dists, 1e-3)
+    ny = (q[1] - y) / np.maximum(dists, 1e-3)
+    return u * nx + v * ny, np.dstack((nx, ny)), dists
+
+
+def correct_epipole(u, v, q, rigidity):
+    """pipeline/compute_structure.py:453-511 (host BFGS on the 21x21 window round the epipole)."""
+    import torch
+    return pp.correct_epipole(torch.from_numpy(np.ascontiguousarray(u)), torch.from_numpy(np.ascontiguousarray(v)), q,
+                              torch.from_numpy(np.ascontiguousarray(np.asarray(rigidity).astype(np.uint8))))
+
+
+def compute_structure(images, flow, rigidity, occlusions_precomputed, homographies, epipoles, params,
+                      infer_mrf=None, stats=None):
+    """pipeline/compute_structure.py:37-449.
+
+    Returns ``[structure_array, homographies, mu_array, B_array, epipoles_new_array,
+    rigidity_refined, occ]`` with the reference's types (structures fp64 [h,w] numpy arrays).
+    ``infer_mrf(I, unaries, lambd)`` defaults to the reference's ``rigidity.inference.infer_mrf``.
+    Raises ``Exception('TooMuchNonRigid')`` / ``Exception('TooFewStructureMatches')`` like the
+    reference (:165, :429) so that mrflow.py's fallback (:153-161) keeps working.
+    """
+    require_cuda()
+    stats = stats or pp.LocalStats()
+    rigidity = np.asarray(rigidity)
+    h, w = rigidity.shape
+    band = pp.Band.from_host(images, flow, rigidity, occlusions_precomputed)
+
+    if not pp.param(params, "debug_use_rigidity_gt"):
+        rigid_mask = device.erode3x3(flag(rigidity > 0.5))                    # :44
+    else:
+        rigid_mask = flag(rigidity > 0)                                       # :47 (used as `> 0`, :77)
+
+    fp = pp.first_pass(band, homographies, epipoles, rigid_mask, stats)        # :67-91
+    q_new, mu_ar = fp["q"], fp["mu"]
+
+    wc = pp.param(params, "rigidity_weight_cnn")
+    p_dir, p_thr, n_thr = device.rigidity_direction(fp["residual"][0], fp["residual"][1], band.occ[0], band.occ[1],
+                                                    band.rigidity, q_new[0], q_new[1],
+                                                    pp.param(params, "rigidity_sigma_direction"), wc)   # :104-153
+    if int(n_thr.cpu()[0]) < h * w * 0.25:
+        raise Exception("TooMuchNonRigid")                                    # :164-165
+
+    pv, B_ar = pp.scales(band, fp, p_thr, stats, pp.param(params, "scale_structure"))   # :172-223
+    S = pp.structures(band, fp, B_ar)                                         # :240-246
+    S_host = [down(S[0]), down(S[1])]
+    homographies = list(homographies) if not isinstance(homographies, list) else homographies
+
+    if pp.param(params, "nonlinear_structure_initialization") > 0:            # :259-356
+        refine = _refine_A()
+        if refine is None:
+            print("(WW) initialization.refine_A (needs chumpy) is not importable: backward H/B/q are not refined")
+        else:
+            occ_ok = (np.asarray(occlusions_precomputed[0]) == 0) * (np.asarray(occlusions_precomputed[1]) == 0)
+            A_new, H_new, B_new, q_b = refine(flow[0][0], flow[0][1], homographies[0], B_ar[0], q_new[0], mu_ar[0],
+                                              mu_ar[1], S_host[1], down(p_thr) > 0, occ_ok)
+            S_host[0] = A_new
+            S[0] = up(A_new, np.float64)
+            homographies[0] = H_new                                           # :349 (in-place update)
+            B_ar[0] = B_new
+            q_new[0] = q_b
+
+    if pp.param(params, "occlusion_reasoning") > 0:                           # :364-367
+        occ = occlusions_precomputed
+        occ_dev = band.occ
+    else:
+        occ = [np.ones((h, w)) > 0, np.ones((h, w)) > 0]
+        occ_dev = [flag(occ[0]), flag(occ[1])]
+
+    rigidity_refined = None
+    if pp.param(params, "rigidity_use_structure"):                            # :374-398
+        un, _ = device.rigidity_structure(S[0], S[1], p_dir, band.rigidity, occ_dev[0], occ_dev[1], mu_ar[0], mu_ar[1],
+                                          pp.param(params, "rigidity_sigma_structure"), wc)
+        infer = infer_mrf or _default_infer_mrf()
+        rigidity_refined = infer(np.asarray(images[1]), down(un), 1.1) > 0.5  # :396-398
+    if pp.param(params, "debug_use_rigidity_gt"):
+        rigidity_refined = rigidity                                           # :424-425
+    if rigidity_refined is None:
+        raise UnboundLocalError("rigidity_refined (rigidity_use_structure=0 without debug_use_rigidity_gt, as in the reference)")
+    if (rigidity_refined == 1).sum() < 0.25 * rigidity_refined.size:
+        raise Exception("TooFewStructureMatches")                             # :427-429
+
+    return [S_host, homographies, mu_ar, B_ar, q_new, rigidity_refined, occ]

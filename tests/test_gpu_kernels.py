@@ -107,8 +107,10 @@ def test_rigidity_unaries(dev, trip):
         q = t["epipoles"][f]
         want = hp.get_unaries_rigid(x, y, ref[f][0], ref[f][1], q[0], q[1], sigma=1.0)
         got = dev.rigidity_unaries(cu(ref[f][0]), cu(ref[f][1]), q, sigma=1.0).cpu().numpy()
-        # transcendental functions (atan2, sin, exp, I0e) agree to a few ulp; one fp32 rounding inside
-        np.testing.assert_allclose(got, want, rtol=2e-6, atol=1e-300)
+        # transcendental functions (atan2, sin, exp, I0e) agree to a few ulp, but the reference
+        # evaluates arctan2 on fp32 data (numpy's fp32 loop: 1-4 ulp, CPU dependent), so a few
+        # pixels move by an fp32 ulp of the angle: probabilities within 1e-5 relative
+        np.testing.assert_allclose(got, want, rtol=1e-5, atol=1e-300)
         assert np.median(np.abs(got - want) / np.maximum(np.abs(want), 1e-300)) < 1e-12
 
 
@@ -125,10 +127,11 @@ def test_compute_structure_dense_parts(dev, trip):
     S, _, mu_ar, B_ar, q_new, _, _ = out
     res = inter["residual"]
     o8 = [cu(o.astype(np.uint8)) for o in occ]
-    p_dir, p_thr = dev.rigidity_direction([cu(res[0][0]), cu(res[0][1])], [cu(res[1][0]), cu(res[1][1])], o8[0], o8[1],
+    p_dir, p_thr, n_thr = dev.rigidity_direction([cu(res[0][0]), cu(res[0][1])], [cu(res[1][0]), cu(res[1][1])], o8[0], o8[1],
                                           cu(t["rigidity"]), q_new[0], q_new[1], 1.0, params.rigidity_weight_cnn)
-    np.testing.assert_allclose(p_dir.cpu().numpy(), inter["p_dir"], rtol=2e-6)
+    np.testing.assert_allclose(p_dir.cpu().numpy(), inter["p_dir"], rtol=1e-5)
     thr_ref = inter["p_thr"]
+    assert int(n_thr.cpu()[0]) == int(p_thr.sum().cpu())
     margin = np.abs(params.rigidity_weight_cnn * t["rigidity"] + (1 - params.rigidity_weight_cnn) * inter["p_dir"] - 0.5)
     assert np.array_equal(p_thr.cpu().numpy()[margin > 1e-5] > 0, thr_ref[margin > 1e-5])
 

@@ -1,0 +1,356 @@
+#!/usr/bin/env python
+"""bench.py -- cost-volume pixel*labels/s of the plane+parallax hot path (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W]                 # our arm
+    python bench.py --impl reference [--gpus N] [--steps K] [--warmup W]  # the reference's CPU path
+
+One step = one pass of the hot path over one synthetic triplet that is already resident in HBM:
+flow -> residual flow -> parallax -> mu, B -> normed structures -> label range -> channels of the
+three frames -> per-label data cost of both neighbour frames (51 labels, min / argmin) -> structure ->
+flow.  Work units = 2 neighbour frames x h x w x 51 labels.  At N > 1 every
+rank owns its own triplet (triplet-parallel, mrflow_dataset.py-style; no data-path collective): weak
+scaling.  ``--mode bands`` runs ONE frame sharded by row bands with halos instead (strong scaling;
+NCCL only for the tiny statistics all-reduces), used for the 4K configuration.
+
+Prints ONE JSON line on rank 0.
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+N_LABELS = 51
+METRIC = "cost_volume_pixel_labels_per_s"
+UNIT = "pixel*labels/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=None)
+    ap.add_argument("--warmup", type=int, default=None)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--shape", default="sintel", help="sintel | kitti | 4k | HxW")
+    ap.add_argument("--interp", default="cubic", choices=["cubic", "linear"])
+    ap.add_argument("--variant", default="staged", choices=["staged", "gather"])
+    ap.add_argument("--mode", default="triplets", choices=["triplets", "bands"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+def shape_of(s):
+    from mrflow_b200 import synth
+    if s in synth.SHAPES:
+        return synth.SHAPES[s]
+    h, w = s.lower().split("x")
+    return int(h), int(w)
+
+
+def workload_name(args, hw):
+    return "%s_%dx%d_L%d_F2_%s" % (args.shape, hw[1], hw[0], N_LABELS, args.interp)
+
+
+def algorithmic_bytes_per_launch(h, w, L=N_LABELS):
+    """per neighbour-frame launch, every input read once and every output
+    written once: cost store L*4, min/argmin 4, neighbour channels 3*4, masks 2, plus half of the
+    reference-frame channels (3*4, shared by the two launches) = 228 B/px at L = 51."""
+    return h * w * (L * 4 + 4 + 12 + 2 + 6)
+
+
+# ------------------------------------------------------------------------------------------ clocks
+class ClockSampler:
+    """Samples SM clock and throttle reasons through NVML while the timed region runs."""
+
+    def __init__(self, index):
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop = threading.Event()
+        self._thr = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:   # noqa: BLE001
+            self.nv = None
+
+    def _run(self):
+        nv = self.nv
+        names = {"hw_slowdown": nv.nvmlClocksThrottleReasonHwSlowdown,
+                 "hw_thermal_slowdown": nv.nvmlClocksThrottleReasonHwThermalSlowdown,
+                 "sw_thermal_slowdown": nv.nvmlClocksThrottleReasonSwThermalSlowdown,
+                 "sw_power_cap": nv.nvmlClocksThrottleReasonSwPowerCap}
+        while not self._stop.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for k, bit in names.items():
+                    if r & bit:
+                        self.reasons.add(k)
+            except Exception:   # noqa: BLE001
+                pass
+            time.sleep(0.002)
+
+    def __enter__(self):
+        if self.nv is not None:
+            self._thr = threading.Thread(target=self._run, daemon=True)
+            self._thr.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        if self._thr is not None:
+            self._thr.join()
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": ["nvml unavailable"]}
+        return {"sm_mhz": float(np.median(self.samples)), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(self.samples)}
+
+
+# ------------------------------------------------------------------------------------------ CPU arm
+def cpu_reference_step(t, ch, state, label_idx):
+    """One bounded sample of the workload on the host: the oracle's cost volume (reference sampler
+    cv2.remap + reference geometry + Lorentzian) for ``label_idx`` of the 51 labels on both frames.
+    Returns (seconds, pixel*labels done)."""
+    from oracle import hotpath as hp
+    h, w = t["shape"]
+    noocc = [np.zeros((h, w), bool)] * 2
+    t0 = time.perf_counter()
+    hp.cost_volume(ch, t["rigidity"], noocc, t["homographies"], state["B"], state["mu"], state["q"], state["labels"],
+                   kind="lorentzian", sigma=1.0, labels=label_idx)
+    return time.perf_counter() - t0, 2 * h * w * len(label_idx)
+
+
+def cpu_front_and_tail(t):
+    """The non-cost-volume part of a step on the host (structure pre-pass, label range, channels,
+    structure -> flow).  Returns (seconds, state)."""
+    from oracle import hotpath as hp
+    h, w = t["shape"]
+    y, x = np.mgrid[:h, :w]
+    t0 = time.perf_counter()
+    par, q_new, mu_ar, dn = [], [], [], []
+    rig = t["rigidity"]
+    for f in range(2):
+        ur, vr = hp.get_residual_flow(x, y, t["flow"][f][0], t["flow"][f][1], t["homographies"][f])
+        qn = hp.correct_epipole(ur, vr, t["epipoles"][f], rig > 0)
+        p, _, d = hp.flow2parallax(ur, vr, qn)
+        par.append(p); q_new.append(qn); mu_ar.append(d.mean()); dn.append(d / mu_ar[-1])
+    pv = np.logical_and(np.logical_and(np.abs(par[0]) > 0.1, np.abs(par[1]) > 0.1), rig > 0)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        target = par[1][pv] / (1.0 * (par[1][pv] / mu_ar[1] - dn[1][pv]))
+        template = mu_ar[1] / mu_ar[0] * par[0][pv] / (par[0][pv] / mu_ar[0] - dn[0][pv])
+        B_ar = [np.median(template / target), 1.0]
+    S = [hp.parallax2normedstructure(par[f], q_new[f], B_ar[f], mu_ar[f]) for f in range(2)]
+    labels = hp.structure_range(S, rig, q_new)
+    ch = [hp.prepare_channels(I) for I in t["images"]]
+    hp.combine_flow(S[1], t["flow"][1], (rig > 0).astype(np.float64), q_new, mu_ar, t["homographies"], B_ar)
+    dt = time.perf_counter() - t0
+    return dt, dict(B=B_ar, mu=mu_ar, q=q_new, labels=labels, S=S), ch
+
+
+def host_threads():
+    try:
+        import cv2
+        return int(cv2.getNumThreads())
+    except Exception:   # noqa: BLE001
+        return os.cpu_count() or 1
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from mrflow_b200 import synth
+    hw = shape_of(args.shape)
+    steps = 8 if args.steps is None else args.steps
+    warm = 1 if args.warmup is None else args.warmup
+    t = synth.make_triplet(hw, seed=1001)
+    t_rest, state, ch = cpu_front_and_tail(t)
+    idx = [0, 17, 34, 50]
+    for _ in range(warm):
+        cpu_reference_step(t, ch, state, idx)
+    tot_s, tot_u = 0.0, 0
+    for _ in range(steps):
+        dt, units = cpu_reference_step(t, ch, state, idx)
+        tot_s += dt + t_rest * len(idx) / N_LABELS       # pro-rated share of the non-cost-volume work
+        tot_u += units
+    value = tot_u / tot_s
+    cores = host_threads()
+    sample = "%d of %d labels x 2 frames per step on the full %dx%d triplet; structure pre-pass / channels / " \
+             "structure->flow timed once (%.3f s) and pro-rated" % (len(idx), N_LABELS, hw[1], hw[0], t_rest)
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
+            "warmup": warm, "ms_per_step": 1e3 * tot_s / max(steps, 1), "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": workload_name(args, hw), "labels": N_LABELS, "frames": 2, "interp": args.interp},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
+                             "host_cpus": os.cpu_count()},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------ our arm
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from mrflow_b200 import device, planeparallax as pp, synth
+    from mrflow_b200.pipeline import build_cost_volume as bcv
+    from mrflow_b200.pipeline import structure2flow as s2f
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py needs a CUDA device; mrflow_b200 has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    steps = 30 if args.steps is None else args.steps
+    warm = 5 if args.warmup is None else max(args.warmup, 3)
+    hw = shape_of(args.shape)
+    h, w = hw
+
+    if args.mode == "bands" and world > 1:
+        from mrflow_b200 import sharding
+        return sharding.bench_bands(args, hw, steps, warm, METRIC, UNIT, workload_name(args, hw), ClockSampler)
+
+    t = synth.make_triplet(hw, seed=1001 + rank)
+    rig_host = t["rigidity"] > 0
+    band = pp.Band.from_host(t["images"], t["flow"], t["rigidity"], None)
+    rigid_mask = torch.from_numpy(rig_host.astype(np.uint8)).cuda()
+    nonrigid = (rigid_mask == 0).to(torch.uint8)
+    stats = pp.LocalStats()
+    cost_out = (torch.empty((N_LABELS, h, w), dtype=torch.float32, device="cuda"),
+                torch.empty((N_LABELS, h, w), dtype=torch.float32, device="cuda"))
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")    # > 126 MB L2
+    kernel_events = []
+
+    def step(events=None):
+        out = bcv.cost_volume_pass(band, t["homographies"], t["epipoles"], rigid_mask, stats, rho="lorentzian", sigma=1.0,
+                                   interp=args.interp, variant=args.variant, out=cost_out, events=events)
+        cost, S, mu_ar, B_ar, q_new, labels, mins, argmins = out
+        u, v = device.structure_to_flow(S[1], q_new[1], mu_ar[1], t["homographies"][1], B_ar[1], nonrigid=nonrigid,
+                                        init_u=band.flow[1][0], init_v=band.flow[1][1])
+        return argmins, u, v
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(warm):
+        step()
+    barrier()
+    device.reset_launch_count()
+    total_ms = 0.0
+    with ClockSampler(local) as clocks:
+        for _ in range(steps):
+            flush.fill_(1)                                   # evict L2 between timed iterations
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            step(kernel_events)
+            e1.record()
+            e1.synchronize()
+            total_ms += e0.elapsed_time(e1)
+    launches = device.launch_count()
+    barrier()
+    tmax = torch.tensor([total_ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+    total_ms_max = float(tmax.cpu()[0])
+    units_per_step = 2 * h * w * N_LABELS
+    value = world * units_per_step * steps / (total_ms_max * 1e-3)
+
+    # dominant kernel: k_cost_volume (one launch per neighbour frame)
+    kms = [a.elapsed_time(b) for a, b in kernel_events]
+    k_avg_ms = float(np.mean(kms))
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:   # noqa: BLE001
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    achieved = algorithmic_bytes_per_launch(h, w) / (k_avg_ms * 1e-3) / 1e9
+    traffic = None
+    try:
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(workload_name(args, hw))
+    except Exception:   # noqa: BLE001
+        pass
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": traffic, "kernel": "k_cost_volume", "kernel_ms": k_avg_ms,
+                "kernel_share_of_step": 2 * k_avg_ms * steps / total_ms,
+                "peak_source": "measured (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks else "fallback"}
+
+    # ---- end to end through the public host API (numpy in pinned memory -> numpy out)
+    e2e = None
+    if not args.no_e2e:
+        def pinned(a):
+            tt = torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
+            return tt.numpy()
+        images = [pinned(I) for I in t["images"]]
+        flow = [[pinned(t["flow"][f][0]), pinned(t["flow"][f][1])] for f in range(2)]
+        rig = pinned(t["rigidity"])
+        h2d = sum(a.nbytes for a in images) + sum(a.nbytes for f in flow for a in f) + rig.nbytes
+        h2d += h * w * (8 + 4 + 4 + 1)                       # structure + initial flow + rigidity flags of combine_flow
+
+        def e2e_step():
+            out = bcv.build_cost_volume(images, flow, rig, t["homographies"], t["epipoles"], None, interp=args.interp,
+                                        variant=args.variant)
+            r, u, v = s2f.combine_flow(out[1][1], flow[1], rig, out[4], out[2], t["homographies"], out[3])
+            return out, u, v
+        n_e2e = max(3, min(steps, 10))
+        for _ in range(2):
+            out, u, v = e2e_step()
+        d2h = sum(a.nbytes for a in out[0]) + sum(a.nbytes for a in out[1]) + u.nbytes + v.nbytes
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(n_e2e):
+            e2e_step()
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        tt = torch.tensor([dt], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        e2e = {"value": world * units_per_step * n_e2e / float(tt.cpu()[0]), "unit": UNIT, "h2d_bytes_per_step": int(h2d),
+               "d2h_bytes_per_step": int(d2h), "steps": n_e2e, "api": "mrflow_b200.pipeline.build_cost_volume + combine_flow"}
+
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        t_rest, state, ch = cpu_front_and_tail(t)
+        idx = list(range(0, N_LABELS, 3))                    # 17 of 51 labels: ~10-20 s on 8 cores
+        dt, units = cpu_reference_step(t, ch, state, idx)
+        cpu_baseline = {"value": units / (dt + t_rest * len(idx) / N_LABELS), "unit": UNIT, "cores": host_threads(),
+                        "kind": "port", "host_cpus": os.cpu_count(),
+                        "sample": "%d of %d labels x 2 frames of the same triplet, 1 pass (%.1f s)" % (len(idx), N_LABELS, dt)}
+
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": warm,
+                "ms_per_step": total_ms_max / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "f64 geometry / f32 sampling", "data": "synthetic",
+                "config": {"workload": workload_name(args, hw), "labels": N_LABELS, "frames": 2, "interp": args.interp,
+                           "variant": args.variant, "parallelism": "triplets x%d" % world,
+                           "l2": "flushed between timed steps (256 MiB fill); outputs 182 MB > L2"},
+                "clocks": clocks.summary(), "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
+                "cpu_baseline": cpu_baseline}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    a = parse()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_ours(a)

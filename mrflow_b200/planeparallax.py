@@ -248,16 +248,22 @@ def channels(band):
 
 def cost_volumes(band, ref64, tex, labels_dev, homographies, q_ar, mu_ar, B_ar, nonrigid, occluded=(None, None),
                  rho="lorentzian", rho_param=1.0, interp="cubic", layout="LHW_F32", variant="staged",
-                 out=(None, None), want_cost=True, i32_scale=1000.0, halo_miss=None, frames=(0, 1)):
+                 out=(None, None), want_cost=True, i32_scale=1000.0, halo_miss=None, frames=(0, 1), events=None):
     """The per-label data cost of both neighbour frames (see device.cost_volume).  The backward
     frame is evaluated at ``label * mu0/mu1`` with the index-0 parameters
     (optimize_structure_single_scale.py:435-442)."""
     res = [None, None]
     for f in frames:
         scale = (mu_ar[0] / mu_ar[1]) if f == 0 else 1.0
+        if events is not None:
+            ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+            ev[0].record()
         res[f] = device.cost_volume(ref64, tex[f], labels_dev, homographies[f], q_ar[f], mu_ar[f], B_ar[f],
                                     label_scale=scale, nonrigid=nonrigid, occluded=occluded[f], rho=rho,
                                     rho_param=rho_param, cw=CHANNEL_WEIGHTS, interp=interp, layout=layout,
                                     i32_scale=i32_scale, variant=variant, y0=band.y0, frame_h=band.frame_h,
                                     nb_y0=band.nb_y0, out=out[f], want_cost=want_cost, halo_miss=halo_miss)
+        if events is not None:
+            ev[1].record()
+            events.append(ev)
     return res

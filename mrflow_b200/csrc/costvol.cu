@@ -23,7 +23,10 @@
 //
 // Arithmetic is written operation by operation in the reference's order and compiled with
 // -fmad=false, so the fp64 coordinates, the 1/32-px bins, the fp32 tap sums and the fp64 residual
-// are the oracle's bit for bit; only log() (<= 1 ulp fp64 before the fp32 rounding) can differ.
+// are the oracle's bit for bit; only log() (relative error < 2^-43 before the fp32 rounding) can
+// differ.  Divisions by per-label / per-launch constants and the two projective divisions that share
+// a divisor are evaluated with a reciprocal and exact FMA remainder corrections (div_rc), which
+// returns the correctly rounded quotient -- the same bits as a division -- at a fifth of the cost.
 #include "sampling.cuh"
 
 namespace mrf {
@@ -118,15 +121,72 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
                ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
 
+// ---------------------------------------------------------------------------------------------
+// Exact fp64 division with a known reciprocal.  For rd = RN(1/d) and no over/underflow,
+// q0 = a*rd is within 2 ulp of a/d, one remainder correction makes it faithful, and by Markstein's
+// theorem the second correction (exact remainder of a faithful quotient, fma with RN(1/d)) returns
+// RN(a/d) -- the same bits as the reference's `/`, in 5 fp64 instructions instead of a division
+// subroutine.  tests/test_exact_division.py replays the sequence in rational arithmetic.
+__device__ __forceinline__ double div_rc(double a, double d, double rd) {
+  double q = a * rd;
+  double r = fma(-d, q, a);
+  q = fma(r, rd, q);
+  r = fma(-d, q, a);
+  return fma(r, rd, q);
+}
+// exponent of a double within [2^-100, 2^100] (and finite, non-zero): the range in which the
+// sequences above cannot over/underflow for this kernel's operands
+__device__ __forceinline__ bool tame(double v) {
+  const unsigned ex = ((unsigned)__double2hiint(v) >> 20) & 0x7ffu;
+  return (ex - 923u) <= 200u;
+}
+
+// log(u) for u >= 1 (u = 1 + z of the Lorentzian, utils/robust_functions.py:52,58).  Argument
+// reduction u = m*2^e with m in [sqrt(1/2), sqrt(2)), s = (m-1)/(m+1), log m = 2 atanh(s) as an
+// odd polynomial through s^15; relative error < 2^-43, i.e. the fp32 cost the kernel stores is the
+// correctly rounded one except for about one sample in 2^19 (then off by one fp32 ulp, 6e-8
+// relative, against the 1e-5 bar).  numpy's own log is only specified to < 1 ulp of fp64 either.
+__device__ __forceinline__ double log_ge1(double u) {
+  int hi = __double2hiint(u);
+  const int lo = __double2loint(u);
+  if (hi >= 0x7ff00000) return u;                       // inf / NaN
+  int e = (hi >> 20) - 1023;
+  hi = (hi & 0x000fffff) | 0x3ff00000;
+  if (hi >= 0x3ff6a09e) { hi -= 0x00100000; e += 1; }   // m >= sqrt(2): halve
+  const double m = __hiloint2double(hi, lo);
+  const double f = m - 1.0;
+  const double d = 2.0 + f;
+  double y;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(d));
+  double t = fma(-d, y, 1.0);
+  y = fma(y, t, y);
+  t = fma(-d, y, 1.0);
+  y = fma(y, t, y);
+  const double sv = f * y;
+  const double s2 = sv * sv;
+  double pl = fma(s2, 1.0 / 15.0, 1.0 / 13.0);
+  pl = fma(s2, pl, 1.0 / 11.0);
+  pl = fma(s2, pl, 1.0 / 9.0);
+  pl = fma(s2, pl, 1.0 / 7.0);
+  pl = fma(s2, pl, 1.0 / 5.0);
+  pl = fma(s2, pl, 1.0 / 3.0);
+  pl = pl * s2;
+  const double two_s = sv + sv;
+  return fma((double)e, 0.6931471805599453094, fma(two_s, pl, two_s));
+}
+
 template <int INTERP, bool STAGED>
 __global__ void __launch_bounds__(kThreads, 3)
 k_cost_volume(const __grid_constant__ CVArgs a) {
   extern __shared__ __align__(128) unsigned char dyn_smem[];
-  __shared__ double s_ab[kMaxLabels];
-  __shared__ double s_den[kMaxLabels];
-  __shared__ double s_c[2];         // min / max over labels of A*B / (B*A/mu - 1)
+  __shared__ double s_ab[kMaxLabels];       // A*B per label
+  __shared__ double s_den[kMaxLabels];      // B*A/mu - 1
+  __shared__ double s_rden[kMaxLabels];     // RN(1 / s_den)
+  __shared__ unsigned char s_safe[kMaxLabels];
+  __shared__ __align__(16) float4 s_wt[32]; // OpenCV's interpolation table: weights at frac/32
+  __shared__ double s_c[2];                 // min / max over labels of A*B / (B*A/mu - 1)
   __shared__ float s_red[kTY][4];
-  __shared__ int s_win[4];          // wx0, wy0, ww, wh
+  __shared__ int s_win[4];                  // wx0, wy0, ww, wh
   __shared__ __align__(8) uint64_t s_bar;
 
   const int lane = threadIdx.x & 31, wrp = threadIdx.x >> 5;
@@ -140,8 +200,17 @@ k_cost_volume(const __grid_constant__ CVArgs a) {
   for (int l = threadIdx.x; l < L; l += kThreads) {
     const double al = a.labels[l] * a.label_scale;
     const double ab = al * a.B;
+    const double den = ab / a.mu - 1.0;
     s_ab[l] = ab;
-    s_den[l] = ab / a.mu - 1.0;
+    s_den[l] = den;
+    s_rden[l] = 1.0 / den;
+    s_safe[l] = (tame(den) && (ab == 0.0 || tame(ab))) ? 1 : 0;
+  }
+  if (threadIdx.x >= 32 && threadIdx.x < 64) {
+    const int fr = threadIdx.x - 32;
+    float wv[4] = {0.f, 0.f, 0.f, 0.f};
+    if (INTERP == MRF_INTERP_CUBIC) cubic_weights(fr, wv); else linear_weights(fr, wv);
+    s_wt[fr] = make_float4(wv[0], wv[1], wv[2], wv[3]);
   }
   if (STAGED && threadIdx.x == 0) mbar_init(&s_bar, 1);
   __syncthreads();
@@ -166,6 +235,7 @@ k_cost_volume(const __grid_constant__ CVArgs a) {
   const double nrm = fmax(0.5, dist);
   const double t1 = vx / nrm, t2 = vy / nrm;
   const double n = dist / a.mu;
+  const bool n_tame = (n == 0.0) || tame(n);
 
   const long long pix = (long long)yl * a.w + x;
   bool dead = !valid;
@@ -236,9 +306,16 @@ k_cost_volume(const __grid_constant__ CVArgs a) {
   if (!valid) return;
 
   const float4* win = reinterpret_cast<const float4*>(dyn_smem);
-  const int wx1 = wx0 + ww - 1, wy1 = wy0 + wh - 1;
+  // first-tap positions whose whole footprint is inside the staged window AND strictly inside the
+  // image (OpenCV's row-sum order): ix0 in [fx_lo, fx_hi], iy0 in [fy_lo, fy_hi]
+  constexpr int kTaps = (INTERP == MRF_INTERP_CUBIC) ? 4 : 2;
+  constexpr int kOff = (INTERP == MRF_INTERP_CUBIC) ? 1 : 0;
+  const int fx_lo = wx0, fx_hi = min(wx0 + ww, a.w) - kTaps;
+  const int fy_lo = wy0, fy_hi = min(wy0 + wh, a.frame_h) - kTaps;
   const int band_lo = a.nb_y0, band_hi = a.nb_y0 + a.nb_rows - 1;
   const double cost_dead = rho_eval(a.rho, 0.0, a.rho_param);
+  const double s2 = a.rho_param * a.rho_param, rs2 = 1.0 / s2;
+  const bool lor_fast = (a.rho == MRF_RHO_LORENTZIAN) && tame(s2);
   float best = 0.f; int best_l = 0;
   float* cost_f = (a.layout == MRF_LAYOUT_LHW_F32) ? (float*)a.cost : nullptr;
   int32_t* cost_i = (a.layout == MRF_LAYOUT_HWL_I32) ? (int32_t*)a.cost : nullptr;
@@ -247,28 +324,67 @@ k_cost_volume(const __grid_constant__ CVArgs a) {
   for (int l = 0; l < L; ++l) {
     double cst = cost_dead;
     if (!dead) {
-      const double r = (s_ab[l] * n) / s_den[l];            // :221
+      // r = A*B*n / (B*A/mu - 1)  :221
+      const double num = s_ab[l] * n;
+      const double r = (s_safe[l] && n_tame) ? div_rc(num, s_den[l], s_rden[l]) : num / s_den[l];
       const double xn = xd + r * t1, yn = yd + r * t2;      // :224-235
-      double X, Y; bool inside;
-      through_H(a.H, xn, yn, a.frame_h, a.w, X, Y, inside);
+      // interpolate_through_H.py:31-35
+      const double den = (xn * a.H.m[6] + yn * a.H.m[7]) + a.H.m[8];
+      const double Xn = (xn * a.H.m[0] + yn * a.H.m[1]) + a.H.m[2];
+      const double Yn = (xn * a.H.m[3] + yn * a.H.m[4]) + a.H.m[5];
+      double X, Y;
+      if (tame(den)) {
+        const double rd = __drcp_rn(den);
+        X = div_rc(Xn, den, rd);
+        Y = div_rc(Yn, den, rd);
+      } else {
+        X = Xn / den; Y = Yn / den;
+      }
+      const bool inside = (X >= 0.0) && (X <= (double)(a.w - 1)) && (Y >= 0.0) && (Y <= (double)(a.frame_h - 1));  // :39
       if (inside) {
         const float xf = (float)X, yf = (float)Y;           // interpolation.py:77-78
+        int ix, iy, fx, fy;
+        cv_quantise(xf, ix, fx); cv_quantise(yf, iy, fy);
+        const int ix0 = ix - kOff, iy0 = iy - kOff;
         F3 J;
-        bool staged = false;
-        if (STAGED) {
-          int ix, iy, fx, fy;
-          cv_quantise(xf, ix, fx); cv_quantise(yf, iy, fy);
-          const int lo = (INTERP == MRF_INTERP_CUBIC) ? -1 : 0, hi = (INTERP == MRF_INTERP_CUBIC) ? 2 : 1;
-          const int xa = max(0, min(a.w - 1, ix + lo)), xb = max(0, min(a.w - 1, ix + hi));
-          const int ya = max(0, min(a.frame_h - 1, iy + lo)), yb = max(0, min(a.frame_h - 1, iy + hi));
-          staged = (xa >= wx0) && (xb <= wx1) && (ya >= wy0) && (yb <= wy1);
-        }
-        if (staged) {
-          FetchWin f{win, ww, wx0, wy0};
-          J = sample<INTERP>(f, a.frame_h, a.w, xf, yf);
+        if (STAGED && ix0 >= fx_lo && ix0 <= fx_hi && iy0 >= fy_lo && iy0 <= fy_hi) {
+          const float4* p = win + ((iy0 - wy0) * ww + (ix0 - wx0));
+          const float4 wxv = s_wt[fx], wyv = s_wt[fy];
+          if (INTERP == MRF_INTERP_CUBIC) {
+            const float wxa[4] = {wxv.x, wxv.y, wxv.z, wxv.w};
+            const float wya[4] = {wyv.x, wyv.y, wyv.z, wyv.w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              F3 row;
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                const float wgt = wya[j] * wxa[i];
+                const float4 tx = p[j * ww + i];
+                const float px = tx.x * wgt, py = tx.y * wgt, pz = tx.z * wgt;
+                if (i == 0) { row.x = px; row.y = py; row.z = pz; }
+                else        { row.x = row.x + px; row.y = row.y + py; row.z = row.z + pz; }
+              }
+              if (j == 0) J = row;
+              else { J.x = J.x + row.x; J.y = J.y + row.y; J.z = J.z + row.z; }
+            }
+          } else {
+            const float wxa[2] = {wxv.x, wxv.y};
+            const float wya[2] = {wyv.x, wyv.y};
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+#pragma unroll
+              for (int i = 0; i < 2; ++i) {
+                const float wgt = wya[j] * wxa[i];
+                const float4 tx = p[j * ww + i];
+                const float px = tx.x * wgt, py = tx.y * wgt, pz = tx.z * wgt;
+                if (i == 0 && j == 0) { J.x = px; J.y = py; J.z = pz; }
+                else { J.x = J.x + px; J.y = J.y + py; J.z = J.z + pz; }
+              }
+            }
+          }
         } else {
-          // halo check for row-band inputs: taps of an in-frame sample lie in rows iy-1..iy+2
-          int iy, fy; cv_quantise(yf, iy, fy);
+          // footprint touches the image border or leaves the staged window: gather from global
+          // memory; for row-band inputs check the halo (taps of an in-frame sample: rows iy-1..iy+2)
           const int ya = max(0, min(a.frame_h - 1, iy - 1)), yb = max(0, min(a.frame_h - 1, iy + 2));
           if (ya < band_lo || yb > band_hi) {
             if (a.halo_miss) atomicAdd(a.halo_miss, 1);
@@ -280,9 +396,14 @@ k_cost_volume(const __grid_constant__ CVArgs a) {
         const double e0 = ((double)J.x - c0) * a.cw0;       // :274
         const double e1 = ((double)J.y - c1) * a.cw1;
         const double e2 = ((double)J.z - c2) * a.cw2;
-        const double Iz = ((e0 + e1) + e2) / 3.0;
-        cst = (a.rho == MRF_RHO_NONE) ? Iz : rho_eval(a.rho, Iz * Iz, a.rho_param);   // :302
-
+        const double sum = (e0 + e1) + e2;
+        const double Iz = div_rc(sum, 3.0, 1.0 / 3.0);      // .mean(axis=2): sum / 3.0, exact
+        if (lor_fast) {
+          const double z = div_rc(Iz * Iz, s2, rs2);        // x / sigma**2  :52
+          cst = log_ge1(1.0 + z);
+        } else {
+          cst = (a.rho == MRF_RHO_NONE) ? Iz : rho_eval(a.rho, Iz * Iz, a.rho_param);   // :302
+        }
       }
     }
     const float cf = (float)cst;

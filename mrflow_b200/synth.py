@@ -36,9 +36,13 @@ class Texture:
         return np.clip(out, 0.0, 1.0)
 
 
-def _warp_points(A, q, mu, H, b, h, w):
-    """Where each reference pixel lands in the neighbour frame for structure A (fp64 model)."""
-    y, x = np.mgrid[:h, :w].astype(np.float64)
+def _warp_points(A, q, mu, H, b, h, w, x=None, y=None):
+    """Where each reference pixel (or continuous point x, y) lands in the neighbour frame for
+    structure A (fp64 model; ``A`` an array or a callable A(x, y))."""
+    if x is None:
+        y, x = np.mgrid[:h, :w].astype(np.float64)
+    if callable(A):
+        A = A(x, y)
     d = np.sqrt((x - q[0]) ** 2 + (y - q[1]) ** 2)
     n = d / mu
     r = (b * A * n) / (b * A / mu - 1.0)
@@ -51,8 +55,19 @@ def _warp_points(A, q, mu, H, b, h, w):
     return X, Y, x, y
 
 
+def _inverse_warp(A_fn, q, mu, H, b, h, w, iters=6):
+    """Points p of the reference frame with w(p) = p' for every pixel p' of the neighbour grid
+    (fixed-point iteration p <- p' - (w(p) - p); the displacement field is smooth, so it contracts)."""
+    yp, xp = np.mgrid[:h, :w].astype(np.float64)
+    x, y = xp.copy(), yp.copy()
+    for _ in range(iters):
+        X, Y, _, _ = _warp_points(A_fn, q, mu, H, b, h, w, x=x, y=y)
+        x, y = x + (xp - X), y + (yp - Y)
+    return x, y
+
+
 def make_triplet(shape="sintel", seed=1001, epipole="outside", moving_objects=False, flow_noise=0.0,
-                 rigidity_value=0.9, n_waves=32):
+                 rigidity_value=0.9, n_waves=32, B=(-4.0, 4.0)):
     """Return a dict with the inputs of compute_structure / build_cost_volume / combine_flow.
 
     ``shape`` is a key of SHAPES or an (h, w) tuple.  ``epipole`` 'outside' puts the FoE at
@@ -81,11 +96,15 @@ def make_triplet(shape="sintel", seed=1001, epipole="outside", moving_objects=Fa
     q0 = q1 + rs.uniform(-2, 2, 2)
     y, x = np.mgrid[:h, :w].astype(np.float64)
     mu = [np.sqrt((x - q[0]) ** 2 + (y - q[1]) ** 2).mean() for q in (q0, q1)]
-    B = [-0.4, 0.4]
+    B = [float(B[0]), float(B[1])]
 
-    A_true = 1.0 + 0.6 * np.sin(x / 130.0) * np.cos(y / 95.0) + 0.002 * (y - h / 2.0)
-    if moving_objects:
-        A_true = A_true + 0.5 * ((x // 97 + y // 61) % 3 == 0)
+    def A_fn(xx, yy):
+        return 1.0 + 0.6 * np.sin(xx / 130.0) * np.cos(yy / 95.0) + 0.002 * (yy - h / 2.0)
+
+    def A_bwd_fn(xx, yy):
+        return A_fn(xx, yy) * mu[0] / mu[1]
+
+    A_true = A_fn(x, y)
     A_bwd = A_true * mu[0] / mu[1]
 
     X1, Y1, _, _ = _warp_points(A_true, q1, mu[1], H_fwd, B[1], h, w)
@@ -112,14 +131,14 @@ def make_triplet(shape="sintel", seed=1001, epipole="outside", moving_objects=Fa
             fl[0] = fl[0] + rs.normal(0, flow_noise, (h, w))
             fl[1] = fl[1] + rs.normal(0, flow_noise, (h, w))
 
-    # Frames: I1 is the texture itself; the neighbours are built by *forward* reasoning on the
-    # reference grid: I_f(p') = T(p) with p' = w_f(p).  Evaluating T at the inverse warp would
-    # need an inversion; instead define the neighbours as T composed with the approximate
-    # inverse map p' -> p' - flow(p') (first order), which keeps exact texture analyticity and
-    # gives sub-0.05 px brightness-constancy error for these smooth flows.
+    # Frames: I1 is the texture itself; a neighbour frame shows at p' the texture of the reference
+    # point p that the (rigid) model maps there, I_f(w_f(p)) = T(p): exact brightness constancy for
+    # the planted structure, so the data cost has its minimum at the planted label.
     I1 = tex(x, y)
-    I2 = tex(x - flow_f[0], y - flow_f[1])
-    I0 = tex(x - flow_b[0], y - flow_b[1])
+    xi, yi = _inverse_warp(A_fn, q1, mu[1], H_fwd, B[1], h, w)
+    I2 = tex(xi, yi)
+    xi, yi = _inverse_warp(A_bwd_fn, q0, mu[0], H_bwd, B[0], h, w)
+    I0 = tex(xi, yi)
 
     occ = [np.zeros((h, w), bool), np.zeros((h, w), bool)]
     return dict(

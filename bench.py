@@ -28,6 +28,11 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 N_LABELS = 51
+# Label range rule: the orphaned reference stage zeroes the pixels with rigidity > 0 before taking the
+# 1.5x[min, max] range (pipeline/build_cost_volume.py:159), which on an all-rigid triplet collapses
+# the 51 labels to zero parallax; the benchmark uses the rule the code evidently intended (range over
+# the rigid pixels) so that the labels span the scene's real parallax range.
+RANGE_MASK = "rigid_only"
 METRIC = "cost_volume_pixel_labels_per_s"
 UNIT = "pixel*labels/s"
 
@@ -40,7 +45,7 @@ def parse():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--shape", default="sintel", help="sintel | kitti | 4k | HxW")
     ap.add_argument("--interp", default="cubic", choices=["cubic", "linear"])
-    ap.add_argument("--variant", default="staged", choices=["staged", "gather"])
+    ap.add_argument("--variant", default="staged", choices=["staged", "gather", "staged_occ2", "gather_occ2"])
     ap.add_argument("--mode", default="triplets", choices=["triplets", "bands"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -152,7 +157,7 @@ def cpu_front_and_tail(t):
         template = mu_ar[1] / mu_ar[0] * par[0][pv] / (par[0][pv] / mu_ar[0] - dn[0][pv])
         B_ar = [np.median(template / target), 1.0]
     S = [hp.parallax2normedstructure(par[f], q_new[f], B_ar[f], mu_ar[f]) for f in range(2)]
-    labels = hp.structure_range(S, rig, q_new)
+    labels = hp.structure_range(S, rig, q_new, range_mask=RANGE_MASK)
     ch = [hp.prepare_channels(I) for I in t["images"]]
     hp.combine_flow(S[1], t["flow"][1], (rig > 0).astype(np.float64), q_new, mu_ar, t["homographies"], B_ar)
     dt = time.perf_counter() - t0
@@ -237,7 +242,8 @@ def run_ours(args):
 
     def step(events=None):
         out = bcv.cost_volume_pass(band, t["homographies"], t["epipoles"], rigid_mask, stats, rho="lorentzian", sigma=1.0,
-                                   interp=args.interp, variant=args.variant, out=cost_out, events=events)
+                                   interp=args.interp, variant=args.variant, out=cost_out, events=events,
+                                   range_mask=RANGE_MASK)
         cost, S, mu_ar, B_ar, q_new, labels, mins, argmins = out
         u, v = device.structure_to_flow(S[1], q_new[1], mu_ar[1], t["homographies"][1], B_ar[1], nonrigid=nonrigid,
                                         init_u=band.flow[1][0], init_v=band.flow[1][1])
@@ -306,7 +312,7 @@ def run_ours(args):
 
         def e2e_step():
             out = bcv.build_cost_volume(images, flow, rig, t["homographies"], t["epipoles"], None, interp=args.interp,
-                                        variant=args.variant)
+                                        variant=args.variant, range_mask=RANGE_MASK)
             r, u, v = s2f.combine_flow(out[1][1], flow[1], rig, out[4], out[2], t["homographies"], out[3])
             return out, u, v
         n_e2e = max(3, min(steps, 10))
@@ -339,7 +345,7 @@ def run_ours(args):
                 "ms_per_step": total_ms_max / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "f64 geometry / f32 sampling", "data": "synthetic",
                 "config": {"workload": workload_name(args, hw), "labels": N_LABELS, "frames": 2, "interp": args.interp,
-                           "variant": args.variant, "parallelism": "triplets x%d" % world,
+                           "variant": args.variant, "range_mask": RANGE_MASK, "parallelism": "triplets x%d" % world,
                            "l2": "flushed between timed steps (256 MiB fill); outputs 182 MB > L2"},
                 "clocks": clocks.summary(), "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
                 "cpu_baseline": cpu_baseline}

@@ -209,6 +209,8 @@ typedef struct {
  * L1/L2 from global memory.  Results are bit-identical. */
 #define MRF_VARIANT_STAGED 0
 #define MRF_VARIANT_GATHER 1
+#define MRF_VARIANT_OCC2   16 /* OR-able tuning flag: compile for 2 resident blocks / SM (128
+                                 registers per thread) instead of 3 */
 
 /* ref_ch: fp64 [rows,w,3] channels of the reference frame band; nb_texels as described;
  * labels: fp64 [n_labels] structure_range (device); nonrigid/occluded: uint8 [rows,w], !=0

@@ -12,7 +12,7 @@ LIB_PATH = os.path.join(HERE, "libmrflow_b200.so")
 INTERP = {"cubic": 0, "linear": 1}
 RHO = {"lorentzian": 0, "charbonnier": 1, "geman_mcclure": 2, "quadratic": 3, "lorentzian_auto": 4, "none": 5}
 LAYOUT = {"LHW_F32": 0, "HWL_I32": 1}
-VARIANT = {"staged": 0, "gather": 1}
+VARIANT = {"staged": 0, "gather": 1, "staged_occ2": 16, "gather_occ2": 17}
 SELECT_HIST_OFFSET = 64
 
 

@@ -56,6 +56,8 @@ struct CVArgs {
   float* min_cost;
   int32_t* argmin;
   int* halo_miss;
+  double wm1, hm1;          // (double)(w - 1), (double)(frame_h - 1)
+  double s2, rs2;           // rho_param^2 and RN(1 / s2)
 };
 
 // utils/robust_functions.py:26-70, argument already squared
@@ -98,6 +100,10 @@ __device__ __noinline__ F3 sample_band(const float4* nb, int w, int nb_y0, int f
 }
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void lds128(uint32_t addr, float& a, float& b, float& c, float& d) {
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(a), "=f"(b), "=f"(c), "=f"(d) : "r"(addr));
+}
 
 __device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
@@ -146,6 +152,10 @@ __device__ __forceinline__ bool tame(double v) {
 // odd polynomial through s^15; relative error < 2^-43, i.e. the fp32 cost the kernel stores is the
 // correctly rounded one except for about one sample in 2^19 (then off by one fp32 ulp, 6e-8
 // relative, against the 1e-5 bar).  numpy's own log is only specified to < 1 ulp of fp64 either.
+__constant__ double kAtanhC[7] = {1.0 / 3.0, 1.0 / 5.0, 1.0 / 7.0, 1.0 / 9.0, 1.0 / 11.0, 1.0 / 13.0, 1.0 / 15.0};
+__constant__ double kLn2 = 0.6931471805599453094;
+__constant__ double kThird = 1.0 / 3.0;
+
 __device__ __forceinline__ double log_ge1(double u) {
   int hi = __double2hiint(u);
   const int lo = __double2loint(u);
@@ -164,19 +174,19 @@ __device__ __forceinline__ double log_ge1(double u) {
   y = fma(y, t, y);
   const double sv = f * y;
   const double s2 = sv * sv;
-  double pl = fma(s2, 1.0 / 15.0, 1.0 / 13.0);
-  pl = fma(s2, pl, 1.0 / 11.0);
-  pl = fma(s2, pl, 1.0 / 9.0);
-  pl = fma(s2, pl, 1.0 / 7.0);
-  pl = fma(s2, pl, 1.0 / 5.0);
-  pl = fma(s2, pl, 1.0 / 3.0);
+  double pl = fma(s2, kAtanhC[6], kAtanhC[5]);
+  pl = fma(s2, pl, kAtanhC[4]);
+  pl = fma(s2, pl, kAtanhC[3]);
+  pl = fma(s2, pl, kAtanhC[2]);
+  pl = fma(s2, pl, kAtanhC[1]);
+  pl = fma(s2, pl, kAtanhC[0]);
   pl = pl * s2;
   const double two_s = sv + sv;
-  return fma((double)e, 0.6931471805599453094, fma(two_s, pl, two_s));
+  return fma((double)e, kLn2, fma(two_s, pl, two_s));
 }
 
-template <int INTERP, bool STAGED>
-__global__ void __launch_bounds__(kThreads, 3)
+template <int INTERP, bool STAGED, int OCC>
+__global__ void __launch_bounds__(kThreads, OCC)
 k_cost_volume(const __grid_constant__ CVArgs a) {
   extern __shared__ __align__(128) unsigned char dyn_smem[];
   __shared__ double s_ab[kMaxLabels];       // A*B per label
@@ -305,20 +315,23 @@ k_cost_volume(const __grid_constant__ CVArgs a) {
   }
   if (!valid) return;
 
-  const float4* win = reinterpret_cast<const float4*>(dyn_smem);
   // first-tap positions whose whole footprint is inside the staged window AND strictly inside the
   // image (OpenCV's row-sum order): ix0 in [fx_lo, fx_hi], iy0 in [fy_lo, fy_hi]
   constexpr int kTaps = (INTERP == MRF_INTERP_CUBIC) ? 4 : 2;
   constexpr int kOff = (INTERP == MRF_INTERP_CUBIC) ? 1 : 0;
-  const int fx_lo = wx0, fx_hi = min(wx0 + ww, a.w) - kTaps;
-  const int fy_lo = wy0, fy_hi = min(wy0 + wh, a.frame_h) - kTaps;
+  const int fx_lo = wx0, fx_span = min(wx0 + ww, a.w) - kTaps - wx0;     // < 0: nothing staged
+  const int fy_lo = wy0, fy_span = min(wy0 + wh, a.frame_h) - kTaps - wy0;
+  const bool any_fast = STAGED && fx_span >= 0 && fy_span >= 0;
+  const uint32_t win_s = smem_u32(dyn_smem);
+  const uint32_t wt_s = smem_u32(s_wt);
+  const uint32_t pitch = (uint32_t)ww * 16u;
   const int band_lo = a.nb_y0, band_hi = a.nb_y0 + a.nb_rows - 1;
   const double cost_dead = rho_eval(a.rho, 0.0, a.rho_param);
-  const double s2 = a.rho_param * a.rho_param, rs2 = 1.0 / s2;
-  const bool lor_fast = (a.rho == MRF_RHO_LORENTZIAN) && tame(s2);
+  const bool lor_fast = (a.rho == MRF_RHO_LORENTZIAN) && tame(a.s2);
+  const bool unit_cw = (a.cw1 == 1.0) && (a.cw2 == 1.0);
   float best = 0.f; int best_l = 0;
-  float* cost_f = (a.layout == MRF_LAYOUT_LHW_F32) ? (float*)a.cost : nullptr;
-  int32_t* cost_i = (a.layout == MRF_LAYOUT_HWL_I32) ? (int32_t*)a.cost : nullptr;
+  float* cost_f = (a.layout == MRF_LAYOUT_LHW_F32 && a.cost) ? (float*)a.cost + pix : nullptr;
+  int32_t* cost_i = (a.layout == MRF_LAYOUT_HWL_I32 && a.cost) ? (int32_t*)a.cost + (size_t)pix * L : nullptr;
   const size_t plane = (size_t)a.rows * a.w;
 
   for (int l = 0; l < L; ++l) {
@@ -340,51 +353,45 @@ k_cost_volume(const __grid_constant__ CVArgs a) {
       } else {
         X = Xn / den; Y = Yn / den;
       }
-      const bool inside = (X >= 0.0) && (X <= (double)(a.w - 1)) && (Y >= 0.0) && (Y <= (double)(a.frame_h - 1));  // :39
+      const bool inside = (X >= 0.0) && (X <= a.wm1) && (Y >= 0.0) && (Y <= a.hm1);   // :39
       if (inside) {
         const float xf = (float)X, yf = (float)Y;           // interpolation.py:77-78
-        int ix, iy, fx, fy;
-        cv_quantise(xf, ix, fx); cv_quantise(yf, iy, fy);
-        const int ix0 = ix - kOff, iy0 = iy - kOff;
+        // cv2.remap's quantisation; inside the frame |coord*32| < 2^31 and the int16 saturation
+        // cannot trigger for any position the window test below accepts
+        const int sx = __float2int_rn(xf * 32.0f), sy = __float2int_rn(yf * 32.0f);
+        const int ix0 = (sx >> 5) - kOff, iy0 = (sy >> 5) - kOff;
         F3 J;
-        if (STAGED && ix0 >= fx_lo && ix0 <= fx_hi && iy0 >= fy_lo && iy0 <= fy_hi) {
-          const float4* p = win + ((iy0 - wy0) * ww + (ix0 - wx0));
-          const float4 wxv = s_wt[fx], wyv = s_wt[fy];
-          if (INTERP == MRF_INTERP_CUBIC) {
-            const float wxa[4] = {wxv.x, wxv.y, wxv.z, wxv.w};
-            const float wya[4] = {wyv.x, wyv.y, wyv.z, wyv.w};
+        if (any_fast && (unsigned)(ix0 - fx_lo) <= (unsigned)fx_span && (unsigned)(iy0 - fy_lo) <= (unsigned)fy_span) {
+          const uint32_t p0 = win_s + (uint32_t)(iy0 - wy0) * pitch + (uint32_t)(ix0 - wx0) * 16u;
+          float wxa[4], wya[4];
+          lds128(wt_s + (uint32_t)(sx & 31) * 16u, wxa[0], wxa[1], wxa[2], wxa[3]);
+          lds128(wt_s + (uint32_t)(sy & 31) * 16u, wya[0], wya[1], wya[2], wya[3]);
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              F3 row;
+          for (int j = 0; j < kTaps; ++j) {
+            F3 row;
 #pragma unroll
-              for (int i = 0; i < 4; ++i) {
-                const float wgt = wya[j] * wxa[i];
-                const float4 tx = p[j * ww + i];
-                const float px = tx.x * wgt, py = tx.y * wgt, pz = tx.z * wgt;
+            for (int i = 0; i < kTaps; ++i) {
+              const float wgt = wya[j] * wxa[i];
+              float tx, ty, tz, tw;
+              lds128(p0 + (uint32_t)j * pitch + (uint32_t)i * 16u, tx, ty, tz, tw);
+              const float px = tx * wgt, py = ty * wgt, pz = tz * wgt;
+              if (INTERP == MRF_INTERP_CUBIC) {               // row sums, then rows
                 if (i == 0) { row.x = px; row.y = py; row.z = pz; }
                 else        { row.x = row.x + px; row.y = row.y + py; row.z = row.z + pz; }
-              }
-              if (j == 0) J = row;
-              else { J.x = J.x + row.x; J.y = J.y + row.y; J.z = J.z + row.z; }
-            }
-          } else {
-            const float wxa[2] = {wxv.x, wxv.y};
-            const float wya[2] = {wyv.x, wyv.y};
-#pragma unroll
-            for (int j = 0; j < 2; ++j) {
-#pragma unroll
-              for (int i = 0; i < 2; ++i) {
-                const float wgt = wya[j] * wxa[i];
-                const float4 tx = p[j * ww + i];
-                const float px = tx.x * wgt, py = tx.y * wgt, pz = tx.z * wgt;
+              } else {                                        // linear: one running sum
                 if (i == 0 && j == 0) { J.x = px; J.y = py; J.z = pz; }
                 else { J.x = J.x + px; J.y = J.y + py; J.z = J.z + pz; }
               }
+            }
+            if (INTERP == MRF_INTERP_CUBIC) {
+              if (j == 0) J = row;
+              else { J.x = J.x + row.x; J.y = J.y + row.y; J.z = J.z + row.z; }
             }
           }
         } else {
           // footprint touches the image border or leaves the staged window: gather from global
           // memory; for row-band inputs check the halo (taps of an in-frame sample: rows iy-1..iy+2)
+          const int iy = sy >> 5;
           const int ya = max(0, min(a.frame_h - 1, iy - 1)), yb = max(0, min(a.frame_h - 1, iy + 2));
           if (ya < band_lo || yb > band_hi) {
             if (a.halo_miss) atomicAdd(a.halo_miss, 1);
@@ -393,13 +400,14 @@ k_cost_volume(const __grid_constant__ CVArgs a) {
             J = sample_band<INTERP>(a.nb, a.w, a.nb_y0, a.frame_h, xf, yf);
           }
         }
-        const double e0 = ((double)J.x - c0) * a.cw0;       // :274
-        const double e1 = ((double)J.y - c1) * a.cw1;
-        const double e2 = ((double)J.z - c2) * a.cw2;
+        double e0 = ((double)J.x - c0) * a.cw0;              // :274
+        double e1 = (double)J.y - c1;
+        double e2 = (double)J.z - c2;
+        if (!unit_cw) { e1 = e1 * a.cw1; e2 = e2 * a.cw2; } // x * 1.0 == x exactly
         const double sum = (e0 + e1) + e2;
-        const double Iz = div_rc(sum, 3.0, 1.0 / 3.0);      // .mean(axis=2): sum / 3.0, exact
+        const double Iz = div_rc(sum, 3.0, kThird);         // .mean(axis=2): sum / 3.0, exact
         if (lor_fast) {
-          const double z = div_rc(Iz * Iz, s2, rs2);        // x / sigma**2  :52
+          const double z = div_rc(Iz * Iz, a.s2, a.rs2);    // x / sigma**2  :52
           cst = log_ge1(1.0 + z);
         } else {
           cst = (a.rho == MRF_RHO_NONE) ? Iz : rho_eval(a.rho, Iz * Iz, a.rho_param);   // :302
@@ -407,8 +415,8 @@ k_cost_volume(const __grid_constant__ CVArgs a) {
       }
     }
     const float cf = (float)cst;
-    if (cost_f) __stcs(cost_f + (size_t)l * plane + pix, cf);
-    if (cost_i) cost_i[(size_t)pix * L + l] = (int32_t)(cf * a.i32_scale);
+    if (cost_f) { __stcs(cost_f, cf); cost_f += plane; }
+    if (cost_i) cost_i[l] = (int32_t)(cf * a.i32_scale);
     if (l == 0 || cf < best) { best = cf; best_l = l; }     // np.argmin: first minimum
   }
   if (a.min_cost) a.min_cost[pix] = best;
@@ -443,19 +451,25 @@ extern "C" int mrf_cost_volume(const mrf_costvol_params* p, const double* ref_ch
   a.ref_ch = ref_ch; a.nb = (const float4*)nb_texels; a.labels = labels;
   a.nonrigid = nonrigid; a.occluded = occluded;
   a.cost = cost; a.min_cost = min_cost; a.argmin = argmin; a.halo_miss = halo_miss;
+  a.wm1 = (double)(p->w - 1); a.hm1 = (double)(p->frame_h - 1);
+  a.s2 = p->rho_param * p->rho_param; a.rs2 = 1.0 / a.s2;
 
   const dim3 grid(cdiv(p->w, kTX), cdiv(p->rows, kTY));
-  const bool staged = (p->variant != MRF_VARIANT_GATHER);
+  const bool staged = ((p->variant & 1) != MRF_VARIANT_GATHER);
+  const int occ = (p->variant & MRF_VARIANT_OCC2) ? 2 : 3;
   const size_t smem = staged ? (size_t)kWinCap * 16 : 0;
   cudaError_t e = cudaSuccess;
-#define MRF_LAUNCH(I, ST)                                                                             \
-  do {                                                                                                \
-    if (smem) e = cudaFuncSetAttribute(k_cost_volume<I, ST>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
-                                       (int)smem);                                                    \
-    if (e == cudaSuccess) k_cost_volume<I, ST><<<grid, kThreads, smem, S(stream)>>>(a);               \
+#define MRF_LAUNCH(I, ST, OC)                                                                             \
+  do {                                                                                                    \
+    if (smem) e = cudaFuncSetAttribute(k_cost_volume<I, ST, OC>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                       (int)smem);                                                        \
+    if (e == cudaSuccess) k_cost_volume<I, ST, OC><<<grid, kThreads, smem, S(stream)>>>(a);               \
   } while (0)
-  if (p->interp == MRF_INTERP_CUBIC) { if (staged) MRF_LAUNCH(MRF_INTERP_CUBIC, true); else MRF_LAUNCH(MRF_INTERP_CUBIC, false); }
-  else                               { if (staged) MRF_LAUNCH(MRF_INTERP_LINEAR, true); else MRF_LAUNCH(MRF_INTERP_LINEAR, false); }
+#define MRF_LAUNCH_ST(I, OC) do { if (staged) MRF_LAUNCH(I, true, OC); else MRF_LAUNCH(I, false, OC); } while (0)
+#define MRF_LAUNCH_OC(I) do { if (occ == 2) MRF_LAUNCH_ST(I, 2); else MRF_LAUNCH_ST(I, 3); } while (0)
+  if (p->interp == MRF_INTERP_CUBIC) MRF_LAUNCH_OC(MRF_INTERP_CUBIC); else MRF_LAUNCH_OC(MRF_INTERP_LINEAR);
+#undef MRF_LAUNCH_OC
+#undef MRF_LAUNCH_ST
 #undef MRF_LAUNCH
   if (e != cudaSuccess) return fail((int)e, "mrf_cost_volume: %s", cudaGetErrorString(e));
   return check_launch("mrf_cost_volume");

@@ -185,14 +185,68 @@ __device__ __forceinline__ double log_ge1(double u) {
   return fma((double)e, kLn2, fma(two_s, pl, two_s));
 }
 
-template <int INTERP, bool STAGED, int OCC>
+// Reciprocal of a tame double, correctly rounded: hardware seed (MUFU.RCP64H, ~2^-23) and three
+// Newton steps.  The third step applied to an estimate already within an ulp returns RN(1/d) unless
+// d's significand is all ones (Markstein; such a divisor is sent down the plain-division path).
+__device__ __forceinline__ double rcp_rn_tame(double d) {
+  double y;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(d));
+  double e = fma(-d, y, 1.0);
+  y = fma(y, e, y);
+  e = fma(-d, y, 1.0);
+  y = fma(y, e, y);
+  e = fma(-d, y, 1.0);
+  return fma(y, e, y);
+}
+// tame exponent and significand not all ones
+__device__ __forceinline__ bool tame_divisor(double v) {
+  const unsigned hi = (unsigned)__double2hiint(v);
+  const unsigned ex = (hi >> 20) & 0x7ffu;
+  const bool ones = ((hi & 0xfffffu) == 0xfffffu) && ((unsigned)__double2loint(v) == 0xffffffffu);
+  return ((ex - 923u) <= 200u) && !ones;
+}
+
+// One sample evaluated with plain IEEE divisions and the library log -- the arithmetic of the
+// reference written naively.  Cold path: taken only for samples whose operands leave the range in
+// which the reciprocal sequences are proven exact (labels at the pole of the parallax formula,
+// degenerate homographies), a handful per frame at most.
+template <int INTERP>
+__device__ __noinline__ float slow_sample_cost(const CVArgs& a, double ab, double dl, double n, double xd, double yd,
+                                               double t1, double t2, double c0, double c1, double c2) {
+  const double r = (ab * n) / dl;
+  const double xn = xd + r * t1, yn = yd + r * t2;
+  double X, Y; bool inside;
+  through_H(a.H, xn, yn, a.frame_h, a.w, X, Y, inside);
+  double cst = rho_eval(a.rho, 0.0, a.rho_param);
+  if (inside) {
+    const float xf = (float)X, yf = (float)Y;
+    int iy, fy; cv_quantise(yf, iy, fy);
+    const int lo = (INTERP == MRF_INTERP_CUBIC) ? -1 : 0, hi = (INTERP == MRF_INTERP_CUBIC) ? 2 : 1;
+    const int ya = max(0, min(a.frame_h - 1, iy + lo)), yb = max(0, min(a.frame_h - 1, iy + hi));
+    F3 J;
+    if (ya < a.nb_y0 || yb > a.nb_y0 + a.nb_rows - 1) {
+      if (a.halo_miss) atomicAdd(a.halo_miss, 1);
+      J.x = J.y = J.z = 0.f;
+    } else {
+      FetchBand f{a.nb, a.w, a.nb_y0};
+      J = sample<INTERP>(f, a.frame_h, a.w, xf, yf);
+    }
+    const double e0 = ((double)J.x - c0) * a.cw0;
+    const double e1 = ((double)J.y - c1) * a.cw1;
+    const double e2 = ((double)J.z - c2) * a.cw2;
+    const double Iz = ((e0 + e1) + e2) / 3.0;
+    cst = (a.rho == MRF_RHO_NONE) ? Iz : rho_eval(a.rho, Iz * Iz, a.rho_param);
+  }
+  return (float)cst;
+}
+
+struct __align__(16) LabelRec { double ab, den, rden, safe; };   // safe: 1.0 / 0.0
+
+template <int INTERP, bool STAGED, int OCC, int LAYOUT>
 __global__ void __launch_bounds__(kThreads, OCC)
 k_cost_volume(const __grid_constant__ CVArgs a) {
   extern __shared__ __align__(128) unsigned char dyn_smem[];
-  __shared__ double s_ab[kMaxLabels];       // A*B per label
-  __shared__ double s_den[kMaxLabels];      // B*A/mu - 1
-  __shared__ double s_rden[kMaxLabels];     // RN(1 / s_den)
-  __shared__ unsigned char s_safe[kMaxLabels];
+  __shared__ LabelRec s_lab[kMaxLabels];    // A*B, B*A/mu - 1, RN(1/that), exact-sequence-safe flag
   __shared__ __align__(16) float4 s_wt[32]; // OpenCV's interpolation table: weights at frac/32
   __shared__ double s_c[2];                 // min / max over labels of A*B / (B*A/mu - 1)
   __shared__ float s_red[kTY][4];
@@ -211,10 +265,10 @@ k_cost_volume(const __grid_constant__ CVArgs a) {
     const double al = a.labels[l] * a.label_scale;
     const double ab = al * a.B;
     const double den = ab / a.mu - 1.0;
-    s_ab[l] = ab;
-    s_den[l] = den;
-    s_rden[l] = 1.0 / den;
-    s_safe[l] = (tame(den) && (ab == 0.0 || tame(ab))) ? 1 : 0;
+    LabelRec rec;
+    rec.ab = ab; rec.den = den; rec.rden = 1.0 / den;
+    rec.safe = (tame(den) && (ab == 0.0 || tame(ab))) ? 1.0 : 0.0;
+    s_lab[l] = rec;
   }
   if (threadIdx.x >= 32 && threadIdx.x < 64) {
     const int fr = threadIdx.x - 32;
@@ -227,7 +281,7 @@ k_cost_volume(const __grid_constant__ CVArgs a) {
   if (STAGED && wrp == 0) {
     double cmin = 1.0e300, cmax = -1.0e300;
     for (int l = lane; l < L; l += 32) {
-      const double c = s_ab[l] / s_den[l];
+      const double c = s_lab[l].ab / s_lab[l].den;
       cmin = fmin(cmin, c); cmax = fmax(cmax, c);
     }
 #pragma unroll
@@ -245,7 +299,6 @@ k_cost_volume(const __grid_constant__ CVArgs a) {
   const double nrm = fmax(0.5, dist);
   const double t1 = vx / nrm, t2 = vy / nrm;
   const double n = dist / a.mu;
-  const bool n_tame = (n == 0.0) || tame(n);
 
   const long long pix = (long long)yl * a.w + x;
   bool dead = !valid;
@@ -316,53 +369,60 @@ k_cost_volume(const __grid_constant__ CVArgs a) {
   if (!valid) return;
 
   // first-tap positions whose whole footprint is inside the staged window AND strictly inside the
-  // image (OpenCV's row-sum order): ix0 in [fx_lo, fx_hi], iy0 in [fy_lo, fy_hi]
+  // image (OpenCV's row-sum order): ix0 in [fx_lo, fx_lo + fx_span], iy0 likewise
   constexpr int kTaps = (INTERP == MRF_INTERP_CUBIC) ? 4 : 2;
   constexpr int kOff = (INTERP == MRF_INTERP_CUBIC) ? 1 : 0;
-  const int fx_lo = wx0, fx_span = min(wx0 + ww, a.w) - kTaps - wx0;     // < 0: nothing staged
-  const int fy_lo = wy0, fy_span = min(wy0 + wh, a.frame_h) - kTaps - wy0;
-  const bool any_fast = STAGED && fx_span >= 0 && fy_span >= 0;
-  const uint32_t win_s = smem_u32(dyn_smem);
-  const uint32_t wt_s = smem_u32(s_wt);
+  int fx_lo = wx0, fy_lo = wy0;
+  int fx_span = min(wx0 + ww, a.w) - kTaps - wx0;            // < 0: nothing staged
+  int fy_span = min(wy0 + wh, a.frame_h) - kTaps - wy0;
+  if (!STAGED || fx_span < 0 || fy_span < 0) { fx_lo = 0x7fff0000; fx_span = 0; fy_span = 0; }   // never matches
+  uint32_t win_s = smem_u32(dyn_smem) - (uint32_t)(wy0 * ww + wx0) * 16u;   // address of texel (0, 0)
+  uint32_t wt_s = smem_u32(s_wt);
+  uint32_t lab_s = smem_u32(s_lab);
   const uint32_t pitch = (uint32_t)ww * 16u;
-  const int band_lo = a.nb_y0, band_hi = a.nb_y0 + a.nb_rows - 1;
-  const double cost_dead = rho_eval(a.rho, 0.0, a.rho_param);
+  // keep the shared-window addresses in registers (the compiler would otherwise rebuild them from
+  // the CTA id on every iteration)
+  asm volatile("" : "+r"(win_s), "+r"(wt_s), "+r"(lab_s));
+  const float cost_dead = (float)rho_eval(a.rho, 0.0, a.rho_param);
   const bool lor_fast = (a.rho == MRF_RHO_LORENTZIAN) && tame(a.s2);
-  const bool unit_cw = (a.cw1 == 1.0) && (a.cw2 == 1.0);
+  const double n_ok = ((n == 0.0) || tame(n)) ? 1.0 : 0.0;
   float best = 0.f; int best_l = 0;
-  float* cost_f = (a.layout == MRF_LAYOUT_LHW_F32 && a.cost) ? (float*)a.cost + pix : nullptr;
-  int32_t* cost_i = (a.layout == MRF_LAYOUT_HWL_I32 && a.cost) ? (int32_t*)a.cost + (size_t)pix * L : nullptr;
-  const size_t plane = (size_t)a.rows * a.w;
+  char* cost_p = nullptr;                                   // this pixel's first cost element
+  if (a.cost) cost_p = (LAYOUT == MRF_LAYOUT_LHW_F32) ? (char*)((float*)a.cost + pix)
+                                                      : (char*)((int32_t*)a.cost + (size_t)pix * L);
+  const uint32_t cost_step = (LAYOUT == MRF_LAYOUT_LHW_F32) ? (uint32_t)((size_t)a.rows * a.w * 4) : 4u;
+  uint32_t cost_off = 0;                                    // host side guarantees L * step < 4 GiB
 
-  for (int l = 0; l < L; ++l) {
-    double cst = cost_dead;
+  for (int l = 0; l < L; ++l, cost_off += cost_step) {
+    float cf = cost_dead;
     if (!dead) {
+      double ab, dl, rdl, safe;
+      asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(ab), "=d"(dl) : "r"(lab_s + (uint32_t)l * 32u));
+      asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(rdl), "=d"(safe) : "r"(lab_s + (uint32_t)l * 32u + 16u));
       // r = A*B*n / (B*A/mu - 1)  :221
-      const double num = s_ab[l] * n;
-      const double r = (s_safe[l] && n_tame) ? div_rc(num, s_den[l], s_rden[l]) : num / s_den[l];
+      const double r = div_rc(ab * n, dl, rdl);
       const double xn = xd + r * t1, yn = yd + r * t2;      // :224-235
       // interpolate_through_H.py:31-35
       const double den = (xn * a.H.m[6] + yn * a.H.m[7]) + a.H.m[8];
       const double Xn = (xn * a.H.m[0] + yn * a.H.m[1]) + a.H.m[2];
       const double Yn = (xn * a.H.m[3] + yn * a.H.m[4]) + a.H.m[5];
-      double X, Y;
-      if (tame(den)) {
-        const double rd = __drcp_rn(den);
-        X = div_rc(Xn, den, rd);
-        Y = div_rc(Yn, den, rd);
-      } else {
-        X = Xn / den; Y = Yn / den;
-      }
+      const double rd = rcp_rn_tame(den);
+      const double X = div_rc(Xn, den, rd);
+      const double Y = div_rc(Yn, den, rd);
+      // every condition under which the sequences above are not proven exact
+      const bool exact = (safe * n_ok != 0.0) && tame_divisor(den);
       const bool inside = (X >= 0.0) && (X <= a.wm1) && (Y >= 0.0) && (Y <= a.hm1);   // :39
-      if (inside) {
+      if (!exact) {
+        cf = slow_sample_cost<INTERP>(a, ab, dl, n, xd, yd, t1, t2, c0, c1, c2);
+      } else if (inside) {
         const float xf = (float)X, yf = (float)Y;           // interpolation.py:77-78
         // cv2.remap's quantisation; inside the frame |coord*32| < 2^31 and the int16 saturation
         // cannot trigger for any position the window test below accepts
         const int sx = __float2int_rn(xf * 32.0f), sy = __float2int_rn(yf * 32.0f);
         const int ix0 = (sx >> 5) - kOff, iy0 = (sy >> 5) - kOff;
         F3 J;
-        if (any_fast && (unsigned)(ix0 - fx_lo) <= (unsigned)fx_span && (unsigned)(iy0 - fy_lo) <= (unsigned)fy_span) {
-          const uint32_t p0 = win_s + (uint32_t)(iy0 - wy0) * pitch + (uint32_t)(ix0 - wx0) * 16u;
+        if ((unsigned)(ix0 - fx_lo) <= (unsigned)fx_span && (unsigned)(iy0 - fy_lo) <= (unsigned)fy_span) {
+          const uint32_t p0 = win_s + (uint32_t)iy0 * pitch + (uint32_t)ix0 * 16u;
           float wxa[4], wya[4];
           lds128(wt_s + (uint32_t)(sx & 31) * 16u, wxa[0], wxa[1], wxa[2], wxa[3]);
           lds128(wt_s + (uint32_t)(sy & 31) * 16u, wya[0], wya[1], wya[2], wya[3]);
@@ -388,35 +448,28 @@ k_cost_volume(const __grid_constant__ CVArgs a) {
               else { J.x = J.x + row.x; J.y = J.y + row.y; J.z = J.z + row.z; }
             }
           }
-        } else {
-          // footprint touches the image border or leaves the staged window: gather from global
-          // memory; for row-band inputs check the halo (taps of an in-frame sample: rows iy-1..iy+2)
-          const int iy = sy >> 5;
-          const int ya = max(0, min(a.frame_h - 1, iy - 1)), yb = max(0, min(a.frame_h - 1, iy + 2));
-          if (ya < band_lo || yb > band_hi) {
-            if (a.halo_miss) atomicAdd(a.halo_miss, 1);
-            J.x = J.y = J.z = 0.f;
+          const double e0 = ((double)J.x - c0) * a.cw0;     // :274
+          const double e1 = ((double)J.y - c1) * a.cw1;
+          const double e2 = ((double)J.z - c2) * a.cw2;
+          const double Iz = div_rc((e0 + e1) + e2, 3.0, kThird);   // .mean(axis=2): sum / 3.0, exact
+          double cst;
+          if (lor_fast) {
+            const double z = div_rc(Iz * Iz, a.s2, a.rs2);  // x / sigma**2  :52
+            cst = log_ge1(1.0 + z);
           } else {
-            J = sample_band<INTERP>(a.nb, a.w, a.nb_y0, a.frame_h, xf, yf);
+            cst = (a.rho == MRF_RHO_NONE) ? Iz : rho_eval(a.rho, Iz * Iz, a.rho_param);   // :302
           }
-        }
-        double e0 = ((double)J.x - c0) * a.cw0;              // :274
-        double e1 = (double)J.y - c1;
-        double e2 = (double)J.z - c2;
-        if (!unit_cw) { e1 = e1 * a.cw1; e2 = e2 * a.cw2; } // x * 1.0 == x exactly
-        const double sum = (e0 + e1) + e2;
-        const double Iz = div_rc(sum, 3.0, kThird);         // .mean(axis=2): sum / 3.0, exact
-        if (lor_fast) {
-          const double z = div_rc(Iz * Iz, a.s2, a.rs2);    // x / sigma**2  :52
-          cst = log_ge1(1.0 + z);
+          cf = (float)cst;
         } else {
-          cst = (a.rho == MRF_RHO_NONE) ? Iz : rho_eval(a.rho, Iz * Iz, a.rho_param);   // :302
+          // footprint touches the image border or leaves the staged window: global-memory gather
+          cf = slow_sample_cost<INTERP>(a, ab, dl, n, xd, yd, t1, t2, c0, c1, c2);
         }
       }
     }
-    const float cf = (float)cst;
-    if (cost_f) { __stcs(cost_f, cf); cost_f += plane; }
-    if (cost_i) cost_i[l] = (int32_t)(cf * a.i32_scale);
+    if (cost_p) {
+      if (LAYOUT == MRF_LAYOUT_LHW_F32) __stcs((float*)(cost_p + cost_off), cf);
+      else *(int32_t*)(cost_p + cost_off) = (int32_t)(cf * a.i32_scale);
+    }
     if (l == 0 || cf < best) { best = cf; best_l = l; }     // np.argmin: first minimum
   }
   if (a.min_cost) a.min_cost[pix] = best;
@@ -440,6 +493,7 @@ extern "C" int mrf_cost_volume(const mrf_costvol_params* p, const double* ref_ch
   MRF_CHECK_ARG(p->layout == MRF_LAYOUT_LHW_F32 || p->layout == MRF_LAYOUT_HWL_I32);
   MRF_CHECK_ARG(cost || min_cost || argmin);
   MRF_CHECK_ARG(((uintptr_t)nb_texels & 15) == 0);
+  MRF_CHECK_ARG((double)p->rows * p->w * 4.0 * p->n_labels < 4294967296.0);   /* 32-bit store offsets */
   CVArgs a;
   a.rows = p->rows; a.w = p->w; a.y0 = p->y0; a.frame_h = p->frame_h;
   a.nb_rows = p->nb_rows; a.nb_y0 = p->nb_y0;
@@ -459,15 +513,17 @@ extern "C" int mrf_cost_volume(const mrf_costvol_params* p, const double* ref_ch
   const int occ = (p->variant & MRF_VARIANT_OCC2) ? 2 : 3;
   const size_t smem = staged ? (size_t)kWinCap * 16 : 0;
   cudaError_t e = cudaSuccess;
-#define MRF_LAUNCH(I, ST, OC)                                                                             \
+#define MRF_LAUNCH(I, ST, OC, LY)                                                                         \
   do {                                                                                                    \
-    if (smem) e = cudaFuncSetAttribute(k_cost_volume<I, ST, OC>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+    if (smem) e = cudaFuncSetAttribute(k_cost_volume<I, ST, OC, LY>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
                                        (int)smem);                                                        \
-    if (e == cudaSuccess) k_cost_volume<I, ST, OC><<<grid, kThreads, smem, S(stream)>>>(a);               \
+    if (e == cudaSuccess) k_cost_volume<I, ST, OC, LY><<<grid, kThreads, smem, S(stream)>>>(a);           \
   } while (0)
-#define MRF_LAUNCH_ST(I, OC) do { if (staged) MRF_LAUNCH(I, true, OC); else MRF_LAUNCH(I, false, OC); } while (0)
+#define MRF_LAUNCH_LY(I, ST, OC) do { if (p->layout == MRF_LAYOUT_LHW_F32) MRF_LAUNCH(I, ST, OC, MRF_LAYOUT_LHW_F32); else MRF_LAUNCH(I, ST, OC, MRF_LAYOUT_HWL_I32); } while (0)
+#define MRF_LAUNCH_ST(I, OC) do { if (staged) MRF_LAUNCH_LY(I, true, OC); else MRF_LAUNCH_LY(I, false, OC); } while (0)
 #define MRF_LAUNCH_OC(I) do { if (occ == 2) MRF_LAUNCH_ST(I, 2); else MRF_LAUNCH_ST(I, 3); } while (0)
   if (p->interp == MRF_INTERP_CUBIC) MRF_LAUNCH_OC(MRF_INTERP_CUBIC); else MRF_LAUNCH_OC(MRF_INTERP_LINEAR);
+#undef MRF_LAUNCH_LY
 #undef MRF_LAUNCH_OC
 #undef MRF_LAUNCH_ST
 #undef MRF_LAUNCH

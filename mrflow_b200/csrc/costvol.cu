@@ -448,22 +448,30 @@ k_cost_volume(const __grid_constant__ CVArgs a) {
               else { J.x = J.x + row.x; J.y = J.y + row.y; J.z = J.z + row.z; }
             }
           }
-          const double e0 = ((double)J.x - c0) * a.cw0;     // :274
-          const double e1 = ((double)J.y - c1) * a.cw1;
-          const double e2 = ((double)J.z - c2) * a.cw2;
-          const double Iz = div_rc((e0 + e1) + e2, 3.0, kThird);   // .mean(axis=2): sum / 3.0, exact
-          double cst;
-          if (lor_fast) {
-            const double z = div_rc(Iz * Iz, a.s2, a.rs2);  // x / sigma**2  :52
-            cst = log_ge1(1.0 + z);
-          } else {
-            cst = (a.rho == MRF_RHO_NONE) ? Iz : rho_eval(a.rho, Iz * Iz, a.rho_param);   // :302
-          }
-          cf = (float)cst;
         } else {
-          // footprint touches the image border or leaves the staged window: global-memory gather
-          cf = slow_sample_cost<INTERP>(a, ab, dl, n, xd, yd, t1, t2, c0, c1, c2);
+          // footprint touches the image border or leaves the staged window: gather from global
+          // memory; for row-band inputs check the halo (taps of an in-frame sample: rows iy-1..iy+2)
+          const int iy = sy >> 5;
+          const int ya = max(0, min(a.frame_h - 1, iy - 1)), yb = max(0, min(a.frame_h - 1, iy + 2));
+          if (ya < a.nb_y0 || yb > a.nb_y0 + a.nb_rows - 1) {
+            if (a.halo_miss) atomicAdd(a.halo_miss, 1);
+            J.x = J.y = J.z = 0.f;
+          } else {
+            J = sample_band<INTERP>(a.nb, a.w, a.nb_y0, a.frame_h, xf, yf);
+          }
         }
+        const double e0 = ((double)J.x - c0) * a.cw0;       // :274
+        const double e1 = ((double)J.y - c1) * a.cw1;
+        const double e2 = ((double)J.z - c2) * a.cw2;
+        const double Iz = div_rc((e0 + e1) + e2, 3.0, kThird);   // .mean(axis=2): sum / 3.0, exact
+        double cst;
+        if (lor_fast) {
+          const double z = div_rc(Iz * Iz, a.s2, a.rs2);    // x / sigma**2  :52
+          cst = log_ge1(1.0 + z);
+        } else {
+          cst = (a.rho == MRF_RHO_NONE) ? Iz : rho_eval(a.rho, Iz * Iz, a.rho_param);   // :302
+        }
+        cf = (float)cst;
       }
     }
     if (cost_p) {

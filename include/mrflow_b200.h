@@ -147,6 +147,15 @@ int mrf_select_kth_f64(const double* keys, size_t n, size_t k, double* out3,
  * order-key above kth) of the state at scratch; result. */
 #define MRF_SELECT_HIST_OFFSET 64
 int mrf_select_begin(size_t k, void* scratch, mrf_stream_t stream);
+/* host-driven form of the same steps (prefix / k-th key passed by value, results in caller buffers):
+ * hist256 = 256 uint64 counts (zeroed by the call) of byte `pass` (0 = most significant) among the
+ * keys whose higher bytes equal `prefix`; out3 = { #keys <= kth, #NaN, min order-key > kth }.  Order
+ * keys: the IEEE bits with the sign flipped for positives and all bits flipped for negatives;
+ * every NaN = 0xFFFF...F. */
+int mrf_select_hist_prefix_f64(const double* keys, size_t n, unsigned long long prefix, int pass,
+                               unsigned long long* hist256, mrf_stream_t stream);
+int mrf_select_successor_key_f64(const double* keys, size_t n, unsigned long long kth_key,
+                                 unsigned long long* out3, mrf_stream_t stream);
 int mrf_select_hist_f64(const double* keys, size_t n, void* scratch, mrf_stream_t stream);
 int mrf_select_pick(void* scratch, mrf_stream_t stream);
 int mrf_select_successor_f64(const double* keys, size_t n, void* scratch, mrf_stream_t stream);
@@ -202,6 +211,11 @@ typedef struct {
   int    layout;        /* MRF_LAYOUT_* */
   double i32_scale;     /* for MRF_LAYOUT_HWL_I32 */
   int    variant;       /* MRF_VARIANT_* */
+  long long cost_plane_stride; /* LHW layout: elements between consecutive label planes of `cost`;
+                                  0 = rows*w.  With frame_h*w and cost = volume + y0*w a band writes
+                                  its rows straight into a whole-frame [L][frame_h][w] volume -- which
+                                  may live on another GPU (peer-mapped memory, mrf_peer_*): the gather
+                                  to the TRW-S rank is then done by the kernel's own stores over NVLink. */
 } mrf_costvol_params;
 
 /* kernel variants: STAGED copies the tile's footprint window of the neighbour frame into shared
@@ -233,6 +247,15 @@ int mrf_robust_apply_f64(const double* x, size_t n, int kind, int deriv, double 
 
 /* ---- pipeline/compute_structure.py:44: cv2.erode(uint8, ones((3,3))) (default border). */
 int mrf_erode3x3_u8(const uint8_t* src, int h, int w, uint8_t* dst, mrf_stream_t stream);
+
+/* ---- peer memory for the row-band gather: a buffer allocated on the
+ * TRW-S rank's GPU is exported as a 64-byte CUDA IPC handle, opened by the other ranks (one process
+ * per GPU), and written by their cost-volume kernels directly over NVLink.  These are the only
+ * calls that allocate; they are not stream-ordered. */
+int mrf_peer_alloc(size_t bytes, void** ptr_out, unsigned char* handle64_out);
+int mrf_peer_open(const unsigned char* handle64, void** ptr_out);
+int mrf_peer_close(void* ptr);
+int mrf_peer_free(void* ptr);
 
 /* number of kernel launches the library has issued in this process (for bench.py's
  * gpu_launches); reset with mrf_reset_launch_count(). */

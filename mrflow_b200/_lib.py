@@ -24,7 +24,8 @@ class CostVolParams(C.Structure):
                 ("mu", C.c_double), ("B", C.c_double), ("label_scale", C.c_double),
                 ("n_labels", C.c_int), ("interp", C.c_int), ("rho", C.c_int),
                 ("rho_param", C.c_double), ("cw", C.c_double * 3),
-                ("layout", C.c_int), ("i32_scale", C.c_double), ("variant", C.c_int)]
+                ("layout", C.c_int), ("i32_scale", C.c_double), ("variant", C.c_int),
+                ("cost_plane_stride", C.c_longlong)]
 
 
 _P, _I, _D, _Z = C.c_void_p, C.c_int, C.c_double, C.c_size_t
@@ -54,6 +55,12 @@ SIGNATURES = {
     "mrf_select_pick": (_I, [_P, _P]),
     "mrf_select_successor_f64": (_I, [_P, _Z, _P, _P]),
     "mrf_select_result": (_I, [_Z, _P, _P, _P]),
+    "mrf_select_hist_prefix_f64": (_I, [_P, _Z, C.c_ulonglong, _I, _P, _P]),
+    "mrf_select_successor_key_f64": (_I, [_P, _Z, C.c_ulonglong, _P, _P]),
+    "mrf_peer_alloc": (_I, [_Z, C.POINTER(C.c_void_p), C.POINTER(C.c_ubyte)]),
+    "mrf_peer_open": (_I, [C.POINTER(C.c_ubyte), C.POINTER(C.c_void_p)]),
+    "mrf_peer_close": (_I, [_P]),
+    "mrf_peer_free": (_I, [_P]),
     "mrf_abs_deviation_f64": (_I, [_P, _Z, _D, _P, _P]),
     "mrf_minmax_scratch_bytes": (_Z, []),
     "mrf_masked_minmax_f64": (_I, [_P, _P, _I, _I, _I, _IP, _P, _P, _P]),

@@ -56,6 +56,7 @@ struct CVArgs {
   float* min_cost;
   int32_t* argmin;
   int* halo_miss;
+  long long plane_stride;   // elements between label planes of the LHW volume
   double wm1, hm1;          // (double)(w - 1), (double)(frame_h - 1)
   double s2, rs2;           // rho_param^2 and RN(1 / s2)
 };
@@ -390,7 +391,7 @@ k_cost_volume(const __grid_constant__ CVArgs a) {
   char* cost_p = nullptr;                                   // this pixel's first cost element
   if (a.cost) cost_p = (LAYOUT == MRF_LAYOUT_LHW_F32) ? (char*)((float*)a.cost + pix)
                                                       : (char*)((int32_t*)a.cost + (size_t)pix * L);
-  const uint32_t cost_step = (LAYOUT == MRF_LAYOUT_LHW_F32) ? (uint32_t)((size_t)a.rows * a.w * 4) : 4u;
+  const uint32_t cost_step = (LAYOUT == MRF_LAYOUT_LHW_F32) ? (uint32_t)(a.plane_stride * 4) : 4u;
   uint32_t cost_off = 0;                                    // host side guarantees L * step < 4 GiB
 
   for (int l = 0; l < L; ++l, cost_off += cost_step) {
@@ -501,7 +502,9 @@ extern "C" int mrf_cost_volume(const mrf_costvol_params* p, const double* ref_ch
   MRF_CHECK_ARG(p->layout == MRF_LAYOUT_LHW_F32 || p->layout == MRF_LAYOUT_HWL_I32);
   MRF_CHECK_ARG(cost || min_cost || argmin);
   MRF_CHECK_ARG(((uintptr_t)nb_texels & 15) == 0);
-  MRF_CHECK_ARG((double)p->rows * p->w * 4.0 * p->n_labels < 4294967296.0);   /* 32-bit store offsets */
+  const long long plane_stride = p->cost_plane_stride > 0 ? p->cost_plane_stride : (long long)p->rows * p->w;
+  MRF_CHECK_ARG(plane_stride >= (long long)p->rows * p->w);
+  MRF_CHECK_ARG((double)plane_stride * 4.0 * p->n_labels < 4294967296.0);   /* 32-bit store offsets */
   CVArgs a;
   a.rows = p->rows; a.w = p->w; a.y0 = p->y0; a.frame_h = p->frame_h;
   a.nb_rows = p->nb_rows; a.nb_y0 = p->nb_y0;
@@ -513,6 +516,7 @@ extern "C" int mrf_cost_volume(const mrf_costvol_params* p, const double* ref_ch
   a.ref_ch = ref_ch; a.nb = (const float4*)nb_texels; a.labels = labels;
   a.nonrigid = nonrigid; a.occluded = occluded;
   a.cost = cost; a.min_cost = min_cost; a.argmin = argmin; a.halo_miss = halo_miss;
+  a.plane_stride = plane_stride;
   a.wm1 = (double)(p->w - 1); a.hm1 = (double)(p->frame_h - 1);
   a.s2 = p->rho_param * p->rho_param; a.rs2 = 1.0 / a.s2;
 

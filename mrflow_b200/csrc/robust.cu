@@ -4,6 +4,7 @@
 // erosion of the thresholded rigidity at pipeline/compute_structure.py:44.  Streaming, HBM-bound.
 #include "common.cuh"
 #include <math.h>
+#include <string.h>
 
 namespace mrf {
 
@@ -74,6 +75,45 @@ int mrf_robust_apply_f64(const double* x, size_t n, int kind, int deriv, double 
   if (b > kSMs * 16) b = kSMs * 16;
   k_robust_apply<<<(unsigned)b, 256, 0, S(stream)>>>(x, n, kind, deriv, p1, p2, out);
   return check_launch("mrf_robust_apply_f64");
+}
+
+int mrf_peer_alloc(size_t bytes, void** ptr_out, unsigned char* handle64_out) {
+  MRF_CHECK_ARG(bytes > 0 && ptr_out && handle64_out);
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+  void* p = nullptr;
+  cudaError_t e = cudaMalloc(&p, bytes);
+  if (e != cudaSuccess) return fail((int)e, "mrf_peer_alloc: %s", cudaGetErrorString(e));
+  cudaIpcMemHandle_t h;
+  e = cudaIpcGetMemHandle(&h, p);
+  if (e != cudaSuccess) { cudaFree(p); return fail((int)e, "mrf_peer_alloc/handle: %s", cudaGetErrorString(e)); }
+  memcpy(handle64_out, &h, 64);
+  *ptr_out = p;
+  return 0;
+}
+
+int mrf_peer_open(const unsigned char* handle64, void** ptr_out) {
+  MRF_CHECK_ARG(handle64 && ptr_out);
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle64, 64);
+  void* p = nullptr;
+  cudaError_t e = cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess);
+  if (e != cudaSuccess) return fail((int)e, "mrf_peer_open: %s", cudaGetErrorString(e));
+  *ptr_out = p;
+  return 0;
+}
+
+int mrf_peer_close(void* ptr) {
+  MRF_CHECK_ARG(ptr);
+  cudaError_t e = cudaIpcCloseMemHandle(ptr);
+  if (e != cudaSuccess) return fail((int)e, "mrf_peer_close: %s", cudaGetErrorString(e));
+  return 0;
+}
+
+int mrf_peer_free(void* ptr) {
+  MRF_CHECK_ARG(ptr);
+  cudaError_t e = cudaFree(ptr);
+  if (e != cudaSuccess) return fail((int)e, "mrf_peer_free: %s", cudaGetErrorString(e));
+  return 0;
 }
 
 int mrf_erode3x3_u8(const uint8_t* src, int h, int w, uint8_t* dst, mrf_stream_t stream) {

@@ -59,6 +59,48 @@ k_select_hist(const double* __restrict__ keys, size_t n, const unsigned long lon
   if (c) atomicAdd(&hist[threadIdx.x], (unsigned long long)c);
 }
 
+// same histogram with the prefix passed by value (host-driven multi-GPU selection)
+__global__ void __launch_bounds__(256)
+k_select_hist_prefix(const double* __restrict__ keys, size_t n, unsigned long long prefix, int pass,
+                     unsigned long long* __restrict__ hist) {
+  __shared__ unsigned int sh[kHistBins];
+  sh[threadIdx.x] = 0;
+  __syncthreads();
+  const int shift = 56 - 8 * pass;
+  const unsigned long long himask = pass == 0 ? 0ull : (~0ull << (shift + 8));
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const unsigned long long k = order_key(keys[i]);
+    if ((k & himask) == prefix) atomicAdd(&sh[(k >> shift) & 0xFF], 1u);
+  }
+  __syncthreads();
+  const unsigned int c = sh[threadIdx.x];
+  if (c) atomicAdd(&hist[threadIdx.x], (unsigned long long)c);
+}
+
+// count(keys <= kth), #NaN, min order-key above kth for a kth key given by value -> out[3] (uint64)
+__global__ void __launch_bounds__(256)
+k_select_successor_key(const double* __restrict__ keys, size_t n, unsigned long long kth,
+                       unsigned long long* __restrict__ out) {
+  unsigned long long cnt_le = 0, nan = 0, min_gt = 0xFFFFFFFFFFFFFFFFull;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const double v = keys[i];
+    const unsigned long long k = order_key(v);
+    if (v != v) ++nan;
+    if (k <= kth) ++cnt_le; else if (k < min_gt) min_gt = k;
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    cnt_le += __shfl_down_sync(0xffffffffu, cnt_le, o);
+    nan += __shfl_down_sync(0xffffffffu, nan, o);
+    const unsigned long long m = __shfl_down_sync(0xffffffffu, min_gt, o);
+    min_gt = m < min_gt ? m : min_gt;
+  }
+  if ((threadIdx.x & 31) == 0) {
+    if (cnt_le) atomicAdd(&out[0], cnt_le);
+    if (nan) atomicAdd(&out[1], nan);
+    if (min_gt != 0xFFFFFFFFFFFFFFFFull) atomicMin(&out[2], min_gt);
+  }
+}
+
 // pick the byte holding the k-th key; clears the histogram for the next pass
 __global__ void __launch_bounds__(32)
 k_select_pick(unsigned long long* st, unsigned long long* hist) {
@@ -233,6 +275,29 @@ int mrf_select_kth_f64(const double* keys, size_t n, size_t k, double* out3, voi
   if (!rc) rc = mrf_select_successor_f64(keys, n, scratch, stream);
   if (!rc) rc = mrf_select_result(k, scratch, out3, stream);
   return rc;
+}
+
+int mrf_select_hist_prefix_f64(const double* keys, size_t n, unsigned long long prefix, int pass,
+                                unsigned long long* hist256, mrf_stream_t stream) {
+  MRF_CHECK_ARG(hist256 && (keys || n == 0) && pass >= 0 && pass < 8);
+  cudaError_t e = cudaMemsetAsync(hist256, 0, sizeof(unsigned long long) * kHistBins, S(stream));
+  if (e != cudaSuccess) return fail((int)e, "mrf_select_hist_prefix_f64: %s", cudaGetErrorString(e));
+  if (n == 0) return 0;
+  const unsigned blocks = (unsigned)((n + 255) / 256 < (size_t)kSelBlocks ? (n + 255) / 256 : kSelBlocks);
+  k_select_hist_prefix<<<blocks, 256, 0, S(stream)>>>(keys, n, prefix, pass, hist256);
+  return check_launch("mrf_select_hist_prefix_f64");
+}
+
+int mrf_select_successor_key_f64(const double* keys, size_t n, unsigned long long kth_key,
+                                 unsigned long long* out3, mrf_stream_t stream) {
+  MRF_CHECK_ARG(out3 && (keys || n == 0));
+  const unsigned long long init[3] = {0ull, 0ull, 0xFFFFFFFFFFFFFFFFull};
+  cudaError_t e = cudaMemcpyAsync(out3, init, sizeof(init), cudaMemcpyHostToDevice, S(stream));
+  if (e != cudaSuccess) return fail((int)e, "mrf_select_successor_key_f64: %s", cudaGetErrorString(e));
+  if (n == 0) return 0;
+  const unsigned blocks = (unsigned)((n + 255) / 256 < (size_t)kSelBlocks ? (n + 255) / 256 : kSelBlocks);
+  k_select_successor_key<<<blocks, 256, 0, S(stream)>>>(keys, n, kth_key, out3);
+  return check_launch("mrf_select_successor_key_f64");
 }
 
 size_t mrf_minmax_scratch_bytes(void) { return sizeof(double) * 3 * kMMBlocks; }

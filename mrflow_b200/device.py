@@ -268,7 +268,7 @@ def warp_sample(img, H, xn, yn, interp="cubic", want_mask=True):
 def cost_volume(ref_ch, nb_texels, labels, H, q, mu, B, label_scale=1.0, nonrigid=None, occluded=None,
                 rho="lorentzian", rho_param=1.0, cw=(0.01, 1.0, 1.0), interp="cubic", layout="LHW_F32",
                 i32_scale=1000.0, variant="staged", y0=0, frame_h=None, nb_y0=0, want_cost=True,
-                want_min=True, want_argmin=True, out=None, halo_miss=None):
+                want_min=True, want_argmin=True, out=None, halo_miss=None, out_ptr=None, plane_stride=0):
     """Per-label data cost of ONE neighbour frame (the missing extension of
     pipeline/build_cost_volume.py:209-219, defined per SURVEY.md section 8c from
     optimize_structure_single_scale.py:210-302).  ``ref_ch`` fp64 [rows,w,3] reference-frame channels
@@ -288,12 +288,16 @@ def cost_volume(ref_ch, nb_texels, labels, H, q, mu, B, label_scale=1.0, nonrigi
     p.n_labels, p.interp, p.rho, p.rho_param = Ln, INTERP[interp], RHO[rho], float(rho_param)
     p.cw = dvec(cw)
     p.layout, p.i32_scale, p.variant = LAYOUT[layout], float(i32_scale), VARIANT[variant]
+    p.cost_plane_stride = int(plane_stride)
     cost = out
-    if cost is None and want_cost:
+    if out_ptr is not None:
+        cost = None                      # raw (possibly peer-mapped) destination
+    elif cost is None and want_cost:
         cost = (torch.empty((Ln, rows, w), dtype=F32, device=dev) if layout == "LHW_F32"
                 else torch.empty((rows, w, Ln), dtype=I32, device=dev))
     mn = torch.empty((rows, w), dtype=F32, device=dev) if want_min else None
     am = torch.empty((rows, w), dtype=I32, device=dev) if want_argmin else None
+    dst = C.c_void_p(int(out_ptr)) if out_ptr is not None else _p(cost)
     check(_lib.lib().mrf_cost_volume(C.byref(p), _p(ref_ch), _p(nb_texels), _p(labels), _p(nonrigid), _p(occluded),
-                                     _p(cost), _p(mn), _p(am), _p(halo_miss), _stream()), "mrf_cost_volume")
+                                     dst, _p(mn), _p(am), _p(halo_miss), _stream()), "mrf_cost_volume")
     return cost, mn, am

@@ -57,7 +57,7 @@ def _down_pinned(t):
 
 def cost_volume_pass(band, homographies, epipoles, rigid_host_mask, stats, rho="lorentzian", sigma=1.0, interp="cubic",
                      range_mask="as_written", layout="LHW_F32", variant="staged", out=(None, None), want_cost=True,
-                     halo_miss=None, events=None):
+                     halo_miss=None, events=None, out_ptr=(None, None), plane_stride=0):
     """The device-resident body of build_cost_volume for one row band (everything stays in HBM)."""
     rigid_mask = flag(rigid_host_mask) if not isinstance(rigid_host_mask, torch.Tensor) else rigid_host_mask
     fp = pp.first_pass(band, homographies, epipoles, rigid_mask, stats)            # :78-106
@@ -70,6 +70,7 @@ def cost_volume_pass(band, homographies, epipoles, rigid_host_mask, stats, rho="
     ref64, tex = pp.channels(band)
     res = pp.cost_volumes(band, ref64, tex, labels_dev, homographies, fp["q"], fp["mu"], B_ar, nonrigid,
                           rho=rho, rho_param=sigma, interp=interp, layout=layout, variant=variant, out=out,
-                          want_cost=want_cost, halo_miss=halo_miss, events=events)
+                          want_cost=want_cost, halo_miss=halo_miss, events=events, out_ptr=out_ptr,
+                          plane_stride=plane_stride)
     cost = [res[0][0], res[1][0]]
     return cost, S, fp["mu"], B_ar, fp["q"], labels, [res[0][1], res[1][1]], [res[0][2], res[1][2]]

@@ -248,7 +248,8 @@ def channels(band):
 
 def cost_volumes(band, ref64, tex, labels_dev, homographies, q_ar, mu_ar, B_ar, nonrigid, occluded=(None, None),
                  rho="lorentzian", rho_param=1.0, interp="cubic", layout="LHW_F32", variant="staged",
-                 out=(None, None), want_cost=True, i32_scale=1000.0, halo_miss=None, frames=(0, 1), events=None):
+                 out=(None, None), want_cost=True, i32_scale=1000.0, halo_miss=None, frames=(0, 1), events=None,
+                 out_ptr=(None, None), plane_stride=0):
     """The per-label data cost of both neighbour frames (see device.cost_volume).  The backward
     frame is evaluated at ``label * mu0/mu1`` with the index-0 parameters
     (optimize_structure_single_scale.py:435-442)."""
@@ -262,7 +263,8 @@ def cost_volumes(band, ref64, tex, labels_dev, homographies, q_ar, mu_ar, B_ar, 
                                     label_scale=scale, nonrigid=nonrigid, occluded=occluded[f], rho=rho,
                                     rho_param=rho_param, cw=CHANNEL_WEIGHTS, interp=interp, layout=layout,
                                     i32_scale=i32_scale, variant=variant, y0=band.y0, frame_h=band.frame_h,
-                                    nb_y0=band.nb_y0, out=out[f], want_cost=want_cost, halo_miss=halo_miss)
+                                    nb_y0=band.nb_y0, out=out[f], want_cost=want_cost, halo_miss=halo_miss,
+                                    out_ptr=out_ptr[f], plane_stride=plane_stride)
         if events is not None:
             ev[1].record()
             events.append(ev)

@@ -1,0 +1,367 @@
+"""Row-band sharding of one triplet over the GPUs of a box.
+
+One process per GPU (``torch.distributed``, NCCL).  Rank r owns rows ``[y0_r, y1_r)`` of the reference
+frame for all labels; per-pixel work is independent given a handful of whole-frame scalars, so the
+only exchange steps are
+
+* tiny all-reduces: the sum behind ``mu`` (pipeline/compute_structure.py:84), the counts of the
+  gates (:164, :183), the label range min/max (pipeline/build_cost_volume.py:190-191);
+* exact distributed medians (compute_structure.py:190, :221): an 8-pass radix select whose 256-bin
+  histogram (2 KB) is all-reduced per pass -- ``DistSelect`` below, a host-side protocol around two
+  per-shard device steps, so the protocol itself is testable on CPU with gloo;
+* the gather of the label-major cost-volume slices to the rank that runs TRW-S: the root exports a
+  whole-frame ``[L][h][w]`` buffer as peer memory and every rank's cost-volume kernel stores its
+  rows straight into it over NVLink (``PeerVolume``) -- the transfer is the kernel's own output
+  stream, tile by tile, not a separate collective.
+
+Neighbour frames are uploaded per band with a halo of ``required_halo`` rows; the kernel reports
+any in-frame sample whose taps fall outside it (``halo_miss``) and the band is then redone with a
+larger halo.
+"""
+import ctypes as C
+import json
+import os
+import time
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from . import _lib, device, planeparallax as pp
+from ._lib import check
+
+
+# ------------------------------------------------------------------------------------------ plan
+def band_plan(h, world, align=8):
+    """Rows [y0, y1) of every rank: equal bands, boundaries aligned to the kernels' 8-row tiles."""
+    units = (h + align - 1) // align
+    base, extra = divmod(units, world)
+    out, y = [], 0
+    for r in range(world):
+        n = (base + (1 if r < extra else 0)) * align
+        out.append((min(y, h), min(y + n, h)))
+        y += n
+    return out
+
+
+def required_halo(rows, w, frame_h, H, q, mu, B, labels, label_scale=1.0, stride=4):
+    """Neighbour rows a band needs beyond its own: the extreme vertical displacement of the warp
+    (optimize_structure_single_scale.py:210-235 + interpolate_through_H.py:31-35) over the label range
+    on a ``stride``-subsampled grid of the band, plus the bicubic taps (-1..+2) and a margin for the
+    subsampling.  Returns (rows above, rows below).  Host-side planning only (fp64 numpy model; the
+    kernel's halo_miss counter is the authority)."""
+    y0, y1 = rows
+    ys = np.unique(np.r_[np.arange(y0, y1, stride), y1 - 1]).astype(np.float64)
+    xs = np.unique(np.r_[np.arange(0, w, stride), w - 1]).astype(np.float64)
+    x, y = np.meshgrid(xs, ys)
+    vx, vy = q[0] - x, q[1] - y
+    d = np.sqrt(vx ** 2 + vy ** 2)
+    nrm = np.maximum(0.5, d)
+    n = d / mu
+    H = np.asarray(H, dtype=np.float64)
+    lo, hi = 0.0, 0.0
+    with np.errstate(all="ignore"):
+        a = np.asarray(labels, dtype=np.float64) * label_scale
+        c = (a * B) / (B * a / mu - 1.0)
+        c = c[np.isfinite(c)]
+        for cc in ((c.min(), c.max()) if c.size else ()):
+            r = cc * n
+            xn, yn = x + r * vx / nrm, y + r * vy / nrm
+            den = xn * H[2, 0] + yn * H[2, 1] + H[2, 2]
+            X = (xn * H[0, 0] + yn * H[0, 1] + H[0, 2]) / den
+            Y = (xn * H[1, 0] + yn * H[1, 1] + H[1, 2]) / den
+            ok = (X >= 0) & (X <= w - 1) & (Y >= 0) & (Y <= frame_h - 1)
+            if ok.any():
+                lo = min(lo, float((Y - y0)[ok].min()))
+                hi = max(hi, float((Y - (y1 - 1))[ok].max()))
+    margin = 3 + stride
+    return int(np.ceil(-lo)) + margin, int(np.ceil(hi)) + margin
+
+
+# ------------------------------------------------------------------------------------------ select
+def order_key(v):
+    """numpy twin of the kernels' order-preserving key (csrc/select.cu)."""
+    v = np.asarray(v, dtype=np.float64)
+    b = v.view(np.uint64)
+    k = np.where(b >> np.uint64(63), ~b, b | np.uint64(1 << 63))
+    return np.where(np.isnan(v), np.uint64(0xFFFFFFFFFFFFFFFF), k)
+
+
+def key_value(k):
+    k = int(k)
+    if k == 0xFFFFFFFFFFFFFFFF:
+        return float("nan")
+    b = (k & 0x7FFFFFFFFFFFFFFF) if (k >> 63) else (~k & 0xFFFFFFFFFFFFFFFF)
+    return float(np.array([b], dtype=np.uint64).view(np.float64)[0])
+
+
+class DistSelect:
+    """Exact k-th order statistic of keys sharded over ranks.
+
+    ``hist_fn(prefix, pass) -> int64[256]`` and ``succ_fn(kth_key) -> (count_le, n_nan, min_key_gt)``
+    are the per-shard steps (device kernels in production, numpy in the CPU tests);
+    ``allreduce(array, op)`` sums / mins small int64 host arrays over the ranks."""
+
+    def __init__(self, hist_fn, succ_fn, allreduce):
+        self.hist_fn, self.succ_fn, self.allreduce = hist_fn, succ_fn, allreduce
+
+    def kth(self, k):
+        """Returns (kth value, (k+1)th value, total NaN count)."""
+        prefix, k_rem = 0, int(k)
+        for p in range(8):
+            hist = self.allreduce(np.asarray(self.hist_fn(prefix, p), dtype=np.int64), "sum")
+            b = 0
+            while b < 255 and k_rem >= int(hist[b]):
+                k_rem -= int(hist[b])
+                b += 1
+            prefix |= b << (56 - 8 * p)
+        cnt_le, n_nan, min_gt = self.succ_fn(prefix)
+        tot = self.allreduce(np.array([cnt_le, n_nan], dtype=np.int64), "sum")
+        # min over ranks of an unsigned key: compare as (high, low) signed halves
+        hi_lo = np.array([(min_gt >> 32) & 0xFFFFFFFF, min_gt & 0xFFFFFFFF], dtype=np.int64)
+        hi = self.allreduce(hi_lo[:1].copy(), "min")
+        lo = self.allreduce(np.array([hi_lo[1] if hi_lo[0] == hi[0] else 0xFFFFFFFF], dtype=np.int64), "min")
+        nxt = (int(hi[0]) << 32) | int(lo[0])
+        kv = key_value(prefix)
+        return kv, (kv if int(tot[0]) >= k + 2 else key_value(nxt)), int(tot[1])
+
+    def median(self, n_total):
+        """numpy.median over all shards (mean of the two middles for even n, NaN if any NaN)."""
+        if n_total == 0:
+            return float("nan")
+        a, b, n_nan = self.kth((n_total - 1) // 2)
+        if n_nan > 0:
+            return float("nan")
+        return a if n_total % 2 == 1 else float(np.mean(np.array([a, b])))
+
+
+class BandStats:
+    """``planeparallax`` statistics over row bands: the ``LocalStats`` interface with collectives."""
+
+    def __init__(self, group=None):
+        self.group = group
+        self.world = dist.get_world_size(group)
+        self.rank = dist.get_rank(group)
+        self.backend = dist.get_backend(group)
+        self.dev = torch.device("cuda", torch.cuda.current_device()) if self.backend == "nccl" else torch.device("cpu")
+
+    # -- small host arrays over the ranks
+    def _allreduce(self, arr, op):
+        t = torch.from_numpy(np.ascontiguousarray(arr)).to(self.dev)
+        dist.all_reduce(t, op={"sum": dist.ReduceOp.SUM, "min": dist.ReduceOp.MIN, "max": dist.ReduceOp.MAX}[op],
+                        group=self.group)
+        return t.cpu().numpy()
+
+    def total(self, value):
+        return int(self._allreduce(np.array([int(value)], dtype=np.int64), "sum")[0])
+
+    def device_sum(self, t):
+        t = t.clone()
+        dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group)
+        return t
+
+    def minmax(self, mm):
+        a = mm.cpu().numpy()
+        nan = self._allreduce(np.array([int(np.isnan(a).any())], dtype=np.int64), "max")[0]
+        lo = self._allreduce(np.array([a[0]]), "min")[0]
+        hi = self._allreduce(np.array([a[1]]), "max")[0]
+        return (float("nan"), float("nan")) if nan else (float(lo), float(hi))
+
+    def median(self, keys, n):
+        L = _lib.lib()
+        hist = torch.empty(256, dtype=torch.int64, device=keys.device)
+        out3 = torch.empty(3, dtype=torch.int64, device=keys.device)
+        stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+        def hist_fn(prefix, p):
+            check(L.mrf_select_hist_prefix_f64(C.c_void_p(keys.data_ptr()), int(n), C.c_ulonglong(prefix), p,
+                                               C.c_void_p(hist.data_ptr()), stream), "mrf_select_hist_prefix_f64")
+            return hist.cpu().numpy()
+
+        def succ_fn(kth):
+            check(L.mrf_select_successor_key_f64(C.c_void_p(keys.data_ptr()), int(n), C.c_ulonglong(kth),
+                                                 C.c_void_p(out3.data_ptr()), stream), "mrf_select_successor_key_f64")
+            o = out3.cpu().numpy().view(np.uint64)
+            return int(o[0]), int(o[1]), int(o[2])
+
+        return DistSelect(hist_fn, succ_fn, self._allreduce).median(self.total(n))
+
+    def epipole(self, fn, q, band):
+        """correct_epipole runs on the rank whose band contains the 21x21 window; the result is
+        broadcast.  A window straddling two bands is left uncorrected on all ranks (logged)."""
+        h, w = band.frame_h, band.w
+        ymin, ymax = int(q[1]) - 10, int(q[1]) + 10
+        xmin, xmax = int(q[0]) - 10, int(q[0]) + 10
+        inside = not (xmin < 0 or xmax >= w or ymin < 0 or ymax >= h)
+        mine = inside and ymin >= band.y0 and ymax < band.y0 + band.rows
+        res = np.zeros(3)
+        if mine:
+            qn = fn()
+            res = np.array([1.0, qn[0], qn[1]])
+        # exact transfer of the two doubles: exactly one rank contributes non-zero values
+        tot = self._allreduce(res, "sum")
+        if tot[0] == 0:
+            if inside and self.rank == 0:
+                print("(WW) epipole window straddles two row bands: epipole not corrected")
+            return np.asarray(q, dtype=np.float64)
+        return tot[1:3].copy()
+
+
+# ------------------------------------------------------------------------------------------ gather
+class PeerVolume:
+    """A whole-frame ``[L][h][w]`` fp32 cost volume on the root GPU that every rank can store into.
+
+    The root allocates it through ``mrf_peer_alloc`` (plain cudaMalloc + CUDA IPC handle); the handle is
+    broadcast and opened by the other ranks, whose cost-volume kernels then write their rows with
+    ``cost = base + y0*w`` and ``cost_plane_stride = h*w`` -- stores over NVLink from inside the
+    compute kernel.  ``tensor()`` on the root views the buffer as a torch tensor (no copy)."""
+
+    def __init__(self, L, h, w, root=0, group=None):
+        self.L, self.h, self.w, self.root = L, h, w, root
+        self.rank = dist.get_rank(group)
+        self.group = group
+        lib = _lib.lib()
+        self.nbytes = L * h * w * 4
+        handle = (C.c_ubyte * 64)()
+        ptr = C.c_void_p()
+        if self.rank == root:
+            check(lib.mrf_peer_alloc(self.nbytes, C.byref(ptr), handle), "mrf_peer_alloc")
+        obj = [bytes(handle)]
+        dist.broadcast_object_list(obj, src=root, group=group)
+        if self.rank != root:
+            h64 = (C.c_ubyte * 64).from_buffer_copy(obj[0])
+            check(lib.mrf_peer_open(h64, C.byref(ptr)), "mrf_peer_open")
+        self.ptr = ptr.value
+
+    def band_ptr(self, y0):
+        return self.ptr + y0 * self.w * 4
+
+    def tensor(self):
+        assert self.rank == self.root
+
+        class _Arr:
+            pass
+        a = _Arr()
+        a.__cuda_array_interface__ = {"shape": (self.L, self.h, self.w), "typestr": "<f4", "data": (self.ptr, False),
+                                      "version": 2}
+        return torch.as_tensor(a, device="cuda")
+
+    def close(self):
+        lib = _lib.lib()
+        torch.cuda.synchronize()
+        dist.barrier(group=self.group)
+        if self.rank == self.root:
+            check(lib.mrf_peer_free(C.c_void_p(self.ptr)), "mrf_peer_free")
+        else:
+            check(lib.mrf_peer_close(C.c_void_p(self.ptr)), "mrf_peer_close")
+        self.ptr = None
+
+
+# ------------------------------------------------------------------------------------------ driver
+def banded_cost_volume(t, stats, rank, world, rho="lorentzian", sigma=1.0, interp="cubic", range_mask="rigid_only",
+                       variant="staged", peer=(None, None), keep_local=True, halo=None, timers=None):
+    """build_cost_volume for this rank's band of the host triplet ``t`` (dict as synth.make_triplet
+    returns).  Returns dict(cost, S, mu, B, q, labels, mins, argmins, rows, halo)."""
+    from .pipeline.build_cost_volume import cost_volume_pass
+    h, w = t["shape"]
+    y0, y1 = band_plan(h, world)[rank]
+    rig = np.asarray(t["rigidity"])
+    # structure pass needs only this band's flows; images come with the halo once it is known
+    halo_rows = 32 if halo is None else int(halo)
+    while True:
+        band = pp.Band.from_host(t["images"], t["flow"], rig, None, rows=(y0, y1), halo=halo_rows)
+        miss = torch.zeros(1, dtype=torch.int32, device="cuda")
+        outs = tuple((p.band_ptr(y0) if p is not None else None) for p in peer)
+        res = cost_volume_pass(band, t["homographies"], t["epipoles"], rig[y0:y1] > 0, stats, rho=rho, sigma=sigma,
+                               interp=interp, range_mask=range_mask, variant=variant, halo_miss=miss,
+                               want_cost=keep_local, out_ptr=outs, plane_stride=(h * w if outs[0] is not None else 0),
+                               events=timers)
+        n_miss = stats.total(int(miss.cpu()[0]))
+        if n_miss == 0:
+            break
+        halo_rows *= 2                      # a sample reached beyond the halo somewhere: widen everywhere
+        if halo_rows > 4 * h:
+            raise RuntimeError("halo search did not converge")
+    cost, S, mu, B, q, labels, mins, argmins = res
+    return dict(cost=cost, S=S, mu=mu, B=B, q=q, labels=labels, mins=mins, argmins=argmins, rows=(y0, y1), halo=halo_rows)
+
+
+def bench_bands(args, hw, steps, warm, metric, unit, workload, ClockSampler):
+    """bench.py --mode bands: ONE frame sharded by row bands over all ranks (strong scaling)."""
+    from . import synth
+    rank, world = dist.get_rank(), dist.get_world_size()
+    h, w = hw
+    L = pp.N_LABELS
+    t = synth.make_triplet(hw, seed=1001)            # every rank builds the same host triplet
+    stats = BandStats()
+    from .pipeline.build_cost_volume import cost_volume_pass
+    y0, y1 = band_plan(h, world)[rank]
+    rig = np.asarray(t["rigidity"])
+    # pick the halo once (planning is outside the timed region, as uploading the inputs is)
+    r0 = banded_cost_volume(t, stats, rank, world, interp=args.interp, variant=args.variant, keep_local=False)
+    halo_rows = r0["halo"]
+    band = pp.Band.from_host(t["images"], t["flow"], rig, None, rows=(y0, y1), halo=halo_rows)
+    rigid_mask = torch.from_numpy((rig[y0:y1] > 0).astype(np.uint8)).cuda()
+    peers = (PeerVolume(L, h, w), PeerVolume(L, h, w))
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+    kernel_events = []
+
+    def step(events=None, gather=True):
+        outs = tuple(p.band_ptr(y0) for p in peers) if gather else (None, None)
+        return cost_volume_pass(band, t["homographies"], t["epipoles"], rigid_mask, stats, interp=args.interp,
+                                range_mask="rigid_only", variant=args.variant, want_cost=not gather, out_ptr=outs,
+                                plane_stride=(h * w if gather else 0), events=events)
+
+    def barrier():
+        torch.cuda.synchronize(); dist.barrier(); torch.cuda.synchronize()
+
+    results = {}
+    for mode, gather in (("compute_only", False), ("compute_and_gather", True)):
+        for _ in range(warm):
+            step(gather=gather)
+        barrier()
+        device.reset_launch_count()
+        tot = 0.0
+        with ClockSampler(torch.cuda.current_device()) as clocks:
+            for _ in range(steps):
+                flush.fill_(1)
+                barrier()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                step(kernel_events if gather else None, gather=gather)
+                e1.record(); e1.synchronize()
+                tot += e0.elapsed_time(e1)
+        launches = device.launch_count()
+        tt = torch.tensor([tot], dtype=torch.float64, device="cuda")
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        results[mode] = (float(tt.cpu()[0]), launches, clocks.summary())
+    units = 2 * h * w * L
+    tot_ms, launches, clk = results["compute_and_gather"]
+    kms = [a.elapsed_time(b) for a, b in kernel_events]
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "MEASURED_PEAKS.json")))
+    except Exception:   # noqa: BLE001
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    rows = y1 - y0
+    bytes_launch = rows * w * (L * 4 + 4 + 12 + 2 + 6)
+    ach = bytes_launch / (float(np.mean(kms)) * 1e-3) / 1e9
+    barrier()
+    for p in peers:
+        p.close()
+    if rank == 0:
+        line = {"metric": metric, "value": units * steps / (tot_ms * 1e-3), "unit": unit, "n_gpus": world, "steps": steps,
+                "warmup": warm, "ms_per_step": tot_ms / steps, "higher_is_better": True, "scaling": "strong",
+                "vs_baseline": None, "dtype": "f64 geometry / f32 sampling", "data": "synthetic",
+                "config": {"workload": workload, "labels": L, "frames": 2, "interp": args.interp, "variant": args.variant,
+                           "range_mask": "rigid_only", "parallelism": "row bands x%d, halo %d rows, peer-store gather to rank 0"
+                           % (world, halo_rows), "l2": "flushed between timed steps"},
+                "compute_only": {"value": units * steps / (results["compute_only"][0] * 1e-3), "ms_per_step": results["compute_only"][0] / steps},
+                "clocks": clk, "e2e": None, "gpu_launches": int(launches),
+                "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
+                             "kernel": "k_cost_volume (this rank's band, stores to rank 0 over NVLink)",
+                             "kernel_ms": float(np.mean(kms))},
+                "cpu_baseline": None}
+        print(json.dumps(line))
+    dist.destroy_process_group()

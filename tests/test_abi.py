@@ -26,7 +26,7 @@ def test_library_exports_every_declared_symbol():
     L = _lib.lib()
     assert L.mrf_version() >= 100
     assert L.mrf_reduce_scratch_bytes() > 0 and L.mrf_select_scratch_bytes(10) > 0
-    assert ctypes.sizeof(_lib.CostVolParams) == 208      # sizeof(mrf_costvol_params), checked with gcc
+    assert ctypes.sizeof(_lib.CostVolParams) == 216      # sizeof(mrf_costvol_params), checked with gcc
 
 
 def test_bad_arguments_are_rejected_without_a_gpu():

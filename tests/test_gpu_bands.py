@@ -1,0 +1,82 @@
+"""Row bands over 2 GPUs (NCCL, one process per GPU): the banded, peer-gathered cost volume equals
+the whole-frame single-GPU volume bit for bit (sharding must not change arithmetic), and the
+whole-frame statistics (mu, B, labels) agree with the single-GPU pass."""
+import os
+import socket
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _free_port():
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); p = s.getsockname()[1]; s.close()
+    return p
+
+
+def _worker(rank, world, port, queue):
+    import torch
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    out = {}
+    try:
+        from mrflow_b200 import device, planeparallax as pp, sharding, synth
+        from mrflow_b200.pipeline.build_cost_volume import cost_volume_pass
+        t = synth.make_triplet((200, 256), seed=31, epipole="inside", n_waves=8)
+        t["rigidity"][20:60, 30:90] = 0.0
+        h, w = t["shape"]
+        stats = sharding.BandStats()
+        peers = (sharding.PeerVolume(51, h, w), sharding.PeerVolume(51, h, w))
+        # deliberately small first halo: the halo_miss retry must kick in
+        res = sharding.banded_cost_volume(t, stats, rank, world, peer=peers, keep_local=True, halo=2)
+        torch.cuda.synchronize(); dist.barrier()
+        out["halo"] = res["halo"]
+        y0, y1 = res["rows"]
+        if rank == 0:
+            band = pp.Band.from_host(t["images"], t["flow"], t["rigidity"], None)
+            one = cost_volume_pass(band, t["homographies"], t["epipoles"], t["rigidity"] > 0, pp.LocalStats(),
+                                   range_mask="rigid_only")
+            out["mu"] = (res["mu"], one[2]); out["B"] = (res["B"], one[3])
+            out["labels_close"] = bool(np.allclose(res["labels"], one[5], rtol=1e-11, atol=0))
+            # whole-frame kernel with the banded run's scalars: must match the gathered volume bitwise
+            ref64, tex = pp.channels(band)
+            nonrigid = torch.from_numpy((t["rigidity"] == 0).astype(np.uint8)).cuda()
+            whole = pp.cost_volumes(band, ref64, tex, torch.from_numpy(res["labels"]).cuda(), t["homographies"], res["q"],
+                                    res["mu"], res["B"], nonrigid)
+            for f in range(2):
+                out["equal%d" % f] = bool(torch.equal(peers[f].tensor(), whole[f][0]))
+                out["local_equal%d" % f] = bool(torch.equal(res["cost"][f], whole[f][0][:, y0:y1]))
+                out["argmin_equal%d" % f] = bool(torch.equal(res["argmins"][f], whole[f][2][y0:y1]))
+        for p in peers:
+            p.close()
+    finally:
+        dist.destroy_process_group()
+    queue.put((rank, out))
+
+
+def test_two_band_volume_equals_whole_frame():
+    import torch
+    import torch.multiprocessing as mp
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = dict(q.get(timeout=300) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    o = res[0]
+    assert o["halo"] > 2                                   # the retry widened the halo
+    np.testing.assert_allclose(o["mu"][0], o["mu"][1], rtol=1e-14)
+    np.testing.assert_allclose(o["B"][0], o["B"][1], rtol=1e-11)
+    assert o["labels_close"]
+    for f in range(2):
+        assert o["equal%d" % f] and o["local_equal%d" % f] and o["argmin_equal%d" % f]

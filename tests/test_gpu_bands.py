@@ -24,6 +24,7 @@ def _worker(rank, world, port, queue):
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
     out = {}
     try:
+        import traceback
         from mrflow_b200 import device, planeparallax as pp, sharding, synth
         from mrflow_b200.pipeline.build_cost_volume import cost_volume_pass
         t = synth.make_triplet((200, 256), seed=31, epipole="inside", n_waves=8)
@@ -32,7 +33,7 @@ def _worker(rank, world, port, queue):
         stats = sharding.BandStats()
         peers = (sharding.PeerVolume(51, h, w), sharding.PeerVolume(51, h, w))
         # deliberately small first halo: the halo_miss retry must kick in
-        res = sharding.banded_cost_volume(t, stats, rank, world, peer=peers, keep_local=True, halo=2)
+        res = sharding.banded_cost_volume(t, stats, rank, world, peer=peers, halo=2)
         torch.cuda.synchronize(); dist.barrier()
         out["halo"] = res["halo"]
         y0, y1 = res["rows"]
@@ -49,13 +50,12 @@ def _worker(rank, world, port, queue):
                                     res["mu"], res["B"], nonrigid)
             for f in range(2):
                 out["equal%d" % f] = bool(torch.equal(peers[f].tensor(), whole[f][0]))
-                out["local_equal%d" % f] = bool(torch.equal(res["cost"][f], whole[f][0][:, y0:y1]))
                 out["argmin_equal%d" % f] = bool(torch.equal(res["argmins"][f], whole[f][2][y0:y1]))
-        for p in peers:
-            p.close()
-    finally:
-        dist.destroy_process_group()
+        torch.cuda.synchronize()
+    except Exception:                       # noqa: BLE001  -- report instead of leaving the peer rank in a barrier
+        out["error"] = traceback.format_exc()
     queue.put((rank, out))
+    os._exit(0)                             # no collective teardown: a failed rank must not hang the other
 
 
 def test_two_band_volume_equals_whole_frame():
@@ -69,14 +69,19 @@ def test_two_band_volume_equals_whole_frame():
     procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
     for p in procs:
         p.start()
-    res = dict(q.get(timeout=300) for _ in procs)
-    for p in procs:
-        p.join(timeout=60)
-        assert p.exitcode == 0
+    try:
+        res = dict(q.get(timeout=150) for _ in procs)
+    finally:
+        for p in procs:
+            p.join(timeout=20)
+            if p.is_alive():
+                p.kill()
+    for r in res.values():
+        assert "error" not in r, r["error"]
     o = res[0]
     assert o["halo"] > 2                                   # the retry widened the halo
     np.testing.assert_allclose(o["mu"][0], o["mu"][1], rtol=1e-14)
     np.testing.assert_allclose(o["B"][0], o["B"][1], rtol=1e-11)
     assert o["labels_close"]
     for f in range(2):
-        assert o["equal%d" % f] and o["local_equal%d" % f] and o["argmin_equal%d" % f]
+        assert o["equal%d" % f] and o["argmin_equal%d" % f]

@@ -240,14 +240,16 @@ def run_ours(args):
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")    # > 126 MB L2
     kernel_events = []
 
+    fbuf = device.FrontBuffers(h, w)
+    zero_mask = nonrigid if RANGE_MASK == "rigid_only" else rigid_mask
+
     def step(events=None):
-        out = bcv.cost_volume_pass(band, t["homographies"], t["epipoles"], rigid_mask, stats, rho="lorentzian", sigma=1.0,
-                                   interp=args.interp, variant=args.variant, out=cost_out, events=events,
-                                   range_mask=RANGE_MASK)
-        cost, S, mu_ar, B_ar, q_new, labels, mins, argmins = out
-        u, v = device.structure_to_flow(S[1], q_new[1], mu_ar[1], t["homographies"][1], B_ar[1], nonrigid=nonrigid,
-                                        init_u=band.flow[1][0], init_v=band.flow[1][1])
-        return argmins, u, v
+        r = bcv.cost_volume_pass_resident(band, t["homographies"], t["epipoles"], rigid_mask, rho="lorentzian", sigma=1.0,
+                                          interp=args.interp, variant=args.variant, out=cost_out, events=events,
+                                          buffers=fbuf, masks=(nonrigid, zero_mask))
+        u, v = device.structure_to_flow(fbuf.S[1], r["q"][1], 0.0, t["homographies"][1], 0.0, nonrigid=nonrigid,
+                                        init_u=band.flow[1][0], init_v=band.flow[1][1], state=fbuf.state, frame=1)
+        return r["argmins"], u, v
 
     def barrier():
         torch.cuda.synchronize()

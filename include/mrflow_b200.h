@@ -57,6 +57,14 @@ typedef void* mrf_stream_t; /* cudaStream_t */
 #define MRF_LAYOUT_HWL_I32 1  /* [rows][w][L] int32 = (int)(cost*i32_scale), what
                                  extern/eff_trws/image.cpp:80 consumes */
 
+/* Device-resident whole-frame scalars ("state", fp64 words) written by mrf_cost_volume_front and read
+ * by mrf_cost_volume / mrf_structure_to_flow when their dev_state argument is non-NULL. */
+#define MRF_STATE_MU      0   /* [2] mu of frame 0 (bwd), 1 (fwd)      compute_structure.py:84 */
+#define MRF_STATE_B       2   /* [2] B_b, B_fwd                         compute_structure.py:190-223 */
+#define MRF_STATE_MINMAX  4   /* [4] (min, max) of the range-masked structures of frame 0, 1 */
+#define MRF_STATE_LABELS  16  /* [n_labels] structure_range             build_cost_volume.py:190-192 */
+#define MRF_STATE_WORDS   (16 + 256)
+
 int         mrf_version(void);
 const char* mrf_last_error(void);
 
@@ -82,11 +90,13 @@ int mrf_parallax_to_structure(const double* parallax, int rows, int w, int y0,
 
 /* ---- a6: pipeline/structure2flow.py:14-38 (structure_to_flow) incl. get_full_flow
  * (utils/flow_homography.py:20-37); if nonrigid != NULL also the paste of
- * combine_flow_simple (:72-73): where nonrigid[p] != 0 the output is flow_init. */
+ * combine_flow_simple (:72-73): where nonrigid[p] != 0 the output is flow_init.  With dev_state
+ * non-NULL, mu and b are read from the device state of frame state_frame instead. */
 int mrf_structure_to_flow(const double* structure, int rows, int w, int y0,
                           const double* q_host, double mu, const double* H_host, double b,
                           const uint8_t* nonrigid, const float* init_u, const float* init_v,
-                          float* u, float* v, mrf_stream_t stream);
+                          float* u, float* v, const double* dev_state, int state_frame,
+                          mrf_stream_t stream);
 
 /* ---- a6 tail on its own: utils/flow_homography.py:20-37 (get_full_flow) and :41-48
  * (homography2flow = get_full_flow of a zero residual).  u_res, v_res fp64 (an fp32 residual
@@ -211,6 +221,7 @@ typedef struct {
   int    layout;        /* MRF_LAYOUT_* */
   double i32_scale;     /* for MRF_LAYOUT_HWL_I32 */
   int    variant;       /* MRF_VARIANT_* */
+  int    state_frame;   /* with dev_state: which frame's mu / B to read (0 = bwd, 1 = fwd) */
   long long cost_plane_stride; /* LHW layout: elements between consecutive label planes of `cost`;
                                   0 = rows*w.  With frame_h*w and cost = volume + y0*w a band writes
                                   its rows straight into a whole-frame [L][frame_h][w] volume -- which
@@ -235,7 +246,37 @@ typedef struct {
  * non-zero value means the caller's halo was too small and the band must be recomputed. */
 int mrf_cost_volume(const mrf_costvol_params* p_host, const double* ref_ch, const float* nb_texels,
                     const double* labels, const uint8_t* nonrigid, const uint8_t* occluded,
-                    void* cost, float* min_cost, int32_t* argmin, int* halo_miss, mrf_stream_t stream);
+                    void* cost, float* min_cost, int32_t* argmin, int* halo_miss,
+                    const double* dev_state, mrf_stream_t stream);
+
+/* ---- the pre-pass of build_cost_volume with no host round trip (pipeline/build_cost_volume.py:78-192
+ * with the live conventions of compute_structure.py): residual flow -> parallax (both frames), mu,
+ * valid mask and B_b = median(template/target) with B_fwd fixed, normed structures, masked min/max,
+ * label set.  All whole-frame scalars land in dev_state (MRF_STATE_*), so the label-major cost
+ * volume can follow on the same stream -- or the whole step be captured in a CUDA graph.  Whole
+ * frame on one GPU only (row bands use the step-wise calls with all-reduces in between).
+ * rigid_mask: uint8 (the reference's rigidity > 0); zero_mask: pixels zeroed before the range is
+ * taken (:159) or NULL; box: the +-10 px square round each epipole {x0,x1,y0,y1} (:154-165).
+ * cand: rows*w doubles; count: device int; scratch: mrf_front_scratch_bytes() bytes. */
+typedef struct {
+  int rows, w, y0, frame_h;
+  double Hinv0[9], Hinv1[9];   /* inverse homographies, utils/flow_homography.py:12 */
+  double q0[2], q1[2];         /* (refined) epipoles */
+  double B_fwd;                /* 1.0 in build_cost_volume.py:131 */
+  int have_box[2];
+  int box[2][4];
+  int n_labels;
+} mrf_front_params;
+size_t mrf_front_scratch_bytes(void);
+int mrf_cost_volume_front(const mrf_front_params* p_host, const float* u0, const float* v0,
+                          const float* u1, const float* v1, const uint8_t* rigid_mask,
+                          const uint8_t* zero_mask, double* par0, double* par1, double* S0, double* S1,
+                          double* cand, int* count, double* dev_state, void* scratch, mrf_stream_t stream);
+/* numpy.median of the first *n_dev keys (n read on the device); np.linspace label set from the
+ * state's min/max.  Building blocks of the front, exported for tests. */
+int mrf_select_median_dev(const double* keys, const int* n_dev, size_t capacity, double* out_median,
+                          void* scratch, mrf_stream_t stream);
+int mrf_label_range_dev(double* dev_state, int n_labels, mrf_stream_t stream);
 
 /* ---- utils/robust_functions.py:26-70 on a device array: out = rho(x) (deriv = 0) or d rho/dx
  * (deriv = 1), x = squared residual.  kind = MRF_RHO_*; p1 = sigma / eps; p2 = Charbonnier

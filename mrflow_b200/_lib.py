@@ -25,7 +25,17 @@ class CostVolParams(C.Structure):
                 ("n_labels", C.c_int), ("interp", C.c_int), ("rho", C.c_int),
                 ("rho_param", C.c_double), ("cw", C.c_double * 3),
                 ("layout", C.c_int), ("i32_scale", C.c_double), ("variant", C.c_int),
-                ("cost_plane_stride", C.c_longlong)]
+                ("state_frame", C.c_int), ("cost_plane_stride", C.c_longlong)]
+
+
+class FrontParams(C.Structure):
+    """mrf_front_params"""
+    _fields_ = [("rows", C.c_int), ("w", C.c_int), ("y0", C.c_int), ("frame_h", C.c_int),
+                ("Hinv0", C.c_double * 9), ("Hinv1", C.c_double * 9), ("q0", C.c_double * 2), ("q1", C.c_double * 2),
+                ("B_fwd", C.c_double), ("have_box", C.c_int * 2), ("box", (C.c_int * 4) * 2), ("n_labels", C.c_int)]
+
+
+STATE_MU, STATE_B, STATE_MINMAX, STATE_LABELS, STATE_WORDS = 0, 2, 4, 16, 16 + 256
 
 
 _P, _I, _D, _Z = C.c_void_p, C.c_int, C.c_double, C.c_size_t
@@ -42,7 +52,7 @@ SIGNATURES = {
     "mrf_reduce_scratch_bytes": (_Z, []),
     "mrf_epipole_dist_sum": (_I, [_I, _I, _I, _DP, _P, _P, _P]),
     "mrf_parallax_to_structure": (_I, [_P, _I, _I, _I, _DP, _D, _D, _P, _P]),
-    "mrf_structure_to_flow": (_I, [_P, _I, _I, _I, _DP, _D, _DP, _D, _P, _P, _P, _P, _P, _P]),
+    "mrf_structure_to_flow": (_I, [_P, _I, _I, _I, _DP, _D, _DP, _D, _P, _P, _P, _P, _P, _P, _I, _P]),
     "mrf_full_flow": (_I, [_P, _P, _I, _I, _I, _DP, _P, _P, _P]),
     "mrf_rigidity_unaries": (_I, [_P, _P, _I, _I, _I, _DP, _D, _D, _D, _P, _P]),
     "mrf_rigidity_direction": (_I, [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _DP, _DP, _D, _D, _P, _P, _P, _P]),
@@ -66,7 +76,11 @@ SIGNATURES = {
     "mrf_masked_minmax_f64": (_I, [_P, _P, _I, _I, _I, _IP, _P, _P, _P]),
     "mrf_prepare_channels": (_I, [_P, _I, _I, _I, _P, _P, _P, _P]),
     "mrf_warp_sample": (_I, [_P, _I, _I, _I, _DP, _P, _P, _Z, _I, _P, _P, _P]),
-    "mrf_cost_volume": (_I, [C.POINTER(CostVolParams), _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
+    "mrf_cost_volume": (_I, [C.POINTER(CostVolParams), _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
+    "mrf_front_scratch_bytes": (_Z, []),
+    "mrf_cost_volume_front": (_I, [C.POINTER(FrontParams), _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
+    "mrf_select_median_dev": (_I, [_P, _P, _Z, _P, _P, _P]),
+    "mrf_label_range_dev": (_I, [_P, _I, _P]),
     "mrf_erode3x3_u8": (_I, [_P, _I, _I, _P, _P]),
     "mrf_robust_apply_f64": (_I, [_P, _Z, _I, _I, _D, _D, _P, _P]),
 }

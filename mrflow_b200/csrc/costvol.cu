@@ -57,6 +57,8 @@ struct CVArgs {
   int32_t* argmin;
   int* halo_miss;
   long long plane_stride;   // elements between label planes of the LHW volume
+  const double* state;      // device-resident scalars (mu, B, labels) or nullptr
+  int frame;
   double wm1, hm1;          // (double)(w - 1), (double)(frame_h - 1)
   double s2, rs2;           // rho_param^2 and RN(1 / s2)
 };
@@ -261,11 +263,20 @@ k_cost_volume(const __grid_constant__ CVArgs a) {
   const int y = yl + a.y0;
   const int L = a.L;
 
+  // whole-frame scalars: from the host, or from the device state the pre-pass left in HBM
+  double g_mu = a.mu, g_B = a.B, g_scale = a.label_scale;
+  const double* g_labels = a.labels;
+  if (a.state) {
+    g_mu = a.state[MRF_STATE_MU + a.frame];
+    g_B = a.state[MRF_STATE_B + a.frame];
+    g_scale = (a.frame == 0) ? a.state[MRF_STATE_MU] / a.state[MRF_STATE_MU + 1] : 1.0;   // :435-436
+    g_labels = a.state + MRF_STATE_LABELS;
+  }
   // per-label scalars: a = label*scale (:435-436), A*B and B*A/mu - 1 (:221)
   for (int l = threadIdx.x; l < L; l += kThreads) {
-    const double al = a.labels[l] * a.label_scale;
-    const double ab = al * a.B;
-    const double den = ab / a.mu - 1.0;
+    const double al = g_labels[l] * g_scale;
+    const double ab = al * g_B;
+    const double den = ab / g_mu - 1.0;
     LabelRec rec;
     rec.ab = ab; rec.den = den; rec.rden = 1.0 / den;
     rec.safe = (tame(den) && (ab == 0.0 || tame(ab))) ? 1.0 : 0.0;
@@ -299,7 +310,7 @@ k_cost_volume(const __grid_constant__ CVArgs a) {
   const double dist = sqrt(vx * vx + vy * vy);
   const double nrm = fmax(0.5, dist);
   const double t1 = vx / nrm, t2 = vy / nrm;
-  const double n = dist / a.mu;
+  const double n = dist / g_mu;
 
   const long long pix = (long long)yl * a.w + x;
   bool dead = !valid;
@@ -492,8 +503,9 @@ using namespace mrf;
 extern "C" int mrf_cost_volume(const mrf_costvol_params* p, const double* ref_ch, const float* nb_texels,
                                const double* labels, const uint8_t* nonrigid, const uint8_t* occluded,
                                void* cost, float* min_cost, int32_t* argmin, int* halo_miss,
-                               mrf_stream_t stream) {
-  MRF_CHECK_ARG(p && ref_ch && nb_texels && labels);
+                               const double* dev_state, mrf_stream_t stream) {
+  MRF_CHECK_ARG(p && ref_ch && nb_texels && (labels || dev_state));
+  MRF_CHECK_ARG(!dev_state || p->state_frame == 0 || p->state_frame == 1);
   MRF_CHECK_ARG(p->rows > 0 && p->w > 0 && p->frame_h >= p->y0 + p->rows && p->y0 >= 0);
   MRF_CHECK_ARG(p->nb_rows > 0 && p->nb_y0 >= 0 && p->nb_y0 + p->nb_rows <= p->frame_h);
   MRF_CHECK_ARG(p->n_labels >= 1 && p->n_labels <= kMaxLabels);
@@ -517,6 +529,7 @@ extern "C" int mrf_cost_volume(const mrf_costvol_params* p, const double* ref_ch
   a.nonrigid = nonrigid; a.occluded = occluded;
   a.cost = cost; a.min_cost = min_cost; a.argmin = argmin; a.halo_miss = halo_miss;
   a.plane_stride = plane_stride;
+  a.state = dev_state; a.frame = p->state_frame;
   a.wm1 = (double)(p->w - 1); a.hm1 = (double)(p->frame_h - 1);
   a.s2 = p->rho_param * p->rho_param; a.rs2 = 1.0 / a.s2;
 

@@ -95,18 +95,19 @@ k_dist_sum_partial(int rows, int w, int y0, Pt2 q, double* __restrict__ partial)
 }
 
 __global__ void __launch_bounds__(kRedBlocks)
-k_sum_final(const double* __restrict__ partial, int n, double* __restrict__ out) {
+k_sum_final(const double* __restrict__ partial, int n, double* __restrict__ out, double divide_by) {
   __shared__ double sh[32];
   double v = (threadIdx.x < n) ? partial[threadIdx.x] : 0.0;
   v = block_sum(v, sh);
-  if (threadIdx.x == 0) out[0] = v;
+  if (threadIdx.x == 0) out[0] = (divide_by != 0.0) ? v / divide_by : v;   // .mean() = sum / n
 }
 
 // ------------------------------------------------------------------------------- a3
 // pipeline/compute_structure.py:25-33
 __global__ void __launch_bounds__(256)
 k_parallax_to_structure(const double* __restrict__ parallax, int rows, int w, int y0, Pt2 q, double B,
-                        double mu, double* __restrict__ structure) {
+                        double mu, double* __restrict__ structure, const double* __restrict__ st, int frame) {
+  if (st) { mu = st[MRF_STATE_MU + frame]; B = st[MRF_STATE_B + frame]; }
   const long long n = (long long)rows * w;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n;
        i += (long long)gridDim.x * blockDim.x) {
@@ -125,7 +126,8 @@ __global__ void __launch_bounds__(256)
 k_structure_to_flow(const double* __restrict__ structure, int rows, int w, int y0, Pt2 q, double mu,
                     Mat3 H, double b, const uint8_t* __restrict__ nonrigid,
                     const float* __restrict__ init_u, const float* __restrict__ init_v,
-                    float* __restrict__ u, float* __restrict__ v) {
+                    float* __restrict__ u, float* __restrict__ v, const double* __restrict__ st, int frame) {
+  if (st) { mu = st[MRF_STATE_MU + frame]; b = st[MRF_STATE_B + frame]; }
   const long long n = (long long)rows * w;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n;
        i += (long long)gridDim.x * blockDim.x) {
@@ -272,7 +274,8 @@ __global__ void __launch_bounds__(256)
 k_structure_candidates(const double* __restrict__ par0, const double* __restrict__ par1,
                        const uint8_t* __restrict__ p_thr, int rows, int w, int y0, Pt2 q0, Pt2 q1,
                        double mu0, double mu1, double B_fwd, int want, uint8_t* __restrict__ pv,
-                       double* __restrict__ cand, int* __restrict__ count) {
+                       double* __restrict__ cand, int* __restrict__ count, const double* __restrict__ st) {
+  if (st) { mu0 = st[MRF_STATE_MU]; mu1 = st[MRF_STATE_MU + 1]; }
   const long long n = (long long)rows * w;
   for (long long i0 = blockIdx.x * (long long)blockDim.x; i0 < n; i0 += (long long)gridDim.x * blockDim.x) {
     const long long i = i0 + threadIdx.x;
@@ -345,6 +348,8 @@ k_abs_dev(const double* __restrict__ x, size_t n, double c, double* __restrict__
     out[i] = fabs(x[i] - c);
 }
 
+__global__ void k_set_f64(double* p, double v) { p[0] = v; }
+
 static inline unsigned grid_for(long long n, int threads = 256) {
   long long b = (n + threads - 1) / threads;
   const long long cap = (long long)kSMs * 16;
@@ -382,7 +387,7 @@ int mrf_epipole_dist_sum(int rows, int w, int y0, const double* q_host, double* 
   k_dist_sum_partial<<<kRedBlocks, kRedThreads, 0, S(stream)>>>(rows, w, y0, pt2(q_host), (double*)scratch);
   int rc = check_launch("mrf_epipole_dist_sum/partial");
   if (rc) return rc;
-  k_sum_final<<<1, kRedBlocks, 0, S(stream)>>>((const double*)scratch, kRedBlocks, out_sum);
+  k_sum_final<<<1, kRedBlocks, 0, S(stream)>>>((const double*)scratch, kRedBlocks, out_sum, 0.0);
   return check_launch("mrf_epipole_dist_sum/final");
 }
 
@@ -390,17 +395,20 @@ int mrf_parallax_to_structure(const double* parallax, int rows, int w, int y0, c
                               double mu, double* structure, mrf_stream_t stream) {
   MRF_CHECK_ARG(parallax && structure && rows > 0 && w > 0 && q_host);
   k_parallax_to_structure<<<grid_for((long long)rows * w), 256, 0, S(stream)>>>(parallax, rows, w, y0,
-                                                                               pt2(q_host), B, mu, structure);
+                                                                               pt2(q_host), B, mu, structure, nullptr, 0);
   return check_launch("mrf_parallax_to_structure");
 }
 
 int mrf_structure_to_flow(const double* structure, int rows, int w, int y0, const double* q_host, double mu,
                           const double* H_host, double b, const uint8_t* nonrigid, const float* init_u,
-                          const float* init_v, float* u, float* v, mrf_stream_t stream) {
+                          const float* init_v, float* u, float* v, const double* dev_state, int state_frame,
+                          mrf_stream_t stream) {
   MRF_CHECK_ARG(structure && u && v && rows > 0 && w > 0 && q_host && H_host);
   MRF_CHECK_ARG(!nonrigid || (init_u && init_v));
+  MRF_CHECK_ARG(!dev_state || state_frame == 0 || state_frame == 1);
   k_structure_to_flow<<<grid_for((long long)rows * w), 256, 0, S(stream)>>>(
-      structure, rows, w, y0, pt2(q_host), mu, mat3(H_host), b, nonrigid, init_u, init_v, u, v);
+      structure, rows, w, y0, pt2(q_host), mu, mat3(H_host), b, nonrigid, init_u, init_v, u, v, dev_state,
+      state_frame);
   return check_launch("mrf_structure_to_flow");
 }
 
@@ -449,7 +457,7 @@ int mrf_structure_candidates(const double* par0, const double* par1, const uint8
     if (e != cudaSuccess) return fail((int)e, "mrf_structure_candidates: %s", cudaGetErrorString(e));
   }
   k_structure_candidates<<<grid_for((long long)rows * w), 256, 0, S(stream)>>>(
-      par0, par1, p_thr, rows, w, y0, pt2(q0_host), pt2(q1_host), mu0, mu1, B_fwd, want, pv, cand, count);
+      par0, par1, p_thr, rows, w, y0, pt2(q0_host), pt2(q1_host), mu0, mu1, B_fwd, want, pv, cand, count, nullptr);
   return check_launch("mrf_structure_candidates");
 }
 
@@ -470,6 +478,69 @@ int mrf_abs_deviation_f64(const double* x, size_t n, double c, double* out, mrf_
   if (n == 0) return 0;
   k_abs_dev<<<grid_for((long long)n), 256, 0, S(stream)>>>(x, n, c, out);
   return check_launch("mrf_abs_deviation_f64");
+}
+
+
+// ---------------------------------------------------------------------------------------------
+// The pre-pass of build_cost_volume with every whole-frame scalar kept on the device
+// (pipeline/build_cost_volume.py:78-192 with the live conventions of compute_structure.py): no host
+// synchronisation between the flows and the label set, so the whole step can be captured in a CUDA
+// graph.  Launch sequence only; the arithmetic is that of the kernels above.
+int mrf_select_median_dev(const double* keys, const int* n_dev, size_t capacity, double* out_median, void* scratch,
+                          mrf_stream_t stream);
+int mrf_label_range_dev(double* dev_state, int n_labels, mrf_stream_t stream);
+
+size_t mrf_front_scratch_bytes(void) { return sizeof(double) * 4096 + mrf_select_scratch_bytes(0) + 64; }
+
+int mrf_cost_volume_front(const mrf_front_params* p, const float* u0, const float* v0, const float* u1,
+                          const float* v1, const uint8_t* rigid_mask, const uint8_t* zero_mask,
+                          double* par0, double* par1, double* S0, double* S1, double* cand, int* count,
+                          double* dev_state, void* scratch, mrf_stream_t stream) {
+  MRF_CHECK_ARG(p && u0 && v0 && u1 && v1 && rigid_mask && par0 && par1 && S0 && S1 && cand && count && dev_state && scratch);
+  MRF_CHECK_ARG(p->rows > 0 && p->w > 0 && p->y0 == 0 && p->frame_h == p->rows);   /* whole frame on one GPU */
+  MRF_CHECK_ARG(p->n_labels >= 2 && p->n_labels <= 256);
+  const long long n = (long long)p->rows * p->w;
+  const unsigned g = grid_for(n);
+  const float* uu[2] = {u0, u1};
+  const float* vv[2] = {v0, v1};
+  double* par[2] = {par0, par1};
+  double* Ss[2] = {S0, S1};
+  const double* Hinv[2] = {p->Hinv0, p->Hinv1};
+  const double* qq[2] = {p->q0, p->q1};
+  int rc = 0;
+  for (int f = 0; f < 2 && !rc; ++f) {
+    k_flow_to_parallax<<<g, 256, 0, S(stream)>>>(uu[f], vv[f], p->rows, p->w, 0, mat3(Hinv[f]), pt2(qq[f]), nullptr,
+                                                 nullptr, par[f], nullptr);
+    rc = check_launch("front/flow_to_parallax");
+    if (rc) break;
+    k_dist_sum_partial<<<kRedBlocks, kRedThreads, 0, S(stream)>>>(p->rows, p->w, 0, pt2(qq[f]), (double*)scratch);
+    rc = check_launch("front/dist_sum");
+    if (rc) break;
+    k_sum_final<<<1, kRedBlocks, 0, S(stream)>>>((const double*)scratch, kRedBlocks, dev_state + MRF_STATE_MU + f, (double)n);
+    rc = check_launch("front/mu");
+  }
+  if (rc) return rc;
+  // pv and the candidate ratios of :209-219 with B_fwd = 1 (build_cost_volume.py:116-131)
+  cudaError_t e = cudaMemsetAsync(count, 0, sizeof(int), S(stream));
+  if (e != cudaSuccess) return fail((int)e, "front: %s", cudaGetErrorString(e));
+  k_structure_candidates<<<g, 256, 0, S(stream)>>>(par0, par1, rigid_mask, p->rows, p->w, 0, pt2(p->q0), pt2(p->q1), 0.0,
+                                                   0.0, 1.0, 2, nullptr, cand, count, dev_state);
+  rc = check_launch("front/candidates");
+  if (rc) return rc;
+  rc = mrf_select_median_dev(cand, count, (size_t)n, dev_state + MRF_STATE_B, (char*)scratch + 4096 * sizeof(double), stream);
+  if (rc) return rc;
+  k_set_f64<<<1, 1, 0, S(stream)>>>(dev_state + MRF_STATE_B + 1, p->B_fwd);
+  rc = check_launch("front/B_fwd");
+  if (rc) return rc;
+  for (int f = 0; f < 2 && !rc; ++f) {
+    k_parallax_to_structure<<<g, 256, 0, S(stream)>>>(par[f], p->rows, p->w, 0, pt2(qq[f]), 0.0, 0.0, Ss[f], dev_state, f);
+    rc = check_launch("front/structure");
+    if (rc) break;
+    rc = mrf_masked_minmax_f64(Ss[f], zero_mask, p->rows, p->w, 0, p->have_box[f] ? p->box[f] : nullptr,
+                               dev_state + MRF_STATE_MINMAX + 2 * f, scratch, stream);
+  }
+  if (rc) return rc;
+  return mrf_label_range_dev(dev_state, p->n_labels, stream);
 }
 
 }  // extern "C"

@@ -33,16 +33,20 @@ __device__ __forceinline__ double key_value(unsigned long long k) {
 }
 
 __global__ void __launch_bounds__(256)
-k_select_init(unsigned long long* st, unsigned long long k, unsigned long long* hist) {
+k_select_init(unsigned long long* st, unsigned long long k, unsigned long long* hist, const int* n_dev) {
   if (threadIdx.x < kStWords) st[threadIdx.x] = 0;
   __syncthreads();
-  if (threadIdx.x == 0) { st[2] = k; st[5] = 0xFFFFFFFFFFFFFFFFull; }
+  if (threadIdx.x == 0) {
+    if (n_dev) { const int n = *n_dev; k = n > 0 ? (unsigned long long)((n - 1) / 2) : 0ull; st[6] = (unsigned long long)(n > 0 ? n : 0); }
+    st[2] = k; st[5] = 0xFFFFFFFFFFFFFFFFull;
+  }
   hist[threadIdx.x] = 0;
 }
 
 __global__ void __launch_bounds__(256)
 k_select_hist(const double* __restrict__ keys, size_t n, const unsigned long long* __restrict__ st,
-              unsigned long long* __restrict__ hist) {
+              unsigned long long* __restrict__ hist, const int* __restrict__ n_dev) {
+  if (n_dev) n = (size_t)max(*n_dev, 0);
   __shared__ unsigned int sh[kHistBins];
   sh[threadIdx.x] = 0;
   __syncthreads();
@@ -124,7 +128,9 @@ k_select_pick(unsigned long long* st, unsigned long long* hist) {
 
 // after the 8th pass st[0] is the k-th key: count keys <= it, the smallest key above it, and NaNs
 __global__ void __launch_bounds__(256)
-k_select_successor(const double* __restrict__ keys, size_t n, unsigned long long* __restrict__ st) {
+k_select_successor(const double* __restrict__ keys, size_t n, unsigned long long* __restrict__ st,
+                   const int* __restrict__ n_dev) {
+  if (n_dev) n = (size_t)max(*n_dev, 0);
   const unsigned long long kth = st[0];
   unsigned long long cnt_le = 0, nan = 0, min_gt = 0xFFFFFFFFFFFFFFFFull;
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
@@ -153,6 +159,39 @@ __global__ void k_select_result(const unsigned long long* __restrict__ st, unsig
   out3[0] = key_value(kth);
   out3[1] = (st[4] >= k_orig + 2) ? key_value(kth) : key_value(st[5]);
   out3[2] = (double)st[3];
+}
+
+// numpy.median from the finished selection state (n in st[6]): middle element, mean of the two
+// middles for even n, NaN if any key is NaN or n == 0
+__global__ void k_select_median(const unsigned long long* __restrict__ st, double* __restrict__ out) {
+  const unsigned long long n = st[6], k = n ? (n - 1) / 2 : 0;
+  const double qnan = __longlong_as_double(0x7FF8000000000000ll);
+  const double a = key_value(st[0]);
+  const double b = (st[4] >= k + 2) ? a : key_value(st[5]);
+  double m = (n % 2 == 1) ? a : (0.0 + a + b) / 2.0;
+  if (n == 0 || st[3] != 0) m = qnan;
+  out[0] = m;
+}
+
+// np.linspace(1.5*min, 1.5*max, L) over both frames' (min, max) in the state
+// (pipeline/build_cost_volume.py:190-192; numpy/_core/function_base.py: step = delta/div,
+// y = arange*step + start, or arange/div*delta + start when step == 0, last element = stop)
+__global__ void k_label_range(double* __restrict__ st, int L) {
+  const int i = threadIdx.x;
+  if (i >= L) return;
+  const double lo0 = st[MRF_STATE_MINMAX], hi0 = st[MRF_STATE_MINMAX + 1];
+  const double lo1 = st[MRF_STATE_MINMAX + 2], hi1 = st[MRF_STATE_MINMAX + 3];
+  const bool nan = (lo0 != lo0) || (lo1 != lo1) || (hi0 != hi0) || (hi1 != hi1);
+  const double qnan = __longlong_as_double(0x7FF8000000000000ll);
+  const double start = nan ? qnan : 1.5 * fmin(lo0, lo1);
+  const double stop = nan ? qnan : 1.5 * fmax(hi0, hi1);
+  const double div = (double)(L - 1);
+  const double delta = stop - start;
+  const double step = delta / div;
+  double y = (step == 0.0) ? ((double)i / div) * delta : (double)i * step;
+  y = y + start;
+  if (i == L - 1) y = stop;
+  st[MRF_STATE_LABELS + i] = y;
 }
 
 // ------------------------------------------------------------------------------ masked min/max
@@ -230,7 +269,7 @@ size_t mrf_select_scratch_bytes(size_t) { return sizeof(unsigned long long) * (k
 int mrf_select_begin(size_t k, void* scratch, mrf_stream_t stream) {
   MRF_CHECK_ARG(scratch);
   unsigned long long* st = (unsigned long long*)scratch;
-  k_select_init<<<1, 256, 0, S(stream)>>>(st, (unsigned long long)k, st + kStWords);
+  k_select_init<<<1, 256, 0, S(stream)>>>(st, (unsigned long long)k, st + kStWords, nullptr);
   return check_launch("mrf_select_begin");
 }
 
@@ -239,7 +278,7 @@ int mrf_select_hist_f64(const double* keys, size_t n, void* scratch, mrf_stream_
   if (n == 0) return 0;
   unsigned long long* st = (unsigned long long*)scratch;
   const unsigned blocks = (unsigned)((n + 255) / 256 < (size_t)kSelBlocks ? (n + 255) / 256 : kSelBlocks);
-  k_select_hist<<<blocks, 256, 0, S(stream)>>>(keys, n, st, st + kStWords);
+  k_select_hist<<<blocks, 256, 0, S(stream)>>>(keys, n, st, st + kStWords, nullptr);
   return check_launch("mrf_select_hist_f64");
 }
 
@@ -254,7 +293,7 @@ int mrf_select_successor_f64(const double* keys, size_t n, void* scratch, mrf_st
   MRF_CHECK_ARG(scratch && (keys || n == 0));
   if (n == 0) return 0;
   const unsigned blocks = (unsigned)((n + 255) / 256 < (size_t)kSelBlocks ? (n + 255) / 256 : kSelBlocks);
-  k_select_successor<<<blocks, 256, 0, S(stream)>>>(keys, n, (unsigned long long*)scratch);
+  k_select_successor<<<blocks, 256, 0, S(stream)>>>(keys, n, (unsigned long long*)scratch, nullptr);
   return check_launch("mrf_select_successor_f64");
 }
 
@@ -298,6 +337,34 @@ int mrf_select_successor_key_f64(const double* keys, size_t n, unsigned long lon
   const unsigned blocks = (unsigned)((n + 255) / 256 < (size_t)kSelBlocks ? (n + 255) / 256 : kSelBlocks);
   k_select_successor_key<<<blocks, 256, 0, S(stream)>>>(keys, n, kth_key, out3);
   return check_launch("mrf_select_successor_key_f64");
+}
+
+int mrf_select_median_dev(const double* keys, const int* n_dev, size_t capacity, double* out_median, void* scratch,
+                          mrf_stream_t stream) {
+  MRF_CHECK_ARG(keys && n_dev && out_median && scratch && capacity > 0);
+  unsigned long long* st = (unsigned long long*)scratch;
+  const unsigned blocks = (unsigned)((capacity + 255) / 256 < (size_t)kSelBlocks ? (capacity + 255) / 256 : kSelBlocks);
+  k_select_init<<<1, 256, 0, S(stream)>>>(st, 0ull, st + kStWords, n_dev);
+  int rc = check_launch("mrf_select_median_dev/init");
+  for (int pass = 0; pass < 8 && !rc; ++pass) {
+    k_select_hist<<<blocks, 256, 0, S(stream)>>>(keys, capacity, st, st + kStWords, n_dev);
+    rc = check_launch("mrf_select_median_dev/hist");
+    if (rc) break;
+    k_select_pick<<<1, 32, 0, S(stream)>>>(st, st + kStWords);
+    rc = check_launch("mrf_select_median_dev/pick");
+  }
+  if (rc) return rc;
+  k_select_successor<<<blocks, 256, 0, S(stream)>>>(keys, capacity, st, n_dev);
+  rc = check_launch("mrf_select_median_dev/successor");
+  if (rc) return rc;
+  k_select_median<<<1, 1, 0, S(stream)>>>(st, out_median);
+  return check_launch("mrf_select_median_dev/median");
+}
+
+int mrf_label_range_dev(double* dev_state, int n_labels, mrf_stream_t stream) {
+  MRF_CHECK_ARG(dev_state && n_labels >= 2 && n_labels <= 256);
+  k_label_range<<<1, 256, 0, S(stream)>>>(dev_state, n_labels);
+  return check_launch("mrf_label_range_dev");
 }
 
 size_t mrf_minmax_scratch_bytes(void) { return sizeof(double) * 3 * kMMBlocks; }

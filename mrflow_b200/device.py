@@ -83,7 +83,7 @@ def parallax_to_structure(parallax, q, B, mu, y0=0):
 
 
 # ------------------------------------------------------------------------------------ a6
-def structure_to_flow(structure, q, mu, H, b, y0=0, nonrigid=None, init_u=None, init_v=None):
+def structure_to_flow(structure, q, mu, H, b, y0=0, nonrigid=None, init_u=None, init_v=None, state=None, frame=1):
     """pipeline/structure2flow.py:14-38 incl. utils/flow_homography.py:20-37; with ``nonrigid`` also
     the paste of combine_flow_simple (:72-73)."""
     _chk(structure, F64, "structure"); _chk(nonrigid, U8, "nonrigid"); _chk(init_u, F32, "init_u"); _chk(init_v, F32, "init_v")
@@ -91,7 +91,8 @@ def structure_to_flow(structure, q, mu, H, b, y0=0, nonrigid=None, init_u=None, 
     u = torch.empty((rows, w), dtype=F32, device=structure.device)
     v = torch.empty_like(u)
     check(_lib.lib().mrf_structure_to_flow(_p(structure), rows, w, y0, _pt(q), float(mu), _mat(H), float(b),
-                                           _p(nonrigid), _p(init_u), _p(init_v), _p(u), _p(v), _stream()),
+                                           _p(nonrigid), _p(init_u), _p(init_v), _p(u), _p(v), _p(state), int(frame),
+                                           _stream()),
           "mrf_structure_to_flow")
     return u, v
 
@@ -268,18 +269,19 @@ def warp_sample(img, H, xn, yn, interp="cubic", want_mask=True):
 def cost_volume(ref_ch, nb_texels, labels, H, q, mu, B, label_scale=1.0, nonrigid=None, occluded=None,
                 rho="lorentzian", rho_param=1.0, cw=(0.01, 1.0, 1.0), interp="cubic", layout="LHW_F32",
                 i32_scale=1000.0, variant="staged", y0=0, frame_h=None, nb_y0=0, want_cost=True,
-                want_min=True, want_argmin=True, out=None, halo_miss=None, out_ptr=None, plane_stride=0):
+                want_min=True, want_argmin=True, out=None, halo_miss=None, out_ptr=None, plane_stride=0,
+                state=None, frame=1, n_labels=None):
     """Per-label data cost of ONE neighbour frame (the missing extension of
     pipeline/build_cost_volume.py:209-219, defined per SURVEY.md section 8c from
     optimize_structure_single_scale.py:210-302).  ``ref_ch`` fp64 [rows,w,3] reference-frame channels
     (band starting at global row ``y0``), ``nb_texels`` fp32 [nb_rows,w,4] neighbour texels (band starting
     at ``nb_y0``), ``labels`` fp64 [L].  Returns (cost, min_cost fp32 [rows,w], argmin int32 [rows,w])."""
     _chk(ref_ch, F64, "ref_ch"); _chk(nb_texels, F32, "nb_texels"); _chk(labels, F64, "labels")
-    _chk(nonrigid, U8, "nonrigid"); _chk(occluded, U8, "occluded")
+    _chk(nonrigid, U8, "nonrigid"); _chk(occluded, U8, "occluded"); _chk(state, F64, "state")
     rows, w = ref_ch.shape[:2]
     nb_rows = nb_texels.shape[0]
     frame_h = rows if frame_h is None else int(frame_h)
-    Ln = labels.numel()
+    Ln = labels.numel() if labels is not None else int(n_labels)
     dev = ref_ch.device
     p = CostVolParams()
     p.rows, p.w, p.y0, p.frame_h, p.nb_rows, p.nb_y0 = rows, w, int(y0), frame_h, nb_rows, int(nb_y0)
@@ -289,6 +291,7 @@ def cost_volume(ref_ch, nb_texels, labels, H, q, mu, B, label_scale=1.0, nonrigi
     p.cw = dvec(cw)
     p.layout, p.i32_scale, p.variant = LAYOUT[layout], float(i32_scale), VARIANT[variant]
     p.cost_plane_stride = int(plane_stride)
+    p.state_frame = int(frame)
     cost = out
     if out_ptr is not None:
         cost = None                      # raw (possibly peer-mapped) destination
@@ -299,5 +302,50 @@ def cost_volume(ref_ch, nb_texels, labels, H, q, mu, B, label_scale=1.0, nonrigi
     am = torch.empty((rows, w), dtype=I32, device=dev) if want_argmin else None
     dst = C.c_void_p(int(out_ptr)) if out_ptr is not None else _p(cost)
     check(_lib.lib().mrf_cost_volume(C.byref(p), _p(ref_ch), _p(nb_texels), _p(labels), _p(nonrigid), _p(occluded),
-                                     dst, _p(mn), _p(am), _p(halo_miss), _stream()), "mrf_cost_volume")
+                                     dst, _p(mn), _p(am), _p(halo_miss), _p(state), _stream()), "mrf_cost_volume")
     return cost, mn, am
+
+
+# ------------------------------------------------------------------------------------ device-resident pre-pass
+class FrontBuffers:
+    """Reusable HBM buffers of cost_volume_front for one frame size (keeps the step allocation-free
+    so it can be captured in a CUDA graph)."""
+
+    def __init__(self, rows, w, dev="cuda"):
+        L = _lib.lib()
+        n = rows * w
+        self.par = [torch.empty((rows, w), dtype=F64, device=dev) for _ in range(2)]
+        self.S = [torch.empty((rows, w), dtype=F64, device=dev) for _ in range(2)]
+        self.cand = torch.empty(n, dtype=F64, device=dev)
+        self.count = torch.zeros(1, dtype=I32, device=dev)
+        self.state = torch.zeros(_lib.STATE_WORDS, dtype=F64, device=dev)
+        self.scratch = torch.empty(L.mrf_front_scratch_bytes(), dtype=U8, device=dev)
+
+
+def cost_volume_front(flow, rigid_mask, zero_mask, homographies, epipoles, frame_h, buf, n_labels=51, B_fwd=1.0):
+    """pipeline/build_cost_volume.py:78-192 without leaving the device: parallax, mu, B_b, structures,
+    label set; every whole-frame scalar is written to ``buf.state`` (see MRF_STATE_* in the header)."""
+    for f in range(2):
+        _chk(flow[f][0], F32, "u"); _chk(flow[f][1], F32, "v")
+    _chk(rigid_mask, U8, "rigid_mask"); _chk(zero_mask, U8, "zero_mask")
+    rows, w = flow[0][0].shape
+    p = _lib.FrontParams()
+    p.rows, p.w, p.y0, p.frame_h = rows, w, 0, int(frame_h)
+    p.Hinv0 = _mat(np.linalg.inv(np.asarray(homographies[0], dtype=np.float64)))
+    p.Hinv1 = _mat(np.linalg.inv(np.asarray(homographies[1], dtype=np.float64)))
+    p.q0 = _pt(epipoles[0]); p.q1 = _pt(epipoles[1])
+    p.B_fwd = float(B_fwd)
+    p.n_labels = int(n_labels)
+    for f in range(2):
+        q = epipoles[f]
+        bx0 = max(0, min(w - 1, int(q[0] - 10))); bx1 = max(0, min(w - 1, int(q[0] + 10)))
+        by0 = max(0, min(frame_h - 1, int(q[1] - 10))); by1 = max(0, min(frame_h - 1, int(q[1] + 10)))
+        has = not (bx0 == w - 1 or bx1 == 0 or by0 == frame_h - 1 or by1 == 0)      # build_cost_volume.py:162-165
+        p.have_box[f] = int(has)
+        for k, v in enumerate((bx0, bx1, by0, by1)):
+            p.box[f][k] = v
+    check(_lib.lib().mrf_cost_volume_front(C.byref(p), _p(flow[0][0]), _p(flow[0][1]), _p(flow[1][0]), _p(flow[1][1]),
+                                           _p(rigid_mask), _p(zero_mask), _p(buf.par[0]), _p(buf.par[1]), _p(buf.S[0]),
+                                           _p(buf.S[1]), _p(buf.cand), _p(buf.count), _p(buf.state), _p(buf.scratch),
+                                           _stream()), "mrf_cost_volume_front")
+    return buf

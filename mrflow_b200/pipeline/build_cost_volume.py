@@ -39,9 +39,15 @@ def build_cost_volume(images, flow, rigidity, homographies, epipoles, params=Non
     stats = stats or pp.LocalStats()
     rigidity = np.asarray(rigidity)
     band = pp.Band.from_host(images, flow, rigidity, None)
-    out = cost_volume_pass(band, homographies, epipoles, rigidity > 0, stats, rho=rho, sigma=sigma, interp=interp,
-                           range_mask=range_mask, layout=layout, variant=variant)
-    cost, S, mu_ar, B_ar, q_new, labels, mins, argmins = out
+    if isinstance(stats, pp.LocalStats):
+        r = cost_volume_pass_resident(band, homographies, epipoles, flag(rigidity > 0), rho=rho, sigma=sigma,
+                                      interp=interp, range_mask=range_mask, layout=layout, variant=variant)
+        mu_ar, B_ar, labels = pp.state_to_host(r["buffers"].state)
+        cost, S, q_new, mins, argmins = r["cost"], r["buffers"].S, r["q"], r["mins"], r["argmins"]
+    else:
+        out = cost_volume_pass(band, homographies, epipoles, rigidity > 0, stats, rho=rho, sigma=sigma, interp=interp,
+                               range_mask=range_mask, layout=layout, variant=variant)
+        cost, S, mu_ar, B_ar, q_new, labels, mins, argmins = out
     if return_device:
         return [cost, S, mu_ar, B_ar, q_new, labels, (mins, argmins)]
     return [[_down_pinned(cost[0]), _down_pinned(cost[1])], [down(S[0]), down(S[1])], mu_ar, B_ar, q_new, labels]
@@ -74,3 +80,25 @@ def cost_volume_pass(band, homographies, epipoles, rigid_host_mask, stats, rho="
                           plane_stride=plane_stride)
     cost = [res[0][0], res[1][0]]
     return cost, S, fp["mu"], B_ar, fp["q"], labels, [res[0][1], res[1][1]], [res[0][2], res[1][2]]
+
+
+def cost_volume_pass_resident(band, homographies, epipoles, rigid_mask, rho="lorentzian", sigma=1.0, interp="cubic",
+                              range_mask="as_written", layout="LHW_F32", variant="staged", out=(None, None),
+                              want_cost=True, buffers=None, masks=None, events=None, n_labels=N_RANGES):
+    """build_cost_volume for a whole frame on one GPU with no host round trip: the pre-pass leaves mu, B
+    and the label set in HBM (device.cost_volume_front) and the cost-volume kernels read them there.
+    The host is only involved when an epipole lies inside the image (441-pixel BFGS).  Returns a dict
+    (cost, mins, argmins, q, buffers); ``planeparallax.state_to_host(buffers.state)`` fetches mu/B/labels."""
+    q_new = pp.refine_epipoles(band, homographies, epipoles, rigid_mask)
+    buf = buffers or device.FrontBuffers(band.rows, band.w, band.device)
+    if masks is None:
+        nonrigid = (rigid_mask == 0).to(torch.uint8)
+        masks = (nonrigid, rigid_mask if range_mask == "as_written" else nonrigid)
+    nonrigid, zero_mask = masks
+    device.cost_volume_front(band.flow, rigid_mask, zero_mask, homographies, q_new, band.frame_h, buf, n_labels=n_labels)
+    ref64, tex = pp.channels(band)
+    res = pp.cost_volumes(band, ref64, tex, None, homographies, q_new, None, None, nonrigid, rho=rho, rho_param=sigma,
+                          interp=interp, layout=layout, variant=variant, out=out, want_cost=want_cost, events=events,
+                          state=buf.state, n_labels=n_labels)
+    return dict(cost=[res[0][0], res[1][0]], mins=[res[0][1], res[1][1]], argmins=[res[0][2], res[1][2]], q=q_new,
+                buffers=buf)

@@ -249,11 +249,13 @@ def channels(band):
 def cost_volumes(band, ref64, tex, labels_dev, homographies, q_ar, mu_ar, B_ar, nonrigid, occluded=(None, None),
                  rho="lorentzian", rho_param=1.0, interp="cubic", layout="LHW_F32", variant="staged",
                  out=(None, None), want_cost=True, i32_scale=1000.0, halo_miss=None, frames=(0, 1), events=None,
-                 out_ptr=(None, None), plane_stride=0):
+                 out_ptr=(None, None), plane_stride=0, state=None, n_labels=N_LABELS):
     """The per-label data cost of both neighbour frames (see device.cost_volume).  The backward
     frame is evaluated at ``label * mu0/mu1`` with the index-0 parameters
     (optimize_structure_single_scale.py:435-442)."""
     res = [None, None]
+    if state is not None:                      # whole-frame scalars stay on the device
+        mu_ar, B_ar = (0.0, 1.0), (0.0, 0.0)
     for f in frames:
         scale = (mu_ar[0] / mu_ar[1]) if f == 0 else 1.0
         if events is not None:
@@ -264,8 +266,33 @@ def cost_volumes(band, ref64, tex, labels_dev, homographies, q_ar, mu_ar, B_ar, 
                                     rho_param=rho_param, cw=CHANNEL_WEIGHTS, interp=interp, layout=layout,
                                     i32_scale=i32_scale, variant=variant, y0=band.y0, frame_h=band.frame_h,
                                     nb_y0=band.nb_y0, out=out[f], want_cost=want_cost, halo_miss=halo_miss,
-                                    out_ptr=out_ptr[f], plane_stride=plane_stride)
+                                    out_ptr=out_ptr[f], plane_stride=plane_stride, state=state, frame=f,
+                                    n_labels=n_labels)
         if events is not None:
             ev[1].record()
             events.append(ev)
     return res
+
+
+def refine_epipoles(band, homographies, epipoles, rigid_mask):
+    """compute_structure.py:77 for both frames.  Touches the device only when the 21x21 window round an
+    epipole lies inside the image (otherwise correct_epipole returns q unchanged, :476-477)."""
+    out = []
+    for f in range(2):
+        q = np.asarray(epipoles[f], dtype=np.float64)
+        xmin, xmax, ymin, ymax = int(q[0]) - 10, int(q[0]) + 10, int(q[1]) - 10, int(q[1]) + 10
+        if xmin < 0 or xmax >= band.w or ymin < 0 or ymax >= band.frame_h:
+            out.append(q)
+            continue
+        Hinv = np.linalg.inv(np.asarray(homographies[f], dtype=np.float64))
+        ur, vr, _, _ = device.flow_to_parallax(band.flow[f][0], band.flow[f][1], Hinv, q, y0=band.y0,
+                                               want_parallax=False, want_dists=False)
+        out.append(correct_epipole(ur, vr, q, rigid_mask, band.y0, band.frame_h))
+    return out
+
+
+def state_to_host(state, n_labels=N_LABELS):
+    """(mu_array, B_array, labels) from the device state (one synchronising copy)."""
+    s = state.cpu().numpy()
+    return ([float(s[_lib.STATE_MU]), float(s[_lib.STATE_MU + 1])], [float(s[_lib.STATE_B]), float(s[_lib.STATE_B + 1])],
+            s[_lib.STATE_LABELS:_lib.STATE_LABELS + n_labels].copy())

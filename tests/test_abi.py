@@ -27,6 +27,7 @@ def test_library_exports_every_declared_symbol():
     assert L.mrf_version() >= 100
     assert L.mrf_reduce_scratch_bytes() > 0 and L.mrf_select_scratch_bytes(10) > 0
     assert ctypes.sizeof(_lib.CostVolParams) == 216      # sizeof(mrf_costvol_params), checked with gcc
+    assert ctypes.sizeof(_lib.FrontParams) == 248        # sizeof(mrf_front_params)
 
 
 def test_bad_arguments_are_rejected_without_a_gpu():

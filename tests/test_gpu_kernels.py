@@ -451,3 +451,61 @@ def test_full_size_properties(dev, shape, epi):
     S2 = dev.parallax_to_structure(par, q, B, mu).cpu().numpy()
     ok = d > 5
     assert np.abs(S2 - A)[ok].max() < 5e-3
+
+
+@pytest.mark.parametrize("n", [0, 1, 2, 7, 1000, 50001])
+def test_device_side_median_and_label_range(dev, n):
+    """The device-resident statistics of the pre-pass: numpy.median with n read on the device, and
+    numpy.linspace(1.5*min, 1.5*max, L) from the state's min/max."""
+    import ctypes as C
+    import torch
+    from mrflow_b200 import _lib
+    L = _lib.lib()
+    rs = np.random.RandomState(100 + n)
+    cap = max(n, 1) + 13
+    x = rs.standard_normal(cap) * 5
+    if n > 4:
+        x[rs.randint(0, n, n // 4)] = x[0]
+    keys = cu(x)
+    cnt = torch.tensor([n], dtype=torch.int32, device="cuda")
+    out = torch.zeros(1, dtype=torch.float64, device="cuda")
+    scratch = torch.empty(L.mrf_front_scratch_bytes(), dtype=torch.uint8, device="cuda")
+    st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    _lib.check(L.mrf_select_median_dev(C.c_void_p(keys.data_ptr()), C.c_void_p(cnt.data_ptr()), cap,
+                                       C.c_void_p(out.data_ptr()), C.c_void_p(scratch.data_ptr()), st), "median_dev")
+    got = float(out.cpu()[0])
+    if n == 0:
+        assert np.isnan(got)
+    else:
+        assert got == np.median(x[:n])
+    state = torch.zeros(_lib.STATE_WORDS, dtype=torch.float64, device="cuda")
+    lo0, hi0, lo1, hi1 = -0.37 - n, 2.11, -0.2, 3.3 + 0.001 * n
+    state[_lib.STATE_MINMAX:_lib.STATE_MINMAX + 4] = torch.tensor([lo0, hi0, lo1, hi1], dtype=torch.float64)
+    for nl in (51, 7, 2):
+        _lib.check(L.mrf_label_range_dev(C.c_void_p(state.data_ptr()), nl, st), "label_range_dev")
+        lab = state[_lib.STATE_LABELS:_lib.STATE_LABELS + nl].cpu().numpy()
+        assert np.array_equal(lab, np.linspace(1.5 * min(lo0, lo1), 1.5 * max(hi0, hi1), nl))
+    state[_lib.STATE_MINMAX:_lib.STATE_MINMAX + 4] = 0.0          # degenerate range: all labels equal
+    _lib.check(L.mrf_label_range_dev(C.c_void_p(state.data_ptr()), 51, st), "label_range_dev")
+    assert np.array_equal(state[_lib.STATE_LABELS:_lib.STATE_LABELS + 51].cpu().numpy(), np.linspace(0.0, 0.0, 51))
+
+
+def test_resident_pass_equals_host_driven_pass(dev, trip):
+    """cost_volume_pass_resident (scalars stay in HBM) against cost_volume_pass (scalars via the host):
+    same kernels, so mu, B, labels, structures and both volumes must agree bit for bit."""
+    import torch
+    from mrflow_b200 import planeparallax as pp
+    from mrflow_b200.pipeline import build_cost_volume as bcv
+    t = trip
+    rig = t["rigidity"].copy(); rig[5:20, 60:80] = 0.0
+    band = pp.Band.from_host(t["images"], t["flow"], rig, None)
+    mask = cu((rig > 0).astype(np.uint8))
+    for mode in ("as_written", "rigid_only"):
+        a = bcv.cost_volume_pass(band, t["homographies"], t["epipoles"], mask, pp.LocalStats(), range_mask=mode)
+        r = bcv.cost_volume_pass_resident(band, t["homographies"], t["epipoles"], mask, range_mask=mode)
+        mu, B, labels = pp.state_to_host(r["buffers"].state)
+        assert mu == list(a[2]) and B == list(a[3]) and np.array_equal(labels, a[5])
+        for f in range(2):
+            assert np.array_equal(r["q"][f], a[4][f])
+            assert torch.equal(r["buffers"].S[f], a[1][f]) or eq(r["buffers"].S[f].cpu(), a[1][f].cpu())
+            assert torch.equal(r["cost"][f], a[0][f]) and torch.equal(r["argmins"][f], a[7][f])

@@ -540,8 +540,12 @@ extern "C" int mrf_cost_volume(const mrf_costvol_params* p, const double* ref_ch
   cudaError_t e = cudaSuccess;
 #define MRF_LAUNCH(I, ST, OC, LY)                                                                         \
   do {                                                                                                    \
-    if (smem) e = cudaFuncSetAttribute(k_cost_volume<I, ST, OC, LY>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
-                                       (int)smem);                                                        \
+    static bool attr_set = false;   /* once per instantiation (and never inside a stream capture) */     \
+    if (smem && !attr_set) {                                                                              \
+      e = cudaFuncSetAttribute(k_cost_volume<I, ST, OC, LY>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                               (int)smem);                                                                \
+      attr_set = (e == cudaSuccess);                                                                      \
+    }                                                                                                     \
     if (e == cudaSuccess) k_cost_volume<I, ST, OC, LY><<<grid, kThreads, smem, S(stream)>>>(a);           \
   } while (0)
 #define MRF_LAUNCH_LY(I, ST, OC) do { if (p->layout == MRF_LAYOUT_LHW_F32) MRF_LAUNCH(I, ST, OC, MRF_LAYOUT_LHW_F32); else MRF_LAUNCH(I, ST, OC, MRF_LAYOUT_HWL_I32); } while (0)

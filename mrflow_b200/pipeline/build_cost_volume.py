@@ -102,3 +102,66 @@ def cost_volume_pass_resident(band, homographies, epipoles, rigid_mask, rho="lor
                           state=buf.state, n_labels=n_labels)
     return dict(cost=[res[0][0], res[1][0]], mins=[res[0][1], res[1][1]], argmins=[res[0][2], res[1][2]], q=q_new,
                 buffers=buf)
+
+
+class ResidentStep:
+    """One triplet resident in HBM, stepped repeatedly (dataset runs, benchmarks): the pre-pass and the
+    channel construction -- some forty short launches -- are captured once in a CUDA graph and replayed
+    with a single launch; the two cost-volume launches and structure -> flow follow on the same stream.
+    Buffers are allocated once.  Falls back to eager launches if an epipole needs the host (BFGS) or the
+    capture fails."""
+
+    def __init__(self, band, homographies, epipoles, rigid_mask, rho="lorentzian", sigma=1.0, interp="cubic",
+                 range_mask="as_written", variant="staged", n_labels=N_RANGES, use_graph=True):
+        self.band, self.H = band, homographies
+        self.kw = dict(rho=rho, rho_param=sigma, interp=interp, variant=variant)
+        self.n_labels = n_labels
+        self.rigid_mask = rigid_mask
+        self.nonrigid = (rigid_mask == 0).to(torch.uint8)
+        self.zero_mask = rigid_mask if range_mask == "as_written" else self.nonrigid
+        self.q = pp.refine_epipoles(band, homographies, epipoles, rigid_mask)
+        self.buf = device.FrontBuffers(band.rows, band.w, band.device)
+        L, rows, w = n_labels, band.rows, band.w
+        self.cost = (torch.empty((L, rows, w), dtype=torch.float32, device=band.device),
+                     torch.empty((L, rows, w), dtype=torch.float32, device=band.device))
+        self.graph = None
+        self.launches_in_graph = 0
+        self._front()                                        # warm up (and allocate) outside any capture
+        torch.cuda.synchronize()
+        if use_graph:
+            try:
+                side = torch.cuda.Stream()
+                side.wait_stream(torch.cuda.current_stream())
+                with torch.cuda.stream(side):
+                    self._front()
+                torch.cuda.current_stream().wait_stream(side)
+                torch.cuda.synchronize()
+                g = torch.cuda.CUDAGraph()
+                n0 = device.launch_count()
+                with torch.cuda.graph(g):
+                    self._front()
+                self.launches_in_graph = device.launch_count() - n0
+                self.graph = g
+            except Exception as e:                           # noqa: BLE001
+                print("(WW) CUDA graph capture failed, running eagerly: %s" % e)
+                self.graph = None
+                torch.cuda.synchronize()
+
+    def _front(self):
+        device.cost_volume_front(self.band.flow, self.rigid_mask, self.zero_mask, self.H, self.q, self.band.frame_h,
+                                 self.buf, n_labels=self.n_labels)
+        self.ref64, self.tex = pp.channels(self.band)
+
+    def run(self, events=None):
+        """One step.  Returns (min costs, argmin labels, u, v) as device tensors; the volumes are in
+        ``self.cost`` and mu / B / labels in ``self.buf.state``."""
+        if self.graph is not None:
+            self.graph.replay()
+        else:
+            self._front()
+        res = pp.cost_volumes(self.band, self.ref64, self.tex, None, self.H, self.q, None, None, self.nonrigid,
+                              out=self.cost, events=events, state=self.buf.state, n_labels=self.n_labels, **self.kw)
+        u, v = device.structure_to_flow(self.buf.S[1], self.q[1], 0.0, self.H[1], 0.0, nonrigid=self.nonrigid,
+                                        init_u=self.band.flow[1][0], init_v=self.band.flow[1][1], state=self.buf.state,
+                                        frame=1)
+        return [res[0][1], res[1][1]], [res[0][2], res[1][2]], u, v

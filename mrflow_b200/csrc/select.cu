@@ -161,6 +161,110 @@ __global__ void k_select_result(const unsigned long long* __restrict__ st, unsig
   out3[2] = (double)st[3];
 }
 
+// Device-median path: one launch per pass.  Every block first resolves the previous pass's byte from
+// that pass's (complete) histogram -- 256 bins, a few hundred cycles, redundantly in every block --
+// then histograms the next byte; hist is [8][256], zeroed up front.  Block 0 records the running
+// prefix / rank in the state for the final pass.
+__device__ __forceinline__ void resolve_prefix(const unsigned long long* __restrict__ hist_all, int upto,
+                                               unsigned long long k, unsigned long long& prefix,
+                                               unsigned long long& k_rem) {
+  // serial over passes, warp-parallel over bins (executed by warp 0 of the block)
+  const int lane = threadIdx.x & 31;
+  prefix = 0; k_rem = k;
+  for (int p = 0; p < upto; ++p) {
+    const unsigned long long* h = hist_all + p * kHistBins;
+    // each lane owns 8 consecutive bins
+    unsigned long long c[8], tot = 0;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { c[j] = h[lane * 8 + j]; tot += c[j]; }
+    unsigned long long incl = tot;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const unsigned long long v = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += v;
+    }
+    const unsigned long long excl = incl - tot;
+    // the lane whose range [excl, incl) holds k_rem (last lane catches any remainder)
+    const bool mine = (k_rem >= excl && k_rem < incl) || (lane == 31 && k_rem >= incl);
+    const unsigned ball = __ballot_sync(0xffffffffu, mine);
+    const int owner = ball ? (__ffs(ball) - 1) : 31;
+    int b = 0; unsigned long long kr = 0;
+    if (lane == owner) {
+      kr = k_rem - excl;
+      for (b = 0; b < 7; ++b) { if (kr < c[b]) break; kr -= c[b]; }
+      b += lane * 8;
+    }
+    b = __shfl_sync(0xffffffffu, b, owner);
+    kr = __shfl_sync(0xffffffffu, kr, owner);
+    prefix |= ((unsigned long long)b) << (56 - 8 * p);
+    k_rem = kr;
+  }
+}
+
+__global__ void __launch_bounds__(256)
+k_select_hist_fused(const double* __restrict__ keys, const int* __restrict__ n_dev, int pass,
+                    unsigned long long* __restrict__ st, unsigned long long* __restrict__ hist_all) {
+  __shared__ unsigned int sh[kHistBins];
+  __shared__ unsigned long long s_prefix;
+  const size_t n = (size_t)max(*n_dev, 0);
+  sh[threadIdx.x] = 0;
+  if (threadIdx.x < 32) {
+    unsigned long long prefix, k_rem;
+    resolve_prefix(hist_all, pass, n ? (unsigned long long)((n - 1) / 2) : 0ull, prefix, k_rem);
+    if (threadIdx.x == 0) s_prefix = prefix;
+  }
+  __syncthreads();
+  const unsigned long long prefix = s_prefix;
+  const int shift = 56 - 8 * pass;
+  const unsigned long long himask = pass == 0 ? 0ull : (~0ull << (shift + 8));
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const unsigned long long k = order_key(keys[i]);
+    if ((k & himask) == prefix) atomicAdd(&sh[(k >> shift) & 0xFF], 1u);
+  }
+  __syncthreads();
+  const unsigned int c = sh[threadIdx.x];
+  if (c) atomicAdd(&hist_all[pass * kHistBins + threadIdx.x], (unsigned long long)c);
+}
+
+// successor pass: resolves the last byte, then counts keys <= kth / NaNs / min key above
+__global__ void __launch_bounds__(256)
+k_select_successor_fused(const double* __restrict__ keys, const int* __restrict__ n_dev,
+                         unsigned long long* __restrict__ st, const unsigned long long* __restrict__ hist_all) {
+  __shared__ unsigned long long s_kth;
+  const size_t n = (size_t)max(*n_dev, 0);
+  if (threadIdx.x < 32) {
+    unsigned long long prefix, k_rem;
+    resolve_prefix(hist_all, 8, n ? (unsigned long long)((n - 1) / 2) : 0ull, prefix, k_rem);
+    if (threadIdx.x == 0) { s_kth = prefix; if (blockIdx.x == 0) { st[0] = prefix; st[6] = (unsigned long long)n; } }
+  }
+  __syncthreads();
+  const unsigned long long kth = s_kth;
+  unsigned long long cnt_le = 0, nan = 0, min_gt = 0xFFFFFFFFFFFFFFFFull;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const double v = keys[i];
+    const unsigned long long k = order_key(v);
+    if (v != v) ++nan;
+    if (k <= kth) ++cnt_le; else if (k < min_gt) min_gt = k;
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    cnt_le += __shfl_down_sync(0xffffffffu, cnt_le, o);
+    nan += __shfl_down_sync(0xffffffffu, nan, o);
+    const unsigned long long m = __shfl_down_sync(0xffffffffu, min_gt, o);
+    min_gt = m < min_gt ? m : min_gt;
+  }
+  if ((threadIdx.x & 31) == 0) {
+    if (cnt_le) atomicAdd(&st[4], cnt_le);
+    if (nan) atomicAdd(&st[3], nan);
+    if (min_gt != 0xFFFFFFFFFFFFFFFFull) atomicMin(&st[5], min_gt);
+  }
+}
+
+__global__ void __launch_bounds__(256)
+k_select_init_fused(unsigned long long* st, unsigned long long* hist_all) {
+  if (threadIdx.x < kStWords) st[threadIdx.x] = (threadIdx.x == 5) ? 0xFFFFFFFFFFFFFFFFull : 0ull;
+  for (int i = threadIdx.x; i < 8 * kHistBins; i += blockDim.x) hist_all[i] = 0;
+}
+
 // numpy.median from the finished selection state (n in st[6]): middle element, mean of the two
 // middles for even n, NaN if any key is NaN or n == 0
 __global__ void k_select_median(const unsigned long long* __restrict__ st, double* __restrict__ out) {
@@ -264,7 +368,7 @@ using namespace mrf;
 
 extern "C" {
 
-size_t mrf_select_scratch_bytes(size_t) { return sizeof(unsigned long long) * (kStWords + kHistBins); }
+size_t mrf_select_scratch_bytes(size_t) { return sizeof(unsigned long long) * (kStWords + 8 * kHistBins); }
 
 int mrf_select_begin(size_t k, void* scratch, mrf_stream_t stream) {
   MRF_CHECK_ARG(scratch);
@@ -343,18 +447,16 @@ int mrf_select_median_dev(const double* keys, const int* n_dev, size_t capacity,
                           mrf_stream_t stream) {
   MRF_CHECK_ARG(keys && n_dev && out_median && scratch && capacity > 0);
   unsigned long long* st = (unsigned long long*)scratch;
+  unsigned long long* hist_all = st + kStWords;              // [8][256]
   const unsigned blocks = (unsigned)((capacity + 255) / 256 < (size_t)kSelBlocks ? (capacity + 255) / 256 : kSelBlocks);
-  k_select_init<<<1, 256, 0, S(stream)>>>(st, 0ull, st + kStWords, n_dev);
+  k_select_init_fused<<<1, 256, 0, S(stream)>>>(st, hist_all);
   int rc = check_launch("mrf_select_median_dev/init");
   for (int pass = 0; pass < 8 && !rc; ++pass) {
-    k_select_hist<<<blocks, 256, 0, S(stream)>>>(keys, capacity, st, st + kStWords, n_dev);
+    k_select_hist_fused<<<blocks, 256, 0, S(stream)>>>(keys, n_dev, pass, st, hist_all);
     rc = check_launch("mrf_select_median_dev/hist");
-    if (rc) break;
-    k_select_pick<<<1, 32, 0, S(stream)>>>(st, st + kStWords);
-    rc = check_launch("mrf_select_median_dev/pick");
   }
   if (rc) return rc;
-  k_select_successor<<<blocks, 256, 0, S(stream)>>>(keys, capacity, st, n_dev);
+  k_select_successor_fused<<<blocks, 256, 0, S(stream)>>>(keys, n_dev, st, hist_all);
   rc = check_launch("mrf_select_median_dev/successor");
   if (rc) return rc;
   k_select_median<<<1, 1, 0, S(stream)>>>(st, out_median);

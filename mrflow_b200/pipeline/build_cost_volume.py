@@ -126,6 +126,7 @@ class ResidentStep:
                      torch.empty((L, rows, w), dtype=torch.float32, device=band.device))
         self.graph = None
         self.launches_in_graph = 0
+        self._side = torch.cuda.Stream()
         self._front()                                        # warm up (and allocate) outside any capture
         torch.cuda.synchronize()
         if use_graph:
@@ -148,9 +149,16 @@ class ResidentStep:
                 torch.cuda.synchronize()
 
     def _front(self):
+        # channel construction is independent of the structure pre-pass: fork it onto a side stream
+        # (inside a capture this becomes a parallel branch of the graph)
+        main = torch.cuda.current_stream()
+        side = self._side
+        side.wait_stream(main)
+        with torch.cuda.stream(side):
+            self.ref64, self.tex = pp.channels(self.band)
         device.cost_volume_front(self.band.flow, self.rigid_mask, self.zero_mask, self.H, self.q, self.band.frame_h,
                                  self.buf, n_labels=self.n_labels)
-        self.ref64, self.tex = pp.channels(self.band)
+        main.wait_stream(side)
 
     def run(self, events=None):
         """One step.  Returns (min costs, argmin labels, u, v) as device tensors; the volumes are in

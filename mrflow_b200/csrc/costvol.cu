@@ -252,6 +252,7 @@ k_cost_volume(const __grid_constant__ CVArgs a) {
   __shared__ LabelRec s_lab[kMaxLabels];    // A*B, B*A/mu - 1, RN(1/that), exact-sequence-safe flag
   __shared__ __align__(16) float4 s_wt[32]; // OpenCV's interpolation table: weights at frac/32
   __shared__ double s_c[2];                 // min / max over labels of A*B / (B*A/mu - 1)
+  __shared__ double s_ref[3][kThreads];     // this thread's reference-frame channels (register relief)
   __shared__ float s_red[kTY][4];
   __shared__ int s_win[4];                  // wx0, wy0, ww, wh
   __shared__ __align__(8) uint64_t s_bar;
@@ -320,6 +321,7 @@ k_cost_volume(const __grid_constant__ CVArgs a) {
     if (a.occluded && a.occluded[pix]) dead = true;    // Iz[occlusions==1] = 0 :285
     c0 = a.ref_ch[3 * pix]; c1 = a.ref_ch[3 * pix + 1]; c2 = a.ref_ch[3 * pix + 2];
   }
+  s_ref[0][threadIdx.x] = c0; s_ref[1][threadIdx.x] = c1; s_ref[2][threadIdx.x] = c2;   // read back by the owner only
 
   int wx0 = 0, wy0 = 0, ww = 0, wh = 0;
   if (STAGED) {
@@ -391,10 +393,13 @@ k_cost_volume(const __grid_constant__ CVArgs a) {
   uint32_t win_s = smem_u32(dyn_smem) - (uint32_t)(wy0 * ww + wx0) * 16u;   // address of texel (0, 0)
   uint32_t wt_s = smem_u32(s_wt);
   uint32_t lab_s = smem_u32(s_lab);
+  uint32_t ref_s = smem_u32(&s_ref[0][threadIdx.x]);
   const uint32_t pitch = (uint32_t)ww * 16u;
   // keep the shared-window addresses in registers (the compiler would otherwise rebuild them from
   // the CTA id on every iteration)
-  asm volatile("" : "+r"(win_s), "+r"(wt_s), "+r"(lab_s));
+  asm volatile("" : "+r"(win_s), "+r"(wt_s), "+r"(lab_s), "+r"(ref_s));
+  double xk = xd, yk = yd;                                  // pinned copies: not rebuilt from the thread id
+  asm volatile("" : "+d"(xk), "+d"(yk));
   const float cost_dead = (float)rho_eval(a.rho, 0.0, a.rho_param);
   const bool lor_fast = (a.rho == MRF_RHO_LORENTZIAN) && tame(a.s2);
   const double n_ok = ((n == 0.0) || tame(n)) ? 1.0 : 0.0;
@@ -413,7 +418,7 @@ k_cost_volume(const __grid_constant__ CVArgs a) {
       asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(rdl), "=d"(safe) : "r"(lab_s + (uint32_t)l * 32u + 16u));
       // r = A*B*n / (B*A/mu - 1)  :221
       const double r = div_rc(ab * n, dl, rdl);
-      const double xn = xd + r * t1, yn = yd + r * t2;      // :224-235
+      const double xn = xk + r * t1, yn = yk + r * t2;      // :224-235
       // interpolate_through_H.py:31-35
       const double den = (xn * a.H.m[6] + yn * a.H.m[7]) + a.H.m[8];
       const double Xn = (xn * a.H.m[0] + yn * a.H.m[1]) + a.H.m[2];
@@ -425,7 +430,8 @@ k_cost_volume(const __grid_constant__ CVArgs a) {
       const bool exact = (safe * n_ok != 0.0) && tame_divisor(den);
       const bool inside = (X >= 0.0) && (X <= a.wm1) && (Y >= 0.0) && (Y <= a.hm1);   // :39
       if (!exact) {
-        cf = slow_sample_cost<INTERP>(a, ab, dl, n, xd, yd, t1, t2, c0, c1, c2);
+        cf = slow_sample_cost<INTERP>(a, ab, dl, n, xk, yk, t1, t2, s_ref[0][threadIdx.x], s_ref[1][threadIdx.x],
+                                      s_ref[2][threadIdx.x]);
       } else if (inside) {
         const float xf = (float)X, yf = (float)Y;           // interpolation.py:77-78
         // cv2.remap's quantisation; inside the frame |coord*32| < 2^31 and the int16 saturation
@@ -472,9 +478,13 @@ k_cost_volume(const __grid_constant__ CVArgs a) {
             J = sample_band<INTERP>(a.nb, a.w, a.nb_y0, a.frame_h, xf, yf);
           }
         }
-        const double e0 = ((double)J.x - c0) * a.cw0;       // :274
-        const double e1 = ((double)J.y - c1) * a.cw1;
-        const double e2 = ((double)J.z - c2) * a.cw2;
+        double r0, r1, r2;                                  // reference-frame channels of this pixel
+        asm volatile("ld.shared.f64 %0, [%1];" : "=d"(r0) : "r"(ref_s));
+        asm volatile("ld.shared.f64 %0, [%1];" : "=d"(r1) : "r"(ref_s + (uint32_t)(kThreads * 8)));
+        asm volatile("ld.shared.f64 %0, [%1];" : "=d"(r2) : "r"(ref_s + (uint32_t)(kThreads * 16)));
+        const double e0 = ((double)J.x - r0) * a.cw0;       // :274
+        const double e1 = ((double)J.y - r1) * a.cw1;
+        const double e2 = ((double)J.z - r2) * a.cw2;
         const double Iz = div_rc((e0 + e1) + e2, 3.0, kThird);   // .mean(axis=2): sum / 3.0, exact
         double cst;
         if (lor_fast) {

@@ -29,7 +29,7 @@ def pytest_collection_modifyitems(config, items):
             it.add_marker(skip)
 
 
-@pytest.fixture(scope="session", params=["outside", "inside"])
+@pytest.fixture(scope="session", params=["outside", "inside", "example"])
 def golden(request):
     return request.param, dict(np.load(os.path.join(GOLDEN, "ref_%s.npz" % request.param)))
 
@@ -37,5 +37,11 @@ def golden(request):
 def golden_triplet(tag):
     from mrflow_b200 import synth
     kw = dict(outside=dict(shape=(72, 96), seed=7, epipole="outside", flow_noise=0.02),
-              inside=dict(shape=(72, 96), seed=8, epipole="inside", moving_objects=True))[tag]
-    return synth.make_triplet(n_waves=8, **kw)
+              inside=dict(shape=(72, 96), seed=8, epipole="inside", moving_objects=True),
+              example=dict(shape=(72, 96), seed=9, epipole="outside", flow_noise=0.05))[tag]
+    t = synth.make_triplet(n_waves=8, **kw)
+    if tag == "example":
+        # crops of the reference's example/frame1-3.png, stored in the fixture by make_golden.py
+        g = np.load(os.path.join(GOLDEN, "ref_example.npz"))
+        t["images"] = [g["images"][i] for i in range(3)]
+    return t

@@ -63,8 +63,15 @@ def main():
     import argparse
 
     for tag, kw in (("outside", dict(shape=(72, 96), seed=7, epipole="outside", flow_noise=0.02)),
-                    ("inside", dict(shape=(72, 96), seed=8, epipole="inside", moving_objects=True))):
+                    ("inside", dict(shape=(72, 96), seed=8, epipole="inside", moving_objects=True)),
+                    ("example", dict(shape=(72, 96), seed=9, epipole="outside", flow_noise=0.05))):
         t = synth.make_triplet(n_waves=8, **kw)
+        example_images = None
+        if tag == "example":
+            # BASELINE.json configs[0]: the reference's own example frames (example/frame1-3.png, loaded as
+            # load_data.py:52 does: BGR -> RGB, /255), a 96x72 crop, with synthetic flows
+            example_images = [cv2.imread(REF + "/example/frame%d.png" % i)[164:236, 400:496, ::-1] / 255.0 for i in (1, 2, 3)]
+            t["images"] = example_images
         h, w = t["shape"]
         y, x = np.mgrid[:h, :w]
         out = {}
@@ -155,6 +162,8 @@ def main():
         out["cv_cost_crop"] = planes[:, :, 20:36, 30:62].copy()
         out["cv_argmin"] = planes.argmin(axis=1).astype(np.int32)
         out["cv_min"] = planes.min(axis=1)
+        if example_images is not None:
+            out["images"] = np.stack(example_images)
         np.savez_compressed(os.path.join(HERE, "ref_%s.npz" % tag), **out)
         print(tag, "written:", len(out), "arrays")
 

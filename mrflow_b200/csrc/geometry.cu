@@ -358,6 +358,154 @@ static inline unsigned grid_for(long long n, int threads = 256) {
   return (unsigned)b;
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// Fused forms of the pre-pass for the device-resident path (same per-pixel arithmetic as the
+// kernels above; fewer, fatter launches).
+constexpr int kFrontBlocks = 592;   // 4 x 148
+
+// both frames: residual flow -> parallax (a1 + a2) and the block partial sums behind mu
+__global__ void __launch_bounds__(256)
+k_front_parallax(const float* __restrict__ u0, const float* __restrict__ v0, const float* __restrict__ u1,
+                 const float* __restrict__ v1, int rows, int w, Mat3 Hinv0, Mat3 Hinv1, Pt2 q0, Pt2 q1,
+                 double* __restrict__ par0, double* __restrict__ par1, double* __restrict__ partial) {
+  __shared__ double sh[32];
+  const long long n = (long long)rows * w;
+  double acc0 = 0.0, acc1 = 0.0;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int y = (int)(i / w);
+    const int x = (int)(i - (long long)y * w);
+#pragma unroll
+    for (int f = 0; f < 2; ++f) {
+      const float* u = f ? u1 : u0; const float* v = f ? v1 : v0;
+      const Mat3& Hinv = f ? Hinv1 : Hinv0; const Pt2 q = f ? q1 : q0;
+      const float x2 = (float)((double)x + (double)u[i]);
+      const float y2 = (float)((double)y + (double)v[i]);
+      float X, Y;
+      persp_f32(x2, y2, Hinv, X, Y);
+      const float ur = X - (float)x, vr = Y - (float)y;
+      const double fx = q.x - (double)x, fy = q.y - (double)y;
+      const double d = sqrt(fx * fx + fy * fy);
+      const double dn = fmax(d, 1e-3);
+      (f ? par1 : par0)[i] = (double)ur * (fx / dn) + (double)vr * (fy / dn);
+      if (f) acc1 += d; else acc0 += d;
+    }
+  }
+  acc0 = block_sum(acc0, sh);
+  acc1 = block_sum(acc1, sh);
+  if (threadIdx.x == 0) { partial[blockIdx.x] = acc0; partial[gridDim.x + blockIdx.x] = acc1; }
+}
+
+__global__ void __launch_bounds__(1024)
+k_front_mu(const double* __restrict__ partial, int nblocks, double n_px, double* __restrict__ st) {
+  __shared__ double sh[32];
+  for (int f = 0; f < 2; ++f) {
+    double v = (threadIdx.x < nblocks) ? partial[f * nblocks + threadIdx.x] : 0.0;
+    v = block_sum(v, sh);
+    if (threadIdx.x == 0) st[MRF_STATE_MU + f] = v / n_px;
+  }
+}
+
+// both frames: parallax -> normed structure (a3) and block partial min / max / NaN of the
+// range-masked structure (build_cost_volume.py:154-169)
+struct Box4 { int x0, x1, y0, y1, on; };
+__global__ void __launch_bounds__(256)
+k_front_structures(const double* __restrict__ par0, const double* __restrict__ par1, int rows, int w, Pt2 q0,
+                   Pt2 q1, double B_fwd, const uint8_t* __restrict__ zero_mask, Box4 b0, Box4 b1,
+                   double* __restrict__ S0, double* __restrict__ S1, double* __restrict__ st,
+                   double* __restrict__ part) {
+  __shared__ double smin[2][8], smax[2][8];
+  __shared__ int snan[2][8];
+  const long long n = (long long)rows * w;
+  const double mu0 = st[MRF_STATE_MU], mu1 = st[MRF_STATE_MU + 1], B0 = st[MRF_STATE_B];
+  if (blockIdx.x == 0 && threadIdx.x == 0) st[MRF_STATE_B + 1] = B_fwd;
+  double lo[2] = {INFINITY, INFINITY}, hi[2] = {-INFINITY, -INFINITY};
+  int nan[2] = {0, 0};
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int y = (int)(i / w);
+    const int x = (int)(i - (long long)y * w);
+    const bool zm = zero_mask && zero_mask[i];
+#pragma unroll
+    for (int f = 0; f < 2; ++f) {
+      const Pt2 q = f ? q1 : q0; const double B = f ? B_fwd : B0; const double mu = f ? mu1 : mu0;
+      const Box4& b = f ? b1 : b0;
+      const double dx = (double)x - q.x, dy = (double)y - q.y;
+      const double dst = sqrt(dx * dx + dy * dy);
+      const double p = (f ? par1 : par0)[i];
+      double v = p / (B * (p / mu - dst / mu));
+      (f ? S1 : S0)[i] = v;
+      if (zm) v = 0.0;
+      if (b.on && x >= b.x0 && x < b.x1 && y >= b.y0 && y < b.y1) v = 0.0;
+      if (v != v) nan[f] = 1;
+      lo[f] = fmin(lo[f], v); hi[f] = fmax(hi[f], v);
+    }
+  }
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+  for (int f = 0; f < 2; ++f) {
+    for (int o = 16; o > 0; o >>= 1) {
+      lo[f] = fmin(lo[f], __shfl_down_sync(0xffffffffu, lo[f], o));
+      hi[f] = fmax(hi[f], __shfl_down_sync(0xffffffffu, hi[f], o));
+      nan[f] |= __shfl_down_sync(0xffffffffu, nan[f], o);
+    }
+    if (lane == 0) { smin[f][wid] = lo[f]; smax[f][wid] = hi[f]; snan[f][wid] = nan[f]; }
+  }
+  __syncthreads();
+  if (threadIdx.x < 2) {
+    const int f = threadIdx.x;
+    double a = smin[f][0], b = smax[f][0]; int c = snan[f][0];
+    for (int k = 1; k < 8; ++k) { a = fmin(a, smin[f][k]); b = fmax(b, smax[f][k]); c |= snan[f][k]; }
+    double* o = part + ((size_t)f * gridDim.x + blockIdx.x) * 3;
+    o[0] = a; o[1] = b; o[2] = (double)c;
+  }
+}
+
+// final min/max of both frames -> state, then np.linspace(1.5*min, 1.5*max, L) (see k_label_range)
+__global__ void __launch_bounds__(256)
+k_front_labels(const double* __restrict__ part, int nblocks, double* __restrict__ st, int L) {
+  __shared__ double smin[8], smax[8];
+  __shared__ int snan[8];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  for (int f = 0; f < 2; ++f) {
+    double lo = INFINITY, hi = -INFINITY; int nan = 0;
+    for (int i = threadIdx.x; i < nblocks; i += blockDim.x) {
+      const double* o = part + ((size_t)f * nblocks + i) * 3;
+      lo = fmin(lo, o[0]); hi = fmax(hi, o[1]); if (o[2] != 0.0) nan = 1;
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+      lo = fmin(lo, __shfl_down_sync(0xffffffffu, lo, o));
+      hi = fmax(hi, __shfl_down_sync(0xffffffffu, hi, o));
+      nan |= __shfl_down_sync(0xffffffffu, nan, o);
+    }
+    if (lane == 0) { smin[wid] = lo; smax[wid] = hi; snan[wid] = nan; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      for (int k = 1; k < 8; ++k) { lo = fmin(lo, smin[k]); hi = fmax(hi, smax[k]); nan |= snan[k]; }
+      const double qnan = __longlong_as_double(0x7FF8000000000000ll);
+      st[MRF_STATE_MINMAX + 2 * f] = nan ? qnan : lo;
+      st[MRF_STATE_MINMAX + 2 * f + 1] = nan ? qnan : hi;
+    }
+    __syncthreads();
+  }
+  const int i = threadIdx.x;
+  if (i >= L) return;
+  const double lo0 = st[MRF_STATE_MINMAX], hi0 = st[MRF_STATE_MINMAX + 1];
+  const double lo1 = st[MRF_STATE_MINMAX + 2], hi1 = st[MRF_STATE_MINMAX + 3];
+  const bool nan = (lo0 != lo0) || (lo1 != lo1) || (hi0 != hi0) || (hi1 != hi1);
+  const double qnan = __longlong_as_double(0x7FF8000000000000ll);
+  const double start = nan ? qnan : 1.5 * fmin(lo0, lo1);
+  const double stop = nan ? qnan : 1.5 * fmax(hi0, hi1);
+  const double div = (double)(L - 1);
+  const double delta = stop - start;
+  const double step = delta / div;
+  double yv = (step == 0.0) ? ((double)i / div) * delta : (double)i * step;
+  yv = yv + start;
+  if (i == L - 1) yv = stop;
+  st[MRF_STATE_LABELS + i] = yv;
+}
+
 }  // namespace mrf
 
 using namespace mrf;
@@ -501,46 +649,37 @@ int mrf_cost_volume_front(const mrf_front_params* p, const float* u0, const floa
   MRF_CHECK_ARG(p->n_labels >= 2 && p->n_labels <= 256);
   const long long n = (long long)p->rows * p->w;
   const unsigned g = grid_for(n);
-  const float* uu[2] = {u0, u1};
-  const float* vv[2] = {v0, v1};
-  double* par[2] = {par0, par1};
-  double* Ss[2] = {S0, S1};
-  const double* Hinv[2] = {p->Hinv0, p->Hinv1};
-  const double* qq[2] = {p->q0, p->q1};
-  int rc = 0;
-  for (int f = 0; f < 2 && !rc; ++f) {
-    k_flow_to_parallax<<<g, 256, 0, S(stream)>>>(uu[f], vv[f], p->rows, p->w, 0, mat3(Hinv[f]), pt2(qq[f]), nullptr,
-                                                 nullptr, par[f], nullptr);
-    rc = check_launch("front/flow_to_parallax");
-    if (rc) break;
-    k_dist_sum_partial<<<kRedBlocks, kRedThreads, 0, S(stream)>>>(p->rows, p->w, 0, pt2(qq[f]), (double*)scratch);
-    rc = check_launch("front/dist_sum");
-    if (rc) break;
-    k_sum_final<<<1, kRedBlocks, 0, S(stream)>>>((const double*)scratch, kRedBlocks, dev_state + MRF_STATE_MU + f, (double)n);
-    rc = check_launch("front/mu");
-  }
+  long long fb = (n + 255) / 256;
+  if (fb > kFrontBlocks) fb = kFrontBlocks;
+  double* partial = (double*)scratch;                                    // 2 * fb doubles, then 6 * fb
+  // same grid and summation tree as mrf_epipole_dist_sum, so mu has the same bits on both routes
+  k_front_parallax<<<kRedBlocks, kRedThreads, 0, S(stream)>>>(u0, v0, u1, v1, p->rows, p->w, mat3(p->Hinv0),
+                                                              mat3(p->Hinv1), pt2(p->q0), pt2(p->q1), par0, par1, partial);
+  int rc = check_launch("front/parallax");
   if (rc) return rc;
-  // pv and the candidate ratios of :209-219 with B_fwd = 1 (build_cost_volume.py:116-131)
+  k_front_mu<<<1, kRedBlocks, 0, S(stream)>>>(partial, kRedBlocks, (double)n, dev_state);
+  rc = check_launch("front/mu");
+  if (rc) return rc;
+  // pv and the candidate ratios of :209-219 with B_fwd fixed (build_cost_volume.py:116-131)
   cudaError_t e = cudaMemsetAsync(count, 0, sizeof(int), S(stream));
   if (e != cudaSuccess) return fail((int)e, "front: %s", cudaGetErrorString(e));
   k_structure_candidates<<<g, 256, 0, S(stream)>>>(par0, par1, rigid_mask, p->rows, p->w, 0, pt2(p->q0), pt2(p->q1), 0.0,
-                                                   0.0, 1.0, 2, nullptr, cand, count, dev_state);
+                                                   0.0, p->B_fwd, 2, nullptr, cand, count, dev_state);
   rc = check_launch("front/candidates");
   if (rc) return rc;
   rc = mrf_select_median_dev(cand, count, (size_t)n, dev_state + MRF_STATE_B, (char*)scratch + 4096 * sizeof(double), stream);
   if (rc) return rc;
-  k_set_f64<<<1, 1, 0, S(stream)>>>(dev_state + MRF_STATE_B + 1, p->B_fwd);
-  rc = check_launch("front/B_fwd");
-  if (rc) return rc;
-  for (int f = 0; f < 2 && !rc; ++f) {
-    k_parallax_to_structure<<<g, 256, 0, S(stream)>>>(par[f], p->rows, p->w, 0, pt2(qq[f]), 0.0, 0.0, Ss[f], dev_state, f);
-    rc = check_launch("front/structure");
-    if (rc) break;
-    rc = mrf_masked_minmax_f64(Ss[f], zero_mask, p->rows, p->w, 0, p->have_box[f] ? p->box[f] : nullptr,
-                               dev_state + MRF_STATE_MINMAX + 2 * f, scratch, stream);
+  Box4 bx[2];
+  for (int f = 0; f < 2; ++f) {
+    bx[f].x0 = p->box[f][0]; bx[f].x1 = p->box[f][1]; bx[f].y0 = p->box[f][2]; bx[f].y1 = p->box[f][3];
+    bx[f].on = p->have_box[f];
   }
+  k_front_structures<<<(unsigned)fb, 256, 0, S(stream)>>>(par0, par1, p->rows, p->w, pt2(p->q0), pt2(p->q1), p->B_fwd,
+                                                          zero_mask, bx[0], bx[1], S0, S1, dev_state, partial);
+  rc = check_launch("front/structures");
   if (rc) return rc;
-  return mrf_label_range_dev(dev_state, p->n_labels, stream);
+  k_front_labels<<<1, 256, 0, S(stream)>>>(partial, (int)fb, dev_state, p->n_labels);
+  return check_launch("front/labels");
 }
 
 }  // extern "C"

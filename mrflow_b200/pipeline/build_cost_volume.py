@@ -50,15 +50,17 @@ def build_cost_volume(images, flow, rigidity, homographies, epipoles, params=Non
         cost, S, mu_ar, B_ar, q_new, labels, mins, argmins = out
     if return_device:
         return [cost, S, mu_ar, B_ar, q_new, labels, (mins, argmins)]
-    return [[_down_pinned(cost[0]), _down_pinned(cost[1])], [down(S[0]), down(S[1])], mu_ar, B_ar, q_new, labels]
+    return [_down_many([cost[0], cost[1]]), _down_many([S[0], S[1]]), mu_ar, B_ar, q_new, labels]
 
 
-def _down_pinned(t):
-    """Device -> host through a pinned staging buffer (the volumes are 91 MB each at Sintel size)."""
-    host = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
-    host.copy_(t, non_blocking=True)
+def _down_many(tensors):
+    """Device -> host through pinned staging buffers, all copies in flight before one synchronisation
+    (the volumes are 91 MB each at Sintel size)."""
+    hosts = [torch.empty(t.shape, dtype=t.dtype, pin_memory=True) for t in tensors]
+    for hbuf, t in zip(hosts, tensors):
+        hbuf.copy_(t, non_blocking=True)
     torch.cuda.current_stream().synchronize()
-    return host.numpy()
+    return [hbuf.numpy() for hbuf in hosts]
 
 
 def cost_volume_pass(band, homographies, epipoles, rigid_host_mask, stats, rho="lorentzian", sigma=1.0, interp="cubic",

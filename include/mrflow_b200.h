@@ -289,6 +289,21 @@ int mrf_robust_apply_f64(const double* x, size_t n, int kind, int deriv, double 
 /* ---- pipeline/compute_structure.py:44: cv2.erode(uint8, ones((3,3))) (default border). */
 int mrf_erode3x3_u8(const uint8_t* src, int h, int w, uint8_t* dst, mrf_stream_t stream);
 
+/* ---- the stages either side of the path.
+ * rigidity/occlusions.py:10-74 (computeOcclusionsFromConsistency): flow[0] = (uf0, vf0) backward,
+ * flow[1] = (uf1, vf1) forward, backflow likewise; all fp32 [h,w].  Masks uint8 [h,w]; occ_both may
+ * be NULL.  The error is compared as fp32 against (float)threshold, as numpy does. */
+int mrf_flow_consistency(const float* uf0, const float* vf0, const float* ub0, const float* vb0,
+                         const float* uf1, const float* vf1, const float* ub1, const float* vb1,
+                         int h, int w, double threshold, uint8_t* occ_backward, uint8_t* occ_forward,
+                         uint8_t* occ_both, mrf_stream_t stream);
+/* rigidity/inference.py:140-167 (get_image_weights): I fp64 [h,w,c]; four fp32 [h,w] planes in the
+ * reference's return order (horizontal, vertical, ne, se), ready for Eff_TRWS.solve
+ * (extern/eff_trws/eff_trws.pyx:25-53).  scratch: mrf_image_weights_scratch_bytes() bytes. */
+size_t mrf_image_weights_scratch_bytes(void);
+int mrf_image_weights(const double* I, int h, int w, int c, float* w_horizontal, float* w_vertical,
+                      float* w_ne, float* w_se, void* scratch, mrf_stream_t stream);
+
 /* ---- peer memory for the row-band gather: a buffer allocated on the
  * TRW-S rank's GPU is exported as a 64-byte CUDA IPC handle, opened by the other ranks (one process
  * per GPU), and written by their cost-volume kernels directly over NVLink.  These are the only

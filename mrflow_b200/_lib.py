@@ -81,6 +81,9 @@ SIGNATURES = {
     "mrf_cost_volume_front": (_I, [C.POINTER(FrontParams), _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "mrf_select_median_dev": (_I, [_P, _P, _Z, _P, _P, _P]),
     "mrf_label_range_dev": (_I, [_P, _I, _P]),
+    "mrf_flow_consistency": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _D, _P, _P, _P, _P]),
+    "mrf_image_weights_scratch_bytes": (_Z, []),
+    "mrf_image_weights": (_I, [_P, _I, _I, _I, _P, _P, _P, _P, _P, _P]),
     "mrf_erode3x3_u8": (_I, [_P, _I, _I, _P, _P]),
     "mrf_robust_apply_f64": (_I, [_P, _Z, _I, _I, _D, _D, _P, _P]),
 }

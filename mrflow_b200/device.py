@@ -306,6 +306,37 @@ def cost_volume(ref_ch, nb_texels, labels, H, q, mu, B, label_scale=1.0, nonrigi
     return cost, mn, am
 
 
+# ------------------------------------------------------------------------------------ neighbours of the path
+def flow_consistency(flow, backflow, threshold):
+    """rigidity/occlusions.py:10-74.  flow / backflow: [[u,v] bwd, [u,v] fwd] fp32 CUDA tensors.
+    Returns (occ_backward, occ_forward, occ_both) uint8."""
+    for f in range(2):
+        for t in (*flow[f], *backflow[f]):
+            _chk(t, F32, "flow")
+    h, w = flow[0][0].shape
+    outs = [torch.empty((h, w), dtype=U8, device=flow[0][0].device) for _ in range(3)]
+    check(_lib.lib().mrf_flow_consistency(_p(flow[0][0]), _p(flow[0][1]), _p(backflow[0][0]), _p(backflow[0][1]),
+                                          _p(flow[1][0]), _p(flow[1][1]), _p(backflow[1][0]), _p(backflow[1][1]), h, w,
+                                          float(threshold), _p(outs[0]), _p(outs[1]), _p(outs[2]), _stream()),
+          "mrf_flow_consistency")
+    return tuple(outs)
+
+
+def image_weights(I):
+    """rigidity/inference.py:140-167.  I fp64 [h,w,c] (or [h,w]).  Returns (w_horizontal, w_vertical, w_ne,
+    w_se) fp32 [h,w]."""
+    _chk(I, F64, "I")
+    if I.dim() == 2:
+        I = I.unsqueeze(2)
+    h, w, c = I.shape
+    L = _lib.lib()
+    outs = [torch.empty((h, w), dtype=F32, device=I.device) for _ in range(4)]
+    scratch = torch.empty(L.mrf_image_weights_scratch_bytes(), dtype=U8, device=I.device)
+    check(L.mrf_image_weights(_p(I), h, w, c, _p(outs[0]), _p(outs[1]), _p(outs[2]), _p(outs[3]), _p(scratch), _stream()),
+          "mrf_image_weights")
+    return tuple(outs)
+
+
 # ------------------------------------------------------------------------------------ device-resident pre-pass
 class FrontBuffers:
     """Reusable HBM buffers of cost_volume_front for one frame size (keeps the step allocation-free

@@ -49,8 +49,10 @@ def quantise(coord32):
     return ipart, s & (INTER_TAB_SIZE - 1)
 
 
-def remap(img32, x32, y32, mode="cubic"):
-    """cv2.remap(img fp32, mapx fp32, mapy fp32, INTER_CUBIC|INTER_LINEAR, BORDER_REPLICATE).
+def remap(img32, x32, y32, mode="cubic", border="replicate"):
+    """cv2.remap(img fp32, mapx fp32, mapy fp32, INTER_CUBIC|INTER_LINEAR, BORDER_REPLICATE), or with
+    ``border='constant'`` (linear only) BORDER_CONSTANT with value 0, cv2.remap's default, which is what
+    rigidity/occlusions.py:33-40 uses: taps outside the image contribute 0.
 
     fp32 throughout; 2-D weight = fp32(wy*wx).  Summation order is OpenCV's.  Cubic: for a
     footprint fully inside the image each row is summed left to right and the four row sums are
@@ -75,13 +77,19 @@ def remap(img32, x32, y32, mode="cubic"):
     inside = (ix0 >= 0) & (ix0 < max(w - (k - 1), 0)) & (iy0 >= 0) & (iy0 < max(h - (k - 1), 0))
     seq = None   # border path: tap-by-tap
     grp = None   # interior path: row sums, then rows
+    if border == "constant" and mode != "linear":
+        raise ValueError("constant border is restated for the linear mode only")
     for j in range(k):
         yy = np.clip(iy0 + j, 0, h - 1)
         row = None
         for i in range(k):
             xx = np.clip(ix0 + i, 0, w - 1)
             wgt = (wy[..., j] * wx[..., i]).astype(F32)
-            p = (img32[yy, xx] * wgt[..., None]).astype(F32)
+            tap = img32[yy, xx]
+            if border == "constant":
+                out_of_image = ((iy0 + j) < 0) | ((iy0 + j) >= h) | ((ix0 + i) < 0) | ((ix0 + i) >= w)
+                tap = np.where(out_of_image[..., None], F32(0), tap)
+            p = (tap * wgt[..., None]).astype(F32)
             row = p if row is None else (row + p).astype(F32)
             seq = p if seq is None else (seq + p).astype(F32)
         grp = row if grp is None else (grp + row).astype(F32)

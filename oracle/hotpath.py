@@ -426,3 +426,45 @@ def build_cost_volume(images, flow, rigidity, homographies, epipoles, params,
     cost, _, _ = cost_volume(ch, rigidity, noocc, homographies, B_ar, mu_ar, q_new, rng,
                              kind=kind, sigma=sigma, mode=mode)
     return [[cost[0], cost[1]], S, mu_ar, B_ar, q_new, rng]
+
+
+# --------------------------------------------------------------------------- section 8f rows
+def compute_occlusions_from_consistency(flow, backflow, threshold=7.0):
+    """rigidity/occlusions.py:10-74 -- forward/backward consistency occlusion maps (cv2.remap,
+    INTER_LINEAR, default BORDER_CONSTANT).  Returns (occ_backward, occ_forward, occ_both)."""
+    def warped_error(uf, vf, ub, vb):
+        y, x = np.mgrid[:uf.shape[0], :uf.shape[1]]
+        mx, my = (x + uf).astype("float32"), (y + vf).astype("float32")
+        uw = cv2.remap(ub, mx, my, interpolation=cv2.INTER_LINEAR)
+        vw = cv2.remap(vb, mx, my, interpolation=cv2.INTER_LINEAR)
+        valid = (y + vf >= 0) * (y + vf < y.shape[0]) * (x + uf >= 0) * (x + uf < x.shape[1])
+        return np.sqrt((uw + uf) ** 2 + (vw + vf) ** 2), valid == 0
+
+    eb, ib = warped_error(flow[0][0], flow[0][1], backflow[0][0], backflow[0][1])
+    ef, i_f = warped_error(flow[1][0], flow[1][1], backflow[1][0], backflow[1][1])
+    ob = np.logical_or(eb > threshold, ib)
+    of = np.logical_or(ef > threshold, i_f)
+    ob[np.logical_and(i_f, ib == 0)] = 0
+    of[np.logical_and(ib, i_f == 0)] = 0
+    return ob, of, ob * of
+
+
+def get_image_weights(I):
+    """rigidity/inference.py:140-167 -- contrast-sensitive 8-neighbourhood edge weights for the MRF."""
+    if I.ndim == 2:
+        I = I[:, :, np.newaxis]
+    h, w, c = I.shape
+    d0 = np.vstack((np.diff(I, axis=0).sum(axis=2) / c, np.zeros((1, w))))
+    d1 = np.hstack((np.diff(I, axis=1).sum(axis=2) / c, np.zeros((h, 1))))
+    dne = np.zeros((h, w)); dne[1:, :-1] = (I[1:, :-1, :] - I[:-1, 1:, :]).sum(axis=2) / c
+    dse = np.zeros((h, w)); dse[:-1, :-1] = (I[:-1, :-1, :] - I[1:, 1:, :]).sum(axis=2) / c
+    out = []
+    for d in (d1, d0, dne, dse):                      # returned order: horizontal, vertical, ne, se
+        beta = 1.0 / (2 * max(1e-6, (d ** 2).mean()))
+        out.append(np.exp(-d ** 2 * beta).astype("float32"))
+    return tuple(out)
+
+
+def pack_unaries(unaries):
+    """rigidity/inference.py:113 -- what Eff_TRWS.solve is fed."""
+    return ((-unaries) * 1000).astype("int32").copy("C")

@@ -162,6 +162,20 @@ def main():
         out["cv_cost_crop"] = planes[:, :, 20:36, 30:62].copy()
         out["cv_argmin"] = planes.argmin(axis=1).astype(np.int32)
         out["cv_min"] = planes.min(axis=1)
+        # --- section 8f rows: occlusion maps (rigidity/occlusions.py) and MRF edge weights (inference.py:140)
+        from rigidity import occlusions as occmod
+        rs2 = np.random.RandomState(123)
+        def smooth(scale):
+            f = cv2.GaussianBlur(rs2.standard_normal((h, w)).astype(np.float32), (0, 0), 4.0) * scale
+            return f.astype(np.float32)
+        backflow = [[(-t["flow"][f][0] + smooth(6.0)).astype(np.float32), (-t["flow"][f][1] + smooth(6.0)).astype(np.float32)]
+                    for f in range(2)]
+        ob, of, oboth = occmod.computeOcclusionsFromConsistency(t["flow"], backflow, threshold=2.0)
+        out["occ_backflow"] = np.array(backflow)
+        out["occ_b"], out["occ_f"], out["occ_both"] = ob, of, oboth
+        wts = inf.get_image_weights(t["images"][1])
+        for k, name in enumerate(("w_h", "w_v", "w_ne", "w_se")):
+            out[name] = wts[k]
         if example_images is not None:
             out["images"] = np.stack(example_images)
         np.savez_compressed(os.path.join(HERE, "ref_%s.npz" % tag), **out)

@@ -195,3 +195,41 @@ def test_build_cost_volume(trip, mask_mode):
     assert ci.shape == (h, w, 51) and ci.dtype == np.int32
     assert np.array_equal(ci, (got[0][1] * np.float32(1000.0)).astype(np.int32).transpose(1, 2, 0))
     _check_argmin(dev[6][1][1].cpu().numpy(), cost[1])
+
+
+def test_occlusions_from_consistency(golden):
+    """rigidity/occlusions.py against the reference's own outputs (tests/golden)."""
+    from mrflow_b200.rigidity.occlusions import computeOcclusionsFromConsistency
+    tag, g = golden
+    t = golden_triplet(tag)
+    backflow = [[g["occ_backflow"][f][0], g["occ_backflow"][f][1]] for f in range(2)]
+    ob, of, both = computeOcclusionsFromConsistency(t["flow"], backflow, threshold=2.0)
+    assert ob.dtype == bool
+    assert np.array_equal(ob, g["occ_b"]) and np.array_equal(of, g["occ_f"]) and np.array_equal(both, g["occ_both"])
+    # flows that leave the frame: the invalid-region bookkeeping (:66-70)
+    far = [[(t["flow"][f][0] + 40).astype(np.float32), t["flow"][f][1]] for f in range(2)]
+    from oracle import hotpath as hp
+    want = hp.compute_occlusions_from_consistency(far, backflow, threshold=2.0)
+    got = computeOcclusionsFromConsistency(far, backflow, threshold=2.0)
+    for a, b in zip(got, want):
+        assert np.array_equal(a, b)
+
+
+def test_image_weights_and_unaries(golden):
+    """rigidity/inference.py:113,140-167 against the reference's own outputs."""
+    from mrflow_b200.rigidity import inference
+    tag, g = golden
+    t = golden_triplet(tag)
+    wts = inference.get_image_weights(t["images"][1])
+    for k, name in enumerate(("w_h", "w_v", "w_ne", "w_se")):
+        assert wts[k].dtype == np.float32 and wts[k].shape == g[name].shape
+        # the mean behind beta is a tree sum here and a pairwise sum in numpy (1e-16 apart): one fp32 ulp
+        np.testing.assert_allclose(wts[k], g[name], rtol=2e-7, atol=0)
+        assert (wts[k] == g[name]).mean() > 0.999
+    gray = t["images"][1][..., 0].copy()
+    w1 = inference.get_image_weights(gray)
+    from oracle import hotpath as hp
+    for a, b in zip(w1, hp.get_image_weights(gray)):
+        np.testing.assert_allclose(a, b, rtol=2e-7, atol=0)
+    un = np.random.RandomState(3).rand(5, 7, 2)
+    assert np.array_equal(inference.pack_unaries(un), hp.pack_unaries(un))

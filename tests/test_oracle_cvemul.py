@@ -53,3 +53,22 @@ def test_identity_sampling_known_answer():
     y, x = np.mgrid[:20, :30].astype(np.float32)
     assert np.array_equal(cvemul.remap(I, x, y, "cubic"), I)
     assert np.array_equal(cvemul.remap(I, x, y, "linear"), I)
+
+
+@pytest.mark.parametrize("cn", [1, 2])
+def test_remap_linear_constant_border_bit_exact(cn):
+    """cv2.remap's default border (BORDER_CONSTANT, 0) with INTER_LINEAR, as rigidity/occlusions.py uses it."""
+    rs = np.random.RandomState(13)
+    h, w = 53, 71
+    I = (rs.standard_normal((h, w, cn)) * 7).astype(np.float32)
+    if cn == 1:
+        I = I[..., 0]
+    x = (rs.rand(h, w) * (w + 12) - 6).astype(np.float32)
+    y = (rs.rand(h, w) * (h + 12) - 6).astype(np.float32)
+    x[0, :8] = [0, -0.5, -1, -1.015625, w - 1, w - 0.5, w, w - 1 + 0.015625]
+    y[0, :8] = [0, 3, 4, 5, h - 1, h - 0.5, h, -1.0]
+    x[1, :5] = [1e9, -1e9, np.nan, np.inf, 70000.0]
+    y[1, :5] = [3.0, 4.0, 5.0, 6.0, -70000.0]
+    ref = cv2.remap(I, x, y, interpolation=cv2.INTER_LINEAR)
+    emu = cvemul.remap(I, x, y, "linear", border="constant")
+    assert np.array_equal(ref, emu)

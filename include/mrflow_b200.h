@@ -304,6 +304,33 @@ size_t mrf_image_weights_scratch_bytes(void);
 int mrf_image_weights(const double* I, int h, int w, int c, float* w_horizontal, float* w_vertical,
                       float* w_ne, float* w_se, void* scratch, mrf_stream_t stream);
 
+/* ---- the linearised data term of the variational refinement.
+ * a9, structure_refinement/interpolate_through_H.py:53-97 (compute_derivs_through_H): I fp64 [h,w,C];
+ * M4 = the four matrices Hinv*T*H of :68 (x+1, x-1, y+1, y-1), Minv4 = their inverses as cv::invert
+ * forms them (closed form), bw0 = OpenCV's warp block width for this frame size; dx, dy fp64 [h,w,C]. */
+int mrf_derivs_through_H(const double* I, int h, int w, int C, const double* M4_host,
+                         const double* Minv4_host, int bw0, double* dx, double* dy, mrf_stream_t stream);
+/* fp64 [h,w,3] -> packed fp32 texels [h,w,4] (interpolation.py:76 casts what it samples to fp32) */
+int mrf_pack_texels(const double* src, int h, int w, float* texels, mrf_stream_t stream);
+/* optimize_structure_single_scale.py:203-291 (computeDataTerm, first half): per-pixel structure A ->
+ * warp -> I2w, dI2w_dx, dI2w_dy (bicubic, through H), averaged with the reference frame's derivatives,
+ * channel-weighted; outputs the residual Iz, the directional derivative dI2w_dphi and dr/da. */
+int mrf_data_term_residual(const double* A, const double* ref_ch, const float* nb_texels,
+                           const float* nb_dx_texels, const float* nb_dy_texels, const double* ref_dx,
+                           const double* ref_dy, const uint8_t* nonrigid, const uint8_t* occluded, int h,
+                           int w, const double* H_host, const double* q_host, double mu, double B,
+                           const double* cw_host, double* Iz, double* dphi, double* dr_da,
+                           mrf_stream_t stream);
+/* :294-302: psi = rho'(Iz^2), diag = psi*dphi^2*dr_da^2, b = psi*Iz*dphi*dr_da (before the median
+ * filters) and the energy sum(rho(Iz^2)) (one double on the device).  rho in MRF_RHO_LORENTZIAN ..
+ * MRF_RHO_LORENTZIAN_AUTO; scratch: mrf_data_term_scratch_bytes() bytes. */
+size_t mrf_data_term_scratch_bytes(void);
+int mrf_data_term_system(const double* Iz, const double* dphi, const double* dr_da, size_t n, int rho,
+                         double rho_param, double* diag, double* b, double* energy, void* scratch,
+                         mrf_stream_t stream);
+/* scipy.ndimage.median_filter(size=5) with its default 'reflect' boundary (:299-300) */
+int mrf_median5x5_f64(const double* src, int h, int w, double* dst, mrf_stream_t stream);
+
 /* ---- peer memory for the row-band gather: a buffer allocated on the
  * TRW-S rank's GPU is exported as a 64-byte CUDA IPC handle, opened by the other ranks (one process
  * per GPU), and written by their cost-volume kernels directly over NVLink.  These are the only

@@ -84,6 +84,12 @@ SIGNATURES = {
     "mrf_flow_consistency": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _D, _P, _P, _P, _P]),
     "mrf_image_weights_scratch_bytes": (_Z, []),
     "mrf_image_weights": (_I, [_P, _I, _I, _I, _P, _P, _P, _P, _P, _P]),
+    "mrf_derivs_through_H": (_I, [_P, _I, _I, _I, _DP, _DP, _I, _P, _P, _P]),
+    "mrf_pack_texels": (_I, [_P, _I, _I, _P, _P]),
+    "mrf_data_term_residual": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _DP, _DP, _D, _D, _DP, _P, _P, _P, _P]),
+    "mrf_data_term_scratch_bytes": (_Z, []),
+    "mrf_data_term_system": (_I, [_P, _P, _P, _Z, _I, _D, _P, _P, _P, _P, _P]),
+    "mrf_median5x5_f64": (_I, [_P, _I, _I, _P, _P]),
     "mrf_erode3x3_u8": (_I, [_P, _I, _I, _P, _P]),
     "mrf_robust_apply_f64": (_I, [_P, _Z, _I, _I, _D, _D, _P, _P]),
 }

@@ -337,6 +337,79 @@ def image_weights(I):
     return tuple(outs)
 
 
+# ------------------------------------------------------------------------------------ linearised data term
+_T4 = [np.array([[1.0, 0, -1.0], [0.0, 1.0, 0.0], [0.0, 0.0, 1.0]]), np.array([[1.0, 0, 1.0], [0.0, 1.0, 0.0], [0.0, 0.0, 1.0]]),
+       np.array([[1.0, 0, 0], [0.0, 1.0, -1.0], [0.0, 0.0, 1.0]]), np.array([[1.0, 0, 0], [0.0, 1.0, 1.0], [0.0, 0.0, 1.0]])]
+
+
+def _cv_invert3x3(M):
+    """cv::invert for a 3x3 fp64 matrix (closed form, OpenCV's operation order) -- what
+    cv2.warpPerspective applies to its matrix argument."""
+    S = np.asarray(M, dtype=np.float64)
+    det = (S[0, 0] * (S[1, 1] * S[2, 2] - S[1, 2] * S[2, 1]) - S[0, 1] * (S[1, 0] * S[2, 2] - S[1, 2] * S[2, 0])
+           + S[0, 2] * (S[1, 0] * S[2, 1] - S[1, 1] * S[2, 0]))
+    d = 1.0 / det
+    return np.array([(S[1, 1] * S[2, 2] - S[1, 2] * S[2, 1]) * d, (S[0, 2] * S[2, 1] - S[0, 1] * S[2, 2]) * d,
+                     (S[0, 1] * S[1, 2] - S[0, 2] * S[1, 1]) * d, (S[1, 2] * S[2, 0] - S[1, 0] * S[2, 2]) * d,
+                     (S[0, 0] * S[2, 2] - S[0, 2] * S[2, 0]) * d, (S[0, 2] * S[1, 0] - S[0, 0] * S[1, 2]) * d,
+                     (S[1, 0] * S[2, 1] - S[1, 1] * S[2, 0]) * d, (S[0, 1] * S[2, 0] - S[0, 0] * S[2, 1]) * d,
+                     (S[0, 0] * S[1, 1] - S[0, 1] * S[1, 0]) * d]).reshape(3, 3)
+
+
+def derivs_through_H(I, H):
+    """structure_refinement/interpolate_through_H.py:53-97.  I fp64 [h,w,C] (C <= 4) or [h,w].  Returns
+    (dx, dy) fp64 of I's shape."""
+    _chk(I, F64, "I")
+    two_d = I.dim() == 2
+    Iv = I.unsqueeze(2) if two_d else I
+    h, w, Cn = Iv.shape
+    H = np.asarray(H, dtype=np.float64)
+    Hinv = np.linalg.inv(H)
+    Ms = [Hinv.dot(T).dot(H) for T in _T4]                          # :68
+    M4 = dvec(np.concatenate([M.reshape(9) for M in Ms]))
+    Mi4 = dvec(np.concatenate([_cv_invert3x3(M).reshape(9) for M in Ms]))
+    bh0 = min(16, h); bw0 = min(1024 // bh0, w)                     # cv::warpPerspective's block shape
+    dx = torch.empty_like(Iv); dy = torch.empty_like(Iv)
+    check(_lib.lib().mrf_derivs_through_H(_p(Iv), h, w, Cn, M4, Mi4, bw0, _p(dx), _p(dy), _stream()), "mrf_derivs_through_H")
+    return (dx[..., 0], dy[..., 0]) if two_d else (dx, dy)
+
+
+def pack_texels(ch64):
+    """fp64 [h,w,3] -> fp32 texels [h,w,4]."""
+    _chk(ch64, F64, "ch64")
+    h, w = ch64.shape[:2]
+    tex = torch.empty((h, w, 4), dtype=F32, device=ch64.device)
+    check(_lib.lib().mrf_pack_texels(_p(ch64), h, w, _p(tex), _stream()), "mrf_pack_texels")
+    return tex
+
+
+def data_term(A, I1, I2, nonrigid, occluded, H, B, mu, q, rho="lorentzian_auto", sigma=0.0, cw=(0.01, 1.0, 1.0)):
+    """optimize_structure_single_scale.py:186-305 (computeDataTerm) on device tensors: A fp64 [h,w], I1 / I2
+    fp64 [h,w,3] channel stacks, masks uint8.  Returns (diag, b, E, intermediates): the two images after
+    their 5x5 median filters, the energy as a 1-element tensor, and dict(Iz, dphi, dr_da, sigma)."""
+    _chk(A, F64, "A"); _chk(I1, F64, "I1"); _chk(I2, F64, "I2"); _chk(nonrigid, U8, "nonrigid"); _chk(occluded, U8, "occluded")
+    L = _lib.lib()
+    h, w = A.shape
+    dev = A.device
+    d2x, d2y = derivs_through_H(I2, H)                              # :238-242 -> interpolate_through_H.py:44-46
+    d1x, d1y = derivs_through_H(I1, np.eye(3))                      # :255-256
+    tex, tdx, tdy = pack_texels(I2), pack_texels(d2x), pack_texels(d2y)
+    Iz = torch.empty((h, w), dtype=F64, device=dev); dphi = torch.empty_like(Iz); drda = torch.empty_like(Iz)
+    check(L.mrf_data_term_residual(_p(A), _p(I1), _p(tex), _p(tdx), _p(tdy), _p(d1x), _p(d1y), _p(nonrigid), _p(occluded),
+                                   h, w, _mat(H), _pt(q), float(mu), float(B), dvec(cw), _p(Iz), _p(dphi), _p(drda),
+                                   _stream()), "mrf_data_term_residual")
+    if rho == "lorentzian_auto":                                    # utils/robust_functions.py:55: MAD auto-sigma
+        sigma = max(1e-6, 1.4826 * median(abs_deviation(Iz.view(-1), 0.0)))
+    diag = torch.empty_like(Iz); b = torch.empty_like(Iz); E = torch.empty(1, dtype=F64, device=dev)
+    scratch = torch.empty(L.mrf_data_term_scratch_bytes(), dtype=U8, device=dev)
+    check(L.mrf_data_term_system(_p(Iz), _p(dphi), _p(drda), h * w, RHO[rho], float(sigma), _p(diag), _p(b), _p(E),
+                                 _p(scratch), _stream()), "mrf_data_term_system")
+    dm = torch.empty_like(diag); bm = torch.empty_like(b)
+    check(L.mrf_median5x5_f64(_p(diag), h, w, _p(dm), _stream()), "mrf_median5x5_f64")      # :299
+    check(L.mrf_median5x5_f64(_p(b), h, w, _p(bm), _stream()), "mrf_median5x5_f64")         # :300
+    return dm, bm, E, dict(Iz=Iz, dphi=dphi, dr_da=drda, sigma=sigma, diag_raw=diag, b_raw=b)
+
+
 # ------------------------------------------------------------------------------------ device-resident pre-pass
 class FrontBuffers:
     """Reusable HBM buffers of cost_volume_front for one frame size (keeps the step allocation-free

@@ -30,20 +30,26 @@ def _auto_sigma(x):
     return max(1e-6, 1.4826 * device.median(s))
 
 
+def _tag(f, df, kind, param):
+    """lets device-side consumers (computeDataTerm) recognise the pair without calling it"""
+    f.mrf_kind = df.mrf_kind = (kind, param)
+    return f, df
+
+
 def generate_charbonnier(eps=0, a=0.5):
     """utils/robust_functions.py:26-43"""
     if eps == 0:
         f = lambda x: _run(x, "charbonnier", 0, _auto_sigma(x), a)
         df = lambda x: _run(x, "charbonnier", 1, _auto_sigma(x), a)
-    else:
-        f = lambda x: _run(x, "charbonnier", 0, eps, a)
-        df = lambda x: _run(x, "charbonnier", 1, eps, a)
-    return f, df
+        return f, df
+    f = lambda x: _run(x, "charbonnier", 0, eps, a)
+    df = lambda x: _run(x, "charbonnier", 1, eps, a)
+    return _tag(f, df, "charbonnier", eps) if a == 0.5 else (f, df)
 
 
 def generate_quadratic():
     """utils/robust_functions.py:45-48"""
-    return (lambda x: _run(x, "quadratic", 0, 0.0)), (lambda x: _run(x, "quadratic", 1, 0.0))
+    return _tag(lambda x: _run(x, "quadratic", 0, 0.0), lambda x: _run(x, "quadratic", 1, 0.0), "quadratic", 0.0)
 
 
 def generate_lorentzian(sigma=0):
@@ -51,10 +57,10 @@ def generate_lorentzian(sigma=0):
     if sigma > 0:
         f = lambda x: _run(x, "lorentzian", 0, sigma)
         df = lambda x: _run(x, "lorentzian", 1, sigma)
-    else:
-        f = lambda x: _run(x, "lorentzian_auto", 0, _auto_sigma(x))
-        df = lambda x: _run(x, "lorentzian_auto", 1, _auto_sigma(x))
-    return f, df
+        return _tag(f, df, "lorentzian", sigma)
+    f = lambda x: _run(x, "lorentzian_auto", 0, _auto_sigma(x))
+    df = lambda x: _run(x, "lorentzian_auto", 1, _auto_sigma(x))
+    return _tag(f, df, "lorentzian_auto", 0.0)
 
 
 def generate_geman_mcclure(sigma=0):
@@ -64,4 +70,4 @@ def generate_geman_mcclure(sigma=0):
         return s, s ** 3
     f = lambda x: _run(x, "geman_mcclure", 0, *pair(x))
     df = lambda x: _run(x, "geman_mcclure", 1, *pair(x))
-    return f, df
+    return _tag(f, df, "geman_mcclure", sigma) if sigma > 0 else (f, df)

@@ -132,3 +132,91 @@ def gaussian_blur3(a):
     p = np.pad(np.asarray(a, np.float64), 1, mode="reflect")
     r = (p[:, :-2] * 0.25 + p[:, 1:-1] * 0.5) + p[:, 2:] * 0.25
     return r[1:-1] * 0.5 + (r[:-2] + r[2:]) * 0.25
+
+
+def invert3x3(M):
+    """cv::invert of a 3x3 CV_64F matrix (closed form: cofactors times 1/det, OpenCV's operation order)."""
+    S = np.asarray(M, dtype=np.float64)
+    det = (S[0, 0] * (S[1, 1] * S[2, 2] - S[1, 2] * S[2, 1]) - S[0, 1] * (S[1, 0] * S[2, 2] - S[1, 2] * S[2, 0])
+           + S[0, 2] * (S[1, 0] * S[2, 1] - S[1, 1] * S[2, 0]))
+    d = 1.0 / det
+    t = np.empty(9)
+    t[0] = (S[1, 1] * S[2, 2] - S[1, 2] * S[2, 1]) * d
+    t[1] = (S[0, 2] * S[2, 1] - S[0, 1] * S[2, 2]) * d
+    t[2] = (S[0, 1] * S[1, 2] - S[0, 2] * S[1, 1]) * d
+    t[3] = (S[1, 2] * S[2, 0] - S[1, 0] * S[2, 2]) * d
+    t[4] = (S[0, 0] * S[2, 2] - S[0, 2] * S[2, 0]) * d
+    t[5] = (S[0, 2] * S[1, 0] - S[0, 0] * S[1, 2]) * d
+    t[6] = (S[1, 0] * S[2, 1] - S[1, 1] * S[2, 0]) * d
+    t[7] = (S[0, 1] * S[2, 0] - S[0, 0] * S[2, 1]) * d
+    t[8] = (S[0, 0] * S[1, 1] - S[0, 1] * S[1, 0]) * d
+    return t.reshape(3, 3)
+
+
+def warp_perspective(img64, M, border="replicate"):
+    """cv2.warpPerspective(fp64 image, M, (w, h), INTER_LINEAR, BORDER_REPLICATE) -- the call of
+    structure_refinement/interpolate_through_H.py:90-93.  OpenCV inverts M (closed form), walks the
+    destination in blocks, maps each pixel as ((X0 + m0*x1) * (32/W)) rounded to an integer with 5
+    fraction bits, and interpolates bilinearly with fp32 table weights in fp64."""
+    img64 = np.asarray(img64, dtype=np.float64)
+    squeeze = img64.ndim == 2
+    if squeeze:
+        img64 = img64[:, :, None]
+    h, w = img64.shape[:2]
+    Mi = invert3x3(M).ravel()
+    BLOCK = 32
+    bh0 = min(BLOCK // 2, h)
+    bw0 = min(BLOCK * BLOCK // bh0, w)
+    bh0 = min(BLOCK * BLOCK // bw0, h)
+    yy, xx = np.mgrid[:h, :w]
+    bx = (xx // bw0) * bw0
+    x1 = (xx - bx).astype(np.float64)
+    bx = bx.astype(np.float64)
+    yf = yy.astype(np.float64)
+    X0 = Mi[0] * bx + Mi[1] * yf + Mi[2]
+    Y0 = Mi[3] * bx + Mi[4] * yf + Mi[5]
+    W0 = Mi[6] * bx + Mi[7] * yf + Mi[8]
+    with np.errstate(divide="ignore", invalid="ignore"):
+        W = W0 + Mi[6] * x1
+        W = np.where(W != 0, INTER_TAB_SIZE / W, 0.0)
+        fX = np.maximum(float(INT_MIN), np.minimum(2147483647.0, (X0 + Mi[0] * x1) * W))
+        fY = np.maximum(float(INT_MIN), np.minimum(2147483647.0, (Y0 + Mi[3] * x1) * W))
+    X = np.rint(fX).astype(np.int64)
+    Y = np.rint(fY).astype(np.int64)
+    sx = np.clip(X >> INTER_BITS, -32768, 32767)
+    sy = np.clip(Y >> INTER_BITS, -32768, 32767)
+    fx = X & (INTER_TAB_SIZE - 1)
+    fy = Y & (INTER_TAB_SIZE - 1)
+    tab = linear_table()
+    wx, wy = tab[fx], tab[fy]
+    out = None
+    for j in range(2):
+        for i in range(2):
+            wgt = (wy[..., j] * wx[..., i]).astype(F32).astype(np.float64)
+            yc = np.clip(sy + j, 0, h - 1)
+            xc = np.clip(sx + i, 0, w - 1)
+            p = img64[yc, xc] * wgt[..., None]
+            out = p if out is None else out + p
+    return out[..., 0] if squeeze else out
+
+
+def _fma(a, b, c):
+    """exact fused multiply-add of python floats (rational arithmetic, one rounding)"""
+    from fractions import Fraction
+    return float(Fraction(a) * Fraction(b) + Fraction(c))
+
+
+def perspective_transform64(pts64, M):
+    """cv2.perspectiveTransform on an [N,2] fp64 array (interpolate_through_H.py:73-79 passes fp64
+    points).  OpenCV 4.13's fp64 kernel is compiled with FMA contraction: each row is
+    ``fma(x, m0, y*m1) + m2``, then ``w = 1/w`` and a multiply (pinned empirically; the fp32 kernel above is
+    not contracted).  Scalar loop -- for small N only."""
+    m = np.asarray(M, dtype=np.float64).ravel()
+    out = np.empty((len(pts64), 2))
+    for i, (x, y) in enumerate(np.asarray(pts64, dtype=np.float64)):
+        x, y = float(x), float(y)
+        w = _fma(x, m[6], y * m[7]) + m[8]
+        iw = 1.0 / w if abs(w) > np.finfo(np.float64).eps else 0.0
+        out[i, 0] = (_fma(x, m[0], y * m[1]) + m[2]) * iw
+        out[i, 1] = (_fma(x, m[3], y * m[4]) + m[5]) * iw
+    return out

@@ -468,3 +468,81 @@ def get_image_weights(I):
 def pack_unaries(unaries):
     """rigidity/inference.py:113 -- what Eff_TRWS.solve is fed."""
     return ((-unaries) * 1000).astype("int32").copy("C")
+
+
+# --------------------------------------------------------------------------- section 8f.1: a9 + a11 linearisation
+def compute_derivs_through_H(I, H):
+    """structure_refinement/interpolate_through_H.py:53-97 -- derivatives of J(x,y) = I(H(x,y)) by four
+    cv2.warpPerspective calls (bilinear, BORDER_REPLICATE) and finite-difference scalings."""
+    h, w = I.shape[:2]
+    Hinv = np.linalg.inv(H)
+    Ts = [np.array([[1.0, 0, -1.0], [0.0, 1.0, 0.0], [0.0, 0.0, 1.0]]), np.array([[1.0, 0, 1.0], [0.0, 1.0, 0.0], [0.0, 0.0, 1.0]]),
+          np.array([[1.0, 0, 0], [0.0, 1.0, -1.0], [0.0, 0.0, 1.0]]), np.array([[1.0, 0, 0], [0.0, 1.0, 1.0], [0.0, 0.0, 1.0]])]
+    Ms = [Hinv.dot(T).dot(H) for T in Ts]
+    y, x = np.mgrid[:h, :w]
+    xy = np.c_[x.flatten(), y.flatten()].astype("float")
+    ds, Iw = [], []
+    for M in Ms:
+        p = cv2.perspectiveTransform(xy[:, np.newaxis, :], M).squeeze()
+        d = np.linalg.norm(xy - p, axis=1).reshape((h, w))
+        ds.append(d[:, :, np.newaxis] if I.ndim > 2 else d)
+        Iw.append(cv2.warpPerspective(I, M, (w, h), borderMode=cv2.BORDER_REPLICATE))
+    dx = 0.5 * ((Iw[0] - I) * ds[0] + (I - Iw[1]) * ds[1])
+    dy = 0.5 * ((Iw[2] - I) * ds[2] + (I - Iw[3]) * ds[3])
+    return dx, dy
+
+
+def interpolate_through_H_derivs(I, H, xn, yn, dIdx=None, dIdy=None):
+    """interpolate_through_H.py:7-51 with compute_derivs=True.  Returns (J, mask, dJdx, dJdy)."""
+    J, mask = interpolate_through_H(I, H, xn, yn)
+    if dIdx is None or dIdy is None:
+        dIdx, dIdy = compute_derivs_through_H(I, H)
+    dJdy, _ = interpolate_through_H(dIdy, H, xn, yn)
+    dJdx, _ = interpolate_through_H(dIdx, H, xn, yn)
+    return J, mask, dJdx, dJdy
+
+
+def compute_data_term(A, I1, I2, rigidity, occlusions, H, B, mu, q, kind="lorentzian", sigma=0.0,
+                      cw=CHANNEL_WEIGHTS, return_intermediates=False):
+    """optimize_structure_single_scale.py:186-305 (computeDataTerm): the linearised data term of the
+    variational refinement.  Returns (diag_data_image, b_data_image, E_data) -- the two images after
+    their 5x5 median filters (:299-300), i.e. the diagonal of A_data and b_data before flattening."""
+    from scipy import ndimage
+    h, w = I1.shape[:2]
+    x, y = _grid(h, w)
+    vx = q[0] - x
+    vy = q[1] - y
+    nrm = np.maximum(0.5, np.sqrt(vx ** 2 + vy ** 2))
+    t1 = vx / nrm
+    t2 = vy / nrm
+    n = np.sqrt(vx ** 2 + vy ** 2) / mu
+    with np.errstate(divide="ignore", invalid="ignore"):
+        r = A * B * n / (B * A / mu - 1)
+        dr_da = - (n * B) / ((B * A / mu - 1) ** 2)
+    xn = x + r * t1
+    yn = y + r * t2
+    I2w, inside, dI2w_dx, dI2w_dy = interpolate_through_H_derivs(I2, H, xn, yn)
+    dI2w_dx[inside == 0, :] = 0
+    dI2w_dy[inside == 0, :] = 0
+    _, _, dI1w_dx, dI1w_dy = interpolate_through_H_derivs(I1, np.eye(3), x, y)
+    dI2w_dx += dI1w_dx
+    dI2w_dy += dI1w_dy
+    dI2w_dx /= (inside[:, :, np.newaxis] + 1)
+    dI2w_dy /= (inside[:, :, np.newaxis] + 1)
+    c = cw[np.newaxis, np.newaxis, :]
+    dx = (dI2w_dx * c).mean(axis=2)
+    dy = (dI2w_dy * c).mean(axis=2)
+    Iz = ((I2w - I1) * c).mean(axis=2)
+    dphi = t1 * dx + t2 * dy
+    Iz[inside == 0] = 0
+    Iz[occlusions == 1] = 0
+    Iz[rigidity == 0] = 0
+    psi = drho(kind, Iz ** 2, sigma=sigma)
+    diag = psi * dphi ** 2 * dr_da ** 2
+    b = psi * Iz * dphi * dr_da
+    diag_m = ndimage.median_filter(diag, size=5)
+    b_m = ndimage.median_filter(b, size=5)
+    E = rho(kind, Iz ** 2, sigma=sigma).sum()
+    if return_intermediates:
+        return diag_m, b_m, E, dict(Iz=Iz, dphi=dphi, dr_da=dr_da, psi=psi, diag=diag, b=b)
+    return diag_m, b_m, E

@@ -135,6 +135,17 @@ def main():
                                           t["epipoles"][f], robust_ev, robust_deriv, 0.0, cw)
             out["dataterm_A%d" % f] = A
             out["dataterm_E%d" % f] = np.array(E)
+            # the full linearised data term as the variational refinement uses it: auto-sigma Lorentzian
+            # (optimize_structure_single_scale.py:333)
+            ev_auto, dv_auto = rf.generate_lorentzian()
+            A_data, b_data, E_auto = oss.computeDataTerm(A, chans[1], chans[nb], rig, occ, t["homographies"][f], B, mu[f],
+                                                         t["epipoles"][f], ev_auto, dv_auto, 0.0, cw)
+            out["lin_diag%d" % f] = np.asarray(A_data.diagonal()).reshape(h, w)
+            out["lin_b%d" % f] = b_data.reshape(h, w)
+            out["lin_E%d" % f] = np.array(E_auto)
+            if f == 1:
+                ddx, ddy = ith.compute_derivs_through_H(chans[nb], t["homographies"][f])
+                out["derivs_dx"], out["derivs_dy"] = ddx, ddy
         out["dataterm_occ"] = occ
         out["dataterm_rig"] = rig
         # --- a12: per-label planes from the reference geometry + sampler + rho ----------------

@@ -10,7 +10,7 @@ from conftest import ROOT
 def _declared():
     src = open(os.path.join(ROOT, "include", "mrflow_b200.h")).read()
     src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
-    return sorted(set(re.findall(r"\b(mrf_[a-z0-9_]+)\s*\(", src)))
+    return sorted(set(re.findall(r"\b(mrf_[A-Za-z0-9_]+)\s*\(", src)))
 
 
 def test_library_exports_every_declared_symbol():

@@ -233,3 +233,81 @@ def test_image_weights_and_unaries(golden):
         np.testing.assert_allclose(a, b, rtol=2e-7, atol=0)
     un = np.random.RandomState(3).rand(5, 7, 2)
     assert np.array_equal(inference.pack_unaries(un), hp.pack_unaries(un))
+
+
+def test_compute_derivs_through_H(golden):
+    """structure_refinement/interpolate_through_H.py:53-97 against the reference's own output."""
+    from mrflow_b200.structure_refinement.interpolate_through_H import compute_derivs_through_H, interpolate_through_H
+    from oracle import hotpath as hp
+    tag, g = golden
+    t = golden_triplet(tag)
+    ch2 = hp.prepare_channels(t["images"][2])
+    dx, dy = compute_derivs_through_H(ch2, t["homographies"][1])
+    assert dx.dtype == np.float64 and dx.shape == ch2.shape
+    assert np.array_equal(dx, g["derivs_dx"]) and np.array_equal(dy, g["derivs_dy"])
+    # identity homography, single channel: central differences with replicated borders
+    I = ch2[..., 0].copy()
+    ex, ey = hp.compute_derivs_through_H(I, np.eye(3))
+    gx, gy = compute_derivs_through_H(I, np.eye(3))
+    assert np.array_equal(gx, ex) and np.array_equal(gy, ey)
+    # compute_derivs=True without supplied derivative images now goes through the kernel as well
+    h, w = I.shape
+    y, x = np.mgrid[:h, :w]
+    rs = np.random.RandomState(4)
+    xn, yn = x + rs.uniform(-3, 3, (h, w)), y + rs.uniform(-3, 3, (h, w))
+    got = interpolate_through_H(ch2, t["homographies"][1], xn, yn, compute_derivs=True)
+    want = hp.interpolate_through_H_derivs(ch2, t["homographies"][1], xn, yn)
+    for a, b in zip(got, want):
+        assert np.array_equal(a, b)
+
+
+def test_compute_data_term(golden):
+    """computeDataTerm (optimize_structure_single_scale.py:186-305) against the reference's own linear
+    system: diag(A_data), b_data and E_data on the golden triplets, auto-sigma Lorentzian (:333)."""
+    from mrflow_b200.structure_refinement.optimize_structure_single_scale import computeDataTerm
+    from mrflow_b200.utils import robust_functions as rf
+    from oracle import hotpath as hp
+    tag, g = golden
+    t = golden_triplet(tag)
+    h, w = t["shape"]
+    ch = [hp.prepare_channels(I) for I in t["images"]]
+    cw = np.array([0.01, 1.0, 1.0])
+    ev, dv = rf.generate_lorentzian()
+    for f, (B, nb) in enumerate(((-0.37, 0), (0.41, 2))):
+        A_data, b_data, E = computeDataTerm(g["dataterm_A%d" % f], ch[1], ch[nb], g["dataterm_rig"], g["dataterm_occ"],
+                                            t["homographies"][f], B, g["mu"][f], t["epipoles"][f], ev, dv, 0.0, cw)
+        assert A_data.shape == (h * w, h * w) and b_data.shape == (h * w,)
+        diag = np.asarray(A_data.diagonal()).reshape(h, w)
+        # sigma comes from an exact median (bit-identical); psi then involves only IEEE operations, so the
+        # system matches to the last bit except where the 1e-16 effects of ... nothing: assert tightly
+        np.testing.assert_allclose(diag, g["lin_diag%d" % f], rtol=1e-12, atol=1e-300)
+        np.testing.assert_allclose(b_data.reshape(h, w), g["lin_b%d" % f], rtol=1e-12, atol=1e-300)
+        assert (diag == g["lin_diag%d" % f]).mean() > 0.99
+        np.testing.assert_allclose(E, float(g["lin_E%d" % f]), rtol=1e-12)
+    # fixed-sigma variant against the oracle, and a foreign closure is rejected
+    ev2, dv2 = rf.generate_lorentzian(1.0)
+    A2, b2, E2 = computeDataTerm(g["dataterm_A1"], ch[1], ch[2], g["dataterm_rig"], g["dataterm_occ"], t["homographies"][1],
+                                 0.41, g["mu"][1], t["epipoles"][1], ev2, dv2, 0.0, cw)
+    d_ref, b_ref, E_ref = hp.compute_data_term(g["dataterm_A1"], ch[1], ch[2], g["dataterm_rig"], g["dataterm_occ"],
+                                               t["homographies"][1], 0.41, g["mu"][1], t["epipoles"][1], sigma=1.0)
+    np.testing.assert_allclose(np.asarray(A2.diagonal()).reshape(h, w), d_ref, rtol=1e-12, atol=1e-300)
+    np.testing.assert_allclose(b2.reshape(h, w), b_ref, rtol=1e-12, atol=1e-300)
+    with pytest.raises(TypeError):
+        computeDataTerm(g["dataterm_A1"], ch[1], ch[2], g["dataterm_rig"], g["dataterm_occ"], t["homographies"][1], 0.41,
+                        g["mu"][1], t["epipoles"][1], lambda x: x, lambda x: x, 0.0, cw)
+
+
+def test_median5x5(golden):
+    import torch
+    from scipy import ndimage
+    from mrflow_b200 import _lib
+    import ctypes as C
+    rs = np.random.RandomState(8)
+    for shape in ((37, 53), (5, 9), (3, 4)):
+        a = rs.standard_normal(shape)
+        a[rs.rand(*shape) < 0.3] = 0.0                      # ties
+        src = torch.from_numpy(a).cuda()
+        dst = torch.empty_like(src)
+        _lib.check(_lib.lib().mrf_median5x5_f64(C.c_void_p(src.data_ptr()), shape[0], shape[1], C.c_void_p(dst.data_ptr()),
+                                                 C.c_void_p(torch.cuda.current_stream().cuda_stream)), "median")
+        assert np.array_equal(dst.cpu().numpy(), ndimage.median_filter(a, size=5))

@@ -72,3 +72,25 @@ def test_remap_linear_constant_border_bit_exact(cn):
     ref = cv2.remap(I, x, y, interpolation=cv2.INTER_LINEAR)
     emu = cvemul.remap(I, x, y, "linear", border="constant")
     assert np.array_equal(ref, emu)
+
+
+@pytest.mark.parametrize("shape", [(61, 83, 3), (120, 200, 1)])
+def test_warp_perspective_and_ptransform64_bit_exact(shape):
+    """cv2.warpPerspective(fp64, INTER_LINEAR, BORDER_REPLICATE) and cv2.perspectiveTransform(fp64), the
+    primitives of compute_derivs_through_H (structure_refinement/interpolate_through_H.py:53-97)."""
+    rs = np.random.RandomState(17)
+    h, w, cn = shape
+    I = rs.rand(h, w, cn) * 255
+    if cn == 1:
+        I = I[..., 0]
+    H = np.array([[1.002, -0.001, 2.3], [0.0015, 0.999, -1.7], [1.5e-6, -1e-6, 1.0]])
+    Hinv = np.linalg.inv(H)
+    y, x = np.mgrid[:h, :w]
+    pts = np.c_[x.ravel(), y.ravel()].astype("float")
+    for T in (np.array([[1.0, 0, -1.0], [0, 1, 0], [0, 0, 1]]), np.array([[1.0, 0, 0], [0, 1, 1.0], [0, 0, 1]]), np.eye(3)):
+        for M in (Hinv.dot(T).dot(H), T):
+            ref = cv2.warpPerspective(I, M, (w, h), borderMode=cv2.BORDER_REPLICATE)
+            assert np.array_equal(ref, cvemul.warp_perspective(I, M))
+            sub = pts[::37]
+            refp = cv2.perspectiveTransform(sub[:, None, :], M).squeeze()
+            assert np.array_equal(refp, cvemul.perspective_transform64(sub, M))

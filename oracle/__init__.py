@@ -14,6 +14,10 @@ pins neither, README.md:19 only says "OpenCV >= 3.0").  ``oracle.cvemul`` additi
 those OpenCV primitives in plain numpy, bit-exactly, so the CUDA kernels have an arithmetic
 specification that does not depend on OpenCV's binary.
 
+``oracle/build_ref.py`` additionally compiles the reference's own C++ MRF solver (extern/eff_trws) from
+the sources under /root/reference into ``oracle/_ref/`` (git-ignored); ``oracle/trws.py`` wraps it as the
+reference's ``infer_mrf`` so that ``compute_structure`` can be compared end to end.
+
 Parity status
 -------------
 * a1-a8, a10 (flow<->structure maps, sampler, robust functions, rigidity unaries): PINNED.
@@ -21,8 +25,12 @@ Parity status
   import shims of SURVEY.md section 8c, none of which alters arithmetic) and stores its outputs on
   seeded inputs in ``tests/golden/*.npz``; ``tests/test_oracle_golden.py`` checks this oracle
   against them.
-* a11 (``computeDataTerm`` residual + energy): PINNED the same way (energy ``E_data`` and the
-  residual image of the reference function on a seeded pair).
+* a11 (``computeDataTerm``): PINNED the same way -- the energy, and the complete linear system
+  (diag(A_data), b_data) of the reference function with its auto-sigma Lorentzian; a9
+  (``compute_derivs_through_H``), ``computeOcclusionsFromConsistency`` and ``get_image_weights`` likewise.
+* a4 end to end: the reference's ``compute_structure`` run with its own solver (oracle/_ref) is stored
+  for the two fixtures whose epipole lies outside the frame; the oracle reproduces all seven outputs
+  bit for bit.  (With the epipole inside, the reference needs chumpy for ``correct_epipole``: unpinned.)
 * a12 (the per-label cost volume): the reference's arithmetic for this step lived in a compiled
   extension that is NOT shipped (``pipeline/build_cost_volume.py:26-27``).  The oracle composes
   it from shipped reference functions exactly as SURVEY.md section 8c defines; each label plane is

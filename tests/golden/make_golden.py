@@ -187,6 +187,25 @@ def main():
         wts = inf.get_image_weights(t["images"][1])
         for k, name in enumerate(("w_h", "w_v", "w_ne", "w_se")):
             out[name] = wts[k]
+        # --- the complete stage, reference code end to end: pipeline/compute_structure.py:37-449 with the
+        # reference's own C++ MRF solver (oracle/_ref, built by oracle/build_ref.py).  Only for epipoles
+        # outside the frame: inside, correct_epipole needs chumpy (absent here).
+        if tag != "inside":
+            sys.path.insert(0, ROOT)
+            from oracle import trws
+            if trws.available():
+                inf.eff_trws = trws._ext()
+                inf.HAVE_TRWS = True
+                occ2 = [rs2.rand(h, w) < 0.04, rs2.rand(h, w) < 0.04]
+                p = argparse.Namespace(debug_use_rigidity_gt=0, debug_save_frames=0, debug_compute_figure=0,
+                                       rigidity_sigma_direction=1.0, rigidity_weight_cnn=0.25, rigidity_sigma_structure=1.0,
+                                       rigidity_use_structure=1, scale_structure=1, nonlinear_structure_initialization=0,
+                                       occlusion_reasoning=1, tempdir=".")
+                full = cs.compute_structure(t["images"], t["flow"], t["rigidity"], occ2,
+                                            [H.copy() for H in t["homographies"]], t["epipoles"], p)
+                out["full_occ"] = np.array(occ2)
+                out["full_S"] = np.array(full[0]); out["full_mu"] = np.array(full[2]); out["full_B"] = np.array(full[3])
+                out["full_q"] = np.array(full[4]); out["full_rigidity"] = np.asarray(full[5])
         if example_images is not None:
             out["images"] = np.stack(example_images)
         np.savez_compressed(os.path.join(HERE, "ref_%s.npz" % tag), **out)

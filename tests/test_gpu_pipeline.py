@@ -309,3 +309,28 @@ def test_median5x5(golden):
         _lib.check(_lib.lib().mrf_median5x5_f64(C.c_void_p(src.data_ptr()), shape[0], shape[1], C.c_void_p(dst.data_ptr()),
                                                  C.c_void_p(torch.cuda.current_stream().cuda_stream)), "median")
         assert np.array_equal(dst.cpu().numpy(), ndimage.median_filter(a, size=5))
+
+
+def test_compute_structure_against_reference_end_to_end(golden):
+    """mrflow_b200.pipeline.compute_structure against the REFERENCE's compute_structure run end to end
+    (tests/golden, generated with the reference's own C++ MRF solver), the same solver serving as the
+    unchanged consumer here (oracle/_ref, prebuilt)."""
+    from mrflow_b200.pipeline.compute_structure import compute_structure
+    from oracle import trws
+    tag, g = golden
+    if "full_S" not in g:
+        pytest.skip("no end-to-end fixture for this case")
+    if not trws.available():
+        pytest.skip("oracle/_ref not built")
+    t = golden_triplet(tag)
+    occ = [g["full_occ"][0], g["full_occ"][1]]
+    S, Hs, mu, B, q, rig, oc = compute_structure(t["images"], t["flow"], t["rigidity"], occ,
+                                                 [H.copy() for H in t["homographies"]], t["epipoles"], _params(),
+                                                 infer_mrf=trws.infer_mrf)
+    np.testing.assert_allclose(mu, g["full_mu"], rtol=1e-14)
+    np.testing.assert_allclose(B, g["full_B"], rtol=1e-11)
+    assert np.array_equal(np.array(q), g["full_q"])
+    for f in range(2):
+        fin = np.isfinite(g["full_S"][f])
+        np.testing.assert_allclose(S[f][fin], g["full_S"][f][fin], rtol=1e-10)
+    assert np.array_equal(rig, g["full_rigidity"])          # the MRF labelling is identical

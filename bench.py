@@ -246,8 +246,10 @@ def run_ours(args):
     # triplet; P = 1 is the plain back-to-back case.
     P = max(1, args.pipeline)
     slots = []
+    host_triplets = []
     for s_i in range(P):
         ts = t if s_i == 0 else synth.make_triplet(hw, seed=2001 + 17 * s_i + rank)
+        host_triplets.append(ts)
         bs = band if s_i == 0 else pp.Band.from_host(ts["images"], ts["flow"], ts["rigidity"], None)
         ms = rigid_mask if s_i == 0 else torch.from_numpy((ts["rigidity"] > 0).astype(np.uint8)).cuda()
         stream = torch.cuda.Stream()
@@ -338,35 +340,63 @@ def run_ours(args):
     # ---- end to end through the public host API (numpy in pinned memory -> numpy out)
     e2e = None
     if not args.no_e2e:
+        from mrflow_b200 import dataset
+
         def pinned(a):
             tt = torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
             return tt.numpy()
-        images = [pinned(I) for I in t["images"]]
-        flow = [[pinned(t["flow"][f][0]), pinned(t["flow"][f][1])] for f in range(2)]
-        rig = pinned(t["rigidity"])
-        h2d = sum(a.nbytes for a in images) + sum(a.nbytes for f in flow for a in f) + rig.nbytes
-        h2d += h * w * (8 + 4 + 4 + 1)                       # structure + initial flow + rigidity flags of combine_flow
+        hosts = []
+        for ts in host_triplets:
+            hosts.append(dict(images=[pinned(I) for I in ts["images"]],
+                              flow=[[pinned(ts["flow"][f][0]), pinned(ts["flow"][f][1])] for f in range(2)],
+                              rigidity=pinned(ts["rigidity"]), homographies=ts["homographies"], epipoles=ts["epipoles"]))
+        h0 = hosts[0]
+        h2d = sum(a.nbytes for a in h0["images"]) + sum(a.nbytes for f in h0["flow"] for a in f) + h0["rigidity"].nbytes
+        h2d += 2 * h * w                                       # rigid / non-rigid flags
+        # the public dataset API: P triplets in flight, every step uploads its inputs from pinned host memory
+        # and downloads both cost volumes, both structures, the flow and the scalars into pinned host memory
+        stream_api = dataset.TripletStream(depth=P, interp=args.interp, variant=args.variant, range_mask=RANGE_MASK)
+        n_e2e = max(6, min(steps, 20))
 
-        def e2e_step():
-            out = bcv.build_cost_volume(images, flow, rig, t["homographies"], t["epipoles"], None, interp=args.interp,
-                                        variant=args.variant, range_mask=RANGE_MASK)
-            r, u, v = s2f.combine_flow(out[1][1], flow[1], rig, out[4], out[2], t["homographies"], out[3])
-            return out, u, v
-        n_e2e = max(3, min(steps, 10))
-        for _ in range(2):
-            out, u, v = e2e_step()
-        d2h = sum(a.nbytes for a in out[0]) + sum(a.nbytes for a in out[1]) + u.nbytes + v.nbytes
+        def e2e_run(n):
+            last = None
+            for k in range(n):
+                if len(stream_api.pending) == len(stream_api.slots):
+                    last = stream_api.collect()
+                hk = hosts[k % P]
+                stream_api.submit(hk["images"], hk["flow"], hk["rigidity"], hk["homographies"], hk["epipoles"])
+            while stream_api.pending:
+                last = stream_api.collect()
+            return last
+        out = e2e_run(2 * P)
+        d2h = sum(a.nbytes for a in out["cost"]) + sum(a.nbytes for a in out["structure"]) + out["u"].nbytes + out["v"].nbytes
+        d2h += 8 * (16 + 256)
         barrier()
         t0 = time.perf_counter()
-        for _ in range(n_e2e):
-            e2e_step()
+        e2e_run(n_e2e)
         torch.cuda.synchronize()
         dt = time.perf_counter() - t0
         tt = torch.tensor([dt], dtype=torch.float64, device="cuda")
         if world > 1:
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         e2e = {"value": world * units_per_step * n_e2e / float(tt.cpu()[0]), "unit": UNIT, "h2d_bytes_per_step": int(h2d),
-               "d2h_bytes_per_step": int(d2h), "steps": n_e2e, "api": "mrflow_b200.pipeline.build_cost_volume + combine_flow"}
+               "d2h_bytes_per_step": int(d2h), "steps": n_e2e, "triplets_in_flight": P,
+               "api": "mrflow_b200.dataset.TripletStream (build_cost_volume + combine_flow per triplet, host numpy in/out)"}
+        # one call at a time through the reference-signature functions, for comparison
+        h1 = hosts[0]
+        for _ in range(2):
+            o1 = bcv.build_cost_volume(h1["images"], h1["flow"], h1["rigidity"], h1["homographies"], h1["epipoles"], None,
+                                       interp=args.interp, variant=args.variant, range_mask=RANGE_MASK)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        n1 = 5
+        for _ in range(n1):
+            o1 = bcv.build_cost_volume(h1["images"], h1["flow"], h1["rigidity"], h1["homographies"], h1["epipoles"], None,
+                                       interp=args.interp, variant=args.variant, range_mask=RANGE_MASK)
+            s2f.combine_flow(o1[1][1], h1["flow"][1], h1["rigidity"], o1[4], o1[2], h1["homographies"], o1[3])
+        torch.cuda.synchronize()
+        e2e["single_call"] = {"value": units_per_step * n1 / (time.perf_counter() - t0),
+                              "api": "mrflow_b200.pipeline.build_cost_volume + combine_flow, one triplet at a time"}
 
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:

@@ -334,3 +334,28 @@ def test_compute_structure_against_reference_end_to_end(golden):
         fin = np.isfinite(g["full_S"][f])
         np.testing.assert_allclose(S[f][fin], g["full_S"][f][fin], rtol=1e-10)
     assert np.array_equal(rig, g["full_rigidity"])          # the MRF labelling is identical
+
+
+def test_triplet_stream_equals_single_calls(trip):
+    """mrflow_b200.dataset.TripletStream (several triplets in flight, pinned result buffers) returns
+    exactly what build_cost_volume + combine_flow return one call at a time."""
+    from mrflow_b200 import dataset
+    from mrflow_b200.pipeline import structure2flow as s2f
+    from mrflow_b200.pipeline.build_cost_volume import build_cost_volume
+    t = trip
+    rig = t["rigidity"].copy(); rig[5:20, 60:80] = 0.0
+    variants = []
+    for k in range(4):
+        fl = [[t["flow"][f][0] + np.float32(0.01 * k), t["flow"][f][1]] for f in range(2)]
+        variants.append(dict(images=t["images"], flow=fl, rigidity=rig, homographies=t["homographies"], epipoles=t["epipoles"]))
+    got = [dict((k, (v if not isinstance(v, (list, np.ndarray)) else ([a.copy() for a in v] if isinstance(v, list) else v.copy())))
+                for k, v in r.items()) for r in dataset.run_triplets(variants, depth=2, range_mask="rigid_only")]
+    assert len(got) == 4
+    for v, r in zip(variants, got):
+        want = build_cost_volume(v["images"], v["flow"], v["rigidity"], v["homographies"], v["epipoles"], None,
+                                 range_mask="rigid_only")
+        for f in range(2):
+            assert np.array_equal(r["cost"][f], want[0][f]) and np.array_equal(r["structure"][f], want[1][f], equal_nan=True)
+        assert r["mu"] == list(want[2]) and r["B"] == list(want[3]) and np.array_equal(r["labels"], want[5])
+        _, u, vv = s2f.combine_flow(want[1][1], v["flow"][1], v["rigidity"], want[4], want[2], v["homographies"], want[3])
+        assert np.array_equal(r["u"], u, equal_nan=True) and np.array_equal(r["v"], vv, equal_nan=True)

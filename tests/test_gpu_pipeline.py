@@ -348,8 +348,8 @@ def test_triplet_stream_equals_single_calls(trip):
     for k in range(4):
         fl = [[t["flow"][f][0] + np.float32(0.01 * k), t["flow"][f][1]] for f in range(2)]
         variants.append(dict(images=t["images"], flow=fl, rigidity=rig, homographies=t["homographies"], epipoles=t["epipoles"]))
-    got = [dict((k, (v if not isinstance(v, (list, np.ndarray)) else ([a.copy() for a in v] if isinstance(v, list) else v.copy())))
-                for k, v in r.items()) for r in dataset.run_triplets(variants, depth=2, range_mask="rigid_only")]
+    import copy
+    got = [copy.deepcopy(r) for r in dataset.run_triplets(variants, depth=2, range_mask="rigid_only")]   # slot buffers are reused
     assert len(got) == 4
     for v, r in zip(variants, got):
         want = build_cost_volume(v["images"], v["flow"], v["rigidity"], v["homographies"], v["epipoles"], None,

@@ -62,6 +62,7 @@ typedef void* mrf_stream_t; /* cudaStream_t */
 #define MRF_STATE_MU      0   /* [2] mu of frame 0 (bwd), 1 (fwd)      compute_structure.py:84 */
 #define MRF_STATE_B       2   /* [2] B_b, B_fwd                         compute_structure.py:190-223 */
 #define MRF_STATE_MINMAX  4   /* [4] (min, max) of the range-masked structures of frame 0, 1 */
+#define MRF_STATE_NANFLAG 8   /* [2] != 0: the range-masked structure of frame 0 / 1 contains a NaN */
 #define MRF_STATE_LABELS  16  /* [n_labels] structure_range             build_cost_volume.py:190-192 */
 #define MRF_STATE_WORDS   (16 + 256)
 
@@ -272,6 +273,32 @@ int mrf_cost_volume_front(const mrf_front_params* p_host, const float* u0, const
                           const float* u1, const float* v1, const uint8_t* rigid_mask,
                           const uint8_t* zero_mask, double* par0, double* par1, double* S0, double* S1,
                           double* cand, int* count, double* dev_state, void* scratch, mrf_stream_t stream);
+/* The same pre-pass in pieces for ROW BANDS (p->y0, p->rows = this rank's band): between the pieces the
+ * caller all-reduces small device buffers with NCCL on the same stream -- no host round trip:
+ *   parallax_band  -> sums2[2] = this band's sum of ||p - q|| per frame;  all-reduce SUM, divide by
+ *                     frame_h*w into dev_state[MRF_STATE_MU..];
+ *   candidates_band-> cand / count (local);  all-reduce SUM of count -> n_total;
+ *   mrf_select_begin_dev(n_total); 8 x { mrf_select_hist_dev(local count); all-reduce SUM of the 256
+ *                     uint64 words at scratch + MRF_SELECT_HIST_OFFSET; mrf_select_pick };
+ *                     mrf_select_successor_dev; all-reduce state words 3,4 (SUM) and 5 (MIN, unsigned);
+ *                     mrf_select_median_state -> dev_state[MRF_STATE_B];
+ *   structures_band-> S0, S1 and this band's range min / max / NaN flag in dev_state;  all-reduce MIN /
+ *                     MAX / MAX;  mrf_label_range_dev. */
+int mrf_front_parallax_band(const mrf_front_params* p_host, const float* u0, const float* v0,
+                            const float* u1, const float* v1, double* par0, double* par1, double* sums2,
+                            void* scratch, mrf_stream_t stream);
+int mrf_front_candidates_band(const mrf_front_params* p_host, const double* par0, const double* par1,
+                              const uint8_t* rigid_mask, const double* dev_state, double* cand, int* count,
+                              mrf_stream_t stream);
+int mrf_front_structures_band(const mrf_front_params* p_host, const double* par0, const double* par1,
+                              const uint8_t* zero_mask, double* S0, double* S1, double* dev_state,
+                              void* scratch, mrf_stream_t stream);
+int mrf_select_begin_dev(const int* n_total_dev, void* scratch, mrf_stream_t stream);
+int mrf_select_hist_dev(const double* keys, const int* n_local_dev, size_t capacity, void* scratch,
+                        mrf_stream_t stream);
+int mrf_select_successor_dev(const double* keys, const int* n_local_dev, size_t capacity, void* scratch,
+                             mrf_stream_t stream);
+int mrf_select_median_state(const void* scratch, double* out_median, mrf_stream_t stream);
 /* numpy.median of the first *n_dev keys (n read on the device); np.linspace label set from the
  * state's min/max.  Building blocks of the front, exported for tests. */
 int mrf_select_median_dev(const double* keys, const int* n_dev, size_t capacity, double* out_median,

@@ -35,7 +35,7 @@ class FrontParams(C.Structure):
                 ("B_fwd", C.c_double), ("have_box", C.c_int * 2), ("box", (C.c_int * 4) * 2), ("n_labels", C.c_int)]
 
 
-STATE_MU, STATE_B, STATE_MINMAX, STATE_LABELS, STATE_WORDS = 0, 2, 4, 16, 16 + 256
+STATE_MU, STATE_B, STATE_MINMAX, STATE_NANFLAG, STATE_LABELS, STATE_WORDS = 0, 2, 4, 8, 16, 16 + 256
 
 
 _P, _I, _D, _Z = C.c_void_p, C.c_int, C.c_double, C.c_size_t
@@ -79,6 +79,13 @@ SIGNATURES = {
     "mrf_cost_volume": (_I, [C.POINTER(CostVolParams), _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "mrf_front_scratch_bytes": (_Z, []),
     "mrf_cost_volume_front": (_I, [C.POINTER(FrontParams), _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
+    "mrf_front_parallax_band": (_I, [C.POINTER(FrontParams), _P, _P, _P, _P, _P, _P, _P, _P, _P]),
+    "mrf_front_candidates_band": (_I, [C.POINTER(FrontParams), _P, _P, _P, _P, _P, _P, _P]),
+    "mrf_front_structures_band": (_I, [C.POINTER(FrontParams), _P, _P, _P, _P, _P, _P, _P, _P]),
+    "mrf_select_begin_dev": (_I, [_P, _P, _P]),
+    "mrf_select_hist_dev": (_I, [_P, _P, _Z, _P, _P]),
+    "mrf_select_successor_dev": (_I, [_P, _P, _Z, _P, _P]),
+    "mrf_select_median_state": (_I, [_P, _P, _P]),
     "mrf_select_median_dev": (_I, [_P, _P, _Z, _P, _P, _P]),
     "mrf_label_range_dev": (_I, [_P, _I, _P]),
     "mrf_flow_consistency": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _D, _P, _P, _P, _P]),

@@ -367,15 +367,16 @@ constexpr int kFrontBlocks = 592;   // 4 x 148
 // both frames: residual flow -> parallax (a1 + a2) and the block partial sums behind mu
 __global__ void __launch_bounds__(256)
 k_front_parallax(const float* __restrict__ u0, const float* __restrict__ v0, const float* __restrict__ u1,
-                 const float* __restrict__ v1, int rows, int w, Mat3 Hinv0, Mat3 Hinv1, Pt2 q0, Pt2 q1,
+                 const float* __restrict__ v1, int rows, int w, int y0, Mat3 Hinv0, Mat3 Hinv1, Pt2 q0, Pt2 q1,
                  double* __restrict__ par0, double* __restrict__ par1, double* __restrict__ partial) {
   __shared__ double sh[32];
   const long long n = (long long)rows * w;
   double acc0 = 0.0, acc1 = 0.0;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n;
        i += (long long)gridDim.x * blockDim.x) {
-    const int y = (int)(i / w);
-    const int x = (int)(i - (long long)y * w);
+    const int yl = (int)(i / w);
+    const int x = (int)(i - (long long)yl * w);
+    const int y = yl + y0;
 #pragma unroll
     for (int f = 0; f < 2; ++f) {
       const float* u = f ? u1 : u0; const float* v = f ? v1 : v0;
@@ -403,7 +404,7 @@ k_front_mu(const double* __restrict__ partial, int nblocks, double n_px, double*
   for (int f = 0; f < 2; ++f) {
     double v = (threadIdx.x < nblocks) ? partial[f * nblocks + threadIdx.x] : 0.0;
     v = block_sum(v, sh);
-    if (threadIdx.x == 0) st[MRF_STATE_MU + f] = v / n_px;
+    if (threadIdx.x == 0) st[MRF_STATE_MU + f] = (n_px != 0.0) ? v / n_px : v;   // n_px = 0: leave the band's sum
   }
 }
 
@@ -411,7 +412,7 @@ k_front_mu(const double* __restrict__ partial, int nblocks, double n_px, double*
 // range-masked structure (build_cost_volume.py:154-169)
 struct Box4 { int x0, x1, y0, y1, on; };
 __global__ void __launch_bounds__(256)
-k_front_structures(const double* __restrict__ par0, const double* __restrict__ par1, int rows, int w, Pt2 q0,
+k_front_structures(const double* __restrict__ par0, const double* __restrict__ par1, int rows, int w, int y0, Pt2 q0,
                    Pt2 q1, double B_fwd, const uint8_t* __restrict__ zero_mask, Box4 b0, Box4 b1,
                    double* __restrict__ S0, double* __restrict__ S1, double* __restrict__ st,
                    double* __restrict__ part) {
@@ -424,8 +425,9 @@ k_front_structures(const double* __restrict__ par0, const double* __restrict__ p
   int nan[2] = {0, 0};
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n;
        i += (long long)gridDim.x * blockDim.x) {
-    const int y = (int)(i / w);
-    const int x = (int)(i - (long long)y * w);
+    const int yl = (int)(i / w);
+    const int x = (int)(i - (long long)yl * w);
+    const int y = yl + y0;
     const bool zm = zero_mask && zero_mask[i];
 #pragma unroll
     for (int f = 0; f < 2; ++f) {
@@ -459,6 +461,36 @@ k_front_structures(const double* __restrict__ par0, const double* __restrict__ p
     for (int k = 1; k < 8; ++k) { a = fmin(a, smin[f][k]); b = fmax(b, smax[f][k]); c |= snan[f][k]; }
     double* o = part + ((size_t)f * gridDim.x + blockIdx.x) * 3;
     o[0] = a; o[1] = b; o[2] = (double)c;
+  }
+}
+
+// final (NaN-ignoring) min / max of both frames and the NaN flags -> state; row bands all-reduce these
+// (MIN, MAX, MAX) before mrf_label_range_dev
+__global__ void __launch_bounds__(256)
+k_front_minmax(const double* __restrict__ part, int nblocks, double* __restrict__ st) {
+  __shared__ double smin[8], smax[8];
+  __shared__ int snan[8];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  for (int f = 0; f < 2; ++f) {
+    double lo = INFINITY, hi = -INFINITY; int nan = 0;
+    for (int i = threadIdx.x; i < nblocks; i += blockDim.x) {
+      const double* o = part + ((size_t)f * nblocks + i) * 3;
+      lo = fmin(lo, o[0]); hi = fmax(hi, o[1]); if (o[2] != 0.0) nan = 1;
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+      lo = fmin(lo, __shfl_down_sync(0xffffffffu, lo, o));
+      hi = fmax(hi, __shfl_down_sync(0xffffffffu, hi, o));
+      nan |= __shfl_down_sync(0xffffffffu, nan, o);
+    }
+    if (lane == 0) { smin[wid] = lo; smax[wid] = hi; snan[wid] = nan; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      for (int k = 1; k < 8; ++k) { lo = fmin(lo, smin[k]); hi = fmax(hi, smax[k]); nan |= snan[k]; }
+      st[MRF_STATE_MINMAX + 2 * f] = lo;
+      st[MRF_STATE_MINMAX + 2 * f + 1] = hi;
+      st[MRF_STATE_NANFLAG + f] = (double)nan;
+    }
+    __syncthreads();
   }
 }
 
@@ -653,7 +685,7 @@ int mrf_cost_volume_front(const mrf_front_params* p, const float* u0, const floa
   if (fb > kFrontBlocks) fb = kFrontBlocks;
   double* partial = (double*)scratch;                                    // 2 * fb doubles, then 6 * fb
   // same grid and summation tree as mrf_epipole_dist_sum, so mu has the same bits on both routes
-  k_front_parallax<<<kRedBlocks, kRedThreads, 0, S(stream)>>>(u0, v0, u1, v1, p->rows, p->w, mat3(p->Hinv0),
+  k_front_parallax<<<kRedBlocks, kRedThreads, 0, S(stream)>>>(u0, v0, u1, v1, p->rows, p->w, 0, mat3(p->Hinv0),
                                                               mat3(p->Hinv1), pt2(p->q0), pt2(p->q1), par0, par1, partial);
   int rc = check_launch("front/parallax");
   if (rc) return rc;
@@ -674,12 +706,63 @@ int mrf_cost_volume_front(const mrf_front_params* p, const float* u0, const floa
     bx[f].x0 = p->box[f][0]; bx[f].x1 = p->box[f][1]; bx[f].y0 = p->box[f][2]; bx[f].y1 = p->box[f][3];
     bx[f].on = p->have_box[f];
   }
-  k_front_structures<<<(unsigned)fb, 256, 0, S(stream)>>>(par0, par1, p->rows, p->w, pt2(p->q0), pt2(p->q1), p->B_fwd,
+  k_front_structures<<<(unsigned)fb, 256, 0, S(stream)>>>(par0, par1, p->rows, p->w, 0, pt2(p->q0), pt2(p->q1), p->B_fwd,
                                                           zero_mask, bx[0], bx[1], S0, S1, dev_state, partial);
   rc = check_launch("front/structures");
   if (rc) return rc;
   k_front_labels<<<1, 256, 0, S(stream)>>>(partial, (int)fb, dev_state, p->n_labels);
   return check_launch("front/labels");
+}
+
+
+// ---- the same pre-pass in pieces for row bands: the caller all-reduces (NCCL, on the stream) between
+// the pieces -- the two sums behind mu, the candidate count, the 256-bin histograms of the distributed
+// median, and the range min / max -- so there is no host round trip either.
+int mrf_front_parallax_band(const mrf_front_params* p, const float* u0, const float* v0, const float* u1,
+                            const float* v1, double* par0, double* par1, double* sums2, void* scratch,
+                            mrf_stream_t stream) {
+  MRF_CHECK_ARG(p && u0 && v0 && u1 && v1 && par0 && par1 && sums2 && scratch && p->rows > 0 && p->w > 0);
+  double* partial = (double*)scratch;
+  k_front_parallax<<<kRedBlocks, kRedThreads, 0, S(stream)>>>(u0, v0, u1, v1, p->rows, p->w, p->y0, mat3(p->Hinv0),
+                                                              mat3(p->Hinv1), pt2(p->q0), pt2(p->q1), par0, par1, partial);
+  int rc = check_launch("front_band/parallax");
+  if (rc) return rc;
+  // sums2 is written at the MU slots of a 2-word pseudo state: pass sums2 - MRF_STATE_MU with n_px = 0
+  k_front_mu<<<1, kRedBlocks, 0, S(stream)>>>(partial, kRedBlocks, 0.0, sums2 - MRF_STATE_MU);
+  return check_launch("front_band/sums");
+}
+
+int mrf_front_candidates_band(const mrf_front_params* p, const double* par0, const double* par1,
+                              const uint8_t* rigid_mask, const double* dev_state, double* cand, int* count,
+                              mrf_stream_t stream) {
+  MRF_CHECK_ARG(p && par0 && par1 && rigid_mask && dev_state && cand && count);
+  cudaError_t e = cudaMemsetAsync(count, 0, sizeof(int), S(stream));
+  if (e != cudaSuccess) return fail((int)e, "front_band: %s", cudaGetErrorString(e));
+  k_structure_candidates<<<grid_for((long long)p->rows * p->w), 256, 0, S(stream)>>>(
+      par0, par1, rigid_mask, p->rows, p->w, p->y0, pt2(p->q0), pt2(p->q1), 0.0, 0.0, p->B_fwd, 2, nullptr, cand, count,
+      dev_state);
+  return check_launch("front_band/candidates");
+}
+
+int mrf_front_structures_band(const mrf_front_params* p, const double* par0, const double* par1,
+                              const uint8_t* zero_mask, double* S0, double* S1, double* dev_state, void* scratch,
+                              mrf_stream_t stream) {
+  MRF_CHECK_ARG(p && par0 && par1 && S0 && S1 && dev_state && scratch);
+  const long long n = (long long)p->rows * p->w;
+  long long fb = (n + 255) / 256;
+  if (fb > kFrontBlocks) fb = kFrontBlocks;
+  Box4 bx[2];
+  for (int f = 0; f < 2; ++f) {
+    bx[f].x0 = p->box[f][0]; bx[f].x1 = p->box[f][1]; bx[f].y0 = p->box[f][2]; bx[f].y1 = p->box[f][3];
+    bx[f].on = p->have_box[f];
+  }
+  double* partial = (double*)scratch;
+  k_front_structures<<<(unsigned)fb, 256, 0, S(stream)>>>(par0, par1, p->rows, p->w, p->y0, pt2(p->q0), pt2(p->q1),
+                                                          p->B_fwd, zero_mask, bx[0], bx[1], S0, S1, dev_state, partial);
+  int rc = check_launch("front_band/structures");
+  if (rc) return rc;
+  k_front_minmax<<<1, 256, 0, S(stream)>>>(partial, (int)fb, dev_state);
+  return check_launch("front_band/minmax");
 }
 
 }  // extern "C"

@@ -285,7 +285,8 @@ __global__ void k_label_range(double* __restrict__ st, int L) {
   if (i >= L) return;
   const double lo0 = st[MRF_STATE_MINMAX], hi0 = st[MRF_STATE_MINMAX + 1];
   const double lo1 = st[MRF_STATE_MINMAX + 2], hi1 = st[MRF_STATE_MINMAX + 3];
-  const bool nan = (lo0 != lo0) || (lo1 != lo1) || (hi0 != hi0) || (hi1 != hi1);
+  const bool nan = (lo0 != lo0) || (lo1 != lo1) || (hi0 != hi0) || (hi1 != hi1) ||
+                   (st[MRF_STATE_NANFLAG] != 0.0) || (st[MRF_STATE_NANFLAG + 1] != 0.0);
   const double qnan = __longlong_as_double(0x7FF8000000000000ll);
   const double start = nan ? qnan : 1.5 * fmin(lo0, lo1);
   const double stop = nan ? qnan : 1.5 * fmax(hi0, hi1);
@@ -461,6 +462,33 @@ int mrf_select_median_dev(const double* keys, const int* n_dev, size_t capacity,
   if (rc) return rc;
   k_select_median<<<1, 1, 0, S(stream)>>>(st, out_median);
   return check_launch("mrf_select_median_dev/median");
+}
+
+// ---- step-wise selection with device-side counts (row bands; see the header)
+int mrf_select_begin_dev(const int* n_total_dev, void* scratch, mrf_stream_t stream) {
+  MRF_CHECK_ARG(n_total_dev && scratch);
+  unsigned long long* st = (unsigned long long*)scratch;
+  k_select_init<<<1, 256, 0, S(stream)>>>(st, 0ull, st + kStWords, n_total_dev);
+  return check_launch("mrf_select_begin_dev");
+}
+int mrf_select_hist_dev(const double* keys, const int* n_local_dev, size_t capacity, void* scratch, mrf_stream_t stream) {
+  MRF_CHECK_ARG(keys && n_local_dev && scratch && capacity > 0);
+  unsigned long long* st = (unsigned long long*)scratch;
+  const unsigned blocks = (unsigned)((capacity + 255) / 256 < (size_t)kSelBlocks ? (capacity + 255) / 256 : kSelBlocks);
+  k_select_hist<<<blocks, 256, 0, S(stream)>>>(keys, capacity, st, st + kStWords, n_local_dev);
+  return check_launch("mrf_select_hist_dev");
+}
+int mrf_select_successor_dev(const double* keys, const int* n_local_dev, size_t capacity, void* scratch,
+                             mrf_stream_t stream) {
+  MRF_CHECK_ARG(keys && n_local_dev && scratch && capacity > 0);
+  const unsigned blocks = (unsigned)((capacity + 255) / 256 < (size_t)kSelBlocks ? (capacity + 255) / 256 : kSelBlocks);
+  k_select_successor<<<blocks, 256, 0, S(stream)>>>(keys, capacity, (unsigned long long*)scratch, n_local_dev);
+  return check_launch("mrf_select_successor_dev");
+}
+int mrf_select_median_state(const void* scratch, double* out_median, mrf_stream_t stream) {
+  MRF_CHECK_ARG(scratch && out_median);
+  k_select_median<<<1, 1, 0, S(stream)>>>((const unsigned long long*)scratch, out_median);
+  return check_launch("mrf_select_median_state");
 }
 
 int mrf_label_range_dev(double* dev_state, int n_labels, mrf_stream_t stream) {

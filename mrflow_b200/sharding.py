@@ -257,25 +257,147 @@ class PeerVolume:
         self.ptr = None
 
 
+# ------------------------------------------------------------------------------------------ resident bands
+class BandBuffers:
+    """Reusable HBM buffers of the banded device-resident pre-pass."""
+
+    def __init__(self, rows, w, dev="cuda"):
+        L = _lib.lib()
+        F64, I32, U8 = torch.float64, torch.int32, torch.uint8
+        self.par = [torch.empty((rows, w), dtype=F64, device=dev) for _ in range(2)]
+        self.S = [torch.empty((rows, w), dtype=F64, device=dev) for _ in range(2)]
+        self.cand = torch.empty(rows * w, dtype=F64, device=dev)
+        self.count = torch.zeros(1, dtype=I32, device=dev)
+        self.n_total = torch.zeros(1, dtype=I32, device=dev)
+        self.sums = torch.zeros(2, dtype=F64, device=dev)
+        self.state = torch.zeros(_lib.STATE_WORDS, dtype=F64, device=dev)
+        self.scratch = torch.empty(L.mrf_front_scratch_bytes(), dtype=U8, device=dev)
+        self.sel = torch.zeros(L.mrf_select_scratch_bytes(0), dtype=U8, device=dev)
+        words = self.sel.view(torch.int64)
+        self.sel_hist = words[_lib.SELECT_HIST_OFFSET // 8:_lib.SELECT_HIST_OFFSET // 8 + 256]
+        self.sel_sum = words[3:5]            # NaN count, count(keys <= kth)
+        self.sel_min = words[5:6]            # smallest order-key above kth (unsigned)
+        self.sign = torch.tensor([-2 ** 63], dtype=torch.int64, device=dev)
+
+
+def _front_params(band, homographies, q_ar, n_labels, B_fwd=1.0):
+    p = _lib.FrontParams()
+    p.rows, p.w, p.y0, p.frame_h = band.rows, band.w, band.y0, band.frame_h
+    p.Hinv0 = device._mat(np.linalg.inv(np.asarray(homographies[0], dtype=np.float64)))
+    p.Hinv1 = device._mat(np.linalg.inv(np.asarray(homographies[1], dtype=np.float64)))
+    p.q0 = device._pt(q_ar[0]); p.q1 = device._pt(q_ar[1])
+    p.B_fwd = float(B_fwd)
+    p.n_labels = int(n_labels)
+    w, h = band.w, band.frame_h
+    for f in range(2):
+        q = q_ar[f]
+        bx0 = max(0, min(w - 1, int(q[0] - 10))); bx1 = max(0, min(w - 1, int(q[0] + 10)))
+        by0 = max(0, min(h - 1, int(q[1] - 10))); by1 = max(0, min(h - 1, int(q[1] + 10)))
+        p.have_box[f] = int(not (bx0 == w - 1 or bx1 == 0 or by0 == h - 1 or by1 == 0))
+        for k, v in enumerate((bx0, bx1, by0, by1)):
+            p.box[f][k] = v
+    return p
+
+
+def banded_front(band, homographies, q_ar, rigid_mask, zero_mask, buf, group=None, n_labels=pp.N_LABELS):
+    """The pre-pass of build_cost_volume for one row band with every whole-frame scalar kept on the device:
+    kernels on this band, tiny NCCL all-reduces (2 doubles, 1 int, 8 x 2 KB histograms, 3 words, 6 doubles)
+    enqueued on the same stream in between -- no host synchronisation.  Leaves mu, B, labels in
+    ``buf.state`` (identical on every rank) and this band's parallax / structures in ``buf``."""
+    L = _lib.lib()
+    P = lambda t: C.c_void_p(t.data_ptr())
+    st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    p = _front_params(band, homographies, q_ar, n_labels)
+    SUM, MIN, MAX = dist.ReduceOp.SUM, dist.ReduceOp.MIN, dist.ReduceOp.MAX
+    fl = band.flow
+    check(L.mrf_front_parallax_band(C.byref(p), P(fl[0][0]), P(fl[0][1]), P(fl[1][0]), P(fl[1][1]), P(buf.par[0]), P(buf.par[1]),
+                                    P(buf.sums), P(buf.scratch), st), "mrf_front_parallax_band")
+    dist.all_reduce(buf.sums, op=SUM, group=group)
+    buf.state[_lib.STATE_MU:_lib.STATE_MU + 2] = buf.sums / float(band.frame_h * band.w)        # compute_structure.py:84
+    check(L.mrf_front_candidates_band(C.byref(p), P(buf.par[0]), P(buf.par[1]), P(rigid_mask), P(buf.state), P(buf.cand),
+                                      P(buf.count), st), "mrf_front_candidates_band")
+    buf.n_total.copy_(buf.count)
+    dist.all_reduce(buf.n_total, op=SUM, group=group)
+    cap = band.rows * band.w
+    check(L.mrf_select_begin_dev(P(buf.n_total), P(buf.sel), st), "mrf_select_begin_dev")
+    for _ in range(8):
+        check(L.mrf_select_hist_dev(P(buf.cand), P(buf.count), cap, P(buf.sel), st), "mrf_select_hist_dev")
+        dist.all_reduce(buf.sel_hist, op=SUM, group=group)
+        check(L.mrf_select_pick(P(buf.sel), st), "mrf_select_pick")
+    check(L.mrf_select_successor_dev(P(buf.cand), P(buf.count), cap, P(buf.sel), st), "mrf_select_successor_dev")
+    dist.all_reduce(buf.sel_sum, op=SUM, group=group)
+    buf.sel_min.bitwise_xor_(buf.sign)                     # unsigned order -> signed order for MIN
+    dist.all_reduce(buf.sel_min, op=MIN, group=group)
+    buf.sel_min.bitwise_xor_(buf.sign)
+    check(L.mrf_select_median_state(P(buf.sel), C.c_void_p(buf.state.data_ptr() + 8 * _lib.STATE_B), st),
+          "mrf_select_median_state")                       # B_b, compute_structure.py:221
+    check(L.mrf_front_structures_band(C.byref(p), P(buf.par[0]), P(buf.par[1]), P(zero_mask), P(buf.S[0]), P(buf.S[1]),
+                                      P(buf.state), P(buf.scratch), st), "mrf_front_structures_band")
+    mm = buf.state[_lib.STATE_MINMAX:_lib.STATE_MINMAX + 4]
+    lo, hi = mm[0::2].contiguous(), mm[1::2].contiguous()
+    flags = buf.state[_lib.STATE_NANFLAG:_lib.STATE_NANFLAG + 2]
+    dist.all_reduce(lo, op=MIN, group=group); dist.all_reduce(hi, op=MAX, group=group); dist.all_reduce(flags, op=MAX, group=group)
+    mm[0::2] = lo; mm[1::2] = hi
+    check(L.mrf_label_range_dev(P(buf.state), int(n_labels), st), "mrf_label_range_dev")
+    return buf
+
+
+def banded_pass_resident(band, homographies, epipoles, rigid_mask, stats, buf=None, rho="lorentzian", sigma=1.0,
+                         interp="cubic", range_mask="rigid_only", variant="staged", out_ptr=(None, None), plane_stride=0,
+                         want_cost=True, halo_miss=None, events=None, masks=None, channels=None):
+    """Row-band cost volumes with the device-resident pre-pass.  Returns dict(cost, mins, argmins, q, buffers)."""
+    q_new = [stats.epipole(lambda f=f: _band_epipole(band, homographies, epipoles, rigid_mask, f), np.asarray(epipoles[f], np.float64), band)
+             for f in range(2)]
+    buf = buf or BandBuffers(band.rows, band.w, band.device)
+    if masks is None:
+        nonrigid = (rigid_mask == 0).to(torch.uint8)
+        masks = (nonrigid, rigid_mask if range_mask == "as_written" else nonrigid)
+    nonrigid, zero_mask = masks
+    banded_front(band, homographies, q_new, rigid_mask, zero_mask, buf, group=stats.group)
+    ref64, tex = channels if channels is not None else pp.channels(band)
+    res = pp.cost_volumes(band, ref64, tex, None, homographies, q_new, None, None, nonrigid, rho=rho, rho_param=sigma,
+                          interp=interp, variant=variant, want_cost=want_cost, halo_miss=halo_miss, events=events,
+                          out_ptr=out_ptr, plane_stride=plane_stride, state=buf.state)
+    return dict(cost=[res[0][0], res[1][0]], mins=[res[0][1], res[1][1]], argmins=[res[0][2], res[1][2]], q=q_new, buffers=buf)
+
+
+def _band_epipole(band, homographies, epipoles, rigid_mask, f):
+    q = np.asarray(epipoles[f], dtype=np.float64)
+    Hinv = np.linalg.inv(np.asarray(homographies[f], dtype=np.float64))
+    ur, vr, _, _ = device.flow_to_parallax(band.flow[f][0], band.flow[f][1], Hinv, q, y0=band.y0, want_parallax=False,
+                                           want_dists=False)
+    return pp.correct_epipole(ur, vr, q, rigid_mask, band.y0, band.frame_h)
+
+
 # ------------------------------------------------------------------------------------------ driver
 def banded_cost_volume(t, stats, rank, world, rho="lorentzian", sigma=1.0, interp="cubic", range_mask="rigid_only",
-                       variant="staged", peer=(None, None), keep_local=True, halo=None, timers=None):
+                       variant="staged", peer=(None, None), keep_local=True, halo=None, timers=None, resident=True):
     """build_cost_volume for this rank's band of the host triplet ``t`` (dict as synth.make_triplet
-    returns).  Returns dict(cost, S, mu, B, q, labels, mins, argmins, rows, halo)."""
+    returns).  ``resident=True`` keeps the whole-frame scalars on the device (``banded_pass_resident``);
+    ``False`` drives the statistics through the host (``BandStats`` / ``DistSelect``, the protocol the gloo
+    tests cover) -- same kernels, bit-identical results.
+    Returns dict(cost, S, mu, B, q, labels, mins, argmins, rows, halo)."""
     from .pipeline.build_cost_volume import cost_volume_pass
     h, w = t["shape"]
     y0, y1 = band_plan(h, world)[rank]
     rig = np.asarray(t["rigidity"])
-    # structure pass needs only this band's flows; images come with the halo once it is known
     halo_rows = 32 if halo is None else int(halo)
     while True:
         band = pp.Band.from_host(t["images"], t["flow"], rig, None, rows=(y0, y1), halo=halo_rows)
         miss = torch.zeros(1, dtype=torch.int32, device="cuda")
         outs = tuple((p.band_ptr(y0) if p is not None else None) for p in peer)
-        res = cost_volume_pass(band, t["homographies"], t["epipoles"], rig[y0:y1] > 0, stats, rho=rho, sigma=sigma,
-                               interp=interp, range_mask=range_mask, variant=variant, halo_miss=miss,
-                               want_cost=keep_local, out_ptr=outs, plane_stride=(h * w if outs[0] is not None else 0),
-                               events=timers)
+        stride = h * w if outs[0] is not None else 0
+        if resident:
+            mask = torch.from_numpy((rig[y0:y1] > 0).astype(np.uint8)).cuda()
+            r = banded_pass_resident(band, t["homographies"], t["epipoles"], mask, stats, rho=rho, sigma=sigma, interp=interp,
+                                     range_mask=range_mask, variant=variant, out_ptr=outs, plane_stride=stride,
+                                     want_cost=keep_local, halo_miss=miss, events=timers)
+            mu, B, labels = pp.state_to_host(r["buffers"].state)
+            res = (r["cost"], r["buffers"].S, mu, B, r["q"], labels, r["mins"], r["argmins"])
+        else:
+            res = cost_volume_pass(band, t["homographies"], t["epipoles"], rig[y0:y1] > 0, stats, rho=rho, sigma=sigma,
+                                   interp=interp, range_mask=range_mask, variant=variant, halo_miss=miss,
+                                   want_cost=keep_local, out_ptr=outs, plane_stride=stride, events=timers)
         n_miss = stats.total(int(miss.cpu()[0]))
         if n_miss == 0:
             break
@@ -306,11 +428,18 @@ def bench_bands(args, hw, steps, warm, metric, unit, workload, ClockSampler):
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
     kernel_events = []
 
+    nonrigid = (rigid_mask == 0).to(torch.uint8)
+    bbuf = BandBuffers(y1 - y0, w)
+    miss = torch.zeros(1, dtype=torch.int32, device="cuda")
+    cost_local = (torch.empty((L, y1 - y0, w), dtype=torch.float32, device="cuda"),
+                  torch.empty((L, y1 - y0, w), dtype=torch.float32, device="cuda"))
+
     def step(events=None, gather=True):
-        outs = tuple(p.band_ptr(y0) for p in peers) if gather else (None, None)
-        return cost_volume_pass(band, t["homographies"], t["epipoles"], rigid_mask, stats, interp=args.interp,
-                                range_mask="rigid_only", variant=args.variant, want_cost=not gather, out_ptr=outs,
-                                plane_stride=(h * w if gather else 0), events=events)
+        outs = tuple(p.band_ptr(y0) for p in peers) if gather else tuple(c.data_ptr() for c in cost_local)
+        return banded_pass_resident(band, t["homographies"], t["epipoles"], rigid_mask, stats, buf=bbuf, interp=args.interp,
+                                    range_mask="rigid_only", variant=args.variant, out_ptr=outs,
+                                    plane_stride=(h * w if gather else 0), halo_miss=miss, events=events,
+                                    masks=(nonrigid, nonrigid), channels=pp.channels(band))
 
     def barrier():
         torch.cuda.synchronize(); dist.barrier(); torch.cuda.synchronize()
@@ -348,15 +477,17 @@ def bench_bands(args, hw, steps, warm, metric, unit, workload, ClockSampler):
     bytes_launch = rows * w * (L * 4 + 4 + 12 + 2 + 6)
     ach = bytes_launch / (float(np.mean(kms)) * 1e-3) / 1e9
     barrier()
+    n_miss = stats.total(int(miss.cpu()[0]))
     for p in peers:
         p.close()
     if rank == 0:
+        assert n_miss == 0, "a timed step sampled outside its halo"
         line = {"metric": metric, "value": units * steps / (tot_ms * 1e-3), "unit": unit, "n_gpus": world, "steps": steps,
                 "warmup": warm, "ms_per_step": tot_ms / steps, "higher_is_better": True, "scaling": "strong",
                 "vs_baseline": None, "dtype": "f64 geometry / f32 sampling", "data": "synthetic",
                 "config": {"workload": workload, "labels": L, "frames": 2, "interp": args.interp, "variant": args.variant,
-                           "range_mask": "rigid_only", "parallelism": "row bands x%d, halo %d rows, peer-store gather to rank 0"
-                           % (world, halo_rows), "l2": "flushed between timed steps"},
+                           "range_mask": "rigid_only", "parallelism": "row bands x%d, halo %d rows, device-resident statistics "
+                           "(NCCL all-reduces on the stream), peer-store gather to rank 0" % (world, halo_rows), "l2": "flushed between timed steps"},
                 "compute_only": {"value": units * steps / (results["compute_only"][0] * 1e-3), "ms_per_step": results["compute_only"][0] / steps},
                 "clocks": clk, "e2e": None, "gpu_launches": int(launches),
                 "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,

@@ -35,6 +35,12 @@ def _worker(rank, world, port, queue):
         # deliberately small first halo: the halo_miss retry must kick in
         res = sharding.banded_cost_volume(t, stats, rank, world, peer=peers, halo=2)
         torch.cuda.synchronize(); dist.barrier()
+        # the host-driven statistics protocol (what the gloo tests cover) gives the same bits
+        res_h = sharding.banded_cost_volume(t, stats, rank, world, halo=res["halo"], resident=False)
+        out["host_equals_resident"] = bool(res_h["mu"] == res["mu"] and res_h["B"] == res["B"]
+                                           and np.array_equal(res_h["labels"], res["labels"])
+                                           and all(torch.equal(res_h["argmins"][f], res["argmins"][f]) for f in range(2)))
+        torch.cuda.synchronize(); dist.barrier()
         out["halo"] = res["halo"]
         y0, y1 = res["rows"]
         if rank == 0:
@@ -92,5 +98,6 @@ def test_two_band_volume_equals_whole_frame():
     np.testing.assert_allclose(o["mu"][0], o["mu"][1], rtol=1e-14)
     np.testing.assert_allclose(o["B"][0], o["B"][1], rtol=1e-11)
     assert o["labels_close"]
+    assert res[0]["host_equals_resident"] and res[1]["host_equals_resident"]
     for f in range(2):
         assert o["equal%d" % f] and o["argmin_equal%d" % f]

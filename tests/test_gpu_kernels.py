@@ -509,3 +509,81 @@ def test_resident_pass_equals_host_driven_pass(dev, trip):
             assert np.array_equal(r["q"][f], a[4][f])
             assert torch.equal(r["buffers"].S[f], a[1][f]) or eq(r["buffers"].S[f].cpu(), a[1][f].cpu())
             assert torch.equal(r["cost"][f], a[0][f]) and torch.equal(r["argmins"][f], a[7][f])
+
+
+# ------------------------------------------------------------------------------------------ edge cases
+def _tiny_case(h, w, seed):
+    rs = np.random.RandomState(seed)
+    ch = [rs.rand(h, w, 3) * np.array([255.0, 20.0, 20.0]) for _ in range(3)]
+    H = np.array([[1.001, 0.002, 0.4], [-0.001, 0.999, -0.3], [1e-5, -2e-5, 1.0]])
+    q = np.array([w * 0.4, h * 0.6])
+    y, x = np.mgrid[:h, :w]
+    mu = np.sqrt((x - q[0]) ** 2 + (y - q[1]) ** 2).mean()
+    return ch, H, q, mu
+
+
+def _run_both(dev, ch, H, q, mu, B, labels, mode="cubic", variant="staged", rig=None, occ=None):
+    from oracle import hotpath as hp
+    h, w = ch[1].shape[:2]
+    rig = np.ones((h, w)) if rig is None else rig
+    occ = np.zeros((h, w), bool) if occ is None else occ
+    with np.errstate(all="ignore"):
+        want, wmin, wam = hp.cost_volume(ch, rig, [occ, occ], [H, H], [B, B], [mu, mu], [q, q], labels, mode=mode, frames=(1,))
+    tex = cu(np.concatenate([ch[2].astype(np.float32), np.zeros((h, w, 1), np.float32)], axis=2))
+    cost, mn, am = dev.cost_volume(cu(ch[1]), tex, cu(np.asarray(labels, dtype=np.float64)), H, q, mu, B,
+                                   nonrigid=cu((rig == 0).astype(np.uint8)), occluded=cu(occ.astype(np.uint8)),
+                                   interp=mode, variant=variant)
+    return cost.cpu().numpy(), mn.cpu().numpy(), am.cpu().numpy(), want[0], wmin[0], wam[0]
+
+
+@pytest.mark.parametrize("shape", [(2, 2), (3, 5), (5, 7), (9, 33), (8, 32), (17, 31)])
+@pytest.mark.parametrize("mode", ["cubic", "linear"])
+def test_cost_volume_tiny_and_ragged_frames(dev, shape, mode):
+    """Frames smaller than a tile, smaller than the bicubic footprint, and with ragged tile edges: every
+    sample is a border sample (OpenCV's tap-by-tap order, replicated taps)."""
+    ch, H, q, mu = _tiny_case(*shape, seed=shape[0] * 100 + shape[1])
+    labels = np.linspace(-2.0, 3.0, 9)
+    for variant in ("staged", "gather"):
+        got, mn, am, want, wmin, wam = _run_both(dev, ch, H, q, mu, 0.6, labels, mode=mode, variant=variant)
+        _check_costs(got, want, "%s %s" % (shape, variant))
+        _check_argmin(am, want)
+        assert eq(mn, got.min(axis=0))
+
+
+def test_cost_volume_label_extremes(dev):
+    """One label, 256 labels, a label exactly at the pole of the parallax formula (B*A/mu == 1: division
+    by zero in the reference), huge / infinite / NaN labels: the cold exact path must reproduce numpy's
+    inf / NaN propagation (samples leave the frame -> residual 0 -> rho(0))."""
+    ch, H, q, mu = _tiny_case(24, 40, seed=5)
+    B = 0.5
+    pole = mu / B                                    # B * a / mu - 1 == 0 exactly for this a? check both sides too
+    for labels in ([1.3], list(np.linspace(-4, 6, 256)), [0.5, pole, np.nextafter(pole, 0), np.nextafter(pole, 1e9), 2.0],
+                   [1e300, -1e300, np.inf, -np.inf, np.nan, 1.0], [0.0, -0.0, 1e-310, 1.0]):
+        got, mn, am, want, wmin, wam = _run_both(dev, ch, H, q, mu, B, labels)
+        assert not np.isnan(got).any()
+        _check_costs(got, want, "labels %s.." % str(labels[:3]))
+        _check_argmin(am, want)
+
+
+def test_cost_volume_degenerate_inputs(dev):
+    """Non-finite flow-free inputs: NaN / inf in the homography, epipole on a pixel centre (|v| = 0, the 0.5
+    clamp of :212), mu tiny, all pixels non-rigid or occluded."""
+    ch, H, q, mu = _tiny_case(16, 48, seed=6)
+    labels = np.linspace(-1.0, 2.0, 5)
+    # epipole exactly on a pixel
+    got, _, am, want, _, _ = _run_both(dev, ch, H, np.array([20.0, 7.0]), mu, 0.4, labels)
+    _check_costs(got, want, "epipole on pixel"); _check_argmin(am, want)
+    # projective row that sends a line of the frame to infinity (den crosses 0 inside the frame)
+    Hs = H.copy(); Hs[2] = [0.05, 0.0, -1.0]
+    got, _, am, want, _, _ = _run_both(dev, ch, Hs, q, mu, 0.4, labels)
+    _check_costs(got, want, "singular den"); _check_argmin(am, want)
+    for bad in (np.nan, np.inf):
+        Hb = H.copy(); Hb[0, 2] = bad
+        got, _, _, want, _, _ = _run_both(dev, ch, Hb, q, mu, 0.4, labels)
+        _check_costs(got, want, "H with %s" % bad)
+    # everything masked
+    h, w = ch[1].shape[:2]
+    got, mn, am, want, _, _ = _run_both(dev, ch, H, q, mu, 0.4, labels, rig=np.zeros((h, w)))
+    assert (got == 0).all() and (am == 0).all()
+    got, _, _, want, _, _ = _run_both(dev, ch, H, q, mu, 0.4, labels, occ=np.ones((h, w), bool))
+    assert (got == 0).all()

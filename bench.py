@@ -235,8 +235,6 @@ def run_ours(args):
     rig_host = t["rigidity"] > 0
     band = pp.Band.from_host(t["images"], t["flow"], t["rigidity"], None)
     rigid_mask = torch.from_numpy(rig_host.astype(np.uint8)).cuda()
-    nonrigid = (rigid_mask == 0).to(torch.uint8)
-    stats = pp.LocalStats()
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")    # > 126 MB L2
     kernel_events = []
 

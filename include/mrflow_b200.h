@@ -77,6 +77,11 @@ int mrf_flow_to_parallax(const float* u, const float* v, int rows, int w, int y0
                          float* u_res, float* v_res, double* parallax, double* dists,
                          mrf_stream_t stream);
 
+/* ---- a2 on its own: pipeline/compute_structure.py:517-537 (flow2parallax) of a given flow (fp64; an
+ * fp32 residual promoted, as numpy promotes fp32 * fp64).  foe_vectors fp64 [rows,w,2]. */
+int mrf_flow2parallax(const double* u, const double* v, int rows, int w, int y0, const double* q_host,
+                      double* parallax, double* foe_vectors, double* dists, mrf_stream_t stream);
+
 /* ---- mu of pipeline/compute_structure.py:84: sum over the band of ||p - q|| (fp64,
  * deterministic two-stage reduction); out_sum is ONE double on the device.
  * scratch: mrf_reduce_scratch_bytes() bytes. */

@@ -49,6 +49,7 @@ SIGNATURES = {
     "mrf_launch_count": (C.c_longlong, []),
     "mrf_reset_launch_count": (None, []),
     "mrf_flow_to_parallax": (_I, [_P, _P, _I, _I, _I, _DP, _DP, _P, _P, _P, _P, _P]),
+    "mrf_flow2parallax": (_I, [_P, _P, _I, _I, _I, _DP, _P, _P, _P, _P]),
     "mrf_reduce_scratch_bytes": (_Z, []),
     "mrf_epipole_dist_sum": (_I, [_I, _I, _I, _DP, _P, _P, _P]),
     "mrf_parallax_to_structure": (_I, [_P, _I, _I, _I, _DP, _D, _D, _P, _P]),

@@ -60,6 +60,26 @@ k_flow_to_parallax(const float* __restrict__ u, const float* __restrict__ v, int
   }
 }
 
+// a2 on its own: pipeline/compute_structure.py:517-537 (flow2parallax) for a given residual flow
+// (fp64, an fp32 residual promoted): parallax, unit vectors to the epipole [rows,w,2], distances
+__global__ void __launch_bounds__(256)
+k_flow2parallax(const double* __restrict__ u, const double* __restrict__ v, int rows, int w, int y0, Pt2 q,
+                double* __restrict__ parallax, double* __restrict__ foe_vectors, double* __restrict__ dists) {
+  const long long n = (long long)rows * w;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int yl = (int)(i / w);
+    const int x = (int)(i - (long long)yl * w);
+    const double fx = q.x - (double)x, fy = q.y - (double)(yl + y0);
+    const double d = sqrt(fx * fx + fy * fy);
+    const double dn = fmax(d, 1e-3);
+    const double nx = fx / dn, ny = fy / dn;
+    if (parallax) parallax[i] = u[i] * nx + v[i] * ny;
+    if (foe_vectors) { foe_vectors[2 * i] = nx; foe_vectors[2 * i + 1] = ny; }
+    if (dists) dists[i] = d;
+  }
+}
+
 // ------------------------------------------------------------------------------- mu
 // pipeline/compute_structure.py:84 -- sum of ||p-q|| over the band; fixed grid, fixed tree ->
 // deterministic.  (numpy's pairwise sum rounds differently by O(1e-16) relative.)
@@ -557,6 +577,14 @@ int mrf_flow_to_parallax(const float* u, const float* v, int rows, int w, int y0
   k_flow_to_parallax<<<grid_for(n), 256, 0, S(stream)>>>(u, v, rows, w, y0, mat3(Hinv_host), pt2(q_host),
                                                         u_res, v_res, parallax, dists);
   return check_launch("mrf_flow_to_parallax");
+}
+
+int mrf_flow2parallax(const double* u, const double* v, int rows, int w, int y0, const double* q_host,
+                      double* parallax, double* foe_vectors, double* dists, mrf_stream_t stream) {
+  MRF_CHECK_ARG(u && v && rows > 0 && w > 0 && q_host && (parallax || foe_vectors || dists));
+  k_flow2parallax<<<grid_for((long long)rows * w), 256, 0, S(stream)>>>(u, v, rows, w, y0, pt2(q_host), parallax,
+                                                                       foe_vectors, dists);
+  return check_launch("mrf_flow2parallax");
 }
 
 size_t mrf_reduce_scratch_bytes(void) { return sizeof(double) * kRedBlocks * 2; }

@@ -62,6 +62,19 @@ def flow_to_parallax(u, v, Hinv, q, y0=0, want_residual=True, want_parallax=True
     return ur, vr, par, dst
 
 
+def flow2parallax(u, v, q, y0=0):
+    """pipeline/compute_structure.py:517-537 for a given flow (fp64).  Returns (parallax, foe_vectors
+    [rows,w,2], dists)."""
+    _chk(u, F64, "u"); _chk(v, F64, "v")
+    rows, w = u.shape
+    par = torch.empty((rows, w), dtype=F64, device=u.device)
+    vec = torch.empty((rows, w, 2), dtype=F64, device=u.device)
+    dst = torch.empty((rows, w), dtype=F64, device=u.device)
+    check(_lib.lib().mrf_flow2parallax(_p(u), _p(v), rows, w, y0, _pt(q), _p(par), _p(vec), _p(dst), _stream()),
+          "mrf_flow2parallax")
+    return par, vec, dst
+
+
 def epipole_dist_sum(rows, w, q, y0=0, device="cuda"):
     """Sum over the band of ||p - q|| (the numerator of mu, pipeline/compute_structure.py:84).
     Returns a 1-element fp64 tensor."""

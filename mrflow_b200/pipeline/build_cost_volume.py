@@ -13,7 +13,7 @@ import numpy as np
 import torch
 
 from .. import device, planeparallax as pp
-from .._host import down, flag, require_cuda, up
+from .._host import flag, require_cuda
 
 N_RANGES = pp.N_LABELS     # pipeline/build_cost_volume.py:50
 

@@ -37,22 +37,11 @@ def parallax2normedstructure(parallax, q, B, mu):
 
 
 def flow2parallax(u, v, q):
-    """pipeline/compute_structure.py:517-537.  ``u, v`` are residual flows (fp32 as
-    get_residual_flow returns them).  Returns (parallax, foe_vectors, foe_dists)."""
+    """pipeline/compute_structure.py:517-537.  ``u, v``: residual flow (fp32 as get_residual_flow returns
+    it, or fp64).  Returns (parallax, foe_vectors, foe_dists) as fp64 arrays."""
     require_cuda()
-    u = np.asarray(u); v = np.asarray(v)
-    h, w = u.shape
-    # identity homography: f32(f32(x+u)) - f32(x) == u for fp32 u on the pixel grid only when the sum
-    # is exact, so the parallax kernel is fed through the residual path with H = I and the result is
-    # recomputed from (u, v) directly below.
-    q = np.asarray(q, dtype=np.float64)
-    y, x = np.mgrid[:h, :w]
-    zero = up(np.zeros((h, w), np.float32), np.float32)
-    _, _, _, dists = device.flow_to_parallax(zero, zero, np.eye(3), q, want_residual=False, want_parallax=False)
-    dists = down(dists)
-    nx = (q[0] - x) / np.maximum(dists, 1e-3)
-    ny = (q[1] - y) / np.maximum(dists, 1e-3)
-    return u * nx + v * ny, np.dstack((nx, ny)), dists
+    par, vec, dst = device.flow2parallax(up(u, np.float64), up(v, np.float64), q)
+    return down(par), down(vec), down(dst)
 
 
 def correct_epipole(u, v, q, rigidity):

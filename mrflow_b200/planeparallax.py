@@ -10,13 +10,10 @@ bands over several GPUs.
 
 All citations are paths inside the reference repository.
 """
-import ctypes as C
-
 import numpy as np
 import torch
 
 from . import _lib, device
-from ._lib import check
 
 N_LABELS = 51                         # pipeline/build_cost_volume.py:50
 CHANNEL_WEIGHTS = (0.01, 1.0, 1.0)    # structure_refinement/optimize_structure_single_scale.py:350,371

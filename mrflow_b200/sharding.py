@@ -21,7 +21,6 @@ larger halo.
 import ctypes as C
 import json
 import os
-import time
 
 import numpy as np
 import torch

@@ -359,3 +359,15 @@ def test_triplet_stream_equals_single_calls(trip):
         assert r["mu"] == list(want[2]) and r["B"] == list(want[3]) and np.array_equal(r["labels"], want[5])
         _, u, vv = s2f.combine_flow(want[1][1], v["flow"][1], v["rigidity"], want[4], want[2], v["homographies"], want[3])
         assert np.array_equal(r["u"], u, equal_nan=True) and np.array_equal(r["v"], vv, equal_nan=True)
+
+
+def test_flow2parallax_and_structure_helpers(golden):
+    """The small public helpers of pipeline/compute_structure.py (:25-33, :517-537) against the reference's outputs."""
+    from mrflow_b200.pipeline import compute_structure as cs
+    tag, g = golden
+    t = golden_triplet(tag)
+    for f, B in ((0, -0.37), (1, 0.41)):
+        p, vec, d = cs.flow2parallax(g["u_res%d" % f], g["v_res%d" % f], t["epipoles"][f])
+        assert np.array_equal(p, g["parallax%d" % f]) and np.array_equal(d, g["dists%d" % f]) and vec.shape == p.shape + (2,)
+        S = cs.parallax2normedstructure(p, t["epipoles"][f], B, g["mu"][f])
+        assert np.array_equal(S, g["structure%d" % f], equal_nan=True)

@@ -204,9 +204,9 @@ __device__ __forceinline__ double rcp_rn_tame(double d) {
 // tame exponent and significand not all ones
 __device__ __forceinline__ bool tame_divisor(double v) {
   const unsigned hi = (unsigned)__double2hiint(v);
-  const unsigned ex = (hi >> 20) & 0x7ffu;
   const bool ones = ((hi & 0xfffffu) == 0xfffffu) && ((unsigned)__double2loint(v) == 0xffffffffu);
-  return ((ex - 923u) <= 200u) && !ones;
+  // |v| in [2^-100, 2^101): biased exponent 923 .. 1123, tested on the high word with the sign cleared
+  return (((hi & 0x7fffffffu) - 0x39b00000u) < 0x0c900000u) && !ones;
 }
 
 // One sample evaluated with plain IEEE divisions and the library log -- the arithmetic of the
@@ -303,9 +303,14 @@ k_cost_volume(const __grid_constant__ CVArgs a) {
     const double al = g_labels[l] * g_scale;
     const double ab = al * g_B;
     const double den = ab / g_mu - 1.0;
+    // a label for which the reciprocal sequence is not proven exact (pole of the formula, huge or
+    // non-finite operands) gets rden = NaN: r, den and the window test below then fail on their own
+    // and the sample goes down the plain-division path
     LabelRec rec;
-    rec.ab = ab; rec.den = den; rec.rden = 1.0 / den;
-    rec.safe = (tame(den) && (ab == 0.0 || tame(ab))) ? 1.0 : 0.0;
+    const bool safe = tame(den) && (ab == 0.0 || tame(ab));
+    rec.ab = ab; rec.den = den;
+    rec.rden = safe ? 1.0 / den : __longlong_as_double(0x7FF8000000000000ll);
+    rec.safe = safe ? 1.0 : 0.0;
     s_lab[l] = rec;
   }
   if (threadIdx.x >= 32 && threadIdx.x < 64) {
@@ -428,7 +433,8 @@ k_cost_volume(const __grid_constant__ CVArgs a) {
   asm volatile("" : "+d"(xk), "+d"(yk));
   const float cost_dead = (float)rho_eval(a.rho, 0.0, a.rho_param);
   const bool lor_fast = (a.rho == MRF_RHO_LORENTZIAN) && tame(a.s2);
-  const double n_ok = ((n == 0.0) || tame(n)) ? 1.0 : 0.0;
+  // a pixel whose n is not tame poisons its own fast path the same way
+  const double n_fast = ((n == 0.0) || tame(n)) ? n : __longlong_as_double(0x7FF8000000000000ll);
   float best = 0.f; int best_l = 0;
   // this pixel's first cost element; without a volume the stores land on the pixel's own min / argmin
   // slot (rewritten after the loop), so the loop needs no null test
@@ -459,11 +465,11 @@ k_cost_volume(const __grid_constant__ CVArgs a) {
         if (l == 0) { best = cost_dead; best_l = 0; }
         continue;
       }
-      double ab, dl, rdl, safe;
+      double ab, dl, rdl;
       asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(ab), "=d"(dl) : "r"(lab_s + (uint32_t)l * 32u));
-      asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(rdl), "=d"(safe) : "r"(lab_s + (uint32_t)l * 32u + 16u));
+      asm volatile("ld.shared.f64 %0, [%1];" : "=d"(rdl) : "r"(lab_s + (uint32_t)l * 32u + 16u));
       // r = A*B*n / (B*A/mu - 1)  :221
-      const double r = div_rc(ab * n, dl, rdl);
+      const double r = div_rc(ab * n_fast, dl, rdl);
       const double xn = xk + r * t1, yn = yk + r * t2;        // :224-235
       // interpolate_through_H.py:31-35
       const double den = (xn * a.H.m[6] + yn * a.H.m[7]) + a.H.m[8];
@@ -472,8 +478,8 @@ k_cost_volume(const __grid_constant__ CVArgs a) {
       const double rd = rcp_rn_tame(den);
       const double X = div_rc(Xn, den, rd);
       const double Y = div_rc(Yn, den, rd);
-      // every condition under which the sequences above are not proven exact
-      const bool exact = (safe * n_ok != 0.0) && tame_divisor(den);
+      // every condition under which the sequences above are not proven exact ends in a NaN or wild den
+      const bool exact = tame_divisor(den);
       const bool inside = (X >= 0.0) && (X <= inside_hi_x) && (Y >= 0.0) && (Y <= inside_hi_y);   // :39
       const float xf = (float)X, yf = (float)Y;               // interpolation.py:77-78
       // cv2.remap's quantisation; inside the frame |coord*32| < 2^31 and the int16 saturation cannot
@@ -538,11 +544,11 @@ k_cost_volume(const __grid_constant__ CVArgs a) {
     for (int l = 0; l < L; ++l, cost_off += cost_step) {
       float cf = cost_dead;
       if (!dead) {
-        double ab, dl, rdl, safe;
+        double ab, dl, rdl;
         asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(ab), "=d"(dl) : "r"(lab_s + (uint32_t)l * 32u));
-        asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(rdl), "=d"(safe) : "r"(lab_s + (uint32_t)l * 32u + 16u));
+        asm volatile("ld.shared.f64 %0, [%1];" : "=d"(rdl) : "r"(lab_s + (uint32_t)l * 32u + 16u));
         // r = A*B*n / (B*A/mu - 1)  :221
-        const double r = div_rc(ab * n, dl, rdl);
+        const double r = div_rc(ab * n_fast, dl, rdl);
         const double xn = xk + r * t1, yn = yk + r * t2;      // :224-235
         // interpolate_through_H.py:31-35
         const double den = (xn * a.H.m[6] + yn * a.H.m[7]) + a.H.m[8];
@@ -552,7 +558,7 @@ k_cost_volume(const __grid_constant__ CVArgs a) {
         const double X = div_rc(Xn, den, rd);
         const double Y = div_rc(Yn, den, rd);
         // every condition under which the sequences above are not proven exact
-        const bool exact = (safe * n_ok != 0.0) && tame_divisor(den);
+        const bool exact = tame_divisor(den);
         const bool inside = (X >= 0.0) && (X <= a.wm1) && (Y >= 0.0) && (Y <= a.hm1);   // :39
         if (!exact) {
           cf = slow_sample_cost<INTERP>(a, ab, dl, n, xk, yk, t1, t2, s_ref[0][threadIdx.x], s_ref[1][threadIdx.x],

@@ -61,6 +61,39 @@ k_erode3(const uint8_t* __restrict__ src, int h, int w, uint8_t* __restrict__ ds
   dst[(long long)y * w + x] = m;
 }
 
+// pipeline/optimize_variational_refinement.py:20-42: cv2.medianBlur(uint8 0/1 map, 3) (BORDER_REPLICATE:
+// the median of nine 0/1 values is 1 iff at least five are set), then the occlusion-aware merge of the
+// two normed structures.  bool * fp64 products are written as multiplications by 0.0 / 1.0 so that
+// inf / NaN propagate exactly as in numpy.
+__device__ __forceinline__ bool median3_bit(const uint8_t* __restrict__ m, int h, int w, int x, int y) {
+  int cnt = 0;
+#pragma unroll
+  for (int dy = -1; dy <= 1; ++dy) {
+    const int yy = max(0, min(h - 1, y + dy));
+#pragma unroll
+    for (int dx = -1; dx <= 1; ++dx) cnt += m[(long long)yy * w + max(0, min(w - 1, x + dx))] ? 1 : 0;
+  }
+  return cnt >= 5;
+}
+
+__global__ void __launch_bounds__(256)
+k_merge_structures(const double* __restrict__ S0, const double* __restrict__ S1, const uint8_t* __restrict__ occ0,
+                   const uint8_t* __restrict__ occ1, int h, int w, double mu0, double mu1, int reasoning,
+                   double* __restrict__ out) {
+  const int x = blockIdx.x * 32 + (threadIdx.x & 31);
+  const int y = blockIdx.y * 8 + (threadIdx.x >> 5);
+  if (x >= w || y >= h) return;
+  const long long i = (long long)y * w + x;
+  const bool ob = median3_bit(occ0, h, w, x, y), of = median3_bit(occ1, h, w, x, y);   // :23-24
+  bool fwd_only = !ob && of, bwd_only = !of && ob;                                     // :28-29
+  bool none = !fwd_only && !bwd_only;                                                  // :30
+  if (reasoning == 0) { bwd_only = true; none = false; }                              // :32-37
+  const double s0 = S0[i] * mu1 / mu0, s1 = S1[i];                                     // :40-41
+  const double a = (fwd_only ? 1.0 : 0.0) * s0, b = (bwd_only ? 1.0 : 0.0) * s1;
+  const double c = ((none ? 1.0 : 0.0) * (s0 + s1)) / 2.0;
+  out[i] = (a + b) + c;                                                                // :42
+}
+
 }  // namespace mrf
 
 using namespace mrf;
@@ -114,6 +147,14 @@ int mrf_peer_free(void* ptr) {
   cudaError_t e = cudaFree(ptr);
   if (e != cudaSuccess) return fail((int)e, "mrf_peer_free: %s", cudaGetErrorString(e));
   return 0;
+}
+
+int mrf_merge_structures(const double* S0, const double* S1, const uint8_t* occ_bwd, const uint8_t* occ_fwd, int h,
+                         int w, double mu0, double mu1, int occlusion_reasoning, double* out, mrf_stream_t stream) {
+  MRF_CHECK_ARG(S0 && S1 && occ_bwd && occ_fwd && out && h > 0 && w > 0);
+  dim3 grid(cdiv(w, 32), cdiv(h, 8));
+  k_merge_structures<<<grid, 256, 0, S(stream)>>>(S0, S1, occ_bwd, occ_fwd, h, w, mu0, mu1, occlusion_reasoning, out);
+  return check_launch("mrf_merge_structures");
 }
 
 int mrf_erode3x3_u8(const uint8_t* src, int h, int w, uint8_t* dst, mrf_stream_t stream) {

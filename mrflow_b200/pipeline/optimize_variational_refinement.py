@@ -1,0 +1,34 @@
+"""``pipeline/optimize_variational_refinement.py`` of the reference on the B200: the stage between
+``compute_structure`` and ``combine_flow``.  With ``params.override_optimization`` (the reference's
+fast mode, README.md:68 and BASELINE.json configs[0]) the stage is the occlusion-aware merge of the two
+structures (:20-73) and runs as one kernel.  Without it the reference continues into the variational
+solver (sparse smoothness operators + MINRES, structure_refinement/optimize_structure_multi_scale.py),
+which is the unchanged consumer: it is called if the reference is importable."""
+import numpy as np
+
+from .. import device
+from .._host import down, flag, require_cuda, up
+
+
+def optimize(images, structures, rigidity, epipoles, homographies, B, mu, occlusions, params):
+    """pipeline/optimize_variational_refinement.py:20-101.  Returns ``[structure]`` like the reference."""
+    require_cuda()
+    reasoning = int(getattr(params, "occlusion_reasoning", 1))
+    merged = device.merge_structures(up(structures[0], np.float64), up(structures[1], np.float64),
+                                     flag(np.asarray(occlusions[0]) != 0), flag(np.asarray(occlusions[1]) != 0),
+                                     mu[0], mu[1], reasoning)
+    structure_optimized = down(merged)
+    if getattr(params, "override_optimization", 0):
+        return [structure_optimized, ]                                   # :72-73
+    try:
+        from structure_refinement import optimize_structure_multi_scale   # the reference's solver
+    except Exception as e:                                                # noqa: BLE001
+        raise NotImplementedError("the variational solver (optimize_structure_multi_scale) is the reference's; put the "
+                                  "reference on sys.path or run with override_optimization=1") from e
+    import cv2
+    occ_b = cv2.medianBlur(np.asarray(occlusions[0]).astype("uint8"), ksize=3) > 0
+    occ_f = cv2.medianBlur(np.asarray(occlusions[1]).astype("uint8"), ksize=3) > 0
+    S0 = np.asarray(structures[0]) * mu[1] / mu[0]
+    A_optimized, _ = optimize_structure_multi_scale.optimizeStructureMultiScale(
+        structure_optimized, S0, structures[1], occ_b, occ_f, rigidity, images, homographies, B, epipoles, mu, params)
+    return [A_optimized, ]

@@ -364,13 +364,23 @@ def compute_structure(images, flow, rigidity, occlusions_precomputed, homographi
     return (out, inter) if return_intermediates else out
 
 
-def merge_structure(S, mu_ar, occ):
-    """pipeline/optimize_variational_refinement.py:40-42 -- what reaches combine_flow when
-    override_optimization=1: bwd structure rescaled where the fwd one is occluded."""
-    A = S[1].copy()
-    sel = occ[1] == 1
-    A[sel] = (S[0] * mu_ar[1] / mu_ar[0])[sel]
-    return A
+def optimize_override(structures, mu, occlusions, occlusion_reasoning=1):
+    """pipeline/optimize_variational_refinement.py:20-42,72-73 -- what reaches combine_flow when
+    ``override_optimization=1`` (BASELINE.json configs[0]): 3x3 median of the two occlusion maps, then
+    bwd structure (rescaled) where only the fwd frame is occluded, fwd structure where only the bwd frame
+    is occluded, their mean elsewhere."""
+    occ_b = cv2.medianBlur(occlusions[0].astype("uint8"), ksize=3) > 0
+    occ_f = cv2.medianBlur(occlusions[1].astype("uint8"), ksize=3) > 0
+    fwd_only = (occ_b == 0) * (occ_f > 0)
+    bwd_only = (occ_f == 0) * (occ_b > 0)
+    none = (fwd_only == 0) * (bwd_only == 0)
+    if occlusion_reasoning == 0:
+        bwd_only[:] = True
+        none[:] = False
+    with np.errstate(invalid="ignore"):
+        S0 = structures[0] * mu[1] / mu[0]
+        S1 = structures[1]
+        return fwd_only * S0 + bwd_only * S1 + none * (S0 + S1) / 2.0
 
 
 # --------------------------------------------------------------------------- a12

@@ -206,6 +206,18 @@ def main():
                 out["full_occ"] = np.array(occ2)
                 out["full_S"] = np.array(full[0]); out["full_mu"] = np.array(full[2]); out["full_B"] = np.array(full[3])
                 out["full_q"] = np.array(full[4]); out["full_rigidity"] = np.asarray(full[5])
+                # stage 5 with --override_optimization 1 (pipeline/optimize_variational_refinement.py:20-73)
+                # and stage 6 (pipeline/structure2flow.py:41-82): the rest of the reference chain of configs[0]
+                from pipeline import optimize_variational_refinement as ovr
+                p.override_optimization = 1
+                for reasoning in (1, 0):
+                    p.occlusion_reasoning = reasoning
+                    merged = ovr.optimize(t["images"], full[0], full[5], full[4], full[1], full[3], full[2], occ2, p)[0]
+                    out["full_merged%d" % reasoning] = merged
+                p.occlusion_reasoning = 1
+                _, fu, fv = s2f.combine_flow(out["full_merged1"], t["flow"][1], full[5], full[4], full[2], full[1], full[3],
+                                             t["images"], p)
+                out["full_u"], out["full_v"] = fu, fv
         if example_images is not None:
             out["images"] = np.stack(example_images)
         np.savez_compressed(os.path.join(HERE, "ref_%s.npz" % tag), **out)

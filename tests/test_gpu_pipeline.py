@@ -371,3 +371,42 @@ def test_flow2parallax_and_structure_helpers(golden):
         assert np.array_equal(p, g["parallax%d" % f]) and np.array_equal(d, g["dists%d" % f]) and vec.shape == p.shape + (2,)
         S = cs.parallax2normedstructure(p, t["epipoles"][f], B, g["mu"][f])
         assert np.array_equal(S, g["structure%d" % f], equal_nan=True)
+
+
+def test_reference_chain_stages_4_to_6(golden):
+    """BASELINE.json configs[0] chain -- compute_structure -> optimize(override_optimization=1) -> combine_flow
+    (mrflow.py:98-140) -- through the drop-in modules, against the REFERENCE's own outputs of the same chain
+    (tests/golden; the reference's C++ MRF solver on both sides)."""
+    from mrflow_b200.pipeline import compute_structure as cs, optimize_variational_refinement as ovr, structure2flow as s2f
+    from oracle import trws
+    tag, g = golden
+    if "full_S" not in g:
+        pytest.skip("no end-to-end fixture for this case")
+    if not trws.available():
+        pytest.skip("oracle/_ref not built")
+    t = golden_triplet(tag)
+    occ = [g["full_occ"][0], g["full_occ"][1]]
+    params = _params(override_optimization=1)
+    S, Hs, mu, B, q, rig, oc = cs.compute_structure(t["images"], t["flow"], t["rigidity"], occ,
+                                                    [H.copy() for H in t["homographies"]], t["epipoles"], params,
+                                                    infer_mrf=trws.infer_mrf)
+    for reasoning in (1, 0):
+        params.occlusion_reasoning = reasoning
+        merged = ovr.optimize(t["images"], S, rig, q, Hs, B, mu, oc, params)[0]
+        want = g["full_merged%d" % reasoning]
+        fin = np.isfinite(want)
+        assert np.array_equal(np.isfinite(merged), fin)
+        np.testing.assert_allclose(merged[fin], want[fin], rtol=1e-10)
+    params.occlusion_reasoning = 1
+    merged = ovr.optimize(t["images"], S, rig, q, Hs, B, mu, oc, params)[0]
+    _, u, v = s2f.combine_flow(merged, t["flow"][1], rig, q, mu, Hs, B, t["images"], params)
+    fin = np.isfinite(g["full_u"])
+    assert np.abs(u - g["full_u"])[fin].max() <= 1e-4 and np.abs(v - g["full_v"])[fin].max() <= 1e-4    # north_star: 1e-4 px
+    # with the reference's own stage-4 outputs as input, stages 5 and 6 are bit-exact
+    params.occlusion_reasoning = 1
+    m2 = ovr.optimize(t["images"], [g["full_S"][0], g["full_S"][1]], g["full_rigidity"], g["full_q"], Hs, g["full_B"],
+                      g["full_mu"], occ, params)[0]
+    assert np.array_equal(m2, g["full_merged1"], equal_nan=True)
+    _, u2, v2 = s2f.combine_flow(m2, t["flow"][1], g["full_rigidity"], g["full_q"], g["full_mu"], Hs, g["full_B"],
+                                 t["images"], params)
+    assert np.array_equal(u2, g["full_u"], equal_nan=True) and np.array_equal(v2, g["full_v"], equal_nan=True)

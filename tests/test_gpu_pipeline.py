@@ -410,3 +410,37 @@ def test_reference_chain_stages_4_to_6(golden):
     _, u2, v2 = s2f.combine_flow(m2, t["flow"][1], g["full_rigidity"], g["full_q"], g["full_mu"], Hs, g["full_B"],
                                  t["images"], params)
     assert np.array_equal(u2, g["full_u"], equal_nan=True) and np.array_equal(v2, g["full_v"], equal_nan=True)
+
+
+def test_full_chain_sintel_size():
+    """The chain of mrflow.py:98-140 at BASELINE.json's Sintel shape: drop-in modules on the GPU against the
+    oracle on the CPU, the reference's C++ MRF solver as the consumer on both sides."""
+    from mrflow_b200 import synth
+    from mrflow_b200.pipeline import compute_structure as cs, optimize_variational_refinement as ovr, structure2flow as s2f
+    from oracle import hotpath as hp, trws
+    if not trws.available():
+        pytest.skip("oracle/_ref not built")
+    t = synth.make_triplet("sintel", seed=1003, flow_noise=0.03)
+    h, w = t["shape"]
+    rs = np.random.RandomState(9)
+    occ = [rs.rand(h, w) < 0.03, rs.rand(h, w) < 0.03]
+    want = hp.compute_structure(t["images"], t["flow"], t["rigidity"], occ, [H.copy() for H in t["homographies"]],
+                                t["epipoles"], hp.Params(), infer_mrf=trws.infer_mrf)
+    wm = hp.optimize_override(want[0], want[2], occ)
+    _, wu, wv = hp.combine_flow(wm, t["flow"][1], want[5], want[4], want[2], want[1], want[3])
+    params = _params(override_optimization=1)
+    S, Hs, mu, B, q, rig, oc = cs.compute_structure(t["images"], t["flow"], t["rigidity"], occ,
+                                                    [H.copy() for H in t["homographies"]], t["epipoles"], params,
+                                                    infer_mrf=trws.infer_mrf)
+    np.testing.assert_allclose(mu, want[2], rtol=1e-13)
+    np.testing.assert_allclose(B, want[3], rtol=1e-10)
+    assert (rig == want[5]).mean() > 0.9999                     # int32 unaries can flip at an integer boundary
+    merged = ovr.optimize(t["images"], S, rig, q, Hs, B, mu, oc, params)[0]
+    _, u, v = s2f.combine_flow(merged, t["flow"][1], rig, q, mu, Hs, B, t["images"], params)
+    same = rig == want[5]
+    fin = np.isfinite(wu) & np.isfinite(u) & same
+    assert fin.mean() > 0.99
+    assert np.abs(u - wu)[fin].max() <= 1e-4 and np.abs(v - wv)[fin].max() <= 1e-4          # north_star: 1e-4 px
+    # and the chain reproduces the input flow on rigid pixels (SURVEY.md section 4 identity)
+    rigid = rig & (~occ[0]) & (~occ[1])
+    assert np.median(np.abs(u - t["flow"][1][0])[rigid]) < 0.05

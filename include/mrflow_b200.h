@@ -320,10 +320,11 @@ int mrf_robust_apply_f64(const double* x, size_t n, int kind, int deriv, double 
 
 /* ---- pipeline/optimize_variational_refinement.py:20-42 (the stage between compute_structure and
  * combine_flow when override_optimization=1): 3x3 median of both occlusion maps (uint8 0/1), then
- * structure = fwd_only*S0' + bwd_only*S1 + none*(S0'+S1)/2 with S0' = S0*mu1/mu0.  Whole frame. */
+ * structure = fwd_only*S0' + bwd_only*S1 + none*(S0'+S1)/2 with S0' = S0*mu1/mu0.  Whole frame.
+ * occ_*_blur (optional, uint8) receive the median-filtered maps the variational solver is given (:83-84). */
 int mrf_merge_structures(const double* S0, const double* S1, const uint8_t* occ_bwd, const uint8_t* occ_fwd,
                          int h, int w, double mu0, double mu1, int occlusion_reasoning, double* out,
-                         mrf_stream_t stream);
+                         uint8_t* occ_bwd_blur, uint8_t* occ_fwd_blur, mrf_stream_t stream);
 
 /* ---- pipeline/compute_structure.py:44: cv2.erode(uint8, ones((3,3))) (default border). */
 int mrf_erode3x3_u8(const uint8_t* src, int h, int w, uint8_t* dst, mrf_stream_t stream);

@@ -98,7 +98,7 @@ SIGNATURES = {
     "mrf_data_term_scratch_bytes": (_Z, []),
     "mrf_data_term_system": (_I, [_P, _P, _P, _Z, _I, _D, _P, _P, _P, _P, _P]),
     "mrf_median5x5_f64": (_I, [_P, _I, _I, _P, _P]),
-    "mrf_merge_structures": (_I, [_P, _P, _P, _P, _I, _I, _D, _D, _I, _P, _P]),
+    "mrf_merge_structures": (_I, [_P, _P, _P, _P, _I, _I, _D, _D, _I, _P, _P, _P, _P]),
     "mrf_erode3x3_u8": (_I, [_P, _I, _I, _P, _P]),
     "mrf_robust_apply_f64": (_I, [_P, _Z, _I, _I, _D, _D, _P, _P]),
 }

@@ -79,12 +79,14 @@ __device__ __forceinline__ bool median3_bit(const uint8_t* __restrict__ m, int h
 __global__ void __launch_bounds__(256)
 k_merge_structures(const double* __restrict__ S0, const double* __restrict__ S1, const uint8_t* __restrict__ occ0,
                    const uint8_t* __restrict__ occ1, int h, int w, double mu0, double mu1, int reasoning,
-                   double* __restrict__ out) {
+                   double* __restrict__ out, uint8_t* __restrict__ occ0_blur, uint8_t* __restrict__ occ1_blur) {
   const int x = blockIdx.x * 32 + (threadIdx.x & 31);
   const int y = blockIdx.y * 8 + (threadIdx.x >> 5);
   if (x >= w || y >= h) return;
   const long long i = (long long)y * w + x;
   const bool ob = median3_bit(occ0, h, w, x, y), of = median3_bit(occ1, h, w, x, y);   // :23-24
+  if (occ0_blur) occ0_blur[i] = ob;
+  if (occ1_blur) occ1_blur[i] = of;
   bool fwd_only = !ob && of, bwd_only = !of && ob;                                     // :28-29
   bool none = !fwd_only && !bwd_only;                                                  // :30
   if (reasoning == 0) { bwd_only = true; none = false; }                              // :32-37
@@ -150,10 +152,13 @@ int mrf_peer_free(void* ptr) {
 }
 
 int mrf_merge_structures(const double* S0, const double* S1, const uint8_t* occ_bwd, const uint8_t* occ_fwd, int h,
-                         int w, double mu0, double mu1, int occlusion_reasoning, double* out, mrf_stream_t stream) {
+                         int w, double mu0, double mu1, int occlusion_reasoning, double* out, uint8_t* occ_bwd_blur,
+                         uint8_t* occ_fwd_blur, mrf_stream_t stream) {
   MRF_CHECK_ARG(S0 && S1 && occ_bwd && occ_fwd && out && h > 0 && w > 0);
+  MRF_CHECK_ARG(occ_bwd_blur != occ_bwd && occ_fwd_blur != occ_fwd);
   dim3 grid(cdiv(w, 32), cdiv(h, 8));
-  k_merge_structures<<<grid, 256, 0, S(stream)>>>(S0, S1, occ_bwd, occ_fwd, h, w, mu0, mu1, occlusion_reasoning, out);
+  k_merge_structures<<<grid, 256, 0, S(stream)>>>(S0, S1, occ_bwd, occ_fwd, h, w, mu0, mu1, occlusion_reasoning, out,
+                                                  occ_bwd_blur, occ_fwd_blur);
   return check_launch("mrf_merge_structures");
 }
 

@@ -178,14 +178,18 @@ def rigidity_structure(S0, S1, p_dir, p_cnn, occ0, occ1, mu0, mu1, sigma_structu
     return un, ui
 
 
-def merge_structures(S0, S1, occ_bwd, occ_fwd, mu0, mu1, occlusion_reasoning=1):
-    """pipeline/optimize_variational_refinement.py:20-42 -- occlusion-aware merge of the two structures."""
+def merge_structures(S0, S1, occ_bwd, occ_fwd, mu0, mu1, occlusion_reasoning=1, want_blurred=False):
+    """pipeline/optimize_variational_refinement.py:20-42 -- occlusion-aware merge of the two structures
+    (and, optionally, the 3x3-median-filtered occlusion maps of :23-24)."""
     _chk(S0, F64, "S0"); _chk(S1, F64, "S1"); _chk(occ_bwd, U8, "occ_bwd"); _chk(occ_fwd, U8, "occ_fwd")
     h, w = S0.shape
     out = torch.empty_like(S0)
+    ob = torch.empty_like(occ_bwd) if want_blurred else None
+    of = torch.empty_like(occ_fwd) if want_blurred else None
     check(_lib.lib().mrf_merge_structures(_p(S0), _p(S1), _p(occ_bwd), _p(occ_fwd), h, w, float(mu0), float(mu1),
-                                          int(occlusion_reasoning), _p(out), _stream()), "mrf_merge_structures")
-    return out
+                                          int(occlusion_reasoning), _p(out), _p(ob), _p(of), _stream()),
+          "mrf_merge_structures")
+    return (out, ob, of) if want_blurred else out
 
 
 def erode3x3(mask_u8):

@@ -14,9 +14,10 @@ def optimize(images, structures, rigidity, epipoles, homographies, B, mu, occlus
     """pipeline/optimize_variational_refinement.py:20-101.  Returns ``[structure]`` like the reference."""
     require_cuda()
     reasoning = int(getattr(params, "occlusion_reasoning", 1))
-    merged = device.merge_structures(up(structures[0], np.float64), up(structures[1], np.float64),
-                                     flag(np.asarray(occlusions[0]) != 0), flag(np.asarray(occlusions[1]) != 0),
-                                     mu[0], mu[1], reasoning)
+    merged, occ_b, occ_f = device.merge_structures(up(structures[0], np.float64), up(structures[1], np.float64),
+                                                   flag(np.asarray(occlusions[0]) != 0),
+                                                   flag(np.asarray(occlusions[1]) != 0), mu[0], mu[1], reasoning,
+                                                   want_blurred=True)
     structure_optimized = down(merged)
     if getattr(params, "override_optimization", 0):
         return [structure_optimized, ]                                   # :72-73
@@ -25,9 +26,7 @@ def optimize(images, structures, rigidity, epipoles, homographies, B, mu, occlus
     except Exception as e:                                                # noqa: BLE001
         raise NotImplementedError("the variational solver (optimize_structure_multi_scale) is the reference's; put the "
                                   "reference on sys.path or run with override_optimization=1") from e
-    import cv2
-    occ_b = cv2.medianBlur(np.asarray(occlusions[0]).astype("uint8"), ksize=3) > 0
-    occ_f = cv2.medianBlur(np.asarray(occlusions[1]).astype("uint8"), ksize=3) > 0
+    occ_b, occ_f = occ_b.cpu().numpy() > 0, occ_f.cpu().numpy() > 0        # :23-24, from the kernel
     S0 = np.asarray(structures[0]) * mu[1] / mu[0]
     A_optimized, _ = optimize_structure_multi_scale.optimizeStructureMultiScale(
         structure_optimized, S0, structures[1], occ_b, occ_f, rigidity, images, homographies, B, epipoles, mu, params)

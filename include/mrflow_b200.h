@@ -371,6 +371,58 @@ int mrf_data_term_system(const double* Iz, const double* dphi, const double* dr_
 /* scipy.ndimage.median_filter(size=5) with its default 'reflect' boundary (:299-300) */
 int mrf_median5x5_f64(const double* src, int h, int w, double* dst, mrf_stream_t stream);
 
+/* ---- the variational structure refinement around the data term:
+ * structure_refinement/optimize_structure_single_scale.py:310-652 without its scipy.sparse matrices.
+ * utils/edge_weights.py:38-55 (computeWeightsLocallyNormalized) on the fp32 gray image + the masking of
+ * :388-392 (rigidity_eroded may be NULL: no masking); wx, wy fp32 [h,w]; tmp_a/tmp_b fp32 [h,w] and
+ * tmp_ra/tmp_rb fp64 [h,w] are caller-provided work planes. */
+int mrf_gray32(const void* rgb, int rgb_is_f64, size_t n, float* gray32, mrf_stream_t stream);
+int mrf_edge_weights_local(const float* gray32, const uint8_t* rigidity_eroded, int h, int w, int norm_radius,
+                           double min_weight, float* wx, float* wy, float* tmp_a, float* tmp_b,
+                           double* tmp_ra, double* tmp_rb, mrf_stream_t stream);
+size_t mrf_var_scratch_bytes(void);
+/* :505-511, :541-547: the robust arguments of the first / second order smoothness terms (differences
+ * with replicated borders, structure_refinement/construct_matrices.py:14-38) */
+int mrf_var_smooth_args(const double* A, const float* wx, const float* wy, int h, int w, double afac_sq,
+                        double* arg1, double* arg2, double* root1, double* root2, mrf_stream_t stream);
+/* Lorentzian weights for given sigmas (:511-512, :547-548) and the two energies (:560-561, two doubles
+ * on the device) */
+int mrf_var_smooth_weights(const double* arg1, const double* arg2, const float* wx, const float* wy, size_t n,
+                           double afac_sq, double sigma1, double sigma2, double* p1x, double* p1y,
+                           double* p2x, double* p2y, double* energies2, void* scratch, mrf_stream_t stream);
+/* :448-461 forward data term with the backward one where the forward frame is occluded, and the
+ * consistency residual / argument of :476-490 */
+int mrf_var_data_merge(const double* diag_f, const double* b_f, const double* diag_b, const double* b_b,
+                       const uint8_t* occ_f, const uint8_t* occ_b, const double* A, const double* A_bwd_ref,
+                       const double* A_fwd_ref, size_t n, double scale_bwd, double scale_ref, double afac_sq,
+                       double* D, double* bd, double* Iz_c, double* arg_c, double* root_c, mrf_stream_t stream);
+/* Charbonnier weight (auto eps from the caller's median) and energy of the consistency term (:491-497) */
+int mrf_var_consistency_weights(const double* arg_c, size_t n, double afac_sq, double eps, double* pc,
+                                double* energy, void* scratch, mrf_stream_t stream);
+/* y = Z (D + l1 G'P1G + l2 G2'P2G2 + lc Pc) Z x + eps x  (:580-595), matrix-free; rigid / D / pc may be
+ * NULL (identity / absent) */
+int mrf_var_apply(const double* x, const uint8_t* rigid, const double* D, const double* p1x, const double* p1y,
+                  const double* p2x, const double* p2y, const double* pc, double l1, double l2, double lc,
+                  double eps, int h, int w, double* y, mrf_stream_t stream);
+/* b = Z (-bd - smooth_A - lc * pc * Iz_c)  (:581, :588) */
+int mrf_var_rhs(const double* bd, const double* smooth_A, const double* pc, const double* Iz_c,
+                const uint8_t* rigid, size_t n, double lc, double* b, mrf_stream_t stream);
+/* the vector steps of scipy.sparse.linalg.minres (the solver behind :86/:593); dot products land in
+ * one device double each, the scalar recurrences stay with the caller */
+int mrf_vec_scale(const double* y, size_t n, double s, double* out, mrf_stream_t stream);
+int mrf_minres_alfa(double* y, const double* r1, double c, int use_r1, const double* v, size_t n,
+                    double* out_dot, void* scratch, mrf_stream_t stream);
+int mrf_minres_beta(double* y, double* r1, double* r2, double c, size_t n, double* out_dot, void* scratch,
+                    mrf_stream_t stream);
+int mrf_minres_update(const double* v, double* w, double* w2, double oldeps, double delta, double denom,
+                      double phi, double* x, size_t n, double* out_dot, void* scratch, mrf_stream_t stream);
+/* :600-612 NaN/inf scrub, clip_dA (:157-183), clip to +-1; writes A + dA */
+int mrf_var_clip_update(const double* da, const double* A, int h, int w, const double* q_host, double mu,
+                        double B, double threshold, double* A_plus_da, mrf_stream_t stream);
+/* scipy.ndimage.median_filter(size=7), 'reflect' (:636) and A <- A + (median - A) (:650) */
+int mrf_median7x7_f64(const double* src, int h, int w, double* dst, mrf_stream_t stream);
+int mrf_var_advance(double* A, const double* median_of_A_plus_da, size_t n, mrf_stream_t stream);
+
 /* ---- peer memory for the row-band gather: a buffer allocated on the
  * TRW-S rank's GPU is exported as a 64-byte CUDA IPC handle, opened by the other ranks (one process
  * per GPU), and written by their cost-volume kernels directly over NVLink.  These are the only

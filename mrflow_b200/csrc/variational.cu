@@ -1,0 +1,550 @@
+// The variational structure refinement around the data term:
+// structure_refinement/optimize_structure_single_scale.py:310-652 without its scipy.sparse matrices.
+//   * edge weights        utils/edge_weights.py:38-55 (computeWeightsLocallyNormalized)
+//   * smoothness terms    :505-550 -- first / second differences with replicated borders
+//                         (structure_refinement/construct_matrices.py:14-38), robust arguments
+//   * the linear operator :580-595 -- A = Z (D + l1 G'P1G + l2 G2'P2G2 + lc Pc) Z + 0.01 I applied
+//                         matrix-free as a 5x5-footprint stencil (one thread per pixel, fp64)
+//   * MINRES vector steps scipy.sparse.linalg.minres (the solver the reference calls, :86,:593): fused
+//                         axpy + deterministic dot-product kernels; the scalar recurrences stay on the host
+//   * update              clip_dA :157-183, clip to +-1 :612, 7x7 median of A + dA :636
+// Unlike the cost volume this stage is iterative and latency-bound (hundreds of dependent stencil + dot
+// launches per solve); it is built for parity and residency, not yet tuned.
+#include "common.cuh"
+#include <math.h>
+
+namespace mrf {
+
+constexpr int kVarBlocks = 1024;
+
+__device__ __forceinline__ double block_sum256(double v, double* sh) {
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = v;
+  __syncthreads();
+  double r = 0.0;
+  if (threadIdx.x == 0) for (int k = 0; k < (int)(blockDim.x >> 5); ++k) r += sh[k];
+  __syncthreads();
+  return r;      // valid in thread 0
+}
+
+__global__ void __launch_bounds__(kVarBlocks)
+k_var_sum_final(const double* __restrict__ partial, int n, int nvals, double* __restrict__ out) {
+  __shared__ double sh[32];
+  for (int k = 0; k < nvals; ++k) {
+    double v = (threadIdx.x < n) ? partial[k * n + threadIdx.x] : 0.0;
+    v = block_sum256(v, sh);
+    if (threadIdx.x == 0) out[k] = v;
+  }
+}
+
+// ------------------------------------------------------------------------------- edge weights
+__device__ __forceinline__ int refl101(int i, int n) {
+  if (n == 1) return 0;
+  while (i < 0 || i >= n) { if (i < 0) i = -i; if (i >= n) i = 2 * n - 2 - i; }
+  return i;
+}
+// cv2.cvtColor(I.astype('float32'), COLOR_RGB2GRAY) (:381-383), kept in fp32
+template <typename T>
+__global__ void __launch_bounds__(256)
+k_gray32(const T* __restrict__ rgb, long long n, float* __restrict__ gray) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const float r = (float)rgb[3 * i], g = (float)rgb[3 * i + 1], b = (float)rgb[3 * i + 2];
+    gray[i] = fmaf(b, 0.114f, fmaf(r, 0.299f, g * 0.587f));
+  }
+}
+// np.gradient of an fp32 image, squared (fp32): gxsq, gysq
+__global__ void __launch_bounds__(256)
+k_grad_sq32(const float* __restrict__ I, int h, int w, float* __restrict__ gxsq, float* __restrict__ gysq) {
+  const int x = blockIdx.x * 32 + (threadIdx.x & 31), y = blockIdx.y * 8 + (threadIdx.x >> 5);
+  if (x >= w || y >= h) return;
+  const long long i = (long long)y * w + x;
+  float gx, gy;
+  if (w == 1) gx = 0.f; else if (x == 0) gx = I[i + 1] - I[i]; else if (x == w - 1) gx = I[i] - I[i - 1]; else gx = (I[i + 1] - I[i - 1]) / 2.0f;
+  if (h == 1) gy = 0.f; else if (y == 0) gy = I[i + w] - I[i]; else if (y == h - 1) gy = I[i] - I[i - w]; else gy = (I[i + w] - I[i - w]) / 2.0f;
+  gxsq[i] = gx * gx; gysq[i] = gy * gy;
+}
+// cv2.blur(fp32, (r, r)) = normalised box filter, BORDER_REFLECT_101, sums in fp64, one rounding to fp32;
+// horizontal pass to fp64, vertical pass + weight exp(-g * 1.0 / (2 * max(1e-6, mean)))  (fp32, :49-50)
+__global__ void __launch_bounds__(256)
+k_box_rows(const float* __restrict__ a, const float* __restrict__ b, int h, int w, int radius, double* __restrict__ ra,
+           double* __restrict__ rb) {
+  const int x = blockIdx.x * 32 + (threadIdx.x & 31), y = blockIdx.y * 8 + (threadIdx.x >> 5);
+  if (x >= w || y >= h) return;
+  const int half = radius / 2;
+  double sa = 0.0, sb = 0.0;
+  for (int k = -half; k <= half; ++k) {
+    const long long j = (long long)y * w + refl101(x + k, w);
+    sa += (double)a[j]; sb += (double)b[j];
+  }
+  ra[(long long)y * w + x] = sa; rb[(long long)y * w + x] = sb;
+}
+__global__ void __launch_bounds__(256)
+k_box_cols_weights(const double* __restrict__ ra, const double* __restrict__ rb, const float* __restrict__ gxsq,
+                   const float* __restrict__ gysq, int h, int w, int radius, float* __restrict__ wx, float* __restrict__ wy) {
+  const int x = blockIdx.x * 32 + (threadIdx.x & 31), y = blockIdx.y * 8 + (threadIdx.x >> 5);
+  if (x >= w || y >= h) return;
+  const int half = radius / 2;
+  double sa = 0.0, sb = 0.0;
+  for (int k = -half; k <= half; ++k) {
+    const long long j = (long long)refl101(y + k, h) * w + x;
+    sa += ra[j]; sb += rb[j];
+  }
+  const double scale = 1.0 / ((double)radius * (double)radius);
+  const float ma = (float)(sa * scale), mb = (float)(sb * scale);
+  const long long i = (long long)y * w + x;
+  wx[i] = expf((-gxsq[i] * 1.0f) / (2.0f * fmaxf(1e-6f, ma)));
+  wy[i] = expf((-gysq[i] * 1.0f) / (2.0f * fmaxf(1e-6f, mb)));
+}
+// weights[eroded == 0] = 0; weights = max(weights, min_weight)  (:388-392)
+__global__ void __launch_bounds__(256)
+k_mask_weights(float* __restrict__ wx, float* __restrict__ wy, const uint8_t* __restrict__ eroded, long long n, float min_w) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    float a = wx[i], b = wy[i];
+    if (!eroded[i]) { a = 0.f; b = 0.f; }
+    wx[i] = fmaxf(a, min_w); wy[i] = fmaxf(b, min_w);
+  }
+}
+
+// ------------------------------------------------------------------------------- differences
+__device__ __forceinline__ double dfx(const double* __restrict__ v, int w, int x, long long i) { return (x + 1 < w) ? v[i + 1] - v[i] : 0.0; }
+__device__ __forceinline__ double dfy(const double* __restrict__ v, int h, int w, int y, long long i) { return (y + 1 < h) ? v[i + w] - v[i] : 0.0; }
+__device__ __forceinline__ double dxx(const double* __restrict__ v, int w, int x, long long i) {
+  return (v[x > 0 ? i - 1 : i] + v[x + 1 < w ? i + 1 : i]) - 2.0 * v[i];
+}
+__device__ __forceinline__ double dyy(const double* __restrict__ v, int h, int w, int y, long long i) {
+  return (v[y > 0 ? i - w : i] + v[y + 1 < h ? i + w : i]) - 2.0 * v[i];
+}
+
+// arg1 = afac_sq * (wx*gx^2 + wy*gy^2), arg2 = afac_sq * (wx*dxx^2 + wy*dyy^2)   (:508-511, :541-547)
+__global__ void __launch_bounds__(256)
+k_smooth_args(const double* __restrict__ A, const float* __restrict__ wx, const float* __restrict__ wy, int h, int w,
+              double afac_sq, double* __restrict__ arg1, double* __restrict__ arg2, double* __restrict__ root1,
+              double* __restrict__ root2) {
+  const int x = blockIdx.x * 32 + (threadIdx.x & 31), y = blockIdx.y * 8 + (threadIdx.x >> 5);
+  if (x >= w || y >= h) return;
+  const long long i = (long long)y * w + x;
+  const double a = (double)wx[i], b = (double)wy[i];
+  const double gx = dfx(A, w, x, i), gy = dfy(A, h, w, y, i);
+  const double sx = dxx(A, w, x, i), sy = dyy(A, h, w, y, i);
+  const double a1 = afac_sq * (a * (gx * gx) + b * (gy * gy));
+  const double a2 = afac_sq * (a * (sx * sx) + b * (sy * sy));
+  arg1[i] = a1; arg2[i] = a2;
+  root1[i] = sqrt(a1); root2[i] = sqrt(a2);      // the samples of the auto-sigma median (robust_functions.py:23-29)
+}
+
+// Lorentzian auto-sigma weights of the two smoothness terms and their energies (:511,:547,:560-561):
+// p1x = wx*psi1, p1y = wy*psi1, p2x = psi2*wx, p2y = psi2*wy ; partial sums of rho(arg1), rho(arg2)
+__global__ void __launch_bounds__(256)
+k_smooth_weights(const double* __restrict__ arg1, const double* __restrict__ arg2, const float* __restrict__ wx,
+                 const float* __restrict__ wy, long long n, double afac_sq, double s1, double s2, double* __restrict__ p1x,
+                 double* __restrict__ p1y, double* __restrict__ p2x, double* __restrict__ p2y, double* __restrict__ partial) {
+  __shared__ double sh[8];
+  double e1 = 0.0, e2 = 0.0;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const double a1 = arg1[i], a2 = arg2[i];
+    const double psi1 = afac_sq * (s1 / (a1 + 2.0 * (s1 * s1)));
+    const double psi2 = afac_sq * (s2 / (a2 + 2.0 * (s2 * s2)));
+    const double a = (double)wx[i], b = (double)wy[i];
+    p1x[i] = a * psi1; p1y[i] = b * psi1; p2x[i] = psi2 * a; p2y[i] = psi2 * b;
+    e1 += s1 * log(1.0 + (0.5 * a1) / (s1 * s1));
+    e2 += s2 * log(1.0 + (0.5 * a2) / (s2 * s2));
+  }
+  e1 = block_sum256(e1, sh);
+  e2 = block_sum256(e2, sh);
+  if (threadIdx.x == 0) { partial[blockIdx.x] = e1; partial[gridDim.x + blockIdx.x] = e2; }
+}
+
+// data-term merge (:448-461) and consistency residual (:476-490)
+__global__ void __launch_bounds__(256)
+k_var_data_merge(const double* __restrict__ diag_f, const double* __restrict__ b_f, const double* __restrict__ diag_b,
+                 const double* __restrict__ b_b, const uint8_t* __restrict__ occ_f, const uint8_t* __restrict__ occ_b,
+                 const double* __restrict__ A, const double* __restrict__ A_bwd_ref, const double* __restrict__ A_fwd_ref,
+                 long long n, double s_bwd, double s_ref, double afac_sq, double* __restrict__ D, double* __restrict__ bd,
+                 double* __restrict__ Izc, double* __restrict__ argc, double* __restrict__ rootc) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const bool of = occ_f[i] != 0, ob = occ_b[i] != 0;
+    D[i] = of ? diag_b[i] * s_bwd : diag_f[i];
+    bd[i] = of ? b_b[i] * s_bwd : b_f[i];
+    const double a = A[i], rb = A_bwd_ref[i] * s_ref, rf = A_fwd_ref[i];
+    const double hi = fmax(rf, rb), lo = fmin(rf, rb);
+    double z = (a - hi) * (a > hi ? 1.0 : 0.0) + (a - lo) * (a < lo ? 1.0 : 0.0);
+    if (ob) z = a - rf;
+    if (of) z = a - rb;
+    Izc[i] = z;
+    const double ac = afac_sq * (z * z);
+    argc[i] = ac;
+    rootc[i] = sqrt(ac);
+  }
+}
+
+// Charbonnier (auto eps) weight and energy of the consistency term (:491-497)
+__global__ void __launch_bounds__(256)
+k_cons_weights(const double* __restrict__ argc, long long n, double afac_sq, double eps, double* __restrict__ pc,
+               double* __restrict__ partial) {
+  __shared__ double sh[8];
+  double e = 0.0;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const double r = sqrt(argc[i] + eps * eps);
+    pc[i] = afac_sq * (1.0 / (2.0 * r));
+    e += r;
+  }
+  e = block_sum256(e, sh);
+  if (threadIdx.x == 0) partial[blockIdx.x] = e;
+}
+
+// ------------------------------------------------------------------------------- the operator
+struct VarOp {
+  const uint8_t* rigid;        // Z = diag(rigidity == 1), may be null (identity)
+  const double* D;             // data diagonal, may be null
+  const double *p1x, *p1y, *p2x, *p2y;
+  const double* pc;            // consistency diagonal, may be null
+  double l1, l2, lc, eps;
+  int h, w;
+};
+
+__device__ __forceinline__ double zval(const VarOp& o, const double* __restrict__ x, long long i) {
+  return (!o.rigid || o.rigid[i]) ? x[i] : 0.0;
+}
+// G'P1G v and G2'P2G2 v at pixel (x, y), v = Z x gathered on the fly
+__device__ __forceinline__ double smooth_apply(const VarOp& o, const double* __restrict__ xv, int x, int y) {
+  const int h = o.h, w = o.w;
+  const long long i = (long long)y * w + x;
+  auto V = [&](int yy, int xx) -> double { return zval(o, xv, (long long)yy * w + xx); };
+  auto DX = [&](int yy, int xx) -> double { return (xx + 1 < w) ? V(yy, xx + 1) - V(yy, xx) : 0.0; };
+  auto DY = [&](int yy, int xx) -> double { return (yy + 1 < h) ? V(yy + 1, xx) - V(yy, xx) : 0.0; };
+  auto DXX = [&](int yy, int xx) -> double { return (V(yy, xx > 0 ? xx - 1 : xx) + V(yy, xx + 1 < w ? xx + 1 : xx)) - 2.0 * V(yy, xx); };
+  auto DYY = [&](int yy, int xx) -> double { return (V(yy > 0 ? yy - 1 : yy, xx) + V(yy + 1 < h ? yy + 1 : yy, xx)) - 2.0 * V(yy, xx); };
+  // first order: (G' u)(p) = -ux(p) + ux(p - ex) - uy(p) + uy(p - ey),  u = P1 G v
+  double s1 = 0.0;
+  s1 -= o.p1x[i] * DX(y, x);
+  if (x > 0) s1 += o.p1x[i - 1] * DX(y, x - 1);
+  s1 -= o.p1y[i] * DY(y, x);
+  if (y > 0) s1 += o.p1y[i - w] * DY(y - 1, x);
+  // second order: (Dxx' u)(p) = u(p-1) + u(p+1) - 2u(p), the replicated ends folding back onto p
+  double s2 = 0.0;
+  {
+    const double uc = o.p2x[i] * DXX(y, x);
+    double t = -2.0 * uc;
+    if (x == 0) t += uc;
+    if (x == w - 1) t += uc;
+    if (x > 0) t += o.p2x[i - 1] * DXX(y, x - 1);
+    if (x + 1 < w) t += o.p2x[i + 1] * DXX(y, x + 1);
+    s2 += t;
+  }
+  {
+    const double uc = o.p2y[i] * DYY(y, x);
+    double t = -2.0 * uc;
+    if (y == 0) t += uc;
+    if (y == h - 1) t += uc;
+    if (y > 0) t += o.p2y[i - w] * DYY(y - 1, x);
+    if (y + 1 < h) t += o.p2y[i + w] * DYY(y + 1, x);
+    s2 += t;
+  }
+  return o.l1 * s1 + o.l2 * s2;
+}
+
+__global__ void __launch_bounds__(256)
+k_var_apply(VarOp o, const double* __restrict__ x, double* __restrict__ y) {
+  const int px = blockIdx.x * 32 + (threadIdx.x & 31), py = blockIdx.y * 8 + (threadIdx.x >> 5);
+  if (px >= o.w || py >= o.h) return;
+  const long long i = (long long)py * o.w + px;
+  double r = 0.0;
+  if (!o.rigid || o.rigid[i]) {
+    const double v = x[i];
+    r = smooth_apply(o, x, px, py);
+    if (o.D) r += o.D[i] * v;
+    if (o.pc) r += o.lc * (o.pc[i] * v);
+  }
+  y[i] = r + o.eps * x[i];
+}
+
+// b = Z (-bd - (l1 A1 + l2 A2) A - lc * pc * Izc)   (:581,:588)
+__global__ void __launch_bounds__(256)
+k_var_rhs(const double* __restrict__ bd, const double* __restrict__ sA, const double* __restrict__ pc,
+          const double* __restrict__ Izc, const uint8_t* __restrict__ rigid, long long n, double lc, double* __restrict__ b) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    double v = -bd[i] - sA[i];
+    if (pc) v -= lc * (pc[i] * Izc[i]);
+    b[i] = rigid[i] ? v : 0.0;
+  }
+}
+
+// ------------------------------------------------------------------------------- MINRES vector steps
+// out = s * y
+__global__ void __launch_bounds__(256)
+k_scale(const double* __restrict__ y, long long n, double s, double* __restrict__ out) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) out[i] = s * y[i];
+}
+// y -= c * r (if use_r);  partial[block] = sum v*y
+__global__ void __launch_bounds__(256)
+k_axpy_dot(double* __restrict__ y, const double* __restrict__ r, double c, int use_r, const double* __restrict__ v, long long n,
+           double* __restrict__ partial) {
+  __shared__ double sh[8];
+  double acc = 0.0;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    double t = y[i];
+    if (use_r) t = t - c * r[i];
+    y[i] = t;
+    acc += v[i] * t;
+  }
+  acc = block_sum256(acc, sh);
+  if (threadIdx.x == 0) partial[blockIdx.x] = acc;
+}
+// y -= c * r2;  r1 = r2;  r2 = y;  partial = sum y*y
+__global__ void __launch_bounds__(256)
+k_lanczos_tail(double* __restrict__ y, double* __restrict__ r1, double* __restrict__ r2, double c, long long n,
+               double* __restrict__ partial) {
+  __shared__ double sh[8];
+  double acc = 0.0;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const double old2 = r2[i];
+    const double t = y[i] - c * old2;
+    y[i] = t; r1[i] = old2; r2[i] = t;
+    acc += t * t;
+  }
+  acc = block_sum256(acc, sh);
+  if (threadIdx.x == 0) partial[blockIdx.x] = acc;
+}
+// w_new = (v - oldeps*w1 - delta*w2) * denom (w1 <- w2, w2 <- w, w <- w_new);  x += phi * w_new;  partial = sum x*x
+__global__ void __launch_bounds__(256)
+k_minres_update(const double* __restrict__ v, double* __restrict__ w, double* __restrict__ w2, double oldeps, double delta,
+                double denom, double phi, double* __restrict__ x, long long n, double* __restrict__ partial) {
+  __shared__ double sh[8];
+  double acc = 0.0;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const double w1_ = w2[i];        // previous w2 becomes w1
+    const double w2_ = w[i];         // previous w becomes w2
+    const double wn = ((v[i] - oldeps * w1_) - delta * w2_) * denom;
+    w2[i] = w2_; w[i] = wn;
+    const double xn = x[i] + phi * wn;
+    x[i] = xn;
+    acc += xn * xn;
+  }
+  acc = block_sum256(acc, sh);
+  if (threadIdx.x == 0) partial[blockIdx.x] = acc;
+}
+
+// ------------------------------------------------------------------------------- update
+// NaN / inf scrub (:600-606), clip_dA (:157-183, threshold 1.0), clip to +-1 (:612); out = A + dA
+__global__ void __launch_bounds__(256)
+k_var_clip(const double* __restrict__ da, const double* __restrict__ A, int h, int w, Pt2 q, double mu, double B, double thr,
+           double* __restrict__ out) {
+  const int x = blockIdx.x * 32 + (threadIdx.x & 31), y = blockIdx.y * 8 + (threadIdx.x >> 5);
+  if (x >= w || y >= h) return;
+  const long long i = (long long)y * w + x;
+  double d = da[i];
+  if (d != d || isinf(d)) d = 0.0;
+  const double vx = q.x - (double)x, vy = q.y - (double)y;
+  const double n = sqrt(vx * vx + vy * vy) / mu;
+  const double a = A[i];
+  const double num = -(((mu * mu) * thr - ((2.0 * mu) * thr) * a * B) + (thr * (a * a)) * (B * B));
+  const double dmax = num / (((thr * a) * (B * B)) + ((-(mu * mu)) * n - mu * thr) * B);
+  const double dmin = num / (((thr * a) * (B * B)) + ((mu * mu) * n - mu * thr) * B);
+  d = fmax(dmin, fmin(d, dmax));         // np.maximum(dA_min, np.minimum(dA, dA_max)); NaN bounds propagate like numpy's
+  if (dmin != dmin || dmax != dmax) d = __longlong_as_double(0x7FF8000000000000ll);
+  d = fmin(fmax(d, -1.0), 1.0);
+  if (d != d) d = __longlong_as_double(0x7FF8000000000000ll);
+  out[i] = a + d;
+}
+
+__device__ __forceinline__ int reflect_sym7(int i, int n) {
+  if (n == 1) return 0;
+  const int p = 2 * n;
+  i %= p; if (i < 0) i += p;
+  return i < n ? i : p - 1 - i;
+}
+// A_new = median_filter(A + dA, size=7)  (scipy 'reflect'); the caller then has dA = A_new - A, A = A + dA (:636,:650)
+__global__ void __launch_bounds__(128)
+k_median7x7(const double* __restrict__ src, int h, int w, double* __restrict__ dst) {
+  const int x = blockIdx.x * 32 + (threadIdx.x & 31), y = blockIdx.y * 4 + (threadIdx.x >> 5);
+  if (x >= w || y >= h) return;
+  double v[49];
+#pragma unroll
+  for (int j = 0; j < 7; ++j) {
+    const int yy = reflect_sym7(y + j - 3, h);
+#pragma unroll
+    for (int i = 0; i < 7; ++i) v[j * 7 + i] = src[(long long)yy * w + reflect_sym7(x + i - 3, w)];
+  }
+#pragma unroll
+  for (int k = 0; k <= 24; ++k) {
+#pragma unroll
+    for (int m = k + 1; m < 49; ++m) {
+      const double lo = fmin(v[k], v[m]), hi = fmax(v[k], v[m]);
+      v[k] = lo; v[m] = hi;
+    }
+  }
+  dst[(long long)y * w + x] = v[24];
+}
+// A <- A + (med - A)   (the reference forms da = median - A and then A + da: two roundings, kept)
+__global__ void __launch_bounds__(256)
+k_var_advance(double* __restrict__ A, const double* __restrict__ med, long long n) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const double a = A[i];
+    const double da = med[i] - a;
+    A[i] = a + da;
+  }
+}
+
+static inline unsigned lin_grid(long long n) {
+  long long b = (n + 255) / 256;
+  if (b > kVarBlocks) b = kVarBlocks;
+  return (unsigned)(b < 1 ? 1 : b);
+}
+
+}  // namespace mrf
+
+using namespace mrf;
+
+extern "C" {
+
+size_t mrf_var_scratch_bytes(void) { return sizeof(double) * (2 * kVarBlocks + 8); }
+
+int mrf_gray32(const void* rgb, int rgb_is_f64, size_t n, float* gray32, mrf_stream_t stream) {
+  MRF_CHECK_ARG(rgb && gray32 && n > 0);
+  const unsigned g = (unsigned)(((long long)n + 255) / 256 > 4096 ? 4096 : ((long long)n + 255) / 256);
+  if (rgb_is_f64) k_gray32<double><<<g, 256, 0, S(stream)>>>((const double*)rgb, (long long)n, gray32);
+  else            k_gray32<float><<<g, 256, 0, S(stream)>>>((const float*)rgb, (long long)n, gray32);
+  return check_launch("mrf_gray32");
+}
+
+int mrf_edge_weights_local(const float* gray32, const uint8_t* rigidity_eroded, int h, int w, int norm_radius, double min_weight,
+                           float* wx, float* wy, float* tmp_a, float* tmp_b, double* tmp_ra, double* tmp_rb,
+                           mrf_stream_t stream) {
+  MRF_CHECK_ARG(gray32 && wx && wy && tmp_a && tmp_b && tmp_ra && tmp_rb && h > 0 && w > 0 && norm_radius > 0 && (norm_radius & 1));
+  dim3 grid(cdiv(w, 32), cdiv(h, 8));
+  k_grad_sq32<<<grid, 256, 0, S(stream)>>>(gray32, h, w, tmp_a, tmp_b);
+  int rc = check_launch("mrf_edge_weights_local/grad");
+  if (rc) return rc;
+  k_box_rows<<<grid, 256, 0, S(stream)>>>(tmp_a, tmp_b, h, w, norm_radius, tmp_ra, tmp_rb);
+  rc = check_launch("mrf_edge_weights_local/rows");
+  if (rc) return rc;
+  k_box_cols_weights<<<grid, 256, 0, S(stream)>>>(tmp_ra, tmp_rb, tmp_a, tmp_b, h, w, norm_radius, wx, wy);
+  rc = check_launch("mrf_edge_weights_local/cols");
+  if (rc || !rigidity_eroded) return rc;
+  const long long n = (long long)h * w;
+  k_mask_weights<<<lin_grid(n), 256, 0, S(stream)>>>(wx, wy, rigidity_eroded, n, (float)min_weight);
+  return check_launch("mrf_edge_weights_local/mask");
+}
+
+int mrf_var_smooth_args(const double* A, const float* wx, const float* wy, int h, int w, double afac_sq, double* arg1,
+                        double* arg2, double* root1, double* root2, mrf_stream_t stream) {
+  MRF_CHECK_ARG(A && wx && wy && arg1 && arg2 && root1 && root2 && h > 0 && w > 0);
+  dim3 grid(cdiv(w, 32), cdiv(h, 8));
+  k_smooth_args<<<grid, 256, 0, S(stream)>>>(A, wx, wy, h, w, afac_sq, arg1, arg2, root1, root2);
+  return check_launch("mrf_var_smooth_args");
+}
+
+int mrf_var_smooth_weights(const double* arg1, const double* arg2, const float* wx, const float* wy, size_t n, double afac_sq,
+                           double sigma1, double sigma2, double* p1x, double* p1y, double* p2x, double* p2y,
+                           double* energies2, void* scratch, mrf_stream_t stream) {
+  MRF_CHECK_ARG(arg1 && arg2 && wx && wy && p1x && p1y && p2x && p2y && energies2 && scratch && n > 0);
+  const unsigned g = lin_grid((long long)n);
+  k_smooth_weights<<<g, 256, 0, S(stream)>>>(arg1, arg2, wx, wy, (long long)n, afac_sq, sigma1, sigma2, p1x, p1y, p2x, p2y,
+                                             (double*)scratch);
+  int rc = check_launch("mrf_var_smooth_weights");
+  if (rc) return rc;
+  k_var_sum_final<<<1, kVarBlocks, 0, S(stream)>>>((const double*)scratch, (int)g, 2, energies2);
+  return check_launch("mrf_var_smooth_weights/energies");
+}
+
+int mrf_var_data_merge(const double* diag_f, const double* b_f, const double* diag_b, const double* b_b, const uint8_t* occ_f,
+                       const uint8_t* occ_b, const double* A, const double* A_bwd_ref, const double* A_fwd_ref, size_t n,
+                       double scale_bwd, double scale_ref, double afac_sq, double* D, double* bd, double* Iz_c, double* arg_c,
+                       double* root_c, mrf_stream_t stream) {
+  MRF_CHECK_ARG(diag_f && b_f && diag_b && b_b && occ_f && occ_b && A && A_bwd_ref && A_fwd_ref && D && bd && Iz_c && arg_c && root_c && n > 0);
+  k_var_data_merge<<<lin_grid((long long)n), 256, 0, S(stream)>>>(diag_f, b_f, diag_b, b_b, occ_f, occ_b, A, A_bwd_ref, A_fwd_ref,
+                                                                  (long long)n, scale_bwd, scale_ref, afac_sq, D, bd, Iz_c, arg_c, root_c);
+  return check_launch("mrf_var_data_merge");
+}
+
+int mrf_var_consistency_weights(const double* arg_c, size_t n, double afac_sq, double eps, double* pc, double* energy,
+                                void* scratch, mrf_stream_t stream) {
+  MRF_CHECK_ARG(arg_c && pc && energy && scratch && n > 0);
+  const unsigned g = lin_grid((long long)n);
+  k_cons_weights<<<g, 256, 0, S(stream)>>>(arg_c, (long long)n, afac_sq, eps, pc, (double*)scratch);
+  int rc = check_launch("mrf_var_consistency_weights");
+  if (rc) return rc;
+  k_var_sum_final<<<1, kVarBlocks, 0, S(stream)>>>((const double*)scratch, (int)g, 1, energy);
+  return check_launch("mrf_var_consistency_weights/energy");
+}
+
+int mrf_var_apply(const double* x, const uint8_t* rigid, const double* D, const double* p1x, const double* p1y, const double* p2x,
+                  const double* p2y, const double* pc, double l1, double l2, double lc, double eps, int h, int w, double* y,
+                  mrf_stream_t stream) {
+  MRF_CHECK_ARG(x && y && x != y && p1x && p1y && p2x && p2y && h > 0 && w > 0);
+  VarOp o;
+  o.rigid = rigid; o.D = D; o.p1x = p1x; o.p1y = p1y; o.p2x = p2x; o.p2y = p2y; o.pc = pc;
+  o.l1 = l1; o.l2 = l2; o.lc = lc; o.eps = eps; o.h = h; o.w = w;
+  dim3 grid(cdiv(w, 32), cdiv(h, 8));
+  k_var_apply<<<grid, 256, 0, S(stream)>>>(o, x, y);
+  return check_launch("mrf_var_apply");
+}
+
+int mrf_var_rhs(const double* bd, const double* smooth_A, const double* pc, const double* Iz_c, const uint8_t* rigid, size_t n,
+                double lc, double* b, mrf_stream_t stream) {
+  MRF_CHECK_ARG(bd && smooth_A && rigid && b && n > 0 && (!pc || Iz_c));
+  k_var_rhs<<<lin_grid((long long)n), 256, 0, S(stream)>>>(bd, smooth_A, pc, Iz_c, rigid, (long long)n, lc, b);
+  return check_launch("mrf_var_rhs");
+}
+
+int mrf_vec_scale(const double* y, size_t n, double s, double* out, mrf_stream_t stream) {
+  MRF_CHECK_ARG(y && out && n > 0);
+  k_scale<<<lin_grid((long long)n), 256, 0, S(stream)>>>(y, (long long)n, s, out);
+  return check_launch("mrf_vec_scale");
+}
+
+int mrf_minres_alfa(double* y, const double* r1, double c, int use_r1, const double* v, size_t n, double* out_dot,
+                    void* scratch, mrf_stream_t stream) {
+  MRF_CHECK_ARG(y && v && out_dot && scratch && n > 0 && (!use_r1 || r1));
+  const unsigned g = lin_grid((long long)n);
+  k_axpy_dot<<<g, 256, 0, S(stream)>>>(y, r1, c, use_r1, v, (long long)n, (double*)scratch);
+  int rc = check_launch("mrf_minres_alfa");
+  if (rc) return rc;
+  k_var_sum_final<<<1, kVarBlocks, 0, S(stream)>>>((const double*)scratch, (int)g, 1, out_dot);
+  return check_launch("mrf_minres_alfa/sum");
+}
+
+int mrf_minres_beta(double* y, double* r1, double* r2, double c, size_t n, double* out_dot, void* scratch,
+                    mrf_stream_t stream) {
+  MRF_CHECK_ARG(y && r1 && r2 && out_dot && scratch && n > 0);
+  const unsigned g = lin_grid((long long)n);
+  k_lanczos_tail<<<g, 256, 0, S(stream)>>>(y, r1, r2, c, (long long)n, (double*)scratch);
+  int rc = check_launch("mrf_minres_beta");
+  if (rc) return rc;
+  k_var_sum_final<<<1, kVarBlocks, 0, S(stream)>>>((const double*)scratch, (int)g, 1, out_dot);
+  return check_launch("mrf_minres_beta/sum");
+}
+
+int mrf_minres_update(const double* v, double* w, double* w2, double oldeps, double delta, double denom, double phi, double* x,
+                      size_t n, double* out_dot, void* scratch, mrf_stream_t stream) {
+  MRF_CHECK_ARG(v && w && w2 && x && out_dot && scratch && n > 0);
+  const unsigned g = lin_grid((long long)n);
+  k_minres_update<<<g, 256, 0, S(stream)>>>(v, w, w2, oldeps, delta, denom, phi, x, (long long)n, (double*)scratch);
+  int rc = check_launch("mrf_minres_update");
+  if (rc) return rc;
+  k_var_sum_final<<<1, kVarBlocks, 0, S(stream)>>>((const double*)scratch, (int)g, 1, out_dot);
+  return check_launch("mrf_minres_update/sum");
+}
+
+int mrf_var_clip_update(const double* da, const double* A, int h, int w, const double* q_host, double mu, double B,
+                        double threshold, double* A_plus_da, mrf_stream_t stream) {
+  MRF_CHECK_ARG(da && A && A_plus_da && q_host && h > 0 && w > 0);
+  dim3 grid(cdiv(w, 32), cdiv(h, 8));
+  k_var_clip<<<grid, 256, 0, S(stream)>>>(da, A, h, w, pt2(q_host), mu, B, threshold, A_plus_da);
+  return check_launch("mrf_var_clip_update");
+}
+
+int mrf_median7x7_f64(const double* src, int h, int w, double* dst, mrf_stream_t stream) {
+  MRF_CHECK_ARG(src && dst && src != dst && h > 0 && w > 0);
+  dim3 grid(cdiv(w, 32), cdiv(h, 4));
+  k_median7x7<<<grid, 128, 0, S(stream)>>>(src, h, w, dst);
+  return check_launch("mrf_median7x7_f64");
+}
+
+int mrf_var_advance(double* A, const double* median_of_A_plus_da, size_t n, mrf_stream_t stream) {
+  MRF_CHECK_ARG(A && median_of_A_plus_da && n > 0);
+  k_var_advance<<<lin_grid((long long)n), 256, 0, S(stream)>>>(A, median_of_A_plus_da, (long long)n);
+  return check_launch("mrf_var_advance");
+}
+
+}  // extern "C"

@@ -410,7 +410,18 @@ def pack_texels(ch64):
     return tex
 
 
-def data_term(A, I1, I2, nonrigid, occluded, H, B, mu, q, rho="lorentzian_auto", sigma=0.0, cw=(0.01, 1.0, 1.0)):
+def data_term_prepare(I1, I2, H):
+    """The parts of computeDataTerm that do not depend on the structure: image derivatives through H
+    (:238-242, :255-256) and the fp32 texel planes the warp samples.  Reusable across the outer iterations
+    of the variational refinement."""
+    _chk(I1, F64, "I1"); _chk(I2, F64, "I2")
+    d2x, d2y = derivs_through_H(I2, H)                              # :238-242 -> interpolate_through_H.py:44-46
+    d1x, d1y = derivs_through_H(I1, np.eye(3))                      # :255-256
+    return dict(d1x=d1x, d1y=d1y, tex=pack_texels(I2), tdx=pack_texels(d2x), tdy=pack_texels(d2y))
+
+
+def data_term(A, I1, I2, nonrigid, occluded, H, B, mu, q, rho="lorentzian_auto", sigma=0.0, cw=(0.01, 1.0, 1.0),
+              prepared=None):
     """optimize_structure_single_scale.py:186-305 (computeDataTerm) on device tensors: A fp64 [h,w], I1 / I2
     fp64 [h,w,3] channel stacks, masks uint8.  Returns (diag, b, E, intermediates): the two images after
     their 5x5 median filters, the energy as a 1-element tensor, and dict(Iz, dphi, dr_da, sigma)."""
@@ -418,9 +429,8 @@ def data_term(A, I1, I2, nonrigid, occluded, H, B, mu, q, rho="lorentzian_auto",
     L = _lib.lib()
     h, w = A.shape
     dev = A.device
-    d2x, d2y = derivs_through_H(I2, H)                              # :238-242 -> interpolate_through_H.py:44-46
-    d1x, d1y = derivs_through_H(I1, np.eye(3))                      # :255-256
-    tex, tdx, tdy = pack_texels(I2), pack_texels(d2x), pack_texels(d2y)
+    pr = prepared if prepared is not None else data_term_prepare(I1, I2, H)
+    d1x, d1y, tex, tdx, tdy = pr["d1x"], pr["d1y"], pr["tex"], pr["tdx"], pr["tdy"]
     Iz = torch.empty((h, w), dtype=F64, device=dev); dphi = torch.empty_like(Iz); drda = torch.empty_like(Iz)
     check(L.mrf_data_term_residual(_p(A), _p(I1), _p(tex), _p(tdx), _p(tdy), _p(d1x), _p(d1y), _p(nonrigid), _p(occluded),
                                    h, w, _mat(H), _pt(q), float(mu), float(B), dvec(cw), _p(Iz), _p(dphi), _p(drda),

@@ -1,0 +1,276 @@
+"""Variational structure refinement, device-resident.
+
+structure_refinement/optimize_structure_single_scale.py:310-652: per outer iteration two linearised data
+terms, image-adaptive robust first / second order smoothness, an optional consistency term, one linear
+solve, clipping and a 7x7 median.  The reference assembles scipy.sparse matrices and calls
+scipy.sparse.linalg.minres (:86, :593); here the operator is applied matrix-free by one stencil kernel
+(``mrf_var_apply``) and MINRES runs as fused vector kernels with its scalar recurrences on the host
+(three dot products per iteration come back through a pinned 8-byte read each).
+
+Everything numeric is fp64 like the reference; the summation order inside the operator and the dot
+products differs from scipy's CSR products, so results agree to solver tolerance (tests state 1e-6 on the
+structure), not bit for bit.
+"""
+import ctypes as C
+import math
+
+import numpy as np
+import torch
+
+from . import _lib, device
+from ._lib import check, dvec
+from .device import F32, F64, U8, _chk, _p, _stream
+
+EPS_DIAG = 0.01          # :591 -- the constant added to the diagonal of the system
+
+
+def gray32(rgb):
+    """cv2.cvtColor(I.astype('float32'), COLOR_RGB2GRAY) (:381-383) as an fp32 [h,w] device tensor."""
+    h, w = rgb.shape[:2]
+    out = torch.empty((h, w), dtype=F32, device=rgb.device)
+    check(_lib.lib().mrf_gray32(_p(rgb), int(rgb.dtype == F64), h * w, _p(out), _stream()), "mrf_gray32")
+    return out
+
+
+def edge_weights_local(gray, rigidity_eroded=None, norm_radius=45, min_weight=0.0):
+    """utils/edge_weights.py:38-55 on the fp32 gray image, then :388-392 (zero outside the eroded rigid
+    region, floor at min_weight).  Returns (weights_x, weights_y) fp32 [h,w]."""
+    _chk(gray, F32, "gray")
+    h, w = gray.shape
+    dev = gray.device
+    wx = torch.empty((h, w), dtype=F32, device=dev); wy = torch.empty_like(wx)
+    ta = torch.empty_like(wx); tb = torch.empty_like(wx)
+    ra = torch.empty((h, w), dtype=F64, device=dev); rb = torch.empty_like(ra)
+    check(_lib.lib().mrf_edge_weights_local(_p(gray), _p(rigidity_eroded), h, w, int(norm_radius), float(min_weight),
+                                            _p(wx), _p(wy), _p(ta), _p(tb), _p(ra), _p(rb), _stream()),
+          "mrf_edge_weights_local")
+    return wx, wy
+
+
+class _Scalar:
+    """One device double + pinned mirror: the dot products MINRES needs on the host."""
+
+    def __init__(self, dev, n=1):
+        self.d = torch.empty(n, dtype=F64, device=dev)
+        self.h = torch.empty(n, dtype=F64, pin_memory=True)
+
+    def get(self):
+        self.h.copy_(self.d, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return self.h.numpy()
+
+
+class Operator:
+    """A = Z (D + l1 G'P1G + l2 G2'P2G2 + lc Pc) Z + eps I  (:580-595) over device planes."""
+
+    def __init__(self, h, w, rigid, D, p1x, p1y, p2x, p2y, pc, l1, l2, lc, eps=EPS_DIAG):
+        self.h, self.w = h, w
+        self.args = (rigid, D, p1x, p1y, p2x, p2y, pc)
+        self.l = (float(l1), float(l2), float(lc), float(eps))
+
+    def apply(self, x, y):
+        rigid, D, p1x, p1y, p2x, p2y, pc = self.args
+        check(_lib.lib().mrf_var_apply(_p(x), _p(rigid), _p(D), _p(p1x), _p(p1y), _p(p2x), _p(p2y), _p(pc), *self.l,
+                                       self.h, self.w, _p(y), _stream()), "mrf_var_apply")
+        return y
+
+
+def minres(op, b, rtol=1e-5, maxiter=None, shift=0.0):
+    """scipy.sparse.linalg.minres(A, b, rtol=...) with x0 = 0 and no preconditioner -- the call behind
+    ``solve(A, b, 'minres', tol)`` (:86).  Same recurrences, same stopping tests, same iteration cap
+    (5 n); vectors stay on the device.  Returns (x, info dict)."""
+    L = _lib.lib()
+    n = b.numel()
+    dev = b.device
+    if maxiter is None:
+        maxiter = 5 * n
+    sc = _Scalar(dev)
+    scratch = torch.empty(L.mrf_var_scratch_bytes(), dtype=U8, device=dev)
+    x = torch.zeros(n, dtype=F64, device=dev)
+    eps = float(np.finfo(np.float64).eps)
+    # r1 = b - A x = b ; y = r1 ; beta1 = <r1, y>
+    r1 = b.reshape(-1).clone()
+    y = r1.clone()
+    v = torch.empty_like(y)
+    check(L.mrf_minres_alfa(_p(y), None, 0.0, 0, _p(r1), n, _p(sc.d), _p(scratch), _stream()), "mrf_minres_alfa")
+    beta1 = float(sc.get()[0])
+    if beta1 < 0:
+        raise ValueError("indefinite preconditioner")
+    if beta1 == 0:
+        return x, dict(istop=0, itn=0)
+    bnorm = math.sqrt(beta1)          # norm(b) (x0 = 0, M = I)
+    beta1 = math.sqrt(beta1)
+    oldb = 0.0; beta = beta1; dbar = 0.0; epsln = 0.0; qrnorm = beta1; phibar = beta1; rhs1 = beta1; rhs2 = 0.0
+    tnorm2 = 0.0; gmax = 0.0; gmin = float(np.finfo(np.float64).max); cs = -1.0; sn = 0.0
+    w = torch.zeros(n, dtype=F64, device=dev)
+    w2 = torch.zeros(n, dtype=F64, device=dev)
+    r2 = r1.clone()
+    istop = 0; itn = 0
+    Anorm = 0.0; Acond = 0.0; rnorm = 0.0; ynorm = 0.0
+    while itn < maxiter:
+        itn += 1
+        s = 1.0 / beta
+        check(L.mrf_vec_scale(_p(y), n, s, _p(v), _stream()), "mrf_vec_scale")                     # v = s*y
+        op.apply(v, y)                                                                              # y = A v - shift v
+        # if itn >= 2: y -= (beta/oldb) r1 ; alfa = <v, y>
+        check(L.mrf_minres_alfa(_p(y), _p(r1), (beta / oldb) if itn >= 2 else 0.0, int(itn >= 2), _p(v), n, _p(sc.d),
+                                _p(scratch), _stream()), "mrf_minres_alfa")
+        alfa = float(sc.get()[0])
+        # y -= (alfa/beta) r2 ; r1 = r2 ; r2 = y ; beta = <r2, y>
+        check(L.mrf_minres_beta(_p(y), _p(r1), _p(r2), alfa / beta, n, _p(sc.d), _p(scratch), _stream()), "mrf_minres_beta")
+        oldb = beta
+        beta = float(sc.get()[0])
+        if beta < 0:
+            raise ValueError("non-symmetric matrix")
+        beta = math.sqrt(beta)
+        tnorm2 += alfa ** 2 + oldb ** 2 + beta ** 2
+        if itn == 1:
+            if beta / beta1 <= 10 * eps:
+                istop = -1
+        oldeps = epsln
+        delta = cs * dbar + sn * alfa
+        gbar = sn * dbar - cs * alfa
+        epsln = sn * beta
+        dbar = -cs * beta
+        root = math.sqrt(gbar * gbar + dbar * dbar)
+        Arnorm = phibar * root
+        gamma = math.sqrt(gbar * gbar + beta * beta)
+        gamma = max(gamma, eps)
+        cs = gbar / gamma
+        sn = beta / gamma
+        phi = cs * phibar
+        phibar = sn * phibar
+        denom = 1.0 / gamma
+        # w1 = w2; w2 = w; w = (v - oldeps*w1 - delta*w2) * denom; x += phi*w ; ynorm = |x|
+        check(L.mrf_minres_update(_p(v), _p(w), _p(w2), oldeps, delta, denom, phi, _p(x), n, _p(sc.d), _p(scratch),
+                                  _stream()), "mrf_minres_update")
+        ynorm = math.sqrt(float(sc.get()[0]))
+        gmax = max(gmax, gamma)
+        gmin = min(gmin, gamma)
+        z = rhs1 / gamma
+        rhs1 = rhs2 - delta * z
+        rhs2 = -epsln * z
+        Anorm = math.sqrt(tnorm2)
+        epsa = Anorm * eps
+        epsx = Anorm * ynorm * eps
+        epsr = Anorm * ynorm * rtol
+        diag = gbar
+        if diag == 0:
+            diag = epsa
+        qrnorm = phibar
+        rnorm = qrnorm
+        if ynorm == 0 or Anorm == 0:
+            test1 = float("inf")
+        else:
+            test1 = rnorm / (Anorm * ynorm)
+        if Anorm == 0:
+            test2 = float("inf")
+        else:
+            test2 = root / Anorm
+        Acond = gmax / gmin
+        if istop == 0:
+            t1 = 1 + test1
+            t2 = 1 + test2
+            if t2 <= 1:
+                istop = 2
+            if t1 <= 1:
+                istop = 1
+            if itn >= maxiter:
+                istop = 6
+            if Acond >= 0.1 / eps:
+                istop = 4
+            if epsx >= beta1:
+                istop = 3
+            if test2 <= rtol:
+                istop = 2
+            if test1 <= rtol:
+                istop = 1
+        if istop != 0:
+            break
+    return x, dict(istop=istop, itn=itn, rnorm=rnorm, Anorm=Anorm, Acond=Acond)
+
+
+class Refiner:
+    """One frame triplet at one scale: the constant device planes (channel stacks, derivative texels,
+    edge weights, masks) and ``step()`` = one outer iteration of :419-650."""
+
+    def __init__(self, images, occlusions_bwd, occlusions_fwd, rigidity, H_ar, B_ar, q_ar, mu_ar, A_bwd_reference,
+                 A_fwd_reference, lambda_1storder, lambda_2ndorder, lambda_consistency, A_scale_factor=1.0,
+                 min_weight=0.0, channel_weights=(0.01, 1.0, 1.0), rtol=1e-5):
+        """``images`` three contiguous CUDA [h,w,3] tensors (fp64 or fp32 RGB in [0,1]); masks uint8 CUDA
+        [h,w] (rigidity = 1 where rigid); structures fp64 CUDA [h,w]; the motion data as host values."""
+        self.h, self.w = images[1].shape[:2]
+        self.n = self.h * self.w
+        self.dev = images[1].device
+        self.ch = [device.prepare_channels(I, want_texels=False)[0] for I in images]      # :350-371
+        self.cw = tuple(float(c) for c in channel_weights)
+        self.rigid = rigidity
+        self.nonrigid = (rigidity == 0).to(U8)
+        self.occ_b, self.occ_f = occlusions_bwd, occlusions_fwd
+        self.H, self.B, self.q, self.mu = H_ar, [float(b) for b in B_ar], q_ar, [float(m) for m in mu_ar]
+        self.prep_f = device.data_term_prepare(self.ch[1], self.ch[2], H_ar[1])
+        self.prep_b = device.data_term_prepare(self.ch[1], self.ch[0], H_ar[0])
+        eroded = device.erode3x3(rigidity)                                               # :387
+        self.wx, self.wy = edge_weights_local(gray32(images[1]), eroded, 45, min_weight)  # :381-392
+        self.A_bwd_ref, self.A_fwd_ref = A_bwd_reference, A_fwd_reference
+        self.l1, self.l2, self.lc = float(lambda_1storder), float(lambda_2ndorder), float(lambda_consistency)
+        self.afac_sq = float(A_scale_factor) ** 2
+        self.rtol = rtol
+        L = _lib.lib()
+        self.scratch = torch.empty(L.mrf_var_scratch_bytes(), dtype=U8, device=self.dev)
+        self.e2 = _Scalar(self.dev, 2)
+        self.ec = _Scalar(self.dev, 1)
+        z = lambda: torch.empty((self.h, self.w), dtype=F64, device=self.dev)
+        self.buf = {k: z() for k in ("arg1", "arg2", "root1", "root2", "p1x", "p1y", "p2x", "p2y", "D", "bd", "Izc", "argc",
+                                     "rootc", "pc", "sA", "b", "Apd", "med")}
+        self.last = None
+
+    def _sigma(self, roots):
+        return max(1e-6, 1.4826 * device.median(roots.view(-1)))           # utils/robust_functions.py:23-29
+
+    def step(self, A):
+        """One outer iteration on ``A`` (fp64 CUDA [h,w], updated in place).  Returns the energy (:564)."""
+        L = _lib.lib()
+        h, w, n, B = self.h, self.w, self.n, self.buf
+        s_bwd = self.mu[0] / self.mu[1]
+        check(L.mrf_vec_scale(_p(A), n, s_bwd, _p(B["med"]), _stream()), "mrf_vec_scale")           # A * mu0/mu1 (:436)
+        df, bf, Ef, _ = device.data_term(A, self.ch[1], self.ch[2], self.nonrigid, self.occ_f, self.H[1], self.B[1],
+                                         self.mu[1], self.q[1], cw=self.cw, prepared=self.prep_f)   # :425-432
+        db, bb, Eb, _ = device.data_term(B["med"], self.ch[1], self.ch[0], self.nonrigid, self.occ_b, self.H[0], self.B[0],
+                                         self.mu[0], self.q[0], cw=self.cw, prepared=self.prep_b)   # :435-442
+        check(L.mrf_var_data_merge(_p(df), _p(bf), _p(db), _p(bb), _p(self.occ_f), _p(self.occ_b), _p(A), _p(self.A_bwd_ref),
+                                   _p(self.A_fwd_ref), n, s_bwd, self.mu[1] / self.mu[0], self.afac_sq, _p(B["D"]), _p(B["bd"]),
+                                   _p(B["Izc"]), _p(B["argc"]), _p(B["rootc"]), _stream()), "mrf_var_data_merge")
+        pc = None
+        E_cons = 0.0
+        if self.lc != 0.0:
+            eps_c = self._sigma(B["rootc"])
+            check(L.mrf_var_consistency_weights(_p(B["argc"]), n, self.afac_sq, eps_c, _p(B["pc"]), _p(self.ec.d),
+                                                _p(self.scratch), _stream()), "mrf_var_consistency_weights")
+            pc = B["pc"]
+        check(L.mrf_var_smooth_args(_p(A), _p(self.wx), _p(self.wy), h, w, self.afac_sq, _p(B["arg1"]), _p(B["arg2"]),
+                                    _p(B["root1"]), _p(B["root2"]), _stream()), "mrf_var_smooth_args")
+        s1 = self._sigma(B["root1"])
+        s2 = self._sigma(B["root2"])
+        check(L.mrf_var_smooth_weights(_p(B["arg1"]), _p(B["arg2"]), _p(self.wx), _p(self.wy), n, self.afac_sq, s1, s2,
+                                       _p(B["p1x"]), _p(B["p1y"]), _p(B["p2x"]), _p(B["p2y"]), _p(self.e2.d), _p(self.scratch),
+                                       _stream()), "mrf_var_smooth_weights")
+        # right-hand side: (l1 A1 + l2 A2) A without the rigidity mask, then b = Z(-bd - ... ) (:581-588)
+        smooth = Operator(h, w, None, None, B["p1x"], B["p1y"], B["p2x"], B["p2y"], None, self.l1, self.l2, 0.0, eps=0.0)
+        smooth.apply(A, B["sA"])
+        check(L.mrf_var_rhs(_p(B["bd"]), _p(B["sA"]), _p(pc), _p(B["Izc"]), _p(self.rigid), n, self.lc, _p(B["b"]), _stream()),
+              "mrf_var_rhs")
+        op = Operator(h, w, self.rigid, B["D"], B["p1x"], B["p1y"], B["p2x"], B["p2y"], pc, self.l1, self.l2, self.lc)
+        da, info = minres(op, B["b"], rtol=self.rtol)                                               # :593
+        check(L.mrf_var_clip_update(_p(da), _p(A), h, w, dvec(self.q[1]), self.mu[1], self.B[1], 1.0, _p(B["Apd"]), _stream()),
+              "mrf_var_clip_update")                                                                # :600-612
+        check(L.mrf_median7x7_f64(_p(B["Apd"]), h, w, _p(B["med"]), _stream()), "mrf_median7x7_f64")   # :636
+        e12 = self.e2.get().copy()
+        if pc is not None:
+            E_cons = float(self.ec.get()[0])
+        energy = (float(Ef.cpu()[0]) + float(Eb.cpu()[0]) + self.l1 * float(e12[0]) + self.l2 * float(e12[1])
+                  + self.lc * E_cons)                                                               # :564
+        self.last = dict(op=op, da_raw=da, info=info, sigma=(s1, s2), E=(float(Ef.cpu()[0]), float(Eb.cpu()[0]),
+                                                                         float(e12[0]), float(e12[1]), E_cons))
+        check(L.mrf_var_advance(_p(A), _p(B["med"]), n, _stream()), "mrf_var_advance")              # :650
+        return energy / (h * w)

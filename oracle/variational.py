@@ -81,9 +81,14 @@ def _robust(kind):
 def optimize_structure_single_scale(A_init, A_bwd_reference, A_fwd_reference, occlusions_bwd, occlusions_fwd,
                                     occlusions_both, rigidity, images, H_ar, B_ar, q_ar, mu_ar, lambda_1storder,
                                     lambda_2ndorder, lambda_consistency, A_scale_factor=1.0, N_outer=10, N_inner=1,
-                                    min_weight=0.0, return_trace=False):
+                                    min_weight=0.0, return_trace=False, weights_ulp_jitter=None):
     """optimize_structure_single_scale.py:310-652.  ``images`` are the three RGB frames (fp64 [h,w,3] in [0,1]).
-    Returns (A, energies) -- and, with return_trace, a list of per-iteration dicts for the kernel tests."""
+    Returns (A, energies) -- and, with return_trace, a list of per-iteration dicts for the kernel tests.
+
+    ``weights_ulp_jitter`` (a seed) moves every fp32 edge weight by one unit in the last place, up or down at
+    random: the tests use it to measure how far the reference's own result moves under the rounding freedom of
+    its fp32 ``np.exp`` (MINRES at rtol 1e-5 on this stiff system amplifies such changes), which is the yardstick
+    for the GPU path whose expf rounds differently."""
     robust_ev, robust_deriv = _robust("lorentzian")                       # :333
     robust_ev_c, robust_deriv_c = _robust("charbonnier")                  # :336
     afac_sq = A_scale_factor ** 2
@@ -92,6 +97,11 @@ def optimize_structure_single_scale(A_init, A_bwd_reference, A_fwd_reference, oc
     h, w = ch[1].shape[:2]
     weights_x, weights_y = weights_locally_normalized(
         cv2.cvtColor(images[1].astype("float32"), cv2.COLOR_RGB2GRAY))    # :381-383
+    if weights_ulp_jitter is not None:
+        rs = np.random.RandomState(weights_ulp_jitter)
+        for wgt in (weights_x, weights_y):
+            up_ = rs.rand(*wgt.shape) < 0.5
+            wgt[...] = np.where(up_, np.nextafter(wgt, np.float32(2)), np.nextafter(wgt, np.float32(-1)))
     rigidity_eroded = cv2.erode(rigidity.astype("uint8"), kernel=None)    # :387
     weights_x[rigidity_eroded == 0] = 0
     weights_y[rigidity_eroded == 0] = 0

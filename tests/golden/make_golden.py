@@ -218,6 +218,34 @@ def main():
                 _, fu, fv = s2f.combine_flow(out["full_merged1"], t["flow"][1], full[5], full[4], full[2], full[1], full[3],
                                              t["images"], p)
                 out["full_u"], out["full_v"] = fu, fv
+                # --- section 8f row 4: the variational refinement itself, optimize_structure_single_scale.py:310-652
+                # (what stage 5 runs without --override_optimization; one scale, parameters.py:43-45).  Two
+                # py2-isms are shimmed: dict.has_key on vars(params) and the tol= keyword of scipy's minres.
+                sys.path.insert(0, os.path.join(ROOT, "tests"))
+                from variational_case import CASES, LAMBDA_1, LAMBDA_2, variational_inputs
+                from scipy.sparse import linalg as spla
+                from oracle import variational as ov
+                import construct_matrices as cm
+
+                class HK(dict):
+                    def has_key(self, k):
+                        return k in self
+                oss.vars = lambda p_: HK(p_.__dict__)
+                oss.solve = lambda A_, b_, method, tol=1e-3: spla.minres(A_, b_, rtol=tol)[0]
+                assert abs(cm.construct_gradient_matrix((h, w)) - ov.gradient_matrix((h, w))).max() == 0
+                assert abs(cm.construct_2ndorder_matrix((h, w)) - ov.second_order_matrix((h, w))).max() == 0
+                pv = argparse.Namespace(variational_dataterm_grayscale=1, variational_min_weight=0.0, debug_save_frames=0,
+                                        tempdir=".")
+                vin = variational_inputs(t, out)
+                for name, lc, n_outer in CASES:
+                    kwv = {k: (v.copy() if isinstance(v, np.ndarray) else [np.array(e).copy() for e in v]) for k, v in vin.items()}
+                    A_ref, en = oss.optimizeStructureSingleScale(
+                        kwv["A_init"], kwv["A_bwd_reference"], kwv["A_fwd_reference"], kwv["occlusions_bwd"],
+                        kwv["occlusions_fwd"], kwv["occlusions_both"], kwv["rigidity"], kwv["images"], kwv["H_ar"],
+                        [float(b) for b in kwv["B_ar"]], kwv["q_ar"], [float(m) for m in kwv["mu_ar"]], LAMBDA_1, LAMBDA_2, lc,
+                        N_outer=n_outer, params=pv)
+                    out["var_A_" + name] = A_ref
+                    out["var_E_" + name] = np.array(en)
         if example_images is not None:
             out["images"] = np.stack(example_images)
         np.savez_compressed(os.path.join(HERE, "ref_%s.npz" % tag), **out)

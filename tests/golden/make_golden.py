@@ -246,6 +246,21 @@ def main():
                         N_outer=n_outer, params=pv)
                     out["var_A_" + name] = A_ref
                     out["var_E_" + name] = np.array(en)
+                # --- the reference's default chain: stage 5 WITH the variational refinement (parameters.py:38-47:
+                # one scale, 5 outer iterations) and stage 6 on its result
+                import optimize_structure_multi_scale as osm
+                osm.optimize_structure_single_scale = oss
+                ovr.optimize_structure_multi_scale = osm
+                p.override_optimization = 0
+                p.occlusion_reasoning = 1
+                for k_, v_ in dict(variational_lambda_1storder=0.5, variational_lambda_2ndorder=5.0, variational_lambda_consistency=0.0,
+                                   variational_N_outer=5, variational_N_inner=1, variational_scale_factor=0.5, variational_N_scales=1,
+                                   variational_last_scale=0, variational_dataterm_grayscale=1, variational_min_weight=0.0).items():
+                    setattr(p, k_, v_)
+                refined = ovr.optimize([I.copy() for I in t["images"]], full[0], full[5], full[4], full[1], full[3], full[2], occ2, p)[0]
+                out["full_refined"] = refined
+                _, fu, fv = s2f.combine_flow(refined, t["flow"][1], full[5], full[4], full[2], full[1], full[3], t["images"], p)
+                out["full_refined_u"], out["full_refined_v"] = fu, fv
         if example_images is not None:
             out["images"] = np.stack(example_images)
         np.savez_compressed(os.path.join(HERE, "ref_%s.npz" % tag), **out)

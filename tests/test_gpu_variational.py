@@ -175,3 +175,68 @@ def test_optimize_structure_single_scale_vs_reference(case):
                                                             **vin)[0] - want).max() for seed in (1, 2))
         err = np.abs(A - want)
         assert err.max() <= max(4 * own, 1e-6) and err.max() <= 5e-4, (name, err.max(), own)
+
+
+def test_default_stage5_and_6_vs_reference(case):
+    """The reference's default chain after compute_structure: optimize() with the variational refinement
+    (parameters.py:38-47) and combine_flow, through the drop-in modules, against the reference's own outputs.
+    Yardstick as above: the reference's own movement under a one-ulp change of its fp32 edge weights."""
+    from mrflow_b200.pipeline import optimize_variational_refinement as ovr, structure2flow as s2f
+    from oracle import hotpath as hp, variational as ov
+    from variational_case import stage5_inputs
+    tag, g, _ = case
+    t = golden_triplet(tag)
+    p = argparse.Namespace(override_optimization=0, occlusion_reasoning=1, debug_save_frames=0, debug_compute_figure=0, tempdir=".",
+                           variational_lambda_1storder=0.5, variational_lambda_2ndorder=5.0, variational_lambda_consistency=0.0,
+                           variational_N_outer=5, variational_N_inner=1, variational_scale_factor=0.5, variational_N_scales=1,
+                           variational_last_scale=0, variational_dataterm_grayscale=1, variational_min_weight=0.0)
+    S = [g["full_S"][0], g["full_S"][1]]
+    occ = [g["full_occ"][0], g["full_occ"][1]]
+    A = ovr.optimize(t["images"], S, g["full_rigidity"], g["full_q"], t["homographies"], g["full_B"], g["full_mu"], occ, p)[0]
+    _, u, v = s2f.combine_flow(A, t["flow"][1], g["full_rigidity"], g["full_q"], g["full_mu"], t["homographies"], g["full_B"],
+                               t["images"], p)
+    vin = stage5_inputs(t, g)
+    own_A, own_f = 0.0, 0.0
+    for seed in (1, 2):
+        Aj, _ = ov.optimize_structure_single_scale(lambda_1storder=0.5, lambda_2ndorder=5.0, lambda_consistency=0.0, N_outer=5,
+                                                   weights_ulp_jitter=seed, **vin)
+        _, uj, vj = hp.combine_flow(Aj, t["flow"][1], g["full_rigidity"], g["full_q"], g["full_mu"], t["homographies"], g["full_B"])
+        own_A = max(own_A, np.abs(Aj - g["full_refined"]).max())
+        own_f = max(own_f, np.abs(uj - g["full_refined_u"]).max(), np.abs(vj - g["full_refined_v"]).max())
+    eA = np.abs(A - g["full_refined"]).max()
+    ef = max(np.abs(u - g["full_refined_u"]).max(), np.abs(v - g["full_refined_v"]).max())
+    assert eA <= max(4 * own_A, 1e-6) and eA <= 2e-3, (eA, own_A)
+    assert ef <= max(4 * own_f, 1e-4) and ef <= 1e-2, (ef, own_f)
+
+
+def test_multi_scale_driver_two_levels(case, monkeypatch):
+    """optimize_structure_multi_scale.py with a two-level pyramid (scaled homographies, epipoles, mu, B per level,
+    :96-104): the driver with the GPU solver against the same driver with the oracle's solver plugged in."""
+    from mrflow_b200.structure_refinement import optimize_structure_multi_scale as osm
+    from oracle import variational as ov
+    from variational_case import stage5_inputs
+    tag, g, _ = case
+    vin = stage5_inputs(golden_triplet(tag), g)
+    p = argparse.Namespace(variational_lambda_1storder=0.5, variational_lambda_2ndorder=5.0, variational_lambda_consistency=0.0,
+                           variational_N_outer=2, variational_N_inner=1, variational_scale_factor=0.5, variational_N_scales=2,
+                           variational_last_scale=0, variational_dataterm_grayscale=1, variational_min_weight=0.0, tempdir=".")
+    args = (vin["A_init"], vin["A_bwd_reference"], vin["A_fwd_reference"], vin["occlusions_bwd"], vin["occlusions_fwd"],
+            vin["rigidity"], vin["images"], vin["H_ar"], vin["B_ar"], vin["q_ar"], vin["mu_ar"], p)
+    A, energies = osm.optimizeStructureMultiScale(*args)
+    assert A.shape == vin["A_init"].shape and np.isfinite(A).all() and len(energies) == 4
+
+    def with_oracle(jitter):
+        def solve(A_init, A_bwd, A_fwd, ob, of, oboth, rig, images, H_ar, B_ar, q_ar, mu_ar, l1, l2, lc, A_scale_factor=1.0,
+                  N_outer=10, N_inner=1, params=None):
+            return ov.optimize_structure_single_scale(A_init, A_bwd, A_fwd, ob, of, oboth, rig, images, H_ar, B_ar, q_ar, mu_ar, l1,
+                                                      l2, lc, A_scale_factor=A_scale_factor, N_outer=N_outer,
+                                                      weights_ulp_jitter=jitter)
+        monkeypatch.setattr(osm.optimize_structure_single_scale, "optimizeStructureSingleScale", solve)
+        return osm.optimizeStructureMultiScale(*args)
+    want, want_e = with_oracle(None)
+    jit = [with_oracle(seed) for seed in (1, 2)]
+    own = max(np.abs(j[0] - want).max() for j in jit)
+    own_e = max(np.abs(np.array(j[1]) / np.array(want_e) - 1).max() for j in jit)
+    err = np.abs(A - want).max()
+    err_e = np.abs(np.array(energies) / np.array(want_e) - 1).max()
+    assert err <= max(4 * own, 1e-6) and err <= 2e-3 and err_e <= max(4 * own_e, 1e-6), (err, own, err_e, own_e)

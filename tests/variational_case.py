@@ -18,3 +18,20 @@ def variational_inputs(t, g):
                 rigidity=g["full_rigidity"].astype(bool), images=[np.asarray(I, dtype=np.float64) for I in t["images"]],
                 H_ar=[np.asarray(H, dtype=np.float64) for H in t["homographies"]], B_ar=[float(b) for b in g["full_B"]],
                 q_ar=[np.asarray(q, dtype=np.float64) for q in g["full_q"]], mu_ar=[float(m) for m in g["full_mu"]])
+
+
+def stage5_inputs(t, g):
+    """What pipeline/optimize_variational_refinement.py:20-89 hands to the solver for the fixture's full-stage
+    outputs (median-blurred occlusion maps :23-24, rescaled backward structure :41, merged initialisation)."""
+    import cv2
+    occ_b = cv2.medianBlur(g["full_occ"][0].astype("uint8"), ksize=3) > 0
+    occ_f = cv2.medianBlur(g["full_occ"][1].astype("uint8"), ksize=3) > 0
+    both = occ_f * occ_b
+    occ_f = occ_f.copy(); occ_b = occ_b.copy()
+    occ_f[both] = 0; occ_b[both] = 0            # optimize_structure_multi_scale.py:80-83
+    mu = [float(m) for m in g["full_mu"]]
+    return dict(A_init=g["full_merged1"], A_bwd_reference=g["full_S"][0] * mu[1] / mu[0], A_fwd_reference=g["full_S"][1],
+                occlusions_bwd=occ_b, occlusions_fwd=occ_f, occlusions_both=both, rigidity=g["full_rigidity"].astype(bool),
+                images=[np.asarray(I, dtype=np.float64) for I in t["images"]],
+                H_ar=[np.asarray(H, dtype=np.float64) for H in t["homographies"]], B_ar=[float(b) for b in g["full_B"]],
+                q_ar=[np.asarray(q, dtype=np.float64) for q in g["full_q"]], mu_ar=mu)

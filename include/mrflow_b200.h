@@ -407,15 +407,28 @@ int mrf_var_apply(const double* x, const uint8_t* rigid, const double* D, const 
 /* b = Z (-bd - smooth_A - lc * pc * Iz_c)  (:581, :588) */
 int mrf_var_rhs(const double* bd, const double* smooth_A, const double* pc, const double* Iz_c,
                 const uint8_t* rigid, size_t n, double lc, double* b, mrf_stream_t stream);
-/* the vector steps of scipy.sparse.linalg.minres (the solver behind :86/:593); dot products land in
- * one device double each, the scalar recurrences stay with the caller */
 int mrf_vec_scale(const double* y, size_t n, double s, double* out, mrf_stream_t stream);
-int mrf_minres_alfa(double* y, const double* r1, double c, int use_r1, const double* v, size_t n,
-                    double* out_dot, void* scratch, mrf_stream_t stream);
-int mrf_minres_beta(double* y, double* r1, double* r2, double c, size_t n, double* out_dot, void* scratch,
+/* scipy.sparse.linalg.minres (the solver behind :86/:593; x0 = 0, no preconditioner) kept on the device:
+ * the scalar recurrences and stopping tests live in ``state`` (MRF_MINRES_STATE_WORDS doubles), so the
+ * host can enqueue iterations in batches and read (itn, istop) once per batch; iterations enqueued after
+ * the solve has stopped do nothing.  r3 = three vectors [3][n] (r1, r2 = y and the next y, rotating),
+ * w2 = two vectors [2][n], v and x one vector each; scratch: mrf_minres_scratch_bytes(h, w) bytes.
+ * mrf_minres_iterate enqueues iterations itn_done+1 .. itn_done+n_iters of the operator of mrf_var_apply. */
+#define MRF_MINRES_STATE_WORDS 32
+#define MRF_MINRES_ITN    18
+#define MRF_MINRES_ISTOP  19   /* scipy's istop (1..6, -1); 100 = b was zero */
+#define MRF_MINRES_ANORM  20
+#define MRF_MINRES_ACOND  21
+#define MRF_MINRES_RNORM  22
+#define MRF_MINRES_YNORM  23
+size_t mrf_minres_scratch_bytes(int h, int w);
+int mrf_minres_init(const double* b, size_t n, double* r3, double* w2, double* x, double* state, void* scratch,
                     mrf_stream_t stream);
-int mrf_minres_update(const double* v, double* w, double* w2, double oldeps, double delta, double denom,
-                      double phi, double* x, size_t n, double* out_dot, void* scratch, mrf_stream_t stream);
+int mrf_minres_iterate(const uint8_t* rigid, const double* D, const double* p1x, const double* p1y,
+                       const double* p2x, const double* p2y, const double* pc, double l1, double l2, double lc,
+                       double eps, int h, int w, double* r3, double* w2, double* v, double* x, double* state,
+                       void* scratch, int itn_done, int n_iters, double rtol, long long maxiter,
+                       mrf_stream_t stream);
 /* :600-612 NaN/inf scrub, clip_dA (:157-183), clip to +-1; writes A + dA */
 int mrf_var_clip_update(const double* da, const double* A, int h, int w, const double* q_host, double mu,
                         double B, double threshold, double* A_plus_da, mrf_stream_t stream);

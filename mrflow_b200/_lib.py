@@ -36,6 +36,8 @@ class FrontParams(C.Structure):
 
 
 STATE_MU, STATE_B, STATE_MINMAX, STATE_NANFLAG, STATE_LABELS, STATE_WORDS = 0, 2, 4, 8, 16, 16 + 256
+# MRF_MINRES_* of the header: the device-resident MINRES state block
+MINRES_STATE_WORDS, MINRES_ITN, MINRES_ISTOP, MINRES_ANORM, MINRES_ACOND, MINRES_RNORM, MINRES_YNORM = 32, 18, 19, 20, 21, 22, 23
 
 
 _P, _I, _D, _Z = C.c_void_p, C.c_int, C.c_double, C.c_size_t
@@ -108,9 +110,10 @@ SIGNATURES = {
     "mrf_var_apply": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _D, _D, _D, _D, _I, _I, _P, _P]),
     "mrf_var_rhs": (_I, [_P, _P, _P, _P, _P, _Z, _D, _P, _P]),
     "mrf_vec_scale": (_I, [_P, _Z, _D, _P, _P]),
-    "mrf_minres_alfa": (_I, [_P, _P, _D, _I, _P, _Z, _P, _P, _P]),
-    "mrf_minres_beta": (_I, [_P, _P, _P, _D, _Z, _P, _P, _P]),
-    "mrf_minres_update": (_I, [_P, _P, _P, _D, _D, _D, _D, _P, _Z, _P, _P, _P]),
+    "mrf_minres_scratch_bytes": (_Z, [_I, _I]),
+    "mrf_minres_init": (_I, [_P, _Z, _P, _P, _P, _P, _P, _P]),
+    "mrf_minres_iterate": (_I, [_P, _P, _P, _P, _P, _P, _P, _D, _D, _D, _D, _I, _I, _P, _P, _P, _P, _P, _P, _I, _I, _D,
+                                C.c_longlong, _P]),
     "mrf_var_clip_update": (_I, [_P, _P, _I, _I, _DP, _D, _D, _D, _P, _P]),
     "mrf_median7x7_f64": (_I, [_P, _I, _I, _P, _P]),
     "mrf_var_advance": (_I, [_P, _P, _Z, _P]),

@@ -206,10 +206,10 @@ __device__ __forceinline__ double zval(const VarOp& o, const double* __restrict_
   return (!o.rigid || o.rigid[i]) ? x[i] : 0.0;
 }
 // G'P1G v and G2'P2G2 v at pixel (x, y), v = Z x gathered on the fly
-__device__ __forceinline__ double smooth_apply(const VarOp& o, const double* __restrict__ xv, int x, int y) {
+__device__ __forceinline__ double smooth_apply(const VarOp& o, const double* __restrict__ xv, int x, int y, double s = 1.0) {
   const int h = o.h, w = o.w;
   const long long i = (long long)y * w + x;
-  auto V = [&](int yy, int xx) -> double { return zval(o, xv, (long long)yy * w + xx); };
+  auto V = [&](int yy, int xx) -> double { return s * zval(o, xv, (long long)yy * w + xx); };   // v = s*y as scipy forms it
   auto DX = [&](int yy, int xx) -> double { return (xx + 1 < w) ? V(yy, xx + 1) - V(yy, xx) : 0.0; };
   auto DY = [&](int yy, int xx) -> double { return (yy + 1 < h) ? V(yy + 1, xx) - V(yy, xx) : 0.0; };
   auto DXX = [&](int yy, int xx) -> double { return (V(yy, xx > 0 ? xx - 1 : xx) + V(yy, xx + 1 < w ? xx + 1 : xx)) - 2.0 * V(yy, xx); };
@@ -269,59 +269,192 @@ k_var_rhs(const double* __restrict__ bd, const double* __restrict__ sA, const do
   }
 }
 
-// ------------------------------------------------------------------------------- MINRES vector steps
+// ------------------------------------------------------------------------------- MINRES, device-resident
+// scipy.sparse.linalg.minres (x0 = 0, no preconditioner, shift 0) with every scalar of the recurrences in a
+// small state block in HBM.  One iteration = three kernels; each ends in a dot product whose partial sums
+// are combined, in index order, by whichever block finishes last, and that block's thread 0 then advances
+// the scalar recurrences -- so no value ever travels to the host inside the loop.  Kernels return at once
+// when the state says the solve has stopped, which lets the host enqueue iterations in batches and look at
+// (itn, istop) once per batch.
+//   A: v = y / beta;  t = Op v  (- (beta/oldb) r1 from the 2nd iteration);  alfa = <v, t>
+//   B: t -= (alfa/beta) r2;  (r1, r2) <- (r2, t) by buffer rotation;  beta' = |t|;  plane rotation scalars
+//   C: w' = (v - oldeps w1 - delta w2) / gamma;  x += phi w';  ynorm = |x|;  norms and stopping tests
+enum {
+  MS_BETA1 = 0, MS_OLDB, MS_BETA, MS_DBAR, MS_EPSLN, MS_PHIBAR, MS_RHS1, MS_RHS2, MS_TNORM2, MS_GMAX, MS_GMIN, MS_CS, MS_SN,
+  MS_ALFA, MS_OLDEPS, MS_DELTA, MS_DENOM, MS_PHI, MS_ITN, MS_ISTOP, MS_ANORM, MS_ACOND, MS_RNORM, MS_YNORM, MS_ROOT, MS_GBAR,
+  MS_GAMMA, MS_TEST1, MS_TEST2, MS_WORDS = 32
+};
+static_assert(MS_ITN == MRF_MINRES_ITN && MS_ISTOP == MRF_MINRES_ISTOP && MS_ANORM == MRF_MINRES_ANORM &&
+              MS_ACOND == MRF_MINRES_ACOND && MS_RNORM == MRF_MINRES_RNORM && MS_YNORM == MRF_MINRES_YNORM &&
+              MS_WORDS == MRF_MINRES_STATE_WORDS, "state layout is part of the ABI");
+constexpr double kEps = 2.220446049250313e-16;
+constexpr double kDblMax = 1.7976931348623157e308;
+
+// sum of this block's value with all others: every block stores its partial, takes a ticket; the last one
+// adds the partials in index order (fixed tree) -> same bits whichever block is last.  Returns true in
+// thread 0 of the last block, with the total in *total.
+__device__ __forceinline__ bool grid_sum_last(double v, double* __restrict__ partial, unsigned* __restrict__ ticket,
+                                              unsigned nblocks, unsigned block_id, double* sh, double* total) {
+  __shared__ bool s_last;
+  v = block_sum256(v, sh);
+  if (threadIdx.x == 0) {
+    partial[block_id] = v;
+    __threadfence();
+    s_last = (atomicAdd(ticket, 1u) == nblocks - 1);
+  }
+  __syncthreads();
+  if (!s_last) return false;
+  __threadfence();
+  double acc = 0.0;
+  for (unsigned k = threadIdx.x; k < nblocks; k += blockDim.x) acc += __ldcg(partial + k);
+  acc = block_sum256(acc, sh);
+  if (threadIdx.x == 0) { *ticket = 0; *total = acc; return true; }
+  return false;
+}
+
+__global__ void __launch_bounds__(256)
+k_minres_init(const double* __restrict__ b, long long n, double* __restrict__ r1, double* __restrict__ r2, double* __restrict__ w,
+              double* __restrict__ w2, double* __restrict__ x, double* __restrict__ state, double* __restrict__ partial,
+              unsigned* __restrict__ ticket) {
+  __shared__ double sh[8];
+  double acc = 0.0;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const double v = b[i];
+    r1[i] = v; r2[i] = v; w[i] = 0.0; w2[i] = 0.0; x[i] = 0.0;
+    acc += v * v;
+  }
+  double tot;
+  if (grid_sum_last(acc, partial, ticket, gridDim.x, blockIdx.x, sh, &tot)) {
+    for (int k = 0; k < MS_WORDS; ++k) state[k] = 0.0;
+    const double beta1 = sqrt(tot);
+    state[MS_BETA1] = beta1; state[MS_BETA] = beta1; state[MS_PHIBAR] = beta1; state[MS_RHS1] = beta1;
+    state[MS_GMIN] = kDblMax; state[MS_CS] = -1.0;
+    if (tot == 0.0) state[MS_ISTOP] = 100.0;          // b = 0: x = 0 is the answer (scipy returns before iterating)
+  }
+}
+
+__global__ void __launch_bounds__(256)
+k_minres_apply(VarOp o, const double* __restrict__ y, const double* __restrict__ r1, double* __restrict__ t,
+               double* __restrict__ v, double* __restrict__ state, double* __restrict__ partial, unsigned* __restrict__ ticket) {
+  __shared__ double sh[8];
+  if (state[MS_ISTOP] != 0.0) return;
+  const double beta = state[MS_BETA], oldb = state[MS_OLDB];
+  const bool later = state[MS_ITN] >= 1.0;
+  const double s = 1.0 / beta;
+  const double c = later ? beta / oldb : 0.0;
+  const int px = blockIdx.x * 32 + (threadIdx.x & 31), py = blockIdx.y * 8 + (threadIdx.x >> 5);
+  double acc = 0.0;
+  if (px < o.w && py < o.h) {
+    const long long i = (long long)py * o.w + px;
+    const double vi = s * y[i];
+    double r = 0.0;
+    if (!o.rigid || o.rigid[i]) {
+      r = smooth_apply(o, y, px, py, s);
+      if (o.D) r += o.D[i] * vi;
+      if (o.pc) r += o.lc * (o.pc[i] * vi);
+    }
+    r = r + o.eps * vi;
+    if (later) r = r - c * r1[i];
+    v[i] = vi; t[i] = r;
+    acc = vi * r;
+  }
+  double tot;
+  const unsigned nb = gridDim.x * gridDim.y, bid = blockIdx.y * gridDim.x + blockIdx.x;
+  if (grid_sum_last(acc, partial, ticket, nb, bid, sh, &tot)) state[MS_ALFA] = tot;
+}
+
+__global__ void __launch_bounds__(256)
+k_minres_tail(double* __restrict__ t, const double* __restrict__ r2, long long n, double* __restrict__ state,
+              double* __restrict__ partial, unsigned* __restrict__ ticket) {
+  __shared__ double sh[8];
+  if (state[MS_ISTOP] != 0.0) return;
+  const double alfa = state[MS_ALFA], beta0 = state[MS_BETA];
+  const double c = alfa / beta0;
+  double acc = 0.0;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const double y = t[i] - c * r2[i];
+    t[i] = y;
+    acc += y * y;
+  }
+  double tot;
+  if (grid_sum_last(acc, partial, ticket, gridDim.x, blockIdx.x, sh, &tot)) {
+    const double itn = state[MS_ITN] + 1.0;
+    const double oldb = beta0;
+    const double beta = sqrt(tot);
+    state[MS_OLDB] = oldb; state[MS_BETA] = beta;
+    state[MS_TNORM2] = state[MS_TNORM2] + ((alfa * alfa + oldb * oldb) + beta * beta);
+    if (itn == 1.0 && beta / state[MS_BETA1] <= 10.0 * kEps) state[MS_ISTOP] = -1.0;
+    const double cs = state[MS_CS], sn = state[MS_SN], dbar0 = state[MS_DBAR];
+    state[MS_OLDEPS] = state[MS_EPSLN];
+    const double delta = cs * dbar0 + sn * alfa;
+    const double gbar = sn * dbar0 - cs * alfa;
+    const double epsln = sn * beta;
+    const double dbar = -cs * beta;
+    const double root = sqrt(gbar * gbar + dbar * dbar);
+    double gamma = sqrt(gbar * gbar + beta * beta);
+    gamma = fmax(gamma, kEps);
+    const double phibar0 = state[MS_PHIBAR];
+    const double cs1 = gbar / gamma, sn1 = beta / gamma;
+    state[MS_DELTA] = delta; state[MS_GBAR] = gbar; state[MS_EPSLN] = epsln; state[MS_DBAR] = dbar; state[MS_ROOT] = root;
+    state[MS_GAMMA] = gamma; state[MS_CS] = cs1; state[MS_SN] = sn1;
+    state[MS_PHI] = cs1 * phibar0; state[MS_PHIBAR] = sn1 * phibar0;
+    state[MS_DENOM] = 1.0 / gamma;
+  }
+}
+
+__global__ void __launch_bounds__(256)
+k_minres_step(const double* __restrict__ v, double* w1n, const double* __restrict__ w2, double* __restrict__ x, long long n, double rtol, double maxiter, double* __restrict__ state,
+              double* __restrict__ partial, unsigned* __restrict__ ticket) {
+  __shared__ double sh[8];
+  const double istop0 = state[MS_ISTOP];
+  if (istop0 != 0.0 && istop0 != -1.0) return;
+  if (istop0 == -1.0 && state[MS_ITN] >= 1.0) return;      // -1 is raised inside iteration 1 and ends it
+  const double oldeps = state[MS_OLDEPS], delta = state[MS_DELTA], denom = state[MS_DENOM], phi = state[MS_PHI];
+  double acc = 0.0;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const double w = ((v[i] - oldeps * w1n[i]) - delta * w2[i]) * denom;      // the new w takes w1's place
+    w1n[i] = w;
+    const double xn = x[i] + phi * w;
+    x[i] = xn;
+    acc += xn * xn;
+  }
+  double tot;
+  if (grid_sum_last(acc, partial, ticket, gridDim.x, blockIdx.x, sh, &tot)) {
+    const double itn = state[MS_ITN] + 1.0;
+    state[MS_ITN] = itn;
+    const double gamma = state[MS_GAMMA];
+    const double gmax = fmax(state[MS_GMAX], gamma), gmin = fmin(state[MS_GMIN], gamma);
+    state[MS_GMAX] = gmax; state[MS_GMIN] = gmin;
+    const double z = state[MS_RHS1] / gamma;
+    state[MS_RHS1] = state[MS_RHS2] - delta * z;
+    state[MS_RHS2] = -state[MS_EPSLN] * z;
+    const double Anorm = sqrt(state[MS_TNORM2]);
+    const double ynorm = sqrt(tot);
+    const double epsx = (Anorm * ynorm) * kEps;
+    const double rnorm = state[MS_PHIBAR];
+    const double inf = __longlong_as_double(0x7FF0000000000000ll);
+    const double test1 = (ynorm == 0.0 || Anorm == 0.0) ? inf : rnorm / (Anorm * ynorm);
+    const double test2 = (Anorm == 0.0) ? inf : state[MS_ROOT] / Anorm;
+    const double Acond = gmax / gmin;
+    double istop = istop0;
+    if (istop == 0.0) {
+      if (1.0 + test2 <= 1.0) istop = 2.0;
+      if (1.0 + test1 <= 1.0) istop = 1.0;
+      if (itn >= maxiter) istop = 6.0;
+      if (Acond >= 0.1 / kEps) istop = 4.0;
+      if (epsx >= state[MS_BETA1]) istop = 3.0;
+      if (test2 <= rtol) istop = 2.0;
+      if (test1 <= rtol) istop = 1.0;
+    }
+    state[MS_ISTOP] = istop; state[MS_ANORM] = Anorm; state[MS_ACOND] = Acond; state[MS_RNORM] = rnorm; state[MS_YNORM] = ynorm;
+    state[MS_TEST1] = test1; state[MS_TEST2] = test2;
+  }
+}
+
 // out = s * y
 __global__ void __launch_bounds__(256)
 k_scale(const double* __restrict__ y, long long n, double s, double* __restrict__ out) {
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) out[i] = s * y[i];
-}
-// y -= c * r (if use_r);  partial[block] = sum v*y
-__global__ void __launch_bounds__(256)
-k_axpy_dot(double* __restrict__ y, const double* __restrict__ r, double c, int use_r, const double* __restrict__ v, long long n,
-           double* __restrict__ partial) {
-  __shared__ double sh[8];
-  double acc = 0.0;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
-    double t = y[i];
-    if (use_r) t = t - c * r[i];
-    y[i] = t;
-    acc += v[i] * t;
-  }
-  acc = block_sum256(acc, sh);
-  if (threadIdx.x == 0) partial[blockIdx.x] = acc;
-}
-// y -= c * r2;  r1 = r2;  r2 = y;  partial = sum y*y
-__global__ void __launch_bounds__(256)
-k_lanczos_tail(double* __restrict__ y, double* __restrict__ r1, double* __restrict__ r2, double c, long long n,
-               double* __restrict__ partial) {
-  __shared__ double sh[8];
-  double acc = 0.0;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
-    const double old2 = r2[i];
-    const double t = y[i] - c * old2;
-    y[i] = t; r1[i] = old2; r2[i] = t;
-    acc += t * t;
-  }
-  acc = block_sum256(acc, sh);
-  if (threadIdx.x == 0) partial[blockIdx.x] = acc;
-}
-// w_new = (v - oldeps*w1 - delta*w2) * denom (w1 <- w2, w2 <- w, w <- w_new);  x += phi * w_new;  partial = sum x*x
-__global__ void __launch_bounds__(256)
-k_minres_update(const double* __restrict__ v, double* __restrict__ w, double* __restrict__ w2, double oldeps, double delta,
-                double denom, double phi, double* __restrict__ x, long long n, double* __restrict__ partial) {
-  __shared__ double sh[8];
-  double acc = 0.0;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
-    const double w1_ = w2[i];        // previous w2 becomes w1
-    const double w2_ = w[i];         // previous w becomes w2
-    const double wn = ((v[i] - oldeps * w1_) - delta * w2_) * denom;
-    w2[i] = w2_; w[i] = wn;
-    const double xn = x[i] + phi * wn;
-    x[i] = xn;
-    acc += xn * xn;
-  }
-  acc = block_sum256(acc, sh);
-  if (threadIdx.x == 0) partial[blockIdx.x] = acc;
 }
 
 // ------------------------------------------------------------------------------- update
@@ -493,37 +626,55 @@ int mrf_vec_scale(const double* y, size_t n, double s, double* out, mrf_stream_t
   return check_launch("mrf_vec_scale");
 }
 
-int mrf_minres_alfa(double* y, const double* r1, double c, int use_r1, const double* v, size_t n, double* out_dot,
-                    void* scratch, mrf_stream_t stream) {
-  MRF_CHECK_ARG(y && v && out_dot && scratch && n > 0 && (!use_r1 || r1));
-  const unsigned g = lin_grid((long long)n);
-  k_axpy_dot<<<g, 256, 0, S(stream)>>>(y, r1, c, use_r1, v, (long long)n, (double*)scratch);
-  int rc = check_launch("mrf_minres_alfa");
-  if (rc) return rc;
-  k_var_sum_final<<<1, kVarBlocks, 0, S(stream)>>>((const double*)scratch, (int)g, 1, out_dot);
-  return check_launch("mrf_minres_alfa/sum");
+size_t mrf_minres_scratch_bytes(int h, int w) {
+  const size_t blocks2d = (size_t)cdiv(w, 32) * cdiv(h, 8);
+  return sizeof(double) * (blocks2d > (size_t)kVarBlocks ? blocks2d : (size_t)kVarBlocks) + 64;
 }
 
-int mrf_minres_beta(double* y, double* r1, double* r2, double c, size_t n, double* out_dot, void* scratch,
+int mrf_minres_init(const double* b, size_t n, double* r3, double* w2, double* x, double* state, void* scratch,
                     mrf_stream_t stream) {
-  MRF_CHECK_ARG(y && r1 && r2 && out_dot && scratch && n > 0);
-  const unsigned g = lin_grid((long long)n);
-  k_lanczos_tail<<<g, 256, 0, S(stream)>>>(y, r1, r2, c, (long long)n, (double*)scratch);
-  int rc = check_launch("mrf_minres_beta");
-  if (rc) return rc;
-  k_var_sum_final<<<1, kVarBlocks, 0, S(stream)>>>((const double*)scratch, (int)g, 1, out_dot);
-  return check_launch("mrf_minres_beta/sum");
+  MRF_CHECK_ARG(b && r3 && w2 && x && state && scratch && n > 0);
+  unsigned* ticket = (unsigned*)scratch;
+  double* partial = (double*)((char*)scratch + 64);
+  cudaError_t e = cudaMemsetAsync(ticket, 0, 64, S(stream));
+  if (e != cudaSuccess) return fail((int)e, "mrf_minres_init: %s", cudaGetErrorString(e));
+  // r1 = r3[0], r2 = r3[1]; both w buffers start at zero
+  k_minres_init<<<lin_grid((long long)n), 256, 0, S(stream)>>>(b, (long long)n, r3, r3 + n, w2, w2 + n, x, state, partial, ticket);
+  return check_launch("mrf_minres_init");
 }
 
-int mrf_minres_update(const double* v, double* w, double* w2, double oldeps, double delta, double denom, double phi, double* x,
-                      size_t n, double* out_dot, void* scratch, mrf_stream_t stream) {
-  MRF_CHECK_ARG(v && w && w2 && x && out_dot && scratch && n > 0);
-  const unsigned g = lin_grid((long long)n);
-  k_minres_update<<<g, 256, 0, S(stream)>>>(v, w, w2, oldeps, delta, denom, phi, x, (long long)n, (double*)scratch);
-  int rc = check_launch("mrf_minres_update");
-  if (rc) return rc;
-  k_var_sum_final<<<1, kVarBlocks, 0, S(stream)>>>((const double*)scratch, (int)g, 1, out_dot);
-  return check_launch("mrf_minres_update/sum");
+int mrf_minres_iterate(const uint8_t* rigid, const double* D, const double* p1x, const double* p1y, const double* p2x,
+                       const double* p2y, const double* pc, double l1, double l2, double lc, double eps, int h, int w,
+                       double* r3, double* w2, double* v, double* x, double* state, void* scratch, int itn_done, int n_iters,
+                       double rtol, long long maxiter, mrf_stream_t stream) {
+  MRF_CHECK_ARG(p1x && p1y && p2x && p2y && r3 && w2 && v && x && state && scratch && h > 0 && w > 0 && itn_done >= 0 && n_iters > 0);
+  VarOp o;
+  o.rigid = rigid; o.D = D; o.p1x = p1x; o.p1y = p1y; o.p2x = p2x; o.p2y = p2y; o.pc = pc;
+  o.l1 = l1; o.l2 = l2; o.lc = lc; o.eps = eps; o.h = h; o.w = w;
+  const long long n = (long long)h * w;
+  unsigned* ticket = (unsigned*)scratch;
+  double* partial = (double*)((char*)scratch + 64);
+  dim3 grid2(cdiv(w, 32), cdiv(h, 8));
+  const unsigned g1 = lin_grid(n);
+  for (int k = itn_done; k < itn_done + n_iters; ++k) {
+    // buffer rotation: iteration k reads r1 = r3[k%3], r2 = y = r3[(k+1)%3], writes t = r3[(k+2)%3];
+    // (w1, w2) = (w2[(k+1)%2], w2[k%2]) and the new w goes where w1 was
+    double* r1 = r3 + (size_t)(k % 3) * n;
+    double* r2 = r3 + (size_t)((k + 1) % 3) * n;
+    double* t = r3 + (size_t)((k + 2) % 3) * n;
+    double* w2_ = w2 + (size_t)(k % 2) * n;
+    double* w1_ = w2 + (size_t)((k + 1) % 2) * n;
+    k_minres_apply<<<grid2, 256, 0, S(stream)>>>(o, r2, r1, t, v, state, partial, ticket);
+    int rc = check_launch("mrf_minres_iterate/apply");
+    if (rc) return rc;
+    k_minres_tail<<<g1, 256, 0, S(stream)>>>(t, r2, n, state, partial, ticket);
+    rc = check_launch("mrf_minres_iterate/tail");
+    if (rc) return rc;
+    k_minres_step<<<g1, 256, 0, S(stream)>>>(v, w1_, w2_, x, n, rtol, (double)maxiter, state, partial, ticket);
+    rc = check_launch("mrf_minres_iterate/step");
+    if (rc) return rc;
+  }
+  return 0;
 }
 
 int mrf_var_clip_update(const double* da, const double* A, int h, int w, const double* q_host, double mu, double B,

@@ -4,16 +4,14 @@ structure_refinement/optimize_structure_single_scale.py:310-652: per outer itera
 terms, image-adaptive robust first / second order smoothness, an optional consistency term, one linear
 solve, clipping and a 7x7 median.  The reference assembles scipy.sparse matrices and calls
 scipy.sparse.linalg.minres (:86, :593); here the operator is applied matrix-free by one stencil kernel
-(``mrf_var_apply``) and MINRES runs as fused vector kernels with its scalar recurrences on the host
-(three dot products per iteration come back through a pinned 8-byte read each).
+(``mrf_var_apply``) and MINRES runs on the device, scalar recurrences and stopping tests included
+(``mrf_minres_iterate``: three kernels per iteration, each finishing its own dot product); the host only
+enqueues batches of iterations and reads the solver state once per batch.
 
 Everything numeric is fp64 like the reference; the summation order inside the operator and the dot
 products differs from scipy's CSR products, so results agree to solver tolerance (tests state 1e-6 on the
 structure), not bit for bit.
 """
-import ctypes as C
-import math
-
 import numpy as np
 import torch
 
@@ -75,119 +73,51 @@ class Operator:
         return y
 
 
-def minres(op, b, rtol=1e-5, maxiter=None, shift=0.0):
+MINRES_BATCH = 24        # iterations enqueued between two looks at the solver state
+
+
+class MinresWorkspace:
+    """Vectors and state of one MINRES solve of size h*w, reusable across solves."""
+
+    def __init__(self, h, w, dev="cuda"):
+        L = _lib.lib()
+        n = h * w
+        self.h, self.w, self.n = h, w, n
+        self.r3 = torch.empty((3, n), dtype=F64, device=dev)
+        self.w2 = torch.empty((2, n), dtype=F64, device=dev)
+        self.v = torch.empty(n, dtype=F64, device=dev)
+        self.x = torch.empty(n, dtype=F64, device=dev)
+        self.state = _Scalar(dev, _lib.MINRES_STATE_WORDS)
+        self.scratch = torch.empty(L.mrf_minres_scratch_bytes(h, w), dtype=U8, device=dev)
+
+
+def minres(op, b, rtol=1e-5, maxiter=None, ws=None, batch=MINRES_BATCH):
     """scipy.sparse.linalg.minres(A, b, rtol=...) with x0 = 0 and no preconditioner -- the call behind
-    ``solve(A, b, 'minres', tol)`` (:86).  Same recurrences, same stopping tests, same iteration cap
-    (5 n); vectors stay on the device.  Returns (x, info dict)."""
+    ``solve(A, b, 'minres', tol)`` (:86).  Same recurrences, same stopping tests, same iteration cap (5 n),
+    all evaluated on the device (``mrf_minres_iterate``); the host enqueues ``batch`` iterations at a time and
+    reads the 256-byte state block in between.  Returns (x, info dict); x is ``ws.x`` (valid until the
+    workspace's next solve)."""
     L = _lib.lib()
     n = b.numel()
-    dev = b.device
+    ws = ws or MinresWorkspace(op.h, op.w, b.device)
     if maxiter is None:
         maxiter = 5 * n
-    sc = _Scalar(dev)
-    scratch = torch.empty(L.mrf_var_scratch_bytes(), dtype=U8, device=dev)
-    x = torch.zeros(n, dtype=F64, device=dev)
-    eps = float(np.finfo(np.float64).eps)
-    # r1 = b - A x = b ; y = r1 ; beta1 = <r1, y>
-    r1 = b.reshape(-1).clone()
-    y = r1.clone()
-    v = torch.empty_like(y)
-    check(L.mrf_minres_alfa(_p(y), None, 0.0, 0, _p(r1), n, _p(sc.d), _p(scratch), _stream()), "mrf_minres_alfa")
-    beta1 = float(sc.get()[0])
-    if beta1 < 0:
-        raise ValueError("indefinite preconditioner")
-    if beta1 == 0:
-        return x, dict(istop=0, itn=0)
-    bnorm = math.sqrt(beta1)          # norm(b) (x0 = 0, M = I)
-    beta1 = math.sqrt(beta1)
-    oldb = 0.0; beta = beta1; dbar = 0.0; epsln = 0.0; qrnorm = beta1; phibar = beta1; rhs1 = beta1; rhs2 = 0.0
-    tnorm2 = 0.0; gmax = 0.0; gmin = float(np.finfo(np.float64).max); cs = -1.0; sn = 0.0
-    w = torch.zeros(n, dtype=F64, device=dev)
-    w2 = torch.zeros(n, dtype=F64, device=dev)
-    r2 = r1.clone()
-    istop = 0; itn = 0
-    Anorm = 0.0; Acond = 0.0; rnorm = 0.0; ynorm = 0.0
-    while itn < maxiter:
-        itn += 1
-        s = 1.0 / beta
-        check(L.mrf_vec_scale(_p(y), n, s, _p(v), _stream()), "mrf_vec_scale")                     # v = s*y
-        op.apply(v, y)                                                                              # y = A v - shift v
-        # if itn >= 2: y -= (beta/oldb) r1 ; alfa = <v, y>
-        check(L.mrf_minres_alfa(_p(y), _p(r1), (beta / oldb) if itn >= 2 else 0.0, int(itn >= 2), _p(v), n, _p(sc.d),
-                                _p(scratch), _stream()), "mrf_minres_alfa")
-        alfa = float(sc.get()[0])
-        # y -= (alfa/beta) r2 ; r1 = r2 ; r2 = y ; beta = <r2, y>
-        check(L.mrf_minres_beta(_p(y), _p(r1), _p(r2), alfa / beta, n, _p(sc.d), _p(scratch), _stream()), "mrf_minres_beta")
-        oldb = beta
-        beta = float(sc.get()[0])
-        if beta < 0:
-            raise ValueError("non-symmetric matrix")
-        beta = math.sqrt(beta)
-        tnorm2 += alfa ** 2 + oldb ** 2 + beta ** 2
-        if itn == 1:
-            if beta / beta1 <= 10 * eps:
-                istop = -1
-        oldeps = epsln
-        delta = cs * dbar + sn * alfa
-        gbar = sn * dbar - cs * alfa
-        epsln = sn * beta
-        dbar = -cs * beta
-        root = math.sqrt(gbar * gbar + dbar * dbar)
-        Arnorm = phibar * root
-        gamma = math.sqrt(gbar * gbar + beta * beta)
-        gamma = max(gamma, eps)
-        cs = gbar / gamma
-        sn = beta / gamma
-        phi = cs * phibar
-        phibar = sn * phibar
-        denom = 1.0 / gamma
-        # w1 = w2; w2 = w; w = (v - oldeps*w1 - delta*w2) * denom; x += phi*w ; ynorm = |x|
-        check(L.mrf_minres_update(_p(v), _p(w), _p(w2), oldeps, delta, denom, phi, _p(x), n, _p(sc.d), _p(scratch),
-                                  _stream()), "mrf_minres_update")
-        ynorm = math.sqrt(float(sc.get()[0]))
-        gmax = max(gmax, gamma)
-        gmin = min(gmin, gamma)
-        z = rhs1 / gamma
-        rhs1 = rhs2 - delta * z
-        rhs2 = -epsln * z
-        Anorm = math.sqrt(tnorm2)
-        epsa = Anorm * eps
-        epsx = Anorm * ynorm * eps
-        epsr = Anorm * ynorm * rtol
-        diag = gbar
-        if diag == 0:
-            diag = epsa
-        qrnorm = phibar
-        rnorm = qrnorm
-        if ynorm == 0 or Anorm == 0:
-            test1 = float("inf")
-        else:
-            test1 = rnorm / (Anorm * ynorm)
-        if Anorm == 0:
-            test2 = float("inf")
-        else:
-            test2 = root / Anorm
-        Acond = gmax / gmin
-        if istop == 0:
-            t1 = 1 + test1
-            t2 = 1 + test2
-            if t2 <= 1:
-                istop = 2
-            if t1 <= 1:
-                istop = 1
-            if itn >= maxiter:
-                istop = 6
-            if Acond >= 0.1 / eps:
-                istop = 4
-            if epsx >= beta1:
-                istop = 3
-            if test2 <= rtol:
-                istop = 2
-            if test1 <= rtol:
-                istop = 1
-        if istop != 0:
+    check(L.mrf_minres_init(_p(b), n, _p(ws.r3), _p(ws.w2), _p(ws.x), _p(ws.state.d), _p(ws.scratch), _stream()),
+          "mrf_minres_init")
+    rigid, D, p1x, p1y, p2x, p2y, pc = op.args
+    done = 0
+    while True:
+        k = int(min(batch, maxiter - done))
+        check(L.mrf_minres_iterate(_p(rigid), _p(D), _p(p1x), _p(p1y), _p(p2x), _p(p2y), _p(pc), *op.l, op.h, op.w, _p(ws.r3),
+                                   _p(ws.w2), _p(ws.v), _p(ws.x), _p(ws.state.d), _p(ws.scratch), done, k, float(rtol),
+                                   int(maxiter), _stream()), "mrf_minres_iterate")
+        done += k
+        st = ws.state.get()
+        if st[_lib.MINRES_ISTOP] != 0 or done >= maxiter:
             break
-    return x, dict(istop=istop, itn=itn, rnorm=rnorm, Anorm=Anorm, Acond=Acond)
+    istop = int(st[_lib.MINRES_ISTOP])
+    return ws.x, dict(istop=0 if istop == 100 else istop, itn=int(st[_lib.MINRES_ITN]), rnorm=float(st[_lib.MINRES_RNORM]),
+                      Anorm=float(st[_lib.MINRES_ANORM]), Acond=float(st[_lib.MINRES_ACOND]), enqueued=done)
 
 
 class Refiner:
@@ -223,6 +153,7 @@ class Refiner:
         z = lambda: torch.empty((self.h, self.w), dtype=F64, device=self.dev)
         self.buf = {k: z() for k in ("arg1", "arg2", "root1", "root2", "p1x", "p1y", "p2x", "p2y", "D", "bd", "Izc", "argc",
                                      "rootc", "pc", "sA", "b", "Apd", "med")}
+        self.ws = MinresWorkspace(self.h, self.w, self.dev)
         self.last = None
 
     def _sigma(self, roots):
@@ -261,7 +192,7 @@ class Refiner:
         check(L.mrf_var_rhs(_p(B["bd"]), _p(B["sA"]), _p(pc), _p(B["Izc"]), _p(self.rigid), n, self.lc, _p(B["b"]), _stream()),
               "mrf_var_rhs")
         op = Operator(h, w, self.rigid, B["D"], B["p1x"], B["p1y"], B["p2x"], B["p2y"], pc, self.l1, self.l2, self.lc)
-        da, info = minres(op, B["b"], rtol=self.rtol)                                               # :593
+        da, info = minres(op, B["b"], rtol=self.rtol, ws=self.ws)                                               # :593
         check(L.mrf_var_clip_update(_p(da), _p(A), h, w, dvec(self.q[1]), self.mu[1], self.B[1], 1.0, _p(B["Apd"]), _stream()),
               "mrf_var_clip_update")                                                                # :600-612
         check(L.mrf_median7x7_f64(_p(B["Apd"]), h, w, _p(B["med"]), _stream()), "mrf_median7x7_f64")   # :636

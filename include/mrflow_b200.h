@@ -409,11 +409,12 @@ int mrf_var_rhs(const double* bd, const double* smooth_A, const double* pc, cons
                 const uint8_t* rigid, size_t n, double lc, double* b, mrf_stream_t stream);
 int mrf_vec_scale(const double* y, size_t n, double s, double* out, mrf_stream_t stream);
 /* scipy.sparse.linalg.minres (the solver behind :86/:593; x0 = 0, no preconditioner) kept on the device:
- * the scalar recurrences and stopping tests live in ``state`` (MRF_MINRES_STATE_WORDS doubles), so the
- * host can enqueue iterations in batches and read (itn, istop) once per batch; iterations enqueued after
- * the solve has stopped do nothing.  r3 = three vectors [3][n] (r1, r2 = y and the next y, rotating),
- * w2 = two vectors [2][n], v and x one vector each; scratch: mrf_minres_scratch_bytes(h, w) bytes.
- * mrf_minres_iterate enqueues iterations itn_done+1 .. itn_done+n_iters of the operator of mrf_var_apply. */
+ * mrf_minres_iterate is ONE persistent cooperative kernel that runs iterations itn_done+1 ..
+ * itn_done+n_iters (or until the stopping tests fire) with two grid barriers per iteration; the scalar
+ * recurrences and stopping tests are evaluated in the kernel and kept in ``state``
+ * (MRF_MINRES_STATE_WORDS doubles), which makes the solve resumable.  r3 = three vectors [3][n] (r1, r2 = y
+ * and the next y, rotating), w2 and v2 = two vectors [2][n] each, x one; scratch:
+ * mrf_minres_scratch_bytes(h, w) bytes.  The operator is that of mrf_var_apply. */
 #define MRF_MINRES_STATE_WORDS 32
 #define MRF_MINRES_ITN    18
 #define MRF_MINRES_ISTOP  19   /* scipy's istop (1..6, -1); 100 = b was zero */
@@ -426,7 +427,7 @@ int mrf_minres_init(const double* b, size_t n, double* r3, double* w2, double* x
                     mrf_stream_t stream);
 int mrf_minres_iterate(const uint8_t* rigid, const double* D, const double* p1x, const double* p1y,
                        const double* p2x, const double* p2y, const double* pc, double l1, double l2, double lc,
-                       double eps, int h, int w, double* r3, double* w2, double* v, double* x, double* state,
+                       double eps, int h, int w, double* r3, double* w2, double* v2, double* x, double* state,
                        void* scratch, int itn_done, int n_iters, double rtol, long long maxiter,
                        mrf_stream_t stream);
 /* :600-612 NaN/inf scrub, clip_dA (:157-183), clip to +-1; writes A + dA */

@@ -11,7 +11,9 @@
 // Unlike the cost volume this stage is iterative and latency-bound (hundreds of dependent stencil + dot
 // launches per solve); it is built for parity and residency, not yet tuned.
 #include "common.cuh"
+#include <cooperative_groups.h>
 #include <math.h>
+#include <stdlib.h>
 
 namespace mrf {
 
@@ -206,10 +208,10 @@ __device__ __forceinline__ double zval(const VarOp& o, const double* __restrict_
   return (!o.rigid || o.rigid[i]) ? x[i] : 0.0;
 }
 // G'P1G v and G2'P2G2 v at pixel (x, y), v = Z x gathered on the fly
-__device__ __forceinline__ double smooth_apply(const VarOp& o, const double* __restrict__ xv, int x, int y, double s = 1.0) {
+template <class Acc>
+__device__ __forceinline__ double smooth_apply_f(const VarOp& o, int x, int y, Acc V) {
   const int h = o.h, w = o.w;
   const long long i = (long long)y * w + x;
-  auto V = [&](int yy, int xx) -> double { return s * zval(o, xv, (long long)yy * w + xx); };   // v = s*y as scipy forms it
   auto DX = [&](int yy, int xx) -> double { return (xx + 1 < w) ? V(yy, xx + 1) - V(yy, xx) : 0.0; };
   auto DY = [&](int yy, int xx) -> double { return (yy + 1 < h) ? V(yy + 1, xx) - V(yy, xx) : 0.0; };
   auto DXX = [&](int yy, int xx) -> double { return (V(yy, xx > 0 ? xx - 1 : xx) + V(yy, xx + 1 < w ? xx + 1 : xx)) - 2.0 * V(yy, xx); };
@@ -242,6 +244,10 @@ __device__ __forceinline__ double smooth_apply(const VarOp& o, const double* __r
   }
   return o.l1 * s1 + o.l2 * s2;
 }
+__device__ __forceinline__ double smooth_apply(const VarOp& o, const double* __restrict__ xv, int x, int y) {
+  const int w = o.w;
+  return smooth_apply_f(o, x, y, [&](int yy, int xx) -> double { return zval(o, xv, (long long)yy * w + xx); });
+}
 
 __global__ void __launch_bounds__(256)
 k_var_apply(VarOp o, const double* __restrict__ x, double* __restrict__ y) {
@@ -270,15 +276,16 @@ k_var_rhs(const double* __restrict__ bd, const double* __restrict__ sA, const do
 }
 
 // ------------------------------------------------------------------------------- MINRES, device-resident
-// scipy.sparse.linalg.minres (x0 = 0, no preconditioner, shift 0) with every scalar of the recurrences in a
-// small state block in HBM.  One iteration = three kernels; each ends in a dot product whose partial sums
-// are combined, in index order, by whichever block finishes last, and that block's thread 0 then advances
-// the scalar recurrences -- so no value ever travels to the host inside the loop.  Kernels return at once
-// when the state says the solve has stopped, which lets the host enqueue iterations in batches and look at
-// (itn, istop) once per batch.
-//   A: v = y / beta;  t = Op v  (- (beta/oldb) r1 from the 2nd iteration);  alfa = <v, t>
-//   B: t -= (alfa/beta) r2;  (r1, r2) <- (r2, t) by buffer rotation;  beta' = |t|;  plane rotation scalars
-//   C: w' = (v - oldeps w1 - delta w2) / gamma;  x += phi w';  ynorm = |x|;  norms and stopping tests
+// scipy.sparse.linalg.minres (x0 = 0, no preconditioner, shift 0) as ONE persistent cooperative kernel: the
+// grid (as many blocks as are co-resident) walks the whole solve, two grid-wide barriers per iteration.
+//   phase A: v = y / beta (tile of v staged in shared memory);  t = Op v  (- (beta/oldb) r1 from the 2nd
+//            iteration);  partial <v, t>                                                  -- barrier 1 --
+//   phase B: t -= (alfa/beta) r2;  (r1, r2) <- (r2, t) by buffer rotation;  partial |t|^2  -- barrier 2 --
+//   phase C: w' = (v - oldeps w1 - delta w2) / gamma;  x += phi w';  partial |x|^2   (no barrier: its sum is
+//            read after barrier 1 of the next iteration, v is double-buffered so phase A may run ahead)
+// After a barrier every block adds the per-block partials in index order and advances the scalar
+// recurrences itself -- identical arithmetic in every block, so no broadcast and no host round trip.  The
+// 256-byte state block makes the solve resumable (the host may bound the iterations per launch).
 enum {
   MS_BETA1 = 0, MS_OLDB, MS_BETA, MS_DBAR, MS_EPSLN, MS_PHIBAR, MS_RHS1, MS_RHS2, MS_TNORM2, MS_GMAX, MS_GMIN, MS_CS, MS_SN,
   MS_ALFA, MS_OLDEPS, MS_DELTA, MS_DENOM, MS_PHI, MS_ITN, MS_ISTOP, MS_ANORM, MS_ACOND, MS_RNORM, MS_YNORM, MS_ROOT, MS_GBAR,
@@ -290,102 +297,20 @@ static_assert(MS_ITN == MRF_MINRES_ITN && MS_ISTOP == MRF_MINRES_ISTOP && MS_ANO
 constexpr double kEps = 2.220446049250313e-16;
 constexpr double kDblMax = 1.7976931348623157e308;
 
-// sum of this block's value with all others: every block stores its partial, takes a ticket; the last one
-// adds the partials in index order (fixed tree) -> same bits whichever block is last.  Returns true in
-// thread 0 of the last block, with the total in *total.
-__device__ __forceinline__ bool grid_sum_last(double v, double* __restrict__ partial, unsigned* __restrict__ ticket,
-                                              unsigned nblocks, unsigned block_id, double* sh, double* total) {
-  __shared__ bool s_last;
-  v = block_sum256(v, sh);
-  if (threadIdx.x == 0) {
-    partial[block_id] = v;
-    __threadfence();
-    s_last = (atomicAdd(ticket, 1u) == nblocks - 1);
-  }
-  __syncthreads();
-  if (!s_last) return false;
-  __threadfence();
-  double acc = 0.0;
-  for (unsigned k = threadIdx.x; k < nblocks; k += blockDim.x) acc += __ldcg(partial + k);
-  acc = block_sum256(acc, sh);
-  if (threadIdx.x == 0) { *ticket = 0; *total = acc; return true; }
-  return false;
-}
-
-__global__ void __launch_bounds__(256)
-k_minres_init(const double* __restrict__ b, long long n, double* __restrict__ r1, double* __restrict__ r2, double* __restrict__ w,
-              double* __restrict__ w2, double* __restrict__ x, double* __restrict__ state, double* __restrict__ partial,
-              unsigned* __restrict__ ticket) {
-  __shared__ double sh[8];
-  double acc = 0.0;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
-    const double v = b[i];
-    r1[i] = v; r2[i] = v; w[i] = 0.0; w2[i] = 0.0; x[i] = 0.0;
-    acc += v * v;
-  }
-  double tot;
-  if (grid_sum_last(acc, partial, ticket, gridDim.x, blockIdx.x, sh, &tot)) {
-    for (int k = 0; k < MS_WORDS; ++k) state[k] = 0.0;
-    const double beta1 = sqrt(tot);
-    state[MS_BETA1] = beta1; state[MS_BETA] = beta1; state[MS_PHIBAR] = beta1; state[MS_RHS1] = beta1;
-    state[MS_GMIN] = kDblMax; state[MS_CS] = -1.0;
-    if (tot == 0.0) state[MS_ISTOP] = 100.0;          // b = 0: x = 0 is the answer (scipy returns before iterating)
-  }
-}
-
-__global__ void __launch_bounds__(256)
-k_minres_apply(VarOp o, const double* __restrict__ y, const double* __restrict__ r1, double* __restrict__ t,
-               double* __restrict__ v, double* __restrict__ state, double* __restrict__ partial, unsigned* __restrict__ ticket) {
-  __shared__ double sh[8];
-  if (state[MS_ISTOP] != 0.0) return;
-  const double beta = state[MS_BETA], oldb = state[MS_OLDB];
-  const bool later = state[MS_ITN] >= 1.0;
-  const double s = 1.0 / beta;
-  const double c = later ? beta / oldb : 0.0;
-  const int px = blockIdx.x * 32 + (threadIdx.x & 31), py = blockIdx.y * 8 + (threadIdx.x >> 5);
-  double acc = 0.0;
-  if (px < o.w && py < o.h) {
-    const long long i = (long long)py * o.w + px;
-    const double vi = s * y[i];
-    double r = 0.0;
-    if (!o.rigid || o.rigid[i]) {
-      r = smooth_apply(o, y, px, py, s);
-      if (o.D) r += o.D[i] * vi;
-      if (o.pc) r += o.lc * (o.pc[i] * vi);
-    }
-    r = r + o.eps * vi;
-    if (later) r = r - c * r1[i];
-    v[i] = vi; t[i] = r;
-    acc = vi * r;
-  }
-  double tot;
-  const unsigned nb = gridDim.x * gridDim.y, bid = blockIdx.y * gridDim.x + blockIdx.x;
-  if (grid_sum_last(acc, partial, ticket, nb, bid, sh, &tot)) state[MS_ALFA] = tot;
-}
-
-__global__ void __launch_bounds__(256)
-k_minres_tail(double* __restrict__ t, const double* __restrict__ r2, long long n, double* __restrict__ state,
-              double* __restrict__ partial, unsigned* __restrict__ ticket) {
-  __shared__ double sh[8];
-  if (state[MS_ISTOP] != 0.0) return;
-  const double alfa = state[MS_ALFA], beta0 = state[MS_BETA];
-  const double c = alfa / beta0;
-  double acc = 0.0;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
-    const double y = t[i] - c * r2[i];
-    t[i] = y;
-    acc += y * y;
-  }
-  double tot;
-  if (grid_sum_last(acc, partial, ticket, gridDim.x, blockIdx.x, sh, &tot)) {
-    const double itn = state[MS_ITN] + 1.0;
-    const double oldb = beta0;
-    const double beta = sqrt(tot);
-    state[MS_OLDB] = oldb; state[MS_BETA] = beta;
-    state[MS_TNORM2] = state[MS_TNORM2] + ((alfa * alfa + oldb * oldb) + beta * beta);
-    if (itn == 1.0 && beta / state[MS_BETA1] <= 10.0 * kEps) state[MS_ISTOP] = -1.0;
-    const double cs = state[MS_CS], sn = state[MS_SN], dbar0 = state[MS_DBAR];
-    state[MS_OLDEPS] = state[MS_EPSLN];
+struct MinresScalars {
+  double s[MS_WORDS];
+  __device__ void load(const double* __restrict__ g) { for (int k = 0; k < MS_WORDS; ++k) s[k] = g[k]; }
+  __device__ void store(double* __restrict__ g) const { for (int k = 0; k < MS_WORDS; ++k) g[k] = s[k]; }
+  // after <r2, y> of the Lanczos step: new beta, the previous plane rotation applied, the next one formed
+  __device__ void lanczos(double alfa, double beta_sq) {
+    const double itn = s[MS_ITN] + 1.0;
+    const double oldb = s[MS_BETA];
+    const double beta = sqrt(beta_sq);
+    s[MS_ALFA] = alfa; s[MS_OLDB] = oldb; s[MS_BETA] = beta;
+    s[MS_TNORM2] = s[MS_TNORM2] + ((alfa * alfa + oldb * oldb) + beta * beta);
+    if (itn == 1.0 && beta / s[MS_BETA1] <= 10.0 * kEps) s[MS_ISTOP] = -1.0;
+    const double cs = s[MS_CS], sn = s[MS_SN], dbar0 = s[MS_DBAR];
+    s[MS_OLDEPS] = s[MS_EPSLN];
     const double delta = cs * dbar0 + sn * alfa;
     const double gbar = sn * dbar0 - cs * alfa;
     const double epsln = sn * beta;
@@ -393,62 +318,195 @@ k_minres_tail(double* __restrict__ t, const double* __restrict__ r2, long long n
     const double root = sqrt(gbar * gbar + dbar * dbar);
     double gamma = sqrt(gbar * gbar + beta * beta);
     gamma = fmax(gamma, kEps);
-    const double phibar0 = state[MS_PHIBAR];
+    const double phibar0 = s[MS_PHIBAR];
     const double cs1 = gbar / gamma, sn1 = beta / gamma;
-    state[MS_DELTA] = delta; state[MS_GBAR] = gbar; state[MS_EPSLN] = epsln; state[MS_DBAR] = dbar; state[MS_ROOT] = root;
-    state[MS_GAMMA] = gamma; state[MS_CS] = cs1; state[MS_SN] = sn1;
-    state[MS_PHI] = cs1 * phibar0; state[MS_PHIBAR] = sn1 * phibar0;
-    state[MS_DENOM] = 1.0 / gamma;
+    s[MS_DELTA] = delta; s[MS_GBAR] = gbar; s[MS_EPSLN] = epsln; s[MS_DBAR] = dbar; s[MS_ROOT] = root;
+    s[MS_GAMMA] = gamma; s[MS_CS] = cs1; s[MS_SN] = sn1;
+    s[MS_PHI] = cs1 * phibar0; s[MS_PHIBAR] = sn1 * phibar0;
+    s[MS_DENOM] = 1.0 / gamma;
   }
-}
-
-__global__ void __launch_bounds__(256)
-k_minres_step(const double* __restrict__ v, double* w1n, const double* __restrict__ w2, double* __restrict__ x, long long n, double rtol, double maxiter, double* __restrict__ state,
-              double* __restrict__ partial, unsigned* __restrict__ ticket) {
-  __shared__ double sh[8];
-  const double istop0 = state[MS_ISTOP];
-  if (istop0 != 0.0 && istop0 != -1.0) return;
-  if (istop0 == -1.0 && state[MS_ITN] >= 1.0) return;      // -1 is raised inside iteration 1 and ends it
-  const double oldeps = state[MS_OLDEPS], delta = state[MS_DELTA], denom = state[MS_DENOM], phi = state[MS_PHI];
-  double acc = 0.0;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
-    const double w = ((v[i] - oldeps * w1n[i]) - delta * w2[i]) * denom;      // the new w takes w1's place
-    w1n[i] = w;
-    const double xn = x[i] + phi * w;
-    x[i] = xn;
-    acc += xn * xn;
-  }
-  double tot;
-  if (grid_sum_last(acc, partial, ticket, gridDim.x, blockIdx.x, sh, &tot)) {
-    const double itn = state[MS_ITN] + 1.0;
-    state[MS_ITN] = itn;
-    const double gamma = state[MS_GAMMA];
-    const double gmax = fmax(state[MS_GMAX], gamma), gmin = fmin(state[MS_GMIN], gamma);
-    state[MS_GMAX] = gmax; state[MS_GMIN] = gmin;
-    const double z = state[MS_RHS1] / gamma;
-    state[MS_RHS1] = state[MS_RHS2] - delta * z;
-    state[MS_RHS2] = -state[MS_EPSLN] * z;
-    const double Anorm = sqrt(state[MS_TNORM2]);
-    const double ynorm = sqrt(tot);
+  // after |x|^2: norms and stopping tests of the iteration
+  __device__ void tests(double ynorm_sq, double rtol, double maxiter) {
+    const double itn = s[MS_ITN] + 1.0;
+    s[MS_ITN] = itn;
+    const double gamma = s[MS_GAMMA];
+    const double gmax = fmax(s[MS_GMAX], gamma), gmin = fmin(s[MS_GMIN], gamma);
+    s[MS_GMAX] = gmax; s[MS_GMIN] = gmin;
+    const double z = s[MS_RHS1] / gamma;
+    s[MS_RHS1] = s[MS_RHS2] - s[MS_DELTA] * z;
+    s[MS_RHS2] = -s[MS_EPSLN] * z;
+    const double Anorm = sqrt(s[MS_TNORM2]);
+    const double ynorm = sqrt(ynorm_sq);
     const double epsx = (Anorm * ynorm) * kEps;
-    const double rnorm = state[MS_PHIBAR];
+    const double rnorm = s[MS_PHIBAR];
     const double inf = __longlong_as_double(0x7FF0000000000000ll);
     const double test1 = (ynorm == 0.0 || Anorm == 0.0) ? inf : rnorm / (Anorm * ynorm);
-    const double test2 = (Anorm == 0.0) ? inf : state[MS_ROOT] / Anorm;
+    const double test2 = (Anorm == 0.0) ? inf : s[MS_ROOT] / Anorm;
     const double Acond = gmax / gmin;
-    double istop = istop0;
+    double istop = s[MS_ISTOP];
     if (istop == 0.0) {
       if (1.0 + test2 <= 1.0) istop = 2.0;
       if (1.0 + test1 <= 1.0) istop = 1.0;
       if (itn >= maxiter) istop = 6.0;
       if (Acond >= 0.1 / kEps) istop = 4.0;
-      if (epsx >= state[MS_BETA1]) istop = 3.0;
+      if (epsx >= s[MS_BETA1]) istop = 3.0;
       if (test2 <= rtol) istop = 2.0;
       if (test1 <= rtol) istop = 1.0;
     }
-    state[MS_ISTOP] = istop; state[MS_ANORM] = Anorm; state[MS_ACOND] = Acond; state[MS_RNORM] = rnorm; state[MS_YNORM] = ynorm;
-    state[MS_TEST1] = test1; state[MS_TEST2] = test2;
+    s[MS_ISTOP] = istop; s[MS_ANORM] = Anorm; s[MS_ACOND] = Acond; s[MS_RNORM] = rnorm; s[MS_YNORM] = ynorm;
+    s[MS_TEST1] = test1; s[MS_TEST2] = test2;
   }
+};
+
+// every block adds the G partials in the same order -> the same bits everywhere; result in all threads
+__device__ __forceinline__ double sum_partials_all(const double* partial, unsigned G, double* sh, double* sh_out) {
+  double acc = 0.0;
+  for (unsigned k = threadIdx.x; k < G; k += blockDim.x) acc += __ldcg(partial + k);
+  acc = block_sum256(acc, sh);
+  if (threadIdx.x == 0) *sh_out = acc;
+  __syncthreads();
+  const double r = *sh_out;
+  __syncthreads();
+  return r;
+}
+
+__global__ void __launch_bounds__(256)
+k_minres_init(const double* __restrict__ b, long long n, double* __restrict__ r1, double* __restrict__ r2, double* __restrict__ w,
+              double* __restrict__ w2, double* __restrict__ x, double* __restrict__ partial) {
+  __shared__ double sh[8];
+  double acc = 0.0;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const double v = b[i];
+    r1[i] = v; r2[i] = v; w[i] = 0.0; w2[i] = 0.0; x[i] = 0.0;
+    acc += v * v;
+  }
+  acc = block_sum256(acc, sh);
+  if (threadIdx.x == 0) partial[blockIdx.x] = acc;
+}
+__global__ void __launch_bounds__(kVarBlocks)
+k_minres_init_state(const double* __restrict__ partial, int nblocks, double* __restrict__ state) {
+  __shared__ double sh[32];
+  double v = (threadIdx.x < nblocks) ? partial[threadIdx.x] : 0.0;
+  v = block_sum256(v, sh);
+  if (threadIdx.x == 0) {
+    for (int k = 0; k < MS_WORDS; ++k) state[k] = 0.0;
+    const double beta1 = sqrt(v);
+    state[MS_BETA1] = beta1; state[MS_BETA] = beta1; state[MS_PHIBAR] = beta1; state[MS_RHS1] = beta1;
+    state[MS_GMIN] = kDblMax; state[MS_CS] = -1.0;
+    if (v == 0.0) state[MS_ISTOP] = 100.0;            // b = 0: x = 0 is the answer (scipy returns before iterating)
+  }
+}
+
+constexpr int kTileW = 32, kTileH = 8, kHalo = 2;
+
+__global__ void __launch_bounds__(256)
+k_minres_persistent(VarOp o, double* r3, double* w2buf, double* v2buf, double* x, double* state, double* partial, int itn_done,
+                    int n_iters, double rtol, double maxiter) {
+  namespace cg = cooperative_groups;
+  cg::grid_group grid = cg::this_grid();
+  __shared__ double tile[kTileH + 2 * kHalo][kTileW + 2 * kHalo + 1];
+  __shared__ double sh[8];
+  __shared__ double sh_out;
+  const unsigned G = gridDim.x, bid = blockIdx.x;
+  const int h = o.h, w = o.w;
+  const long long n = (long long)h * w;
+  const int tiles_x = (w + kTileW - 1) / kTileW, tiles_y = (h + kTileH - 1) / kTileH;
+  const int ntiles = tiles_x * tiles_y;
+  double* pa = partial; double* pb = partial + G; double* pcn = partial + 2 * (size_t)G;
+  MinresScalars m;
+  m.load(state);
+  bool pending = false;                        // |x|^2 of the previous iteration not yet reduced
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  for (int k = itn_done; k < itn_done + n_iters; ++k) {
+    if (m.s[MS_ISTOP] != 0.0) break;
+    double* r1 = r3 + (size_t)(k % 3) * n;
+    double* r2 = r3 + (size_t)((k + 1) % 3) * n;
+    double* t = r3 + (size_t)((k + 2) % 3) * n;
+    double* w2_ = w2buf + (size_t)(k % 2) * n;
+    double* w1_ = w2buf + (size_t)((k + 1) % 2) * n;
+    double* v = v2buf + (size_t)(k % 2) * n;
+    // ---- phase A
+    {
+      const double beta = m.s[MS_BETA], oldb = m.s[MS_OLDB];
+      const bool later = k >= 1;               // (MS_ITN still lags by one here: the previous tests are pending)
+      const double sc = 1.0 / beta;
+      const double c = later ? beta / oldb : 0.0;
+      double acc = 0.0;
+      for (int tl = bid; tl < ntiles; tl += G) {
+        const int x0 = (tl % tiles_x) * kTileW, y0 = (tl / tiles_x) * kTileH;
+        for (int e = threadIdx.x; e < (kTileH + 2 * kHalo) * (kTileW + 2 * kHalo); e += 256) {
+          const int ry = e / (kTileW + 2 * kHalo), rx = e % (kTileW + 2 * kHalo);
+          const int gy = y0 + ry - kHalo, gx = x0 + rx - kHalo;
+          double val = 0.0;
+          if (gx >= 0 && gx < w && gy >= 0 && gy < h) {
+            const long long j = (long long)gy * w + gx;
+            val = (!o.rigid || o.rigid[j]) ? sc * r2[j] : 0.0;          // v = s*y as scipy forms it, masked by Z
+          }
+          tile[ry][rx] = val;
+        }
+        __syncthreads();
+        const int px = x0 + tx, py = y0 + ty;
+        if (px < w && py < h) {
+          const long long i = (long long)py * w + px;
+          const double vi = sc * r2[i];
+          double r = 0.0;
+          if (!o.rigid || o.rigid[i]) {
+            r = smooth_apply_f(o, px, py, [&](int yy, int xx) -> double { return tile[yy - y0 + kHalo][xx - x0 + kHalo]; });
+            if (o.D) r += o.D[i] * vi;
+            if (o.pc) r += o.lc * (o.pc[i] * vi);
+          }
+          r = r + o.eps * vi;
+          if (later) r = r - c * r1[i];
+          v[i] = vi; t[i] = r;
+          acc += vi * r;
+        }
+        __syncthreads();
+      }
+      acc = block_sum256(acc, sh);
+      if (threadIdx.x == 0) pa[bid] = acc;
+    }
+    grid.sync();                                                        // barrier 1
+    if (pending) {
+      m.tests(sum_partials_all(pcn, G, sh, &sh_out), rtol, maxiter);
+      pending = false;
+      if (m.s[MS_ISTOP] != 0.0) break;                                  // the previous iteration converged; x is final
+    }
+    const double alfa = sum_partials_all(pa, G, sh, &sh_out);
+    // ---- phase B
+    {
+      const double c2 = alfa / m.s[MS_BETA];
+      double acc = 0.0;
+      for (long long i = bid * 256ll + threadIdx.x; i < n; i += (long long)G * 256) {
+        const double y = t[i] - c2 * r2[i];
+        t[i] = y;
+        acc += y * y;
+      }
+      acc = block_sum256(acc, sh);
+      if (threadIdx.x == 0) pb[bid] = acc;
+    }
+    grid.sync();                                                        // barrier 2
+    m.lanczos(alfa, sum_partials_all(pb, G, sh, &sh_out));
+    // ---- phase C
+    {
+      const double oldeps = m.s[MS_OLDEPS], delta = m.s[MS_DELTA], denom = m.s[MS_DENOM], phi = m.s[MS_PHI];
+      double acc = 0.0;
+      for (long long i = bid * 256ll + threadIdx.x; i < n; i += (long long)G * 256) {
+        const double wn = ((v[i] - oldeps * w1_[i]) - delta * w2_[i]) * denom;      // the new w takes w1's place
+        w1_[i] = wn;
+        const double xn = x[i] + phi * wn;
+        x[i] = xn;
+        acc += xn * xn;
+      }
+      acc = block_sum256(acc, sh);
+      if (threadIdx.x == 0) pcn[bid] = acc;
+      pending = true;
+    }
+  }
+  if (pending) {                                                        // uniform across the grid
+    grid.sync();
+    m.tests(sum_partials_all(pcn, G, sh, &sh_out), rtol, maxiter);
+  }
+  if (bid == 0 && threadIdx.x == 0) m.store(state);
 }
 
 // out = s * y
@@ -626,55 +684,60 @@ int mrf_vec_scale(const double* y, size_t n, double s, double* out, mrf_stream_t
   return check_launch("mrf_vec_scale");
 }
 
+static int persistent_grid(int* blocks_out) {
+  static int cached = 0;
+  if (!cached) {
+    int dev = 0, sms = 0, per_sm = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e == cudaSuccess) e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_minres_persistent, 256, 0);
+    if (e != cudaSuccess) return fail((int)e, "mrf_minres: occupancy query: %s", cudaGetErrorString(e));
+    if (per_sm < 1 || sms < 1) return fail(MRF_E_BADARG, "mrf_minres: kernel does not fit an SM");
+    int cap = 2;                                // resident blocks per SM used (MRF_MINRES_BLOCKS_PER_SM overrides)
+    if (const char* env = getenv("MRF_MINRES_BLOCKS_PER_SM")) { const int v = atoi(env); if (v >= 1) cap = v; }
+    if (per_sm > cap) per_sm = cap;
+    cached = sms * per_sm;
+  }
+  *blocks_out = cached;
+  return 0;
+}
+
 size_t mrf_minres_scratch_bytes(int h, int w) {
-  const size_t blocks2d = (size_t)cdiv(w, 32) * cdiv(h, 8);
-  return sizeof(double) * (blocks2d > (size_t)kVarBlocks ? blocks2d : (size_t)kVarBlocks) + 64;
+  (void)h; (void)w;
+  return sizeof(double) * 4 * 2048;             // per-block partials of the three reductions (grid <= 2048) + init
 }
 
 int mrf_minres_init(const double* b, size_t n, double* r3, double* w2, double* x, double* state, void* scratch,
                     mrf_stream_t stream) {
   MRF_CHECK_ARG(b && r3 && w2 && x && state && scratch && n > 0);
-  unsigned* ticket = (unsigned*)scratch;
-  double* partial = (double*)((char*)scratch + 64);
-  cudaError_t e = cudaMemsetAsync(ticket, 0, 64, S(stream));
-  if (e != cudaSuccess) return fail((int)e, "mrf_minres_init: %s", cudaGetErrorString(e));
+  double* partial = (double*)scratch;
+  const unsigned g = lin_grid((long long)n);
   // r1 = r3[0], r2 = r3[1]; both w buffers start at zero
-  k_minres_init<<<lin_grid((long long)n), 256, 0, S(stream)>>>(b, (long long)n, r3, r3 + n, w2, w2 + n, x, state, partial, ticket);
-  return check_launch("mrf_minres_init");
+  k_minres_init<<<g, 256, 0, S(stream)>>>(b, (long long)n, r3, r3 + n, w2, w2 + n, x, partial);
+  int rc = check_launch("mrf_minres_init");
+  if (rc) return rc;
+  k_minres_init_state<<<1, kVarBlocks, 0, S(stream)>>>(partial, (int)g, state);
+  return check_launch("mrf_minres_init/state");
 }
 
 int mrf_minres_iterate(const uint8_t* rigid, const double* D, const double* p1x, const double* p1y, const double* p2x,
                        const double* p2y, const double* pc, double l1, double l2, double lc, double eps, int h, int w,
-                       double* r3, double* w2, double* v, double* x, double* state, void* scratch, int itn_done, int n_iters,
+                       double* r3, double* w2, double* v2, double* x, double* state, void* scratch, int itn_done, int n_iters,
                        double rtol, long long maxiter, mrf_stream_t stream) {
-  MRF_CHECK_ARG(p1x && p1y && p2x && p2y && r3 && w2 && v && x && state && scratch && h > 0 && w > 0 && itn_done >= 0 && n_iters > 0);
+  MRF_CHECK_ARG(p1x && p1y && p2x && p2y && r3 && w2 && v2 && x && state && scratch && h > 0 && w > 0 && itn_done >= 0 && n_iters > 0);
   VarOp o;
   o.rigid = rigid; o.D = D; o.p1x = p1x; o.p1y = p1y; o.p2x = p2x; o.p2y = p2y; o.pc = pc;
   o.l1 = l1; o.l2 = l2; o.lc = lc; o.eps = eps; o.h = h; o.w = w;
-  const long long n = (long long)h * w;
-  unsigned* ticket = (unsigned*)scratch;
-  double* partial = (double*)((char*)scratch + 64);
-  dim3 grid2(cdiv(w, 32), cdiv(h, 8));
-  const unsigned g1 = lin_grid(n);
-  for (int k = itn_done; k < itn_done + n_iters; ++k) {
-    // buffer rotation: iteration k reads r1 = r3[k%3], r2 = y = r3[(k+1)%3], writes t = r3[(k+2)%3];
-    // (w1, w2) = (w2[(k+1)%2], w2[k%2]) and the new w goes where w1 was
-    double* r1 = r3 + (size_t)(k % 3) * n;
-    double* r2 = r3 + (size_t)((k + 1) % 3) * n;
-    double* t = r3 + (size_t)((k + 2) % 3) * n;
-    double* w2_ = w2 + (size_t)(k % 2) * n;
-    double* w1_ = w2 + (size_t)((k + 1) % 2) * n;
-    k_minres_apply<<<grid2, 256, 0, S(stream)>>>(o, r2, r1, t, v, state, partial, ticket);
-    int rc = check_launch("mrf_minres_iterate/apply");
-    if (rc) return rc;
-    k_minres_tail<<<g1, 256, 0, S(stream)>>>(t, r2, n, state, partial, ticket);
-    rc = check_launch("mrf_minres_iterate/tail");
-    if (rc) return rc;
-    k_minres_step<<<g1, 256, 0, S(stream)>>>(v, w1_, w2_, x, n, rtol, (double)maxiter, state, partial, ticket);
-    rc = check_launch("mrf_minres_iterate/step");
-    if (rc) return rc;
-  }
-  return 0;
+  int blocks = 0;
+  int rc = persistent_grid(&blocks);
+  if (rc) return rc;
+  if (blocks > 2048) blocks = 2048;
+  double* partial = (double*)scratch;
+  double maxit = (double)maxiter;
+  void* args[] = {&o, &r3, &w2, &v2, &x, &state, &partial, &itn_done, &n_iters, &rtol, &maxit};
+  cudaError_t e = cudaLaunchCooperativeKernel((const void*)k_minres_persistent, dim3(blocks), dim3(256), args, 0, S(stream));
+  if (e != cudaSuccess) return fail((int)e, "mrf_minres_iterate: cooperative launch: %s", cudaGetErrorString(e));
+  return check_launch("mrf_minres_iterate");
 }
 
 int mrf_var_clip_update(const double* da, const double* A, int h, int w, const double* q_host, double mu, double B,

@@ -5,8 +5,8 @@ terms, image-adaptive robust first / second order smoothness, an optional consis
 solve, clipping and a 7x7 median.  The reference assembles scipy.sparse matrices and calls
 scipy.sparse.linalg.minres (:86, :593); here the operator is applied matrix-free by one stencil kernel
 (``mrf_var_apply``) and MINRES runs on the device, scalar recurrences and stopping tests included
-(``mrf_minres_iterate``: three kernels per iteration, each finishing its own dot product); the host only
-enqueues batches of iterations and reads the solver state once per batch.
+(``mrf_minres_iterate``: one persistent cooperative kernel, two grid barriers per iteration); the host reads
+the solver state once per solve.
 
 Everything numeric is fp64 like the reference; the summation order inside the operator and the dot
 products differs from scipy's CSR products, so results agree to solver tolerance (tests state 1e-6 on the
@@ -73,7 +73,7 @@ class Operator:
         return y
 
 
-MINRES_BATCH = 24        # iterations enqueued between two looks at the solver state
+MINRES_BATCH = 2000      # iteration bound of one launch of the persistent solver kernel
 
 
 class MinresWorkspace:
@@ -85,7 +85,7 @@ class MinresWorkspace:
         self.h, self.w, self.n = h, w, n
         self.r3 = torch.empty((3, n), dtype=F64, device=dev)
         self.w2 = torch.empty((2, n), dtype=F64, device=dev)
-        self.v = torch.empty(n, dtype=F64, device=dev)
+        self.v2 = torch.empty((2, n), dtype=F64, device=dev)
         self.x = torch.empty(n, dtype=F64, device=dev)
         self.state = _Scalar(dev, _lib.MINRES_STATE_WORDS)
         self.scratch = torch.empty(L.mrf_minres_scratch_bytes(h, w), dtype=U8, device=dev)
@@ -94,8 +94,8 @@ class MinresWorkspace:
 def minres(op, b, rtol=1e-5, maxiter=None, ws=None, batch=MINRES_BATCH):
     """scipy.sparse.linalg.minres(A, b, rtol=...) with x0 = 0 and no preconditioner -- the call behind
     ``solve(A, b, 'minres', tol)`` (:86).  Same recurrences, same stopping tests, same iteration cap (5 n),
-    all evaluated on the device (``mrf_minres_iterate``); the host enqueues ``batch`` iterations at a time and
-    reads the 256-byte state block in between.  Returns (x, info dict); x is ``ws.x`` (valid until the
+    all evaluated on the device by one persistent cooperative kernel (``mrf_minres_iterate``) that runs until
+    the solve stops or ``batch`` iterations have passed; the host then reads the 256-byte state block.  Returns (x, info dict); x is ``ws.x`` (valid until the
     workspace's next solve)."""
     L = _lib.lib()
     n = b.numel()
@@ -109,7 +109,7 @@ def minres(op, b, rtol=1e-5, maxiter=None, ws=None, batch=MINRES_BATCH):
     while True:
         k = int(min(batch, maxiter - done))
         check(L.mrf_minres_iterate(_p(rigid), _p(D), _p(p1x), _p(p1y), _p(p2x), _p(p2y), _p(pc), *op.l, op.h, op.w, _p(ws.r3),
-                                   _p(ws.w2), _p(ws.v), _p(ws.x), _p(ws.state.d), _p(ws.scratch), done, k, float(rtol),
+                                   _p(ws.w2), _p(ws.v2), _p(ws.x), _p(ws.state.d), _p(ws.scratch), done, k, float(rtol),
                                    int(maxiter), _stream()), "mrf_minres_iterate")
         done += k
         st = ws.state.get()

@@ -363,11 +363,13 @@ int mrf_data_term_residual(const double* A, const double* ref_ch, const float* n
                            mrf_stream_t stream);
 /* :294-302: psi = rho'(Iz^2), diag = psi*dphi^2*dr_da^2, b = psi*Iz*dphi*dr_da (before the median
  * filters) and the energy sum(rho(Iz^2)) (one double on the device).  rho in MRF_RHO_LORENTZIAN ..
- * MRF_RHO_LORENTZIAN_AUTO; scratch: mrf_data_term_scratch_bytes() bytes. */
+ * MRF_RHO_LORENTZIAN_AUTO; dev_median (optional, device): the median of |Iz| -- the kernel then forms the
+ * auto-sigma max(1e-6, 1.4826*median) itself and rho_param is ignored, so the host never has to see it;
+ * scratch: mrf_data_term_scratch_bytes() bytes. */
 size_t mrf_data_term_scratch_bytes(void);
 int mrf_data_term_system(const double* Iz, const double* dphi, const double* dr_da, size_t n, int rho,
-                         double rho_param, double* diag, double* b, double* energy, void* scratch,
-                         mrf_stream_t stream);
+                         double rho_param, const double* dev_median, double* diag, double* b, double* energy,
+                         void* scratch, mrf_stream_t stream);
 /* scipy.ndimage.median_filter(size=5) with its default 'reflect' boundary (:299-300) */
 int mrf_median5x5_f64(const double* src, int h, int w, double* dst, mrf_stream_t stream);
 
@@ -386,10 +388,12 @@ size_t mrf_var_scratch_bytes(void);
 int mrf_var_smooth_args(const double* A, const float* wx, const float* wy, int h, int w, double afac_sq,
                         double* arg1, double* arg2, double* root1, double* root2, mrf_stream_t stream);
 /* Lorentzian weights for given sigmas (:511-512, :547-548) and the two energies (:560-561, two doubles
- * on the device) */
+ * on the device); dev_medians2 (optional, device): medians of root1 / root2, the auto-sigmas are then formed
+ * in the kernel */
 int mrf_var_smooth_weights(const double* arg1, const double* arg2, const float* wx, const float* wy, size_t n,
-                           double afac_sq, double sigma1, double sigma2, double* p1x, double* p1y,
-                           double* p2x, double* p2y, double* energies2, void* scratch, mrf_stream_t stream);
+                           double afac_sq, double sigma1, double sigma2, const double* dev_medians2,
+                           double* p1x, double* p1y, double* p2x, double* p2y, double* energies2, void* scratch,
+                           mrf_stream_t stream);
 /* :448-461 forward data term with the backward one where the forward frame is occluded, and the
  * consistency residual / argument of :476-490 */
 int mrf_var_data_merge(const double* diag_f, const double* b_f, const double* diag_b, const double* b_b,
@@ -397,8 +401,9 @@ int mrf_var_data_merge(const double* diag_f, const double* b_f, const double* di
                        const double* A_fwd_ref, size_t n, double scale_bwd, double scale_ref, double afac_sq,
                        double* D, double* bd, double* Iz_c, double* arg_c, double* root_c, mrf_stream_t stream);
 /* Charbonnier weight (auto eps from the caller's median) and energy of the consistency term (:491-497) */
-int mrf_var_consistency_weights(const double* arg_c, size_t n, double afac_sq, double eps, double* pc,
-                                double* energy, void* scratch, mrf_stream_t stream);
+int mrf_var_consistency_weights(const double* arg_c, size_t n, double afac_sq, double eps,
+                                const double* dev_median, double* pc, double* energy, void* scratch,
+                                mrf_stream_t stream);
 /* y = Z (D + l1 G'P1G + l2 G2'P2G2 + lc Pc) Z x + eps x  (:580-595), matrix-free; rigid / D / pc may be
  * NULL (identity / absent) */
 int mrf_var_apply(const double* x, const uint8_t* rigid, const double* D, const double* p1x, const double* p1y,

@@ -98,15 +98,15 @@ SIGNATURES = {
     "mrf_pack_texels": (_I, [_P, _I, _I, _P, _P]),
     "mrf_data_term_residual": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _DP, _DP, _D, _D, _DP, _P, _P, _P, _P]),
     "mrf_data_term_scratch_bytes": (_Z, []),
-    "mrf_data_term_system": (_I, [_P, _P, _P, _Z, _I, _D, _P, _P, _P, _P, _P]),
+    "mrf_data_term_system": (_I, [_P, _P, _P, _Z, _I, _D, _P, _P, _P, _P, _P, _P]),
     "mrf_median5x5_f64": (_I, [_P, _I, _I, _P, _P]),
     "mrf_gray32": (_I, [_P, _I, _Z, _P, _P]),
     "mrf_edge_weights_local": (_I, [_P, _P, _I, _I, _I, _D, _P, _P, _P, _P, _P, _P, _P]),
     "mrf_var_scratch_bytes": (_Z, []),
     "mrf_var_smooth_args": (_I, [_P, _P, _P, _I, _I, _D, _P, _P, _P, _P, _P]),
-    "mrf_var_smooth_weights": (_I, [_P, _P, _P, _P, _Z, _D, _D, _D, _P, _P, _P, _P, _P, _P, _P]),
+    "mrf_var_smooth_weights": (_I, [_P, _P, _P, _P, _Z, _D, _D, _D, _P, _P, _P, _P, _P, _P, _P, _P]),
     "mrf_var_data_merge": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _Z, _D, _D, _D, _P, _P, _P, _P, _P, _P]),
-    "mrf_var_consistency_weights": (_I, [_P, _Z, _D, _D, _P, _P, _P, _P]),
+    "mrf_var_consistency_weights": (_I, [_P, _Z, _D, _D, _P, _P, _P, _P, _P]),
     "mrf_var_apply": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _D, _D, _D, _D, _I, _I, _P, _P]),
     "mrf_var_rhs": (_I, [_P, _P, _P, _P, _P, _Z, _D, _P, _P]),
     "mrf_vec_scale": (_I, [_P, _Z, _D, _P, _P]),

@@ -155,9 +155,13 @@ k_data_term_residual(const double* __restrict__ A, const double* __restrict__ re
 constexpr int kDtBlocks = 1024;
 __global__ void __launch_bounds__(256)
 k_data_term_system(const double* __restrict__ Iz, const double* __restrict__ dphi, const double* __restrict__ drda,
-                   long long n, int kind, double p1, double* __restrict__ diag, double* __restrict__ b,
-                   double* __restrict__ partial) {
+                   long long n, int kind, double p1, const double* __restrict__ dev_median, double* __restrict__ diag,
+                   double* __restrict__ b, double* __restrict__ partial) {
   __shared__ double sh[8];
+  if (dev_median) {                            // auto-sigma from a device-resident median of |Iz| (robust_functions.py:23-29)
+    const double m = *dev_median;
+    p1 = (m != m) ? m : fmax(1e-6, 1.4826 * m);
+  }
   const double s2 = p1 * p1;
   double acc = 0.0;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
@@ -267,11 +271,12 @@ int mrf_data_term_residual(const double* A, const double* ref_ch, const float* n
 
 size_t mrf_data_term_scratch_bytes(void) { return sizeof(double) * kDtBlocks; }
 
-int mrf_data_term_system(const double* Iz, const double* dphi, const double* dr_da, size_t n, int rho, double rho_param,
+int mrf_data_term_system(const double* Iz, const double* dphi, const double* dr_da, size_t n, int rho, double rho_param, const double* dev_median,
                          double* diag, double* b, double* energy, void* scratch, mrf_stream_t stream) {
   MRF_CHECK_ARG(Iz && dphi && dr_da && diag && b && energy && scratch && n > 0);
   MRF_CHECK_ARG(rho >= MRF_RHO_LORENTZIAN && rho <= MRF_RHO_LORENTZIAN_AUTO);
-  k_data_term_system<<<kDtBlocks, 256, 0, S(stream)>>>(Iz, dphi, dr_da, (long long)n, rho, rho_param, diag, b, (double*)scratch);
+  k_data_term_system<<<kDtBlocks, 256, 0, S(stream)>>>(Iz, dphi, dr_da, (long long)n, rho, rho_param, dev_median, diag, b,
+                                                       (double*)scratch);
   int rc = check_launch("mrf_data_term_system");
   if (rc) return rc;
   k_sum_partials<<<1, kDtBlocks, 0, S(stream)>>>((const double*)scratch, kDtBlocks, energy);

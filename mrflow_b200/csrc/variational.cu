@@ -19,6 +19,9 @@ namespace mrf {
 
 constexpr int kVarBlocks = 1024;
 
+// utils/robust_functions.py:23-29 from the median of sqrt(x): max(1e-6, 1.4826 * median), NaN kept
+__device__ __forceinline__ double auto_sigma(double m) { return (m != m) ? m : fmax(1e-6, 1.4826 * m); }
+
 __device__ __forceinline__ double block_sum256(double v, double* sh) {
   for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
   if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = v;
@@ -138,9 +141,11 @@ k_smooth_args(const double* __restrict__ A, const float* __restrict__ wx, const 
 // p1x = wx*psi1, p1y = wy*psi1, p2x = psi2*wx, p2y = psi2*wy ; partial sums of rho(arg1), rho(arg2)
 __global__ void __launch_bounds__(256)
 k_smooth_weights(const double* __restrict__ arg1, const double* __restrict__ arg2, const float* __restrict__ wx,
-                 const float* __restrict__ wy, long long n, double afac_sq, double s1, double s2, double* __restrict__ p1x,
-                 double* __restrict__ p1y, double* __restrict__ p2x, double* __restrict__ p2y, double* __restrict__ partial) {
+                 const float* __restrict__ wy, long long n, double afac_sq, double s1, double s2,
+                 const double* __restrict__ dev_medians, double* __restrict__ p1x, double* __restrict__ p1y,
+                 double* __restrict__ p2x, double* __restrict__ p2y, double* __restrict__ partial) {
   __shared__ double sh[8];
+  if (dev_medians) { s1 = auto_sigma(dev_medians[0]); s2 = auto_sigma(dev_medians[1]); }
   double e1 = 0.0, e2 = 0.0;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
     const double a1 = arg1[i], a2 = arg2[i];
@@ -181,9 +186,10 @@ k_var_data_merge(const double* __restrict__ diag_f, const double* __restrict__ b
 
 // Charbonnier (auto eps) weight and energy of the consistency term (:491-497)
 __global__ void __launch_bounds__(256)
-k_cons_weights(const double* __restrict__ argc, long long n, double afac_sq, double eps, double* __restrict__ pc,
-               double* __restrict__ partial) {
+k_cons_weights(const double* __restrict__ argc, long long n, double afac_sq, double eps, const double* __restrict__ dev_median,
+               double* __restrict__ pc, double* __restrict__ partial) {
   __shared__ double sh[8];
+  if (dev_median) eps = auto_sigma(*dev_median);
   double e = 0.0;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
     const double r = sqrt(argc[i] + eps * eps);
@@ -626,12 +632,12 @@ int mrf_var_smooth_args(const double* A, const float* wx, const float* wy, int h
 }
 
 int mrf_var_smooth_weights(const double* arg1, const double* arg2, const float* wx, const float* wy, size_t n, double afac_sq,
-                           double sigma1, double sigma2, double* p1x, double* p1y, double* p2x, double* p2y,
-                           double* energies2, void* scratch, mrf_stream_t stream) {
+                           double sigma1, double sigma2, const double* dev_medians2, double* p1x, double* p1y, double* p2x,
+                           double* p2y, double* energies2, void* scratch, mrf_stream_t stream) {
   MRF_CHECK_ARG(arg1 && arg2 && wx && wy && p1x && p1y && p2x && p2y && energies2 && scratch && n > 0);
   const unsigned g = lin_grid((long long)n);
-  k_smooth_weights<<<g, 256, 0, S(stream)>>>(arg1, arg2, wx, wy, (long long)n, afac_sq, sigma1, sigma2, p1x, p1y, p2x, p2y,
-                                             (double*)scratch);
+  k_smooth_weights<<<g, 256, 0, S(stream)>>>(arg1, arg2, wx, wy, (long long)n, afac_sq, sigma1, sigma2, dev_medians2, p1x, p1y, p2x,
+                                             p2y, (double*)scratch);
   int rc = check_launch("mrf_var_smooth_weights");
   if (rc) return rc;
   k_var_sum_final<<<1, kVarBlocks, 0, S(stream)>>>((const double*)scratch, (int)g, 2, energies2);
@@ -648,11 +654,11 @@ int mrf_var_data_merge(const double* diag_f, const double* b_f, const double* di
   return check_launch("mrf_var_data_merge");
 }
 
-int mrf_var_consistency_weights(const double* arg_c, size_t n, double afac_sq, double eps, double* pc, double* energy,
-                                void* scratch, mrf_stream_t stream) {
+int mrf_var_consistency_weights(const double* arg_c, size_t n, double afac_sq, double eps, const double* dev_median, double* pc,
+                                double* energy, void* scratch, mrf_stream_t stream) {
   MRF_CHECK_ARG(arg_c && pc && energy && scratch && n > 0);
   const unsigned g = lin_grid((long long)n);
-  k_cons_weights<<<g, 256, 0, S(stream)>>>(arg_c, (long long)n, afac_sq, eps, pc, (double*)scratch);
+  k_cons_weights<<<g, 256, 0, S(stream)>>>(arg_c, (long long)n, afac_sq, eps, dev_median, pc, (double*)scratch);
   int rc = check_launch("mrf_var_consistency_weights");
   if (rc) return rc;
   k_var_sum_final<<<1, kVarBlocks, 0, S(stream)>>>((const double*)scratch, (int)g, 1, energy);

@@ -214,19 +214,33 @@ def select_kth(keys, k, n=None):
     return out
 
 
+_COUNTS = {}
+
+
+def median_dev(keys, n=None, out=None):
+    """numpy.median of the first ``n`` keys as a 1-element fp64 device tensor (no host synchronisation): the
+    fused radix select of the front (8 histogram passes that each resolve the previous byte, one successor
+    pass, mean of the two middle order statistics for even n, NaN if any key is NaN)."""
+    _chk(keys, F64, "keys")
+    L = _lib.lib()
+    n = keys.numel() if n is None else int(n)
+    key = (n, keys.device)
+    cnt = _COUNTS.get(key)
+    if cnt is None:
+        cnt = _COUNTS[key] = torch.tensor([n], dtype=torch.int32, device=keys.device)
+    out = torch.empty(1, dtype=F64, device=keys.device) if out is None else out
+    scratch = torch.empty(L.mrf_select_scratch_bytes(n), dtype=U8, device=keys.device)
+    check(L.mrf_select_median_dev(_p(keys), _p(cnt), max(n, 1), _p(out), _p(scratch), _stream()), "mrf_select_median_dev")
+    return out
+
+
 def median(keys, n=None):
     """numpy.median of the first ``n`` keys (mean of the two middle order statistics for even n,
     NaN if any key is NaN).  Synchronises (returns a Python float)."""
     n = keys.numel() if n is None else int(n)
     if n == 0:
         return float("nan")
-    k = (n - 1) // 2
-    r = select_kth(keys, k, n).cpu().numpy()
-    if r[2] > 0:
-        return float("nan")
-    if n % 2 == 1:
-        return float(r[0])
-    return float(np.mean(np.array([r[0], r[1]])))
+    return float(median_dev(keys, n).cpu()[0])
 
 
 def abs_deviation(x, c, n=None):
@@ -424,7 +438,9 @@ def data_term(A, I1, I2, nonrigid, occluded, H, B, mu, q, rho="lorentzian_auto",
               prepared=None):
     """optimize_structure_single_scale.py:186-305 (computeDataTerm) on device tensors: A fp64 [h,w], I1 / I2
     fp64 [h,w,3] channel stacks, masks uint8.  Returns (diag, b, E, intermediates): the two images after
-    their 5x5 median filters, the energy as a 1-element tensor, and dict(Iz, dphi, dr_da, sigma)."""
+    their 5x5 median filters, the energy as a 1-element tensor, and dict(Iz, dphi, dr_da, sigma) -- with the
+    auto-sigma Lorentzian, ``sigma`` is the device-resident median of |Iz| (sigma = max(1e-6, 1.4826 * median));
+    nothing in here synchronises with the host."""
     _chk(A, F64, "A"); _chk(I1, F64, "I1"); _chk(I2, F64, "I2"); _chk(nonrigid, U8, "nonrigid"); _chk(occluded, U8, "occluded")
     L = _lib.lib()
     h, w = A.shape
@@ -435,12 +451,14 @@ def data_term(A, I1, I2, nonrigid, occluded, H, B, mu, q, rho="lorentzian_auto",
     check(L.mrf_data_term_residual(_p(A), _p(I1), _p(tex), _p(tdx), _p(tdy), _p(d1x), _p(d1y), _p(nonrigid), _p(occluded),
                                    h, w, _mat(H), _pt(q), float(mu), float(B), dvec(cw), _p(Iz), _p(dphi), _p(drda),
                                    _stream()), "mrf_data_term_residual")
-    if rho == "lorentzian_auto":                                    # utils/robust_functions.py:55: MAD auto-sigma
-        sigma = max(1e-6, 1.4826 * median(abs_deviation(Iz.view(-1), 0.0)))
+    med = None
+    if rho == "lorentzian_auto":                                    # utils/robust_functions.py:55: MAD auto-sigma,
+        med = median_dev(abs_deviation(Iz.view(-1), 0.0))           # formed in the kernel from the device-resident median
+        sigma = med
     diag = torch.empty_like(Iz); b = torch.empty_like(Iz); E = torch.empty(1, dtype=F64, device=dev)
     scratch = torch.empty(L.mrf_data_term_scratch_bytes(), dtype=U8, device=dev)
-    check(L.mrf_data_term_system(_p(Iz), _p(dphi), _p(drda), h * w, RHO[rho], float(sigma), _p(diag), _p(b), _p(E),
-                                 _p(scratch), _stream()), "mrf_data_term_system")
+    check(L.mrf_data_term_system(_p(Iz), _p(dphi), _p(drda), h * w, RHO[rho], 0.0 if med is not None else float(sigma), _p(med),
+                                 _p(diag), _p(b), _p(E), _p(scratch), _stream()), "mrf_data_term_system")
     dm = torch.empty_like(diag); bm = torch.empty_like(b)
     check(L.mrf_median5x5_f64(_p(diag), h, w, _p(dm), _stream()), "mrf_median5x5_f64")      # :299
     check(L.mrf_median5x5_f64(_p(b), h, w, _p(bm), _stream()), "mrf_median5x5_f64")         # :300

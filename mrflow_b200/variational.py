@@ -148,19 +148,18 @@ class Refiner:
         self.rtol = rtol
         L = _lib.lib()
         self.scratch = torch.empty(L.mrf_var_scratch_bytes(), dtype=U8, device=self.dev)
-        self.e2 = _Scalar(self.dev, 2)
-        self.ec = _Scalar(self.dev, 1)
+        self.energies = _Scalar(self.dev, 5)             # E_fwd, E_bwd, E_1st, E_2nd, E_cons (:564)
+        self.med = torch.zeros(3, dtype=F64, device=self.dev)   # medians behind the auto-sigmas: 1st, 2nd order, consistency
         z = lambda: torch.empty((self.h, self.w), dtype=F64, device=self.dev)
         self.buf = {k: z() for k in ("arg1", "arg2", "root1", "root2", "p1x", "p1y", "p2x", "p2y", "D", "bd", "Izc", "argc",
                                      "rootc", "pc", "sA", "b", "Apd", "med")}
         self.ws = MinresWorkspace(self.h, self.w, self.dev)
         self.last = None
 
-    def _sigma(self, roots):
-        return max(1e-6, 1.4826 * device.median(roots.view(-1)))           # utils/robust_functions.py:23-29
-
     def step(self, A):
-        """One outer iteration on ``A`` (fp64 CUDA [h,w], updated in place).  Returns the energy (:564)."""
+        """One outer iteration on ``A`` (fp64 CUDA [h,w], updated in place).  Returns the energy (:564).  The
+        only host synchronisations are the read of the solver state after the MINRES launch and of the five
+        energy terms at the end; the auto-sigmas stay on the device as medians."""
         L = _lib.lib()
         h, w, n, B = self.h, self.w, self.n, self.buf
         s_bwd = self.mu[0] / self.mu[1]
@@ -173,35 +172,34 @@ class Refiner:
                                    _p(self.A_fwd_ref), n, s_bwd, self.mu[1] / self.mu[0], self.afac_sq, _p(B["D"]), _p(B["bd"]),
                                    _p(B["Izc"]), _p(B["argc"]), _p(B["rootc"]), _stream()), "mrf_var_data_merge")
         pc = None
-        E_cons = 0.0
         if self.lc != 0.0:
-            eps_c = self._sigma(B["rootc"])
-            check(L.mrf_var_consistency_weights(_p(B["argc"]), n, self.afac_sq, eps_c, _p(B["pc"]), _p(self.ec.d),
-                                                _p(self.scratch), _stream()), "mrf_var_consistency_weights")
+            device.median_dev(B["rootc"].view(-1), out=self.med[2:3])                               # :491-497
+            check(L.mrf_var_consistency_weights(_p(B["argc"]), n, self.afac_sq, 0.0, _p(self.med[2:3]), _p(B["pc"]),
+                                                _p(self.energies.d[4:5]), _p(self.scratch), _stream()),
+                  "mrf_var_consistency_weights")
             pc = B["pc"]
         check(L.mrf_var_smooth_args(_p(A), _p(self.wx), _p(self.wy), h, w, self.afac_sq, _p(B["arg1"]), _p(B["arg2"]),
                                     _p(B["root1"]), _p(B["root2"]), _stream()), "mrf_var_smooth_args")
-        s1 = self._sigma(B["root1"])
-        s2 = self._sigma(B["root2"])
-        check(L.mrf_var_smooth_weights(_p(B["arg1"]), _p(B["arg2"]), _p(self.wx), _p(self.wy), n, self.afac_sq, s1, s2,
-                                       _p(B["p1x"]), _p(B["p1y"]), _p(B["p2x"]), _p(B["p2y"]), _p(self.e2.d), _p(self.scratch),
-                                       _stream()), "mrf_var_smooth_weights")
+        device.median_dev(B["root1"].view(-1), out=self.med[0:1])                                   # auto-sigma medians,
+        device.median_dev(B["root2"].view(-1), out=self.med[1:2])                                   # robust_functions.py:23-29
+        check(L.mrf_var_smooth_weights(_p(B["arg1"]), _p(B["arg2"]), _p(self.wx), _p(self.wy), n, self.afac_sq, 0.0, 0.0,
+                                       _p(self.med), _p(B["p1x"]), _p(B["p1y"]), _p(B["p2x"]), _p(B["p2y"]),
+                                       _p(self.energies.d[2:4]), _p(self.scratch), _stream()), "mrf_var_smooth_weights")
         # right-hand side: (l1 A1 + l2 A2) A without the rigidity mask, then b = Z(-bd - ... ) (:581-588)
         smooth = Operator(h, w, None, None, B["p1x"], B["p1y"], B["p2x"], B["p2y"], None, self.l1, self.l2, 0.0, eps=0.0)
         smooth.apply(A, B["sA"])
         check(L.mrf_var_rhs(_p(B["bd"]), _p(B["sA"]), _p(pc), _p(B["Izc"]), _p(self.rigid), n, self.lc, _p(B["b"]), _stream()),
               "mrf_var_rhs")
         op = Operator(h, w, self.rigid, B["D"], B["p1x"], B["p1y"], B["p2x"], B["p2y"], pc, self.l1, self.l2, self.lc)
-        da, info = minres(op, B["b"], rtol=self.rtol, ws=self.ws)                                               # :593
+        self.energies.d[0:1].copy_(Ef); self.energies.d[1:2].copy_(Eb)
+        da, info = minres(op, B["b"], rtol=self.rtol, ws=self.ws)                                   # :593
         check(L.mrf_var_clip_update(_p(da), _p(A), h, w, dvec(self.q[1]), self.mu[1], self.B[1], 1.0, _p(B["Apd"]), _stream()),
               "mrf_var_clip_update")                                                                # :600-612
         check(L.mrf_median7x7_f64(_p(B["Apd"]), h, w, _p(B["med"]), _stream()), "mrf_median7x7_f64")   # :636
-        e12 = self.e2.get().copy()
-        if pc is not None:
-            E_cons = float(self.ec.get()[0])
-        energy = (float(Ef.cpu()[0]) + float(Eb.cpu()[0]) + self.l1 * float(e12[0]) + self.l2 * float(e12[1])
-                  + self.lc * E_cons)                                                               # :564
-        self.last = dict(op=op, da_raw=da, info=info, sigma=(s1, s2), E=(float(Ef.cpu()[0]), float(Eb.cpu()[0]),
-                                                                         float(e12[0]), float(e12[1]), E_cons))
         check(L.mrf_var_advance(_p(A), _p(B["med"]), n, _stream()), "mrf_var_advance")              # :650
+        E = [float(e) for e in self.energies.get()]
+        if pc is None:
+            E[4] = 0.0
+        energy = E[0] + E[1] + self.l1 * E[2] + self.l2 * E[3] + self.lc * E[4]                      # :564
+        self.last = dict(op=op, da_raw=da, info=info, medians=self.med, E=tuple(E))
         return energy / (h * w)

@@ -214,41 +214,56 @@ __device__ __forceinline__ double zval(const VarOp& o, const double* __restrict_
   return (!o.rigid || o.rigid[i]) ? x[i] : 0.0;
 }
 // G'P1G v and G2'P2G2 v at pixel (x, y), v = Z x gathered on the fly
-template <class Acc>
-__device__ __forceinline__ double smooth_apply_f(const VarOp& o, int x, int y, Acc V) {
+// the ten smoothness weights a pixel's row of the operator touches (centre, left / up, right / down)
+struct SmoothCoef { double p1x_c, p1x_l, p1y_c, p1y_u, p2x_l, p2x_c, p2x_r, p2y_u, p2y_c, p2y_d; };
+__device__ __forceinline__ SmoothCoef load_coef(const VarOp& o, int x, int y) {
   const int h = o.h, w = o.w;
   const long long i = (long long)y * w + x;
+  SmoothCoef c;
+  c.p1x_c = o.p1x[i]; c.p1y_c = o.p1y[i]; c.p2x_c = o.p2x[i]; c.p2y_c = o.p2y[i];
+  c.p1x_l = x > 0 ? o.p1x[i - 1] : 0.0;     c.p2x_l = x > 0 ? o.p2x[i - 1] : 0.0;
+  c.p1y_u = y > 0 ? o.p1y[i - w] : 0.0;     c.p2y_u = y > 0 ? o.p2y[i - w] : 0.0;
+  c.p2x_r = x + 1 < w ? o.p2x[i + 1] : 0.0; c.p2y_d = y + 1 < h ? o.p2y[i + w] : 0.0;
+  return c;
+}
+template <class Acc>
+__device__ __forceinline__ double smooth_apply_c(const VarOp& o, int x, int y, const SmoothCoef& c, Acc V) {
+  const int h = o.h, w = o.w;
   auto DX = [&](int yy, int xx) -> double { return (xx + 1 < w) ? V(yy, xx + 1) - V(yy, xx) : 0.0; };
   auto DY = [&](int yy, int xx) -> double { return (yy + 1 < h) ? V(yy + 1, xx) - V(yy, xx) : 0.0; };
   auto DXX = [&](int yy, int xx) -> double { return (V(yy, xx > 0 ? xx - 1 : xx) + V(yy, xx + 1 < w ? xx + 1 : xx)) - 2.0 * V(yy, xx); };
   auto DYY = [&](int yy, int xx) -> double { return (V(yy > 0 ? yy - 1 : yy, xx) + V(yy + 1 < h ? yy + 1 : yy, xx)) - 2.0 * V(yy, xx); };
   // first order: (G' u)(p) = -ux(p) + ux(p - ex) - uy(p) + uy(p - ey),  u = P1 G v
   double s1 = 0.0;
-  s1 -= o.p1x[i] * DX(y, x);
-  if (x > 0) s1 += o.p1x[i - 1] * DX(y, x - 1);
-  s1 -= o.p1y[i] * DY(y, x);
-  if (y > 0) s1 += o.p1y[i - w] * DY(y - 1, x);
+  s1 -= c.p1x_c * DX(y, x);
+  if (x > 0) s1 += c.p1x_l * DX(y, x - 1);
+  s1 -= c.p1y_c * DY(y, x);
+  if (y > 0) s1 += c.p1y_u * DY(y - 1, x);
   // second order: (Dxx' u)(p) = u(p-1) + u(p+1) - 2u(p), the replicated ends folding back onto p
   double s2 = 0.0;
   {
-    const double uc = o.p2x[i] * DXX(y, x);
+    const double uc = c.p2x_c * DXX(y, x);
     double t = -2.0 * uc;
     if (x == 0) t += uc;
     if (x == w - 1) t += uc;
-    if (x > 0) t += o.p2x[i - 1] * DXX(y, x - 1);
-    if (x + 1 < w) t += o.p2x[i + 1] * DXX(y, x + 1);
+    if (x > 0) t += c.p2x_l * DXX(y, x - 1);
+    if (x + 1 < w) t += c.p2x_r * DXX(y, x + 1);
     s2 += t;
   }
   {
-    const double uc = o.p2y[i] * DYY(y, x);
+    const double uc = c.p2y_c * DYY(y, x);
     double t = -2.0 * uc;
     if (y == 0) t += uc;
     if (y == h - 1) t += uc;
-    if (y > 0) t += o.p2y[i - w] * DYY(y - 1, x);
-    if (y + 1 < h) t += o.p2y[i + w] * DYY(y + 1, x);
+    if (y > 0) t += c.p2y_u * DYY(y - 1, x);
+    if (y + 1 < h) t += c.p2y_d * DYY(y + 1, x);
     s2 += t;
   }
   return o.l1 * s1 + o.l2 * s2;
+}
+template <class Acc>
+__device__ __forceinline__ double smooth_apply_f(const VarOp& o, int x, int y, Acc V) {
+  return smooth_apply_c(o, x, y, load_coef(o, x, y), V);
 }
 __device__ __forceinline__ double smooth_apply(const VarOp& o, const double* __restrict__ xv, int x, int y) {
   const int w = o.w;
@@ -295,7 +310,7 @@ k_var_rhs(const double* __restrict__ bd, const double* __restrict__ sA, const do
 enum {
   MS_BETA1 = 0, MS_OLDB, MS_BETA, MS_DBAR, MS_EPSLN, MS_PHIBAR, MS_RHS1, MS_RHS2, MS_TNORM2, MS_GMAX, MS_GMIN, MS_CS, MS_SN,
   MS_ALFA, MS_OLDEPS, MS_DELTA, MS_DENOM, MS_PHI, MS_ITN, MS_ISTOP, MS_ANORM, MS_ACOND, MS_RNORM, MS_YNORM, MS_ROOT, MS_GBAR,
-  MS_GAMMA, MS_TEST1, MS_TEST2, MS_WORDS = 32
+  MS_GAMMA, MS_TEST1, MS_TEST2, MS_NS_A, MS_NS_BC, MS_NS_SYNC, MS_WORDS = 32
 };
 static_assert(MS_ITN == MRF_MINRES_ITN && MS_ISTOP == MRF_MINRES_ISTOP && MS_ANORM == MRF_MINRES_ANORM &&
               MS_ACOND == MRF_MINRES_ACOND && MS_RNORM == MRF_MINRES_RNORM && MS_YNORM == MRF_MINRES_YNORM &&
@@ -404,23 +419,29 @@ k_minres_init_state(const double* __restrict__ partial, int nblocks, double* __r
 }
 
 constexpr int kTileW = 32, kTileH = 8, kHalo = 2;
+__device__ __forceinline__ unsigned long long gtime() { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
+constexpr int kBatch = 3;                      // elements per thread whose loads are issued together in phases B, C
 
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 2)
 k_minres_persistent(VarOp o, double* r3, double* w2buf, double* v2buf, double* x, double* state, double* partial, int itn_done,
                     int n_iters, double rtol, double maxiter) {
   namespace cg = cooperative_groups;
   cg::grid_group grid = cg::this_grid();
+  __shared__ MinresScalars m;                  // every block keeps its own copy, advanced by its thread 0
   __shared__ double tile[kTileH + 2 * kHalo][kTileW + 2 * kHalo + 1];
   __shared__ double sh[8];
   __shared__ double sh_out;
   const unsigned G = gridDim.x, bid = blockIdx.x;
+  const bool prof = (bid == 0 && threadIdx.x == 0);       // block 0 accounts its own time per phase (ns) in the state
+  unsigned long long nsA = 0, nsBC = 0, nsSync = 0;
   const int h = o.h, w = o.w;
   const long long n = (long long)h * w;
+  const long long stride = (long long)G * 256;
   const int tiles_x = (w + kTileW - 1) / kTileW, tiles_y = (h + kTileH - 1) / kTileH;
   const int ntiles = tiles_x * tiles_y;
   double* pa = partial; double* pb = partial + G; double* pcn = partial + 2 * (size_t)G;
-  MinresScalars m;
-  m.load(state);
+  if (threadIdx.x == 0) m.load(state);
+  __syncthreads();
   bool pending = false;                        // |x|^2 of the previous iteration not yet reduced
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   for (int k = itn_done; k < itn_done + n_iters; ++k) {
@@ -432,37 +453,56 @@ k_minres_persistent(VarOp o, double* r3, double* w2buf, double* v2buf, double* x
     double* w1_ = w2buf + (size_t)((k + 1) % 2) * n;
     double* v = v2buf + (size_t)(k % 2) * n;
     // ---- phase A
+    const unsigned long long tA = prof ? gtime() : 0ull;
     {
       const double beta = m.s[MS_BETA], oldb = m.s[MS_OLDB];
       const bool later = k >= 1;               // (MS_ITN still lags by one here: the previous tests are pending)
       const double sc = 1.0 / beta;
       const double c = later ? beta / oldb : 0.0;
       double acc = 0.0;
+      constexpr int kTW = kTileW + 2 * kHalo, kTE = (kTileH + 2 * kHalo) * kTW;       // 36 x 12 staged values
       for (int tl = bid; tl < ntiles; tl += G) {
         const int x0 = (tl % tiles_x) * kTileW, y0 = (tl / tiles_x) * kTileH;
-        for (int e = threadIdx.x; e < (kTileH + 2 * kHalo) * (kTileW + 2 * kHalo); e += 256) {
-          const int ry = e / (kTileW + 2 * kHalo), rx = e % (kTileW + 2 * kHalo);
+        // issue every load of this tile at once: the (up to two) staged values of this thread with their masks,
+        // and the thread's own coefficients -- one round trip to L2 instead of four
+        double sv[2]; unsigned char sm[2]; bool in[2];
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+          const int e = threadIdx.x + u * 256;
+          const int ry = e / kTW, rx = e % kTW;
           const int gy = y0 + ry - kHalo, gx = x0 + rx - kHalo;
-          double val = 0.0;
-          if (gx >= 0 && gx < w && gy >= 0 && gy < h) {
-            const long long j = (long long)gy * w + gx;
-            val = (!o.rigid || o.rigid[j]) ? sc * r2[j] : 0.0;          // v = s*y as scipy forms it, masked by Z
-          }
-          tile[ry][rx] = val;
+          in[u] = e < kTE && gx >= 0 && gx < w && gy >= 0 && gy < h;
+          const long long j = in[u] ? (long long)gy * w + gx : 0;
+          sv[u] = in[u] ? r2[j] : 0.0;
+          sm[u] = (in[u] && o.rigid) ? o.rigid[j] : (unsigned char)1;
+        }
+        const int px = x0 + tx, py = y0 + ty;
+        const bool own = px < w && py < h;
+        const long long i = own ? (long long)py * w + px : 0;
+        SmoothCoef cf = {};
+        double Di = 0.0, pci = 0.0, r1i = 0.0;
+        if (own) {
+          cf = load_coef(o, px, py);
+          if (o.D) Di = o.D[i];
+          if (o.pc) pci = o.pc[i];
+          if (later) r1i = r1[i];
+        }
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+          const int e = threadIdx.x + u * 256;
+          if (e < kTE) tile[e / kTW][e % kTW] = (in[u] && sm[u]) ? sc * sv[u] : 0.0;     // v = s*y as scipy forms it, masked by Z
         }
         __syncthreads();
-        const int px = x0 + tx, py = y0 + ty;
-        if (px < w && py < h) {
-          const long long i = (long long)py * w + px;
+        if (own) {
           const double vi = sc * r2[i];
           double r = 0.0;
           if (!o.rigid || o.rigid[i]) {
-            r = smooth_apply_f(o, px, py, [&](int yy, int xx) -> double { return tile[yy - y0 + kHalo][xx - x0 + kHalo]; });
-            if (o.D) r += o.D[i] * vi;
-            if (o.pc) r += o.lc * (o.pc[i] * vi);
+            r = smooth_apply_c(o, px, py, cf, [&](int yy, int xx) -> double { return tile[yy - y0 + kHalo][xx - x0 + kHalo]; });
+            if (o.D) r += Di * vi;
+            if (o.pc) r += o.lc * (pci * vi);
           }
           r = r + o.eps * vi;
-          if (later) r = r - c * r1[i];
+          if (later) r = r - c * r1i;
           v[i] = vi; t[i] = r;
           acc += vi * r;
         }
@@ -471,9 +511,13 @@ k_minres_persistent(VarOp o, double* r3, double* w2buf, double* v2buf, double* x
       acc = block_sum256(acc, sh);
       if (threadIdx.x == 0) pa[bid] = acc;
     }
+    const unsigned long long tA1 = prof ? gtime() : 0ull;
     grid.sync();                                                        // barrier 1
+    const unsigned long long tB0 = prof ? gtime() : 0ull;
     if (pending) {
-      m.tests(sum_partials_all(pcn, G, sh, &sh_out), rtol, maxiter);
+      const double ysq = sum_partials_all(pcn, G, sh, &sh_out);
+      if (threadIdx.x == 0) m.tests(ysq, rtol, maxiter);
+      __syncthreads();
       pending = false;
       if (m.s[MS_ISTOP] != 0.0) break;                                  // the previous iteration converged; x is final
     }
@@ -482,37 +526,73 @@ k_minres_persistent(VarOp o, double* r3, double* w2buf, double* v2buf, double* x
     {
       const double c2 = alfa / m.s[MS_BETA];
       double acc = 0.0;
-      for (long long i = bid * 256ll + threadIdx.x; i < n; i += (long long)G * 256) {
-        const double y = t[i] - c2 * r2[i];
-        t[i] = y;
-        acc += y * y;
+      for (long long base = bid * 256ll + threadIdx.x; base < n; base += kBatch * stride) {
+        double a[kBatch], b[kBatch];
+#pragma unroll
+        for (int u = 0; u < kBatch; ++u) {
+          const long long i = base + u * stride;
+          if (i < n) { a[u] = t[i]; b[u] = r2[i]; }
+        }
+#pragma unroll
+        for (int u = 0; u < kBatch; ++u) {
+          const long long i = base + u * stride;
+          if (i < n) {
+            const double y = a[u] - c2 * b[u];
+            t[i] = y;
+            acc += y * y;
+          }
+        }
       }
       acc = block_sum256(acc, sh);
       if (threadIdx.x == 0) pb[bid] = acc;
     }
+    const unsigned long long tB1 = prof ? gtime() : 0ull;
     grid.sync();                                                        // barrier 2
-    m.lanczos(alfa, sum_partials_all(pb, G, sh, &sh_out));
+    const unsigned long long tC0 = prof ? gtime() : 0ull;
+    {
+      const double bsq = sum_partials_all(pb, G, sh, &sh_out);
+      if (threadIdx.x == 0) m.lanczos(alfa, bsq);
+      __syncthreads();
+    }
     // ---- phase C
     {
       const double oldeps = m.s[MS_OLDEPS], delta = m.s[MS_DELTA], denom = m.s[MS_DENOM], phi = m.s[MS_PHI];
       double acc = 0.0;
-      for (long long i = bid * 256ll + threadIdx.x; i < n; i += (long long)G * 256) {
-        const double wn = ((v[i] - oldeps * w1_[i]) - delta * w2_[i]) * denom;      // the new w takes w1's place
-        w1_[i] = wn;
-        const double xn = x[i] + phi * wn;
-        x[i] = xn;
-        acc += xn * xn;
+      for (long long base = bid * 256ll + threadIdx.x; base < n; base += kBatch * stride) {
+        double a[kBatch], b[kBatch], cw[kBatch], d[kBatch];
+#pragma unroll
+        for (int u = 0; u < kBatch; ++u) {
+          const long long i = base + u * stride;
+          if (i < n) { a[u] = v[i]; b[u] = w1_[i]; cw[u] = w2_[i]; d[u] = x[i]; }
+        }
+#pragma unroll
+        for (int u = 0; u < kBatch; ++u) {
+          const long long i = base + u * stride;
+          if (i < n) {
+            const double wn = ((a[u] - oldeps * b[u]) - delta * cw[u]) * denom;       // the new w takes w1's place
+            w1_[i] = wn;
+            const double xn = d[u] + phi * wn;
+            x[i] = xn;
+            acc += xn * xn;
+          }
+        }
       }
       acc = block_sum256(acc, sh);
       if (threadIdx.x == 0) pcn[bid] = acc;
       pending = true;
     }
+    if (prof) { const unsigned long long tC1 = gtime(); nsA += tA1 - tA; nsSync += (tB0 - tA1) + (tC0 - tB1); nsBC += (tB1 - tB0) + (tC1 - tC0); }
   }
   if (pending) {                                                        // uniform across the grid
     grid.sync();
-    m.tests(sum_partials_all(pcn, G, sh, &sh_out), rtol, maxiter);
+    const double ysq = sum_partials_all(pcn, G, sh, &sh_out);
+    if (threadIdx.x == 0) m.tests(ysq, rtol, maxiter);
+    __syncthreads();
   }
-  if (bid == 0 && threadIdx.x == 0) m.store(state);
+  if (bid == 0 && threadIdx.x == 0) {
+    m.s[MS_NS_A] += (double)nsA; m.s[MS_NS_BC] += (double)nsBC; m.s[MS_NS_SYNC] += (double)nsSync;
+    m.store(state);
+  }
 }
 
 // out = s * y

@@ -23,5 +23,7 @@ for rtol in (1e-5, 1e-9):
         x, info = variational.minres(op, b, rtol=rtol, ws=ws)
     e.record(); e.synchronize()
     ms = a.elapsed_time(e) / 5
+    st = ws.state.get()
+    print("   block 0 per iteration: phase A %.2f us, phases B+C %.2f us, barrier waits %.2f us" % tuple(st[k] / 1e3 / info["itn"] for k in (29, 30, 31)))
     print("blocks/SM=%s rtol=%g itn=%d  %.3f ms/solve  %.2f us/iteration" % (os.environ.get("MRF_MINRES_BLOCKS_PER_SM", "default"), rtol,
                                                                          info["itn"], ms, ms * 1e3 / info["itn"]))

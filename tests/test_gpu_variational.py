@@ -148,6 +148,16 @@ def test_minres_matches_scipy():
         got, info = variational.minres(op, torch.from_numpy(b).cuda(), rtol=rtol)
         assert info["itn"] == len(its)
         np.testing.assert_allclose(got.cpu().numpy(), want, rtol=0, atol=1e-9 * np.abs(want).max())
+        # the state block makes the solve resumable: 7 iterations per launch give the same bits
+        first = got.cpu().numpy().copy()
+        again, info2 = variational.minres(op, torch.from_numpy(b).cuda(), rtol=rtol, batch=7)
+        assert info2["itn"] == info["itn"] and info2["istop"] == info["istop"]
+        assert np.array_equal(again.cpu().numpy(), first)
+    # b = 0 -> x = 0 without iterating; an iteration cap is honoured (istop 6)
+    x0, i0 = variational.minres(op, torch.zeros(n, dtype=torch.float64, device="cuda"))
+    assert i0["itn"] == 0 and float(x0.abs().max()) == 0.0
+    _, i6 = variational.minres(op, torch.from_numpy(b).cuda(), rtol=1e-14, maxiter=5)
+    assert i6["itn"] == 5 and i6["istop"] == 6
 
 
 def test_optimize_structure_single_scale_vs_reference(case):

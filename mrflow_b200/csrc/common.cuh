@@ -74,6 +74,32 @@ __device__ __forceinline__ void linear_weights(int frac, float w[2]) {
   w[1] = t;
 }
 
+// Exact median of N (odd) values by forgetful selection: keep N/2+2 candidates, repeatedly move their minimum
+// and maximum to the ends (neither can be the median), replace the minimum by the next unseen value and drop
+// the maximum; three values remain, the middle one is the median.  ~1.5*len compare-exchanges per round
+// instead of the N^2/4 of a partial selection sort.  fetch(k) returns the k-th value (k is a compile-time
+// constant after unrolling, so the candidates stay in registers).
+__device__ __forceinline__ void sort2(double& a, double& b) { const double lo = fmin(a, b), hi = fmax(a, b); a = lo; b = hi; }
+template <int N, class Fetch>
+__device__ __forceinline__ double median_forgetful(Fetch fetch) {
+  static_assert(N % 2 == 1 && N >= 3, "odd window");
+  constexpr int R = N / 2 + 2;
+  double v[R];
+#pragma unroll
+  for (int k = 0; k < R; ++k) v[k] = fetch(k);
+#pragma unroll
+  for (int len = R; len >= 3; --len) {
+#pragma unroll
+    for (int i = 0; i < len / 2; ++i) sort2(v[i], v[len - 1 - i]);
+#pragma unroll
+    for (int i = 1; i < (len + 1) / 2; ++i) sort2(v[0], v[i]);             // minimum -> v[0]
+#pragma unroll
+    for (int i = len / 2; i < len - 1; ++i) sort2(v[i], v[len - 1]);       // maximum -> v[len-1]
+    if (len > 3) v[0] = fetch(N - (len - 3));                              // next unseen value replaces the minimum
+  }
+  return v[1];
+}
+
 }  // namespace mrf
 
 #define MRF_CHECK_ARG(cond) do { if (!(cond)) return mrf::fail(MRF_E_BADARG, "%s: bad argument: %s", __func__, #cond); } while (0)

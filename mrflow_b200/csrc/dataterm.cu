@@ -211,23 +211,11 @@ k_median5x5(const double* __restrict__ src, int h, int w, double* __restrict__ d
   const int x = blockIdx.x * 32 + (threadIdx.x & 31);
   const int y = blockIdx.y * 8 + (threadIdx.x >> 5);
   if (x >= w || y >= h) return;
-  double v[25];
+  int xs[5]; long long ys[5];
 #pragma unroll
-  for (int j = 0; j < 5; ++j) {
-    const int yy = reflect_sym(y + j - 2, h);
-#pragma unroll
-    for (int i = 0; i < 5; ++i) v[j * 5 + i] = src[(long long)yy * w + reflect_sym(x + i - 2, w)];
-  }
-  // partial selection: after pass k the k smallest are in place; the median is element 12
-#pragma unroll
-  for (int k = 0; k <= 12; ++k) {
-#pragma unroll
-    for (int m = k + 1; m < 25; ++m) {
-      const double lo = fmin(v[k], v[m]), hi = fmax(v[k], v[m]);
-      v[k] = lo; v[m] = hi;
-    }
-  }
-  dst[(long long)y * w + x] = v[12];
+  for (int k = 0; k < 5; ++k) { xs[k] = reflect_sym(x + k - 2, w); ys[k] = (long long)reflect_sym(y + k - 2, h) * w; }
+  const double med = median_forgetful<25>([&](int k) -> double { return src[ys[k / 5] + xs[k % 5]]; });
+  dst[(long long)y * w + x] = med;
 }
 
 }  // namespace mrf

@@ -635,22 +635,11 @@ __global__ void __launch_bounds__(128)
 k_median7x7(const double* __restrict__ src, int h, int w, double* __restrict__ dst) {
   const int x = blockIdx.x * 32 + (threadIdx.x & 31), y = blockIdx.y * 4 + (threadIdx.x >> 5);
   if (x >= w || y >= h) return;
-  double v[49];
+  int xs[7]; long long ys[7];
 #pragma unroll
-  for (int j = 0; j < 7; ++j) {
-    const int yy = reflect_sym7(y + j - 3, h);
-#pragma unroll
-    for (int i = 0; i < 7; ++i) v[j * 7 + i] = src[(long long)yy * w + reflect_sym7(x + i - 3, w)];
-  }
-#pragma unroll
-  for (int k = 0; k <= 24; ++k) {
-#pragma unroll
-    for (int m = k + 1; m < 49; ++m) {
-      const double lo = fmin(v[k], v[m]), hi = fmax(v[k], v[m]);
-      v[k] = lo; v[m] = hi;
-    }
-  }
-  dst[(long long)y * w + x] = v[24];
+  for (int k = 0; k < 7; ++k) { xs[k] = reflect_sym7(x + k - 3, w); ys[k] = (long long)reflect_sym7(y + k - 3, h) * w; }
+  const double med = median_forgetful<49>([&](int k) -> double { return src[ys[k / 7] + xs[k % 7]]; });
+  dst[(long long)y * w + x] = med;
 }
 // A <- A + (med - A)   (the reference forms da = median - A and then A + da: two roundings, kept)
 __global__ void __launch_bounds__(256)

@@ -19,6 +19,7 @@ namespace mrf {
 // state layout (uint64 words, device): 0 prefix (high bits found so far), 1 pass (0..8),
 // 2 k remaining inside the prefix class, 3 NaN count, 4 count(keys <= kth), 5 min key > kth
 constexpr int kStWords = 8;
+constexpr int kMemoWords = 32;        // (prefix, rank) after each pass of the fused select
 constexpr int kHistBins = 256;
 
 __device__ __forceinline__ unsigned long long order_key(double v) {
@@ -162,16 +163,20 @@ __global__ void k_select_result(const unsigned long long* __restrict__ st, unsig
 }
 
 // Device-median path: one launch per pass.  Every block first resolves the previous pass's byte from
-// that pass's (complete) histogram -- 256 bins, a few hundred cycles, redundantly in every block --
-// then histograms the next byte; hist is [8][256], zeroed up front.  Block 0 records the running
-// prefix / rank in the state for the final pass.
-__device__ __forceinline__ void resolve_prefix(const unsigned long long* __restrict__ hist_all, int upto,
+// that pass's (complete) histogram -- 256 bins, one round trip to L2 plus a warp scan, redundantly in every
+// block -- then histograms the next byte; hist is [8][256], zeroed up front.  Block 0 memoises the running
+// (prefix, rank) after each pass so that later passes resolve one byte, not all previous ones.
+__device__ __forceinline__ void resolve_prefix(const unsigned long long* __restrict__ hist_all,
+                                               const unsigned long long* __restrict__ memo, int upto,
                                                unsigned long long k, unsigned long long& prefix,
                                                unsigned long long& k_rem) {
-  // serial over passes, warp-parallel over bins (executed by warp 0 of the block)
+  // executed by warp 0 of the block; memo[2*p], memo[2*p+1] = (prefix, rank) after p passes (p >= 1)
   const int lane = threadIdx.x & 31;
   prefix = 0; k_rem = k;
-  for (int p = 0; p < upto; ++p) {
+  if (upto == 0) return;
+  if (upto >= 2) { prefix = memo[2 * (upto - 1)]; k_rem = memo[2 * (upto - 1) + 1]; }
+  {
+    const int p = upto - 1;
     const unsigned long long* h = hist_all + p * kHistBins;
     // each lane owns 8 consecutive bins
     unsigned long long c[8], tot = 0;
@@ -203,23 +208,42 @@ __device__ __forceinline__ void resolve_prefix(const unsigned long long* __restr
 
 __global__ void __launch_bounds__(256)
 k_select_hist_fused(const double* __restrict__ keys, const int* __restrict__ n_dev, int pass,
-                    unsigned long long* __restrict__ st, unsigned long long* __restrict__ hist_all) {
+                    unsigned long long* __restrict__ st, unsigned long long* __restrict__ hist_all,
+                    unsigned long long* __restrict__ memo) {
   __shared__ unsigned int sh[kHistBins];
   __shared__ unsigned long long s_prefix;
   const size_t n = (size_t)max(*n_dev, 0);
   sh[threadIdx.x] = 0;
   if (threadIdx.x < 32) {
     unsigned long long prefix, k_rem;
-    resolve_prefix(hist_all, pass, n ? (unsigned long long)((n - 1) / 2) : 0ull, prefix, k_rem);
-    if (threadIdx.x == 0) s_prefix = prefix;
+    resolve_prefix(hist_all, memo, pass, n ? (unsigned long long)((n - 1) / 2) : 0ull, prefix, k_rem);
+    if (threadIdx.x == 0) {
+      s_prefix = prefix;
+      if (blockIdx.x == 0 && pass >= 1) { memo[2 * pass] = prefix; memo[2 * pass + 1] = k_rem; }
+    }
   }
   __syncthreads();
   const unsigned long long prefix = s_prefix;
   const int shift = 56 - 8 * pass;
   const unsigned long long himask = pass == 0 ? 0ull : (~0ull << (shift + 8));
-  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
-    const unsigned long long k = order_key(keys[i]);
-    if ((k & himask) == prefix) atomicAdd(&sh[(k >> shift) & 0xFF], 1u);
+  // warp-aggregated shared atomics: the leading bytes of real data are concentrated in a few bins, so the
+  // lanes of a warp that hit the same bin send one atomic with their count
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  const size_t first = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  const size_t warp_first = first - (threadIdx.x & 31);
+  for (size_t base = warp_first; base < n; base += stride) {
+    const size_t i = base + (threadIdx.x & 31);
+    bool act = false; unsigned bin = 0;
+    if (i < n) {
+      const unsigned long long k = order_key(keys[i]);
+      act = (k & himask) == prefix;
+      bin = (unsigned)((k >> shift) & 0xFF);
+    }
+    const unsigned amask = __ballot_sync(0xffffffffu, act);
+    if (act) {
+      const unsigned peers = __match_any_sync(amask, bin);
+      if ((threadIdx.x & 31) == (unsigned)(__ffs(peers) - 1)) atomicAdd(&sh[bin], (unsigned)__popc(peers));
+    }
   }
   __syncthreads();
   const unsigned int c = sh[threadIdx.x];
@@ -229,12 +253,13 @@ k_select_hist_fused(const double* __restrict__ keys, const int* __restrict__ n_d
 // successor pass: resolves the last byte, then counts keys <= kth / NaNs / min key above
 __global__ void __launch_bounds__(256)
 k_select_successor_fused(const double* __restrict__ keys, const int* __restrict__ n_dev,
-                         unsigned long long* __restrict__ st, const unsigned long long* __restrict__ hist_all) {
+                         unsigned long long* __restrict__ st, const unsigned long long* __restrict__ hist_all,
+                         const unsigned long long* __restrict__ memo) {
   __shared__ unsigned long long s_kth;
   const size_t n = (size_t)max(*n_dev, 0);
   if (threadIdx.x < 32) {
     unsigned long long prefix, k_rem;
-    resolve_prefix(hist_all, 8, n ? (unsigned long long)((n - 1) / 2) : 0ull, prefix, k_rem);
+    resolve_prefix(hist_all, memo, 8, n ? (unsigned long long)((n - 1) / 2) : 0ull, prefix, k_rem);
     if (threadIdx.x == 0) { s_kth = prefix; if (blockIdx.x == 0) { st[0] = prefix; st[6] = (unsigned long long)n; } }
   }
   __syncthreads();
@@ -369,7 +394,7 @@ using namespace mrf;
 
 extern "C" {
 
-size_t mrf_select_scratch_bytes(size_t) { return sizeof(unsigned long long) * (kStWords + 8 * kHistBins); }
+size_t mrf_select_scratch_bytes(size_t) { return sizeof(unsigned long long) * (kStWords + 8 * kHistBins + kMemoWords); }
 
 int mrf_select_begin(size_t k, void* scratch, mrf_stream_t stream) {
   MRF_CHECK_ARG(scratch);
@@ -453,11 +478,11 @@ int mrf_select_median_dev(const double* keys, const int* n_dev, size_t capacity,
   k_select_init_fused<<<1, 256, 0, S(stream)>>>(st, hist_all);
   int rc = check_launch("mrf_select_median_dev/init");
   for (int pass = 0; pass < 8 && !rc; ++pass) {
-    k_select_hist_fused<<<blocks, 256, 0, S(stream)>>>(keys, n_dev, pass, st, hist_all);
+    k_select_hist_fused<<<blocks, 256, 0, S(stream)>>>(keys, n_dev, pass, st, hist_all, hist_all + 8 * kHistBins);
     rc = check_launch("mrf_select_median_dev/hist");
   }
   if (rc) return rc;
-  k_select_successor_fused<<<blocks, 256, 0, S(stream)>>>(keys, n_dev, st, hist_all);
+  k_select_successor_fused<<<blocks, 256, 0, S(stream)>>>(keys, n_dev, st, hist_all, hist_all + 8 * kHistBins);
   rc = check_launch("mrf_select_median_dev/successor");
   if (rc) return rc;
   k_select_median<<<1, 1, 0, S(stream)>>>(st, out_median);

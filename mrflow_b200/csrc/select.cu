@@ -229,20 +229,25 @@ k_select_hist_fused(const double* __restrict__ keys, const int* __restrict__ n_d
   // warp-aggregated shared atomics: the leading bytes of real data are concentrated in a few bins, so the
   // lanes of a warp that hit the same bin send one atomic with their count
   const size_t stride = (size_t)gridDim.x * blockDim.x;
-  const size_t first = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
-  const size_t warp_first = first - (threadIdx.x & 31);
-  for (size_t base = warp_first; base < n; base += stride) {
-    const size_t i = base + (threadIdx.x & 31);
-    bool act = false; unsigned bin = 0;
-    if (i < n) {
-      const unsigned long long k = order_key(keys[i]);
-      act = (k & himask) == prefix;
-      bin = (unsigned)((k >> shift) & 0xFF);
+  const size_t warp_first = blockIdx.x * (size_t)blockDim.x + threadIdx.x - (threadIdx.x & 31);
+  constexpr int U = 4;                                   // keys per lane whose loads are issued together
+  for (size_t base = warp_first; base < n; base += U * stride) {
+    unsigned long long kk[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const size_t i = base + u * stride + (threadIdx.x & 31);
+      kk[u] = (i < n) ? order_key(keys[i]) : 0ull;
     }
-    const unsigned amask = __ballot_sync(0xffffffffu, act);
-    if (act) {
-      const unsigned peers = __match_any_sync(amask, bin);
-      if ((threadIdx.x & 31) == (unsigned)(__ffs(peers) - 1)) atomicAdd(&sh[bin], (unsigned)__popc(peers));
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const size_t i = base + u * stride + (threadIdx.x & 31);
+      const bool act = (i < n) && ((kk[u] & himask) == prefix);
+      const unsigned bin = (unsigned)((kk[u] >> shift) & 0xFF);
+      const unsigned amask = __ballot_sync(0xffffffffu, act);
+      if (act) {
+        const unsigned peers = __match_any_sync(amask, bin);
+        if ((threadIdx.x & 31) == (unsigned)(__ffs(peers) - 1)) atomicAdd(&sh[bin], (unsigned)__popc(peers));
+      }
     }
   }
   __syncthreads();
@@ -277,7 +282,13 @@ k_select_successor_fused(const double* __restrict__ keys, const int* __restrict_
     const unsigned long long m = __shfl_down_sync(0xffffffffu, min_gt, o);
     min_gt = m < min_gt ? m : min_gt;
   }
-  if ((threadIdx.x & 31) == 0) {
+  // one set of atomics per block, not per warp
+  __shared__ unsigned long long s_red[3][8];
+  if ((threadIdx.x & 31) == 0) { s_red[0][threadIdx.x >> 5] = cnt_le; s_red[1][threadIdx.x >> 5] = nan; s_red[2][threadIdx.x >> 5] = min_gt; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    cnt_le = 0; nan = 0; min_gt = 0xFFFFFFFFFFFFFFFFull;
+    for (int k = 0; k < 8; ++k) { cnt_le += s_red[0][k]; nan += s_red[1][k]; min_gt = s_red[2][k] < min_gt ? s_red[2][k] : min_gt; }
     if (cnt_le) atomicAdd(&st[4], cnt_le);
     if (nan) atomicAdd(&st[3], nan);
     if (min_gt != 0xFFFFFFFFFFFFFFFFull) atomicMin(&st[5], min_gt);
@@ -474,7 +485,10 @@ int mrf_select_median_dev(const double* keys, const int* n_dev, size_t capacity,
   MRF_CHECK_ARG(keys && n_dev && out_median && scratch && capacity > 0);
   unsigned long long* st = (unsigned long long*)scratch;
   unsigned long long* hist_all = st + kStWords;              // [8][256]
-  const unsigned blocks = (unsigned)((capacity + 255) / 256 < (size_t)kSelBlocks ? (capacity + 255) / 256 : kSelBlocks);
+  // two blocks per SM: every block ends with up to 256 global atomics on the pass's histogram and starts
+  // with the (redundant) resolve of the previous byte, so few fat blocks beat many thin ones
+  const size_t cap_blocks = (size_t)kSMs * 2;
+  const unsigned blocks = (unsigned)((capacity + 255) / 256 < cap_blocks ? (capacity + 255) / 256 : cap_blocks);
   k_select_init_fused<<<1, 256, 0, S(stream)>>>(st, hist_all);
   int rc = check_launch("mrf_select_median_dev/init");
   for (int pass = 0; pass < 8 && !rc; ++pass) {

@@ -250,3 +250,35 @@ def test_multi_scale_driver_two_levels(case, monkeypatch):
     err = np.abs(A - want).max()
     err_e = np.abs(np.array(energies) / np.array(want_e) - 1).max()
     assert err <= max(4 * own, 1e-6) and err <= 2e-3 and err_e <= max(4 * own_e, 1e-6), (err, own, err_e, own_e)
+
+
+def test_sintel_size_against_oracle():
+    """BASELINE.json's Sintel shape (1024x436): two outer iterations of the refinement on the GPU against the
+    oracle (scipy sparse + MINRES on the CPU).  On this well-conditioned synthetic scene the two agree to 1e-8;
+    same MINRES iteration counts, energies to 1e-9 relative."""
+    import cv2
+    import torch
+    from mrflow_b200 import synth, variational
+    from mrflow_b200._host import flag, up
+    from oracle import variational as ov
+    t = synth.make_triplet("sintel", seed=1001)
+    h, w = t["shape"]
+    rs = np.random.RandomState(0)
+    A_true = np.nan_to_num(t["A_true"])
+    A_init = A_true + cv2.GaussianBlur(rs.standard_normal((h, w)), (0, 0), 3.0) * 0.05
+    rig = t["rigidity"] > 0.5
+    occ_b = rs.rand(h, w) < 0.02
+    occ_f = (rs.rand(h, w) < 0.02) & ~occ_b
+    vin = dict(A_init=A_init, A_bwd_reference=A_true * (t["mu"][0] / t["mu"][1]), A_fwd_reference=A_true, occlusions_bwd=occ_b,
+               occlusions_fwd=occ_f, occlusions_both=np.zeros((h, w), bool), rigidity=rig,
+               images=[np.asarray(I, np.float64) for I in t["images"]], H_ar=t["homographies"], B_ar=[float(b) for b in t["B"]],
+               q_ar=[np.asarray(q, np.float64) for q in t["epipoles"]], mu_ar=[float(m) for m in t["mu"]])
+    want, want_e, trace = ov.optimize_structure_single_scale(lambda_1storder=LAMBDA_1, lambda_2ndorder=LAMBDA_2,
+                                                             lambda_consistency=0.05, N_outer=2, return_trace=True, **vin)
+    ref = variational.Refiner([up(I, np.float64) for I in vin["images"]], flag(occ_b), flag(occ_f), flag(rig), vin["H_ar"],
+                              vin["B_ar"], vin["q_ar"], vin["mu_ar"], up(vin["A_bwd_reference"], np.float64),
+                              up(vin["A_fwd_reference"], np.float64), LAMBDA_1, LAMBDA_2, 0.05)
+    A = up(A_init, np.float64).clone()
+    energies = [ref.step(A) for _ in range(2)]
+    np.testing.assert_allclose(energies, want_e, rtol=1e-9)
+    assert np.abs(A.cpu().numpy() - want).max() <= 1e-8

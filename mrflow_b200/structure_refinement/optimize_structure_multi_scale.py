@@ -16,7 +16,7 @@ from . import optimize_structure_single_scale
 def _resize(a, s, interpolation=None, **kw):
     import cv2
     if s == 1.0 and not kw:
-        return np.array(a, copy=True)                      # cv::resize copies when the size does not change
+        return np.asarray(a)            # cv::resize only copies when the size does not change; the solver does not write its inputs
     if interpolation is None:
         return cv2.resize(a, dsize=None, fx=s, fy=s, **kw)
     return cv2.resize(a, dsize=None, fx=s, fy=s, interpolation=interpolation, **kw)

@@ -427,6 +427,9 @@ int mrf_vec_scale(const double* y, size_t n, double s, double* out, mrf_stream_t
 #define MRF_MINRES_ACOND  21
 #define MRF_MINRES_RNORM  22
 #define MRF_MINRES_YNORM  23
+#define MRF_MINRES_NS_A    29  /* block 0's own time in phase A / phases B+C / barrier waits, nanoseconds, */
+#define MRF_MINRES_NS_BC   30  /* accumulated over the launches of a solve (for profiles/, not for control) */
+#define MRF_MINRES_NS_SYNC 31
 size_t mrf_minres_scratch_bytes(int h, int w);
 int mrf_minres_init(const double* b, size_t n, double* r3, double* w2, double* x, double* state, void* scratch,
                     mrf_stream_t stream);

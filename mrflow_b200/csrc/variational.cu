@@ -5,11 +5,12 @@
 //                         (structure_refinement/construct_matrices.py:14-38), robust arguments
 //   * the linear operator :580-595 -- A = Z (D + l1 G'P1G + l2 G2'P2G2 + lc Pc) Z + 0.01 I applied
 //                         matrix-free as a 5x5-footprint stencil (one thread per pixel, fp64)
-//   * MINRES vector steps scipy.sparse.linalg.minres (the solver the reference calls, :86,:593): fused
-//                         axpy + deterministic dot-product kernels; the scalar recurrences stay on the host
+//   * MINRES              scipy.sparse.linalg.minres (the solver the reference calls, :86,:593) as one persistent
+//                         cooperative kernel: operator, Lanczos step, solution update, the scalar recurrences
+//                         and the stopping tests all on the device, two grid barriers per iteration
 //   * update              clip_dA :157-183, clip to +-1 :612, 7x7 median of A + dA :636
-// Unlike the cost volume this stage is iterative and latency-bound (hundreds of dependent stencil + dot
-// launches per solve); it is built for parity and residency, not yet tuned.
+// Unlike the cost volume this stage is iterative and latency-bound (two grid-wide reductions per MINRES
+// iteration, ~100 iterations per solve, 5 solves per frame); DESIGN.md section 4.5 has the measured breakdown.
 #include "common.cuh"
 #include <cooperative_groups.h>
 #include <math.h>

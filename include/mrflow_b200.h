@@ -422,7 +422,7 @@ int mrf_vec_scale(const double* y, size_t n, double s, double* out, mrf_stream_t
  * mrf_minres_scratch_bytes(h, w) bytes.  The operator is that of mrf_var_apply. */
 #define MRF_MINRES_STATE_WORDS 32
 #define MRF_MINRES_ITN    18
-#define MRF_MINRES_ISTOP  19   /* scipy's istop (1..6, -1); 100 = b was zero */
+#define MRF_MINRES_ISTOP  19   /* scipy's istop (1..6, -1); 100 = b was zero; 7 = non-finite system (stopped at once) */
 #define MRF_MINRES_ANORM  20
 #define MRF_MINRES_ACOND  21
 #define MRF_MINRES_RNORM  22

@@ -328,6 +328,9 @@ struct MinresScalars {
     const double itn = s[MS_ITN] + 1.0;
     const double oldb = s[MS_BETA];
     const double beta = sqrt(beta_sq);
+    // a non-finite system never satisfies a stopping test (scipy would grind through all 5n iterations on
+    // NaNs): stop at once with istop 7; the caller then marks the whole solution non-finite, as scipy's is
+    if (!(alfa - alfa == 0.0) || !(beta_sq - beta_sq == 0.0)) s[MS_ISTOP] = 7.0;
     s[MS_ALFA] = alfa; s[MS_OLDB] = oldb; s[MS_BETA] = beta;
     s[MS_TNORM2] = s[MS_TNORM2] + ((alfa * alfa + oldb * oldb) + beta * beta);
     if (itn == 1.0 && beta / s[MS_BETA1] <= 10.0 * kEps) s[MS_ISTOP] = -1.0;
@@ -416,6 +419,7 @@ k_minres_init_state(const double* __restrict__ partial, int nblocks, double* __r
     state[MS_BETA1] = beta1; state[MS_BETA] = beta1; state[MS_PHIBAR] = beta1; state[MS_RHS1] = beta1;
     state[MS_GMIN] = kDblMax; state[MS_CS] = -1.0;
     if (v == 0.0) state[MS_ISTOP] = 100.0;            // b = 0: x = 0 is the answer (scipy returns before iterating)
+    if (!(v - v == 0.0)) state[MS_ISTOP] = 7.0;       // non-finite right-hand side
   }
 }
 

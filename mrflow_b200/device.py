@@ -214,9 +214,6 @@ def select_kth(keys, k, n=None):
     return out
 
 
-_COUNTS = {}
-
-
 def median_dev(keys, n=None, out=None):
     """numpy.median of the first ``n`` keys as a 1-element fp64 device tensor (no host synchronisation): the
     fused radix select of the front (8 histogram passes that each resolve the previous byte, one successor
@@ -224,10 +221,7 @@ def median_dev(keys, n=None, out=None):
     _chk(keys, F64, "keys")
     L = _lib.lib()
     n = keys.numel() if n is None else int(n)
-    key = (n, keys.device)
-    cnt = _COUNTS.get(key)
-    if cnt is None:
-        cnt = _COUNTS[key] = torch.tensor([n], dtype=torch.int32, device=keys.device)
+    cnt = torch.full((1,), n, dtype=torch.int32, device=keys.device)      # the kernels read n on the device (no H2D copy)
     out = torch.empty(1, dtype=F64, device=keys.device) if out is None else out
     scratch = torch.empty(L.mrf_select_scratch_bytes(n), dtype=U8, device=keys.device)
     check(L.mrf_select_median_dev(_p(keys), _p(cnt), max(n, 1), _p(out), _p(scratch), _stream()), "mrf_select_median_dev")

@@ -116,6 +116,10 @@ def minres(op, b, rtol=1e-5, maxiter=None, ws=None, batch=MINRES_BATCH):
         if st[_lib.MINRES_ISTOP] != 0 or done >= maxiter:
             break
     istop = int(st[_lib.MINRES_ISTOP])
+    if istop == 7:
+        # NaN / inf in the system: scipy's iterates are all-NaN from the first dot product on (and the reference
+        # then zeroes the update, :600-606); same outcome here without running 5n iterations on NaNs
+        ws.x.fill_(float("nan"))
     return ws.x, dict(istop=0 if istop == 100 else istop, itn=int(st[_lib.MINRES_ITN]), rnorm=float(st[_lib.MINRES_RNORM]),
                       Anorm=float(st[_lib.MINRES_ANORM]), Acond=float(st[_lib.MINRES_ACOND]), enqueued=done)
 

@@ -158,6 +158,11 @@ def test_minres_matches_scipy():
     assert i0["itn"] == 0 and float(x0.abs().max()) == 0.0
     _, i6 = variational.minres(op, torch.from_numpy(b).cuda(), rtol=1e-14, maxiter=5)
     assert i6["itn"] == 5 and i6["istop"] == 6
+    # a non-finite right-hand side stops at once and yields an all-NaN solution, as scipy's does
+    bn = b.copy(); bn[7] = np.nan
+    xn, i7 = variational.minres(op, torch.from_numpy(bn).cuda())
+    assert i7["istop"] == 7 and i7["itn"] == 0 and bool(torch.isnan(xn).all())
+    assert np.isnan(spla.minres(M.tocsr(), bn, rtol=1e-5, maxiter=3)[0]).all()
 
 
 def test_optimize_structure_single_scale_vs_reference(case):

@@ -227,44 +227,49 @@ __device__ __forceinline__ SmoothCoef load_coef(const VarOp& o, int x, int y) {
   c.p2x_r = x + 1 < w ? o.p2x[i + 1] : 0.0; c.p2y_d = y + 1 < h ? o.p2y[i + w] : 0.0;
   return c;
 }
-template <class Acc>
+// INTERIOR: every neighbour within two pixels is inside the frame, so the border cases fold away at compile time
+template <bool INTERIOR, class Acc>
 __device__ __forceinline__ double smooth_apply_c(const VarOp& o, int x, int y, const SmoothCoef& c, Acc V) {
   const int h = o.h, w = o.w;
-  auto DX = [&](int yy, int xx) -> double { return (xx + 1 < w) ? V(yy, xx + 1) - V(yy, xx) : 0.0; };
-  auto DY = [&](int yy, int xx) -> double { return (yy + 1 < h) ? V(yy + 1, xx) - V(yy, xx) : 0.0; };
-  auto DXX = [&](int yy, int xx) -> double { return (V(yy, xx > 0 ? xx - 1 : xx) + V(yy, xx + 1 < w ? xx + 1 : xx)) - 2.0 * V(yy, xx); };
-  auto DYY = [&](int yy, int xx) -> double { return (V(yy > 0 ? yy - 1 : yy, xx) + V(yy + 1 < h ? yy + 1 : yy, xx)) - 2.0 * V(yy, xx); };
+  auto DX = [&](int yy, int xx) -> double { return (INTERIOR || xx + 1 < w) ? V(yy, xx + 1) - V(yy, xx) : 0.0; };
+  auto DY = [&](int yy, int xx) -> double { return (INTERIOR || yy + 1 < h) ? V(yy + 1, xx) - V(yy, xx) : 0.0; };
+  auto DXX = [&](int yy, int xx) -> double {
+    return (V(yy, (INTERIOR || xx > 0) ? xx - 1 : xx) + V(yy, (INTERIOR || xx + 1 < w) ? xx + 1 : xx)) - 2.0 * V(yy, xx);
+  };
+  auto DYY = [&](int yy, int xx) -> double {
+    return (V((INTERIOR || yy > 0) ? yy - 1 : yy, xx) + V((INTERIOR || yy + 1 < h) ? yy + 1 : yy, xx)) - 2.0 * V(yy, xx);
+  };
   // first order: (G' u)(p) = -ux(p) + ux(p - ex) - uy(p) + uy(p - ey),  u = P1 G v
   double s1 = 0.0;
   s1 -= c.p1x_c * DX(y, x);
-  if (x > 0) s1 += c.p1x_l * DX(y, x - 1);
+  if (INTERIOR || x > 0) s1 += c.p1x_l * DX(y, x - 1);
   s1 -= c.p1y_c * DY(y, x);
-  if (y > 0) s1 += c.p1y_u * DY(y - 1, x);
+  if (INTERIOR || y > 0) s1 += c.p1y_u * DY(y - 1, x);
   // second order: (Dxx' u)(p) = u(p-1) + u(p+1) - 2u(p), the replicated ends folding back onto p
   double s2 = 0.0;
   {
     const double uc = c.p2x_c * DXX(y, x);
     double t = -2.0 * uc;
-    if (x == 0) t += uc;
-    if (x == w - 1) t += uc;
-    if (x > 0) t += c.p2x_l * DXX(y, x - 1);
-    if (x + 1 < w) t += c.p2x_r * DXX(y, x + 1);
+    if (!INTERIOR && x == 0) t += uc;
+    if (!INTERIOR && x == w - 1) t += uc;
+    if (INTERIOR || x > 0) t += c.p2x_l * DXX(y, x - 1);
+    if (INTERIOR || x + 1 < w) t += c.p2x_r * DXX(y, x + 1);
     s2 += t;
   }
   {
     const double uc = c.p2y_c * DYY(y, x);
     double t = -2.0 * uc;
-    if (y == 0) t += uc;
-    if (y == h - 1) t += uc;
-    if (y > 0) t += c.p2y_u * DYY(y - 1, x);
-    if (y + 1 < h) t += c.p2y_d * DYY(y + 1, x);
+    if (!INTERIOR && y == 0) t += uc;
+    if (!INTERIOR && y == h - 1) t += uc;
+    if (INTERIOR || y > 0) t += c.p2y_u * DYY(y - 1, x);
+    if (INTERIOR || y + 1 < h) t += c.p2y_d * DYY(y + 1, x);
     s2 += t;
   }
   return o.l1 * s1 + o.l2 * s2;
 }
 template <class Acc>
 __device__ __forceinline__ double smooth_apply_f(const VarOp& o, int x, int y, Acc V) {
-  return smooth_apply_c(o, x, y, load_coef(o, x, y), V);
+  return smooth_apply_c<false>(o, x, y, load_coef(o, x, y), V);
 }
 __device__ __forceinline__ double smooth_apply(const VarOp& o, const double* __restrict__ xv, int x, int y) {
   const int w = o.w;
@@ -468,6 +473,7 @@ k_minres_persistent(VarOp o, double* r3, double* w2buf, double* v2buf, double* x
       constexpr int kTW = kTileW + 2 * kHalo, kTE = (kTileH + 2 * kHalo) * kTW;       // 36 x 12 staged values
       for (int tl = bid; tl < ntiles; tl += G) {
         const int x0 = (tl % tiles_x) * kTileW, y0 = (tl / tiles_x) * kTileH;
+        const bool interior = x0 >= kHalo && y0 >= kHalo && x0 + kTileW + kHalo <= w && y0 + kTileH + kHalo <= h;
         // issue every load of this tile at once: the (up to two) staged values of this thread with their masks,
         // and the thread's own coefficients -- one round trip to L2 instead of four
         double sv[2]; unsigned char sm[2]; bool in[2];
@@ -476,7 +482,7 @@ k_minres_persistent(VarOp o, double* r3, double* w2buf, double* v2buf, double* x
           const int e = threadIdx.x + u * 256;
           const int ry = e / kTW, rx = e % kTW;
           const int gy = y0 + ry - kHalo, gx = x0 + rx - kHalo;
-          in[u] = e < kTE && gx >= 0 && gx < w && gy >= 0 && gy < h;
+          in[u] = e < kTE && (interior || (gx >= 0 && gx < w && gy >= 0 && gy < h));
           const long long j = in[u] ? (long long)gy * w + gx : 0;
           sv[u] = in[u] ? r2[j] : 0.0;
           sm[u] = (in[u] && o.rigid) ? o.rigid[j] : (unsigned char)1;
@@ -502,7 +508,8 @@ k_minres_persistent(VarOp o, double* r3, double* w2buf, double* v2buf, double* x
           const double vi = sc * r2[i];
           double r = 0.0;
           if (!o.rigid || o.rigid[i]) {
-            r = smooth_apply_c(o, px, py, cf, [&](int yy, int xx) -> double { return tile[yy - y0 + kHalo][xx - x0 + kHalo]; });
+            auto Vt = [&](int yy, int xx) -> double { return tile[yy - y0 + kHalo][xx - x0 + kHalo]; };
+            r = interior ? smooth_apply_c<true>(o, px, py, cf, Vt) : smooth_apply_c<false>(o, px, py, cf, Vt);
             if (o.D) r += Di * vi;
             if (o.pc) r += o.lc * (pci * vi);
           }

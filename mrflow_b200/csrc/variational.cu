@@ -400,6 +400,19 @@ __device__ __forceinline__ double sum_partials_all(const double* partial, unsign
   return r;
 }
 
+// two reductions at once (their loads overlap): sums of pa[0..G) and pb[0..G), same fixed order as above
+__device__ __forceinline__ void sum_partials_all2(const double* pa, const double* pb, unsigned G, double* sh, double* sh_out2,
+                                                  double& ra, double& rb) {
+  double a = 0.0, b = 0.0;
+  for (unsigned k = threadIdx.x; k < G; k += blockDim.x) { a += __ldcg(pa + k); b += __ldcg(pb + k); }
+  a = block_sum256(a, sh);
+  b = block_sum256(b, sh);
+  if (threadIdx.x == 0) { sh_out2[0] = a; sh_out2[1] = b; }
+  __syncthreads();
+  ra = sh_out2[0]; rb = sh_out2[1];
+  __syncthreads();
+}
+
 __global__ void __launch_bounds__(256)
 k_minres_init(const double* __restrict__ b, long long n, double* __restrict__ r1, double* __restrict__ r2, double* __restrict__ w,
               double* __restrict__ w2, double* __restrict__ x, double* __restrict__ partial) {
@@ -441,6 +454,7 @@ k_minres_persistent(VarOp o, double* r3, double* w2buf, double* v2buf, double* x
   __shared__ double tile[kTileH + 2 * kHalo][kTileW + 2 * kHalo + 1];
   __shared__ double sh[8];
   __shared__ double sh_out;
+  __shared__ double sh_out2[2];
   const unsigned G = gridDim.x, bid = blockIdx.x;
   const bool prof = (bid == 0 && threadIdx.x == 0);       // block 0 accounts its own time per phase (ns) in the state
   unsigned long long nsA = 0, nsBC = 0, nsSync = 0;
@@ -526,14 +540,14 @@ k_minres_persistent(VarOp o, double* r3, double* w2buf, double* v2buf, double* x
     const unsigned long long tA1 = prof ? gtime() : 0ull;
     grid.sync();                                                        // barrier 1
     const unsigned long long tB0 = prof ? gtime() : 0ull;
+    double alfa, ysq;
+    sum_partials_all2(pa, pcn, G, sh, sh_out2, alfa, ysq);              // (|x|^2 partials are only meaningful when pending)
     if (pending) {
-      const double ysq = sum_partials_all(pcn, G, sh, &sh_out);
       if (threadIdx.x == 0) m.tests(ysq, rtol, maxiter);
       __syncthreads();
       pending = false;
       if (m.s[MS_ISTOP] != 0.0) break;                                  // the previous iteration converged; x is final
     }
-    const double alfa = sum_partials_all(pa, G, sh, &sh_out);
     // ---- phase B
     {
       const double c2 = alfa / m.s[MS_BETA];

@@ -95,8 +95,8 @@ def minres(op, b, rtol=1e-5, maxiter=None, ws=None, batch=MINRES_BATCH):
     """scipy.sparse.linalg.minres(A, b, rtol=...) with x0 = 0 and no preconditioner -- the call behind
     ``solve(A, b, 'minres', tol)`` (:86).  Same recurrences, same stopping tests, same iteration cap (5 n),
     all evaluated on the device by one persistent cooperative kernel (``mrf_minres_iterate``) that runs until
-    the solve stops or ``batch`` iterations have passed; the host then reads the 256-byte state block.  Returns (x, info dict); x is ``ws.x`` (valid until the
-    workspace's next solve)."""
+    the solve stops or ``batch`` iterations have passed; the host then reads the 256-byte state block.
+    Returns (x, info dict); x is ``ws.x`` (valid until the workspace's next solve)."""
     L = _lib.lib()
     n = b.numel()
     ws = ws or MinresWorkspace(op.h, op.w, b.device)
@@ -106,7 +106,8 @@ def minres(op, b, rtol=1e-5, maxiter=None, ws=None, batch=MINRES_BATCH):
           "mrf_minres_init")
     rigid, D, p1x, p1y, p2x, p2y, pc = op.args
     done = 0
-    while True:
+    st = ws.state.get() if maxiter <= 0 else None
+    while maxiter > 0:
         k = int(min(batch, maxiter - done))
         check(L.mrf_minres_iterate(_p(rigid), _p(D), _p(p1x), _p(p1y), _p(p2x), _p(p2y), _p(pc), *op.l, op.h, op.w, _p(ws.r3),
                                    _p(ws.w2), _p(ws.v2), _p(ws.x), _p(ws.state.d), _p(ws.scratch), done, k, float(rtol),

@@ -192,7 +192,11 @@ class BandStats:
         ymin, ymax = int(q[1]) - 10, int(q[1]) + 10
         xmin, xmax = int(q[0]) - 10, int(q[0]) + 10
         inside = not (xmin < 0 or xmax >= w or ymin < 0 or ymax >= h)
-        mine = inside and ymin >= band.y0 and ymax < band.y0 + band.rows
+        if not inside:
+            # compute_structure.py:476-477: the window leaves the image, the epipole stays -- every rank knows that
+            # from (q, w, h) alone, so no collective and no host synchronisation
+            return np.asarray(q, dtype=np.float64)
+        mine = ymin >= band.y0 and ymax < band.y0 + band.rows
         res = np.zeros(3)
         if mine:
             qn = fn()
@@ -332,11 +336,12 @@ def banded_front(band, homographies, q_ar, rigid_mask, zero_mask, buf, group=Non
           "mrf_select_median_state")                       # B_b, compute_structure.py:221
     check(L.mrf_front_structures_band(C.byref(p), P(buf.par[0]), P(buf.par[1]), P(zero_mask), P(buf.S[0]), P(buf.S[1]),
                                       P(buf.state), P(buf.scratch), st), "mrf_front_structures_band")
+    # one MIN all-reduce for (min, -max, -nanflag) of both frames instead of three collectives (negation is exact)
     mm = buf.state[_lib.STATE_MINMAX:_lib.STATE_MINMAX + 4]
-    lo, hi = mm[0::2].contiguous(), mm[1::2].contiguous()
     flags = buf.state[_lib.STATE_NANFLAG:_lib.STATE_NANFLAG + 2]
-    dist.all_reduce(lo, op=MIN, group=group); dist.all_reduce(hi, op=MAX, group=group); dist.all_reduce(flags, op=MAX, group=group)
-    mm[0::2] = lo; mm[1::2] = hi
+    packed = torch.cat((mm[0::2], -mm[1::2], -flags))
+    dist.all_reduce(packed, op=MIN, group=group)
+    mm[0::2] = packed[0:2]; mm[1::2] = -packed[2:4]; flags.copy_(-packed[4:6])
     check(L.mrf_label_range_dev(P(buf.state), int(n_labels), st), "mrf_label_range_dev")
     return buf
 
@@ -352,12 +357,37 @@ def banded_pass_resident(band, homographies, epipoles, rigid_mask, stats, buf=No
         nonrigid = (rigid_mask == 0).to(torch.uint8)
         masks = (nonrigid, rigid_mask if range_mask == "as_written" else nonrigid)
     nonrigid, zero_mask = masks
+    cur = torch.cuda.current_stream()
+    ch_done = None
+    if channels is None:
+        # the channel stacks do not depend on the pre-pass: build them on a side stream while the pre-pass and
+        # its collectives run
+        side = _side_stream(band.device)
+        side.wait_stream(cur)
+        with torch.cuda.stream(side):
+            channels = pp.channels(band)
+            ch_done = torch.cuda.Event()
+            ch_done.record(side)
+        for tns in (channels[0], *channels[1]):
+            tns.record_stream(cur)
     banded_front(band, homographies, q_new, rigid_mask, zero_mask, buf, group=stats.group)
-    ref64, tex = channels if channels is not None else pp.channels(band)
+    if ch_done is not None:
+        cur.wait_event(ch_done)
+    ref64, tex = channels
     res = pp.cost_volumes(band, ref64, tex, None, homographies, q_new, None, None, nonrigid, rho=rho, rho_param=sigma,
                           interp=interp, variant=variant, want_cost=want_cost, halo_miss=halo_miss, events=events,
                           out_ptr=out_ptr, plane_stride=plane_stride, state=buf.state)
     return dict(cost=[res[0][0], res[1][0]], mins=[res[0][1], res[1][1]], argmins=[res[0][2], res[1][2]], q=q_new, buffers=buf)
+
+
+_SIDE = {}
+
+
+def _side_stream(dev):
+    key = str(dev)
+    if key not in _SIDE:
+        _SIDE[key] = torch.cuda.Stream(device=dev)
+    return _SIDE[key]
 
 
 def _band_epipole(band, homographies, epipoles, rigid_mask, f):
@@ -438,7 +468,7 @@ def bench_bands(args, hw, steps, warm, metric, unit, workload, ClockSampler):
         return banded_pass_resident(band, t["homographies"], t["epipoles"], rigid_mask, stats, buf=bbuf, interp=args.interp,
                                     range_mask="rigid_only", variant=args.variant, out_ptr=outs,
                                     plane_stride=(h * w if gather else 0), halo_miss=miss, events=events,
-                                    masks=(nonrigid, nonrigid), channels=pp.channels(band))
+                                    masks=(nonrigid, nonrigid))
 
     def barrier():
         torch.cuda.synchronize(); dist.barrier(); torch.cuda.synchronize()

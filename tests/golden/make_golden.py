@@ -222,7 +222,7 @@ def main():
                 # (what stage 5 runs without --override_optimization; one scale, parameters.py:43-45).  Two
                 # py2-isms are shimmed: dict.has_key on vars(params) and the tol= keyword of scipy's minres.
                 sys.path.insert(0, os.path.join(ROOT, "tests"))
-                from variational_case import CASES, LAMBDA_1, LAMBDA_2, variational_inputs
+                from variational_case import CASES, LAMBDA_1, LAMBDA_2, variational_inputs, with_nonrigid
                 from scipy.sparse import linalg as spla
                 from oracle import variational as ov
                 import construct_matrices as cm
@@ -237,8 +237,9 @@ def main():
                 pv = argparse.Namespace(variational_dataterm_grayscale=1, variational_min_weight=0.0, debug_save_frames=0,
                                         tempdir=".")
                 vin = variational_inputs(t, out)
-                for name, lc, n_outer in CASES:
-                    kwv = {k: (v.copy() if isinstance(v, np.ndarray) else [np.array(e).copy() for e in v]) for k, v in vin.items()}
+                for name, lc, n_outer, masked in CASES:
+                    src = with_nonrigid(vin) if masked else vin
+                    kwv = {k: (v.copy() if isinstance(v, np.ndarray) else [np.array(e).copy() for e in v]) for k, v in src.items()}
                     A_ref, en = oss.optimizeStructureSingleScale(
                         kwv["A_init"], kwv["A_bwd_reference"], kwv["A_fwd_reference"], kwv["occlusions_bwd"],
                         kwv["occlusions_fwd"], kwv["occlusions_both"], kwv["rigidity"], kwv["images"], kwv["H_ar"],

@@ -14,7 +14,7 @@ import numpy as np
 import pytest
 
 from conftest import GOLDEN, golden_triplet
-from variational_case import CASES, LAMBDA_1, LAMBDA_2, variational_inputs
+from variational_case import CASES, LAMBDA_1, LAMBDA_2, variational_inputs, with_nonrigid
 
 pytestmark = pytest.mark.gpu
 
@@ -74,14 +74,16 @@ def test_median7x7_bit_exact(shape):
     assert np.array_equal(dst.cpu().numpy(), ndimage.median_filter(a, size=7))
 
 
-@pytest.mark.parametrize("lc", [0.0, 0.1])
-def test_first_iteration_system_and_solve(case, lc):
+@pytest.mark.parametrize("lc,masked", [(0.0, False), (0.1, False), (0.05, True)])
+def test_first_iteration_system_and_solve(case, lc, masked):
     """One outer iteration: weights, operator, right-hand side and the MINRES solution against the
     oracle's sparse system (trace of oracle.variational)."""
     import torch
     from mrflow_b200 import variational
     from oracle import variational as ov
     _, _, vin = case
+    if masked:
+        vin = with_nonrigid(vin)
     _, _, trace = ov.optimize_structure_single_scale(lambda_1storder=LAMBDA_1, lambda_2ndorder=LAMBDA_2, lambda_consistency=lc,
                                                      N_outer=1, return_trace=True, **vin)
     tr = trace[0]
@@ -175,9 +177,10 @@ def test_optimize_structure_single_scale_vs_reference(case):
     within 5e-4 absolutely; energies to 1e-6 relative."""
     from mrflow_b200.structure_refinement.optimize_structure_single_scale import optimizeStructureSingleScale
     from oracle import variational as ov
-    _, g, vin = case
+    _, g, vin0 = case
     params = argparse.Namespace(variational_dataterm_grayscale=1, variational_min_weight=0.0, debug_save_frames=0, tempdir=".")
-    for name, lc, n_outer in CASES:
+    for name, lc, n_outer, masked in CASES:
+        vin = with_nonrigid(vin0) if masked else vin0
         A, energies = optimizeStructureSingleScale(vin["A_init"], vin["A_bwd_reference"], vin["A_fwd_reference"],
                                                    vin["occlusions_bwd"], vin["occlusions_fwd"], vin["occlusions_both"],
                                                    vin["rigidity"], vin["images"], vin["H_ar"], vin["B_ar"], vin["q_ar"],

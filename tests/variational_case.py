@@ -4,7 +4,20 @@ structures as references, exclusive occlusion maps, the refined rigidity."""
 import numpy as np
 
 LAMBDA_1, LAMBDA_2 = 0.5, 5.0        # parameters.py:38-39
-CASES = (("lc0", 0.0, 3), ("lc01", 0.1, 2))     # (name, lambda_consistency, N_outer)
+# (name, lambda_consistency, N_outer, with_nonrigid): the fixtures' own rigidity maps are all-rigid, so one case
+# carves a non-rigid block and speckles into the map (Z masking, eroded edge weights, zeroed data term)
+CASES = (("lc0", 0.0, 3, False), ("lc01", 0.1, 2, False), ("mask", 0.05, 2, True))
+
+
+def with_nonrigid(vin):
+    out = dict(vin)
+    rig = np.array(vin["rigidity"], dtype=bool, copy=True)
+    h, w = rig.shape
+    rig[h // 4:h // 2 + 5, w // 3:2 * w // 3] = False
+    rs = np.random.RandomState(77)
+    rig[rs.rand(h, w) < 0.03] = False
+    out["rigidity"] = rig
+    return out
 
 
 def variational_inputs(t, g):

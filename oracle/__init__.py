@@ -29,12 +29,13 @@ Parity status
   (diag(A_data), b_data) of the reference function with its auto-sigma Lorentzian; a9
   (``compute_derivs_through_H``), ``computeOcclusionsFromConsistency`` and ``get_image_weights`` likewise.
 * a4 end to end: the reference's ``compute_structure`` run with its own solver (oracle/_ref) is stored
-  for the two fixtures whose epipole lies outside the frame; the oracle reproduces all seven outputs
+  for the three fixtures whose epipole lies outside the frame (one with moving objects, 14 % non-rigid after
+  the MRF); the oracle reproduces all seven outputs
   bit for bit.  (With the epipole inside, the reference needs chumpy for ``correct_epipole``: unpinned.)
 * stage 5 (``oracle/variational.py``): the variational refinement ``optimizeStructureSingleScale``
   (optimize_structure_single_scale.py:310-652) and the reference's whole default stage 5
   (``optimize`` -> ``optimizeStructureMultiScale`` -> ...): PINNED -- bit-identical structure and energies
-  on the two outside-epipole fixtures (same scipy / OpenCV calls; the explicit stencil matrices are asserted
+  on the three outside-epipole fixtures, plus a case with a carved non-rigid block (same scipy / OpenCV calls; the explicit stencil matrices are asserted
   equal to construct_matrices.py's when the goldens are generated).
 * a12 (the per-label cost volume): the reference's arithmetic for this step lived in a compiled
   extension that is NOT shipped (``pipeline/build_cost_volume.py:26-27``).  The oracle composes

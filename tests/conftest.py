@@ -29,7 +29,7 @@ def pytest_collection_modifyitems(config, items):
             it.add_marker(skip)
 
 
-@pytest.fixture(scope="session", params=["outside", "inside", "example"])
+@pytest.fixture(scope="session", params=["outside", "inside", "example", "moving"])
 def golden(request):
     return request.param, dict(np.load(os.path.join(GOLDEN, "ref_%s.npz" % request.param)))
 
@@ -38,7 +38,8 @@ def golden_triplet(tag):
     from mrflow_b200 import synth
     kw = dict(outside=dict(shape=(72, 96), seed=7, epipole="outside", flow_noise=0.02),
               inside=dict(shape=(72, 96), seed=8, epipole="inside", moving_objects=True),
-              example=dict(shape=(72, 96), seed=9, epipole="outside", flow_noise=0.05))[tag]
+              example=dict(shape=(72, 96), seed=9, epipole="outside", flow_noise=0.05),
+              moving=dict(shape=(72, 96), seed=11, epipole="outside", moving_objects=True, flow_noise=0.02))[tag]
     t = synth.make_triplet(n_waves=8, **kw)
     if tag == "example":
         # crops of the reference's example/frame1-3.png, stored in the fixture by make_golden.py

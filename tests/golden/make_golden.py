@@ -64,7 +64,8 @@ def main():
 
     for tag, kw in (("outside", dict(shape=(72, 96), seed=7, epipole="outside", flow_noise=0.02)),
                     ("inside", dict(shape=(72, 96), seed=8, epipole="inside", moving_objects=True)),
-                    ("example", dict(shape=(72, 96), seed=9, epipole="outside", flow_noise=0.05))):
+                    ("example", dict(shape=(72, 96), seed=9, epipole="outside", flow_noise=0.05)),
+                    ("moving", dict(shape=(72, 96), seed=11, epipole="outside", moving_objects=True, flow_noise=0.02))):
         t = synth.make_triplet(n_waves=8, **kw)
         example_images = None
         if tag == "example":

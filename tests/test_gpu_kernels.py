@@ -32,7 +32,7 @@ def eq(a, b):
     return np.array_equal(np.asarray(a), np.asarray(b), equal_nan=True)
 
 
-@pytest.fixture(scope="module", params=["outside", "inside", "example"])
+@pytest.fixture(scope="module", params=["outside", "inside", "example", "moving"])
 def trip(request):
     return golden_triplet(request.param)
 

@@ -27,7 +27,7 @@ def _stub_mrf(I, unaries, lambd):
     return (unaries[:, :, 1] > unaries[:, :, 0]).astype(np.int32)
 
 
-@pytest.fixture(scope="module", params=["outside", "inside", "example"])
+@pytest.fixture(scope="module", params=["outside", "inside", "example", "moving"])
 def trip(request):
     return golden_triplet(request.param)
 

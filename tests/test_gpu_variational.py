@@ -19,7 +19,7 @@ from variational_case import CASES, LAMBDA_1, LAMBDA_2, variational_inputs, with
 pytestmark = pytest.mark.gpu
 
 
-@pytest.fixture(scope="module", params=["outside", "example"])
+@pytest.fixture(scope="module", params=["outside", "example", "moving"])
 def case(request):
     g = dict(np.load(os.path.join(GOLDEN, "ref_%s.npz" % request.param)))
     return request.param, g, variational_inputs(golden_triplet(request.param), g)

@@ -454,6 +454,21 @@ int mrf_peer_open(const unsigned char* handle64, void** ptr_out);
 int mrf_peer_close(void* ptr);
 int mrf_peer_free(void* ptr);
 
+/* ---- small all-reduces over peer memory for the row-band pre-pass: the eight
+ * 2 KB histogram all-reduces of each exact median, and the other integer / min reductions of the pre-pass,
+ * as ONE kernel per rank that stores into every rank's mailbox over NVLink, publishes a flag with
+ * system-scope release, waits for all sources in its own mailbox (bounded) and reduces in rank order.
+ * A mailbox is mrf_mailbox_bytes(world) bytes from mrf_peer_alloc, zeroed once, opened by every peer
+ * (mrf_peer_open); mailboxes_host[world] are this process's pointers to all of them (its own at [rank]).
+ * call_index must count the collectives 0, 1, 2, ... identically on every rank.  inout: nwords <= 256
+ * 64-bit words on the device.  Only order-independent reductions, so results equal NCCL's bit for bit. */
+#define MRF_PEER_SUM_U64 0
+#define MRF_PEER_MIN_U64 1
+#define MRF_PEER_MIN_F64 2
+size_t mrf_mailbox_bytes(int world);
+int mrf_mailbox_allreduce(void* local_mailbox, void* const* mailboxes_host, int world, int rank,
+                          long long call_index, int op, void* inout_words, int nwords, mrf_stream_t stream);
+
 /* number of kernel launches the library has issued in this process (for bench.py's
  * gpu_launches); reset with mrf_reset_launch_count(). */
 long long mrf_launch_count(void);

@@ -12,7 +12,7 @@ from concurrent.futures import ThreadPoolExecutor
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libmrflow_b200.so")
-SOURCES = ["geometry.cu", "sampling.cu", "costvol.cu", "select.cu", "robust.cu", "adjacent.cu", "dataterm.cu", "variational.cu"]
+SOURCES = ["geometry.cu", "sampling.cu", "costvol.cu", "select.cu", "robust.cu", "adjacent.cu", "dataterm.cu", "variational.cu", "peercoll.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-fmad=false",
               "-std=c++17", "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"]
 

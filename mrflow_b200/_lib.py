@@ -74,6 +74,8 @@ SIGNATURES = {
     "mrf_peer_open": (_I, [C.POINTER(C.c_ubyte), C.POINTER(C.c_void_p)]),
     "mrf_peer_close": (_I, [_P]),
     "mrf_peer_free": (_I, [_P]),
+    "mrf_mailbox_bytes": (_Z, [_I]),
+    "mrf_mailbox_allreduce": (_I, [_P, C.POINTER(C.c_void_p), _I, _I, C.c_longlong, _I, _P, _I, _P]),
     "mrf_abs_deviation_f64": (_I, [_P, _Z, _D, _P, _P]),
     "mrf_minmax_scratch_bytes": (_Z, []),
     "mrf_masked_minmax_f64": (_I, [_P, _P, _I, _I, _I, _IP, _P, _P, _P]),

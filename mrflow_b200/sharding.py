@@ -261,6 +261,72 @@ class PeerVolume:
 
 
 # ------------------------------------------------------------------------------------------ resident bands
+class PeerMailbox:
+    """Every rank's small IPC-shared buffer for ``mrf_mailbox_allreduce``: the integer / min all-reduces of the
+    row-band pre-pass as one kernel per rank over NVLink peer memory instead of NCCL launches (bit-identical
+    results: only order-independent reductions)."""
+
+    def __init__(self, group=None):
+        lib = _lib.lib()
+        self.group = group
+        self.world = dist.get_world_size(group)
+        self.rank = dist.get_rank(group)
+        self.nbytes = lib.mrf_mailbox_bytes(self.world)
+        handle = (C.c_ubyte * 64)()
+        ptr = C.c_void_p()
+        check(lib.mrf_peer_alloc(self.nbytes, C.byref(ptr), handle), "mrf_peer_alloc")
+        self.local = ptr.value
+
+        class _Arr:
+            pass
+        a = _Arr()
+        a.__cuda_array_interface__ = {"shape": (self.nbytes,), "typestr": "|u1", "data": (self.local, False), "version": 2}
+        torch.as_tensor(a, device="cuda").zero_()
+        torch.cuda.synchronize()
+        handles = [None] * self.world
+        dist.all_gather_object(handles, bytes(handle), group=group)
+        self.ptrs = (C.c_void_p * self.world)()
+        for r in range(self.world):
+            if r == self.rank:
+                self.ptrs[r] = self.local
+            else:
+                p = C.c_void_p()
+                check(lib.mrf_peer_open((C.c_ubyte * 64).from_buffer_copy(handles[r]), C.byref(p)), "mrf_peer_open")
+                self.ptrs[r] = p.value
+        self.calls = 0
+        dist.barrier(group=group)                # every mailbox is zeroed and mapped before the first store
+
+    def allreduce(self, words, op):
+        """In-place all-reduce of a contiguous device tensor of <= 256 8-byte elements (int64 / float64)."""
+        assert words.is_cuda and words.is_contiguous() and words.element_size() == 8 and words.numel() <= 256
+        code = {"sum_u64": 0, "min_u64": 1, "min_f64": 2}[op]
+        check(_lib.lib().mrf_mailbox_allreduce(C.c_void_p(self.local), self.ptrs, self.world, self.rank, self.calls, code,
+                                               C.c_void_p(words.data_ptr()), words.numel(),
+                                               C.c_void_p(torch.cuda.current_stream().cuda_stream)), "mrf_mailbox_allreduce")
+        self.calls += 1
+
+    def status(self):
+        """0, or the 1-based index of the first collective that gave up waiting for a peer."""
+        out = torch.empty(1, dtype=torch.int64, device="cuda")
+
+        class _Arr:
+            pass
+        a = _Arr()
+        a.__cuda_array_interface__ = {"shape": (self.nbytes // 8,), "typestr": "<i8", "data": (self.local, False), "version": 2}
+        return int(torch.as_tensor(a, device="cuda")[self.nbytes // 8 - 8].cpu())
+
+    def close(self):
+        lib = _lib.lib()
+        torch.cuda.synchronize()
+        dist.barrier(group=self.group)
+        for r in range(self.world):
+            if r != self.rank:
+                check(lib.mrf_peer_close(C.c_void_p(self.ptrs[r])), "mrf_peer_close")
+        dist.barrier(group=self.group)
+        check(lib.mrf_peer_free(C.c_void_p(self.local)), "mrf_peer_free")
+        self.local = None
+
+
 class BandBuffers:
     """Reusable HBM buffers of the banded device-resident pre-pass."""
 
@@ -302,7 +368,7 @@ def _front_params(band, homographies, q_ar, n_labels, B_fwd=1.0):
     return p
 
 
-def banded_front(band, homographies, q_ar, rigid_mask, zero_mask, buf, group=None, n_labels=pp.N_LABELS):
+def banded_front(band, homographies, q_ar, rigid_mask, zero_mask, buf, group=None, n_labels=pp.N_LABELS, mailbox=None):
     """The pre-pass of build_cost_volume for one row band with every whole-frame scalar kept on the device:
     kernels on this band, tiny NCCL all-reduces (2 doubles, 1 int, 8 x 2 KB histograms, 3 words, 6 doubles)
     enqueued on the same stream in between -- no host synchronisation.  Leaves mu, B, labels in
@@ -325,13 +391,20 @@ def banded_front(band, homographies, q_ar, rigid_mask, zero_mask, buf, group=Non
     check(L.mrf_select_begin_dev(P(buf.n_total), P(buf.sel), st), "mrf_select_begin_dev")
     for _ in range(8):
         check(L.mrf_select_hist_dev(P(buf.cand), P(buf.count), cap, P(buf.sel), st), "mrf_select_hist_dev")
-        dist.all_reduce(buf.sel_hist, op=SUM, group=group)
+        if mailbox is not None:
+            mailbox.allreduce(buf.sel_hist, "sum_u64")
+        else:
+            dist.all_reduce(buf.sel_hist, op=SUM, group=group)
         check(L.mrf_select_pick(P(buf.sel), st), "mrf_select_pick")
     check(L.mrf_select_successor_dev(P(buf.cand), P(buf.count), cap, P(buf.sel), st), "mrf_select_successor_dev")
-    dist.all_reduce(buf.sel_sum, op=SUM, group=group)
-    buf.sel_min.bitwise_xor_(buf.sign)                     # unsigned order -> signed order for MIN
-    dist.all_reduce(buf.sel_min, op=MIN, group=group)
-    buf.sel_min.bitwise_xor_(buf.sign)
+    if mailbox is not None:
+        mailbox.allreduce(buf.sel_sum, "sum_u64")
+        mailbox.allreduce(buf.sel_min, "min_u64")
+    else:
+        dist.all_reduce(buf.sel_sum, op=SUM, group=group)
+        buf.sel_min.bitwise_xor_(buf.sign)                 # unsigned order -> signed order for MIN
+        dist.all_reduce(buf.sel_min, op=MIN, group=group)
+        buf.sel_min.bitwise_xor_(buf.sign)
     check(L.mrf_select_median_state(P(buf.sel), C.c_void_p(buf.state.data_ptr() + 8 * _lib.STATE_B), st),
           "mrf_select_median_state")                       # B_b, compute_structure.py:221
     check(L.mrf_front_structures_band(C.byref(p), P(buf.par[0]), P(buf.par[1]), P(zero_mask), P(buf.S[0]), P(buf.S[1]),
@@ -340,7 +413,10 @@ def banded_front(band, homographies, q_ar, rigid_mask, zero_mask, buf, group=Non
     mm = buf.state[_lib.STATE_MINMAX:_lib.STATE_MINMAX + 4]
     flags = buf.state[_lib.STATE_NANFLAG:_lib.STATE_NANFLAG + 2]
     packed = torch.cat((mm[0::2], -mm[1::2], -flags))
-    dist.all_reduce(packed, op=MIN, group=group)
+    if mailbox is not None:
+        mailbox.allreduce(packed, "min_f64")
+    else:
+        dist.all_reduce(packed, op=MIN, group=group)
     mm[0::2] = packed[0:2]; mm[1::2] = -packed[2:4]; flags.copy_(-packed[4:6])
     check(L.mrf_label_range_dev(P(buf.state), int(n_labels), st), "mrf_label_range_dev")
     return buf
@@ -348,7 +424,7 @@ def banded_front(band, homographies, q_ar, rigid_mask, zero_mask, buf, group=Non
 
 def banded_pass_resident(band, homographies, epipoles, rigid_mask, stats, buf=None, rho="lorentzian", sigma=1.0,
                          interp="cubic", range_mask="rigid_only", variant="staged", out_ptr=(None, None), plane_stride=0,
-                         want_cost=True, halo_miss=None, events=None, masks=None, channels=None):
+                         want_cost=True, halo_miss=None, events=None, masks=None, channels=None, mailbox=None):
     """Row-band cost volumes with the device-resident pre-pass.  Returns dict(cost, mins, argmins, q, buffers)."""
     q_new = [stats.epipole(lambda f=f: _band_epipole(band, homographies, epipoles, rigid_mask, f), np.asarray(epipoles[f], np.float64), band)
              for f in range(2)]
@@ -370,7 +446,7 @@ def banded_pass_resident(band, homographies, epipoles, rigid_mask, stats, buf=No
             ch_done.record(side)
         for tns in (channels[0], *channels[1]):
             tns.record_stream(cur)
-    banded_front(band, homographies, q_new, rigid_mask, zero_mask, buf, group=stats.group)
+    banded_front(band, homographies, q_new, rigid_mask, zero_mask, buf, group=stats.group, mailbox=mailbox)
     if ch_done is not None:
         cur.wait_event(ch_done)
     ref64, tex = channels
@@ -400,11 +476,13 @@ def _band_epipole(band, homographies, epipoles, rigid_mask, f):
 
 # ------------------------------------------------------------------------------------------ driver
 def banded_cost_volume(t, stats, rank, world, rho="lorentzian", sigma=1.0, interp="cubic", range_mask="rigid_only",
-                       variant="staged", peer=(None, None), keep_local=True, halo=None, timers=None, resident=True):
+                       variant="staged", peer=(None, None), keep_local=True, halo=None, timers=None, resident=True,
+                       mailbox=None):
     """build_cost_volume for this rank's band of the host triplet ``t`` (dict as synth.make_triplet
     returns).  ``resident=True`` keeps the whole-frame scalars on the device (``banded_pass_resident``);
     ``False`` drives the statistics through the host (``BandStats`` / ``DistSelect``, the protocol the gloo
-    tests cover) -- same kernels, bit-identical results.
+    tests cover) -- same kernels, bit-identical results.  ``mailbox`` (a ``PeerMailbox``) routes the integer / min
+    all-reduces of the resident pre-pass through NVLink peer memory instead of NCCL.
     Returns dict(cost, S, mu, B, q, labels, mins, argmins, rows, halo)."""
     from .pipeline.build_cost_volume import cost_volume_pass
     h, w = t["shape"]
@@ -420,7 +498,7 @@ def banded_cost_volume(t, stats, rank, world, rho="lorentzian", sigma=1.0, inter
             mask = torch.from_numpy((rig[y0:y1] > 0).astype(np.uint8)).cuda()
             r = banded_pass_resident(band, t["homographies"], t["epipoles"], mask, stats, rho=rho, sigma=sigma, interp=interp,
                                      range_mask=range_mask, variant=variant, out_ptr=outs, plane_stride=stride,
-                                     want_cost=keep_local, halo_miss=miss, events=timers)
+                                     want_cost=keep_local, halo_miss=miss, events=timers, mailbox=mailbox)
             mu, B, labels = pp.state_to_host(r["buffers"].state)
             res = (r["cost"], r["buffers"].S, mu, B, r["q"], labels, r["mins"], r["argmins"])
         else:
@@ -458,6 +536,7 @@ def bench_bands(args, hw, steps, warm, metric, unit, workload, ClockSampler):
     kernel_events = []
 
     nonrigid = (rigid_mask == 0).to(torch.uint8)
+    mailbox = PeerMailbox()
     bbuf = BandBuffers(y1 - y0, w)
     miss = torch.zeros(1, dtype=torch.int32, device="cuda")
     cost_local = (torch.empty((L, y1 - y0, w), dtype=torch.float32, device="cuda"),
@@ -468,7 +547,7 @@ def bench_bands(args, hw, steps, warm, metric, unit, workload, ClockSampler):
         return banded_pass_resident(band, t["homographies"], t["epipoles"], rigid_mask, stats, buf=bbuf, interp=args.interp,
                                     range_mask="rigid_only", variant=args.variant, out_ptr=outs,
                                     plane_stride=(h * w if gather else 0), halo_miss=miss, events=events,
-                                    masks=(nonrigid, nonrigid))
+                                    masks=(nonrigid, nonrigid), mailbox=mailbox)
 
     def barrier():
         torch.cuda.synchronize(); dist.barrier(); torch.cuda.synchronize()
@@ -507,16 +586,19 @@ def bench_bands(args, hw, steps, warm, metric, unit, workload, ClockSampler):
     ach = bytes_launch / (float(np.mean(kms)) * 1e-3) / 1e9
     barrier()
     n_miss = stats.total(int(miss.cpu()[0]))
+    mbox_status = stats.total(int(mailbox.status() != 0))
     for p in peers:
         p.close()
+    mailbox.close()
     if rank == 0:
         assert n_miss == 0, "a timed step sampled outside its halo"
+        assert mbox_status == 0, "a peer-memory all-reduce gave up waiting for a rank"
         line = {"metric": metric, "value": units * steps / (tot_ms * 1e-3), "unit": unit, "n_gpus": world, "steps": steps,
                 "warmup": warm, "ms_per_step": tot_ms / steps, "higher_is_better": True, "scaling": "strong",
                 "vs_baseline": None, "dtype": "f64 geometry / f32 sampling", "data": "synthetic",
                 "config": {"workload": workload, "labels": L, "frames": 2, "interp": args.interp, "variant": args.variant,
                            "range_mask": "rigid_only", "parallelism": "row bands x%d, halo %d rows, device-resident statistics "
-                           "(NCCL all-reduces on the stream), peer-store gather to rank 0" % (world, halo_rows), "l2": "flushed between timed steps"},
+                           "(histogram / min all-reduces as one kernel per rank over NVLink peer memory, two NCCL sums), peer-store gather to rank 0" % (world, halo_rows), "l2": "flushed between timed steps"},
                 "compute_only": {"value": units * steps / (results["compute_only"][0] * 1e-3), "ms_per_step": results["compute_only"][0] / steps},
                 "clocks": clk, "e2e": None, "gpu_launches": int(launches),
                 "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,

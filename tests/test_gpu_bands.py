@@ -41,6 +41,30 @@ def _worker(rank, world, port, queue):
                                            and np.array_equal(res_h["labels"], res["labels"])
                                            and all(torch.equal(res_h["argmins"][f], res["argmins"][f]) for f in range(2)))
         torch.cuda.synchronize(); dist.barrier()
+        # the small all-reduces through NVLink peer memory (one kernel per rank) instead of NCCL: the ops
+        # themselves, slot wrap-around included, then the whole banded pass -- same bits
+        mb = sharding.PeerMailbox()
+        ok = True
+        for it in range(40):
+            a = (torch.arange(256, dtype=torch.int64, device="cuda") + it) * (rank + 1)
+            mb.allreduce(a, "sum_u64")
+            ok &= bool(torch.equal(a, (torch.arange(256, dtype=torch.int64, device="cuda") + it) * 3))
+            b = torch.tensor([5 + rank, 7 - rank, -1 if rank else 3], dtype=torch.int64, device="cuda")
+            mb.allreduce(b, "min_u64")
+            ok &= b.tolist() == [5, 6, 3]                   # unsigned order: -1 is the largest key
+            c = torch.tensor([1.5 - rank, -2.0 * rank, float("nan") if rank == it % 2 else 0.0, 4.0], dtype=torch.float64,
+                             device="cuda")
+            mb.allreduce(c, "min_f64")
+            cl = c.tolist()
+            ok &= cl[0] == 0.5 and cl[1] == -2.0 and cl[2] != cl[2] and cl[3] == 4.0
+        out["mailbox_ops"] = bool(ok)
+        res_m = sharding.banded_cost_volume(t, stats, rank, world, halo=res["halo"], mailbox=mb)
+        out["mailbox_equals_nccl"] = bool(res_m["mu"] == res["mu"] and res_m["B"] == res["B"]
+                                          and np.array_equal(res_m["labels"], res["labels"])
+                                          and all(torch.equal(res_m["argmins"][f], res["argmins"][f]) for f in range(2))
+                                          and all(torch.equal(res_m["cost"][f], res_h["cost"][f]) for f in range(2)))
+        out["mailbox_status"] = mb.status()
+        mb.close()
         out["halo"] = res["halo"]
         y0, y1 = res["rows"]
         if rank == 0:
@@ -99,5 +123,7 @@ def test_two_band_volume_equals_whole_frame():
     np.testing.assert_allclose(o["B"][0], o["B"][1], rtol=1e-11)
     assert o["labels_close"]
     assert res[0]["host_equals_resident"] and res[1]["host_equals_resident"]
+    for r in (0, 1):
+        assert res[r]["mailbox_ops"] and res[r]["mailbox_equals_nccl"] and res[r]["mailbox_status"] == 0
     for f in range(2):
         assert o["equal%d" % f] and o["argmin_equal%d" % f]

@@ -47,6 +47,8 @@ def parse():
     ap.add_argument("--interp", default="cubic", choices=["cubic", "linear"])
     ap.add_argument("--variant", default="staged", choices=["staged", "gather", "staged_occ2", "gather_occ2"])
     ap.add_argument("--mode", default="triplets", choices=["triplets", "bands"])
+    ap.add_argument("--band-allreduce", default="nccl", choices=["nccl", "peer"],
+                    help="--mode bands: small all-reduces of the pre-pass through NCCL or through the peer-memory mailbox kernel")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="launch the pre-pass eagerly instead of replaying its CUDA graph")

@@ -536,7 +536,9 @@ def bench_bands(args, hw, steps, warm, metric, unit, workload, ClockSampler):
     kernel_events = []
 
     nonrigid = (rigid_mask == 0).to(torch.uint8)
-    mailbox = PeerMailbox()
+    # measured on 8 GPUs / 4K (profiles/r1g_scale8_bands4k*.json): the peer-memory all-reduce kernel is no faster than
+    # NCCL's low-latency protocol for these 2 KB messages (2.57 ms vs 2.37 ms per step), so NCCL stays the default
+    mailbox = PeerMailbox() if getattr(args, "band_allreduce", "nccl") == "peer" else None
     bbuf = BandBuffers(y1 - y0, w)
     miss = torch.zeros(1, dtype=torch.int32, device="cuda")
     cost_local = (torch.empty((L, y1 - y0, w), dtype=torch.float32, device="cuda"),
@@ -586,10 +588,11 @@ def bench_bands(args, hw, steps, warm, metric, unit, workload, ClockSampler):
     ach = bytes_launch / (float(np.mean(kms)) * 1e-3) / 1e9
     barrier()
     n_miss = stats.total(int(miss.cpu()[0]))
-    mbox_status = stats.total(int(mailbox.status() != 0))
+    mbox_status = stats.total(int(mailbox.status() != 0)) if mailbox is not None else 0
     for p in peers:
         p.close()
-    mailbox.close()
+    if mailbox is not None:
+        mailbox.close()
     if rank == 0:
         assert n_miss == 0, "a timed step sampled outside its halo"
         assert mbox_status == 0, "a peer-memory all-reduce gave up waiting for a rank"
@@ -598,7 +601,9 @@ def bench_bands(args, hw, steps, warm, metric, unit, workload, ClockSampler):
                 "vs_baseline": None, "dtype": "f64 geometry / f32 sampling", "data": "synthetic",
                 "config": {"workload": workload, "labels": L, "frames": 2, "interp": args.interp, "variant": args.variant,
                            "range_mask": "rigid_only", "parallelism": "row bands x%d, halo %d rows, device-resident statistics "
-                           "(histogram / min all-reduces as one kernel per rank over NVLink peer memory, two NCCL sums), peer-store gather to rank 0" % (world, halo_rows), "l2": "flushed between timed steps"},
+                           "(%s), peer-store gather to rank 0" % (world, halo_rows, "NCCL all-reduces on the stream" if mailbox is None else
+                                                                "histogram / min all-reduces as one kernel per rank over NVLink peer memory, two NCCL sums"),
+                           "l2": "flushed between timed steps"},
                 "compute_only": {"value": units * steps / (results["compute_only"][0] * 1e-3), "ms_per_step": results["compute_only"][0] / steps},
                 "clocks": clk, "e2e": None, "gpu_launches": int(launches),
                 "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,

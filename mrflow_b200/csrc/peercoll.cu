@@ -2,8 +2,8 @@
 // The exact medians of pipeline/compute_structure.py:190,221 need eight 2 KB histogram all-reduces per
 // median; through NCCL each costs a launch plus ~20-30 us of latency that does not shrink with the band.
 // Here every rank owns a "mailbox" in its own HBM, exported over CUDA IPC (mrf_peer_alloc / mrf_peer_open):
-// one kernel stores this rank's words into every rank's mailbox (plain stores over NVLink), publishes a flag
-// per destination with system-scope release, waits for the flags of all sources in its own mailbox
+// one kernel stores this rank's words into every rank's mailbox (plain stores over NVLink), fences at system
+// scope, publishes a flag per destination, waits for the flags of all sources in its own mailbox
 // (system-scope acquire, bounded spin), and reduces the world's contributions in rank order.  Only
 // order-independent reductions are offered (integer sums, minima), so the result is bit-identical to NCCL's.
 // One process per GPU, one kernel per GPU: no rank ever waits on a kernel that shares its device.
@@ -29,8 +29,10 @@ __device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long
   asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
   return v;
 }
-__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
-  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+// the flag store itself is relaxed: every thread fenced its data stores at system scope and the block
+// synchronised before any flag is written, so a second release fence (one more NVLink round trip) is not needed
+__device__ __forceinline__ void st_relaxed_sys(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
 
 __global__ void __launch_bounds__(kMboxWords)
@@ -45,7 +47,7 @@ k_mbox_allreduce(unsigned long long* local, PeerPtrs peers, int world, int rank,
   __threadfence_system();
   __syncthreads();
   if (t < world) {
-    st_release_sys(peers.p[t] + mbox_flag_off(world, slot, rank), epoch);           // "rank's words for this call are in place"
+    st_relaxed_sys(peers.p[t] + mbox_flag_off(world, slot, rank), epoch);           // "rank's words for this call are in place"
     const unsigned long long* f = local + mbox_flag_off(world, slot, t);
     long long spins = 0;
     while (ld_acquire_sys(f) != epoch) {

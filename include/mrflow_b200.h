@@ -456,8 +456,10 @@ int mrf_peer_free(void* ptr);
 
 /* ---- small all-reduces over peer memory for the row-band pre-pass: the eight
  * 2 KB histogram all-reduces of each exact median, and the other integer / min reductions of the pre-pass,
- * as ONE kernel per rank that stores into every rank's mailbox over NVLink, publishes a flag with
- * system-scope release, waits for all sources in its own mailbox (bounded) and reduces in rank order.
+ * as ONE kernel per rank with a low-latency protocol: every 64-bit value travels as two 8-byte words
+ * (tag<<32 | half) stored straight into every rank's mailbox over NVLink -- an 8-byte store is one
+ * transaction, so a word carrying the call's tag is the data: no fence, no flag; the receiver polls its
+ * own mailbox (bounded) and reduces in rank order.
  * A mailbox is mrf_mailbox_bytes(world) bytes from mrf_peer_alloc, zeroed once, opened by every peer
  * (mrf_peer_open); mailboxes_host[world] are this process's pointers to all of them (its own at [rank]).
  * call_index must count the collectives 0, 1, 2, ... identically on every rank.  inout: nwords <= 256

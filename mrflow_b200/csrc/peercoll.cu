@@ -1,12 +1,13 @@
 // Small all-reduces over NVLink peer memory for the row-band pre-pass.
 // The exact medians of pipeline/compute_structure.py:190,221 need eight 2 KB histogram all-reduces per
-// median; through NCCL each costs a launch plus ~20-30 us of latency that does not shrink with the band.
-// Here every rank owns a "mailbox" in its own HBM, exported over CUDA IPC (mrf_peer_alloc / mrf_peer_open):
-// one kernel stores this rank's words into every rank's mailbox (plain stores over NVLink), fences at system
-// scope, publishes a flag per destination, waits for the flags of all sources in its own mailbox
-// (system-scope acquire, bounded spin), and reduces the world's contributions in rank order.  Only
-// order-independent reductions are offered (integer sums, minima), so the result is bit-identical to NCCL's.
-// One process per GPU, one kernel per GPU: no rank ever waits on a kernel that shares its device.
+// median; each costs latency that does not shrink with the band.  Here every rank owns a "mailbox" in its own
+// HBM, exported over CUDA IPC (mrf_peer_alloc / mrf_peer_open), and ONE kernel per rank does the collective
+// with a low-latency protocol: each 64-bit value travels as two 8-byte words, (tag << 32 | low half) and
+// (tag << 32 | high half), stored straight into every rank's mailbox over NVLink.  An 8-byte store is a
+// single transaction, so a word whose tag equals the call's tag IS the data -- no fence, no separate flag, one
+// one-way NVLink latency.  The receiver polls its own mailbox (bounded) and reduces the world's contributions
+// in rank order.  Only order-independent reductions are offered (integer sums, minima), so the result is
+// bit-identical to NCCL's.  One process per GPU, one kernel per GPU: no rank waits on a kernel on its own device.
 #include "common.cuh"
 
 namespace mrf {
@@ -18,62 +19,57 @@ constexpr long long kMboxSpinLimit = 3000000ll;       // a second or two of poll
 
 struct PeerPtrs { unsigned long long* p[kMboxMaxWorld]; };
 
-__host__ __device__ inline size_t mbox_data_off(int world, int slot, int src) { return ((size_t)slot * world + src) * kMboxWords; }
-__host__ __device__ inline size_t mbox_flag_off(int world, int slot, int src) {
-  return (size_t)kMboxSlots * world * kMboxWords + (size_t)slot * world + src;
-}
-__host__ __device__ inline size_t mbox_status_off(int world) { return (size_t)kMboxSlots * world * (kMboxWords + 1); }
+// two tagged words per value
+__host__ __device__ inline size_t mbox_data_off(int world, int slot, int src) { return ((size_t)slot * world + src) * kMboxWords * 2; }
+__host__ __device__ inline size_t mbox_status_off(int world) { return (size_t)kMboxSlots * world * kMboxWords * 2; }
 
-__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
+__device__ __forceinline__ unsigned long long ld_relaxed_sys(const unsigned long long* p) {
   unsigned long long v;
-  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
   return v;
 }
-// the flag store itself is relaxed: every thread fenced its data stores at system scope and the block
-// synchronised before any flag is written, so a second release fence (one more NVLink round trip) is not needed
 __device__ __forceinline__ void st_relaxed_sys(unsigned long long* p, unsigned long long v) {
   asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
 
 __global__ void __launch_bounds__(kMboxWords)
-k_mbox_allreduce(unsigned long long* local, PeerPtrs peers, int world, int rank, int slot, unsigned long long epoch, int op,
+k_mbox_allreduce(unsigned long long* local, PeerPtrs peers, int world, int rank, int slot, unsigned int tag, int op,
                  unsigned long long* inout, int nwords) {
   __shared__ int s_timeout;
   const int t = threadIdx.x;
   if (t == 0) s_timeout = 0;
-  const unsigned long long mine = (t < nwords) ? inout[t] : 0ull;
-  if (t < nwords)
-    for (int p = 0; p < world; ++p) peers.p[p][mbox_data_off(world, slot, rank) + t] = mine;
-  __threadfence_system();
   __syncthreads();
-  if (t < world) {
-    st_relaxed_sys(peers.p[t] + mbox_flag_off(world, slot, rank), epoch);           // "rank's words for this call are in place"
-    const unsigned long long* f = local + mbox_flag_off(world, slot, t);
-    long long spins = 0;
-    while (ld_acquire_sys(f) != epoch) {
-      if (++spins > kMboxSpinLimit) { s_timeout = 1; break; }
-    }
-  }
-  __syncthreads();
-  if (s_timeout) {
-    if (t == 0) local[mbox_status_off(world)] = epoch;                                // non-zero status = the call that gave up
-    return;
-  }
+  const unsigned long long tag_hi = (unsigned long long)tag << 32;
   if (t < nwords) {
-    unsigned long long acc = __ldcv(local + mbox_data_off(world, slot, 0) + t);
-    for (int r = 1; r < world; ++r) {
-      const unsigned long long v = __ldcv(local + mbox_data_off(world, slot, r) + t);
+    const unsigned long long mine = inout[t];
+    const unsigned long long w_lo = tag_hi | (mine & 0xffffffffull), w_hi = tag_hi | (mine >> 32);
+    const size_t off = mbox_data_off(world, slot, rank) + 2 * (size_t)t;
+    for (int p = 0; p < world; ++p) { st_relaxed_sys(peers.p[p] + off, w_lo); st_relaxed_sys(peers.p[p] + off + 1, w_hi); }
+    unsigned long long acc = 0;
+    for (int r = 0; r < world; ++r) {
+      const unsigned long long* src = local + mbox_data_off(world, slot, r) + 2 * (size_t)t;
+      unsigned long long a, b;
+      long long spins = 0;
+      while (true) {
+        a = ld_relaxed_sys(src); b = ld_relaxed_sys(src + 1);
+        if ((a >> 32) == tag && (b >> 32) == tag) break;
+        if (++spins > kMboxSpinLimit) { s_timeout = 1; break; }
+      }
+      const unsigned long long v = (a & 0xffffffffull) | (b << 32);
+      if (r == 0) { acc = v; continue; }
       switch (op) {
         case MRF_PEER_SUM_U64: acc += v; break;
         case MRF_PEER_MIN_U64: acc = v < acc ? v : acc; break;
         default: {   // MRF_PEER_MIN_F64: a NaN from any rank wins, like numpy's min
-          const double a = __longlong_as_double((long long)acc), b = __longlong_as_double((long long)v);
-          acc = (a != a) ? acc : ((b != b || b < a) ? v : acc);
+          const double x = __longlong_as_double((long long)acc), y = __longlong_as_double((long long)v);
+          acc = (x != x) ? acc : ((y != y || y < x) ? v : acc);
         }
       }
     }
     inout[t] = acc;
   }
+  __syncthreads();
+  if (t == 0 && s_timeout) local[mbox_status_off(world)] = (unsigned long long)tag;   // non-zero status = the call that gave up
 }
 
 }  // namespace mrf
@@ -92,9 +88,10 @@ int mrf_mailbox_allreduce(void* local_mailbox, void* const* mailboxes_host, int 
   PeerPtrs pp;
   for (int i = 0; i < kMboxMaxWorld; ++i) pp.p[i] = (i < world) ? (unsigned long long*)mailboxes_host[i] : nullptr;
   MRF_CHECK_ARG(pp.p[rank] == (unsigned long long*)local_mailbox);
+  // tags 1 .. 2^32-1 (never 0: a zeroed mailbox holds no valid word)
+  const unsigned int tag = (unsigned int)(call_index % 0xffffffffll) + 1u;
   k_mbox_allreduce<<<1, kMboxWords, 0, S(stream)>>>((unsigned long long*)local_mailbox, pp, world, rank,
-                                                    (int)(call_index % kMboxSlots), (unsigned long long)(call_index + 1), op,
-                                                    (unsigned long long*)inout_words, nwords);
+                                                    (int)(call_index % kMboxSlots), tag, op, (unsigned long long*)inout_words, nwords);
   return check_launch("mrf_mailbox_allreduce");
 }
 

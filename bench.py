@@ -388,14 +388,18 @@ def run_ours(args):
             o1 = bcv.build_cost_volume(h1["images"], h1["flow"], h1["rigidity"], h1["homographies"], h1["epipoles"], None,
                                        interp=args.interp, variant=args.variant, range_mask=RANGE_MASK)
         torch.cuda.synchronize()
-        t0 = time.perf_counter()
-        n1 = 5
+        n1 = 9
+        times = []
         for _ in range(n1):
+            t0 = time.perf_counter()
             o1 = bcv.build_cost_volume(h1["images"], h1["flow"], h1["rigidity"], h1["homographies"], h1["epipoles"], None,
                                        interp=args.interp, variant=args.variant, range_mask=RANGE_MASK)
             s2f.combine_flow(o1[1][1], h1["flow"][1], h1["rigidity"], o1[4], o1[2], h1["homographies"], o1[3])
-        torch.cuda.synchronize()
-        e2e["single_call"] = {"value": units_per_step * n1 / (time.perf_counter() - t0),
+            torch.cuda.synchronize()
+            times.append(time.perf_counter() - t0)
+        # median call: the pinned result buffers are re-allocated now and then, which stalls single calls for tens of ms
+        e2e["single_call"] = {"value": units_per_step / float(np.median(times)), "calls": n1,
+                              "ms_per_call_median": float(np.median(times)) * 1e3, "ms_per_call_max": float(max(times)) * 1e3,
                               "api": "mrflow_b200.pipeline.build_cost_volume + combine_flow, one triplet at a time"}
 
     cpu_baseline = None

@@ -263,6 +263,12 @@ def main():
                 out["full_refined"] = refined
                 _, fu, fv = s2f.combine_flow(refined, t["flow"][1], full[5], full[4], full[2], full[1], full[3], t["images"], p)
                 out["full_refined_u"], out["full_refined_v"] = fu, fv
+                # a two-level pyramid (optimize_structure_multi_scale.py:52-143: resampling of images, structures and
+                # masks, scaled H / B / q / mu per level), two outer iterations per level
+                p.variational_N_scales = 2
+                p.variational_N_outer = 2
+                out["full_refined_ms2"] = ovr.optimize([I.copy() for I in t["images"]], full[0], full[5], full[4], full[1], full[3],
+                                                       full[2], occ2, p)[0]
         if example_images is not None:
             out["images"] = np.stack(example_images)
         np.savez_compressed(os.path.join(HERE, "ref_%s.npz" % tag), **out)

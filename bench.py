@@ -4,13 +4,14 @@
     python bench.py [--gpus N] [--steps K] [--warmup W]                 # our arm
     python bench.py --impl reference [--gpus N] [--steps K] [--warmup W]  # the reference's CPU path
 
-One step = one pass of the hot path over one synthetic triplet that is already resident in HBM:
-flow -> residual flow -> parallax -> mu, B -> normed structures -> label range -> channels of the
-three frames -> per-label data cost of both neighbour frames (51 labels, min / argmin) -> structure ->
-flow.  Work units = 2 neighbour frames x h x w x 51 labels.  At N > 1 every
-rank owns its own triplet (triplet-parallel, mrflow_dataset.py-style; no data-path collective): weak
-scaling.  ``--mode bands`` runs ONE frame sharded by row bands with halos instead (strong scaling;
-NCCL only for the tiny statistics all-reduces), used for the 4K configuration.
+One step = one pass of the hot path over one batch (``--batch``, default 16) of synthetic Sintel-shape
+triplets that are already resident in HBM; per triplet: flow -> residual flow -> parallax -> mu, B ->
+normed structures -> label range -> channels of the three frames -> per-label data cost of both
+neighbour frames (51 labels, min / argmin) -> structure -> flow.  Work units = 2 neighbour frames x h x w
+x 51 labels per triplet.  At N > 1 every rank owns its own triplets
+(triplet-parallel, mrflow_dataset.py-style; no data-path collective): weak scaling.  The same line carries
+``bands_4k``: ONE 4K frame sharded by row bands with halos over the N GPUs (strong scaling; NCCL only for
+the small statistics collectives), at N = 1 the whole 4K frame on one GPU, the base of that speed-up.
 
 Prints ONE JSON line on rank 0.
 """
@@ -46,9 +47,8 @@ def parse():
     ap.add_argument("--shape", default="sintel", help="sintel | kitti | 4k | HxW")
     ap.add_argument("--interp", default="cubic", choices=["cubic", "linear"])
     ap.add_argument("--variant", default="staged", choices=["staged", "gather", "staged_occ2", "gather_occ2"])
-    ap.add_argument("--mode", default="triplets", choices=["triplets", "bands"])
-    ap.add_argument("--band-allreduce", default="nccl", choices=["nccl", "peer"],
-                    help="--mode bands: small all-reduces of the pre-pass through NCCL or through the peer-memory mailbox kernel")
+    ap.add_argument("--batch", type=int, default=16, help="triplets per step (a step = one pass of the path over one batch)")
+    ap.add_argument("--no-bands", action="store_true", help="skip the 4K row-band record (bands_4k)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="launch the pre-pass eagerly instead of replaying its CUDA graph")
@@ -209,6 +209,29 @@ def run_reference(args):
 
 
 # ------------------------------------------------------------------------------------------ our arm
+def parity_against_oracle(t, gpu_cost, state, planes):
+    """The checker (cpu_baseline leg): label planes of the GPU's volumes against the CPU oracle evaluated at the
+    GPU's own whole-frame scalars.  ``gpu_cost``: the two device volumes; ``planes``: label indices."""
+    from oracle import hotpath as hp
+    h, w = t["shape"]
+    ch = [hp.prepare_channels(I) for I in t["images"]]
+    noocc = [np.zeros((h, w), bool)] * 2
+    t0 = time.perf_counter()
+    want, _, _ = hp.cost_volume(ch, t["rigidity"], noocc, t["homographies"], state["B"], state["mu"], state["q"], state["labels"],
+                                kind="lorentzian", sigma=1.0, labels=planes)
+    dt = time.perf_counter() - t0
+    worst, exact, n = 0.0, 0, 0
+    for f in range(2):
+        got = gpu_cost[f][planes].cpu().numpy().astype(np.float64)
+        ref = want[f].astype(np.float64)
+        err = np.abs(got - ref) / np.maximum(np.abs(ref), 1e-2)
+        worst = max(worst, float(err.max()))
+        exact += int((got == ref).sum()); n += got.size
+    return {"max_rel_err": worst, "frac_bit_exact": exact / n, "labels_checked": len(planes), "frames": 2,
+            "against": "CPU oracle (oracle/hotpath.py) at the GPU's mu / B / labels, same triplet as the timed one",
+            "tolerance": 1e-5}, dt, 2 * h * w * len(planes)
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -224,26 +247,22 @@ def run_ours(args):
     torch.cuda.set_device(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    steps = 30 if args.steps is None else args.steps
+    steps = 20 if args.steps is None else args.steps
     warm = 5 if args.warmup is None else max(args.warmup, 3)
     hw = shape_of(args.shape)
     h, w = hw
-
-    if args.mode == "bands" and world > 1:
-        from mrflow_b200 import sharding
-        return sharding.bench_bands(args, hw, steps, warm, METRIC, UNIT, workload_name(args, hw), ClockSampler)
+    T = max(1, args.batch)                       # triplets per step
 
     t = synth.make_triplet(hw, seed=1001 + rank)
     rig_host = t["rigidity"] > 0
     band = pp.Band.from_host(t["images"], t["flow"], t["rigidity"], None)
     rigid_mask = torch.from_numpy(rig_host.astype(np.uint8)).cuda()
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")    # > 126 MB L2
-    kernel_events = []
 
-    # ``--pipeline P``: P distinct triplets resident per GPU, each with its own stream; consecutive steps
-    # alternate between them, so the short pre-pass launches of one triplet overlap the cost-volume kernels
-    # of the other (what a dataset run over many triplets does).  Every step still processes one whole
-    # triplet; P = 1 is the plain back-to-back case.
+    # ``--pipeline P``: P distinct triplets resident per GPU, each with its own stream; consecutive triplets of a
+    # step alternate between them, so the short pre-pass launches of one overlap the cost-volume kernels of
+    # another (what a dataset run over many triplets does).  A step = one pass of the path over a batch of
+    # ``--batch`` triplets (default 16: ~10 ms, so that 20 timed steps make a 0.2 s region).
     P = max(1, args.pipeline)
     slots = []
     host_triplets = []
@@ -261,65 +280,69 @@ def run_ours(args):
         slots.append((st, stream))
     stepper = slots[0][0]
 
-    def step(k, events=None):
-        st, stream = slots[k % P]
-        with torch.cuda.stream(stream):
-            return st.run(events)
-
     def barrier():
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    for k in range(warm * P):
-        step(k)
+    k_run = 0
+    for _ in range(warm):
+        for _ in range(T):
+            st, stream = slots[k_run % P]
+            with torch.cuda.stream(stream):
+                st.run()
+            k_run += 1
     barrier()
     device.reset_launch_count()
     main = torch.cuda.current_stream()
+    ev_batch, ev_single = [], []
+    n_single = max(steps, 10)
     with ClockSampler(local) as clocks:
-        # (1) one triplet at a time: per-step CUDA events, L2 flushed before every step.  This is the
-        #     latency of the path and the region in which the dominant kernel is timed for the roofline.
+        # (1) THE timed region: K steps, each one batch of T triplets, P in flight
+        flush.fill_(1)
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(main)
+        for _, stream in slots:
+            stream.wait_stream(main)
+        for _ in range(steps * T):
+            st, stream = slots[k_run % P]
+            with torch.cuda.stream(stream):
+                st.run(ev_batch)
+            k_run += 1
+        for _, stream in slots:
+            main.wait_stream(stream)
+        e1.record(main)
+        e1.synchronize()
+        total_ms = e0.elapsed_time(e1)
+        # (2) one triplet at a time, L2 flushed before each: the latency of the path
         single_ms = 0.0
-        for k in range(steps):
+        for k in range(n_single):
             flush.fill_(1)
             slots[0][1].wait_stream(main)
             with torch.cuda.stream(slots[0][1]):
-                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                e0.record()
-                slots[0][0].run(kernel_events)
-                e1.record()
-            e1.synchronize()
-            single_ms += e0.elapsed_time(e1)
-        total_ms = single_ms
-        # (2) P triplets in flight (the dataset-run form): one timed region over K steps
-        if P > 1:
-            barrier()
-            flush.fill_(1)
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record(main)
-            for _, stream in slots:
-                stream.wait_stream(main)
-            for k in range(steps):
-                step(k)
-            for _, stream in slots:
-                main.wait_stream(stream)
-            e1.record(main)
-            e1.synchronize()
-            total_ms = e0.elapsed_time(e1)
-    n_runs = steps * (2 if P > 1 else 1)
+                a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a0.record()
+                slots[0][0].run(ev_single)
+                a1.record()
+            a1.synchronize()
+            single_ms += a0.elapsed_time(a1)
+    n_runs = steps * T + n_single
     launches = device.launch_count() + n_runs * stepper.launches_in_graph     # replayed launches are not re-counted
     barrier()
     tmax = torch.tensor([total_ms, single_ms], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
     total_ms_max, single_ms_max = float(tmax.cpu()[0]), float(tmax.cpu()[1])
-    units_per_step = 2 * h * w * N_LABELS
-    value = world * units_per_step * steps / (total_ms_max * 1e-3)
+    units_per_triplet = 2 * h * w * N_LABELS
+    value = world * units_per_triplet * T * steps / (total_ms_max * 1e-3)
 
-    # dominant kernel: k_cost_volume (one launch per neighbour frame)
-    kms = [a.elapsed_time(b) for a, b in kernel_events]
-    k_avg_ms = float(np.mean(kms))
+    # dominant kernel: k_cost_volume (one launch per neighbour frame), timed with events inside the SAME region
+    # as `value`; with P triplets in flight a launch can share the GPU with another triplet's short pre-pass
+    # kernels, so its duration in the single-triplet region is reported next to it
+    k_avg_ms = float(np.mean([a.elapsed_time(b) for a, b in ev_batch]))
+    k_single_ms = float(np.mean([a.elapsed_time(b) for a, b in ev_single]))
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -327,14 +350,19 @@ def run_ours(args):
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
     achieved = algorithmic_bytes_per_launch(h, w) / (k_avg_ms * 1e-3) / 1e9
-    traffic = None
+    traffic, traffic_src = None, None
     try:
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(workload_name(args, hw))
+        tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+        traffic = tj.get(workload_name(args, hw))
+        traffic_src = tj.get("_capture")
     except Exception:   # noqa: BLE001
         pass
+    ms_per_triplet = total_ms_max / (steps * T)
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": traffic, "kernel": "k_cost_volume", "kernel_ms": k_avg_ms,
-                "kernel_share_of_step": 2 * k_avg_ms * steps / single_ms, "timed_in": "single-triplet region",
+                "traffic": traffic, "traffic_source": traffic_src, "kernel": "k_cost_volume", "kernel_ms": k_avg_ms,
+                "kernel_share_of_step": 2 * k_avg_ms / ms_per_triplet, "timed_in": "the timed region of `value` (CUDA events on "
+                "the launching streams)", "kernel_ms_single_triplet_region": k_single_ms,
+                "algorithmic_bytes_per_launch": algorithmic_bytes_per_launch(h, w),
                 "peak_source": "measured (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks else "fallback"}
 
     # ---- end to end through the public host API (numpy in pinned memory -> numpy out)
@@ -352,11 +380,10 @@ def run_ours(args):
                               rigidity=pinned(ts["rigidity"]), homographies=ts["homographies"], epipoles=ts["epipoles"]))
         h0 = hosts[0]
         h2d = sum(a.nbytes for a in h0["images"]) + sum(a.nbytes for f in h0["flow"] for a in f) + h0["rigidity"].nbytes
-        h2d += 2 * h * w                                       # rigid / non-rigid flags
-        # the public dataset API: P triplets in flight, every step uploads its inputs from pinned host memory
+        # the public dataset API: P triplets in flight, every triplet uploads its inputs from pinned host memory
         # and downloads both cost volumes, both structures, the flow and the scalars into pinned host memory
         stream_api = dataset.TripletStream(depth=P, interp=args.interp, variant=args.variant, range_mask=RANGE_MASK)
-        n_e2e = max(6, min(steps, 20))
+        n_e2e = steps * T
 
         def e2e_run(n):
             last = None
@@ -379,16 +406,19 @@ def run_ours(args):
         tt = torch.tensor([dt], dtype=torch.float64, device="cuda")
         if world > 1:
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        e2e = {"value": world * units_per_step * n_e2e / float(tt.cpu()[0]), "unit": UNIT, "h2d_bytes_per_step": int(h2d),
-               "d2h_bytes_per_step": int(d2h), "steps": n_e2e, "triplets_in_flight": P,
+        e2e = {"value": world * units_per_triplet * n_e2e / float(tt.cpu()[0]), "unit": UNIT,
+               "h2d_bytes_per_step": int(h2d) * T, "d2h_bytes_per_step": int(d2h) * T, "steps": steps, "triplets_per_step": T,
+               "triplets_in_flight": P, "ms_per_triplet": 1e3 * float(tt.cpu()[0]) / n_e2e,
+               "h2d_bytes_per_triplet": int(h2d), "d2h_bytes_per_triplet": int(d2h),
+               "pcie_gbs_achieved": world * (h2d + d2h) * n_e2e / float(tt.cpu()[0]) / 1e9,
                "api": "mrflow_b200.dataset.TripletStream (build_cost_volume + combine_flow per triplet, host numpy in/out)"}
         # one call at a time through the reference-signature functions, for comparison
         h1 = hosts[0]
-        for _ in range(3):          # the pinned result buffers of `down()` settle after three calls (two sets alive at once)
+        for _ in range(3):
             o1 = bcv.build_cost_volume(h1["images"], h1["flow"], h1["rigidity"], h1["homographies"], h1["epipoles"], None,
                                        interp=args.interp, variant=args.variant, range_mask=RANGE_MASK)
         torch.cuda.synchronize()
-        n1 = 9
+        n1 = 15
         times = []
         for _ in range(n1):
             t0 = time.perf_counter()
@@ -397,36 +427,58 @@ def run_ours(args):
             s2f.combine_flow(o1[1][1], h1["flow"][1], h1["rigidity"], o1[4], o1[2], h1["homographies"], o1[3])
             torch.cuda.synchronize()
             times.append(time.perf_counter() - t0)
-        # median call: the pinned result buffers are re-allocated now and then, which stalls single calls for tens of ms
-        e2e["single_call"] = {"value": units_per_step / float(np.median(times)), "calls": n1,
+        e2e["single_call"] = {"value": units_per_triplet / float(np.median(times)), "calls": n1,
                               "ms_per_call_median": float(np.median(times)) * 1e3, "ms_per_call_max": float(max(times)) * 1e3,
                               "api": "mrflow_b200.pipeline.build_cost_volume + combine_flow, one triplet at a time"}
 
-    cpu_baseline = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        t_rest, state, ch = cpu_front_and_tail(t)
-        idx = list(range(N_LABELS))                          # the whole workload once: ~5-10 s of host time
-        dt, units = cpu_reference_step(t, ch, state, idx)
-        cpu_baseline = {"value": units / (dt + t_rest * len(idx) / N_LABELS), "unit": UNIT, "cores": host_threads(),
-                        "kind": "port", "host_cpus": os.cpu_count(),
-                        "sample": "%d of %d labels x 2 frames of the same triplet, 1 pass (%.1f s)" % (len(idx), N_LABELS, dt)}
+    # ---- the CPU leg (rank 0): the oracle as the checker of the volumes just timed and, at N = 1, as the baseline
+    cpu_baseline, parity = None, None
+    if rank == 0 and not args.no_cpu_baseline:
+        mu_g, B_g, labels_g = pp.state_to_host(stepper.buf.state)
+        state_g = dict(mu=mu_g, B=B_g, labels=labels_g, q=stepper.q)
+        if world == 1:
+            t_rest, _, _ = cpu_front_and_tail(t)
+            idx = list(range(N_LABELS))                      # the whole workload once: ~5-10 s of host time
+            parity, dt, units = parity_against_oracle(t, stepper.cost, state_g, idx)
+            cpu_baseline = {"value": units / (dt + t_rest * len(idx) / N_LABELS), "unit": UNIT, "cores": host_threads(),
+                            "kind": "port", "host_cpus": os.cpu_count(),
+                            "sample": "%d of %d labels x 2 frames of the same triplet, 1 pass (%.1f s) + pre-pass / channels / "
+                                      "structure->flow (%.2f s)" % (len(idx), N_LABELS, dt, t_rest)}
+        else:
+            parity, _, _ = parity_against_oracle(t, stepper.cost, state_g, [0, 25, 50])
+
+    # ---- BASELINE.json configs[3]: one 4K frame in row bands over the N GPUs (strong scaling); at N = 1 the base
+    bands = None
+    if not args.no_bands:
+        for st, _ in slots:
+            del st
+        slots.clear()
+        stepper_launches = stepper.launches_in_graph
+        cuda_graph = stepper.graph is not None
+        stepper = None
+        torch.cuda.empty_cache()
+        from mrflow_b200 import sharding
+        bands = sharding.bench_bands(synth.SHAPES["4k"], max(5, min(steps, 20)), 3, interp=args.interp, variant=args.variant)
+    else:
+        stepper_launches = stepper.launches_in_graph
+        cuda_graph = stepper.graph is not None
 
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": warm,
                 "ms_per_step": total_ms_max / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "f64 geometry / f32 sampling", "data": "synthetic",
-                "config": {"workload": workload_name(args, hw), "labels": N_LABELS, "frames": 2, "interp": args.interp,
-                           "variant": args.variant, "range_mask": RANGE_MASK,
-                           "cuda_graph": "pre-pass + channels (%d launches) replayed as one graph" % stepper.launches_in_graph
-                           if stepper.graph is not None else "off", "triplets_in_flight": P, "parallelism": "triplets x%d" % world,
-                           "l2": ("flushed between timed steps (256 MiB fill); outputs 182 MB > L2" if P == 1 else
-                                  "flushed before the timed region; steps cycle over %d resident triplets and each writes "
-                                  "182 MB (> L2)" % P)},
-                "single_triplet": {"ms_per_step": single_ms_max / steps,
-                                   "value": world * units_per_step * steps / (single_ms_max * 1e-3),
+                "config": {"workload": workload_name(args, hw), "labels": N_LABELS, "frames": 2, "interp": args.interp},
+                "details": {"triplets_per_step": T, "ms_per_triplet": ms_per_triplet, "variant": args.variant,
+                            "range_mask": RANGE_MASK,
+                            "cuda_graph": "pre-pass + channels (%d launches) replayed as one graph" % stepper_launches
+                            if cuda_graph else "off", "triplets_in_flight": P, "parallelism": "triplets x%d" % world,
+                            "l2": "flushed before the timed region; the batch cycles over %d resident triplets and each "
+                                  "writes 182 MB (> 126 MB L2)" % P},
+                "single_triplet": {"ms_per_step": single_ms_max / n_single, "steps": n_single,
+                                   "value": world * units_per_triplet * n_single / (single_ms_max * 1e-3),
                                    "note": "one triplet at a time, L2 flushed before every step (path latency)"},
                 "clocks": clocks.summary(), "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
-                "cpu_baseline": cpu_baseline}
+                "cpu_baseline": cpu_baseline, "parity": parity, "bands_4k": bands}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

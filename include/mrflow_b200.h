@@ -35,7 +35,6 @@ extern "C" {
 typedef void* mrf_stream_t; /* cudaStream_t */
 
 #define MRF_E_BADARG   (-1)
-#define MRF_E_NOTMA    (-2) /* driver entry point for tensor-map encoding unavailable */
 #define MRF_E_SCRATCH  (-3)
 
 /* sampling modes: the reference samples with cv2.remap(INTER_CUBIC, BORDER_REPLICATE) on
@@ -278,37 +277,52 @@ int mrf_cost_volume_front(const mrf_front_params* p_host, const float* u0, const
                           const float* u1, const float* v1, const uint8_t* rigid_mask,
                           const uint8_t* zero_mask, double* par0, double* par1, double* S0, double* S1,
                           double* cand, int* count, double* dev_state, void* scratch, mrf_stream_t stream);
-/* The same pre-pass in pieces for ROW BANDS (p->y0, p->rows = this rank's band): between the pieces the
- * caller all-reduces small device buffers with NCCL on the same stream -- no host round trip:
- *   parallax_band  -> sums2[2] = this band's sum of ||p - q|| per frame;  all-reduce SUM, divide by
- *                     frame_h*w into dev_state[MRF_STATE_MU..];
- *   candidates_band-> cand / count (local);  all-reduce SUM of count -> n_total;
- *   mrf_select_begin_dev(n_total); 8 x { mrf_select_hist_dev(local count); all-reduce SUM of the 256
- *                     uint64 words at scratch + MRF_SELECT_HIST_OFFSET; mrf_select_pick };
- *                     mrf_select_successor_dev; all-reduce state words 3,4 (SUM) and 5 (MIN, unsigned);
- *                     mrf_select_median_state -> dev_state[MRF_STATE_B];
- *   structures_band-> S0, S1 and this band's range min / max / NaN flag in dev_state;  all-reduce MIN /
- *                     MAX / MAX;  mrf_label_range_dev. */
+/* The same pre-pass in pieces for ROW BANDS (p->y0, p->rows = this rank's band).  Between the pieces the
+ * caller runs SEVEN small collectives on the same stream (NCCL) -- no host round trip, and none for mu:
+ *   mrf_front_mu_whole     -> dev_state[MRF_STATE_MU..]: the sum of ||p - q|| over the WHOLE frame depends
+ *                             only on (q, frame_h, w), so every rank evaluates it itself, in the grid and
+ *                             summation tree of mrf_cost_volume_front: the bits of the one-GPU run;
+ *   mrf_front_parallax_band-> par0, par1 of the band;
+ *   mrf_front_candidates_band -> cand / count (local) and the first-digit histogram of the exact median
+ *                             (select13: five passes of 12+13+13+13+13 bits);
+ *   5 x { all-reduce SUM of the MRF_SELECT13_BINS uint32 words of pass p at select_scratch +
+ *         MRF_SELECT13_HIST_OFFSET + p * 4 * MRF_SELECT13_BINS;  mrf_select13_hist_dev(pass p+1) -- after the
+ *         fifth all-reduce mrf_select13_successor_dev instead };
+ *   all-gather the 3 uint64 words at select_scratch + MRF_SELECT13_SUCC_OFFSET of every rank;
+ *   mrf_front_structures_band(gathered) -> dev_state[MRF_STATE_B] = the median, S0, S1, and this band's
+ *                             range min / max / NaN flags in dev_state[MRF_STATE_MINMAX .. MRF_STATE_NANFLAG+1];
+ *   all-gather those 6 doubles of every rank;  mrf_label_range_dev(gathered). */
+#define MRF_SELECT13_BINS        8192
+#define MRF_SELECT13_HIST_OFFSET 256
+#define MRF_SELECT13_SUCC_OFFSET 24
+int mrf_front_mu_whole(const mrf_front_params* p_host, double* dev_state, void* scratch, mrf_stream_t stream);
 int mrf_front_parallax_band(const mrf_front_params* p_host, const float* u0, const float* v0,
-                            const float* u1, const float* v1, double* par0, double* par1, double* sums2,
+                            const float* u1, const float* v1, double* par0, double* par1,
                             void* scratch, mrf_stream_t stream);
 int mrf_front_candidates_band(const mrf_front_params* p_host, const double* par0, const double* par1,
-                              const uint8_t* rigid_mask, const double* dev_state, double* cand, int* count,
-                              mrf_stream_t stream);
+                              const uint8_t* rigid_mask, double* dev_state, double* cand, int* count,
+                              void* select_scratch, mrf_stream_t stream);
 int mrf_front_structures_band(const mrf_front_params* p_host, const double* par0, const double* par1,
                               const uint8_t* zero_mask, double* S0, double* S1, double* dev_state,
+                              const void* select_scratch, const unsigned long long* gathered_successor, int world,
                               void* scratch, mrf_stream_t stream);
-int mrf_select_begin_dev(const int* n_total_dev, void* scratch, mrf_stream_t stream);
-int mrf_select_hist_dev(const double* keys, const int* n_local_dev, size_t capacity, void* scratch,
+/* Exact median in five radix passes with the counts read on the device (csrc/select13.cuh): zero the
+ * scratch (mrf_select_scratch_bytes), histogram pass 0..4 (each resolves the previous digit from the
+ * finished -- for row bands all-reduced -- histogram), successor pass, median (gathered = the successor
+ * words of all ranks [world][3], or NULL on one GPU). */
+int mrf_select13_begin(void* scratch, mrf_stream_t stream);
+int mrf_select13_hist_dev(const double* keys, const int* n_local_dev, size_t capacity, int pass, void* scratch,
+                          mrf_stream_t stream);
+int mrf_select13_successor_dev(const double* keys, const int* n_local_dev, size_t capacity, void* scratch,
+                               mrf_stream_t stream);
+int mrf_select13_median(const void* scratch, const unsigned long long* gathered, int world, double* out_median,
                         mrf_stream_t stream);
-int mrf_select_successor_dev(const double* keys, const int* n_local_dev, size_t capacity, void* scratch,
-                             mrf_stream_t stream);
-int mrf_select_median_state(const void* scratch, double* out_median, mrf_stream_t stream);
 /* numpy.median of the first *n_dev keys (n read on the device); np.linspace label set from the
  * state's min/max.  Building blocks of the front, exported for tests. */
 int mrf_select_median_dev(const double* keys, const int* n_dev, size_t capacity, double* out_median,
                           void* scratch, mrf_stream_t stream);
-int mrf_label_range_dev(double* dev_state, int n_labels, mrf_stream_t stream);
+/* gathered: the six words MRF_STATE_MINMAX .. MRF_STATE_NANFLAG+1 of every band [world][6], or NULL */
+int mrf_label_range_dev(double* dev_state, int n_labels, const double* gathered, int world, mrf_stream_t stream);
 
 /* ---- utils/robust_functions.py:26-70 on a device array: out = rho(x) (deriv = 0) or d rho/dx
  * (deriv = 1), x = squared residual.  kind = MRF_RHO_*; p1 = sigma / eps; p2 = Charbonnier
@@ -454,12 +468,22 @@ int mrf_peer_open(const unsigned char* handle64, void** ptr_out);
 int mrf_peer_close(void* ptr);
 int mrf_peer_free(void* ptr);
 
-/* ---- small all-reduces over peer memory for the row-band pre-pass: the eight
- * 2 KB histogram all-reduces of each exact median, and the other integer / min reductions of the pre-pass,
- * as ONE kernel per rank with a low-latency protocol: every 64-bit value travels as two 8-byte words
+/* ---- device -> host of a row chunk of a label-major volume: rows [y0, y0+rows) of every plane of a
+ * device [n_planes][frame_h][w] array into the same rows of a (pinned) host array of the same shape, as one
+ * pitched DMA on `stream` -- the download of chunk k overlaps the kernel of chunk k+1
+ * (the 91 MB per neighbour frame that pipeline/build_cost_volume.py:226-231 returns is the long pole of a
+ * host-API call). */
+int mrf_download_rows(void* dst_host, const void* src_dev, size_t elem_bytes, int n_planes, int frame_h,
+                      int w, int y0, int rows, mrf_stream_t stream);
+
+/* ---- small all-reduces over peer memory: integer / min reductions of up to 256
+ * words (a building block; the resident row-band pre-pass itself uses NCCL for its 32 KB histograms) as ONE
+ * kernel per rank with a low-latency protocol: every 64-bit value travels as two 8-byte words
  * (tag<<32 | half) stored straight into every rank's mailbox over NVLink -- an 8-byte store is one
  * transaction, so a word carrying the call's tag is the data: no fence, no flag; the receiver polls its
- * own mailbox (bounded) and reduces in rank order.
+ * own mailbox and reduces in rank order.  A peer that has not arrived after 20 s of wall clock
+ * (%globaltimer) turns the WHOLE result into all-ones words and sets the mailbox's status word (its last 8
+ * words): callers must check it (mrflow_b200.sharding.PeerMailbox.check) before using results.
  * A mailbox is mrf_mailbox_bytes(world) bytes from mrf_peer_alloc, zeroed once, opened by every peer
  * (mrf_peer_open); mailboxes_host[world] are this process's pointers to all of them (its own at [rank]).
  * call_index must count the collectives 0, 1, 2, ... identically on every rank.  inout: nwords <= 256

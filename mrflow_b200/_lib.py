@@ -14,6 +14,7 @@ RHO = {"lorentzian": 0, "charbonnier": 1, "geman_mcclure": 2, "quadratic": 3, "l
 LAYOUT = {"LHW_F32": 0, "HWL_I32": 1}
 VARIANT = {"staged": 0, "gather": 1, "staged_occ2": 16, "gather_occ2": 17}
 SELECT_HIST_OFFSET = 64
+SELECT13_BINS, SELECT13_HIST_OFFSET, SELECT13_SUCC_OFFSET, SELECT13_PASSES = 8192, 256, 24, 5
 
 
 class CostVolParams(C.Structure):
@@ -74,6 +75,7 @@ SIGNATURES = {
     "mrf_peer_open": (_I, [C.POINTER(C.c_ubyte), C.POINTER(C.c_void_p)]),
     "mrf_peer_close": (_I, [_P]),
     "mrf_peer_free": (_I, [_P]),
+    "mrf_download_rows": (_I, [_P, _P, _Z, _I, _I, _I, _I, _I, _P]),
     "mrf_mailbox_bytes": (_Z, [_I]),
     "mrf_mailbox_allreduce": (_I, [_P, C.POINTER(C.c_void_p), _I, _I, C.c_longlong, _I, _P, _I, _P]),
     "mrf_abs_deviation_f64": (_I, [_P, _Z, _D, _P, _P]),
@@ -84,15 +86,16 @@ SIGNATURES = {
     "mrf_cost_volume": (_I, [C.POINTER(CostVolParams), _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "mrf_front_scratch_bytes": (_Z, []),
     "mrf_cost_volume_front": (_I, [C.POINTER(FrontParams), _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
-    "mrf_front_parallax_band": (_I, [C.POINTER(FrontParams), _P, _P, _P, _P, _P, _P, _P, _P, _P]),
-    "mrf_front_candidates_band": (_I, [C.POINTER(FrontParams), _P, _P, _P, _P, _P, _P, _P]),
-    "mrf_front_structures_band": (_I, [C.POINTER(FrontParams), _P, _P, _P, _P, _P, _P, _P, _P]),
-    "mrf_select_begin_dev": (_I, [_P, _P, _P]),
-    "mrf_select_hist_dev": (_I, [_P, _P, _Z, _P, _P]),
-    "mrf_select_successor_dev": (_I, [_P, _P, _Z, _P, _P]),
-    "mrf_select_median_state": (_I, [_P, _P, _P]),
+    "mrf_front_mu_whole": (_I, [C.POINTER(FrontParams), _P, _P, _P]),
+    "mrf_front_parallax_band": (_I, [C.POINTER(FrontParams), _P, _P, _P, _P, _P, _P, _P, _P]),
+    "mrf_front_candidates_band": (_I, [C.POINTER(FrontParams), _P, _P, _P, _P, _P, _P, _P, _P]),
+    "mrf_front_structures_band": (_I, [C.POINTER(FrontParams), _P, _P, _P, _P, _P, _P, _P, _P, _I, _P, _P]),
+    "mrf_select13_begin": (_I, [_P, _P]),
+    "mrf_select13_hist_dev": (_I, [_P, _P, _Z, _I, _P, _P]),
+    "mrf_select13_successor_dev": (_I, [_P, _P, _Z, _P, _P]),
+    "mrf_select13_median": (_I, [_P, _P, _I, _P, _P]),
     "mrf_select_median_dev": (_I, [_P, _P, _Z, _P, _P, _P]),
-    "mrf_label_range_dev": (_I, [_P, _I, _P]),
+    "mrf_label_range_dev": (_I, [_P, _I, _P, _I, _P]),
     "mrf_flow_consistency": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _D, _P, _P, _P, _P]),
     "mrf_image_weights_scratch_bytes": (_Z, []),
     "mrf_image_weights": (_I, [_P, _I, _I, _I, _P, _P, _P, _P, _P, _P]),

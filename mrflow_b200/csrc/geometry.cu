@@ -3,7 +3,7 @@
 // with a few dozen fp64 flops per pixel.  Arithmetic follows the reference operation by
 // operation (compiled with -fmad=false) so results are bit-identical wherever the reference only
 // uses IEEE +,-,*,/,sqrt; transcendental functions (atan2, sin, exp, I0e) agree to a few ulp.
-#include "common.cuh"
+#include "select13.cuh"
 #include <stdarg.h>
 #include <math.h>
 
@@ -383,6 +383,13 @@ static inline unsigned grid_for(long long n, int threads = 256) {
 // Fused forms of the pre-pass for the device-resident path (same per-pixel arithmetic as the
 // kernels above; fewer, fatter launches).
 constexpr int kFrontBlocks = 592;   // 4 x 148
+// blocks of the candidates kernel: each zeroes and flushes an 8192-bin shared histogram, so two fat blocks
+// per SM at most
+static inline unsigned front_cand_blocks(long long n) {
+  long long b = (n + 1023) / 1024;
+  if (b > 2 * kSMs) b = 2 * kSMs;
+  return (unsigned)(b < 1 ? 1 : b);
+}
 
 // both frames: residual flow -> parallax (a1 + a2) and the block partial sums behind mu
 __global__ void __launch_bounds__(256)
@@ -428,6 +435,85 @@ k_front_mu(const double* __restrict__ partial, int nblocks, double n_px, double*
   }
 }
 
+// mu of both frames from the 2 x kRedBlocks block partials, in k_front_mu's summation tree (32 warp sums of
+// 32 consecutive partials each, then one warp over those), evaluated by a 256-thread block -- every block
+// of the candidates kernel gets the same bits without a separate launch
+__device__ __forceinline__ void front_mu_from_partials(const double* __restrict__ partial, double n_px, double* s_mu,
+                                                       double* sh) {
+  static_assert(kRedBlocks == 1024, "summation tree written for 1024 partials");
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  for (int f = 0; f < 2; ++f) {
+    for (int g = wid; g < 32; g += 8) {
+      double v = partial[f * kRedBlocks + 32 * g + lane];
+      for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+      if (lane == 0) sh[g] = v;
+    }
+    __syncthreads();
+    if (wid == 0) {
+      double v = sh[lane];
+      for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+      if (lane == 0) s_mu[f] = v / n_px;
+    }
+    __syncthreads();
+  }
+}
+
+// pipeline/compute_structure.py:172-221 with B_fwd fixed (build_cost_volume.py:116-131): valid pixels,
+// the compacted candidate ratios template/target, and -- fused -- the first pass of the exact median over
+// them (select13.cuh).  partial != nullptr: mu is formed here from the parallax kernel's block partials
+// (whole frame on one GPU) and block 0 writes it to the state; otherwise mu is read from the state.
+__global__ void __launch_bounds__(256)
+k_front_candidates13(const double* __restrict__ par0, const double* __restrict__ par1,
+                     const uint8_t* __restrict__ p_thr, int rows, int w, int y0, Pt2 q0, Pt2 q1, double B_fwd,
+                     double* __restrict__ cand, int* __restrict__ count, double* __restrict__ st,
+                     const double* __restrict__ partial, double n_px, void* sel) {
+  __shared__ unsigned int sh[kS13Bins];
+  __shared__ double s_mu[2];
+  __shared__ double s_red[32];
+  s13_zero(sh);
+  if (partial) {
+    front_mu_from_partials(partial, n_px, s_mu, s_red);
+    if (blockIdx.x == 0 && threadIdx.x == 0) { st[MRF_STATE_MU] = s_mu[0]; st[MRF_STATE_MU + 1] = s_mu[1]; }
+  } else {
+    if (threadIdx.x < 2) s_mu[threadIdx.x] = st[MRF_STATE_MU + threadIdx.x];
+  }
+  __syncthreads();
+  const double mu0 = s_mu[0], mu1 = s_mu[1];
+  const long long n = (long long)rows * w;
+  for (long long i0 = blockIdx.x * (long long)blockDim.x; i0 < n; i0 += (long long)gridDim.x * blockDim.x) {
+    const long long i = i0 + threadIdx.x;
+    bool valid = false;
+    double val = 0.0;
+    if (i < n) {
+      const double p0 = par0[i], p1 = par1[i];
+      valid = (fabs(p0) > 0.1) && (fabs(p1) > 0.1) && (p_thr[i] != 0);
+      if (valid) {
+        const int yl = (int)(i / w);
+        const int x = (int)(i - (long long)yl * w);
+        const int y = yl + y0;
+        // :209-219; dists_normed = foe_dists/mu with foe_dists from flow2parallax (q - x)
+        const double fx0 = q0.x - (double)x, fy0 = q0.y - (double)y;
+        const double dn0 = sqrt(fx0 * fx0 + fy0 * fy0) / mu0;
+        const double fx1 = q1.x - (double)x, fy1 = q1.y - (double)y;
+        const double dn1 = sqrt(fx1 * fx1 + fy1 * fy1) / mu1;
+        const double target = p1 / (B_fwd * (p1 / mu1 - dn1));
+        const double templ = mu1 / mu0 * p0 / (p0 / mu0 - dn0);
+        val = templ / target;
+      }
+    }
+    // warp-aggregated compaction (order is irrelevant for order statistics)
+    const unsigned m = __ballot_sync(0xffffffffu, valid);
+    const int lane = threadIdx.x & 31;
+    int base = 0;
+    if (lane == 0 && m) base = atomicAdd(count, __popc(m));
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (valid) cand[base + __popc(m & ((1u << lane) - 1u))] = val;
+    s13_count(sh, valid, (unsigned)(order_key(val) >> s13_shift(0)));
+  }
+  __syncthreads();
+  s13_flush(sh, s13_hist(sel, 0));
+}
+
 // both frames: parallax -> normed structure (a3) and block partial min / max / NaN of the
 // range-masked structure (build_cost_volume.py:154-169)
 struct Box4 { int x0, x1, y0, y1, on; };
@@ -435,12 +521,14 @@ __global__ void __launch_bounds__(256)
 k_front_structures(const double* __restrict__ par0, const double* __restrict__ par1, int rows, int w, int y0, Pt2 q0,
                    Pt2 q1, double B_fwd, const uint8_t* __restrict__ zero_mask, Box4 b0, Box4 b1,
                    double* __restrict__ S0, double* __restrict__ S1, double* __restrict__ st,
-                   double* __restrict__ part) {
+                   double* __restrict__ part, const void* __restrict__ sel,
+                   const unsigned long long* __restrict__ gathered, int world) {
   __shared__ double smin[2][8], smax[2][8];
   __shared__ int snan[2][8];
   const long long n = (long long)rows * w;
-  const double mu0 = st[MRF_STATE_MU], mu1 = st[MRF_STATE_MU + 1], B0 = st[MRF_STATE_B];
-  if (blockIdx.x == 0 && threadIdx.x == 0) st[MRF_STATE_B + 1] = B_fwd;
+  // B_b = median(template / target)  compute_structure.py:221 -- the same bits in every block
+  const double mu0 = st[MRF_STATE_MU], mu1 = st[MRF_STATE_MU + 1], B0 = s13_median(sel, gathered, world);
+  if (blockIdx.x == 0 && threadIdx.x == 0) { st[MRF_STATE_B] = B0; st[MRF_STATE_B + 1] = B_fwd; }
   double lo[2] = {INFINITY, INFINITY}, hi[2] = {-INFINITY, -INFINITY};
   int nan[2] = {0, 0};
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n;
@@ -694,10 +782,6 @@ int mrf_abs_deviation_f64(const double* x, size_t n, double c, double* out, mrf_
 // (pipeline/build_cost_volume.py:78-192 with the live conventions of compute_structure.py): no host
 // synchronisation between the flows and the label set, so the whole step can be captured in a CUDA
 // graph.  Launch sequence only; the arithmetic is that of the kernels above.
-int mrf_select_median_dev(const double* keys, const int* n_dev, size_t capacity, double* out_median, void* scratch,
-                          mrf_stream_t stream);
-int mrf_label_range_dev(double* dev_state, int n_labels, mrf_stream_t stream);
-
 size_t mrf_front_scratch_bytes(void) { return sizeof(double) * 4096 + mrf_select_scratch_bytes(0) + 64; }
 
 int mrf_cost_volume_front(const mrf_front_params* p, const float* u0, const float* v0, const float* u1,
@@ -708,26 +792,26 @@ int mrf_cost_volume_front(const mrf_front_params* p, const float* u0, const floa
   MRF_CHECK_ARG(p->rows > 0 && p->w > 0 && p->y0 == 0 && p->frame_h == p->rows);   /* whole frame on one GPU */
   MRF_CHECK_ARG(p->n_labels >= 2 && p->n_labels <= 256);
   const long long n = (long long)p->rows * p->w;
-  const unsigned g = grid_for(n);
   long long fb = (n + 255) / 256;
   if (fb > kFrontBlocks) fb = kFrontBlocks;
-  double* partial = (double*)scratch;                                    // 2 * fb doubles, then 6 * fb
+  double* partial = (double*)scratch;                                    // 2 * kRedBlocks doubles, then 6 * fb
+  void* sel = (char*)scratch + 4096 * sizeof(double);
+  cudaError_t e = cudaMemsetAsync(sel, 0, kS13Bytes, S(stream));
+  if (e == cudaSuccess) e = cudaMemsetAsync(count, 0, sizeof(int), S(stream));
+  if (e != cudaSuccess) return fail((int)e, "front: %s", cudaGetErrorString(e));
   // same grid and summation tree as mrf_epipole_dist_sum, so mu has the same bits on both routes
   k_front_parallax<<<kRedBlocks, kRedThreads, 0, S(stream)>>>(u0, v0, u1, v1, p->rows, p->w, 0, mat3(p->Hinv0),
                                                               mat3(p->Hinv1), pt2(p->q0), pt2(p->q1), par0, par1, partial);
   int rc = check_launch("front/parallax");
   if (rc) return rc;
-  k_front_mu<<<1, kRedBlocks, 0, S(stream)>>>(partial, kRedBlocks, (double)n, dev_state);
-  rc = check_launch("front/mu");
-  if (rc) return rc;
-  // pv and the candidate ratios of :209-219 with B_fwd fixed (build_cost_volume.py:116-131)
-  cudaError_t e = cudaMemsetAsync(count, 0, sizeof(int), S(stream));
-  if (e != cudaSuccess) return fail((int)e, "front: %s", cudaGetErrorString(e));
-  k_structure_candidates<<<g, 256, 0, S(stream)>>>(par0, par1, rigid_mask, p->rows, p->w, 0, pt2(p->q0), pt2(p->q1), 0.0,
-                                                   0.0, p->B_fwd, 2, nullptr, cand, count, dev_state);
+  // mu, pv and the candidate ratios of :209-219 with B_fwd fixed (build_cost_volume.py:116-131), first select pass
+  k_front_candidates13<<<front_cand_blocks(n), 256, 0, S(stream)>>>(par0, par1, rigid_mask, p->rows, p->w, 0, pt2(p->q0),
+                                                                    pt2(p->q1), p->B_fwd, cand, count, dev_state, partial,
+                                                                    (double)n, sel);
   rc = check_launch("front/candidates");
   if (rc) return rc;
-  rc = mrf_select_median_dev(cand, count, (size_t)n, dev_state + MRF_STATE_B, (char*)scratch + 4096 * sizeof(double), stream);
+  for (int pass = 1; pass < kS13Passes && !rc; ++pass) rc = mrf_select13_hist_dev(cand, count, (size_t)n, pass, sel, stream);
+  if (!rc) rc = mrf_select13_successor_dev(cand, count, (size_t)n, sel, stream);
   if (rc) return rc;
   Box4 bx[2];
   for (int f = 0; f < 2; ++f) {
@@ -735,7 +819,7 @@ int mrf_cost_volume_front(const mrf_front_params* p, const float* u0, const floa
     bx[f].on = p->have_box[f];
   }
   k_front_structures<<<(unsigned)fb, 256, 0, S(stream)>>>(par0, par1, p->rows, p->w, 0, pt2(p->q0), pt2(p->q1), p->B_fwd,
-                                                          zero_mask, bx[0], bx[1], S0, S1, dev_state, partial);
+                                                          zero_mask, bx[0], bx[1], S0, S1, dev_state, partial, sel, nullptr, 0);
   rc = check_launch("front/structures");
   if (rc) return rc;
   k_front_labels<<<1, 256, 0, S(stream)>>>(partial, (int)fb, dev_state, p->n_labels);
@@ -746,36 +830,48 @@ int mrf_cost_volume_front(const mrf_front_params* p, const float* u0, const floa
 // ---- the same pre-pass in pieces for row bands: the caller all-reduces (NCCL, on the stream) between
 // the pieces -- the two sums behind mu, the candidate count, the 256-bin histograms of the distributed
 // median, and the range min / max -- so there is no host round trip either.
-int mrf_front_parallax_band(const mrf_front_params* p, const float* u0, const float* v0, const float* u1,
-                            const float* v1, double* par0, double* par1, double* sums2, void* scratch,
-                            mrf_stream_t stream) {
-  MRF_CHECK_ARG(p && u0 && v0 && u1 && v1 && par0 && par1 && sums2 && scratch && p->rows > 0 && p->w > 0);
+int mrf_front_mu_whole(const mrf_front_params* p, double* dev_state, void* scratch, mrf_stream_t stream) {
+  MRF_CHECK_ARG(p && dev_state && scratch && p->frame_h > 0 && p->w > 0);
   double* partial = (double*)scratch;
+  for (int f = 0; f < 2; ++f) {
+    k_dist_sum_partial<<<kRedBlocks, kRedThreads, 0, S(stream)>>>(p->frame_h, p->w, 0, pt2(f ? p->q1 : p->q0),
+                                                                  partial + f * kRedBlocks);
+    const int rc = check_launch("front_mu_whole/partial");
+    if (rc) return rc;
+  }
+  k_front_mu<<<1, kRedBlocks, 0, S(stream)>>>(partial, kRedBlocks, (double)p->frame_h * (double)p->w, dev_state);
+  return check_launch("front_mu_whole/mu");
+}
+
+int mrf_front_parallax_band(const mrf_front_params* p, const float* u0, const float* v0, const float* u1,
+                            const float* v1, double* par0, double* par1, void* scratch, mrf_stream_t stream) {
+  MRF_CHECK_ARG(p && u0 && v0 && u1 && v1 && par0 && par1 && scratch && p->rows > 0 && p->w > 0);
+  double* partial = (double*)scratch;        // the band's own distance sums: not used (mu comes from mrf_front_mu_whole)
   k_front_parallax<<<kRedBlocks, kRedThreads, 0, S(stream)>>>(u0, v0, u1, v1, p->rows, p->w, p->y0, mat3(p->Hinv0),
                                                               mat3(p->Hinv1), pt2(p->q0), pt2(p->q1), par0, par1, partial);
-  int rc = check_launch("front_band/parallax");
-  if (rc) return rc;
-  // sums2 is written at the MU slots of a 2-word pseudo state: pass sums2 - MRF_STATE_MU with n_px = 0
-  k_front_mu<<<1, kRedBlocks, 0, S(stream)>>>(partial, kRedBlocks, 0.0, sums2 - MRF_STATE_MU);
-  return check_launch("front_band/sums");
+  return check_launch("front_band/parallax");
 }
 
 int mrf_front_candidates_band(const mrf_front_params* p, const double* par0, const double* par1,
-                              const uint8_t* rigid_mask, const double* dev_state, double* cand, int* count,
-                              mrf_stream_t stream) {
-  MRF_CHECK_ARG(p && par0 && par1 && rigid_mask && dev_state && cand && count);
-  cudaError_t e = cudaMemsetAsync(count, 0, sizeof(int), S(stream));
+                              const uint8_t* rigid_mask, double* dev_state, double* cand, int* count,
+                              void* select_scratch, mrf_stream_t stream) {
+  MRF_CHECK_ARG(p && par0 && par1 && rigid_mask && dev_state && cand && count && select_scratch);
+  cudaError_t e = cudaMemsetAsync(select_scratch, 0, kS13Bytes, S(stream));
+  if (e == cudaSuccess) e = cudaMemsetAsync(count, 0, sizeof(int), S(stream));
   if (e != cudaSuccess) return fail((int)e, "front_band: %s", cudaGetErrorString(e));
-  k_structure_candidates<<<grid_for((long long)p->rows * p->w), 256, 0, S(stream)>>>(
-      par0, par1, rigid_mask, p->rows, p->w, p->y0, pt2(p->q0), pt2(p->q1), 0.0, 0.0, p->B_fwd, 2, nullptr, cand, count,
-      dev_state);
+  const long long n = (long long)p->rows * p->w;
+  k_front_candidates13<<<front_cand_blocks(n), 256, 0, S(stream)>>>(par0, par1, rigid_mask, p->rows, p->w, p->y0,
+                                                                    pt2(p->q0), pt2(p->q1), p->B_fwd, cand, count,
+                                                                    dev_state, nullptr, 0.0, select_scratch);
   return check_launch("front_band/candidates");
 }
 
 int mrf_front_structures_band(const mrf_front_params* p, const double* par0, const double* par1,
-                              const uint8_t* zero_mask, double* S0, double* S1, double* dev_state, void* scratch,
-                              mrf_stream_t stream) {
-  MRF_CHECK_ARG(p && par0 && par1 && S0 && S1 && dev_state && scratch);
+                              const uint8_t* zero_mask, double* S0, double* S1, double* dev_state,
+                              const void* select_scratch, const unsigned long long* gathered_successor, int world,
+                              void* scratch, mrf_stream_t stream) {
+  MRF_CHECK_ARG(p && par0 && par1 && S0 && S1 && dev_state && scratch && select_scratch);
+  MRF_CHECK_ARG(!gathered_successor || world >= 1);
   const long long n = (long long)p->rows * p->w;
   long long fb = (n + 255) / 256;
   if (fb > kFrontBlocks) fb = kFrontBlocks;
@@ -786,7 +882,8 @@ int mrf_front_structures_band(const mrf_front_params* p, const double* par0, con
   }
   double* partial = (double*)scratch;
   k_front_structures<<<(unsigned)fb, 256, 0, S(stream)>>>(par0, par1, p->rows, p->w, p->y0, pt2(p->q0), pt2(p->q1),
-                                                          p->B_fwd, zero_mask, bx[0], bx[1], S0, S1, dev_state, partial);
+                                                          p->B_fwd, zero_mask, bx[0], bx[1], S0, S1, dev_state, partial,
+                                                          select_scratch, gathered_successor, world);
   int rc = check_launch("front_band/structures");
   if (rc) return rc;
   k_front_minmax<<<1, 256, 0, S(stream)>>>(partial, (int)fb, dev_state);

@@ -15,7 +15,8 @@ namespace mrf {
 constexpr int kMboxSlots = 16;           // consecutive collectives use consecutive slots (a rank is at most one ahead)
 constexpr int kMboxWords = 256;
 constexpr int kMboxMaxWorld = 16;
-constexpr long long kMboxSpinLimit = 3000000ll;       // a second or two of polling: a lost peer becomes an error, not a hang
+constexpr unsigned long long kMboxTimeoutNs = 20000000000ull;   // 20 s of wall time (%globaltimer): a lost peer becomes an error, not a hang;
+                                                                // a peer that is merely late (lazy module load, IPC mapping, host hiccup) is waited for
 
 struct PeerPtrs { unsigned long long* p[kMboxMaxWorld]; };
 
@@ -27,6 +28,11 @@ __device__ __forceinline__ unsigned long long ld_relaxed_sys(const unsigned long
   unsigned long long v;
   asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
   return v;
+}
+__device__ __forceinline__ unsigned long long global_timer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
 }
 __device__ __forceinline__ void st_relaxed_sys(unsigned long long* p, unsigned long long v) {
   asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
@@ -49,11 +55,16 @@ k_mbox_allreduce(unsigned long long* local, PeerPtrs peers, int world, int rank,
     for (int r = 0; r < world; ++r) {
       const unsigned long long* src = local + mbox_data_off(world, slot, r) + 2 * (size_t)t;
       unsigned long long a, b;
-      long long spins = 0;
+      unsigned int spins = 0;
+      unsigned long long t0 = 0;
       while (true) {
         a = ld_relaxed_sys(src); b = ld_relaxed_sys(src + 1);
         if ((a >> 32) == tag && (b >> 32) == tag) break;
-        if (++spins > kMboxSpinLimit) { s_timeout = 1; break; }
+        if ((++spins & 0x3ffu) == 0) {                       // look at the clock every 1024 polls
+          const unsigned long long now = global_timer_ns();
+          if (t0 == 0) t0 = now;
+          else if (now - t0 > kMboxTimeoutNs) { s_timeout = 1; break; }
+        }
       }
       const unsigned long long v = (a & 0xffffffffull) | (b << 32);
       if (r == 0) { acc = v; continue; }
@@ -69,7 +80,12 @@ k_mbox_allreduce(unsigned long long* local, PeerPtrs peers, int world, int rank,
     inout[t] = acc;
   }
   __syncthreads();
-  if (t == 0 && s_timeout) local[mbox_status_off(world)] = (unsigned long long)tag;   // non-zero status = the call that gave up
+  if (s_timeout) {
+    // a peer never arrived: poison the WHOLE result (all ones = NaN as fp64, the largest key as uint64) so that
+    // nothing downstream can mistake it for data, and record the call in the status word
+    if (t < nwords) inout[t] = 0xFFFFFFFFFFFFFFFFull;
+    if (t == 0) local[mbox_status_off(world)] = (unsigned long long)tag;             // non-zero status = the call that gave up
+  }
 }
 
 }  // namespace mrf

@@ -126,6 +126,20 @@ int mrf_peer_alloc(size_t bytes, void** ptr_out, unsigned char* handle64_out) {
   return 0;
 }
 
+// Rows [y0, y0 + rows) of every label plane of a device [L][frame_h][w] volume into the same rows of a host
+// volume of the same shape (pinned memory): one pitched DMA (cudaMemcpy2DAsync), so a row chunk can travel
+// over PCIe while the next chunk is being computed.
+int mrf_download_rows(void* dst_host, const void* src_dev, size_t elem_bytes, int n_planes, int frame_h, int w, int y0,
+                      int rows, mrf_stream_t stream) {
+  MRF_CHECK_ARG(dst_host && src_dev && elem_bytes > 0 && n_planes > 0 && frame_h > 0 && w > 0 && y0 >= 0 && rows > 0 &&
+                y0 + rows <= frame_h);
+  const size_t pitch = (size_t)frame_h * w * elem_bytes, off = (size_t)y0 * w * elem_bytes, width = (size_t)rows * w * elem_bytes;
+  cudaError_t e = cudaMemcpy2DAsync((char*)dst_host + off, pitch, (const char*)src_dev + off, pitch, width, (size_t)n_planes,
+                                    cudaMemcpyDeviceToHost, S(stream));
+  if (e != cudaSuccess) return fail((int)e, "mrf_download_rows: %s", cudaGetErrorString(e));
+  return 0;
+}
+
 int mrf_peer_open(const unsigned char* handle64, void** ptr_out) {
   MRF_CHECK_ARG(handle64 && ptr_out);
   cudaIpcMemHandle_t h;

@@ -12,7 +12,7 @@
 // pick are separate entry points so that a multi-GPU caller can all-reduce the 256-bin histogram
 // (2 KB over NCCL) between them -- the exchange step of SURVEY.md section 8e.  NaNs order last
 // (numpy's sort order) and are counted, since numpy's median is NaN when any is present.
-#include "common.cuh"
+#include "select13.cuh"
 
 namespace mrf {
 
@@ -21,17 +21,6 @@ namespace mrf {
 constexpr int kStWords = 8;
 constexpr int kMemoWords = 32;        // (prefix, rank) after each pass of the fused select
 constexpr int kHistBins = 256;
-
-__device__ __forceinline__ unsigned long long order_key(double v) {
-  if (v != v) return 0xFFFFFFFFFFFFFFFFull;                 // every NaN sorts last
-  const unsigned long long b = (unsigned long long)__double_as_longlong(v);
-  return (b & 0x8000000000000000ull) ? ~b : (b | 0x8000000000000000ull);
-}
-__device__ __forceinline__ double key_value(unsigned long long k) {
-  if (k == 0xFFFFFFFFFFFFFFFFull) return __longlong_as_double(0x7FF8000000000000ll);
-  const unsigned long long b = (k & 0x8000000000000000ull) ? (k & 0x7FFFFFFFFFFFFFFFull) : ~k;
-  return __longlong_as_double((long long)b);
-}
 
 __global__ void __launch_bounds__(256)
 k_select_init(unsigned long long* st, unsigned long long k, unsigned long long* hist, const int* n_dev) {
@@ -162,72 +151,25 @@ __global__ void k_select_result(const unsigned long long* __restrict__ st, unsig
   out3[2] = (double)st[3];
 }
 
-// Device-median path: one launch per pass.  Every block first resolves the previous pass's byte from
-// that pass's (complete) histogram -- 256 bins, one round trip to L2 plus a warp scan, redundantly in every
-// block -- then histograms the next byte; hist is [8][256], zeroed up front.  Block 0 memoises the running
-// (prefix, rank) after each pass so that later passes resolve one byte, not all previous ones.
-__device__ __forceinline__ void resolve_prefix(const unsigned long long* __restrict__ hist_all,
-                                               const unsigned long long* __restrict__ memo, int upto,
-                                               unsigned long long k, unsigned long long& prefix,
-                                               unsigned long long& k_rem) {
-  // executed by warp 0 of the block; memo[2*p], memo[2*p+1] = (prefix, rank) after p passes (p >= 1)
-  const int lane = threadIdx.x & 31;
-  prefix = 0; k_rem = k;
-  if (upto == 0) return;
-  if (upto >= 2) { prefix = memo[2 * (upto - 1)]; k_rem = memo[2 * (upto - 1) + 1]; }
-  {
-    const int p = upto - 1;
-    const unsigned long long* h = hist_all + p * kHistBins;
-    // each lane owns 8 consecutive bins
-    unsigned long long c[8], tot = 0;
-#pragma unroll
-    for (int j = 0; j < 8; ++j) { c[j] = h[lane * 8 + j]; tot += c[j]; }
-    unsigned long long incl = tot;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      const unsigned long long v = __shfl_up_sync(0xffffffffu, incl, o);
-      if (lane >= o) incl += v;
-    }
-    const unsigned long long excl = incl - tot;
-    // the lane whose range [excl, incl) holds k_rem (last lane catches any remainder)
-    const bool mine = (k_rem >= excl && k_rem < incl) || (lane == 31 && k_rem >= incl);
-    const unsigned ball = __ballot_sync(0xffffffffu, mine);
-    const int owner = ball ? (__ffs(ball) - 1) : 31;
-    int b = 0; unsigned long long kr = 0;
-    if (lane == owner) {
-      kr = k_rem - excl;
-      for (b = 0; b < 7; ++b) { if (kr < c[b]) break; kr -= c[b]; }
-      b += lane * 8;
-    }
-    b = __shfl_sync(0xffffffffu, b, owner);
-    kr = __shfl_sync(0xffffffffu, kr, owner);
-    prefix |= ((unsigned long long)b) << (56 - 8 * p);
-    k_rem = kr;
-  }
-}
-
+// ------------------------------------------------------------------------------ five-pass select
+// (select13.cuh).  Pass `pass` (0..4): resolve the previous digit, histogram this one.
 __global__ void __launch_bounds__(256)
-k_select_hist_fused(const double* __restrict__ keys, const int* __restrict__ n_dev, int pass,
-                    unsigned long long* __restrict__ st, unsigned long long* __restrict__ hist_all,
-                    unsigned long long* __restrict__ memo) {
-  __shared__ unsigned int sh[kHistBins];
-  __shared__ unsigned long long s_prefix;
+k_s13_hist(const double* __restrict__ keys, const int* __restrict__ n_dev, int pass, void* scratch) {
+  __shared__ unsigned int sh[kS13Bins];
+  __shared__ unsigned long long s_tmp[16];
   const size_t n = (size_t)max(*n_dev, 0);
-  sh[threadIdx.x] = 0;
-  if (threadIdx.x < 32) {
-    unsigned long long prefix, k_rem;
-    resolve_prefix(hist_all, memo, pass, n ? (unsigned long long)((n - 1) / 2) : 0ull, prefix, k_rem);
-    if (threadIdx.x == 0) {
-      s_prefix = prefix;
-      if (blockIdx.x == 0 && pass >= 1) { memo[2 * pass] = prefix; memo[2 * pass + 1] = k_rem; }
+  s13_zero(sh);
+  unsigned long long prefix = 0, k_rem = 0, n_total = 0;
+  if (pass >= 1) {
+    s13_resolve(scratch, pass, prefix, k_rem, n_total, s_tmp);
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+      unsigned long long* memo = s13_memo(scratch);
+      memo[3 * pass] = prefix; memo[3 * pass + 1] = k_rem; memo[3 * pass + 2] = n_total;
     }
   }
   __syncthreads();
-  const unsigned long long prefix = s_prefix;
-  const int shift = 56 - 8 * pass;
-  const unsigned long long himask = pass == 0 ? 0ull : (~0ull << (shift + 8));
-  // warp-aggregated shared atomics: the leading bytes of real data are concentrated in a few bins, so the
-  // lanes of a warp that hit the same bin send one atomic with their count
+  const int shift = s13_shift(pass);
+  const unsigned long long himask = s13_himask(pass);
   const size_t stride = (size_t)gridDim.x * blockDim.x;
   const size_t warp_first = blockIdx.x * (size_t)blockDim.x + threadIdx.x - (threadIdx.x & 31);
   constexpr int U = 4;                                   // keys per lane whose loads are issued together
@@ -241,34 +183,23 @@ k_select_hist_fused(const double* __restrict__ keys, const int* __restrict__ n_d
 #pragma unroll
     for (int u = 0; u < U; ++u) {
       const size_t i = base + u * stride + (threadIdx.x & 31);
-      const bool act = (i < n) && ((kk[u] & himask) == prefix);
-      const unsigned bin = (unsigned)((kk[u] >> shift) & 0xFF);
-      const unsigned amask = __ballot_sync(0xffffffffu, act);
-      if (act) {
-        const unsigned peers = __match_any_sync(amask, bin);
-        if ((threadIdx.x & 31) == (unsigned)(__ffs(peers) - 1)) atomicAdd(&sh[bin], (unsigned)__popc(peers));
-      }
+      s13_count(sh, (i < n) && ((kk[u] & himask) == prefix), (unsigned)((kk[u] >> shift) & (kS13Bins - 1)));
     }
   }
   __syncthreads();
-  const unsigned int c = sh[threadIdx.x];
-  if (c) atomicAdd(&hist_all[pass * kHistBins + threadIdx.x], (unsigned long long)c);
+  s13_flush(sh, s13_hist(scratch, pass));
 }
 
-// successor pass: resolves the last byte, then counts keys <= kth / NaNs / min key above
+// successor pass: resolves the last digit, then counts keys <= kth / NaNs / the smallest key above
 __global__ void __launch_bounds__(256)
-k_select_successor_fused(const double* __restrict__ keys, const int* __restrict__ n_dev,
-                         unsigned long long* __restrict__ st, const unsigned long long* __restrict__ hist_all,
-                         const unsigned long long* __restrict__ memo) {
-  __shared__ unsigned long long s_kth;
+k_s13_successor(const double* __restrict__ keys, const int* __restrict__ n_dev, void* scratch) {
+  __shared__ unsigned long long s_tmp[16];
+  __shared__ unsigned long long s_red[3][8];
   const size_t n = (size_t)max(*n_dev, 0);
-  if (threadIdx.x < 32) {
-    unsigned long long prefix, k_rem;
-    resolve_prefix(hist_all, memo, 8, n ? (unsigned long long)((n - 1) / 2) : 0ull, prefix, k_rem);
-    if (threadIdx.x == 0) { s_kth = prefix; if (blockIdx.x == 0) { st[0] = prefix; st[6] = (unsigned long long)n; } }
-  }
-  __syncthreads();
-  const unsigned long long kth = s_kth;
+  unsigned long long kth, k_rem, n_total;
+  s13_resolve(scratch, kS13Passes, kth, k_rem, n_total, s_tmp);
+  unsigned long long* st = s13_st(scratch);
+  if (blockIdx.x == 0 && threadIdx.x == 0) { st[0] = kth; st[6] = n_total; }
   unsigned long long cnt_le = 0, nan = 0, min_gt = 0xFFFFFFFFFFFFFFFFull;
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
     const double v = keys[i];
@@ -282,8 +213,6 @@ k_select_successor_fused(const double* __restrict__ keys, const int* __restrict_
     const unsigned long long m = __shfl_down_sync(0xffffffffu, min_gt, o);
     min_gt = m < min_gt ? m : min_gt;
   }
-  // one set of atomics per block, not per warp
-  __shared__ unsigned long long s_red[3][8];
   if ((threadIdx.x & 31) == 0) { s_red[0][threadIdx.x >> 5] = cnt_le; s_red[1][threadIdx.x >> 5] = nan; s_red[2][threadIdx.x >> 5] = min_gt; }
   __syncthreads();
   if (threadIdx.x == 0) {
@@ -291,14 +220,13 @@ k_select_successor_fused(const double* __restrict__ keys, const int* __restrict_
     for (int k = 0; k < 8; ++k) { cnt_le += s_red[0][k]; nan += s_red[1][k]; min_gt = s_red[2][k] < min_gt ? s_red[2][k] : min_gt; }
     if (cnt_le) atomicAdd(&st[4], cnt_le);
     if (nan) atomicAdd(&st[3], nan);
-    if (min_gt != 0xFFFFFFFFFFFFFFFFull) atomicMin(&st[5], min_gt);
+    if (min_gt != 0xFFFFFFFFFFFFFFFFull) atomicMax(&st[5], ~min_gt);     // stored inverted: zeroed scratch = none
   }
 }
 
-__global__ void __launch_bounds__(256)
-k_select_init_fused(unsigned long long* st, unsigned long long* hist_all) {
-  if (threadIdx.x < kStWords) st[threadIdx.x] = (threadIdx.x == 5) ? 0xFFFFFFFFFFFFFFFFull : 0ull;
-  for (int i = threadIdx.x; i < 8 * kHistBins; i += blockDim.x) hist_all[i] = 0;
+__global__ void k_s13_median(const void* __restrict__ scratch, const unsigned long long* __restrict__ gathered, int world,
+                             double* __restrict__ out) {
+  out[0] = s13_median(scratch, gathered, world);
 }
 
 // numpy.median from the finished selection state (n in st[6]): middle element, mean of the two
@@ -316,13 +244,29 @@ __global__ void k_select_median(const unsigned long long* __restrict__ st, doubl
 // np.linspace(1.5*min, 1.5*max, L) over both frames' (min, max) in the state
 // (pipeline/build_cost_volume.py:190-192; numpy/_core/function_base.py: step = delta/div,
 // y = arange*step + start, or arange/div*delta + start when step == 0, last element = stop)
-__global__ void k_label_range(double* __restrict__ st, int L) {
+// Row bands pass the six words MRF_STATE_MINMAX .. MRF_STATE_NANFLAG+1 of all ranks (`gathered` = [world][6]);
+// their min / max / NaN flags are combined here and written back to the state.
+__global__ void k_label_range(double* __restrict__ st, int L, const double* __restrict__ gathered, int world) {
   const int i = threadIdx.x;
+  double lo0 = st[MRF_STATE_MINMAX], hi0 = st[MRF_STATE_MINMAX + 1];
+  double lo1 = st[MRF_STATE_MINMAX + 2], hi1 = st[MRF_STATE_MINMAX + 3];
+  double f0 = st[MRF_STATE_NANFLAG], f1 = st[MRF_STATE_NANFLAG + 1];
+  if (gathered) {
+    lo0 = lo1 = INFINITY; hi0 = hi1 = -INFINITY; f0 = f1 = 0.0;
+    for (int r = 0; r < world; ++r) {
+      const double* g = gathered + 6 * r;
+      lo0 = fmin(lo0, g[0]); hi0 = fmax(hi0, g[1]); lo1 = fmin(lo1, g[2]); hi1 = fmax(hi1, g[3]);
+      if (g[4] != 0.0) f0 = 1.0;
+      if (g[5] != 0.0) f1 = 1.0;
+    }
+  }
+  __syncthreads();
+  if (gathered && i == 0) {
+    st[MRF_STATE_MINMAX] = lo0; st[MRF_STATE_MINMAX + 1] = hi0; st[MRF_STATE_MINMAX + 2] = lo1; st[MRF_STATE_MINMAX + 3] = hi1;
+    st[MRF_STATE_NANFLAG] = f0; st[MRF_STATE_NANFLAG + 1] = f1;
+  }
   if (i >= L) return;
-  const double lo0 = st[MRF_STATE_MINMAX], hi0 = st[MRF_STATE_MINMAX + 1];
-  const double lo1 = st[MRF_STATE_MINMAX + 2], hi1 = st[MRF_STATE_MINMAX + 3];
-  const bool nan = (lo0 != lo0) || (lo1 != lo1) || (hi0 != hi0) || (hi1 != hi1) ||
-                   (st[MRF_STATE_NANFLAG] != 0.0) || (st[MRF_STATE_NANFLAG + 1] != 0.0);
+  const bool nan = (lo0 != lo0) || (lo1 != lo1) || (hi0 != hi0) || (hi1 != hi1) || (f0 != 0.0) || (f1 != 0.0);
   const double qnan = __longlong_as_double(0x7FF8000000000000ll);
   const double start = nan ? qnan : 1.5 * fmin(lo0, lo1);
   const double stop = nan ? qnan : 1.5 * fmax(hi0, hi1);
@@ -405,7 +349,10 @@ using namespace mrf;
 
 extern "C" {
 
-size_t mrf_select_scratch_bytes(size_t) { return sizeof(unsigned long long) * (kStWords + 8 * kHistBins + kMemoWords); }
+size_t mrf_select_scratch_bytes(size_t) {
+  const size_t old8 = sizeof(unsigned long long) * (kStWords + kHistBins);
+  return kS13Bytes > old8 ? kS13Bytes : old8;
+}
 
 int mrf_select_begin(size_t k, void* scratch, mrf_stream_t stream) {
   MRF_CHECK_ARG(scratch);
@@ -480,59 +427,63 @@ int mrf_select_successor_key_f64(const double* keys, size_t n, unsigned long lon
   return check_launch("mrf_select_successor_key_f64");
 }
 
+static unsigned s13_blocks(size_t capacity) {
+  // few fat blocks: every block zeroes / scans / flushes 8192 bins, so at most one block per SM and at
+  // least ~4K keys per block
+  size_t b = (capacity + 4095) / 4096;
+  if (b > (size_t)kSMs) b = kSMs;
+  if (b < 1) b = 1;
+  return (unsigned)b;
+}
+
 int mrf_select_median_dev(const double* keys, const int* n_dev, size_t capacity, double* out_median, void* scratch,
                           mrf_stream_t stream) {
   MRF_CHECK_ARG(keys && n_dev && out_median && scratch && capacity > 0);
-  unsigned long long* st = (unsigned long long*)scratch;
-  unsigned long long* hist_all = st + kStWords;              // [8][256]
-  // two blocks per SM: every block ends with up to 256 global atomics on the pass's histogram and starts
-  // with the (redundant) resolve of the previous byte, so few fat blocks beat many thin ones
-  const size_t cap_blocks = (size_t)kSMs * 2;
-  const unsigned blocks = (unsigned)((capacity + 255) / 256 < cap_blocks ? (capacity + 255) / 256 : cap_blocks);
-  k_select_init_fused<<<1, 256, 0, S(stream)>>>(st, hist_all);
-  int rc = check_launch("mrf_select_median_dev/init");
-  for (int pass = 0; pass < 8 && !rc; ++pass) {
-    k_select_hist_fused<<<blocks, 256, 0, S(stream)>>>(keys, n_dev, pass, st, hist_all, hist_all + 8 * kHistBins);
-    rc = check_launch("mrf_select_median_dev/hist");
+  cudaError_t e = cudaMemsetAsync(scratch, 0, kS13Bytes, S(stream));
+  if (e != cudaSuccess) return fail((int)e, "mrf_select_median_dev: %s", cudaGetErrorString(e));
+  const unsigned blocks = s13_blocks(capacity);
+  for (int pass = 0; pass < kS13Passes; ++pass) {
+    k_s13_hist<<<blocks, 256, 0, S(stream)>>>(keys, n_dev, pass, scratch);
+    const int rc = check_launch("mrf_select_median_dev/hist");
+    if (rc) return rc;
   }
+  k_s13_successor<<<blocks, 256, 0, S(stream)>>>(keys, n_dev, scratch);
+  int rc = check_launch("mrf_select_median_dev/successor");
   if (rc) return rc;
-  k_select_successor_fused<<<blocks, 256, 0, S(stream)>>>(keys, n_dev, st, hist_all, hist_all + 8 * kHistBins);
-  rc = check_launch("mrf_select_median_dev/successor");
-  if (rc) return rc;
-  k_select_median<<<1, 1, 0, S(stream)>>>(st, out_median);
+  k_s13_median<<<1, 1, 0, S(stream)>>>(scratch, nullptr, 0, out_median);
   return check_launch("mrf_select_median_dev/median");
 }
 
-// ---- step-wise selection with device-side counts (row bands; see the header)
-int mrf_select_begin_dev(const int* n_total_dev, void* scratch, mrf_stream_t stream) {
-  MRF_CHECK_ARG(n_total_dev && scratch);
-  unsigned long long* st = (unsigned long long*)scratch;
-  k_select_init<<<1, 256, 0, S(stream)>>>(st, 0ull, st + kStWords, n_total_dev);
-  return check_launch("mrf_select_begin_dev");
+// ---- the same selection in steps for keys sharded over row bands (see the header): the caller
+// all-reduces the pass's histogram between two calls
+int mrf_select13_begin(void* scratch, mrf_stream_t stream) {
+  MRF_CHECK_ARG(scratch);
+  cudaError_t e = cudaMemsetAsync(scratch, 0, kS13Bytes, S(stream));
+  if (e != cudaSuccess) return fail((int)e, "mrf_select13_begin: %s", cudaGetErrorString(e));
+  return 0;
 }
-int mrf_select_hist_dev(const double* keys, const int* n_local_dev, size_t capacity, void* scratch, mrf_stream_t stream) {
+int mrf_select13_hist_dev(const double* keys, const int* n_local_dev, size_t capacity, int pass, void* scratch,
+                          mrf_stream_t stream) {
+  MRF_CHECK_ARG(keys && n_local_dev && scratch && capacity > 0 && pass >= 0 && pass < kS13Passes);
+  k_s13_hist<<<s13_blocks(capacity), 256, 0, S(stream)>>>(keys, n_local_dev, pass, scratch);
+  return check_launch("mrf_select13_hist_dev");
+}
+int mrf_select13_successor_dev(const double* keys, const int* n_local_dev, size_t capacity, void* scratch,
+                               mrf_stream_t stream) {
   MRF_CHECK_ARG(keys && n_local_dev && scratch && capacity > 0);
-  unsigned long long* st = (unsigned long long*)scratch;
-  const unsigned blocks = (unsigned)((capacity + 255) / 256 < (size_t)kSelBlocks ? (capacity + 255) / 256 : kSelBlocks);
-  k_select_hist<<<blocks, 256, 0, S(stream)>>>(keys, capacity, st, st + kStWords, n_local_dev);
-  return check_launch("mrf_select_hist_dev");
+  k_s13_successor<<<s13_blocks(capacity), 256, 0, S(stream)>>>(keys, n_local_dev, scratch);
+  return check_launch("mrf_select13_successor_dev");
 }
-int mrf_select_successor_dev(const double* keys, const int* n_local_dev, size_t capacity, void* scratch,
-                             mrf_stream_t stream) {
-  MRF_CHECK_ARG(keys && n_local_dev && scratch && capacity > 0);
-  const unsigned blocks = (unsigned)((capacity + 255) / 256 < (size_t)kSelBlocks ? (capacity + 255) / 256 : kSelBlocks);
-  k_select_successor<<<blocks, 256, 0, S(stream)>>>(keys, capacity, (unsigned long long*)scratch, n_local_dev);
-  return check_launch("mrf_select_successor_dev");
-}
-int mrf_select_median_state(const void* scratch, double* out_median, mrf_stream_t stream) {
-  MRF_CHECK_ARG(scratch && out_median);
-  k_select_median<<<1, 1, 0, S(stream)>>>((const unsigned long long*)scratch, out_median);
-  return check_launch("mrf_select_median_state");
+int mrf_select13_median(const void* scratch, const unsigned long long* gathered, int world, double* out_median,
+                        mrf_stream_t stream) {
+  MRF_CHECK_ARG(scratch && out_median && (!gathered || world >= 1));
+  k_s13_median<<<1, 1, 0, S(stream)>>>(scratch, gathered, world, out_median);
+  return check_launch("mrf_select13_median");
 }
 
-int mrf_label_range_dev(double* dev_state, int n_labels, mrf_stream_t stream) {
-  MRF_CHECK_ARG(dev_state && n_labels >= 2 && n_labels <= 256);
-  k_label_range<<<1, 256, 0, S(stream)>>>(dev_state, n_labels);
+int mrf_label_range_dev(double* dev_state, int n_labels, const double* gathered, int world, mrf_stream_t stream) {
+  MRF_CHECK_ARG(dev_state && n_labels >= 2 && n_labels <= 256 && (!gathered || world >= 1));
+  k_label_range<<<1, 256, 0, S(stream)>>>(dev_state, n_labels, gathered, world);
   return check_launch("mrf_label_range_dev");
 }
 

@@ -38,6 +38,8 @@ def build_cost_volume(images, flow, rigidity, homographies, epipoles, params=Non
     require_cuda()
     stats = stats or pp.LocalStats()
     rigidity = np.asarray(rigidity)
+    if isinstance(stats, pp.LocalStats) and not return_device:
+        return _host_call(images, flow, rigidity, homographies, epipoles, rho, sigma, interp, range_mask, layout, variant)
     band = pp.Band.from_host(images, flow, rigidity, None)
     if isinstance(stats, pp.LocalStats):
         r = cost_volume_pass_resident(band, homographies, epipoles, flag(rigidity > 0), rho=rho, sigma=sigma,
@@ -51,6 +53,101 @@ def build_cost_volume(images, flow, rigidity, homographies, epipoles, params=Non
     if return_device:
         return [cost, S, mu_ar, B_ar, q_new, labels, (mins, argmins)]
     return [_down_many([cost[0], cost[1]]), _down_many([S[0], S[1]]), mu_ar, B_ar, q_new, labels]
+
+
+_CALL_STREAMS = {}
+
+
+def _call_streams():
+    dev = torch.cuda.current_device()
+    if dev not in _CALL_STREAMS:
+        _CALL_STREAMS[dev] = (torch.cuda.Stream(), torch.cuda.Stream())
+    return _CALL_STREAMS[dev]
+
+
+def row_chunks(h, n, align=8):
+    """``n`` row ranges covering ``h`` rows, boundaries on the kernel's 8-row tiles."""
+    units = (h + align - 1) // align
+    per = max(1, (units + n - 1) // n)
+    out, y = [], 0
+    while y < h:
+        out.append((y, min(h, y + per * align)))
+        y += per * align
+    return out
+
+
+def _host_call(images, flow, rigidity, homographies, epipoles, rho, sigma, interp, range_mask, layout, variant, n_chunks=4):
+    """One host-API call, pipelined over PCIe: the flows go up first and the pre-pass starts while the images are
+    still uploading; each neighbour frame's volume is computed in row chunks (the kernel takes bands natively) and
+    every chunk starts its pitched device->host DMA as soon as it is done, so only the first chunk's compute and
+    the last chunk's copy are exposed.  Same kernels and arithmetic as the device-resident pass."""
+    from .. import _lib
+    import ctypes as C
+    main = torch.cuda.current_stream()
+    up, down = _call_streams()
+    h, w = rigidity.shape
+    F64, F32, U8, I32 = torch.float64, torch.float32, torch.uint8, torch.int32
+
+    def src(a, dtype):
+        return torch.from_numpy(np.ascontiguousarray(np.asarray(a), dtype=dtype))
+
+    d_flow = [[torch.empty((h, w), dtype=F32, device="cuda") for _ in range(2)] for _ in range(2)]
+    d_rig = torch.empty((h, w), dtype=F64, device="cuda")
+    d_img = [torch.empty((h, w, 3), dtype=F64, device="cuda") for _ in range(3)]
+    up.wait_stream(main)
+    with torch.cuda.stream(up):
+        for f in range(2):
+            for c in range(2):
+                d_flow[f][c].copy_(src(flow[f][c], np.float32), non_blocking=True)
+        d_rig.copy_(src(rigidity, np.float64), non_blocking=True)
+        ev_flow = torch.cuda.Event(); ev_flow.record()
+        for i in range(3):
+            d_img[i].copy_(src(images[i], np.float64), non_blocking=True)
+        ev_img = torch.cuda.Event(); ev_img.record()
+    main.wait_event(ev_flow)
+    rigid_mask = (d_rig > 0).to(U8)
+    nonrigid = (rigid_mask == 0).to(U8)
+    band = pp.Band(d_img, d_flow, d_rig, None)
+    q_new = pp.refine_epipoles(band, homographies, epipoles, rigid_mask)
+    buf = device.FrontBuffers(h, w, band.device)
+    device.cost_volume_front(d_flow, rigid_mask, rigid_mask if range_mask == "as_written" else nonrigid, homographies, q_new, h,
+                             buf, n_labels=N_RANGES)
+    ev_front = torch.cuda.Event(); ev_front.record(main)
+    L = N_RANGES
+    lhw = layout == "LHW_F32"
+    shape = (L, h, w) if lhw else (h, w, L)
+    dt = F32 if lhw else I32
+    host_S = [torch.empty((h, w), dtype=F64, pin_memory=True) for _ in range(2)]
+    host_cost = [torch.empty(shape, dtype=dt, pin_memory=True) for _ in range(2)]
+    down.wait_event(ev_front)
+    with torch.cuda.stream(down):
+        for f in range(2):
+            host_S[f].copy_(buf.S[f], non_blocking=True)
+    main.wait_event(ev_img)
+    ref64, tex = pp.channels(band)
+    cost = [torch.empty(shape, dtype=dt, device="cuda") for _ in range(2)]
+    lib = _lib.lib()
+    chunks = row_chunks(h, n_chunks)
+    for f in range(2):
+        for (y0, y1) in chunks:
+            off = y0 * w * 4 if lhw else y0 * w * L * 4
+            device.cost_volume(ref64[y0:y1], tex[f], None, homographies[f], q_new[f], 0.0, 0.0, nonrigid=nonrigid[y0:y1],
+                               rho=rho, rho_param=sigma, cw=pp.CHANNEL_WEIGHTS, interp=interp, layout=layout, variant=variant,
+                               y0=y0, frame_h=h, nb_y0=0, want_min=False, want_argmin=False, out_ptr=cost[f].data_ptr() + off,
+                               plane_stride=(h * w if lhw else 0), state=buf.state, frame=f, n_labels=L)
+            ev = torch.cuda.Event(); ev.record(main)
+            down.wait_event(ev)
+            if lhw:
+                rc = lib.mrf_download_rows(C.c_void_p(host_cost[f].data_ptr()), C.c_void_p(cost[f].data_ptr()), 4, L, h, w, y0,
+                                           y1 - y0, C.c_void_p(down.cuda_stream))
+            else:       # [h][w][L]: a row chunk is one contiguous run
+                rc = lib.mrf_download_rows(C.c_void_p(host_cost[f].data_ptr()), C.c_void_p(cost[f].data_ptr()), 4, 1, h, w * L, y0,
+                                           y1 - y0, C.c_void_p(down.cuda_stream))
+            _lib.check(rc, "mrf_download_rows")
+    mu_ar, B_ar, labels = pp.state_to_host(buf.state)
+    down.synchronize()
+    main.synchronize()
+    return [[host_cost[0].numpy(), host_cost[1].numpy()], [host_S[0].numpy(), host_S[1].numpy()], mu_ar, B_ar, q_new, labels]
 
 
 def _down_many(tensors):

@@ -49,6 +49,10 @@ class LocalStats:
         a = mm.cpu().numpy()
         return float(a[0]), float(a[1])
 
+    def window(self, win):
+        """sum over bands of the (disjoint) epipole windows"""
+        return win
+
 
 def _as_u8(t):
     return t if t.dtype == torch.uint8 else t.to(torch.uint8)
@@ -104,31 +108,43 @@ class Band:
 
 
 # ----------------------------------------------------------------------------------------------
-def correct_epipole(u_res, v_res, q, rigid_mask, y0=0, frame_h=None):
-    """pipeline/compute_structure.py:453-511.  ``u_res``/``v_res`` are device tensors; only the 21x21
-    window round the epipole (441 pixels) comes to the host, where the reference's own objective
-    sum(|u*(qx-x) + v*(qy-y)| / max(1e-3, |q-x|^2)) is minimised with scipy's BFGS exactly as the
-    reference does (:507) -- the gradient chumpy derived by autodiff (:495-504) written out.
-    Returns ``q`` unchanged when the window leaves the image (:476), when more than half of it is
-    non-rigid (:489-491), or when the optimum moved 10 px or more (:509)."""
-    from scipy import optimize
+def epipole_window(u_res, v_res, rigid_mask, q, y0=0, frame_h=None):
+    """The 21x21 window of residual flow and rigidity round the epipole that ``correct_epipole`` looks at
+    (pipeline/compute_structure.py:463-487), fetched from the device: fp64 [3,21,21] = (u_res, v_res,
+    rigid).  ``None`` when the window leaves the image (:476-477: the epipole stays).  Rows of the window
+    outside this band ``[y0, y0+rows)`` are zero, so the windows of all row bands add up to the whole one."""
     q = np.asarray(q, dtype=np.float64)
     rows, w = u_res.shape
     h = rows if frame_h is None else frame_h
     xmin, xmax = int(q[0]) - 10, int(q[0]) + 10
     ymin, ymax = int(q[1]) - 10, int(q[1]) + 10
     if xmin < 0 or xmax >= w or ymin < 0 or ymax >= h:
-        return q
-    if ymin < y0 or ymax >= y0 + rows:
-        raise ValueError("epipole window rows %d..%d are not inside this band" % (ymin, ymax))
-    sl = (slice(ymin - y0, ymax - y0 + 1), slice(xmin, xmax + 1))
-    uw = u_res[sl].cpu().numpy().astype(np.float64)
-    vw = v_res[sl].cpu().numpy().astype(np.float64)
-    r = rigid_mask[sl].cpu().numpy() > 0
+        return None
+    win = np.zeros((3, 21, 21))
+    lo, hi = max(ymin, y0), min(ymax + 1, y0 + rows)
+    if hi > lo:
+        sl = (slice(lo - y0, hi - y0), slice(xmin, xmax + 1))
+        dst = slice(lo - ymin, hi - ymin)
+        win[0, dst] = u_res[sl].cpu().numpy().astype(np.float64)
+        win[1, dst] = v_res[sl].cpu().numpy().astype(np.float64)
+        win[2, dst] = rigid_mask[sl].cpu().numpy() > 0
+    return win
+
+
+def epipole_from_window(win, q):
+    """pipeline/compute_structure.py:487-511 on the window ``epipole_window`` returns.  The reference's own
+    objective sum(|u*(qx-x) + v*(qy-y)| / max(1e-3, |q-x|^2)) over the rigid pixels of the window is
+    minimised with scipy's BFGS exactly as the reference does (:507) -- the gradient chumpy derives by
+    autodiff (:495-504) written out.  Returns ``q`` unchanged when more than half of the window is non-rigid
+    (:489-491) or when the optimum moved 10 px or more (:509)."""
+    from scipy import optimize
+    q = np.asarray(q, dtype=np.float64)
+    xmin, ymin = int(q[0]) - 10, int(q[1]) - 10
+    r = win[2] > 0
     if (~r).sum() > (r.size / 2):
         return q
-    yy, xx = np.mgrid[ymin:ymax + 1, xmin:xmax + 1]
-    uw, vw, xw, yw = uw[r], vw[r], xx[r].astype(np.float64), yy[r].astype(np.float64)
+    yy, xx = np.mgrid[ymin:ymin + 21, xmin:xmin + 21]
+    uw, vw, xw, yw = win[0][r], win[1][r], xx[r].astype(np.float64), yy[r].astype(np.float64)
 
     def fun(qe):
         fx, fy = qe[0] - xw, qe[1] - yw
@@ -145,6 +161,21 @@ def correct_epipole(u_res, v_res, q, rigid_mask, y0=0, frame_h=None):
     return res.x if np.linalg.norm(res.x - q) < 10 else q
 
 
+def correct_epipole(u_res, v_res, q, rigid_mask, y0=0, frame_h=None, stats=None):
+    """pipeline/compute_structure.py:453-511.  ``u_res``/``v_res`` are device tensors; only the 21x21
+    window round the epipole (441 pixels) comes to the host (``epipole_window`` / ``epipole_from_window``).
+    With row bands, ``stats.window`` adds the bands' windows up (disjoint rows, so the sum is exact) and every
+    rank solves the same 441-pixel problem -- also when the window straddles a band boundary."""
+    win = epipole_window(u_res, v_res, rigid_mask, q, y0, frame_h)
+    if win is None:
+        return np.asarray(q, dtype=np.float64)
+    if stats is not None:
+        win = stats.window(win)
+    elif y0 != 0 or (frame_h is not None and frame_h != u_res.shape[0]):
+        raise ValueError("a row band needs stats= to assemble the epipole window")
+    return epipole_from_window(win, q)
+
+
 def first_pass(band, homographies, epipoles, rigid_mask, stats, fix_epipole=True):
     """pipeline/compute_structure.py:67-91 for both neighbour frames: residual flow, refined epipole,
     parallax, mu.  Returns dict(residual, parallax, q, mu)."""
@@ -155,22 +186,17 @@ def first_pass(band, homographies, epipoles, rigid_mask, stats, fix_epipole=True
         q = np.asarray(epipoles[f], dtype=np.float64)
         ur, vr, p, _ = device.flow_to_parallax(band.flow[f][0], band.flow[f][1], Hinv, q, y0=band.y0, want_dists=False)
         if fix_epipole:
-            q_new = stats.epipole(lambda: correct_epipole(ur, vr, q, rigid_mask, band.y0, band.frame_h), q, band)
+            q_new = correct_epipole(ur, vr, q, rigid_mask, band.y0, band.frame_h, stats)
             if not np.array_equal(q_new, q):
                 _, _, p, _ = device.flow_to_parallax(band.flow[f][0], band.flow[f][1], Hinv, q_new, y0=band.y0,
                                                      want_residual=False, want_dists=False)
                 q = q_new
-        dsum = device.epipole_dist_sum(band.rows, band.w, q, y0=band.y0, device=band.device)
-        mu = float(stats.device_sum(dsum).cpu()[0]) / n_px                    # :84
+        # mu = foe_dists.mean() (:84) depends only on (q, h, w): every band evaluates the whole-frame sum
+        # itself (same grid and summation tree everywhere), so no exchange and the bits of a one-GPU run
+        dsum = device.epipole_dist_sum(band.frame_h, band.w, q, y0=0, device=band.device)
+        mu = float(dsum.cpu()[0]) / n_px
         res.append((ur, vr)); par.append(p); qs.append(q); mus.append(mu)
     return dict(residual=res, parallax=par, q=qs, mu=mus)
-
-
-def _local_epipole(self, fn, q, band):
-    return fn()
-
-
-LocalStats.epipole = _local_epipole
 
 
 def scales(band, fp, p_thr, stats, scale_structure=1, B_fwd_fixed=None):
@@ -271,7 +297,7 @@ def cost_volumes(band, ref64, tex, labels_dev, homographies, q_ar, mu_ar, B_ar, 
     return res
 
 
-def refine_epipoles(band, homographies, epipoles, rigid_mask):
+def refine_epipoles(band, homographies, epipoles, rigid_mask, stats=None):
     """compute_structure.py:77 for both frames.  Touches the device only when the 21x21 window round an
     epipole lies inside the image (otherwise correct_epipole returns q unchanged, :476-477)."""
     out = []
@@ -284,7 +310,7 @@ def refine_epipoles(band, homographies, epipoles, rigid_mask):
         Hinv = np.linalg.inv(np.asarray(homographies[f], dtype=np.float64))
         ur, vr, _, _ = device.flow_to_parallax(band.flow[f][0], band.flow[f][1], Hinv, q, y0=band.y0,
                                                want_parallax=False, want_dists=False)
-        out.append(correct_epipole(ur, vr, q, rigid_mask, band.y0, band.frame_h))
+        out.append(correct_epipole(ur, vr, q, rigid_mask, band.y0, band.frame_h, stats))
     return out
 
 

@@ -134,6 +134,43 @@ class DistSelect:
         return a if n_total % 2 == 1 else float(np.mean(np.array([a, b])))
 
 
+class DistSelect13:
+    """Host twin of the DEVICE protocol the resident row-band pre-pass runs (csrc/select13.cuh,
+    ``banded_front``): five radix passes over digits of 12+13+13+13+13 bits, one 8192-bin histogram
+    all-reduce per pass (n = the total of the first one, no separate count exchange), then one all-gather of
+    the three successor words (NaN count, count(keys <= kth), inverted smallest key above kth).  The per-shard
+    steps are callables so the protocol is testable on CPU with gloo; the GPU tests cover the kernels.
+
+    ``hist_fn(prefix, pass) -> int64[8192]``, ``succ_fn(kth_key) -> (n_nan, count_le, inv_min_gt)``,
+    ``allreduce(array, 'sum')``, ``allgather(int-list) -> list of int-lists (one per rank)``."""
+    SHIFTS = (52, 39, 26, 13, 0)
+    BINS = 8192
+
+    def __init__(self, hist_fn, succ_fn, allreduce, allgather):
+        self.hist_fn, self.succ_fn, self.allreduce, self.allgather = hist_fn, succ_fn, allreduce, allgather
+
+    def median(self):
+        prefix, k_rem, n = 0, 0, 0
+        for p, shift in enumerate(self.SHIFTS):
+            hist = self.allreduce(np.asarray(self.hist_fn(prefix, p), dtype=np.int64), "sum")
+            if p == 0:
+                n = int(hist.sum())
+                k_rem = (n - 1) // 2 if n else 0
+            b = 0
+            while b < self.BINS - 1 and k_rem >= int(hist[b]):
+                k_rem -= int(hist[b])
+                b += 1
+            prefix = (prefix | (b << shift)) & 0xFFFFFFFFFFFFFFFF
+        rows = self.allgather([int(v) for v in self.succ_fn(prefix)])
+        n_nan = sum(r[0] for r in rows); cnt_le = sum(r[1] for r in rows); inv_min = max(r[2] for r in rows)
+        if n == 0 or n_nan > 0:
+            return float("nan")
+        a = key_value(prefix)
+        k = (n - 1) // 2
+        b = a if cnt_le >= k + 2 else key_value(~inv_min & 0xFFFFFFFFFFFFFFFF)
+        return a if n % 2 == 1 else float(np.mean(np.array([a, b])))
+
+
 class BandStats:
     """``planeparallax`` statistics over row bands: the ``LocalStats`` interface with collectives."""
 
@@ -150,6 +187,13 @@ class BandStats:
         dist.all_reduce(t, op={"sum": dist.ReduceOp.SUM, "min": dist.ReduceOp.MIN, "max": dist.ReduceOp.MAX}[op],
                         group=self.group)
         return t.cpu().numpy()
+
+    def _allgather(self, values):
+        """small unsigned 64-bit integers, one list per rank"""
+        mine = torch.from_numpy(np.array([v & 0xFFFFFFFFFFFFFFFF for v in values], dtype=np.uint64).view(np.int64)).to(self.dev)
+        out = [torch.empty_like(mine) for _ in range(self.world)]
+        dist.all_gather(out, mine, group=self.group)
+        return [[int(x) for x in o.cpu().numpy().view(np.uint64)] for o in out]
 
     def total(self, value):
         return int(self._allreduce(np.array([int(value)], dtype=np.int64), "sum")[0])
@@ -185,29 +229,12 @@ class BandStats:
 
         return DistSelect(hist_fn, succ_fn, self._allreduce).median(self.total(n))
 
-    def epipole(self, fn, q, band):
-        """correct_epipole runs on the rank whose band contains the 21x21 window; the result is
-        broadcast.  A window straddling two bands is left uncorrected on all ranks (logged)."""
-        h, w = band.frame_h, band.w
-        ymin, ymax = int(q[1]) - 10, int(q[1]) + 10
-        xmin, xmax = int(q[0]) - 10, int(q[0]) + 10
-        inside = not (xmin < 0 or xmax >= w or ymin < 0 or ymax >= h)
-        if not inside:
-            # compute_structure.py:476-477: the window leaves the image, the epipole stays -- every rank knows that
-            # from (q, w, h) alone, so no collective and no host synchronisation
-            return np.asarray(q, dtype=np.float64)
-        mine = ymin >= band.y0 and ymax < band.y0 + band.rows
-        res = np.zeros(3)
-        if mine:
-            qn = fn()
-            res = np.array([1.0, qn[0], qn[1]])
-        # exact transfer of the two doubles: exactly one rank contributes non-zero values
-        tot = self._allreduce(res, "sum")
-        if tot[0] == 0:
-            if inside and self.rank == 0:
-                print("(WW) epipole window straddles two row bands: epipole not corrected")
-            return np.asarray(q, dtype=np.float64)
-        return tot[1:3].copy()
+    def window(self, win):
+        """The 21x21 epipole window (planeparallax.epipole_window) summed over the bands: every rank holds
+        the rows it owns and zeros elsewhere, so the sum is exact and every rank then solves the same
+        441-pixel problem (compute_structure.py:453-511) -- no broadcast, and a window that straddles a band
+        boundary is handled like any other."""
+        return self._allreduce(np.ascontiguousarray(win), "sum")
 
 
 # ------------------------------------------------------------------------------------------ gather
@@ -262,9 +289,11 @@ class PeerVolume:
 
 # ------------------------------------------------------------------------------------------ resident bands
 class PeerMailbox:
-    """Every rank's small IPC-shared buffer for ``mrf_mailbox_allreduce``: the integer / min all-reduces of the
-    row-band pre-pass as one kernel per rank over NVLink peer memory instead of NCCL launches (bit-identical
-    results: only order-independent reductions)."""
+    """Every rank's small IPC-shared buffer for ``mrf_mailbox_allreduce``: integer / min all-reduces of up to 256
+    words as one kernel per rank over NVLink peer memory (bit-identical to NCCL: only order-independent
+    reductions).  A building block: the row-band pre-pass itself uses NCCL (its histograms are 32 KB).  A rank
+    that never shows up turns the result into all-ones after 20 s and sets the status word: call ``check()``
+    (a collective) before trusting results."""
 
     def __init__(self, group=None):
         lib = _lib.lib()
@@ -315,6 +344,13 @@ class PeerMailbox:
         a.__cuda_array_interface__ = {"shape": (self.nbytes // 8,), "typestr": "<i8", "data": (self.local, False), "version": 2}
         return int(torch.as_tensor(a, device="cuda")[self.nbytes // 8 - 8].cpu())
 
+    def check(self):
+        """Raise on every rank if any rank's collective gave up waiting for a peer (results are poisoned then)."""
+        bad = torch.tensor([int(self.status() != 0)], dtype=torch.int64, device="cuda")
+        dist.all_reduce(bad, op=dist.ReduceOp.MAX, group=self.group)
+        if int(bad.cpu()[0]):
+            raise RuntimeError("a peer-memory all-reduce timed out waiting for a rank; its results are poisoned")
+
     def close(self):
         lib = _lib.lib()
         torch.cuda.synchronize()
@@ -330,23 +366,25 @@ class PeerMailbox:
 class BandBuffers:
     """Reusable HBM buffers of the banded device-resident pre-pass."""
 
-    def __init__(self, rows, w, dev="cuda"):
+    def __init__(self, rows, w, dev="cuda", world=1):
         L = _lib.lib()
-        F64, I32, U8 = torch.float64, torch.int32, torch.uint8
+        F64, I32, U8, I64 = torch.float64, torch.int32, torch.uint8, torch.int64
         self.par = [torch.empty((rows, w), dtype=F64, device=dev) for _ in range(2)]
         self.S = [torch.empty((rows, w), dtype=F64, device=dev) for _ in range(2)]
         self.cand = torch.empty(rows * w, dtype=F64, device=dev)
         self.count = torch.zeros(1, dtype=I32, device=dev)
-        self.n_total = torch.zeros(1, dtype=I32, device=dev)
-        self.sums = torch.zeros(2, dtype=F64, device=dev)
         self.state = torch.zeros(_lib.STATE_WORDS, dtype=F64, device=dev)
         self.scratch = torch.empty(L.mrf_front_scratch_bytes(), dtype=U8, device=dev)
+        self.mu_scratch = torch.empty(L.mrf_front_scratch_bytes(), dtype=U8, device=dev)
         self.sel = torch.zeros(L.mrf_select_scratch_bytes(0), dtype=U8, device=dev)
-        words = self.sel.view(torch.int64)
-        self.sel_hist = words[_lib.SELECT_HIST_OFFSET // 8:_lib.SELECT_HIST_OFFSET // 8 + 256]
-        self.sel_sum = words[3:5]            # NaN count, count(keys <= kth)
-        self.sel_min = words[5:6]            # smallest order-key above kth (unsigned)
-        self.sign = torch.tensor([-2 ** 63], dtype=torch.int64, device=dev)
+        w32 = self.sel.view(I32)
+        o, nb = _lib.SELECT13_HIST_OFFSET // 4, _lib.SELECT13_BINS
+        self.sel_hist = [w32[o + p * nb:o + (p + 1) * nb] for p in range(_lib.SELECT13_PASSES)]   # one 32 KB histogram per pass
+        self.sel_succ = self.sel.view(I64)[_lib.SELECT13_SUCC_OFFSET // 8:_lib.SELECT13_SUCC_OFFSET // 8 + 3]
+        self.succ_all = torch.zeros(3 * world, dtype=I64, device=dev)
+        self.mm = self.state[_lib.STATE_MINMAX:_lib.STATE_MINMAX + 6]          # min0 max0 min1 max1 nan0 nan1
+        self.mm_all = torch.zeros(6 * world, dtype=F64, device=dev)
+        self.mu_done = torch.cuda.Event()
 
 
 def _front_params(band, homographies, q_ar, n_labels, B_fwd=1.0):
@@ -368,85 +406,79 @@ def _front_params(band, homographies, q_ar, n_labels, B_fwd=1.0):
     return p
 
 
-def banded_front(band, homographies, q_ar, rigid_mask, zero_mask, buf, group=None, n_labels=pp.N_LABELS, mailbox=None):
+def banded_mu(band, homographies, q_ar, buf, n_labels=pp.N_LABELS):
+    """mu of both frames (compute_structure.py:84) on this rank, no collective: the sum of ||p - q|| over
+    the WHOLE frame depends only on (q, h, w), and is evaluated in the one-GPU front's grid and summation
+    tree -- bit-identical to a single-GPU run.  Enqueued on the current stream; records ``buf.mu_done``."""
+    p = _front_params(band, homographies, q_ar, n_labels)
+    check(_lib.lib().mrf_front_mu_whole(C.byref(p), C.c_void_p(buf.state.data_ptr()), C.c_void_p(buf.mu_scratch.data_ptr()),
+                                        C.c_void_p(torch.cuda.current_stream().cuda_stream)), "mrf_front_mu_whole")
+    buf.mu_done.record()
+
+
+def banded_front(band, homographies, q_ar, rigid_mask, zero_mask, buf, group=None, n_labels=pp.N_LABELS, mu_ready=False):
     """The pre-pass of build_cost_volume for one row band with every whole-frame scalar kept on the device:
-    kernels on this band, tiny NCCL all-reduces (2 doubles, 1 int, 8 x 2 KB histograms, 3 words, 6 doubles)
-    enqueued on the same stream in between -- no host synchronisation.  Leaves mu, B, labels in
-    ``buf.state`` (identical on every rank) and this band's parallax / structures in ``buf``."""
+    kernels on this band and SEVEN small NCCL collectives enqueued on the same stream in between -- five 32 KB
+    histogram all-reduces of the exact median (13-bit digits), one all-gather of its 3 successor words, one
+    all-gather of the 6 range words -- and no host synchronisation.  mu needs no collective (``banded_mu``).
+    Leaves mu, B, labels in ``buf.state`` (identical on every rank) and this band's parallax / structures in
+    ``buf``."""
     L = _lib.lib()
     P = lambda t: C.c_void_p(t.data_ptr())
     st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
     p = _front_params(band, homographies, q_ar, n_labels)
-    SUM, MIN, MAX = dist.ReduceOp.SUM, dist.ReduceOp.MIN, dist.ReduceOp.MAX
+    world = dist.get_world_size(group)
     fl = band.flow
     check(L.mrf_front_parallax_band(C.byref(p), P(fl[0][0]), P(fl[0][1]), P(fl[1][0]), P(fl[1][1]), P(buf.par[0]), P(buf.par[1]),
-                                    P(buf.sums), P(buf.scratch), st), "mrf_front_parallax_band")
-    dist.all_reduce(buf.sums, op=SUM, group=group)
-    buf.state[_lib.STATE_MU:_lib.STATE_MU + 2] = buf.sums / float(band.frame_h * band.w)        # compute_structure.py:84
+                                    P(buf.scratch), st), "mrf_front_parallax_band")
+    if mu_ready:
+        torch.cuda.current_stream().wait_event(buf.mu_done)
+    else:
+        banded_mu(band, homographies, q_ar, buf, n_labels)
     check(L.mrf_front_candidates_band(C.byref(p), P(buf.par[0]), P(buf.par[1]), P(rigid_mask), P(buf.state), P(buf.cand),
-                                      P(buf.count), st), "mrf_front_candidates_band")
-    buf.n_total.copy_(buf.count)
-    dist.all_reduce(buf.n_total, op=SUM, group=group)
+                                      P(buf.count), P(buf.sel), st), "mrf_front_candidates_band")
     cap = band.rows * band.w
-    check(L.mrf_select_begin_dev(P(buf.n_total), P(buf.sel), st), "mrf_select_begin_dev")
-    for _ in range(8):
-        check(L.mrf_select_hist_dev(P(buf.cand), P(buf.count), cap, P(buf.sel), st), "mrf_select_hist_dev")
-        if mailbox is not None:
-            mailbox.allreduce(buf.sel_hist, "sum_u64")
+    for ps in range(_lib.SELECT13_PASSES):
+        dist.all_reduce(buf.sel_hist[ps], op=dist.ReduceOp.SUM, group=group)
+        if ps + 1 < _lib.SELECT13_PASSES:
+            check(L.mrf_select13_hist_dev(P(buf.cand), P(buf.count), cap, ps + 1, P(buf.sel), st), "mrf_select13_hist_dev")
         else:
-            dist.all_reduce(buf.sel_hist, op=SUM, group=group)
-        check(L.mrf_select_pick(P(buf.sel), st), "mrf_select_pick")
-    check(L.mrf_select_successor_dev(P(buf.cand), P(buf.count), cap, P(buf.sel), st), "mrf_select_successor_dev")
-    if mailbox is not None:
-        mailbox.allreduce(buf.sel_sum, "sum_u64")
-        mailbox.allreduce(buf.sel_min, "min_u64")
-    else:
-        dist.all_reduce(buf.sel_sum, op=SUM, group=group)
-        buf.sel_min.bitwise_xor_(buf.sign)                 # unsigned order -> signed order for MIN
-        dist.all_reduce(buf.sel_min, op=MIN, group=group)
-        buf.sel_min.bitwise_xor_(buf.sign)
-    check(L.mrf_select_median_state(P(buf.sel), C.c_void_p(buf.state.data_ptr() + 8 * _lib.STATE_B), st),
-          "mrf_select_median_state")                       # B_b, compute_structure.py:221
+            check(L.mrf_select13_successor_dev(P(buf.cand), P(buf.count), cap, P(buf.sel), st), "mrf_select13_successor_dev")
+    dist.all_gather_into_tensor(buf.succ_all, buf.sel_succ, group=group)
+    # B_b = the median (compute_structure.py:221), structures, this band's range min / max
     check(L.mrf_front_structures_band(C.byref(p), P(buf.par[0]), P(buf.par[1]), P(zero_mask), P(buf.S[0]), P(buf.S[1]),
-                                      P(buf.state), P(buf.scratch), st), "mrf_front_structures_band")
-    # one MIN all-reduce for (min, -max, -nanflag) of both frames instead of three collectives (negation is exact)
-    mm = buf.state[_lib.STATE_MINMAX:_lib.STATE_MINMAX + 4]
-    flags = buf.state[_lib.STATE_NANFLAG:_lib.STATE_NANFLAG + 2]
-    packed = torch.cat((mm[0::2], -mm[1::2], -flags))
-    if mailbox is not None:
-        mailbox.allreduce(packed, "min_f64")
-    else:
-        dist.all_reduce(packed, op=MIN, group=group)
-    mm[0::2] = packed[0:2]; mm[1::2] = -packed[2:4]; flags.copy_(-packed[4:6])
-    check(L.mrf_label_range_dev(P(buf.state), int(n_labels), st), "mrf_label_range_dev")
+                                      P(buf.state), P(buf.sel), P(buf.succ_all), world, P(buf.scratch), st),
+          "mrf_front_structures_band")
+    dist.all_gather_into_tensor(buf.mm_all, buf.mm, group=group)
+    check(L.mrf_label_range_dev(P(buf.state), int(n_labels), P(buf.mm_all), world, st), "mrf_label_range_dev")
     return buf
 
 
 def banded_pass_resident(band, homographies, epipoles, rigid_mask, stats, buf=None, rho="lorentzian", sigma=1.0,
                          interp="cubic", range_mask="rigid_only", variant="staged", out_ptr=(None, None), plane_stride=0,
-                         want_cost=True, halo_miss=None, events=None, masks=None, channels=None, mailbox=None):
+                         want_cost=True, halo_miss=None, events=None, masks=None, channels=None):
     """Row-band cost volumes with the device-resident pre-pass.  Returns dict(cost, mins, argmins, q, buffers)."""
-    q_new = [stats.epipole(lambda f=f: _band_epipole(band, homographies, epipoles, rigid_mask, f), np.asarray(epipoles[f], np.float64), band)
-             for f in range(2)]
-    buf = buf or BandBuffers(band.rows, band.w, band.device)
+    q_new = pp.refine_epipoles(band, homographies, epipoles, rigid_mask, stats)
+    buf = buf or BandBuffers(band.rows, band.w, band.device, world=stats.world)
     if masks is None:
         nonrigid = (rigid_mask == 0).to(torch.uint8)
         masks = (nonrigid, rigid_mask if range_mask == "as_written" else nonrigid)
     nonrigid, zero_mask = masks
     cur = torch.cuda.current_stream()
+    # mu (whole-frame, no collective) and the channel stacks do not depend on the band's pre-pass: they run on a
+    # side stream while the pre-pass and its collectives run
+    side = _side_stream(band.device)
+    side.wait_stream(cur)
     ch_done = None
-    if channels is None:
-        # the channel stacks do not depend on the pre-pass: build them on a side stream while the pre-pass and
-        # its collectives run
-        side = _side_stream(band.device)
-        side.wait_stream(cur)
-        with torch.cuda.stream(side):
+    with torch.cuda.stream(side):
+        banded_mu(band, homographies, q_new, buf)
+        if channels is None:
             channels = pp.channels(band)
             ch_done = torch.cuda.Event()
             ch_done.record(side)
-        for tns in (channels[0], *channels[1]):
-            tns.record_stream(cur)
-    banded_front(band, homographies, q_new, rigid_mask, zero_mask, buf, group=stats.group, mailbox=mailbox)
+            for tns in (channels[0], *channels[1]):
+                tns.record_stream(cur)
+    banded_front(band, homographies, q_new, rigid_mask, zero_mask, buf, group=stats.group, mu_ready=True)
     if ch_done is not None:
         cur.wait_event(ch_done)
     ref64, tex = channels
@@ -466,23 +498,13 @@ def _side_stream(dev):
     return _SIDE[key]
 
 
-def _band_epipole(band, homographies, epipoles, rigid_mask, f):
-    q = np.asarray(epipoles[f], dtype=np.float64)
-    Hinv = np.linalg.inv(np.asarray(homographies[f], dtype=np.float64))
-    ur, vr, _, _ = device.flow_to_parallax(band.flow[f][0], band.flow[f][1], Hinv, q, y0=band.y0, want_parallax=False,
-                                           want_dists=False)
-    return pp.correct_epipole(ur, vr, q, rigid_mask, band.y0, band.frame_h)
-
-
 # ------------------------------------------------------------------------------------------ driver
 def banded_cost_volume(t, stats, rank, world, rho="lorentzian", sigma=1.0, interp="cubic", range_mask="rigid_only",
-                       variant="staged", peer=(None, None), keep_local=True, halo=None, timers=None, resident=True,
-                       mailbox=None):
+                       variant="staged", peer=(None, None), keep_local=True, halo=None, timers=None, resident=True):
     """build_cost_volume for this rank's band of the host triplet ``t`` (dict as synth.make_triplet
     returns).  ``resident=True`` keeps the whole-frame scalars on the device (``banded_pass_resident``);
     ``False`` drives the statistics through the host (``BandStats`` / ``DistSelect``, the protocol the gloo
-    tests cover) -- same kernels, bit-identical results.  ``mailbox`` (a ``PeerMailbox``) routes the integer / min
-    all-reduces of the resident pre-pass through NVLink peer memory instead of NCCL.
+    tests cover) -- same kernels, bit-identical results.
     Returns dict(cost, S, mu, B, q, labels, mins, argmins, rows, halo)."""
     from .pipeline.build_cost_volume import cost_volume_pass
     h, w = t["shape"]
@@ -498,7 +520,7 @@ def banded_cost_volume(t, stats, rank, world, rho="lorentzian", sigma=1.0, inter
             mask = torch.from_numpy((rig[y0:y1] > 0).astype(np.uint8)).cuda()
             r = banded_pass_resident(band, t["homographies"], t["epipoles"], mask, stats, rho=rho, sigma=sigma, interp=interp,
                                      range_mask=range_mask, variant=variant, out_ptr=outs, plane_stride=stride,
-                                     want_cost=keep_local, halo_miss=miss, events=timers, mailbox=mailbox)
+                                     want_cost=keep_local, halo_miss=miss, events=timers)
             mu, B, labels = pp.state_to_host(r["buffers"].state)
             res = (r["cost"], r["buffers"].S, mu, B, r["q"], labels, r["mins"], r["argmins"])
         else:
@@ -515,100 +537,140 @@ def banded_cost_volume(t, stats, rank, world, rho="lorentzian", sigma=1.0, inter
     return dict(cost=cost, S=S, mu=mu, B=B, q=q, labels=labels, mins=mins, argmins=argmins, rows=(y0, y1), halo=halo_rows)
 
 
-def bench_bands(args, hw, steps, warm, metric, unit, workload, ClockSampler):
-    """bench.py --mode bands: ONE frame sharded by row bands over all ranks (strong scaling)."""
+def device_band(td, rows, halo):
+    """``planeparallax.Band`` of rows ``(y0, y1)`` cut from a device-resident triplet (``synth.make_triplet_device``),
+    with ``halo`` neighbour rows and the 2-row stencil margin of the channel construction."""
+    h, w = td["shape"]
+    y0, y1 = rows
+    n0, n1 = max(0, y0 - halo), min(h, y1 + halo)
+    m0, m1 = max(0, n0 - 2), min(h, n1 + 2)
+    imgs = [I[m0:m1].contiguous() for I in td["images"]]
+    fl = [[c[y0:y1].contiguous() for c in td["flow"][f]] for f in range(2)]
+    return pp.Band(imgs, fl, td["rigidity"][y0:y1].contiguous(), None, y0=y0, frame_h=h, nb_y0=n0, nb_rows=n1 - n0, img_y0=m0)
+
+
+def bench_bands(hw, steps, warm, interp="cubic", variant="staged", ClockSampler=None, verify=True, seed=1001, n_waves=16):
+    """ONE frame (BASELINE.json configs[3]: 4K) sharded by row bands over all ranks -- strong scaling; with one
+    rank the whole frame on one GPU, which is the base of the speed-up.  The synthetic triplet is generated on
+    rank 0's GPU and broadcast.  Timed per step (CUDA events, L2 flushed, max over ranks):
+      compute_only        every rank keeps its band of both volumes;
+      compute_and_gather  the bands are stored straight into rank 0's whole-frame volumes over NVLink
+                          (PeerVolume: the gather is the kernel's own output stream);
+      compute_and_d2h     every rank copies its band to pinned host memory over its own PCIe link (what a
+                          host-side consumer such as TRW-S needs: N links instead of one).
+    ``verify``: the gathered volumes equal a whole-frame run on rank 0 bit for bit, and mu / B / labels equal
+    the one-GPU pre-pass's.  Returns the record on rank 0 (None elsewhere)."""
     from . import synth
-    rank, world = dist.get_rank(), dist.get_world_size()
+    from .pipeline import build_cost_volume as bcv
+    world = dist.get_world_size() if dist.is_initialized() else 1
+    rank = dist.get_rank() if dist.is_initialized() else 0
     h, w = hw
     L = pp.N_LABELS
-    t = synth.make_triplet(hw, seed=1001)            # every rank builds the same host triplet
-    stats = BandStats()
-    from .pipeline.build_cost_volume import cost_volume_pass
-    y0, y1 = band_plan(h, world)[rank]
-    rig = np.asarray(t["rigidity"])
-    # pick the halo once (planning is outside the timed region, as uploading the inputs is)
-    r0 = banded_cost_volume(t, stats, rank, world, interp=args.interp, variant=args.variant, keep_local=False)
-    halo_rows = r0["halo"]
-    band = pp.Band.from_host(t["images"], t["flow"], rig, None, rows=(y0, y1), halo=halo_rows)
-    rigid_mask = torch.from_numpy((rig[y0:y1] > 0).astype(np.uint8)).cuda()
-    peers = (PeerVolume(L, h, w), PeerVolume(L, h, w))
+    td = synth.make_triplet_device(hw, seed=seed, n_waves=n_waves)
+    if world > 1:
+        for tns in (*td["images"], *td["flow"][0], *td["flow"][1]):
+            dist.broadcast(tns, 0)
+    H_ar, q_ar = td["homographies"], td["epipoles"]
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
-    kernel_events = []
-
-    nonrigid = (rigid_mask == 0).to(torch.uint8)
-    # measured on 8 GPUs / 4K (profiles/r1g_scale8_bands4k*.json): the peer-memory all-reduce kernel is no faster than
-    # NCCL's low-latency protocol for these 2 KB messages (2.57 ms vs 2.37 ms per step), so NCCL stays the default
-    mailbox = PeerMailbox() if getattr(args, "band_allreduce", "nccl") == "peer" else None
-    bbuf = BandBuffers(y1 - y0, w)
-    miss = torch.zeros(1, dtype=torch.int32, device="cuda")
-    cost_local = (torch.empty((L, y1 - y0, w), dtype=torch.float32, device="cuda"),
-                  torch.empty((L, y1 - y0, w), dtype=torch.float32, device="cuda"))
-
-    def step(events=None, gather=True):
-        outs = tuple(p.band_ptr(y0) for p in peers) if gather else tuple(c.data_ptr() for c in cost_local)
-        return banded_pass_resident(band, t["homographies"], t["epipoles"], rigid_mask, stats, buf=bbuf, interp=args.interp,
-                                    range_mask="rigid_only", variant=args.variant, out_ptr=outs,
-                                    plane_stride=(h * w if gather else 0), halo_miss=miss, events=events,
-                                    masks=(nonrigid, nonrigid), mailbox=mailbox)
 
     def barrier():
-        torch.cuda.synchronize(); dist.barrier(); torch.cuda.synchronize()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
 
-    results = {}
-    for mode, gather in (("compute_only", False), ("compute_and_gather", True)):
+    def timed(step):
         for _ in range(warm):
-            step(gather=gather)
+            step()
         barrier()
-        device.reset_launch_count()
         tot = 0.0
-        with ClockSampler(torch.cuda.current_device()) as clocks:
-            for _ in range(steps):
-                flush.fill_(1)
-                barrier()
-                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                e0.record()
-                step(kernel_events if gather else None, gather=gather)
-                e1.record(); e1.synchronize()
-                tot += e0.elapsed_time(e1)
-        launches = device.launch_count()
+        for _ in range(steps):
+            flush.fill_(1)
+            barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            step()
+            e1.record(); e1.synchronize()
+            tot += e0.elapsed_time(e1)
         tt = torch.tensor([tot], dtype=torch.float64, device="cuda")
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        results[mode] = (float(tt.cpu()[0]), launches, clocks.summary())
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        return float(tt.cpu()[0]) / steps
+
     units = 2 * h * w * L
-    tot_ms, launches, clk = results["compute_and_gather"]
-    kms = [a.elapsed_time(b) for a, b in kernel_events]
-    peaks = {}
-    try:
-        peaks = json.load(open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "MEASURED_PEAKS.json")))
-    except Exception:   # noqa: BLE001
-        pass
-    peak = float(peaks.get("hbm_gbs", 6650.0))
+    rec = {"workload": "4k_%dx%d_L%d_F2_%s" % (w, h, L, interp), "n_gpus": world, "steps": steps, "scaling": "strong",
+           "unit": "pixel*labels/s"}
+    if world == 1:
+        band = device_band(td, (0, h), 0)
+        rigid = (td["rigidity"] > 0).to(torch.uint8)
+        st = bcv.ResidentStep(band, H_ar, q_ar, rigid, interp=interp, range_mask="rigid_only", variant=variant, use_graph=False)
+        ms = timed(lambda: st.run())
+        rec.update({"parallelism": "whole frame on one GPU", "compute_only": {"ms_per_step": ms, "value": units / (ms * 1e-3)}})
+        return rec
+
+    stats = BandStats()
+    y0, y1 = band_plan(h, world)[rank]
     rows = y1 - y0
-    bytes_launch = rows * w * (L * 4 + 4 + 12 + 2 + 6)
-    ach = bytes_launch / (float(np.mean(kms)) * 1e-3) / 1e9
+    halo_rows = 32
+    while True:                                      # planning, outside the timed region (as uploading the inputs is)
+        band = device_band(td, (y0, y1), halo_rows)
+        rigid = (td["rigidity"][y0:y1] > 0).to(torch.uint8).contiguous()
+        nonrigid = (rigid == 0).to(torch.uint8)
+        miss = torch.zeros(1, dtype=torch.int32, device="cuda")
+        bbuf = BandBuffers(rows, w, world=world)
+        banded_pass_resident(band, H_ar, q_ar, rigid, stats, buf=bbuf, interp=interp, variant=variant, want_cost=False,
+                             halo_miss=miss, masks=(nonrigid, nonrigid))
+        if stats.total(int(miss.cpu()[0])) == 0:
+            break
+        halo_rows *= 2
+        if halo_rows > 4 * h:
+            raise RuntimeError("halo search did not converge")
+    peers = (PeerVolume(L, h, w), PeerVolume(L, h, w))
+    cost_local = tuple(torch.empty((L, rows, w), dtype=torch.float32, device="cuda") for _ in range(2))
+    host = tuple(torch.empty((L, rows, w), dtype=torch.float32, pin_memory=True) for _ in range(2))
+    kernel_events = []
+
+    def step(mode, events=None):
+        gather = mode == "gather"
+        outs = tuple(p.band_ptr(y0) for p in peers) if gather else tuple(c.data_ptr() for c in cost_local)
+        r = banded_pass_resident(band, H_ar, q_ar, rigid, stats, buf=bbuf, interp=interp, range_mask="rigid_only",
+                                 variant=variant, out_ptr=outs, plane_stride=(h * w if gather else 0), halo_miss=miss,
+                                 events=events, masks=(nonrigid, nonrigid))
+        if mode == "d2h":
+            for f in range(2):
+                host[f].copy_(cost_local[f], non_blocking=True)
+        return r
+
+    res = {}
+    res["compute_only"] = timed(lambda: step("local", kernel_events))
+    res["compute_and_gather"] = timed(lambda: step("gather"))
+    res["compute_and_d2h"] = timed(lambda: step("d2h"))
     barrier()
     n_miss = stats.total(int(miss.cpu()[0]))
-    mbox_status = stats.total(int(mailbox.status() != 0)) if mailbox is not None else 0
+    kms = float(np.mean([a.elapsed_time(b) for a, b in kernel_events]))
+    for k, ms in res.items():
+        rec[k] = {"ms_per_step": ms, "value": units / (ms * 1e-3)}
+    rec.update({"parallelism": "row bands x%d, device-resident statistics: 7 NCCL collectives on the stream "
+                               "(5 x 32 KB histogram all-reduce, 2 small all-gathers), none for mu" % world,
+                "halo_rows": halo_rows, "n_miss": int(n_miss), "kernel_ms_per_launch": kms,
+                "band_rows": rows, "d2h_bytes_per_rank": int(2 * L * rows * w * 4)})
+    if verify:
+        step("gather")
+        barrier()
+        ok = None
+        if rank == 0:
+            whole = device_band(td, (0, h), 0)
+            rig_w = (td["rigidity"] > 0).to(torch.uint8)
+            one = bcv.cost_volume_pass_resident(whole, H_ar, q_ar, rig_w, interp=interp, range_mask="rigid_only", variant=variant)
+            lab = slice(_lib.STATE_LABELS, _lib.STATE_LABELS + L)
+            ok = bool(torch.equal(one["buffers"].state[:4], bbuf.state[:4]) and torch.equal(one["buffers"].state[lab], bbuf.state[lab]))
+            for f in range(2):
+                ok = ok and bool(torch.equal(peers[f].tensor(), one["cost"][f]))
+            del one
+        rec["bands_bit_exact"] = ok
+    barrier()
     for p in peers:
         p.close()
-    if mailbox is not None:
-        mailbox.close()
-    if rank == 0:
-        assert n_miss == 0, "a timed step sampled outside its halo"
-        assert mbox_status == 0, "a peer-memory all-reduce gave up waiting for a rank"
-        line = {"metric": metric, "value": units * steps / (tot_ms * 1e-3), "unit": unit, "n_gpus": world, "steps": steps,
-                "warmup": warm, "ms_per_step": tot_ms / steps, "higher_is_better": True, "scaling": "strong",
-                "vs_baseline": None, "dtype": "f64 geometry / f32 sampling", "data": "synthetic",
-                "config": {"workload": workload, "labels": L, "frames": 2, "interp": args.interp, "variant": args.variant,
-                           "range_mask": "rigid_only", "parallelism": "row bands x%d, halo %d rows, device-resident statistics "
-                           "(%s), peer-store gather to rank 0" % (world, halo_rows, "NCCL all-reduces on the stream" if mailbox is None else
-                                                                "histogram / min all-reduces as one kernel per rank over NVLink peer memory, two NCCL sums"),
-                           "l2": "flushed between timed steps"},
-                "compute_only": {"value": units * steps / (results["compute_only"][0] * 1e-3), "ms_per_step": results["compute_only"][0] / steps},
-                "clocks": clk, "e2e": None, "gpu_launches": int(launches),
-                "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
-                             "kernel": "k_cost_volume (this rank's band, stores to rank 0 over NVLink)",
-                             "kernel_ms": float(np.mean(kms))},
-                "cpu_baseline": None}
-        print(json.dumps(line))
-    dist.destroy_process_group()
+    if n_miss:
+        raise RuntimeError("a timed step sampled outside its halo")
+    return rec if rank == 0 else None

@@ -24,6 +24,51 @@ ROOT = os.path.dirname(os.path.dirname(HERE))
 REF = "/root/reference"
 
 
+class _Ch:
+    """The handful of chumpy.Ch operations correct_epipole uses (pipeline/compute_structure.py:494-504), on a
+    torch fp64 tensor with autograd standing in for chumpy's own automatic differentiation.  Lives in this
+    generator only: it lets the reference's REAL correct_epipole run (objective, BFGS call, acceptance rule
+    all untouched) so that its result can be stored and the restated analytic gradient checked against it."""
+    __array_priority__ = 1000.0          # numpy defers ndarray (op) _Ch to the reflected method, as it does for chumpy
+
+    def __init__(self, t):
+        self.t = t
+
+    @staticmethod
+    def _t(o):
+        import torch
+        if isinstance(o, _Ch):
+            return o.t
+        return torch.as_tensor(np.asarray(o, dtype=np.float64))
+
+    def __getitem__(self, i): return _Ch(self.t[i])
+    def __add__(self, o): return _Ch(self.t + self._t(o))
+    __radd__ = __add__
+    def __sub__(self, o): return _Ch(self.t - self._t(o))
+    def __rsub__(self, o): return _Ch(self._t(o) - self.t)
+    def __mul__(self, o): return _Ch(self.t * self._t(o))
+    __rmul__ = __mul__
+    def __truediv__(self, o): return _Ch(self.t / self._t(o))
+    def __rtruediv__(self, o): return _Ch(self._t(o) / self.t)
+    def __pow__(self, e): return _Ch(self.t ** e)
+    def sum(self): return _Ch(self.t.sum())
+    def __call__(self): return self.t.detach().numpy().copy()
+
+    def dr_wrt(self, wrt):
+        import torch
+        (g,) = torch.autograd.grad(self.t, wrt.t, retain_graph=True)
+        return g.detach().numpy().reshape(1, -1)
+
+
+def _ch_namespace():
+    import torch
+    ns = types.SimpleNamespace()
+    ns.array = lambda a: _Ch(torch.tensor(np.asarray(a, dtype=np.float64), requires_grad=True))
+    ns.maximum = lambda a, b: _Ch(torch.maximum(_Ch._t(a), _Ch._t(b)))
+    ns.abs = lambda a: _Ch(torch.abs(_Ch._t(a)))
+    return ns
+
+
 def import_reference():
     os.environ["MRFLOW_HOME"] = REF
     for p in (REF, REF + "/structure_refinement", REF + "/utils"):
@@ -32,7 +77,7 @@ def import_reference():
     if not hasattr(np, "float"):
         np.float = float
     ch_mod = types.ModuleType("chumpy")
-    ch_mod.ch = types.SimpleNamespace()
+    ch_mod.ch = _ch_namespace()          # only correct_epipole's few operations exist; refine_A stays disabled
     sys.modules.setdefault("chumpy", ch_mod)
     for name in ("utils.plot_debug", "utils.compute_figure", "utils.print_exception", "utils.spyder_debug"):
         m = types.ModuleType(name)
@@ -188,10 +233,21 @@ def main():
         wts = inf.get_image_weights(t["images"][1])
         for k, name in enumerate(("w_h", "w_v", "w_ne", "w_se")):
             out[name] = wts[k]
+        # --- a5: the reference's own correct_epipole (pipeline/compute_structure.py:453-511), its chumpy
+        # derivative supplied by the torch-autograd shim above
+        import contextlib, io
+        rig_thr = cv2.erode((t["rigidity"] > 0.5).astype("uint8"), np.ones((3, 3))) > 0       # :44
+        qs = []
+        for f in range(2):
+            with contextlib.redirect_stdout(io.StringIO()):
+                qs.append(np.asarray(cs.correct_epipole(res[f][0], res[f][1], np.asarray(t["epipoles"][f], dtype=np.float64), rig_thr),
+                                     dtype=np.float64))
+        out["epi_rigid"] = rig_thr
+        out["epi_q_new"] = np.array(qs)
         # --- the complete stage, reference code end to end: pipeline/compute_structure.py:37-449 with the
-        # reference's own C++ MRF solver (oracle/_ref, built by oracle/build_ref.py).  Only for epipoles
-        # outside the frame: inside, correct_epipole needs chumpy (absent here).
-        if tag != "inside":
+        # reference's own C++ MRF solver (oracle/_ref, built by oracle/build_ref.py); with the epipole inside the
+        # frame its correct_epipole runs on the shimmed chumpy.
+        if True:
             sys.path.insert(0, ROOT)
             from oracle import trws
             if trws.available():
@@ -202,8 +258,9 @@ def main():
                                        rigidity_sigma_direction=1.0, rigidity_weight_cnn=0.25, rigidity_sigma_structure=1.0,
                                        rigidity_use_structure=1, scale_structure=1, nonlinear_structure_initialization=0,
                                        occlusion_reasoning=1, tempdir=".")
-                full = cs.compute_structure(t["images"], t["flow"], t["rigidity"], occ2,
-                                            [H.copy() for H in t["homographies"]], t["epipoles"], p)
+                with contextlib.redirect_stdout(io.StringIO()):
+                    full = cs.compute_structure(t["images"], t["flow"], t["rigidity"], occ2,
+                                                [H.copy() for H in t["homographies"]], t["epipoles"], p)
                 out["full_occ"] = np.array(occ2)
                 out["full_S"] = np.array(full[0]); out["full_mu"] = np.array(full[2]); out["full_B"] = np.array(full[3])
                 out["full_q"] = np.array(full[4]); out["full_rigidity"] = np.asarray(full[5])

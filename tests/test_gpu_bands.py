@@ -41,11 +41,15 @@ def _worker(rank, world, port, queue):
                                            and np.array_equal(res_h["labels"], res["labels"])
                                            and all(torch.equal(res_h["argmins"][f], res["argmins"][f]) for f in range(2)))
         torch.cuda.synchronize(); dist.barrier()
-        # the small all-reduces through NVLink peer memory (one kernel per rank) instead of NCCL: the ops
-        # themselves, slot wrap-around included, then the whole banded pass -- same bits
+        # small all-reduces through NVLink peer memory (one kernel per rank), a building block next to NCCL: the
+        # ops themselves, slot wrap-around included; a rank that arrives 1.5 s late is waited for (the time-out is
+        # 20 s of wall clock, after which the result is poisoned and check() raises)
+        import time
         mb = sharding.PeerMailbox()
         ok = True
         for it in range(40):
+            if it == 3 and rank == 1:
+                torch.cuda.synchronize(); time.sleep(1.5)
             a = (torch.arange(256, dtype=torch.int64, device="cuda") + it) * (rank + 1)
             mb.allreduce(a, "sum_u64")
             ok &= bool(torch.equal(a, (torch.arange(256, dtype=torch.int64, device="cuda") + it) * 3))
@@ -58,13 +62,14 @@ def _worker(rank, world, port, queue):
             cl = c.tolist()
             ok &= cl[0] == 0.5 and cl[1] == -2.0 and cl[2] != cl[2] and cl[3] == 4.0
         out["mailbox_ops"] = bool(ok)
-        res_m = sharding.banded_cost_volume(t, stats, rank, world, halo=res["halo"], mailbox=mb)
-        out["mailbox_equals_nccl"] = bool(res_m["mu"] == res["mu"] and res_m["B"] == res["B"]
-                                          and np.array_equal(res_m["labels"], res["labels"])
-                                          and all(torch.equal(res_m["argmins"][f], res["argmins"][f]) for f in range(2))
-                                          and all(torch.equal(res_m["cost"][f], res_h["cost"][f]) for f in range(2)))
+        mb.check()
         out["mailbox_status"] = mb.status()
         mb.close()
+        # an epipole estimate whose 21x21 window straddles the band boundary (row 104): the bands assemble the
+        # window and every rank solves the same 441-pixel problem -- same bits as one GPU
+        t2 = dict(t, epipoles=[t["epipoles"][0] + np.array([0.0, 11.0]), t["epipoles"][1] + np.array([0.0, 12.0])])
+        res2 = sharding.banded_cost_volume(t2, stats, rank, world, halo=res["halo"])
+        out["straddle_q"] = [q.tolist() for q in res2["q"]]
         out["halo"] = res["halo"]
         y0, y1 = res["rows"]
         if rank == 0:
@@ -81,6 +86,22 @@ def _worker(rank, world, port, queue):
             for f in range(2):
                 out["equal%d" % f] = bool(torch.equal(peers[f].tensor(), whole[f][0]))
                 out["argmin_equal%d" % f] = bool(torch.equal(res["argmins"][f], whole[f][2][y0:y1]))
+            # the statistics of the banded pre-pass are the one-GPU pre-pass's, bit for bit (mu: same summation
+            # tree; B: exact median; labels: exact min / max)
+            from mrflow_b200.pipeline.build_cost_volume import cost_volume_pass_resident
+            one_r = cost_volume_pass_resident(band, t["homographies"], t["epipoles"], torch.from_numpy(
+                (t["rigidity"] > 0).astype(np.uint8)).cuda(), range_mask="rigid_only", want_cost=False)
+            mu1, B1, lab1 = pp.state_to_host(one_r["buffers"].state)
+            out["stats_bit_equal"] = bool(mu1 == res["mu"] and B1 == res["B"] and np.array_equal(lab1, res["labels"])
+                                          and all(np.array_equal(a, b) for a, b in zip(one_r["q"], res["q"])))
+            band2 = pp.Band.from_host(t2["images"], t2["flow"], t2["rigidity"], None)
+            one2 = cost_volume_pass_resident(band2, t2["homographies"], t2["epipoles"], torch.from_numpy(
+                (t2["rigidity"] > 0).astype(np.uint8)).cuda(), range_mask="rigid_only", want_cost=False)
+            mu2, B2, lab2 = pp.state_to_host(one2["buffers"].state)
+            out["straddle_equal"] = bool(all(np.array_equal(a, b) for a, b in zip(one2["q"], res2["q"])) and mu2 == res2["mu"]
+                                         and B2 == res2["B"] and np.array_equal(lab2, res2["labels"])
+                                         and all(torch.equal(res2["argmins"][f], one2["argmins"][f][y0:y1]) for f in range(2)))
+            out["straddle_moved"] = bool(any(not np.array_equal(a, b) for a, b in zip(one2["q"], t2["epipoles"])))
         torch.cuda.synchronize()
     except Exception:                       # noqa: BLE001  -- report instead of leaving the peer rank in a barrier
         out["error"] = traceback.format_exc()
@@ -124,6 +145,8 @@ def test_two_band_volume_equals_whole_frame():
     assert o["labels_close"]
     assert res[0]["host_equals_resident"] and res[1]["host_equals_resident"]
     for r in (0, 1):
-        assert res[r]["mailbox_ops"] and res[r]["mailbox_equals_nccl"] and res[r]["mailbox_status"] == 0
+        assert res[r]["mailbox_ops"] and res[r]["mailbox_status"] == 0
+    assert res[0]["straddle_q"] == res[1]["straddle_q"]
+    assert o["stats_bit_equal"] and o["straddle_equal"]
     for f in range(2):
         assert o["equal%d" % f] and o["argmin_equal%d" % f]

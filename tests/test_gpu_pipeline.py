@@ -311,7 +311,7 @@ def test_median5x5(golden):
         assert np.array_equal(dst.cpu().numpy(), ndimage.median_filter(a, size=5))
 
 
-def test_compute_structure_against_reference_end_to_end(golden):
+def test_compute_structure_against_reference_end_to_end(golden, monkeypatch):
     """mrflow_b200.pipeline.compute_structure against the REFERENCE's compute_structure run end to end
     (tests/golden, generated with the reference's own C++ MRF solver), the same solver serving as the
     unchanged consumer here (oracle/_ref, prebuilt)."""
@@ -323,6 +323,10 @@ def test_compute_structure_against_reference_end_to_end(golden):
     if not trws.available():
         pytest.skip("oracle/_ref not built")
     t = golden_triplet(tag)
+    if tag == "inside":
+        from mrflow_b200 import planeparallax as pp
+        from test_oracle_golden import pin_epipoles
+        pin_epipoles(monkeypatch, pp, "epipole_from_window", t, g)
     occ = [g["full_occ"][0], g["full_occ"][1]]
     S, Hs, mu, B, q, rig, oc = compute_structure(t["images"], t["flow"], t["rigidity"], occ,
                                                  [H.copy() for H in t["homographies"]], t["epipoles"], _params(),
@@ -373,7 +377,7 @@ def test_flow2parallax_and_structure_helpers(golden):
         assert np.array_equal(S, g["structure%d" % f], equal_nan=True)
 
 
-def test_reference_chain_stages_4_to_6(golden):
+def test_reference_chain_stages_4_to_6(golden, monkeypatch):
     """BASELINE.json configs[0] chain -- compute_structure -> optimize(override_optimization=1) -> combine_flow
     (mrflow.py:98-140) -- through the drop-in modules, against the REFERENCE's own outputs of the same chain
     (tests/golden; the reference's C++ MRF solver on both sides)."""
@@ -385,6 +389,10 @@ def test_reference_chain_stages_4_to_6(golden):
     if not trws.available():
         pytest.skip("oracle/_ref not built")
     t = golden_triplet(tag)
+    if tag == "inside":
+        from mrflow_b200 import planeparallax as pp
+        from test_oracle_golden import pin_epipoles
+        pin_epipoles(monkeypatch, pp, "epipole_from_window", t, g)
     occ = [g["full_occ"][0], g["full_occ"][1]]
     params = _params(override_optimization=1)
     S, Hs, mu, B, q, rig, oc = cs.compute_structure(t["images"], t["flow"], t["rigidity"], occ,

@@ -32,6 +32,24 @@ def _np_steps(keys):
     return hist_fn, succ_fn
 
 
+def _np_steps13(keys):
+    """numpy twins of k_s13_hist / k_s13_successor (csrc/select13.cuh)"""
+    from mrflow_b200.sharding import DistSelect13, order_key
+    k = order_key(keys).astype(np.uint64)
+
+    def hist_fn(prefix, p):
+        shift = DistSelect13.SHIFTS[p]
+        sel = k if p == 0 else k[(k >> np.uint64(shift + 13)) == np.uint64(prefix >> (shift + 13))]
+        return np.bincount(((sel >> np.uint64(shift)) & np.uint64(8191)).astype(np.int64), minlength=8192)
+
+    def succ_fn(kth):
+        le = k <= np.uint64(kth)
+        gt = k[~le]
+        gt = gt[gt != np.uint64(0xFFFFFFFFFFFFFFFF)]
+        return int(np.isnan(keys).sum()), int(le.sum()), (~int(gt.min()) & 0xFFFFFFFFFFFFFFFF) if gt.size else 0
+    return hist_fn, succ_fn
+
+
 def _worker(rank, world, port, queue):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
@@ -53,22 +71,38 @@ def _worker(rank, world, port, queue):
             out[case] = (sel.median(stats.total(mine.size)), float(np.median(full)))
             ks = sorted({0, n // 2, n - 1})
             out[case + "_kth"] = [(sel.kth(k)[0], float(np.sort(full)[k])) for k in ks]
+            h13, s13 = _np_steps13(mine)
+            out[case + "_13"] = sharding.DistSelect13(h13, s13, stats._allreduce, stats._allgather).median()
         full = rs.standard_normal(101); full[7] = np.nan
         mine = full[:50] if rank == 0 else full[50:]
         h, s = _np_steps(mine)
         out["nan"] = sharding.DistSelect(h, s, stats._allreduce).median(101)
+        h13, s13 = _np_steps13(mine)
+        out["nan13"] = sharding.DistSelect13(h13, s13, stats._allreduce, stats._allgather).median()
+        h13, s13 = _np_steps13(np.zeros(0))
+        out["empty13"] = sharding.DistSelect13(h13, s13, stats._allreduce, stats._allgather).median()
         out["total"] = stats.total(rank + 5)
         mm = stats.minmax(torch.tensor([-1.0 - rank, 3.0 + rank], dtype=torch.float64))
         out["minmax"] = mm
         out["sum"] = float(stats.device_sum(torch.tensor([1.5 + rank], dtype=torch.float64))[0])
 
-        class B:            # a band of a 100-row frame
-            frame_h, w = 100, 200
-            y0, rows = (0, 48) if rank == 0 else (48, 52)
-        q = np.array([90.3, 70.6])                         # window rows 60..80 -> rank 1's band
-        out["epi"] = stats.epipole(lambda: q + 0.125 * (rank + 1), q, B).tolist()
-        out["epi_outside"] = stats.epipole(lambda: q * 0, np.array([500.0, 70.0]), B).tolist()
-        out["epi_straddle"] = stats.epipole(lambda: q * 0, np.array([90.0, 50.0]), B).tolist()
+        # the 21x21 epipole window of a 100-row frame cut into bands 0..48 / 48..100: a window inside rank 1's
+        # band and one that straddles the boundary both add up to the whole-frame window on both ranks, and
+        # both ranks then find the same epipole (compute_structure.py:453-511)
+        from mrflow_b200 import planeparallax as pp
+        rs2 = np.random.RandomState(11)
+        y0, y1 = (0, 48) if rank == 0 else (48, 100)
+        yy, xx = np.mgrid[:100, :200].astype(np.float64)
+        for name, qe in (("epi_inside", np.array([90.3, 70.6])), ("epi_straddle", np.array([90.0, 50.0]))):
+            qt = qe + np.array([1.5, -0.8])                # the objective's minimum: flow perpendicular to (qt - p)
+            u = torch.from_numpy((-(yy - qt[1]) * 0.01 + 0.002 * rs2.standard_normal(xx.shape)).astype(np.float32))
+            v = torch.from_numpy(((xx - qt[0]) * 0.01 + 0.002 * rs2.standard_normal(xx.shape)).astype(np.float32))
+            rigid = torch.ones((100, 200), dtype=torch.uint8); rigid[65:70, 85:90] = 0; rigid[45:50, 95:99] = 0
+            whole = pp.correct_epipole(u, v, qe, rigid)
+            mine_q = pp.correct_epipole(u[y0:y1], v[y0:y1], qe, rigid[y0:y1], y0=y0, frame_h=100, stats=stats)
+            out[name] = (mine_q.tolist(), whole.tolist(), float(np.linalg.norm(whole - qe)))
+        out["epi_outside"] = pp.correct_epipole(u[y0:y1], v[y0:y1], np.array([500.0, 70.0]), rigid[y0:y1], y0=y0,
+                                                frame_h=100, stats=stats).tolist()
     finally:
         q_out = out
         dist.destroy_process_group()
@@ -90,12 +124,16 @@ def test_distributed_statistics_gloo_world2():
         o = res[r]
         for case in ("odd", "even", "dup", "tiny"):
             assert o[case][0] == o[case][1], (case, o[case])
+            assert o[case + "_13"] == o[case][1], (case, o[case + "_13"], o[case][1])
             for got, want in o[case + "_kth"]:
                 assert got == want
-        assert np.isnan(o["nan"])
+        assert np.isnan(o["nan"]) and np.isnan(o["nan13"]) and np.isnan(o["empty13"])
         assert o["total"] == 11 and o["minmax"] == (-2.0, 4.0) and o["sum"] == 4.0
-        assert o["epi"] == [90.3 + 0.25, 70.6 + 0.25]      # computed by rank 1, bit-exact on both
-        assert o["epi_outside"] == [500.0, 70.0] and o["epi_straddle"] == [90.0, 50.0]
+        for name in ("epi_inside", "epi_straddle"):
+            got, whole, moved = o[name]
+            assert got == whole, (name, got, whole)         # bands == whole frame, bit for bit, on both ranks
+            assert 0 < moved < 10                           # and the BFGS did run and move the epipole
+        assert o["epi_outside"] == [500.0, 70.0]
 
 
 def test_band_plan_and_halo():

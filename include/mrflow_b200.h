@@ -241,6 +241,10 @@ typedef struct {
 #define MRF_VARIANT_GATHER 1
 #define MRF_VARIANT_OCC2   16 /* OR-able tuning flag: compile for 2 resident blocks / SM (128
                                  registers per thread) instead of 3 */
+#define MRF_VARIANT_OCC4   32 /* OR-able: 4 resident blocks / SM (64 registers, 40 KB staged window) */
+#define MRF_VARIANT_WARPFAST 64 /* OR-able, bicubic only: a warp-uniform straight-line fast path round the
+                                   gather instead of per-lane branches (same arithmetic; measured 7 % slower
+                                   at 80 registers, profiles/r2d_kernel_variants_sintel.jsonl; kept for comparison) */
 
 /* ref_ch: fp64 [rows,w,3] channels of the reference frame band; nb_texels as described;
  * labels: fp64 [n_labels] structure_range (device); nonrigid/occluded: uint8 [rows,w], !=0

@@ -34,6 +34,7 @@ namespace mrf {
 constexpr int kTX = 32, kTY = 8, kThreads = kTX * kTY;
 constexpr int kMaxLabels = 256;
 constexpr int kWinCap = 3072;      // staged window capacity in texels (48 KB)
+constexpr int kWinCap4 = 2560;     // ... with four blocks per SM (40 KB)
 constexpr int kWinMaxW = 384;      // widest staged row
 
 struct CVArgs {
@@ -59,6 +60,7 @@ struct CVArgs {
   long long plane_stride;   // elements between label planes of the LHW volume
   const double* state;      // device-resident scalars (mu, B, labels) or nullptr
   int frame;
+  int win_cap;              // staged window capacity in texels (<= kWinCap; smaller when 4 blocks share an SM)
   double wm1, hm1;          // (double)(w - 1), (double)(frame_h - 1)
   double s2, rs2;           // rho_param^2 and RN(1 / s2)
 };
@@ -270,7 +272,7 @@ __device__ __noinline__ float band_sample_cost(const CVArgs& a, float xf, float 
 
 struct __align__(16) LabelRec { double ab, den, rden, safe; };   // safe: 1.0 / 0.0
 
-template <int INTERP, bool STAGED, int OCC, int LAYOUT>
+template <int INTERP, bool STAGED, int OCC, int LAYOUT, bool WF>
 __global__ void __launch_bounds__(kThreads, OCC)
 k_cost_volume(const __grid_constant__ CVArgs a) {
   extern __shared__ __align__(128) unsigned char dyn_smem[];
@@ -393,7 +395,7 @@ k_cost_volume(const __grid_constant__ CVArgs a) {
         if (x1 >= x0 && y1 >= y0) {
           W = x1 - x0 + 1; Hh = y1 - y0 + 1;
           if (W > kWinMaxW) { x0 += (W - kWinMaxW) / 2; W = kWinMaxW; }
-          const int hmax = kWinCap / W;
+          const int hmax = a.win_cap / W;
           if (Hh > hmax) { y0 += (Hh - hmax) / 2; Hh = hmax; }
           X0 = x0; Y0 = y0;
         }
@@ -540,6 +542,80 @@ k_cost_volume(const __grid_constant__ CVArgs a) {
       else *(int32_t*)(cost_p + cost_off) = (int32_t)(cf * a.i32_scale);
       if (l == 0 || cf < best) { best = cf; best_l = l; }     // np.argmin: first minimum
     }
+  } else if constexpr (WF) {
+    // Bicubic, warp-uniform form.  Geometry for every lane (a dead lane -- non-rigid / occluded pixel -- computes
+    // along and is discarded at the end); if EVERY lane of the warp is either dead or has an exact, in-frame,
+    // in-window sample -- the overwhelmingly common case -- the 16-tap gather, residual and rho run as one
+    // straight line under a warp-uniform branch: no divergence bookkeeping, and the compiler is free to overlap
+    // the gathers of this label with the fp64 tail.  Otherwise the warp takes the general per-lane form for this
+    // label.  Same operations in the same order on every path.
+    const unsigned full = __activemask();
+    const bool warp_dead = __all_sync(full, dead);            // nothing to sample (and, unstaged, no window to read)
+    for (int l = 0; l < L; ++l, cost_off += cost_step) {
+      double ab, dl, rdl;
+      asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(ab), "=d"(dl) : "r"(lab_s + (uint32_t)l * 32u));
+      asm volatile("ld.shared.f64 %0, [%1];" : "=d"(rdl) : "r"(lab_s + (uint32_t)l * 32u + 16u));
+      const double r = div_rc(ab * n_fast, dl, rdl);          // r = A*B*n / (B*A/mu - 1)  :221
+      const double xn = xk + r * t1, yn = yk + r * t2;        // :224-235
+      const double den = (xn * a.H.m[6] + yn * a.H.m[7]) + a.H.m[8];   // interpolate_through_H.py:31-35
+      const double Xn = (xn * a.H.m[0] + yn * a.H.m[1]) + a.H.m[2];
+      const double Yn = (xn * a.H.m[3] + yn * a.H.m[4]) + a.H.m[5];
+      const double rd = rcp_rn_tame(den);
+      const double X = div_rc(Xn, den, rd);
+      const double Y = div_rc(Yn, den, rd);
+      const bool exact = tame_divisor(den);
+      const bool inside = (X >= 0.0) && (X <= a.wm1) && (Y >= 0.0) && (Y <= a.hm1);   // :39
+      const float xf = (float)X, yf = (float)Y;               // interpolation.py:77-78
+      const int sx = __float2int_rn(xf * 32.0f), sy = __float2int_rn(yf * 32.0f);
+      const int ix0 = (sx >> 5) - kOff, iy0 = (sy >> 5) - kOff;
+      const bool inwin = (unsigned)(ix0 - fx_lo) <= (unsigned)fx_span && (unsigned)(iy0 - fy_lo) <= (unsigned)fy_span;
+      const bool ok = exact && inside && inwin;
+      float cf;
+      if (!warp_dead && __all_sync(full, ok || dead)) {
+        const uint32_t p0 = ok ? (win_s + (uint32_t)iy0 * pitch + (uint32_t)ix0 * 16u) : win_base;
+        float wxa[4], wya[4];
+        lds128(wt_s + (uint32_t)(sx & 31) * 16u, wxa[0], wxa[1], wxa[2], wxa[3]);
+        lds128(wt_s + (uint32_t)(sy & 31) * 16u, wya[0], wya[1], wya[2], wya[3]);
+        F3 J;
+  #pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          F3 row;
+  #pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const float wgt = wya[j] * wxa[i];
+            float tx, ty, tz, tw;
+            lds128(p0 + (uint32_t)j * pitch + (uint32_t)i * 16u, tx, ty, tz, tw);
+            const float px = tx * wgt, py = ty * wgt, pz = tz * wgt;
+            if (i == 0) { row.x = px; row.y = py; row.z = pz; }
+            else        { row.x = row.x + px; row.y = row.y + py; row.z = row.z + pz; }
+          }
+          if (j == 0) J = row;
+          else { J.x = J.x + row.x; J.y = J.y + row.y; J.z = J.z + row.z; }
+        }
+        double r0, r1, r2;                                    // reference-frame channels of this pixel
+        asm volatile("ld.shared.f64 %0, [%1];" : "=d"(r0) : "r"(ref_s));
+        asm volatile("ld.shared.f64 %0, [%1];" : "=d"(r1) : "r"(ref_s + (uint32_t)(kThreads * 8)));
+        asm volatile("ld.shared.f64 %0, [%1];" : "=d"(r2) : "r"(ref_s + (uint32_t)(kThreads * 16)));
+        const double e0 = ((double)J.x - r0) * a.cw0;         // :274
+        const double e1 = ((double)J.y - r1) * a.cw1;
+        const double e2 = ((double)J.z - r2) * a.cw2;
+        const double Iz = div_rc((e0 + e1) + e2, 3.0, kThird);
+        double cst;
+        if (lor_fast) cst = log_ge1(1.0 + div_rc(Iz * Iz, a.s2, a.rs2));
+        else cst = (a.rho == MRF_RHO_NONE) ? Iz : rho_eval(a.rho, Iz * Iz, a.rho_param);
+        cf = dead ? cost_dead : (float)cst;
+      } else {
+        cf = cost_dead;
+        if (!dead) {
+          const double r0 = s_ref[0][threadIdx.x], r1 = s_ref[1][threadIdx.x], r2 = s_ref[2][threadIdx.x];
+          if (!exact) cf = slow_sample_cost<INTERP>(a, ab, dl, n, xk, yk, t1, t2, r0, r1, r2);
+          else if (inside) cf = band_sample_cost<INTERP>(a, xf, yf, r0, r1, r2);   // global gather (window or border miss)
+        }
+      }
+      if (LAYOUT == MRF_LAYOUT_LHW_F32) __stcs((float*)(cost_p + cost_off), cf);
+      else *(int32_t*)(cost_p + cost_off) = (int32_t)(cf * a.i32_scale);
+      if (l == 0 || cf < best) { best = cf; best_l = l; }     // np.argmin: first minimum
+    }
   } else {
     for (int l = 0; l < L; ++l, cost_off += cost_step) {
       float cf = cost_dead;
@@ -675,23 +751,29 @@ extern "C" int mrf_cost_volume(const mrf_costvol_params* p, const double* ref_ch
 
   const dim3 grid(cdiv(p->w, kTX), cdiv(p->rows, kTY));
   const bool staged = ((p->variant & 1) != MRF_VARIANT_GATHER);
-  const int occ = (p->variant & MRF_VARIANT_OCC2) ? 2 : 3;
-  const size_t smem = staged ? (size_t)kWinCap * 16 : 0;
+  const int occ = (p->variant & MRF_VARIANT_OCC2) ? 2 : ((p->variant & MRF_VARIANT_OCC4) ? 4 : 3);
+  const bool wf = (p->variant & MRF_VARIANT_WARPFAST) != 0;
+  a.win_cap = (occ == 4) ? kWinCap4 : kWinCap;
+  const size_t smem = staged ? (size_t)a.win_cap * 16 : 0;
   cudaError_t e = cudaSuccess;
-#define MRF_LAUNCH(I, ST, OC, LY)                                                                         \
-  do {                                                                                                    \
-    static bool attr_set = false;   /* once per instantiation (and never inside a stream capture) */     \
-    if (smem && !attr_set) {                                                                              \
-      e = cudaFuncSetAttribute(k_cost_volume<I, ST, OC, LY>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
-                               (int)smem);                                                                \
-      attr_set = (e == cudaSuccess);                                                                      \
-    }                                                                                                     \
-    if (e == cudaSuccess) k_cost_volume<I, ST, OC, LY><<<grid, kThreads, smem, S(stream)>>>(a);           \
+#define MRF_LAUNCH(I, ST, OC, LY, WFv)                                                                         \
+  do {                                                                                                         \
+    /* the opt-in is per device and per instantiation: remember it per device (one bit each) */               \
+    static std::atomic<unsigned long long> attr_set{0};                                                       \
+    int dev_ = 0;                                                                                              \
+    if (smem) cudaGetDevice(&dev_);                                                                            \
+    if (smem && !((attr_set.load() >> (dev_ & 63)) & 1ull)) {                                                  \
+      e = cudaFuncSetAttribute(k_cost_volume<I, ST, OC, LY, WFv>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                               (int)smem);                                                                     \
+      if (e == cudaSuccess) attr_set.fetch_or(1ull << (dev_ & 63));                                            \
+    }                                                                                                          \
+    if (e == cudaSuccess) k_cost_volume<I, ST, OC, LY, WFv><<<grid, kThreads, smem, S(stream)>>>(a);           \
   } while (0)
-#define MRF_LAUNCH_LY(I, ST, OC) do { if (p->layout == MRF_LAYOUT_LHW_F32) MRF_LAUNCH(I, ST, OC, MRF_LAYOUT_LHW_F32); else MRF_LAUNCH(I, ST, OC, MRF_LAYOUT_HWL_I32); } while (0)
-#define MRF_LAUNCH_ST(I, OC) do { if (staged) MRF_LAUNCH_LY(I, true, OC); else MRF_LAUNCH_LY(I, false, OC); } while (0)
-#define MRF_LAUNCH_OC(I) do { if (occ == 2) MRF_LAUNCH_ST(I, 2); else MRF_LAUNCH_ST(I, 3); } while (0)
-  if (p->interp == MRF_INTERP_CUBIC) MRF_LAUNCH_OC(MRF_INTERP_CUBIC); else MRF_LAUNCH_OC(MRF_INTERP_LINEAR);
+#define MRF_LAUNCH_LY(I, ST, OC, WFv) do { if (p->layout == MRF_LAYOUT_LHW_F32) MRF_LAUNCH(I, ST, OC, MRF_LAYOUT_LHW_F32, WFv); else MRF_LAUNCH(I, ST, OC, MRF_LAYOUT_HWL_I32, WFv); } while (0)
+#define MRF_LAUNCH_ST(I, OC, WFv) do { if (staged) MRF_LAUNCH_LY(I, true, OC, WFv); else MRF_LAUNCH_LY(I, false, OC, WFv); } while (0)
+#define MRF_LAUNCH_OC(I, WFv) do { if (occ == 2) MRF_LAUNCH_ST(I, 2, WFv); else if (occ == 4) MRF_LAUNCH_ST(I, 4, WFv); else MRF_LAUNCH_ST(I, 3, WFv); } while (0)
+  if (p->interp == MRF_INTERP_CUBIC) { if (wf) MRF_LAUNCH_OC(MRF_INTERP_CUBIC, true); else MRF_LAUNCH_OC(MRF_INTERP_CUBIC, false); }
+  else MRF_LAUNCH_OC(MRF_INTERP_LINEAR, false);
 #undef MRF_LAUNCH_LY
 #undef MRF_LAUNCH_OC
 #undef MRF_LAUNCH_ST

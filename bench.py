@@ -429,6 +429,7 @@ def run_ours(args):
             times.append(time.perf_counter() - t0)
         e2e["single_call"] = {"value": units_per_triplet / float(np.median(times)), "calls": n1,
                               "ms_per_call_median": float(np.median(times)) * 1e3, "ms_per_call_max": float(max(times)) * 1e3,
+                              "ms_per_call_all": [round(x * 1e3, 3) for x in times],
                               "api": "mrflow_b200.pipeline.build_cost_volume + combine_flow, one triplet at a time"}
 
     # ---- the CPU leg (rank 0): the oracle as the checker of the volumes just timed and, at N = 1, as the baseline

@@ -275,6 +275,11 @@ typedef struct {
   int have_box[2];
   int box[2][4];
   int n_labels;
+  int fused;                   /* 0 (default): nine short launches; 1: the same pre-pass as ONE persistent
+                                  cooperative kernel with grid barriers -- identical results.  Measured at Sintel
+                                  size (profiles/r2g_*): 92 us alone against ~105 us for the launches, but a
+                                  cooperative grid that spins at barriers takes the SMs from the cost-volume
+                                  kernels of other triplets in flight (0.68 vs 0.63 ms per triplet), hence opt-in */
 } mrf_front_params;
 size_t mrf_front_scratch_bytes(void);
 int mrf_cost_volume_front(const mrf_front_params* p_host, const float* u0, const float* v0,

@@ -34,7 +34,7 @@ class FrontParams(C.Structure):
     """mrf_front_params"""
     _fields_ = [("rows", C.c_int), ("w", C.c_int), ("y0", C.c_int), ("frame_h", C.c_int),
                 ("Hinv0", C.c_double * 9), ("Hinv1", C.c_double * 9), ("q0", C.c_double * 2), ("q1", C.c_double * 2),
-                ("B_fwd", C.c_double), ("have_box", C.c_int * 2), ("box", (C.c_int * 4) * 2), ("n_labels", C.c_int)]
+                ("B_fwd", C.c_double), ("have_box", C.c_int * 2), ("box", (C.c_int * 4) * 2), ("n_labels", C.c_int), ("fused", C.c_int)]
 
 
 STATE_MU, STATE_B, STATE_MINMAX, STATE_NANFLAG, STATE_LABELS, STATE_WORDS = 0, 2, 4, 8, 16, 16 + 256

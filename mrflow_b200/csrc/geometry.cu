@@ -4,6 +4,7 @@
 // operation (compiled with -fmad=false) so results are bit-identical wherever the reference only
 // uses IEEE +,-,*,/,sqrt; transcendental functions (atan2, sin, exp, I0e) agree to a few ulp.
 #include "select13.cuh"
+#include <cooperative_groups.h>
 #include <stdarg.h>
 #include <math.h>
 
@@ -383,12 +384,38 @@ static inline unsigned grid_for(long long n, int threads = 256) {
 // Fused forms of the pre-pass for the device-resident path (same per-pixel arithmetic as the
 // kernels above; fewer, fatter launches).
 constexpr int kFrontBlocks = 592;   // 4 x 148
-// blocks of the candidates kernel: each zeroes and flushes an 8192-bin shared histogram, so two fat blocks
+// blocks of the candidates kernel: each zeroes and flushes an 8192-bin shared histogram, so four fat blocks
 // per SM at most
 static inline unsigned front_cand_blocks(long long n) {
   long long b = (n + 1023) / 1024;
-  if (b > 2 * kSMs) b = 2 * kSMs;
+  if (b > 4 * kSMs) b = 4 * kSMs;
   return (unsigned)(b < 1 ? 1 : b);
+}
+
+// one pixel, one frame: residual flow -> parallax (a1 + a2); d = ||p - q||
+__device__ __forceinline__ double front_parallax_px(float u, float v, int x, int y, const Mat3& Hinv, const Pt2 q, double& d) {
+  const float x2 = (float)((double)x + (double)u);
+  const float y2 = (float)((double)y + (double)v);
+  float X, Y;
+  persp_f32(x2, y2, Hinv, X, Y);
+  const float ur = X - (float)x, vr = Y - (float)y;
+  const double fx = q.x - (double)x, fy = q.y - (double)y;
+  d = sqrt(fx * fx + fy * fy);
+  const double dn = fmax(d, 1e-3);
+  return (double)ur * (fx / dn) + (double)vr * (fy / dn);
+}
+
+// one pixel: the candidate ratio template / target of compute_structure.py:209-219 (B_fwd fixed)
+__device__ __forceinline__ double front_candidate_px(double p0, double p1, int x, int y, const Pt2 q0, const Pt2 q1, double mu0,
+                                                     double mu1, double B_fwd) {
+  // dists_normed = foe_dists/mu with foe_dists from flow2parallax (q - x)
+  const double fx0 = q0.x - (double)x, fy0 = q0.y - (double)y;
+  const double dn0 = sqrt(fx0 * fx0 + fy0 * fy0) / mu0;
+  const double fx1 = q1.x - (double)x, fy1 = q1.y - (double)y;
+  const double dn1 = sqrt(fx1 * fx1 + fy1 * fy1) / mu1;
+  const double target = p1 / (B_fwd * (p1 / mu1 - dn1));
+  const double templ = mu1 / mu0 * p0 / (p0 / mu0 - dn0);
+  return templ / target;
 }
 
 // both frames: residual flow -> parallax (a1 + a2) and the block partial sums behind mu
@@ -406,17 +433,8 @@ k_front_parallax(const float* __restrict__ u0, const float* __restrict__ v0, con
     const int y = yl + y0;
 #pragma unroll
     for (int f = 0; f < 2; ++f) {
-      const float* u = f ? u1 : u0; const float* v = f ? v1 : v0;
-      const Mat3& Hinv = f ? Hinv1 : Hinv0; const Pt2 q = f ? q1 : q0;
-      const float x2 = (float)((double)x + (double)u[i]);
-      const float y2 = (float)((double)y + (double)v[i]);
-      float X, Y;
-      persp_f32(x2, y2, Hinv, X, Y);
-      const float ur = X - (float)x, vr = Y - (float)y;
-      const double fx = q.x - (double)x, fy = q.y - (double)y;
-      const double d = sqrt(fx * fx + fy * fy);
-      const double dn = fmax(d, 1e-3);
-      (f ? par1 : par0)[i] = (double)ur * (fx / dn) + (double)vr * (fy / dn);
+      double d;
+      (f ? par1 : par0)[i] = front_parallax_px((f ? u1 : u0)[i], (f ? v1 : v0)[i], x, y, f ? Hinv1 : Hinv0, f ? q1 : q0, d);
       if (f) acc1 += d; else acc0 += d;
     }
   }
@@ -491,14 +509,7 @@ k_front_candidates13(const double* __restrict__ par0, const double* __restrict__
         const int yl = (int)(i / w);
         const int x = (int)(i - (long long)yl * w);
         const int y = yl + y0;
-        // :209-219; dists_normed = foe_dists/mu with foe_dists from flow2parallax (q - x)
-        const double fx0 = q0.x - (double)x, fy0 = q0.y - (double)y;
-        const double dn0 = sqrt(fx0 * fx0 + fy0 * fy0) / mu0;
-        const double fx1 = q1.x - (double)x, fy1 = q1.y - (double)y;
-        const double dn1 = sqrt(fx1 * fx1 + fy1 * fy1) / mu1;
-        const double target = p1 / (B_fwd * (p1 / mu1 - dn1));
-        const double templ = mu1 / mu0 * p0 / (p0 / mu0 - dn0);
-        val = templ / target;
+        val = front_candidate_px(p0, p1, x, y, q0, q1, mu0, mu1, B_fwd);          // :209-219
       }
     }
     // warp-aggregated compaction (order is irrelevant for order statistics)
@@ -517,22 +528,18 @@ k_front_candidates13(const double* __restrict__ par0, const double* __restrict__
 // both frames: parallax -> normed structure (a3) and block partial min / max / NaN of the
 // range-masked structure (build_cost_volume.py:154-169)
 struct Box4 { int x0, x1, y0, y1, on; };
-__global__ void __launch_bounds__(256)
-k_front_structures(const double* __restrict__ par0, const double* __restrict__ par1, int rows, int w, int y0, Pt2 q0,
-                   Pt2 q1, double B_fwd, const uint8_t* __restrict__ zero_mask, Box4 b0, Box4 b1,
-                   double* __restrict__ S0, double* __restrict__ S1, double* __restrict__ st,
-                   double* __restrict__ part, const void* __restrict__ sel,
-                   const unsigned long long* __restrict__ gathered, int world) {
-  __shared__ double smin[2][8], smax[2][8];
-  __shared__ int snan[2][8];
+// sweep of this block over the band: parallax -> normed structure, running min / max / NaN of the range-masked
+// structure; the block's result goes to part[(f * nblocks + block) * 3 ..]
+__device__ __forceinline__ void front_structures_block(const double* __restrict__ par0, const double* __restrict__ par1, int rows,
+                                                       int w, int y0, const Pt2 q0, const Pt2 q1, double B_fwd, double B0,
+                                                       double mu0, double mu1, const uint8_t* __restrict__ zero_mask,
+                                                       const Box4& b0, const Box4& b1, double* __restrict__ S0,
+                                                       double* __restrict__ S1, double* __restrict__ part, unsigned block,
+                                                       unsigned nblocks, double (*smin)[8], double (*smax)[8], int (*snan)[8]) {
   const long long n = (long long)rows * w;
-  // B_b = median(template / target)  compute_structure.py:221 -- the same bits in every block
-  const double mu0 = st[MRF_STATE_MU], mu1 = st[MRF_STATE_MU + 1], B0 = s13_median(sel, gathered, world);
-  if (blockIdx.x == 0 && threadIdx.x == 0) { st[MRF_STATE_B] = B0; st[MRF_STATE_B + 1] = B_fwd; }
   double lo[2] = {INFINITY, INFINITY}, hi[2] = {-INFINITY, -INFINITY};
   int nan[2] = {0, 0};
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n;
-       i += (long long)gridDim.x * blockDim.x) {
+  for (long long i = block * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)nblocks * blockDim.x) {
     const int yl = (int)(i / w);
     const int x = (int)(i - (long long)yl * w);
     const int y = yl + y0;
@@ -567,9 +574,24 @@ k_front_structures(const double* __restrict__ par0, const double* __restrict__ p
     const int f = threadIdx.x;
     double a = smin[f][0], b = smax[f][0]; int c = snan[f][0];
     for (int k = 1; k < 8; ++k) { a = fmin(a, smin[f][k]); b = fmax(b, smax[f][k]); c |= snan[f][k]; }
-    double* o = part + ((size_t)f * gridDim.x + blockIdx.x) * 3;
+    double* o = part + ((size_t)f * nblocks + block) * 3;
     o[0] = a; o[1] = b; o[2] = (double)c;
   }
+}
+
+__global__ void __launch_bounds__(256)
+k_front_structures(const double* __restrict__ par0, const double* __restrict__ par1, int rows, int w, int y0, Pt2 q0,
+                   Pt2 q1, double B_fwd, const uint8_t* __restrict__ zero_mask, Box4 b0, Box4 b1,
+                   double* __restrict__ S0, double* __restrict__ S1, double* __restrict__ st,
+                   double* __restrict__ part, const void* __restrict__ sel,
+                   const unsigned long long* __restrict__ gathered, int world) {
+  __shared__ double smin[2][8], smax[2][8];
+  __shared__ int snan[2][8];
+  // B_b = median(template / target)  compute_structure.py:221 -- the same bits in every block
+  const double mu0 = st[MRF_STATE_MU], mu1 = st[MRF_STATE_MU + 1], B0 = s13_median(sel, gathered, world);
+  if (blockIdx.x == 0 && threadIdx.x == 0) { st[MRF_STATE_B] = B0; st[MRF_STATE_B + 1] = B_fwd; }
+  front_structures_block(par0, par1, rows, w, y0, q0, q1, B_fwd, B0, mu0, mu1, zero_mask, b0, b1, S0, S1, part, blockIdx.x,
+                         gridDim.x, smin, smax, snan);
 }
 
 // final (NaN-ignoring) min / max of both frames and the NaN flags -> state; row bands all-reduce these
@@ -602,11 +624,9 @@ k_front_minmax(const double* __restrict__ part, int nblocks, double* __restrict_
   }
 }
 
-// final min/max of both frames -> state, then np.linspace(1.5*min, 1.5*max, L) (see k_label_range)
-__global__ void __launch_bounds__(256)
-k_front_labels(const double* __restrict__ part, int nblocks, double* __restrict__ st, int L) {
-  __shared__ double smin[8], smax[8];
-  __shared__ int snan[8];
+// final min/max of both frames -> state, then np.linspace(1.5*min, 1.5*max, L) (see k_label_range); one block
+__device__ __forceinline__ void front_labels_block(const double* __restrict__ part, int nblocks, double* __restrict__ st, int L,
+                                                   double* smin, double* smax, int* snan) {
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   for (int f = 0; f < 2; ++f) {
     double lo = INFINITY, hi = -INFINITY; int nan = 0;
@@ -644,6 +664,195 @@ k_front_labels(const double* __restrict__ part, int nblocks, double* __restrict_
   yv = yv + start;
   if (i == L - 1) yv = stop;
   st[MRF_STATE_LABELS + i] = yv;
+}
+
+__global__ void __launch_bounds__(256)
+k_front_labels(const double* __restrict__ part, int nblocks, double* __restrict__ st, int L) {
+  __shared__ double smin[8], smax[8];
+  __shared__ int snan[8];
+  front_labels_block(part, nblocks, st, L, smin, smax, snan);
+}
+
+// ---------------------------------------------------------------------------------------------
+// The whole pre-pass of a frame on one GPU as ONE persistent cooperative kernel (grid barriers instead of
+// launches): parallax of both frames and the sums behind mu | mu, valid pixels, compacted candidate ratios and the
+// first radix pass of their exact median | further radix passes only until the class of the median holds at most
+// kFusedCap keys | gather of that class (and the smallest key above it) | rank selection of the two middle order
+// statistics in shared memory, B_b, normed structures, range min / max | label set.  Same per-pixel arithmetic and
+// the same summation tree for mu as the stepwise kernels (and as mrf_front_mu_whole for row bands), so the state it
+// leaves is bit-identical to theirs.
+constexpr int kFusedCap = 1024;
+struct FrontFusedArgs {
+  const float *u0, *v0, *u1, *v1;
+  const uint8_t *rigid, *zero_mask;
+  int rows, w, L;
+  Mat3 Hinv0, Hinv1;
+  Pt2 q0, q1;
+  double B_fwd;
+  Box4 b0, b1;
+  double *par0, *par1, *S0, *S1, *cand;
+  int* count;
+  double* st;
+  double* partial;            // 4096 doubles: 2 x kRedBlocks distance sums, later 6 x gridDim range partials
+  void* sel;                  // select13 scratch (zeroed); st[7] = gather counter
+  unsigned long long* gbuf;   // kFusedCap keys
+};
+
+__global__ void __launch_bounds__(256, 3)
+k_front_fused(const __grid_constant__ FrontFusedArgs a) {
+  namespace cg = cooperative_groups;
+  cg::grid_group grid = cg::this_grid();
+  __shared__ unsigned int sh[kS13Bins];
+  __shared__ unsigned long long s_tmp[16];
+  __shared__ unsigned long long s_keys[kFusedCap];
+  __shared__ double s_mu[2];
+  __shared__ double s_red[32];
+  __shared__ double smin[2][8], smax[2][8];
+  __shared__ int snan[2][8];
+  const unsigned G = gridDim.x;
+  const long long n = (long long)a.rows * a.w;
+  unsigned long long* st13 = s13_st(a.sel);
+
+  // ---- phase 1: parallax, in the 1024 virtual blocks of k_front_parallax (same partial sums, same bits of mu)
+  for (unsigned v = blockIdx.x; v < (unsigned)kRedBlocks; v += G) {
+    double acc0 = 0.0, acc1 = 0.0;
+    for (long long i = v * (long long)kRedThreads + threadIdx.x; i < n; i += (long long)kRedBlocks * kRedThreads) {
+      const int y = (int)(i / a.w);
+      const int x = (int)(i - (long long)y * a.w);
+      double d0, d1;
+      a.par0[i] = front_parallax_px(a.u0[i], a.v0[i], x, y, a.Hinv0, a.q0, d0);
+      a.par1[i] = front_parallax_px(a.u1[i], a.v1[i], x, y, a.Hinv1, a.q1, d1);
+      acc0 += d0; acc1 += d1;
+    }
+    acc0 = block_sum(acc0, s_red);
+    acc1 = block_sum(acc1, s_red);
+    if (threadIdx.x == 0) { a.partial[v] = acc0; a.partial[kRedBlocks + v] = acc1; }
+  }
+  s13_zero(sh);
+  grid.sync();
+
+  // ---- phase 2: mu, candidates, first radix pass
+  front_mu_from_partials(a.partial, (double)n, s_mu, s_red);
+  if (blockIdx.x == 0 && threadIdx.x == 0) { a.st[MRF_STATE_MU] = s_mu[0]; a.st[MRF_STATE_MU + 1] = s_mu[1]; }
+  const double mu0 = s_mu[0], mu1 = s_mu[1];
+  unsigned int my_nan = 0;
+  for (long long i0 = blockIdx.x * (long long)blockDim.x; i0 < n; i0 += (long long)G * blockDim.x) {
+    const long long i = i0 + threadIdx.x;
+    bool valid = false;
+    double val = 0.0;
+    if (i < n) {
+      const double p0 = a.par0[i], p1 = a.par1[i];
+      valid = (fabs(p0) > 0.1) && (fabs(p1) > 0.1) && (a.rigid[i] != 0);
+      if (valid) {
+        const int y = (int)(i / a.w);
+        const int x = (int)(i - (long long)y * a.w);
+        val = front_candidate_px(p0, p1, x, y, a.q0, a.q1, mu0, mu1, a.B_fwd);
+        if (val != val) ++my_nan;
+      }
+    }
+    const unsigned m = __ballot_sync(0xffffffffu, valid);
+    const int lane = threadIdx.x & 31;
+    int base = 0;
+    if (lane == 0 && m) base = atomicAdd(a.count, __popc(m));
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (valid) a.cand[base + __popc(m & ((1u << lane) - 1u))] = val;
+    s13_count(sh, valid, (unsigned)(order_key(val) >> s13_shift(0)));
+  }
+  for (int o = 16; o > 0; o >>= 1) my_nan += __shfl_down_sync(0xffffffffu, my_nan, o);
+  if ((threadIdx.x & 31) == 0 && my_nan) atomicAdd(&st13[3], (unsigned long long)my_nan);
+  __syncthreads();
+  s13_flush(sh, s13_hist(a.sel, 0));
+  grid.sync();
+
+  // ---- radix passes until the median's class is small
+  const size_t nc = (size_t)max(*a.count, 0);
+  const size_t stride = (size_t)G * blockDim.x;
+  const size_t warp_first = blockIdx.x * (size_t)blockDim.x + threadIdx.x - (threadIdx.x & 31);
+  unsigned long long prefix = 0, k_rem = 0, n_total = 0, class_count = 0;
+  int pass = 0;
+  while (true) {
+    s13_resolve_digit(s13_hist(a.sel, pass), pass, prefix, k_rem, n_total, class_count, s_tmp);
+    ++pass;
+    if (class_count <= (unsigned long long)kFusedCap || pass == kS13Passes) break;
+    s13_zero(sh);
+    __syncthreads();
+    const int shift = s13_shift(pass);
+    const unsigned long long himask = s13_himask(pass);
+    for (size_t base = warp_first; base < nc; base += 4 * stride) {
+      unsigned long long kk[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const size_t i = base + u * stride + (threadIdx.x & 31);
+        kk[u] = (i < nc) ? order_key(a.cand[i]) : 0ull;
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const size_t i = base + u * stride + (threadIdx.x & 31);
+        s13_count(sh, (i < nc) && ((kk[u] & himask) == prefix), (unsigned)((kk[u] >> shift) & (kS13Bins - 1)));
+      }
+    }
+    __syncthreads();
+    s13_flush(sh, s13_hist(a.sel, pass));
+    grid.sync();
+  }
+
+  // ---- gather the class of the median (if it fits) and the smallest key above the class
+  {
+    const unsigned long long himask = s13_himask(pass);       // pass == 5: every bit
+    const bool fits = class_count <= (unsigned long long)kFusedCap;
+    unsigned long long min_above = 0xFFFFFFFFFFFFFFFFull;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < nc; i += stride) {
+      const unsigned long long k = order_key(a.cand[i]);
+      const unsigned long long kp = k & himask;
+      if (kp == prefix) {
+        if (fits) a.gbuf[atomicAdd(&st13[7], 1ull)] = k;
+      } else if (kp > prefix && k < min_above) {
+        min_above = k;
+      }
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+      const unsigned long long m = __shfl_down_sync(0xffffffffu, min_above, o);
+      min_above = m < min_above ? m : min_above;
+    }
+    if ((threadIdx.x & 31) == 0 && min_above != 0xFFFFFFFFFFFFFFFFull) atomicMax(&st13[5], ~min_above);   // inverted: 0 = none
+  }
+  grid.sync();
+
+  // ---- the two middle order statistics (every block, redundantly), B_b, structures, range partials
+  {
+    const unsigned long long none = 0xFFFFFFFFFFFFFFFFull;
+    const unsigned long long above = ~st13[5];                // smallest key above the class (all ones: none)
+    if (threadIdx.x == 0) { s_tmp[11] = none; s_tmp[12] = none; }
+    const int c = (class_count <= (unsigned long long)kFusedCap) ? (int)class_count : 0;
+    for (int j = threadIdx.x; j < c; j += blockDim.x) s_keys[j] = a.gbuf[j];
+    __syncthreads();
+    if (c > 0) {
+      for (int j = threadIdx.x; j < c; j += blockDim.x) {
+        const unsigned long long kj = s_keys[j];
+        unsigned long long r = 0;
+        for (int t = 0; t < c; ++t) { const unsigned long long kt = s_keys[t]; r += (kt < kj) || (kt == kj && t < j); }
+        if (r == k_rem) s_tmp[11] = kj;
+        if (r == k_rem + 1) s_tmp[12] = kj;
+      }
+    } else if (threadIdx.x == 0 && class_count > 0) {         // more than kFusedCap copies of one key
+      s_tmp[11] = prefix;
+      if (k_rem + 1 < class_count) s_tmp[12] = prefix;
+    }
+    __syncthreads();
+    const unsigned long long ka = s_tmp[11];
+    const unsigned long long kb = (s_tmp[12] != none) ? s_tmp[12] : above;
+    const double va = key_value(ka), vb = key_value(kb);
+    double B0 = (n_total % 2 == 1) ? va : (0.0 + va + vb) / 2.0;     // numpy.median
+    if (n_total == 0 || st13[3] != 0) B0 = __longlong_as_double(0x7FF8000000000000ll);
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+      a.st[MRF_STATE_B] = B0; a.st[MRF_STATE_B + 1] = a.B_fwd;
+      st13[0] = ka; st13[6] = n_total;
+    }
+    front_structures_block(a.par0, a.par1, a.rows, a.w, 0, a.q0, a.q1, a.B_fwd, B0, mu0, mu1, a.zero_mask, a.b0, a.b1, a.S0, a.S1,
+                           a.partial, blockIdx.x, G, smin, smax, snan);
+  }
+  grid.sync();
+  if (blockIdx.x == 0) front_labels_block(a.partial, (int)G, a.st, a.L, smin[0], smax[0], snan[0]);
 }
 
 }  // namespace mrf
@@ -782,7 +991,30 @@ int mrf_abs_deviation_f64(const double* x, size_t n, double c, double* out, mrf_
 // (pipeline/build_cost_volume.py:78-192 with the live conventions of compute_structure.py): no host
 // synchronisation between the flows and the label set, so the whole step can be captured in a CUDA
 // graph.  Launch sequence only; the arithmetic is that of the kernels above.
-size_t mrf_front_scratch_bytes(void) { return sizeof(double) * 4096 + mrf_select_scratch_bytes(0) + 64; }
+// co-resident blocks of the fused pre-pass (cooperative launch): occupancy x SM count of the CURRENT device
+static int front_fused_grid(int* blocks_out) {
+  static int cached[64] = {0};
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return fail((int)e, "front: %s", cudaGetErrorString(e));
+  if (dev < 0 || dev >= 64 || cached[dev] == 0) {
+    int per_sm = 0, sms = 0;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_front_fused, 256, 0);
+    if (e == cudaSuccess) e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (e != cudaSuccess) return fail((int)e, "front: occupancy query: %s", cudaGetErrorString(e));
+    int b = per_sm * sms;
+    if (b < 1) return fail(MRF_E_SCRATCH, "front: the fused pre-pass kernel cannot be resident");
+    if (b > 2 * sms) b = 2 * sms;          // two blocks per SM: the grid barriers cost more than extra blocks give
+    if (dev >= 0 && dev < 64) cached[dev] = b;
+    *blocks_out = b;
+    return 0;
+  }
+  *blocks_out = cached[dev];
+  return 0;
+}
+
+static size_t front_sel_bytes() { return (mrf_select_scratch_bytes(0) + 255) / 256 * 256; }
+size_t mrf_front_scratch_bytes(void) { return sizeof(double) * 4096 + front_sel_bytes() + sizeof(unsigned long long) * kFusedCap + 64; }
 
 int mrf_cost_volume_front(const mrf_front_params* p, const float* u0, const float* v0, const float* u1,
                           const float* v1, const uint8_t* rigid_mask, const uint8_t* zero_mask,
@@ -799,6 +1031,30 @@ int mrf_cost_volume_front(const mrf_front_params* p, const float* u0, const floa
   cudaError_t e = cudaMemsetAsync(sel, 0, kS13Bytes, S(stream));
   if (e == cudaSuccess) e = cudaMemsetAsync(count, 0, sizeof(int), S(stream));
   if (e != cudaSuccess) return fail((int)e, "front: %s", cudaGetErrorString(e));
+  Box4 bx[2];
+  for (int f = 0; f < 2; ++f) {
+    bx[f].x0 = p->box[f][0]; bx[f].x1 = p->box[f][1]; bx[f].y0 = p->box[f][2]; bx[f].y1 = p->box[f][3];
+    bx[f].on = p->have_box[f];
+  }
+  if (p->fused) {
+    // one persistent cooperative kernel (grid barriers instead of nine launches)
+    int blocks = 0;
+    int rc = front_fused_grid(&blocks);
+    if (rc) return rc;
+    FrontFusedArgs fa;
+    fa.u0 = u0; fa.v0 = v0; fa.u1 = u1; fa.v1 = v1; fa.rigid = rigid_mask; fa.zero_mask = zero_mask;
+    fa.rows = p->rows; fa.w = p->w; fa.L = p->n_labels;
+    fa.Hinv0 = mat3(p->Hinv0); fa.Hinv1 = mat3(p->Hinv1); fa.q0 = pt2(p->q0); fa.q1 = pt2(p->q1);
+    fa.B_fwd = p->B_fwd; fa.b0 = bx[0]; fa.b1 = bx[1];
+    fa.par0 = par0; fa.par1 = par1; fa.S0 = S0; fa.S1 = S1; fa.cand = cand; fa.count = count; fa.st = dev_state;
+    fa.partial = partial; fa.sel = sel;
+    fa.gbuf = (unsigned long long*)((char*)sel + front_sel_bytes());
+    void* args[] = {&fa};
+    e = cudaLaunchCooperativeKernel((const void*)k_front_fused, dim3((unsigned)blocks), dim3(256), args, 0, S(stream));
+    if (e != cudaSuccess) return fail((int)e, "front: cooperative launch: %s", cudaGetErrorString(e));
+    return check_launch("front/fused");
+  }
+  // separate launches (the default; what row bands run too, with collectives in between)
   // same grid and summation tree as mrf_epipole_dist_sum, so mu has the same bits on both routes
   k_front_parallax<<<kRedBlocks, kRedThreads, 0, S(stream)>>>(u0, v0, u1, v1, p->rows, p->w, 0, mat3(p->Hinv0),
                                                               mat3(p->Hinv1), pt2(p->q0), pt2(p->q1), par0, par1, partial);
@@ -813,11 +1069,6 @@ int mrf_cost_volume_front(const mrf_front_params* p, const float* u0, const floa
   for (int pass = 1; pass < kS13Passes && !rc; ++pass) rc = mrf_select13_hist_dev(cand, count, (size_t)n, pass, sel, stream);
   if (!rc) rc = mrf_select13_successor_dev(cand, count, (size_t)n, sel, stream);
   if (rc) return rc;
-  Box4 bx[2];
-  for (int f = 0; f < 2; ++f) {
-    bx[f].x0 = p->box[f][0]; bx[f].x1 = p->box[f][1]; bx[f].y0 = p->box[f][2]; bx[f].y1 = p->box[f][3];
-    bx[f].on = p->have_box[f];
-  }
   k_front_structures<<<(unsigned)fb, 256, 0, S(stream)>>>(par0, par1, p->rows, p->w, 0, pt2(p->q0), pt2(p->q1), p->B_fwd,
                                                           zero_mask, bx[0], bx[1], S0, S1, dev_state, partial, sel, nullptr, 0);
   rc = check_launch("front/structures");

@@ -68,16 +68,13 @@ __device__ __forceinline__ void s13_flush(const unsigned int* sh, unsigned int* 
   }
 }
 
-// Resolve the digits of passes 0 .. upto-1 (upto >= 1): prefix = the high bits of the k-th key found so
-// far, k_rem = its rank inside that prefix class, n = the number of keys.  Needs the finished histogram
-// of pass upto-1 and (for upto >= 2) the memo block 0 wrote while resolving upto-1.  k = (n-1)/2 (the lower
-// median) with n = the total of the first histogram.  Block-wide, blockDim.x == 256; s_tmp: >= 16 words.
-__device__ __forceinline__ void s13_resolve(void* scratch, int upto, unsigned long long& prefix,
-                                            unsigned long long& k_rem, unsigned long long& n_total,
-                                            unsigned long long* s_tmp) {
-  const unsigned long long* memo = s13_memo(scratch);
-  const int p = upto - 1;
-  const unsigned int* h = s13_hist(scratch, p);
+// Resolve ONE digit: given the finished histogram `h` of pass p and the running (prefix, k_rem, n_total) after
+// passes 0 .. p-1 (ignored for p == 0: n_total = the histogram's total, k_rem = (n-1)/2, the lower median),
+// find the bin holding rank k_rem, append it to the prefix and reduce k_rem to the rank inside that bin.
+// class_count = the number of keys in the chosen bin.  Block-wide, blockDim.x == 256; s_tmp: >= 16 words.
+__device__ __forceinline__ void s13_resolve_digit(const unsigned int* __restrict__ h, int p, unsigned long long& prefix,
+                                                  unsigned long long& k_rem, unsigned long long& n_total,
+                                                  unsigned long long& class_count, unsigned long long* s_tmp) {
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   // thread t owns bins [32 t, 32 t + 32)
   unsigned int c[32];
@@ -102,7 +99,6 @@ __device__ __forceinline__ void s13_resolve(void* scratch, int upto, unsigned lo
   for (int k = 0; k < 8; ++k) { const unsigned long long v = s_tmp[k]; if (k < wid) wbase += v; total += v; }
   const unsigned long long excl = wbase + incl - tot;
   if (p == 0) { prefix = 0; n_total = total; k_rem = total ? (total - 1) / 2 : 0ull; }
-  else { prefix = memo[3 * p]; k_rem = memo[3 * p + 1]; n_total = memo[3 * p + 2]; }
   // the thread whose range [excl, excl + tot) holds k_rem; an out-of-range rank (n == 0) falls to the last bin
   const bool mine = (k_rem >= excl && k_rem < excl + tot) || (threadIdx.x == blockDim.x - 1 && k_rem >= excl + tot);
   __syncthreads();
@@ -111,13 +107,31 @@ __device__ __forceinline__ void s13_resolve(void* scratch, int upto, unsigned lo
     int b = 0;
 #pragma unroll
     for (int j = 0; j < 32; ++j) { if (b == j && j < 31 && kr >= c[j]) { kr -= c[j]; b = j + 1; } }
+    unsigned int cc = 0;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) { if (b == j) cc = c[j]; }
     s_tmp[8] = (unsigned long long)(threadIdx.x * 32 + b);
     s_tmp[9] = kr;
+    s_tmp[10] = (unsigned long long)cc;
   }
   __syncthreads();
   prefix |= s_tmp[8] << s13_shift(p);
   k_rem = s_tmp[9];
+  class_count = s_tmp[10];
   __syncthreads();
+}
+
+// Resolve the digits of passes 0 .. upto-1 (upto >= 1) from the scratch block: needs the finished histogram
+// of pass upto-1 and (for upto >= 2) the memo block 0 wrote while resolving upto-1.
+__device__ __forceinline__ void s13_resolve(void* scratch, int upto, unsigned long long& prefix,
+                                            unsigned long long& k_rem, unsigned long long& n_total,
+                                            unsigned long long* s_tmp) {
+  const unsigned long long* memo = s13_memo(scratch);
+  const int p = upto - 1;
+  prefix = 0; k_rem = 0; n_total = 0;
+  if (p >= 1) { prefix = memo[3 * p]; k_rem = memo[3 * p + 1]; n_total = memo[3 * p + 2]; }
+  unsigned long long cc;
+  s13_resolve_digit(s13_hist(scratch, p), p, prefix, k_rem, n_total, cc, s_tmp);
 }
 
 // numpy.median from the finished selection state: middle element, mean of the two middles for even n,

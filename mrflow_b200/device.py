@@ -475,9 +475,11 @@ class FrontBuffers:
         self.scratch = torch.empty(L.mrf_front_scratch_bytes(), dtype=U8, device=dev)
 
 
-def cost_volume_front(flow, rigid_mask, zero_mask, homographies, epipoles, frame_h, buf, n_labels=51, B_fwd=1.0):
+def cost_volume_front(flow, rigid_mask, zero_mask, homographies, epipoles, frame_h, buf, n_labels=51, B_fwd=1.0, fused=False):
     """pipeline/build_cost_volume.py:78-192 without leaving the device: parallax, mu, B_b, structures,
-    label set; every whole-frame scalar is written to ``buf.state`` (see MRF_STATE_* in the header)."""
+    label set; every whole-frame scalar is written to ``buf.state`` (see MRF_STATE_* in the header).
+    ``fused=True`` runs the same pre-pass as one persistent cooperative kernel (identical bits; see the header for
+    why it is not the default)."""
     for f in range(2):
         _chk(flow[f][0], F32, "u"); _chk(flow[f][1], F32, "v")
     _chk(rigid_mask, U8, "rigid_mask"); _chk(zero_mask, U8, "zero_mask")
@@ -489,6 +491,7 @@ def cost_volume_front(flow, rigid_mask, zero_mask, homographies, epipoles, frame
     p.q0 = _pt(epipoles[0]); p.q1 = _pt(epipoles[1])
     p.B_fwd = float(B_fwd)
     p.n_labels = int(n_labels)
+    p.fused = int(bool(fused))
     for f in range(2):
         q = epipoles[f]
         bx0 = max(0, min(w - 1, int(q[0] - 10))); bx1 = max(0, min(w - 1, int(q[0] + 10)))

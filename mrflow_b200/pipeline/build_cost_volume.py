@@ -95,15 +95,16 @@ def _host_call(images, flow, rigidity, homographies, epipoles, rho, sigma, inter
     d_rig = torch.empty((h, w), dtype=F64, device="cuda")
     d_img = [torch.empty((h, w, 3), dtype=F64, device="cuda") for _ in range(3)]
     up.wait_stream(main)
+    ev_img = [None, None, None]
     with torch.cuda.stream(up):
         for f in range(2):
             for c in range(2):
                 d_flow[f][c].copy_(src(flow[f][c], np.float32), non_blocking=True)
         d_rig.copy_(src(rigidity, np.float64), non_blocking=True)
         ev_flow = torch.cuda.Event(); ev_flow.record()
-        for i in range(3):
-            d_img[i].copy_(src(images[i], np.float64), non_blocking=True)
-        ev_img = torch.cuda.Event(); ev_img.record()
+        for i in (1, 0, 2):                       # the reference frame and the backward neighbour first: frame 0's
+            d_img[i].copy_(src(images[i], np.float64), non_blocking=True)      # volume starts while frame t+1 uploads
+            ev_img[i] = torch.cuda.Event(); ev_img[i].record()
     main.wait_event(ev_flow)
     rigid_mask = (d_rig > 0).to(U8)
     nonrigid = (rigid_mask == 0).to(U8)
@@ -119,19 +120,19 @@ def _host_call(images, flow, rigidity, homographies, epipoles, rho, sigma, inter
     dt = F32 if lhw else I32
     host_S = [torch.empty((h, w), dtype=F64, pin_memory=True) for _ in range(2)]
     host_cost = [torch.empty(shape, dtype=dt, pin_memory=True) for _ in range(2)]
-    down.wait_event(ev_front)
-    with torch.cuda.stream(down):
-        for f in range(2):
-            host_S[f].copy_(buf.S[f], non_blocking=True)
-    main.wait_event(ev_img)
-    ref64, tex = pp.channels(band)
     cost = [torch.empty(shape, dtype=dt, device="cuda") for _ in range(2)]
     lib = _lib.lib()
-    chunks = row_chunks(h, n_chunks)
+    # a short first chunk, so that the download -- the long pole -- starts as early as possible
+    chunks = row_chunks(h, 2 * n_chunks)
+    chunks = chunks[:2] + [(chunks[k][0], chunks[min(k + 1, len(chunks) - 1)][1]) for k in range(2, len(chunks), 2)]
+    main.wait_event(ev_img[1])
+    ref64, _ = device.prepare_channels(d_img[1], want_texels=False)
     for f in range(2):
+        main.wait_event(ev_img[0 if f == 0 else 2])
+        _, tex = device.prepare_channels(d_img[0 if f == 0 else 2], want_ch64=False)
         for (y0, y1) in chunks:
             off = y0 * w * 4 if lhw else y0 * w * L * 4
-            device.cost_volume(ref64[y0:y1], tex[f], None, homographies[f], q_new[f], 0.0, 0.0, nonrigid=nonrigid[y0:y1],
+            device.cost_volume(ref64[y0:y1], tex, None, homographies[f], q_new[f], 0.0, 0.0, nonrigid=nonrigid[y0:y1],
                                rho=rho, rho_param=sigma, cw=pp.CHANNEL_WEIGHTS, interp=interp, layout=layout, variant=variant,
                                y0=y0, frame_h=h, nb_y0=0, want_min=False, want_argmin=False, out_ptr=cost[f].data_ptr() + off,
                                plane_stride=(h * w if lhw else 0), state=buf.state, frame=f, n_labels=L)
@@ -144,6 +145,10 @@ def _host_call(images, flow, rigidity, homographies, epipoles, rho, sigma, inter
                 rc = lib.mrf_download_rows(C.c_void_p(host_cost[f].data_ptr()), C.c_void_p(cost[f].data_ptr()), 4, 1, h, w * L, y0,
                                            y1 - y0, C.c_void_p(down.cuda_stream))
             _lib.check(rc, "mrf_download_rows")
+    down.wait_event(ev_front)
+    with torch.cuda.stream(down):
+        for f in range(2):
+            host_S[f].copy_(buf.S[f], non_blocking=True)
     mu_ar, B_ar, labels = pp.state_to_host(buf.state)
     down.synchronize()
     main.synchronize()

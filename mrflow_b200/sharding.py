@@ -21,6 +21,7 @@ larger halo.
 import ctypes as C
 import json
 import os
+import sys
 
 import numpy as np
 import torch
@@ -456,9 +457,12 @@ def banded_front(band, homographies, q_ar, rigid_mask, zero_mask, buf, group=Non
 
 def banded_pass_resident(band, homographies, epipoles, rigid_mask, stats, buf=None, rho="lorentzian", sigma=1.0,
                          interp="cubic", range_mask="rigid_only", variant="staged", out_ptr=(None, None), plane_stride=0,
-                         want_cost=True, halo_miss=None, events=None, masks=None, channels=None):
-    """Row-band cost volumes with the device-resident pre-pass.  Returns dict(cost, mins, argmins, q, buffers)."""
-    q_new = pp.refine_epipoles(band, homographies, epipoles, rigid_mask, stats)
+                         want_cost=True, halo_miss=None, events=None, masks=None, channels=None, q_new=None):
+    """Row-band cost volumes with the device-resident pre-pass.  Returns dict(cost, mins, argmins, q, buffers).
+    ``q_new``: already refined epipoles (then nothing in here touches the host, so the whole step -- kernels,
+    NCCL collectives, the side-stream fork -- can be captured in a CUDA graph)."""
+    if q_new is None:
+        q_new = pp.refine_epipoles(band, homographies, epipoles, rigid_mask, stats)
     buf = buf or BandBuffers(band.rows, band.w, band.device, world=stats.world)
     if masks is None:
         nonrigid = (rigid_mask == 0).to(torch.uint8)
@@ -549,7 +553,8 @@ def device_band(td, rows, halo):
     return pp.Band(imgs, fl, td["rigidity"][y0:y1].contiguous(), None, y0=y0, frame_h=h, nb_y0=n0, nb_rows=n1 - n0, img_y0=m0)
 
 
-def bench_bands(hw, steps, warm, interp="cubic", variant="staged", ClockSampler=None, verify=True, seed=1001, n_waves=16):
+def bench_bands(hw, steps, warm, interp="cubic", variant="staged", ClockSampler=None, verify=True, seed=1001, n_waves=16,
+                use_graph=True):
     """ONE frame (BASELINE.json configs[3]: 4K) sharded by row bands over all ranks -- strong scaling; with one
     rank the whole frame on one GPU, which is the base of the speed-up.  The synthetic triplet is generated on
     rank 0's GPU and broadcast.  Timed per step (CUDA events, L2 flushed, max over ranks):
@@ -603,7 +608,7 @@ def bench_bands(hw, steps, warm, interp="cubic", variant="staged", ClockSampler=
     if world == 1:
         band = device_band(td, (0, h), 0)
         rigid = (td["rigidity"] > 0).to(torch.uint8)
-        st = bcv.ResidentStep(band, H_ar, q_ar, rigid, interp=interp, range_mask="rigid_only", variant=variant, use_graph=False)
+        st = bcv.ResidentStep(band, H_ar, q_ar, rigid, interp=interp, range_mask="rigid_only", variant=variant, use_graph=use_graph)
         ms = timed(lambda: st.run())
         rec.update({"parallelism": "whole frame on one GPU", "compute_only": {"ms_per_step": ms, "value": units / (ms * 1e-3)}})
         return rec
@@ -630,28 +635,67 @@ def bench_bands(hw, steps, warm, interp="cubic", variant="staged", ClockSampler=
     host = tuple(torch.empty((L, rows, w), dtype=torch.float32, pin_memory=True) for _ in range(2))
     kernel_events = []
 
-    def step(mode, events=None):
+    q_new = pp.refine_epipoles(band, H_ar, q_ar, rigid, stats)
+
+    def eager(mode, events=None):
         gather = mode == "gather"
         outs = tuple(p.band_ptr(y0) for p in peers) if gather else tuple(c.data_ptr() for c in cost_local)
-        r = banded_pass_resident(band, H_ar, q_ar, rigid, stats, buf=bbuf, interp=interp, range_mask="rigid_only",
-                                 variant=variant, out_ptr=outs, plane_stride=(h * w if gather else 0), halo_miss=miss,
-                                 events=events, masks=(nonrigid, nonrigid))
+        return banded_pass_resident(band, H_ar, q_ar, rigid, stats, buf=bbuf, interp=interp, range_mask="rigid_only",
+                                    variant=variant, out_ptr=outs, plane_stride=(h * w if gather else 0), halo_miss=miss,
+                                    events=events, masks=(nonrigid, nonrigid), q_new=q_new)
+
+    # The step is ~25 short launches and 7 collectives: enqueued from Python it is bound by the host, not the GPUs.
+    # Capture it once per output mode (NCCL collectives are capturable) and replay with one launch.
+    graphs = {}
+    if use_graph:
+        try:
+            for mode in ("local", "gather"):
+                for _ in range(2):
+                    eager(mode)
+                barrier()
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    eager(mode)
+                graphs[mode] = g
+                barrier()
+        except Exception as e:                               # noqa: BLE001
+            if rank == 0:
+                print("(WW) CUDA graph capture of the banded step failed, running eagerly: %s" % e, file=sys.stderr)
+            graphs = {}
+            torch.cuda.synchronize()
+
+    def step(mode, events=None):
+        key = "gather" if mode == "gather" else "local"
+        if key in graphs and events is None:
+            graphs[key].replay()
+        else:
+            eager(key, events)
         if mode == "d2h":
             for f in range(2):
                 host[f].copy_(cost_local[f], non_blocking=True)
-        return r
 
     res = {}
-    res["compute_only"] = timed(lambda: step("local", kernel_events))
+    res["compute_only"] = timed(lambda: step("local"))
     res["compute_and_gather"] = timed(lambda: step("gather"))
     res["compute_and_d2h"] = timed(lambda: step("d2h"))
+    for _ in range(3):                                       # the kernel alone: eager launches with events round it
+        flush.fill_(1)
+        eager("local", kernel_events)
+    torch.cuda.synchronize()
+    if not graphs:
+        res_eager = None
+    else:
+        res_eager = timed(lambda: eager("local"))
     barrier()
     n_miss = stats.total(int(miss.cpu()[0]))
     kms = float(np.mean([a.elapsed_time(b) for a, b in kernel_events]))
     for k, ms in res.items():
         rec[k] = {"ms_per_step": ms, "value": units / (ms * 1e-3)}
+    if res_eager is not None:
+        rec["compute_only_eager_launches"] = {"ms_per_step": res_eager, "value": units / (res_eager * 1e-3)}
     rec.update({"parallelism": "row bands x%d, device-resident statistics: 7 NCCL collectives on the stream "
-                               "(5 x 32 KB histogram all-reduce, 2 small all-gathers), none for mu" % world,
+                               "(5 x 32 KB histogram all-reduce, 2 small all-gathers), none for mu; %s" % (
+                                   world, "the step replayed as one CUDA graph" if graphs else "eager launches"),
                 "halo_rows": halo_rows, "n_miss": int(n_miss), "kernel_ms_per_launch": kms,
                 "band_rows": rows, "d2h_bytes_per_rank": int(2 * L * rows * w * 4)})
     if verify:

@@ -547,6 +547,53 @@ def test_select13_sharded_steps(dev, n, kind):
         assert (np.isnan(got) and np.isnan(want)) or got == want, (n, kind, r, got, want)
 
 
+@pytest.mark.parametrize("case", ["plain", "few", "none", "nan", "const", "sintel"])
+def test_fused_front_equals_stepwise(dev, case):
+    """mrf_cost_volume_front as one cooperative kernel against the same pre-pass as separate launches: every
+    output (parallax, structures, the device state with mu, B, min/max, labels) bit for bit -- including the
+    corners of the exact median: fewer candidates than the gather capacity, none at all, a NaN candidate, and
+    candidate ratios spread over many binades."""
+    import torch
+    from mrflow_b200 import synth
+    shape = (436, 1024) if case == "sintel" else (120, 160)
+    t = synth.make_triplet(shape, seed=41, epipole="inside" if case == "const" else "outside", flow_noise=0.0 if case == "const" else 0.03,
+                           n_waves=4)
+    h, w = t["shape"]
+    fl = [[cu(t["flow"][f][c].copy()) for c in range(2)] for f in range(2)]
+    rigid = np.ones((h, w), np.uint8)
+    if case == "few":
+        rigid[:] = 0; rigid[40:44, 50:90] = 1
+    if case == "none":
+        rigid[:] = 0
+    if case == "nan":
+        fl[1][0][60, 70] = float("nan")
+    if case == "const":                     # constant flows, epipole inside the frame: ratios over many binades
+        for f in range(2):
+            fl[f][0].fill_(1.5 + f); fl[f][1].fill_(-0.75)
+    rm = cu(rigid)
+    zm = cu((1 - rigid).astype(np.uint8))
+    outs = []
+    for fused in (True, False):
+        buf = dev.FrontBuffers(h, w)
+        buf.state.fill_(-7.0)
+        dev.cost_volume_front(fl, rm, zm, t["homographies"], t["epipoles"], h, buf, fused=fused)
+        torch.cuda.synchronize()
+        outs.append(buf)
+    a, b = outs
+    from mrflow_b200 import _lib
+    lab = slice(_lib.STATE_LABELS, _lib.STATE_LABELS + 51)
+    sa, sb = a.state.cpu().numpy(), b.state.cpu().numpy()
+    assert np.array_equal(sa[:10], sb[:10], equal_nan=True), (sa[:10], sb[:10])
+    assert np.array_equal(sa[lab], sb[lab], equal_nan=True)
+    for f in range(2):
+        assert eq(a.par[f].cpu(), b.par[f].cpu()) and eq(a.S[f].cpu(), b.S[f].cpu())
+    n = int(a.count.cpu()[0])
+    assert n == int(b.count.cpu()[0])
+    if n:
+        want = np.median(a.cand[:n].cpu().numpy())
+        assert (np.isnan(want) and np.isnan(sa[_lib.STATE_B])) or want == sa[_lib.STATE_B]
+
+
 def test_resident_pass_equals_host_driven_pass(dev, trip):
     """cost_volume_pass_resident (scalars stay in HBM) against cost_volume_pass (scalars via the host):
     same kernels, so mu, B, labels, structures and both volumes must agree bit for bit."""

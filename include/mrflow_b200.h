@@ -304,26 +304,42 @@ int mrf_cost_volume_front(const mrf_front_params* p_host, const float* u0, const
 #define MRF_SELECT13_BINS        8192
 #define MRF_SELECT13_HIST_OFFSET 256
 #define MRF_SELECT13_SUCC_OFFSET 24
+/* The same exchanges WITHOUT collective launches (csrc/peersync.cuh): with a non-NULL `peer` the kernels add
+ * their histogram bins straight into every rank's histogram over NVLink (remote reductions on peer-mapped
+ * memory), their last block sends the few gathered words to every rank, publishes the phase with a flag store,
+ * and the next kernel polls its own flags -- one one-way NVLink latency per exchange.  Every rank owns a context
+ * of mrf_peer_sync_bytes() bytes from mrf_peer_alloc, zeroed once, opened by all peers (ctx[r] = this process's
+ * pointer to rank r's context, its own at [rank]).  Call sequence per step, all ranks alike:
+ *   mrf_peer_sync_begin; mrf_front_mu_whole / parallax_band; candidates_band(peer); mrf_select13_hist_dev(pass
+ *   1..4, peer); mrf_select13_successor_dev(peer); mrf_front_structures_band(gathered NULL, peer);
+ *   mrf_label_range_dev(gathered NULL, peer).  A rank that never shows up sets the context's error word (second
+ * 8-byte word) after 20 s of wall clock; check it before trusting results. */
+typedef struct {
+  void* ctx[8];
+  int world, rank;
+} mrf_peer_sync;
+size_t mrf_peer_sync_bytes(void);
+int mrf_peer_sync_begin(const mrf_peer_sync* peer_host, mrf_stream_t stream);
 int mrf_front_mu_whole(const mrf_front_params* p_host, double* dev_state, void* scratch, mrf_stream_t stream);
 int mrf_front_parallax_band(const mrf_front_params* p_host, const float* u0, const float* v0,
                             const float* u1, const float* v1, double* par0, double* par1,
                             void* scratch, mrf_stream_t stream);
 int mrf_front_candidates_band(const mrf_front_params* p_host, const double* par0, const double* par1,
                               const uint8_t* rigid_mask, double* dev_state, double* cand, int* count,
-                              void* select_scratch, mrf_stream_t stream);
+                              void* select_scratch, const mrf_peer_sync* peer_host, mrf_stream_t stream);
 int mrf_front_structures_band(const mrf_front_params* p_host, const double* par0, const double* par1,
                               const uint8_t* zero_mask, double* S0, double* S1, double* dev_state,
                               const void* select_scratch, const unsigned long long* gathered_successor, int world,
-                              void* scratch, mrf_stream_t stream);
+                              void* scratch, const mrf_peer_sync* peer_host, mrf_stream_t stream);
 /* Exact median in five radix passes with the counts read on the device (csrc/select13.cuh): zero the
  * scratch (mrf_select_scratch_bytes), histogram pass 0..4 (each resolves the previous digit from the
  * finished -- for row bands all-reduced -- histogram), successor pass, median (gathered = the successor
  * words of all ranks [world][3], or NULL on one GPU). */
 int mrf_select13_begin(void* scratch, mrf_stream_t stream);
 int mrf_select13_hist_dev(const double* keys, const int* n_local_dev, size_t capacity, int pass, void* scratch,
-                          mrf_stream_t stream);
+                          const mrf_peer_sync* peer_host, mrf_stream_t stream);
 int mrf_select13_successor_dev(const double* keys, const int* n_local_dev, size_t capacity, void* scratch,
-                               mrf_stream_t stream);
+                               const mrf_peer_sync* peer_host, mrf_stream_t stream);
 int mrf_select13_median(const void* scratch, const unsigned long long* gathered, int world, double* out_median,
                         mrf_stream_t stream);
 /* numpy.median of the first *n_dev keys (n read on the device); np.linspace label set from the
@@ -331,7 +347,8 @@ int mrf_select13_median(const void* scratch, const unsigned long long* gathered,
 int mrf_select_median_dev(const double* keys, const int* n_dev, size_t capacity, double* out_median,
                           void* scratch, mrf_stream_t stream);
 /* gathered: the six words MRF_STATE_MINMAX .. MRF_STATE_NANFLAG+1 of every band [world][6], or NULL */
-int mrf_label_range_dev(double* dev_state, int n_labels, const double* gathered, int world, mrf_stream_t stream);
+int mrf_label_range_dev(double* dev_state, int n_labels, const double* gathered, int world,
+                        const mrf_peer_sync* peer_host, mrf_stream_t stream);
 
 /* ---- utils/robust_functions.py:26-70 on a device array: out = rho(x) (deriv = 0) or d rho/dx
  * (deriv = 1), x = squared residual.  kind = MRF_RHO_*; p1 = sigma / eps; p2 = Charbonnier

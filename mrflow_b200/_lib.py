@@ -30,6 +30,11 @@ class CostVolParams(C.Structure):
                 ("state_frame", C.c_int), ("cost_plane_stride", C.c_longlong)]
 
 
+class PeerSyncArg(C.Structure):
+    """mrf_peer_sync"""
+    _fields_ = [("ctx", C.c_void_p * 8), ("world", C.c_int), ("rank", C.c_int)]
+
+
 class FrontParams(C.Structure):
     """mrf_front_params"""
     _fields_ = [("rows", C.c_int), ("w", C.c_int), ("y0", C.c_int), ("frame_h", C.c_int),
@@ -89,14 +94,16 @@ SIGNATURES = {
     "mrf_cost_volume_front": (_I, [C.POINTER(FrontParams), _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "mrf_front_mu_whole": (_I, [C.POINTER(FrontParams), _P, _P, _P]),
     "mrf_front_parallax_band": (_I, [C.POINTER(FrontParams), _P, _P, _P, _P, _P, _P, _P, _P]),
-    "mrf_front_candidates_band": (_I, [C.POINTER(FrontParams), _P, _P, _P, _P, _P, _P, _P, _P]),
-    "mrf_front_structures_band": (_I, [C.POINTER(FrontParams), _P, _P, _P, _P, _P, _P, _P, _P, _I, _P, _P]),
+    "mrf_front_candidates_band": (_I, [C.POINTER(FrontParams), _P, _P, _P, _P, _P, _P, _P, _P, _P]),
+    "mrf_front_structures_band": (_I, [C.POINTER(FrontParams), _P, _P, _P, _P, _P, _P, _P, _P, _I, _P, _P, _P]),
+    "mrf_peer_sync_bytes": (_Z, []),
+    "mrf_peer_sync_begin": (_I, [_P, _P]),
     "mrf_select13_begin": (_I, [_P, _P]),
-    "mrf_select13_hist_dev": (_I, [_P, _P, _Z, _I, _P, _P]),
-    "mrf_select13_successor_dev": (_I, [_P, _P, _Z, _P, _P]),
+    "mrf_select13_hist_dev": (_I, [_P, _P, _Z, _I, _P, _P, _P]),
+    "mrf_select13_successor_dev": (_I, [_P, _P, _Z, _P, _P, _P]),
     "mrf_select13_median": (_I, [_P, _P, _I, _P, _P]),
     "mrf_select_median_dev": (_I, [_P, _P, _Z, _P, _P, _P]),
-    "mrf_label_range_dev": (_I, [_P, _I, _P, _I, _P]),
+    "mrf_label_range_dev": (_I, [_P, _I, _P, _I, _P, _P]),
     "mrf_flow_consistency": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _D, _P, _P, _P, _P]),
     "mrf_image_weights_scratch_bytes": (_Z, []),
     "mrf_image_weights": (_I, [_P, _I, _I, _I, _P, _P, _P, _P, _P, _P]),

@@ -3,7 +3,7 @@
 // with a few dozen fp64 flops per pixel.  Arithmetic follows the reference operation by
 // operation (compiled with -fmad=false) so results are bit-identical wherever the reference only
 // uses IEEE +,-,*,/,sqrt; transcendental functions (atan2, sin, exp, I0e) agree to a few ulp.
-#include "select13.cuh"
+#include "peersync.cuh"
 #include <cooperative_groups.h>
 #include <stdarg.h>
 #include <math.h>
@@ -484,7 +484,7 @@ __global__ void __launch_bounds__(256)
 k_front_candidates13(const double* __restrict__ par0, const double* __restrict__ par1,
                      const uint8_t* __restrict__ p_thr, int rows, int w, int y0, Pt2 q0, Pt2 q1, double B_fwd,
                      double* __restrict__ cand, int* __restrict__ count, double* __restrict__ st,
-                     const double* __restrict__ partial, double n_px, void* sel) {
+                     const double* __restrict__ partial, double n_px, void* sel, const PeerArg pa) {
   __shared__ unsigned int sh[kS13Bins];
   __shared__ double s_mu[2];
   __shared__ double s_red[32];
@@ -522,7 +522,7 @@ k_front_candidates13(const double* __restrict__ par0, const double* __restrict__
     s13_count(sh, valid, (unsigned)(order_key(val) >> s13_shift(0)));
   }
   __syncthreads();
-  s13_flush(sh, s13_hist(sel, 0));
+  s13_flush(sh, s13_hist(sel, 0));                // this rank's histogram; the next kernel sums it over the ranks
 }
 
 // both frames: parallax -> normed structure (a3) and block partial min / max / NaN of the
@@ -584,11 +584,17 @@ k_front_structures(const double* __restrict__ par0, const double* __restrict__ p
                    Pt2 q1, double B_fwd, const uint8_t* __restrict__ zero_mask, Box4 b0, Box4 b1,
                    double* __restrict__ S0, double* __restrict__ S1, double* __restrict__ st,
                    double* __restrict__ part, const void* __restrict__ sel,
-                   const unsigned long long* __restrict__ gathered, int world) {
+                   const unsigned long long* __restrict__ gathered, int world, const PeerArg pa) {
   __shared__ double smin[2][8], smax[2][8];
   __shared__ int snan[2][8];
+  int gstride = 3;
+  if (pa.world > 0) {          // row bands over peer memory: wait for every rank's successor words
+    peer_phase_wait(pa, kS13Passes);
+    gathered = &pa.p[pa.rank]->gather[0][0][0];
+    world = pa.world; gstride = 8;
+  }
   // B_b = median(template / target)  compute_structure.py:221 -- the same bits in every block
-  const double mu0 = st[MRF_STATE_MU], mu1 = st[MRF_STATE_MU + 1], B0 = s13_median(sel, gathered, world);
+  const double mu0 = st[MRF_STATE_MU], mu1 = st[MRF_STATE_MU + 1], B0 = s13_median(sel, gathered, world, gstride);
   if (blockIdx.x == 0 && threadIdx.x == 0) { st[MRF_STATE_B] = B0; st[MRF_STATE_B + 1] = B_fwd; }
   front_structures_block(par0, par1, rows, w, y0, q0, q1, B_fwd, B0, mu0, mu1, zero_mask, b0, b1, S0, S1, part, blockIdx.x,
                          gridDim.x, smin, smax, snan);
@@ -597,7 +603,7 @@ k_front_structures(const double* __restrict__ par0, const double* __restrict__ p
 // final (NaN-ignoring) min / max of both frames and the NaN flags -> state; row bands all-reduce these
 // (MIN, MAX, MAX) before mrf_label_range_dev
 __global__ void __launch_bounds__(256)
-k_front_minmax(const double* __restrict__ part, int nblocks, double* __restrict__ st) {
+k_front_minmax(const double* __restrict__ part, int nblocks, double* __restrict__ st, const PeerArg pa) {
   __shared__ double smin[8], smax[8];
   __shared__ int snan[8];
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -622,6 +628,8 @@ k_front_minmax(const double* __restrict__ part, int nblocks, double* __restrict_
     }
     __syncthreads();
   }
+  // row bands over peer memory: this (single-block) kernel sends the band's six range words to every rank
+  if (pa.world > 0) peer_phase_done(pa, kS13Passes + 1, reinterpret_cast<const unsigned long long*>(st + MRF_STATE_MINMAX), 6, 1);
 }
 
 // final min/max of both frames -> state, then np.linspace(1.5*min, 1.5*max, L) (see k_label_range); one block
@@ -1063,14 +1071,14 @@ int mrf_cost_volume_front(const mrf_front_params* p, const float* u0, const floa
   // mu, pv and the candidate ratios of :209-219 with B_fwd fixed (build_cost_volume.py:116-131), first select pass
   k_front_candidates13<<<front_cand_blocks(n), 256, 0, S(stream)>>>(par0, par1, rigid_mask, p->rows, p->w, 0, pt2(p->q0),
                                                                     pt2(p->q1), p->B_fwd, cand, count, dev_state, partial,
-                                                                    (double)n, sel);
+                                                                    (double)n, sel, PeerArg{});
   rc = check_launch("front/candidates");
   if (rc) return rc;
-  for (int pass = 1; pass < kS13Passes && !rc; ++pass) rc = mrf_select13_hist_dev(cand, count, (size_t)n, pass, sel, stream);
-  if (!rc) rc = mrf_select13_successor_dev(cand, count, (size_t)n, sel, stream);
+  for (int pass = 1; pass < kS13Passes && !rc; ++pass) rc = mrf_select13_hist_dev(cand, count, (size_t)n, pass, sel, nullptr, stream);
+  if (!rc) rc = mrf_select13_successor_dev(cand, count, (size_t)n, sel, nullptr, stream);
   if (rc) return rc;
   k_front_structures<<<(unsigned)fb, 256, 0, S(stream)>>>(par0, par1, p->rows, p->w, 0, pt2(p->q0), pt2(p->q1), p->B_fwd,
-                                                          zero_mask, bx[0], bx[1], S0, S1, dev_state, partial, sel, nullptr, 0);
+                                                          zero_mask, bx[0], bx[1], S0, S1, dev_state, partial, sel, nullptr, 0, PeerArg{});
   rc = check_launch("front/structures");
   if (rc) return rc;
   k_front_labels<<<1, 256, 0, S(stream)>>>(partial, (int)fb, dev_state, p->n_labels);
@@ -1105,24 +1113,28 @@ int mrf_front_parallax_band(const mrf_front_params* p, const float* u0, const fl
 
 int mrf_front_candidates_band(const mrf_front_params* p, const double* par0, const double* par1,
                               const uint8_t* rigid_mask, double* dev_state, double* cand, int* count,
-                              void* select_scratch, mrf_stream_t stream) {
+                              void* select_scratch, const mrf_peer_sync* peer, mrf_stream_t stream) {
   MRF_CHECK_ARG(p && par0 && par1 && rigid_mask && dev_state && cand && count && select_scratch);
+  PeerArg pa;
+  if (peer_arg(peer, &pa)) return MRF_E_BADARG;
   cudaError_t e = cudaMemsetAsync(select_scratch, 0, kS13Bytes, S(stream));
   if (e == cudaSuccess) e = cudaMemsetAsync(count, 0, sizeof(int), S(stream));
   if (e != cudaSuccess) return fail((int)e, "front_band: %s", cudaGetErrorString(e));
   const long long n = (long long)p->rows * p->w;
   k_front_candidates13<<<front_cand_blocks(n), 256, 0, S(stream)>>>(par0, par1, rigid_mask, p->rows, p->w, p->y0,
                                                                     pt2(p->q0), pt2(p->q1), p->B_fwd, cand, count,
-                                                                    dev_state, nullptr, 0.0, select_scratch);
+                                                                    dev_state, nullptr, 0.0, select_scratch, pa);
   return check_launch("front_band/candidates");
 }
 
 int mrf_front_structures_band(const mrf_front_params* p, const double* par0, const double* par1,
                               const uint8_t* zero_mask, double* S0, double* S1, double* dev_state,
                               const void* select_scratch, const unsigned long long* gathered_successor, int world,
-                              void* scratch, mrf_stream_t stream) {
+                              void* scratch, const mrf_peer_sync* peer, mrf_stream_t stream) {
   MRF_CHECK_ARG(p && par0 && par1 && S0 && S1 && dev_state && scratch && select_scratch);
   MRF_CHECK_ARG(!gathered_successor || world >= 1);
+  PeerArg pa;
+  if (peer_arg(peer, &pa)) return MRF_E_BADARG;
   const long long n = (long long)p->rows * p->w;
   long long fb = (n + 255) / 256;
   if (fb > kFrontBlocks) fb = kFrontBlocks;
@@ -1134,10 +1146,10 @@ int mrf_front_structures_band(const mrf_front_params* p, const double* par0, con
   double* partial = (double*)scratch;
   k_front_structures<<<(unsigned)fb, 256, 0, S(stream)>>>(par0, par1, p->rows, p->w, p->y0, pt2(p->q0), pt2(p->q1),
                                                           p->B_fwd, zero_mask, bx[0], bx[1], S0, S1, dev_state, partial,
-                                                          select_scratch, gathered_successor, world);
+                                                          select_scratch, gathered_successor, world, pa);
   int rc = check_launch("front_band/structures");
   if (rc) return rc;
-  k_front_minmax<<<1, 256, 0, S(stream)>>>(partial, (int)fb, dev_state);
+  k_front_minmax<<<1, 256, 0, S(stream)>>>(partial, (int)fb, dev_state, pa);
   return check_launch("front_band/minmax");
 }
 

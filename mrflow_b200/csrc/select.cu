@@ -12,7 +12,7 @@
 // pick are separate entry points so that a multi-GPU caller can all-reduce the 256-bin histogram
 // (2 KB over NCCL) between them -- the exchange step of SURVEY.md section 8e.  NaNs order last
 // (numpy's sort order) and are counted, since numpy's median is NaN when any is present.
-#include "select13.cuh"
+#include "peersync.cuh"
 
 namespace mrf {
 
@@ -154,14 +154,28 @@ __global__ void k_select_result(const unsigned long long* __restrict__ st, unsig
 // ------------------------------------------------------------------------------ five-pass select
 // (select13.cuh).  Pass `pass` (0..4): resolve the previous digit, histogram this one.
 __global__ void __launch_bounds__(256)
-k_s13_hist(const double* __restrict__ keys, const int* __restrict__ n_dev, int pass, void* scratch) {
+k_s13_hist(const double* __restrict__ keys, const int* __restrict__ n_dev, int pass, void* scratch, const PeerArg pa) {
   __shared__ unsigned int sh[kS13Bins];
   __shared__ unsigned long long s_tmp[16];
   const size_t n = (size_t)max(*n_dev, 0);
   s13_zero(sh);
-  unsigned long long prefix = 0, k_rem = 0, n_total = 0;
+  unsigned long long prefix = 0, k_rem = 0, n_total = 0, epoch = 0;
+  const unsigned int* h_prev = (pass >= 1) ? s13_hist(scratch, pass - 1) : nullptr;
+  if (pa.world > 0) {
+    PeerCtx* me = pa.p[pa.rank];
+    // sum the previous pass's histogram over the ranks (peersync.cuh)
+    epoch = (pass >= 1) ? peer_hist_exchange(pa, pass - 1, s13_hist(scratch, pass - 1)) : me->epoch;
+    if (pass >= 1) h_prev = me->hist[epoch & 1ull][pass - 1];
+    if (pass == 1) {
+      // zero the histogram set of the NEXT step: every rank is past the previous step (its last user), and this
+      // rank publishes nothing further before this kernel ends (see peersync.cuh)
+      unsigned int* nxt = &me->hist[(epoch + 1ull) & 1ull][0][0];
+      for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < (size_t)kS13Passes * kS13Bins; i += (size_t)gridDim.x * blockDim.x)
+        nxt[i] = 0u;
+    }
+  }
   if (pass >= 1) {
-    s13_resolve(scratch, pass, prefix, k_rem, n_total, s_tmp);
+    s13_resolve_from(h_prev, scratch, pass, prefix, k_rem, n_total, s_tmp);
     if (blockIdx.x == 0 && threadIdx.x == 0) {
       unsigned long long* memo = s13_memo(scratch);
       memo[3 * pass] = prefix; memo[3 * pass + 1] = k_rem; memo[3 * pass + 2] = n_total;
@@ -187,17 +201,22 @@ k_s13_hist(const double* __restrict__ keys, const int* __restrict__ n_dev, int p
     }
   }
   __syncthreads();
-  s13_flush(sh, s13_hist(scratch, pass));
+  s13_flush(sh, s13_hist(scratch, pass));         // this rank's histogram; the next kernel sums it over the ranks
 }
 
 // successor pass: resolves the last digit, then counts keys <= kth / NaNs / the smallest key above
 __global__ void __launch_bounds__(256)
-k_s13_successor(const double* __restrict__ keys, const int* __restrict__ n_dev, void* scratch) {
+k_s13_successor(const double* __restrict__ keys, const int* __restrict__ n_dev, void* scratch, const PeerArg pa) {
   __shared__ unsigned long long s_tmp[16];
   __shared__ unsigned long long s_red[3][8];
   const size_t n = (size_t)max(*n_dev, 0);
   unsigned long long kth, k_rem, n_total;
-  s13_resolve(scratch, kS13Passes, kth, k_rem, n_total, s_tmp);
+  const unsigned int* h_last = s13_hist(scratch, kS13Passes - 1);
+  if (pa.world > 0) {
+    const unsigned long long epoch = peer_hist_exchange(pa, kS13Passes - 1, s13_hist(scratch, kS13Passes - 1));
+    h_last = pa.p[pa.rank]->hist[epoch & 1ull][kS13Passes - 1];
+  }
+  s13_resolve_from(h_last, scratch, kS13Passes, kth, k_rem, n_total, s_tmp);
   unsigned long long* st = s13_st(scratch);
   if (blockIdx.x == 0 && threadIdx.x == 0) { st[0] = kth; st[6] = n_total; }
   unsigned long long cnt_le = 0, nan = 0, min_gt = 0xFFFFFFFFFFFFFFFFull;
@@ -222,7 +241,11 @@ k_s13_successor(const double* __restrict__ keys, const int* __restrict__ n_dev, 
     if (nan) atomicAdd(&st[3], nan);
     if (min_gt != 0xFFFFFFFFFFFFFFFFull) atomicMax(&st[5], ~min_gt);     // stored inverted: zeroed scratch = none
   }
+  // row bands over peer memory: the last block sends this rank's three successor words to every rank
+  if (pa.world > 0) peer_phase_done(pa, kS13Passes, st + 3, 3, 0);
 }
+
+__global__ void k_peer_begin(PeerCtx* me) { me->epoch = me->epoch + 1ull; }
 
 __global__ void k_s13_median(const void* __restrict__ scratch, const unsigned long long* __restrict__ gathered, int world,
                              double* __restrict__ out) {
@@ -246,15 +269,21 @@ __global__ void k_select_median(const unsigned long long* __restrict__ st, doubl
 // y = arange*step + start, or arange/div*delta + start when step == 0, last element = stop)
 // Row bands pass the six words MRF_STATE_MINMAX .. MRF_STATE_NANFLAG+1 of all ranks (`gathered` = [world][6]);
 // their min / max / NaN flags are combined here and written back to the state.
-__global__ void k_label_range(double* __restrict__ st, int L, const double* __restrict__ gathered, int world) {
+__global__ void k_label_range(double* __restrict__ st, int L, const double* __restrict__ gathered, int world, const PeerArg pa) {
   const int i = threadIdx.x;
+  int gstride = 6;
+  if (pa.world > 0) {                       // row bands over peer memory: wait for every rank's range words
+    peer_phase_wait(pa, kS13Passes + 1);
+    gathered = reinterpret_cast<const double*>(&pa.p[pa.rank]->gather[1][0][0]);
+    world = pa.world; gstride = 8;
+  }
   double lo0 = st[MRF_STATE_MINMAX], hi0 = st[MRF_STATE_MINMAX + 1];
   double lo1 = st[MRF_STATE_MINMAX + 2], hi1 = st[MRF_STATE_MINMAX + 3];
   double f0 = st[MRF_STATE_NANFLAG], f1 = st[MRF_STATE_NANFLAG + 1];
   if (gathered) {
     lo0 = lo1 = INFINITY; hi0 = hi1 = -INFINITY; f0 = f1 = 0.0;
     for (int r = 0; r < world; ++r) {
-      const double* g = gathered + 6 * r;
+      const double* g = gathered + gstride * r;
       lo0 = fmin(lo0, g[0]); hi0 = fmax(hi0, g[1]); lo1 = fmin(lo1, g[2]); hi1 = fmax(hi1, g[3]);
       if (g[4] != 0.0) f0 = 1.0;
       if (g[5] != 0.0) f1 = 1.0;
@@ -443,11 +472,11 @@ int mrf_select_median_dev(const double* keys, const int* n_dev, size_t capacity,
   if (e != cudaSuccess) return fail((int)e, "mrf_select_median_dev: %s", cudaGetErrorString(e));
   const unsigned blocks = s13_blocks(capacity);
   for (int pass = 0; pass < kS13Passes; ++pass) {
-    k_s13_hist<<<blocks, 256, 0, S(stream)>>>(keys, n_dev, pass, scratch);
+    k_s13_hist<<<blocks, 256, 0, S(stream)>>>(keys, n_dev, pass, scratch, PeerArg{});
     const int rc = check_launch("mrf_select_median_dev/hist");
     if (rc) return rc;
   }
-  k_s13_successor<<<blocks, 256, 0, S(stream)>>>(keys, n_dev, scratch);
+  k_s13_successor<<<blocks, 256, 0, S(stream)>>>(keys, n_dev, scratch, PeerArg{});
   int rc = check_launch("mrf_select_median_dev/successor");
   if (rc) return rc;
   k_s13_median<<<1, 1, 0, S(stream)>>>(scratch, nullptr, 0, out_median);
@@ -463,16 +492,29 @@ int mrf_select13_begin(void* scratch, mrf_stream_t stream) {
   return 0;
 }
 int mrf_select13_hist_dev(const double* keys, const int* n_local_dev, size_t capacity, int pass, void* scratch,
-                          mrf_stream_t stream) {
+                          const mrf_peer_sync* peer, mrf_stream_t stream) {
   MRF_CHECK_ARG(keys && n_local_dev && scratch && capacity > 0 && pass >= 0 && pass < kS13Passes);
-  k_s13_hist<<<s13_blocks(capacity), 256, 0, S(stream)>>>(keys, n_local_dev, pass, scratch);
+  PeerArg pa;
+  if (peer_arg(peer, &pa)) return MRF_E_BADARG;
+  k_s13_hist<<<s13_blocks(capacity), 256, 0, S(stream)>>>(keys, n_local_dev, pass, scratch, pa);
   return check_launch("mrf_select13_hist_dev");
 }
 int mrf_select13_successor_dev(const double* keys, const int* n_local_dev, size_t capacity, void* scratch,
-                               mrf_stream_t stream) {
+                               const mrf_peer_sync* peer, mrf_stream_t stream) {
   MRF_CHECK_ARG(keys && n_local_dev && scratch && capacity > 0);
-  k_s13_successor<<<s13_blocks(capacity), 256, 0, S(stream)>>>(keys, n_local_dev, scratch);
+  PeerArg pa;
+  if (peer_arg(peer, &pa)) return MRF_E_BADARG;
+  k_s13_successor<<<s13_blocks(capacity), 256, 0, S(stream)>>>(keys, n_local_dev, scratch, pa);
   return check_launch("mrf_select13_successor_dev");
+}
+
+// ---- peer-memory synchronisation context of the row-band pre-pass (peersync.cuh)
+size_t mrf_peer_sync_bytes(void) { return sizeof(PeerCtx); }
+int mrf_peer_sync_begin(const mrf_peer_sync* peer, mrf_stream_t stream) {
+  PeerArg pa;
+  if (peer_arg(peer, &pa) || pa.world == 0) return fail(MRF_E_BADARG, "mrf_peer_sync_begin: bad peer context");
+  k_peer_begin<<<1, 1, 0, S(stream)>>>(pa.p[pa.rank]);
+  return check_launch("mrf_peer_sync_begin");
 }
 int mrf_select13_median(const void* scratch, const unsigned long long* gathered, int world, double* out_median,
                         mrf_stream_t stream) {
@@ -481,9 +523,12 @@ int mrf_select13_median(const void* scratch, const unsigned long long* gathered,
   return check_launch("mrf_select13_median");
 }
 
-int mrf_label_range_dev(double* dev_state, int n_labels, const double* gathered, int world, mrf_stream_t stream) {
+int mrf_label_range_dev(double* dev_state, int n_labels, const double* gathered, int world, const mrf_peer_sync* peer,
+                        mrf_stream_t stream) {
   MRF_CHECK_ARG(dev_state && n_labels >= 2 && n_labels <= 256 && (!gathered || world >= 1));
-  k_label_range<<<1, 256, 0, S(stream)>>>(dev_state, n_labels, gathered, world);
+  PeerArg pa;
+  if (peer_arg(peer, &pa)) return MRF_E_BADARG;
+  k_label_range<<<1, 256, 0, S(stream)>>>(dev_state, n_labels, gathered, world, pa);
   return check_launch("mrf_label_range_dev");
 }
 

@@ -121,30 +121,37 @@ __device__ __forceinline__ void s13_resolve_digit(const unsigned int* __restrict
   __syncthreads();
 }
 
-// Resolve the digits of passes 0 .. upto-1 (upto >= 1) from the scratch block: needs the finished histogram
-// of pass upto-1 and (for upto >= 2) the memo block 0 wrote while resolving upto-1.
-__device__ __forceinline__ void s13_resolve(void* scratch, int upto, unsigned long long& prefix,
-                                            unsigned long long& k_rem, unsigned long long& n_total,
-                                            unsigned long long* s_tmp) {
+// Resolve the digits of passes 0 .. upto-1 (upto >= 1): needs the finished histogram `h` of pass upto-1 and (for
+// upto >= 2) the memo block 0 wrote into the scratch block while resolving upto-1.
+__device__ __forceinline__ void s13_resolve_from(const unsigned int* h, void* scratch, int upto, unsigned long long& prefix,
+                                                 unsigned long long& k_rem, unsigned long long& n_total,
+                                                 unsigned long long* s_tmp) {
   const unsigned long long* memo = s13_memo(scratch);
   const int p = upto - 1;
   prefix = 0; k_rem = 0; n_total = 0;
   if (p >= 1) { prefix = memo[3 * p]; k_rem = memo[3 * p + 1]; n_total = memo[3 * p + 2]; }
   unsigned long long cc;
-  s13_resolve_digit(s13_hist(scratch, p), p, prefix, k_rem, n_total, cc, s_tmp);
+  s13_resolve_digit(h, p, prefix, k_rem, n_total, cc, s_tmp);
+}
+__device__ __forceinline__ void s13_resolve(void* scratch, int upto, unsigned long long& prefix,
+                                            unsigned long long& k_rem, unsigned long long& n_total,
+                                            unsigned long long* s_tmp) {
+  s13_resolve_from(s13_hist(scratch, upto - 1), scratch, upto, prefix, k_rem, n_total, s_tmp);
 }
 
 // numpy.median from the finished selection state: middle element, mean of the two middles for even n,
 // NaN if any key is NaN or n == 0.  Row bands pass the successor words (st[3..5]) of all ranks,
 // `gathered` = [world][3]: NaN counts and counts(<= kth) add up, the inverted successor keys take the max.
-__device__ __forceinline__ double s13_median(const void* scratch, const unsigned long long* gathered, int world) {
+__device__ __forceinline__ double s13_median(const void* scratch, const unsigned long long* gathered, int world,
+                                             int stride = 3) {
   const unsigned long long* st = (const unsigned long long*)scratch;
   unsigned long long n_nan = st[3], cnt_le = st[4], inv_min = st[5];
   if (gathered) {
     n_nan = 0; cnt_le = 0; inv_min = 0;
     for (int r = 0; r < world; ++r) {
-      n_nan += gathered[3 * r]; cnt_le += gathered[3 * r + 1];
-      inv_min = gathered[3 * r + 2] > inv_min ? gathered[3 * r + 2] : inv_min;
+      const unsigned long long* g = gathered + (size_t)stride * r;
+      n_nan += g[0]; cnt_le += g[1];
+      inv_min = g[2] > inv_min ? g[2] : inv_min;
     }
   }
   const unsigned long long n = st[6], k = n ? (n - 1) / 2 : 0;

@@ -364,6 +364,79 @@ class PeerMailbox:
         self.local = None
 
 
+class PeerSync:
+    """The peer-memory context of the row-band pre-pass (csrc/peersync.cuh): every rank's IPC-shared block of
+    flags, gather slots and double-buffered histograms, mapped by all ranks.  With it the pre-pass runs WITHOUT
+    collective launches: its kernels reduce into every rank's histogram over NVLink, publish a flag, and the
+    next kernel polls its own flags.  Create once per process group (a collective), pass to ``banded_front`` /
+    ``banded_pass_resident``; every rank must then run the same sequence of steps.  ``check()`` (a collective)
+    raises if a rank timed out waiting for a peer."""
+
+    def __init__(self, group=None):
+        lib = _lib.lib()
+        self.group = group
+        self.world = dist.get_world_size(group)
+        self.rank = dist.get_rank(group)
+        if self.world > 8:
+            raise ValueError("PeerSync supports up to 8 ranks (one NVSwitch box)")
+        self.nbytes = lib.mrf_peer_sync_bytes()
+        handle = (C.c_ubyte * 64)()
+        ptr = C.c_void_p()
+        check(lib.mrf_peer_alloc(self.nbytes, C.byref(ptr), handle), "mrf_peer_alloc")
+        self.local = ptr.value
+        self._view().zero_()
+        torch.cuda.synchronize()
+        handles = [None] * self.world
+        dist.all_gather_object(handles, bytes(handle), group=group)
+        self.arg = _lib.PeerSyncArg()
+        self.arg.world, self.arg.rank = self.world, self.rank
+        for r in range(self.world):
+            if r == self.rank:
+                self.arg.ctx[r] = self.local
+            else:
+                p = C.c_void_p()
+                check(lib.mrf_peer_open((C.c_ubyte * 64).from_buffer_copy(handles[r]), C.byref(p)), "mrf_peer_open")
+                self.arg.ctx[r] = p.value
+        dist.barrier(group=group)                # every context is zeroed and mapped before the first step
+
+    def _view(self):
+        class _Arr:
+            pass
+        a = _Arr()
+        a.__cuda_array_interface__ = {"shape": (self.nbytes // 8,), "typestr": "<i8", "data": (self.local, False), "version": 2}
+        return torch.as_tensor(a, device="cuda")
+
+    def ref(self):
+        return C.byref(self.arg)
+
+    def begin(self):
+        """start of a step on the current stream: advances the device-side epoch"""
+        check(_lib.lib().mrf_peer_sync_begin(C.byref(self.arg), C.c_void_p(torch.cuda.current_stream().cuda_stream)),
+              "mrf_peer_sync_begin")
+
+    def status(self):
+        """(epoch, error) of this rank; error != 0: 1 + the phase whose wait timed out"""
+        w = self._view()[:2].cpu()
+        return int(w[0]), int(w[1])
+
+    def check(self):
+        bad = torch.tensor([int(self.status()[1] != 0)], dtype=torch.int64, device="cuda")
+        dist.all_reduce(bad, op=dist.ReduceOp.MAX, group=self.group)
+        if int(bad.cpu()[0]):
+            raise RuntimeError("a rank timed out waiting for a peer in the row-band pre-pass; results of that step are invalid")
+
+    def close(self):
+        lib = _lib.lib()
+        torch.cuda.synchronize()
+        dist.barrier(group=self.group)
+        for r in range(self.world):
+            if r != self.rank:
+                check(lib.mrf_peer_close(C.c_void_p(self.arg.ctx[r])), "mrf_peer_close")
+        dist.barrier(group=self.group)
+        check(lib.mrf_peer_free(C.c_void_p(self.local)), "mrf_peer_free")
+        self.local = None
+
+
 class BandBuffers:
     """Reusable HBM buffers of the banded device-resident pre-pass."""
 
@@ -417,11 +490,14 @@ def banded_mu(band, homographies, q_ar, buf, n_labels=pp.N_LABELS):
     buf.mu_done.record()
 
 
-def banded_front(band, homographies, q_ar, rigid_mask, zero_mask, buf, group=None, n_labels=pp.N_LABELS, mu_ready=False):
-    """The pre-pass of build_cost_volume for one row band with every whole-frame scalar kept on the device:
-    kernels on this band and SEVEN small NCCL collectives enqueued on the same stream in between -- five 32 KB
-    histogram all-reduces of the exact median (13-bit digits), one all-gather of its 3 successor words, one
-    all-gather of the 6 range words -- and no host synchronisation.  mu needs no collective (``banded_mu``).
+def banded_front(band, homographies, q_ar, rigid_mask, zero_mask, buf, group=None, n_labels=pp.N_LABELS, mu_ready=False,
+                 peer=None):
+    """The pre-pass of build_cost_volume for one row band with every whole-frame scalar kept on the device and no
+    host synchronisation.  The exact median (13-bit digits) needs five histogram sums over the ranks, its two
+    middle order statistics one gather of 3 words, the label range one gather of 6; mu needs nothing
+    (``banded_mu``).  ``peer=None``: SEVEN small NCCL collectives enqueued on the stream between the kernels.
+    ``peer`` (a ``PeerSync``): NO collective launch -- the kernels exchange over NVLink peer memory themselves
+    (remote reductions into every rank's histogram, flag stores, the next kernel polls).  Same bits either way.
     Leaves mu, B, labels in ``buf.state`` (identical on every rank) and this band's parallax / structures in
     ``buf``."""
     L = _lib.lib()
@@ -429,7 +505,10 @@ def banded_front(band, homographies, q_ar, rigid_mask, zero_mask, buf, group=Non
     st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
     p = _front_params(band, homographies, q_ar, n_labels)
     world = dist.get_world_size(group)
+    pr = peer.ref() if peer is not None else None
     fl = band.flow
+    if peer is not None:
+        peer.begin()
     check(L.mrf_front_parallax_band(C.byref(p), P(fl[0][0]), P(fl[0][1]), P(fl[1][0]), P(fl[1][1]), P(buf.par[0]), P(buf.par[1]),
                                     P(buf.scratch), st), "mrf_front_parallax_band")
     if mu_ready:
@@ -437,27 +516,31 @@ def banded_front(band, homographies, q_ar, rigid_mask, zero_mask, buf, group=Non
     else:
         banded_mu(band, homographies, q_ar, buf, n_labels)
     check(L.mrf_front_candidates_band(C.byref(p), P(buf.par[0]), P(buf.par[1]), P(rigid_mask), P(buf.state), P(buf.cand),
-                                      P(buf.count), P(buf.sel), st), "mrf_front_candidates_band")
+                                      P(buf.count), P(buf.sel), pr, st), "mrf_front_candidates_band")
     cap = band.rows * band.w
     for ps in range(_lib.SELECT13_PASSES):
-        dist.all_reduce(buf.sel_hist[ps], op=dist.ReduceOp.SUM, group=group)
+        if peer is None:
+            dist.all_reduce(buf.sel_hist[ps], op=dist.ReduceOp.SUM, group=group)
         if ps + 1 < _lib.SELECT13_PASSES:
-            check(L.mrf_select13_hist_dev(P(buf.cand), P(buf.count), cap, ps + 1, P(buf.sel), st), "mrf_select13_hist_dev")
+            check(L.mrf_select13_hist_dev(P(buf.cand), P(buf.count), cap, ps + 1, P(buf.sel), pr, st), "mrf_select13_hist_dev")
         else:
-            check(L.mrf_select13_successor_dev(P(buf.cand), P(buf.count), cap, P(buf.sel), st), "mrf_select13_successor_dev")
-    dist.all_gather_into_tensor(buf.succ_all, buf.sel_succ, group=group)
+            check(L.mrf_select13_successor_dev(P(buf.cand), P(buf.count), cap, P(buf.sel), pr, st), "mrf_select13_successor_dev")
+    if peer is None:
+        dist.all_gather_into_tensor(buf.succ_all, buf.sel_succ, group=group)
     # B_b = the median (compute_structure.py:221), structures, this band's range min / max
     check(L.mrf_front_structures_band(C.byref(p), P(buf.par[0]), P(buf.par[1]), P(zero_mask), P(buf.S[0]), P(buf.S[1]),
-                                      P(buf.state), P(buf.sel), P(buf.succ_all), world, P(buf.scratch), st),
-          "mrf_front_structures_band")
-    dist.all_gather_into_tensor(buf.mm_all, buf.mm, group=group)
-    check(L.mrf_label_range_dev(P(buf.state), int(n_labels), P(buf.mm_all), world, st), "mrf_label_range_dev")
+                                      P(buf.state), P(buf.sel), None if peer is not None else P(buf.succ_all), world,
+                                      P(buf.scratch), pr, st), "mrf_front_structures_band")
+    if peer is None:
+        dist.all_gather_into_tensor(buf.mm_all, buf.mm, group=group)
+    check(L.mrf_label_range_dev(P(buf.state), int(n_labels), None if peer is not None else P(buf.mm_all), world, pr, st),
+          "mrf_label_range_dev")
     return buf
 
 
 def banded_pass_resident(band, homographies, epipoles, rigid_mask, stats, buf=None, rho="lorentzian", sigma=1.0,
                          interp="cubic", range_mask="rigid_only", variant="staged", out_ptr=(None, None), plane_stride=0,
-                         want_cost=True, halo_miss=None, events=None, masks=None, channels=None, q_new=None):
+                         want_cost=True, halo_miss=None, events=None, masks=None, channels=None, q_new=None, peer=None):
     """Row-band cost volumes with the device-resident pre-pass.  Returns dict(cost, mins, argmins, q, buffers).
     ``q_new``: already refined epipoles (then nothing in here touches the host, so the whole step -- kernels,
     NCCL collectives, the side-stream fork -- can be captured in a CUDA graph)."""
@@ -482,7 +565,7 @@ def banded_pass_resident(band, homographies, epipoles, rigid_mask, stats, buf=No
             ch_done.record(side)
             for tns in (channels[0], *channels[1]):
                 tns.record_stream(cur)
-    banded_front(band, homographies, q_new, rigid_mask, zero_mask, buf, group=stats.group, mu_ready=True)
+    banded_front(band, homographies, q_new, rigid_mask, zero_mask, buf, group=stats.group, mu_ready=True, peer=peer)
     if ch_done is not None:
         cur.wait_event(ch_done)
     ref64, tex = channels
@@ -504,7 +587,8 @@ def _side_stream(dev):
 
 # ------------------------------------------------------------------------------------------ driver
 def banded_cost_volume(t, stats, rank, world, rho="lorentzian", sigma=1.0, interp="cubic", range_mask="rigid_only",
-                       variant="staged", peer=(None, None), keep_local=True, halo=None, timers=None, resident=True):
+                       variant="staged", peer=(None, None), keep_local=True, halo=None, timers=None, resident=True,
+                       peer_sync=None):
     """build_cost_volume for this rank's band of the host triplet ``t`` (dict as synth.make_triplet
     returns).  ``resident=True`` keeps the whole-frame scalars on the device (``banded_pass_resident``);
     ``False`` drives the statistics through the host (``BandStats`` / ``DistSelect``, the protocol the gloo
@@ -524,7 +608,7 @@ def banded_cost_volume(t, stats, rank, world, rho="lorentzian", sigma=1.0, inter
             mask = torch.from_numpy((rig[y0:y1] > 0).astype(np.uint8)).cuda()
             r = banded_pass_resident(band, t["homographies"], t["epipoles"], mask, stats, rho=rho, sigma=sigma, interp=interp,
                                      range_mask=range_mask, variant=variant, out_ptr=outs, plane_stride=stride,
-                                     want_cost=keep_local, halo_miss=miss, events=timers)
+                                     want_cost=keep_local, halo_miss=miss, events=timers, peer=peer_sync)
             mu, B, labels = pp.state_to_host(r["buffers"].state)
             res = (r["cost"], r["buffers"].S, mu, B, r["q"], labels, r["mins"], r["argmins"])
         else:
@@ -614,6 +698,7 @@ def bench_bands(hw, steps, warm, interp="cubic", variant="staged", ClockSampler=
         return rec
 
     stats = BandStats()
+    ps = PeerSync()
     y0, y1 = band_plan(h, world)[rank]
     rows = y1 - y0
     halo_rows = 32
@@ -624,7 +709,7 @@ def bench_bands(hw, steps, warm, interp="cubic", variant="staged", ClockSampler=
         miss = torch.zeros(1, dtype=torch.int32, device="cuda")
         bbuf = BandBuffers(rows, w, world=world)
         banded_pass_resident(band, H_ar, q_ar, rigid, stats, buf=bbuf, interp=interp, variant=variant, want_cost=False,
-                             halo_miss=miss, masks=(nonrigid, nonrigid))
+                             halo_miss=miss, masks=(nonrigid, nonrigid), peer=ps)
         if stats.total(int(miss.cpu()[0])) == 0:
             break
         halo_rows *= 2
@@ -642,14 +727,15 @@ def bench_bands(hw, steps, warm, interp="cubic", variant="staged", ClockSampler=
         outs = tuple(p.band_ptr(y0) for p in peers) if gather else tuple(c.data_ptr() for c in cost_local)
         return banded_pass_resident(band, H_ar, q_ar, rigid, stats, buf=bbuf, interp=interp, range_mask="rigid_only",
                                     variant=variant, out_ptr=outs, plane_stride=(h * w if gather else 0), halo_miss=miss,
-                                    events=events, masks=(nonrigid, nonrigid), q_new=q_new)
+                                    events=events, masks=(nonrigid, nonrigid), q_new=q_new,
+                                    peer=None if mode == "local_nccl" else ps)
 
     # The step is ~25 short launches and 7 collectives: enqueued from Python it is bound by the host, not the GPUs.
     # Capture it once per output mode (NCCL collectives are capturable) and replay with one launch.
     graphs = {}
     if use_graph:
         try:
-            for mode in ("local", "gather"):
+            for mode in ("local", "gather", "local_nccl"):
                 for _ in range(2):
                     eager(mode)
                 barrier()
@@ -665,7 +751,7 @@ def bench_bands(hw, steps, warm, interp="cubic", variant="staged", ClockSampler=
             torch.cuda.synchronize()
 
     def step(mode, events=None):
-        key = "gather" if mode == "gather" else "local"
+        key = mode if mode in ("gather", "local_nccl") else "local"
         if key in graphs and events is None:
             graphs[key].replay()
         else:
@@ -678,6 +764,7 @@ def bench_bands(hw, steps, warm, interp="cubic", variant="staged", ClockSampler=
     res["compute_only"] = timed(lambda: step("local"))
     res["compute_and_gather"] = timed(lambda: step("gather"))
     res["compute_and_d2h"] = timed(lambda: step("d2h"))
+    res["compute_only_nccl_collectives"] = timed(lambda: step("local_nccl"))
     for _ in range(3):                                       # the kernel alone: eager launches with events round it
         flush.fill_(1)
         eager("local", kernel_events)
@@ -693,9 +780,12 @@ def bench_bands(hw, steps, warm, interp="cubic", variant="staged", ClockSampler=
         rec[k] = {"ms_per_step": ms, "value": units / (ms * 1e-3)}
     if res_eager is not None:
         rec["compute_only_eager_launches"] = {"ms_per_step": res_eager, "value": units / (res_eager * 1e-3)}
-    rec.update({"parallelism": "row bands x%d, device-resident statistics: 7 NCCL collectives on the stream "
-                               "(5 x 32 KB histogram all-reduce, 2 small all-gathers), none for mu; %s" % (
+    ps.check()
+    rec.update({"parallelism": "row bands x%d, device-resident statistics exchanged over NVLink peer memory from inside the "
+                               "pre-pass kernels (5 histogram reductions, 2 small gathers; no collective launch; none at all "
+                               "for mu); compute_only_nccl_collectives = the same step with 7 NCCL collectives instead; %s" % (
                                    world, "the step replayed as one CUDA graph" if graphs else "eager launches"),
+                "peer_sync_epochs": ps.status()[0],
                 "halo_rows": halo_rows, "n_miss": int(n_miss), "kernel_ms_per_launch": kms,
                 "band_rows": rows, "d2h_bytes_per_rank": int(2 * L * rows * w * 4)})
     if verify:
@@ -715,6 +805,7 @@ def bench_bands(hw, steps, warm, interp="cubic", variant="staged", ClockSampler=
     barrier()
     for p in peers:
         p.close()
+    ps.close()
     if n_miss:
         raise RuntimeError("a timed step sampled outside its halo")
     return rec if rank == 0 else None

@@ -65,6 +65,22 @@ def _worker(rank, world, port, queue):
         mb.check()
         out["mailbox_status"] = mb.status()
         mb.close()
+        # the pre-pass WITHOUT collective launches: histogram reductions, successor and range gathers over NVLink
+        # peer memory from inside the kernels (csrc/peersync.cuh) -- same bits as the NCCL route, step after step
+        # (the histogram sets alternate with the step's parity), also when one rank arrives late
+        ps = sharding.PeerSync()
+        same = True
+        for it in range(5):
+            if it == 2 and rank == 0:
+                torch.cuda.synchronize(); time.sleep(0.7)
+            res_p = sharding.banded_cost_volume(t, stats, rank, world, halo=res["halo"], peer_sync=ps)
+            same &= bool(res_p["mu"] == res["mu"] and res_p["B"] == res["B"] and np.array_equal(res_p["labels"], res["labels"])
+                         and all(torch.equal(res_p["argmins"][f], res["argmins"][f]) for f in range(2))
+                         and all(torch.equal(res_p["cost"][f], res_h["cost"][f]) for f in range(2)))
+        ps.check()
+        out["peer_sync_equals_nccl"] = same
+        out["peer_sync_status"] = ps.status()
+        ps.close()
         # an epipole estimate whose 21x21 window straddles the band boundary (row 104): the bands assemble the
         # window and every rank solves the same 441-pixel problem -- same bits as one GPU
         t2 = dict(t, epipoles=[t["epipoles"][0] + np.array([0.0, 11.0]), t["epipoles"][1] + np.array([0.0, 12.0])])
@@ -146,6 +162,7 @@ def test_two_band_volume_equals_whole_frame():
     assert res[0]["host_equals_resident"] and res[1]["host_equals_resident"]
     for r in (0, 1):
         assert res[r]["mailbox_ops"] and res[r]["mailbox_status"] == 0
+        assert res[r]["peer_sync_equals_nccl"] and res[r]["peer_sync_status"][1] == 0 and res[r]["peer_sync_status"][0] == 5
     assert res[0]["straddle_q"] == res[1]["straddle_q"]
     assert o["stats_bit_equal"] and o["straddle_equal"]
     for f in range(2):

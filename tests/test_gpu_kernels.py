@@ -482,21 +482,21 @@ def test_device_side_median_and_label_range(dev, n):
     lo0, hi0, lo1, hi1 = -0.37 - n, 2.11, -0.2, 3.3 + 0.001 * n
     state[_lib.STATE_MINMAX:_lib.STATE_MINMAX + 4] = torch.tensor([lo0, hi0, lo1, hi1], dtype=torch.float64)
     for nl in (51, 7, 2):
-        _lib.check(L.mrf_label_range_dev(C.c_void_p(state.data_ptr()), nl, None, 0, st), "label_range_dev")
+        _lib.check(L.mrf_label_range_dev(C.c_void_p(state.data_ptr()), nl, None, 0, None, st), "label_range_dev")
         lab = state[_lib.STATE_LABELS:_lib.STATE_LABELS + nl].cpu().numpy()
         assert np.array_equal(lab, np.linspace(1.5 * min(lo0, lo1), 1.5 * max(hi0, hi1), nl))
     state[_lib.STATE_MINMAX:_lib.STATE_MINMAX + 4] = 0.0          # degenerate range: all labels equal
-    _lib.check(L.mrf_label_range_dev(C.c_void_p(state.data_ptr()), 51, None, 0, st), "label_range_dev")
+    _lib.check(L.mrf_label_range_dev(C.c_void_p(state.data_ptr()), 51, None, 0, None, st), "label_range_dev")
     assert np.array_equal(state[_lib.STATE_LABELS:_lib.STATE_LABELS + 51].cpu().numpy(), np.linspace(0.0, 0.0, 51))
     # row bands: the six range words of every band are gathered and combined in the kernel
     g = torch.tensor([[lo0, 1.0, 0.5, hi1, 0, 0], [-0.1, hi0, lo1, 2.0, 0, 0], [0.0, 0.0, 0.0, 0.0, 0, 0]], dtype=torch.float64,
                      device="cuda")
-    _lib.check(L.mrf_label_range_dev(C.c_void_p(state.data_ptr()), 51, C.c_void_p(g.data_ptr()), 3, st), "label_range_dev")
+    _lib.check(L.mrf_label_range_dev(C.c_void_p(state.data_ptr()), 51, C.c_void_p(g.data_ptr()), 3, None, st), "label_range_dev")
     assert np.array_equal(state[_lib.STATE_LABELS:_lib.STATE_LABELS + 51].cpu().numpy(),
                           np.linspace(1.5 * min(lo0, lo1), 1.5 * max(hi0, hi1), 51))
     assert state[_lib.STATE_MINMAX:_lib.STATE_MINMAX + 4].tolist() == [min(lo0, -0.1, 0.0), max(1.0, hi0), min(0.5, lo1, 0.0), max(hi1, 2.0)]
     g[1, 4] = 1.0                                                  # a NaN flag on one band poisons the label set
-    _lib.check(L.mrf_label_range_dev(C.c_void_p(state.data_ptr()), 51, C.c_void_p(g.data_ptr()), 3, st), "label_range_dev")
+    _lib.check(L.mrf_label_range_dev(C.c_void_p(state.data_ptr()), 51, C.c_void_p(g.data_ptr()), 3, None, st), "label_range_dev")
     assert np.isnan(state[_lib.STATE_LABELS:_lib.STATE_LABELS + 51].cpu().numpy()).all()
 
 
@@ -527,16 +527,16 @@ def test_select13_sharded_steps(dev, n, kind):
     o, bins = _lib.SELECT13_HIST_OFFSET // 4, _lib.SELECT13_BINS
     for r in range(2):
         _lib.check(L.mrf_select13_begin(P(scr[r]), st), "begin")
-        _lib.check(L.mrf_select13_hist_dev(P(keys[r]), P(cnt[r]), keys[r].numel(), 0, P(scr[r]), st), "hist0")
+        _lib.check(L.mrf_select13_hist_dev(P(keys[r]), P(cnt[r]), keys[r].numel(), 0, P(scr[r]), None, st), "hist0")
     for ps in range(_lib.SELECT13_PASSES):
         hs = [scr[r].view(torch.int32)[o + ps * bins:o + (ps + 1) * bins] for r in range(2)]
         tot = hs[0] + hs[1]                                               # the all-reduce
         hs[0].copy_(tot); hs[1].copy_(tot)
         for r in range(2):
             if ps + 1 < _lib.SELECT13_PASSES:
-                _lib.check(L.mrf_select13_hist_dev(P(keys[r]), P(cnt[r]), keys[r].numel(), ps + 1, P(scr[r]), st), "hist")
+                _lib.check(L.mrf_select13_hist_dev(P(keys[r]), P(cnt[r]), keys[r].numel(), ps + 1, P(scr[r]), None, st), "hist")
             else:
-                _lib.check(L.mrf_select13_successor_dev(P(keys[r]), P(cnt[r]), keys[r].numel(), P(scr[r]), st), "succ")
+                _lib.check(L.mrf_select13_successor_dev(P(keys[r]), P(cnt[r]), keys[r].numel(), P(scr[r]), None, st), "succ")
     so = _lib.SELECT13_SUCC_OFFSET // 8
     gathered = torch.cat([scr[r].view(torch.int64)[so:so + 3] for r in range(2)]).contiguous()   # the all-gather
     for r in range(2):

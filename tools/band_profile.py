@@ -22,7 +22,7 @@ def main():
     ap.add_argument("--shape", default="4k")
     ap.add_argument("--steps", type=int, default=2)
     args = ap.parse_args()
-    hw = synth.SHAPES[args.shape]
+    hw = synth.SHAPES[args.shape] if args.shape in synth.SHAPES else tuple(int(v) for v in args.shape.split("x"))
     td = synth.make_triplet_device(hw, seed=1001, n_waves=8)
     band = sharding.device_band(td, (0, hw[0]), 0)
     rigid = (td["rigidity"] > 0).to(torch.uint8)

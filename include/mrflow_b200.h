@@ -257,6 +257,15 @@ int mrf_cost_volume(const mrf_costvol_params* p_host, const double* ref_ch, cons
                     const double* labels, const uint8_t* nonrigid, const uint8_t* occluded,
                     void* cost, float* min_cost, int32_t* argmin, int* halo_miss,
                     const double* dev_state, mrf_stream_t stream);
+/* Both neighbour frames of a triplet in ONE launch (grid.z = frame): same arithmetic, but the tail of one
+ * frame's blocks overlaps the head of the other's, and there is one launch less.  p0 / p1: the per-frame
+ * parameters (H, q, mu, B, label_scale, state_frame, nb band); shape, sampler, rho, layout, variant and
+ * n_labels must agree.  ref_ch, labels, nonrigid, halo_miss and dev_state are shared. */
+int mrf_cost_volume_pair(const mrf_costvol_params* p0_host, const mrf_costvol_params* p1_host, const double* ref_ch,
+                         const float* nb_texels0, const float* nb_texels1, const double* labels,
+                         const uint8_t* nonrigid, const uint8_t* occluded0, const uint8_t* occluded1,
+                         void* cost0, void* cost1, float* min_cost0, float* min_cost1, int32_t* argmin0,
+                         int32_t* argmin1, int* halo_miss, const double* dev_state, mrf_stream_t stream);
 
 /* ---- the pre-pass of build_cost_volume with no host round trip (pipeline/build_cost_volume.py:78-192
  * with the live conventions of compute_structure.py): residual flow -> parallax (both frames), mu,

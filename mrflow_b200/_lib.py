@@ -90,6 +90,8 @@ SIGNATURES = {
     "mrf_prepare_channels": (_I, [_P, _I, _I, _I, _P, _P, _P, _P]),
     "mrf_warp_sample": (_I, [_P, _I, _I, _I, _DP, _P, _P, _Z, _I, _P, _P, _P]),
     "mrf_cost_volume": (_I, [C.POINTER(CostVolParams), _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
+    "mrf_cost_volume_pair": (_I, [C.POINTER(CostVolParams), C.POINTER(CostVolParams), _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P,
+                                  _P, _P, _P, _P, _P]),
     "mrf_front_scratch_bytes": (_Z, []),
     "mrf_cost_volume_front": (_I, [C.POINTER(FrontParams), _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "mrf_front_mu_whole": (_I, [C.POINTER(FrontParams), _P, _P, _P]),

@@ -274,7 +274,10 @@ struct __align__(16) LabelRec { double ab, den, rden, safe; };   // safe: 1.0 / 
 
 template <int INTERP, bool STAGED, int OCC, int LAYOUT, bool WF>
 __global__ void __launch_bounds__(kThreads, OCC)
-k_cost_volume(const __grid_constant__ CVArgs a) {
+k_cost_volume(const __grid_constant__ CVArgs a0, const __grid_constant__ CVArgs a1) {
+  // blockIdx.z selects the neighbour frame: both frames of a triplet share one grid, so the tail of one
+  // frame's blocks overlaps the head of the other's (grid.z = 1: a0 only)
+  const CVArgs& a = (blockIdx.z == 0) ? a0 : a1;
   extern __shared__ __align__(128) unsigned char dyn_smem[];
   __shared__ LabelRec s_lab[kMaxLabels];    // A*B, B*A/mu - 1, RN(1/that), exact-sequence-safe flag
   __shared__ __align__(16) float4 s_wt[32]; // OpenCV's interpolation table: weights at frac/32
@@ -716,11 +719,13 @@ k_cost_volume(const __grid_constant__ CVArgs a) {
 
 using namespace mrf;
 
-extern "C" int mrf_cost_volume(const mrf_costvol_params* p, const double* ref_ch, const float* nb_texels,
-                               const double* labels, const uint8_t* nonrigid, const uint8_t* occluded,
-                               void* cost, float* min_cost, int32_t* argmin, int* halo_miss,
-                               const double* dev_state, mrf_stream_t stream) {
-  MRF_CHECK_ARG(p && ref_ch && nb_texels && (labels || dev_state));
+struct CVHost {            // the device-pointer half of one frame's arguments
+  const float* nb_texels; const uint8_t* occluded; void* cost; float* min_cost; int32_t* argmin;
+};
+
+static int cv_fill(const mrf_costvol_params* p, const double* ref_ch, const double* labels, const uint8_t* nonrigid,
+                   const CVHost& h, int* halo_miss, const double* dev_state, CVArgs* out) {
+  MRF_CHECK_ARG(p && ref_ch && h.nb_texels && (labels || dev_state));
   MRF_CHECK_ARG(!dev_state || p->state_frame == 0 || p->state_frame == 1);
   MRF_CHECK_ARG(p->rows > 0 && p->w > 0 && p->frame_h >= p->y0 + p->rows && p->y0 >= 0);
   MRF_CHECK_ARG(p->nb_rows > 0 && p->nb_y0 >= 0 && p->nb_y0 + p->nb_rows <= p->frame_h);
@@ -728,12 +733,12 @@ extern "C" int mrf_cost_volume(const mrf_costvol_params* p, const double* ref_ch
   MRF_CHECK_ARG(p->interp == MRF_INTERP_CUBIC || p->interp == MRF_INTERP_LINEAR);
   MRF_CHECK_ARG(p->rho >= MRF_RHO_LORENTZIAN && p->rho <= MRF_RHO_NONE);
   MRF_CHECK_ARG(p->layout == MRF_LAYOUT_LHW_F32 || p->layout == MRF_LAYOUT_HWL_I32);
-  MRF_CHECK_ARG(cost || min_cost || argmin);
-  MRF_CHECK_ARG(((uintptr_t)nb_texels & 15) == 0);
+  MRF_CHECK_ARG(h.cost || h.min_cost || h.argmin);
+  MRF_CHECK_ARG(((uintptr_t)h.nb_texels & 15) == 0);
   const long long plane_stride = p->cost_plane_stride > 0 ? p->cost_plane_stride : (long long)p->rows * p->w;
   MRF_CHECK_ARG(plane_stride >= (long long)p->rows * p->w);
   MRF_CHECK_ARG((double)plane_stride * 4.0 * p->n_labels < 4294967296.0);   /* 32-bit store offsets */
-  CVArgs a;
+  CVArgs& a = *out;
   a.rows = p->rows; a.w = p->w; a.y0 = p->y0; a.frame_h = p->frame_h;
   a.nb_rows = p->nb_rows; a.nb_y0 = p->nb_y0;
   a.H = mat3(p->H); a.q = pt2(p->q);
@@ -741,19 +746,25 @@ extern "C" int mrf_cost_volume(const mrf_costvol_params* p, const double* ref_ch
   a.L = p->n_labels; a.rho = p->rho; a.rho_param = p->rho_param;
   a.cw0 = p->cw[0]; a.cw1 = p->cw[1]; a.cw2 = p->cw[2];
   a.layout = p->layout; a.i32_scale = (float)p->i32_scale;
-  a.ref_ch = ref_ch; a.nb = (const float4*)nb_texels; a.labels = labels;
-  a.nonrigid = nonrigid; a.occluded = occluded;
-  a.cost = cost; a.min_cost = min_cost; a.argmin = argmin; a.halo_miss = halo_miss;
+  a.ref_ch = ref_ch; a.nb = (const float4*)h.nb_texels; a.labels = labels;
+  a.nonrigid = nonrigid; a.occluded = h.occluded;
+  a.cost = h.cost; a.min_cost = h.min_cost; a.argmin = h.argmin; a.halo_miss = halo_miss;
   a.plane_stride = plane_stride;
   a.state = dev_state; a.frame = p->state_frame;
   a.wm1 = (double)(p->w - 1); a.hm1 = (double)(p->frame_h - 1);
   a.s2 = p->rho_param * p->rho_param; a.rs2 = 1.0 / a.s2;
+  const int occ = (p->variant & MRF_VARIANT_OCC2) ? 2 : ((p->variant & MRF_VARIANT_OCC4) ? 4 : 3);
+  a.win_cap = (occ == 4) ? kWinCap4 : kWinCap;
+  return 0;
+}
 
-  const dim3 grid(cdiv(p->w, kTX), cdiv(p->rows, kTY));
+// launch for one frame (nz = 1) or both frames of a triplet in one grid (nz = 2; p = the first frame's params:
+// shape, sampler, layout and variant are common to both)
+static int cv_launch(const mrf_costvol_params* p, const CVArgs& a, const CVArgs& b, int nz, mrf_stream_t stream) {
+  const dim3 grid(cdiv(p->w, kTX), cdiv(p->rows, kTY), (unsigned)nz);
   const bool staged = ((p->variant & 1) != MRF_VARIANT_GATHER);
   const int occ = (p->variant & MRF_VARIANT_OCC2) ? 2 : ((p->variant & MRF_VARIANT_OCC4) ? 4 : 3);
   const bool wf = (p->variant & MRF_VARIANT_WARPFAST) != 0;
-  a.win_cap = (occ == 4) ? kWinCap4 : kWinCap;
   const size_t smem = staged ? (size_t)a.win_cap * 16 : 0;
   cudaError_t e = cudaSuccess;
 #define MRF_LAUNCH(I, ST, OC, LY, WFv)                                                                         \
@@ -767,7 +778,7 @@ extern "C" int mrf_cost_volume(const mrf_costvol_params* p, const double* ref_ch
                                (int)smem);                                                                     \
       if (e == cudaSuccess) attr_set.fetch_or(1ull << (dev_ & 63));                                            \
     }                                                                                                          \
-    if (e == cudaSuccess) k_cost_volume<I, ST, OC, LY, WFv><<<grid, kThreads, smem, S(stream)>>>(a);           \
+    if (e == cudaSuccess) k_cost_volume<I, ST, OC, LY, WFv><<<grid, kThreads, smem, S(stream)>>>(a, b);        \
   } while (0)
 #define MRF_LAUNCH_LY(I, ST, OC, WFv) do { if (p->layout == MRF_LAYOUT_LHW_F32) MRF_LAUNCH(I, ST, OC, MRF_LAYOUT_LHW_F32, WFv); else MRF_LAUNCH(I, ST, OC, MRF_LAYOUT_HWL_I32, WFv); } while (0)
 #define MRF_LAUNCH_ST(I, OC, WFv) do { if (staged) MRF_LAUNCH_LY(I, true, OC, WFv); else MRF_LAUNCH_LY(I, false, OC, WFv); } while (0)
@@ -780,4 +791,31 @@ extern "C" int mrf_cost_volume(const mrf_costvol_params* p, const double* ref_ch
 #undef MRF_LAUNCH
   if (e != cudaSuccess) return fail((int)e, "mrf_cost_volume: %s", cudaGetErrorString(e));
   return check_launch("mrf_cost_volume");
+}
+
+extern "C" int mrf_cost_volume(const mrf_costvol_params* p, const double* ref_ch, const float* nb_texels,
+                               const double* labels, const uint8_t* nonrigid, const uint8_t* occluded,
+                               void* cost, float* min_cost, int32_t* argmin, int* halo_miss,
+                               const double* dev_state, mrf_stream_t stream) {
+  CVArgs a;
+  const CVHost h{nb_texels, occluded, cost, min_cost, argmin};
+  const int rc = cv_fill(p, ref_ch, labels, nonrigid, h, halo_miss, dev_state, &a);
+  if (rc) return rc;
+  return cv_launch(p, a, a, 1, stream);
+}
+
+extern "C" int mrf_cost_volume_pair(const mrf_costvol_params* p0, const mrf_costvol_params* p1, const double* ref_ch,
+                                    const float* nb_texels0, const float* nb_texels1, const double* labels,
+                                    const uint8_t* nonrigid, const uint8_t* occluded0, const uint8_t* occluded1,
+                                    void* cost0, void* cost1, float* min_cost0, float* min_cost1, int32_t* argmin0,
+                                    int32_t* argmin1, int* halo_miss, const double* dev_state, mrf_stream_t stream) {
+  MRF_CHECK_ARG(p0 && p1);
+  MRF_CHECK_ARG(p0->rows == p1->rows && p0->w == p1->w && p0->y0 == p1->y0 && p0->frame_h == p1->frame_h);
+  MRF_CHECK_ARG(p0->interp == p1->interp && p0->layout == p1->layout && p0->variant == p1->variant && p0->n_labels == p1->n_labels);
+  CVArgs a, b;
+  const CVHost h0{nb_texels0, occluded0, cost0, min_cost0, argmin0}, h1{nb_texels1, occluded1, cost1, min_cost1, argmin1};
+  int rc = cv_fill(p0, ref_ch, labels, nonrigid, h0, halo_miss, dev_state, &a);
+  if (!rc) rc = cv_fill(p1, ref_ch, labels, nonrigid, h1, halo_miss, dev_state, &b);
+  if (rc) return rc;
+  return cv_launch(p0, a, b, 2, stream);
 }

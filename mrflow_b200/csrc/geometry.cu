@@ -387,7 +387,7 @@ constexpr int kFrontBlocks = 592;   // 4 x 148
 // blocks of the candidates kernel: each zeroes and flushes an 8192-bin shared histogram, so four fat blocks
 // per SM at most
 static inline unsigned front_cand_blocks(long long n) {
-  long long b = (n + 1023) / 1024;
+  long long b = (n + 2047) / 2048;
   if (b > 4 * kSMs) b = 4 * kSMs;
   return (unsigned)(b < 1 ? 1 : b);
 }

@@ -457,9 +457,10 @@ int mrf_select_successor_key_f64(const double* keys, size_t n, unsigned long lon
 }
 
 static unsigned s13_blocks(size_t capacity) {
-  // every block zeroes / scans / flushes 8192 bins (a fixed ~3 us), so at least ~2K keys per block; up to four
-  // blocks per SM (32 KB of shared memory each) so that a large sweep has enough loads in flight
-  size_t b = (capacity + 2047) / 2048;
+  // every block zeroes / scans / flushes 8192 bins (a fixed ~3 us) and takes a residency slot from a concurrent
+  // cost-volume kernel, so at least ~4K keys per block; up to four blocks per SM (32 KB of shared memory each) so
+  // that a large sweep has enough loads in flight
+  size_t b = (capacity + 4095) / 4096;
   if (b > (size_t)kSMs * 4) b = (size_t)kSMs * 4;
   if (b < 1) b = 1;
   return (unsigned)b;

@@ -301,6 +301,20 @@ def warp_sample(img, H, xn, yn, interp="cubic", want_mask=True):
     return J, mask
 
 
+def _cv_params(rows, w, nb_rows, H, q, mu, B, label_scale, Ln, rho, rho_param, cw, interp, layout, i32_scale, variant, y0, frame_h,
+               nb_y0, plane_stride, frame):
+    p = CostVolParams()
+    p.rows, p.w, p.y0, p.frame_h, p.nb_rows, p.nb_y0 = rows, w, int(y0), frame_h, nb_rows, int(nb_y0)
+    p.H = _mat(H); p.q = _pt(q)
+    p.mu, p.B, p.label_scale = float(mu), float(B), float(label_scale)
+    p.n_labels, p.interp, p.rho, p.rho_param = Ln, INTERP[interp], RHO[rho], float(rho_param)
+    p.cw = dvec(cw)
+    p.layout, p.i32_scale, p.variant = LAYOUT[layout], float(i32_scale), VARIANT[variant]
+    p.cost_plane_stride = int(plane_stride)
+    p.state_frame = int(frame)
+    return p
+
+
 def cost_volume(ref_ch, nb_texels, labels, H, q, mu, B, label_scale=1.0, nonrigid=None, occluded=None,
                 rho="lorentzian", rho_param=1.0, cw=(0.01, 1.0, 1.0), interp="cubic", layout="LHW_F32",
                 i32_scale=1000.0, variant="staged", y0=0, frame_h=None, nb_y0=0, want_cost=True,
@@ -318,15 +332,8 @@ def cost_volume(ref_ch, nb_texels, labels, H, q, mu, B, label_scale=1.0, nonrigi
     frame_h = rows if frame_h is None else int(frame_h)
     Ln = labels.numel() if labels is not None else int(n_labels)
     dev = ref_ch.device
-    p = CostVolParams()
-    p.rows, p.w, p.y0, p.frame_h, p.nb_rows, p.nb_y0 = rows, w, int(y0), frame_h, nb_rows, int(nb_y0)
-    p.H = _mat(H); p.q = _pt(q)
-    p.mu, p.B, p.label_scale = float(mu), float(B), float(label_scale)
-    p.n_labels, p.interp, p.rho, p.rho_param = Ln, INTERP[interp], RHO[rho], float(rho_param)
-    p.cw = dvec(cw)
-    p.layout, p.i32_scale, p.variant = LAYOUT[layout], float(i32_scale), VARIANT[variant]
-    p.cost_plane_stride = int(plane_stride)
-    p.state_frame = int(frame)
+    p = _cv_params(rows, w, nb_rows, H, q, mu, B, label_scale, Ln, rho, rho_param, cw, interp, layout, i32_scale, variant, y0,
+                   frame_h, nb_y0, plane_stride, frame)
     cost = out
     if out_ptr is not None:
         cost = None                      # raw (possibly peer-mapped) destination
@@ -339,6 +346,43 @@ def cost_volume(ref_ch, nb_texels, labels, H, q, mu, B, label_scale=1.0, nonrigi
     check(_lib.lib().mrf_cost_volume(C.byref(p), _p(ref_ch), _p(nb_texels), _p(labels), _p(nonrigid), _p(occluded),
                                      dst, _p(mn), _p(am), _p(halo_miss), _p(state), _stream()), "mrf_cost_volume")
     return cost, mn, am
+
+
+def cost_volume_pair(ref_ch, nb_texels, labels, H, q, mu, B, label_scale=(1.0, 1.0), nonrigid=None, occluded=(None, None),
+                     rho="lorentzian", rho_param=1.0, cw=(0.01, 1.0, 1.0), interp="cubic", layout="LHW_F32", i32_scale=1000.0,
+                     variant="staged", y0=0, frame_h=None, nb_y0=0, want_cost=True, want_min=True, want_argmin=True,
+                     out=(None, None), halo_miss=None, out_ptr=(None, None), plane_stride=0, state=None, n_labels=None):
+    """``cost_volume`` for BOTH neighbour frames of a triplet in one launch (grid.z = frame; the tail of one
+    frame's blocks overlaps the head of the other's).  Per-frame arguments are pairs indexed by frame (0 = bwd,
+    1 = fwd).  Returns [(cost, min, argmin), (cost, min, argmin)]."""
+    _chk(ref_ch, F64, "ref_ch"); _chk(labels, F64, "labels"); _chk(nonrigid, U8, "nonrigid"); _chk(state, F64, "state")
+    for f in range(2):
+        _chk(nb_texels[f], F32, "nb_texels"); _chk(occluded[f], U8, "occluded")
+    rows, w = ref_ch.shape[:2]
+    assert nb_texels[0].shape == nb_texels[1].shape
+    nb_rows = nb_texels[0].shape[0]
+    frame_h = rows if frame_h is None else int(frame_h)
+    Ln = labels.numel() if labels is not None else int(n_labels)
+    dev = ref_ch.device
+    ps, cost, mn, am, dst = [], [], [], [], []
+    for f in range(2):
+        ps.append(_cv_params(rows, w, nb_rows, H[f], q[f], mu[f], B[f], label_scale[f], Ln, rho, rho_param, cw, interp, layout,
+                             i32_scale, variant, y0, frame_h, nb_y0, plane_stride, f))
+        c = out[f]
+        if out_ptr[f] is not None:
+            c = None
+        elif c is None and want_cost:
+            c = (torch.empty((Ln, rows, w), dtype=F32, device=dev) if layout == "LHW_F32"
+                 else torch.empty((rows, w, Ln), dtype=I32, device=dev))
+        cost.append(c)
+        mn.append(torch.empty((rows, w), dtype=F32, device=dev) if want_min else None)
+        am.append(torch.empty((rows, w), dtype=I32, device=dev) if want_argmin else None)
+        dst.append(C.c_void_p(int(out_ptr[f])) if out_ptr[f] is not None else _p(c))
+    check(_lib.lib().mrf_cost_volume_pair(C.byref(ps[0]), C.byref(ps[1]), _p(ref_ch), _p(nb_texels[0]), _p(nb_texels[1]),
+                                          _p(labels), _p(nonrigid), _p(occluded[0]), _p(occluded[1]), dst[0], dst[1],
+                                          _p(mn[0]), _p(mn[1]), _p(am[0]), _p(am[1]), _p(halo_miss), _p(state), _stream()),
+          "mrf_cost_volume_pair")
+    return [(cost[0], mn[0], am[0]), (cost[1], mn[1], am[1])]
 
 
 # ------------------------------------------------------------------------------------ neighbours of the path

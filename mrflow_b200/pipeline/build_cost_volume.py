@@ -210,14 +210,17 @@ def cost_volume_pass_resident(band, homographies, epipoles, rigid_mask, rho="lor
 
 class ResidentStep:
     """One triplet resident in HBM, stepped repeatedly (dataset runs, benchmarks): the pre-pass and the
-    channel construction -- some forty short launches -- are captured once in a CUDA graph and replayed
-    with a single launch; the two cost-volume launches and structure -> flow follow on the same stream.
-    Buffers are allocated once.  Falls back to eager launches if an epipole needs the host (BFGS) or the
+    channel construction -- some fifteen short launches -- are captured once in a CUDA graph and replayed
+    with a single launch on a HIGH-PRIORITY stream; the cost-volume launch (both neighbour frames) and
+    structure -> flow follow on the caller's stream.  With several triplets in flight the short pre-pass
+    kernels of the next triplet are then scheduled ahead of the pending blocks of the current cost-volume
+    kernel instead of queueing behind them.  Buffers are allocated once.  Falls back to eager launches if the
     capture fails."""
 
     def __init__(self, band, homographies, epipoles, rigid_mask, rho="lorentzian", sigma=1.0, interp="cubic",
-                 range_mask="as_written", variant="staged", n_labels=N_RANGES, use_graph=True):
+                 range_mask="as_written", variant="staged", n_labels=N_RANGES, use_graph=True, pair=True, priority=True):
         self.band, self.H = band, homographies
+        self.pair = pair
         self.kw = dict(rho=rho, rho_param=sigma, interp=interp, variant=variant)
         self.n_labels = n_labels
         self.rigid_mask = rigid_mask
@@ -230,20 +233,20 @@ class ResidentStep:
                      torch.empty((L, rows, w), dtype=torch.float32, device=band.device))
         self.graph = None
         self.launches_in_graph = 0
-        self._side = torch.cuda.Stream()
+        self._side = torch.cuda.Stream(priority=-1 if priority else 0)
+        self._pre = torch.cuda.Stream(priority=-1 if priority else 0)
         self._front()                                        # warm up (and allocate) outside any capture
         torch.cuda.synchronize()
         if use_graph:
             try:
-                side = torch.cuda.Stream()
-                side.wait_stream(torch.cuda.current_stream())
-                with torch.cuda.stream(side):
+                self._pre.wait_stream(torch.cuda.current_stream())
+                with torch.cuda.stream(self._pre):
                     self._front()
-                torch.cuda.current_stream().wait_stream(side)
+                torch.cuda.current_stream().wait_stream(self._pre)
                 torch.cuda.synchronize()
                 g = torch.cuda.CUDAGraph()
                 n0 = device.launch_count()
-                with torch.cuda.graph(g):
+                with torch.cuda.graph(g, stream=self._pre):
                     self._front()
                 self.launches_in_graph = device.launch_count() - n0
                 self.graph = g
@@ -267,12 +270,17 @@ class ResidentStep:
     def run(self, events=None):
         """One step.  Returns (min costs, argmin labels, u, v) as device tensors; the volumes are in
         ``self.cost`` and mu / B / labels in ``self.buf.state``."""
-        if self.graph is not None:
-            self.graph.replay()
-        else:
-            self._front()
+        cur = torch.cuda.current_stream()
+        self._pre.wait_stream(cur)           # after the previous step's consumers of the state / channel buffers
+        with torch.cuda.stream(self._pre):
+            if self.graph is not None:
+                self.graph.replay()
+            else:
+                self._front()
+        cur.wait_stream(self._pre)
         res = pp.cost_volumes(self.band, self.ref64, self.tex, None, self.H, self.q, None, None, self.nonrigid,
-                              out=self.cost, events=events, state=self.buf.state, n_labels=self.n_labels, **self.kw)
+                              out=self.cost, events=events, state=self.buf.state, n_labels=self.n_labels, pair=self.pair,
+                              **self.kw)
         u, v = device.structure_to_flow(self.buf.S[1], self.q[1], 0.0, self.H[1], 0.0, nonrigid=self.nonrigid,
                                         init_u=self.band.flow[1][0], init_v=self.band.flow[1][1], state=self.buf.state,
                                         frame=1)

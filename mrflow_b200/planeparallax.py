@@ -272,20 +272,35 @@ def channels(band):
 def cost_volumes(band, ref64, tex, labels_dev, homographies, q_ar, mu_ar, B_ar, nonrigid, occluded=(None, None),
                  rho="lorentzian", rho_param=1.0, interp="cubic", layout="LHW_F32", variant="staged",
                  out=(None, None), want_cost=True, i32_scale=1000.0, halo_miss=None, frames=(0, 1), events=None,
-                 out_ptr=(None, None), plane_stride=0, state=None, n_labels=N_LABELS):
+                 out_ptr=(None, None), plane_stride=0, state=None, n_labels=N_LABELS, pair=True):
     """The per-label data cost of both neighbour frames (see device.cost_volume).  The backward
     frame is evaluated at ``label * mu0/mu1`` with the index-0 parameters
-    (optimize_structure_single_scale.py:435-442)."""
+    (optimize_structure_single_scale.py:435-442).  Both frames go out as ONE launch (``device.cost_volume_pair``)
+    unless ``pair=False`` or a single frame is asked for; ``events`` then receives one (start, end) pair that
+    spans both frames."""
     res = [None, None]
     if state is not None:                      # whole-frame scalars stay on the device
         mu_ar, B_ar = (0.0, 1.0), (0.0, 0.0)
+    scales = ((mu_ar[0] / mu_ar[1]), 1.0)
+    if pair and tuple(frames) == (0, 1) and tex[0].shape == tex[1].shape:
+        if events is not None:
+            ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+            ev[0].record()
+        res = device.cost_volume_pair(ref64, tex, labels_dev, homographies, q_ar, mu_ar, B_ar, label_scale=scales,
+                                      nonrigid=nonrigid, occluded=occluded, rho=rho, rho_param=rho_param, cw=CHANNEL_WEIGHTS,
+                                      interp=interp, layout=layout, i32_scale=i32_scale, variant=variant, y0=band.y0,
+                                      frame_h=band.frame_h, nb_y0=band.nb_y0, out=out, want_cost=want_cost, halo_miss=halo_miss,
+                                      out_ptr=out_ptr, plane_stride=plane_stride, state=state, n_labels=n_labels)
+        if events is not None:
+            ev[1].record()
+            events.append(ev)
+        return res
     for f in frames:
-        scale = (mu_ar[0] / mu_ar[1]) if f == 0 else 1.0
         if events is not None:
             ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
             ev[0].record()
         res[f] = device.cost_volume(ref64, tex[f], labels_dev, homographies[f], q_ar[f], mu_ar[f], B_ar[f],
-                                    label_scale=scale, nonrigid=nonrigid, occluded=occluded[f], rho=rho,
+                                    label_scale=scales[f], nonrigid=nonrigid, occluded=occluded[f], rho=rho,
                                     rho_param=rho_param, cw=CHANNEL_WEIGHTS, interp=interp, layout=layout,
                                     i32_scale=i32_scale, variant=variant, y0=band.y0, frame_h=band.frame_h,
                                     nb_y0=band.nb_y0, out=out[f], want_cost=want_cost, halo_miss=halo_miss,

@@ -786,7 +786,7 @@ def bench_bands(hw, steps, warm, interp="cubic", variant="staged", ClockSampler=
                                "for mu); compute_only_nccl_collectives = the same step with 7 NCCL collectives instead; %s" % (
                                    world, "the step replayed as one CUDA graph" if graphs else "eager launches"),
                 "peer_sync_epochs": ps.status()[0],
-                "halo_rows": halo_rows, "n_miss": int(n_miss), "kernel_ms_per_launch": kms,
+                "halo_rows": halo_rows, "n_miss": int(n_miss), "kernel_ms_per_launch": kms, "launches_per_step": 1,
                 "band_rows": rows, "d2h_bytes_per_rank": int(2 * L * rows * w * 4)})
     if verify:
         step("gather")

@@ -146,6 +146,30 @@ int mrf_rigidity_structure(const double* S0, const double* S1, const double* p_d
                            double mu0, double mu1, double sigma_structure, double weight_cnn,
                            double* unaries_f64, int32_t* unaries_i32, mrf_stream_t stream);
 
+/* ---- a4 without a host round trip: the same pieces with the whole-frame scalars (mu of both frames, B_b,
+ * B_fwd) read from the device state (MRF_STATE_*) instead of passed from the host, plus the two one-thread
+ * steps that turn the device-resident medians into B_fwd / B_b with the reference's fall-backs
+ * (pipeline/compute_structure.py:183-223).  mrflow_b200.planeparallax.structure_pass strings them together:
+ * the stage then synchronises with the host once, when its results are downloaded.
+ *   mrf_structure_candidates_dev: want = 1 (:187, B = 1) or 2 (:209-219, B_fwd = dev_state[MRF_STATE_B+1]);
+ *   mrf_abs_deviation_dev: |x - *c_dev| over the first *n_dev elements (:190, the MAD);
+ *   mrf_scales_finalize: mode 1 -> dev_state[MRF_STATE_B+1] = 1.426 * *median_dev, or 1.0 if *n_valid_dev < 100
+ *       or scale_structure != 1; mode 2 -> dev_state[MRF_STATE_B] = *median_dev, or -B_fwd if *n_valid_dev < 100;
+ *   mrf_parallax_to_structure_dev / mrf_rigidity_structure_dev: :25-33 / :374-394 with B, mu from the state. */
+int mrf_structure_candidates_dev(const double* par0, const double* par1, const uint8_t* p_thr, int rows, int w, int y0,
+                                 const double* q0_host, const double* q1_host, const double* dev_state, int want,
+                                 uint8_t* pv, double* cand, int* count, mrf_stream_t stream);
+int mrf_abs_deviation_dev(const double* x, const int* n_dev, size_t capacity, const double* c_dev, double* out,
+                          mrf_stream_t stream);
+int mrf_scales_finalize(double* dev_state, const int* n_valid_dev, const double* median_dev, int mode,
+                        int scale_structure, mrf_stream_t stream);
+int mrf_parallax_to_structure_dev(const double* parallax, int rows, int w, int y0, const double* q_host,
+                                  const double* dev_state, int frame, double* structure, mrf_stream_t stream);
+int mrf_rigidity_structure_dev(const double* S0, const double* S1, const double* p_dir, const double* p_cnn,
+                               const uint8_t* occ0, const uint8_t* occ1, int rows, int w, const double* dev_state,
+                               double sigma_structure, double weight_cnn, double* unaries_f64, int32_t* unaries_i32,
+                               mrf_stream_t stream);
+
 /* ---- exact order statistics for the medians of compute_structure.py:190,221 and the
  * auto-sigma of utils/robust_functions.py:23-29.  keys: n fp64 values (not modified);
  * out3[0] = k-th smallest (0-based), out3[1] = (k+1)-th smallest (so the caller forms numpy's
@@ -266,6 +290,20 @@ int mrf_cost_volume_pair(const mrf_costvol_params* p0_host, const mrf_costvol_pa
                          const uint8_t* nonrigid, const uint8_t* occluded0, const uint8_t* occluded1,
                          void* cost0, void* cost1, float* min_cost0, float* min_cost1, int32_t* argmin0,
                          int32_t* argmin1, int* halo_miss, const double* dev_state, mrf_stream_t stream);
+
+/* ---- auto-sigma mode of the cost volume (utils/robust_functions.py:55-58, the reference's default
+ * generate_lorentzian()): sigma = max(1e-6, 1.4826 * median |Iz|) over the WHOLE residual plane of a label, so
+ * each label plane is built in three steps -- mrf_cost_residual_plane (fp64 residual Iz of
+ * optimize_structure_single_scale.py:210-286 and |Iz|; `cost` semantics of mrf_cost_volume apply to the other
+ * arguments), mrf_select_median_dev over |Iz|, mrf_cost_auto_rho_plane (sigma * log(1 + 0.5 Iz^2 / sigma^2) as
+ * fp32, running min / first argmin over the labels, label = 0, 1, ... in order).  Plain kernels: the reference
+ * arithmetic written naively. */
+int mrf_cost_residual_plane(const mrf_costvol_params* p_host, const double* ref_ch, const float* nb_texels,
+                            const double* labels, const uint8_t* nonrigid, const uint8_t* occluded, int label,
+                            double* residual, double* abs_residual, int* halo_miss, const double* dev_state,
+                            mrf_stream_t stream);
+int mrf_cost_auto_rho_plane(const double* residual, size_t n, const double* median_abs_dev, int label,
+                            float* cost_plane, float* min_cost, int32_t* argmin, mrf_stream_t stream);
 
 /* ---- the pre-pass of build_cost_volume with no host round trip (pipeline/build_cost_volume.py:78-192
  * with the live conventions of compute_structure.py): residual flow -> parallax (both frames), mu,

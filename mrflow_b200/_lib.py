@@ -68,6 +68,11 @@ SIGNATURES = {
     "mrf_rigidity_direction": (_I, [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _DP, _DP, _D, _D, _P, _P, _P, _P]),
     "mrf_structure_candidates": (_I, [_P, _P, _P, _I, _I, _I, _DP, _DP, _D, _D, _D, _I, _P, _P, _P, _P]),
     "mrf_rigidity_structure": (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _D, _D, _D, _D, _P, _P, _P]),
+    "mrf_structure_candidates_dev": (_I, [_P, _P, _P, _I, _I, _I, _DP, _DP, _P, _I, _P, _P, _P, _P]),
+    "mrf_abs_deviation_dev": (_I, [_P, _P, _Z, _P, _P, _P]),
+    "mrf_scales_finalize": (_I, [_P, _P, _P, _I, _I, _P]),
+    "mrf_parallax_to_structure_dev": (_I, [_P, _I, _I, _I, _DP, _P, _I, _P, _P]),
+    "mrf_rigidity_structure_dev": (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _P, _D, _D, _P, _P, _P]),
     "mrf_select_scratch_bytes": (_Z, [_Z]),
     "mrf_select_kth_f64": (_I, [_P, _Z, _Z, _P, _P, _P]),
     "mrf_select_begin": (_I, [_Z, _P, _P]),
@@ -92,6 +97,8 @@ SIGNATURES = {
     "mrf_cost_volume": (_I, [C.POINTER(CostVolParams), _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "mrf_cost_volume_pair": (_I, [C.POINTER(CostVolParams), C.POINTER(CostVolParams), _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P,
                                   _P, _P, _P, _P, _P]),
+    "mrf_cost_residual_plane": (_I, [C.POINTER(CostVolParams), _P, _P, _P, _P, _P, _I, _P, _P, _P, _P, _P]),
+    "mrf_cost_auto_rho_plane": (_I, [_P, _Z, _P, _I, _P, _P, _P, _P]),
     "mrf_front_scratch_bytes": (_Z, []),
     "mrf_cost_volume_front": (_I, [C.POINTER(FrontParams), _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "mrf_front_mu_whole": (_I, [C.POINTER(FrontParams), _P, _P, _P]),

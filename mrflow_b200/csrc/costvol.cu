@@ -715,6 +715,80 @@ k_cost_volume(const __grid_constant__ CVArgs a0, const __grid_constant__ CVArgs 
   if (a.argmin) a.argmin[pix] = best_l;
 }
 
+// ---------------------------------------------------------------------------------------------
+// Auto-sigma mode of the cost volume (utils/robust_functions.py:55-58): the Lorentzian's sigma is
+// max(1e-6, 1.4826 * median |Iz|) over the WHOLE residual plane of a label, so a plane needs its fp64
+// residual first, then an exact median, then rho.  Two plain kernels per label (the reference arithmetic
+// written naively: IEEE divisions, library log); a second mode, not the tuned path.
+template <int INTERP>
+__global__ void __launch_bounds__(256)
+k_residual_plane(const __grid_constant__ CVArgs a, int label, double* __restrict__ Iz_out, double* __restrict__ abs_out) {
+  const long long n = (long long)a.rows * a.w;
+  double g_mu = a.mu, g_B = a.B, g_scale = a.label_scale;
+  const double* g_labels = a.labels;
+  if (a.state) {
+    g_mu = a.state[MRF_STATE_MU + a.frame];
+    g_B = a.state[MRF_STATE_B + a.frame];
+    g_scale = (a.frame == 0) ? a.state[MRF_STATE_MU] / a.state[MRF_STATE_MU + 1] : 1.0;
+    g_labels = a.state + MRF_STATE_LABELS;
+  }
+  const double al = g_labels[label] * g_scale;
+  const double ab = al * g_B;
+  const double den_l = ab / g_mu - 1.0;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const int yl = (int)(i / a.w);
+    const int x = (int)(i - (long long)yl * a.w);
+    const double xd = (double)x, yd = (double)(yl + a.y0);
+    double Iz = 0.0;
+    const bool dead = (a.nonrigid && a.nonrigid[i]) || (a.occluded && a.occluded[i]);
+    if (!dead) {
+      const double vx = a.q.x - xd, vy = a.q.y - yd;                         // :210-218
+      const double dist = sqrt(vx * vx + vy * vy);
+      const double nrm = fmax(0.5, dist);
+      const double r = (ab * (dist / g_mu)) / den_l;                         // :221
+      const double xn = xd + r * (vx / nrm), yn = yd + r * (vy / nrm);
+      double X, Y; bool inside;
+      through_H(a.H, xn, yn, a.frame_h, a.w, X, Y, inside);
+      if (inside) {
+        const float xf = (float)X, yf = (float)Y;
+        int iy, fy; cv_quantise(yf, iy, fy);
+        const int lo = (INTERP == MRF_INTERP_CUBIC) ? -1 : 0, hi = (INTERP == MRF_INTERP_CUBIC) ? 2 : 1;
+        const int ya = max(0, min(a.frame_h - 1, iy + lo)), yb = max(0, min(a.frame_h - 1, iy + hi));
+        F3 J;
+        if (ya < a.nb_y0 || yb > a.nb_y0 + a.nb_rows - 1) {
+          if (a.halo_miss) atomicAdd(a.halo_miss, 1);
+          J.x = J.y = J.z = 0.f;
+        } else {
+          FetchBand f{a.nb, a.w, a.nb_y0};
+          J = sample<INTERP>(f, a.frame_h, a.w, xf, yf);
+        }
+        const double e0 = ((double)J.x - a.ref_ch[3 * i]) * a.cw0;           // :274
+        const double e1 = ((double)J.y - a.ref_ch[3 * i + 1]) * a.cw1;
+        const double e2 = ((double)J.z - a.ref_ch[3 * i + 2]) * a.cw2;
+        Iz = ((e0 + e1) + e2) / 3.0;
+      }
+    }
+    Iz_out[i] = Iz;
+    abs_out[i] = fabs(Iz);
+  }
+}
+
+// cost = rho(Iz^2) with sigma = max(1e-6, 1.4826 * median) read from the device; fp32 plane, running min / argmin
+__global__ void __launch_bounds__(256)
+k_auto_rho_plane(const double* __restrict__ Iz, long long n, const double* __restrict__ median_abs, int label,
+                 float* __restrict__ cost_plane, float* __restrict__ min_cost, int32_t* __restrict__ argmin) {
+  const double sg = fmax(1e-6, 1.4826 * median_abs[0]);                      // robust_functions.py:29,55
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const double x = Iz[i] * Iz[i];
+    const float cf = (float)(sg * log(1.0 + (0.5 * x) / (sg * sg)));        // :58
+    if (cost_plane) cost_plane[i] = cf;
+    if (min_cost && (label == 0 || cf < min_cost[i])) {                      // np.argmin: first minimum
+      min_cost[i] = cf;
+      if (argmin) argmin[i] = label;
+    }
+  }
+}
+
 }  // namespace mrf
 
 using namespace mrf;
@@ -818,4 +892,32 @@ extern "C" int mrf_cost_volume_pair(const mrf_costvol_params* p0, const mrf_cost
   if (!rc) rc = cv_fill(p1, ref_ch, labels, nonrigid, h1, halo_miss, dev_state, &b);
   if (rc) return rc;
   return cv_launch(p0, a, b, 2, stream);
+}
+
+// One label plane of the auto-sigma cost volume: residual (fp64) + |residual| into scratch planes.
+extern "C" int mrf_cost_residual_plane(const mrf_costvol_params* p, const double* ref_ch, const float* nb_texels,
+                                       const double* labels, const uint8_t* nonrigid, const uint8_t* occluded, int label,
+                                       double* residual, double* abs_residual, int* halo_miss, const double* dev_state,
+                                       mrf_stream_t stream) {
+  MRF_CHECK_ARG(residual && abs_residual && p && label >= 0 && label < p->n_labels);
+  CVArgs a;
+  const CVHost h{nb_texels, occluded, residual, nullptr, nullptr};
+  const int rc = cv_fill(p, ref_ch, labels, nonrigid, h, halo_miss, dev_state, &a);
+  if (rc) return rc;
+  const long long n = (long long)p->rows * p->w;
+  const unsigned blocks = (unsigned)((n + 255) / 256 < (long long)kSMs * 8 ? (n + 255) / 256 : (long long)kSMs * 8);
+  if (p->interp == MRF_INTERP_CUBIC) k_residual_plane<MRF_INTERP_CUBIC><<<blocks, 256, 0, S(stream)>>>(a, label, residual, abs_residual);
+  else k_residual_plane<MRF_INTERP_LINEAR><<<blocks, 256, 0, S(stream)>>>(a, label, residual, abs_residual);
+  return check_launch("mrf_cost_residual_plane");
+}
+
+// Lorentzian with sigma = max(1e-6, 1.4826 * *median_abs_dev) applied to a residual plane; updates the running
+// min / argmin over labels (call with label = 0, 1, 2, ... in order)
+extern "C" int mrf_cost_auto_rho_plane(const double* residual, size_t n, const double* median_abs_dev, int label,
+                                       float* cost_plane, float* min_cost, int32_t* argmin, mrf_stream_t stream) {
+  MRF_CHECK_ARG(residual && median_abs_dev && n > 0 && label >= 0 && (cost_plane || min_cost));
+  MRF_CHECK_ARG(!argmin || min_cost);
+  const unsigned blocks = (unsigned)((n + 255) / 256 < (size_t)kSMs * 8 ? (n + 255) / 256 : (size_t)kSMs * 8);
+  k_auto_rho_plane<<<blocks, 256, 0, S(stream)>>>(residual, (long long)n, median_abs_dev, label, cost_plane, min_cost, argmin);
+  return check_launch("mrf_cost_auto_rho_plane");
 }

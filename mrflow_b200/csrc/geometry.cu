@@ -296,7 +296,7 @@ k_structure_candidates(const double* __restrict__ par0, const double* __restrict
                        const uint8_t* __restrict__ p_thr, int rows, int w, int y0, Pt2 q0, Pt2 q1,
                        double mu0, double mu1, double B_fwd, int want, uint8_t* __restrict__ pv,
                        double* __restrict__ cand, int* __restrict__ count, const double* __restrict__ st) {
-  if (st) { mu0 = st[MRF_STATE_MU]; mu1 = st[MRF_STATE_MU + 1]; }
+  if (st) { mu0 = st[MRF_STATE_MU]; mu1 = st[MRF_STATE_MU + 1]; if (B_fwd < 0.0) B_fwd = st[MRF_STATE_B + 1]; }
   const long long n = (long long)rows * w;
   for (long long i0 = blockIdx.x * (long long)blockDim.x; i0 < n; i0 += (long long)gridDim.x * blockDim.x) {
     const long long i = i0 + threadIdx.x;
@@ -345,7 +345,8 @@ k_rigidity_structure(const double* __restrict__ S0, const double* __restrict__ S
                      const double* __restrict__ p_dir, const double* __restrict__ p_cnn,
                      const uint8_t* __restrict__ occ0, const uint8_t* __restrict__ occ1, long long n,
                      double mu0, double mu1, double ss, double wc, double* __restrict__ un64,
-                     int32_t* __restrict__ un32) {
+                     int32_t* __restrict__ un32, const double* __restrict__ st) {
+  if (st) { mu0 = st[MRF_STATE_MU]; mu1 = st[MRF_STATE_MU + 1]; }
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n;
        i += (long long)gridDim.x * blockDim.x) {
     const double ad = S0[i] * mu1 / mu0 - S1[i];
@@ -364,9 +365,23 @@ k_rigidity_structure(const double* __restrict__ S0, const double* __restrict__ S
 }
 
 __global__ void __launch_bounds__(256)
-k_abs_dev(const double* __restrict__ x, size_t n, double c, double* __restrict__ out) {
+k_abs_dev(const double* __restrict__ x, size_t n, double c, double* __restrict__ out, const int* __restrict__ n_dev,
+          const double* __restrict__ c_dev) {
+  if (n_dev) n = (size_t)max(*n_dev, 0);
+  if (c_dev) c = *c_dev;
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
     out[i] = fabs(x[i] - c);
+}
+
+// B_fwd and B_b of pipeline/compute_structure.py:183-223 from device-resident pieces, so that the stage needs
+// no host round trip: mode 1 -> st[B+1] = B_fwd = 1.426 * MAD (:190), or 1.0 with fewer than 100 valid pixels
+// (:183-184) or scale_structure outside {1} (:198); mode 2 -> st[B] = B_b = the median ratio (:221), or -B_fwd
+// with fewer than 100 valid pixels (:206)
+__global__ void k_scales_finalize(double* __restrict__ st, const int* __restrict__ n_valid, const double* __restrict__ med,
+                                  int mode, int scale_structure) {
+  const bool few = *n_valid < 100;
+  if (mode == 1) st[MRF_STATE_B + 1] = (few || scale_structure != 1) ? 1.0 : 1.426 * med[0];
+  else st[MRF_STATE_B] = few ? -st[MRF_STATE_B + 1] : med[0];
 }
 
 __global__ void k_set_f64(double* p, double v) { p[0] = v; }
@@ -982,14 +997,58 @@ int mrf_rigidity_structure(const double* S0, const double* S1, const double* p_d
   const long long n = (long long)rows * w;
   k_rigidity_structure<<<grid_for(n), 256, 0, S(stream)>>>(S0, S1, p_dir, p_cnn, occ0, occ1, n, mu0, mu1,
                                                           sigma_structure, weight_cnn, unaries_f64,
-                                                          unaries_i32);
+                                                          unaries_i32, nullptr);
   return check_launch("mrf_rigidity_structure");
+}
+
+// ---- the same stage pieces with the whole-frame scalars (mu, B) read from the device state instead of the host:
+// pipeline/compute_structure.py:172-246,374-394 without a host round trip (mrflow_b200.planeparallax.structure_pass)
+int mrf_structure_candidates_dev(const double* par0, const double* par1, const uint8_t* p_thr, int rows, int w, int y0,
+                                 const double* q0_host, const double* q1_host, const double* dev_state, int want,
+                                 uint8_t* pv, double* cand, int* count, mrf_stream_t stream) {
+  MRF_CHECK_ARG(par0 && par1 && p_thr && rows > 0 && w > 0 && q0_host && q1_host && dev_state && cand && count);
+  MRF_CHECK_ARG(want == 1 || want == 2);
+  cudaError_t e = cudaMemsetAsync(count, 0, sizeof(int), S(stream));
+  if (e != cudaSuccess) return fail((int)e, "mrf_structure_candidates_dev: %s", cudaGetErrorString(e));
+  // B_fwd < 0 asks the kernel to read it (like mu) from the state
+  k_structure_candidates<<<grid_for((long long)rows * w), 256, 0, S(stream)>>>(
+      par0, par1, p_thr, rows, w, y0, pt2(q0_host), pt2(q1_host), 0.0, 0.0, -1.0, want, pv, cand, count, dev_state);
+  return check_launch("mrf_structure_candidates_dev");
+}
+int mrf_abs_deviation_dev(const double* x, const int* n_dev, size_t capacity, const double* c_dev, double* out,
+                          mrf_stream_t stream) {
+  MRF_CHECK_ARG(x && n_dev && c_dev && out && capacity > 0);
+  k_abs_dev<<<grid_for((long long)capacity), 256, 0, S(stream)>>>(x, capacity, 0.0, out, n_dev, c_dev);
+  return check_launch("mrf_abs_deviation_dev");
+}
+int mrf_scales_finalize(double* dev_state, const int* n_valid_dev, const double* median_dev, int mode, int scale_structure,
+                        mrf_stream_t stream) {
+  MRF_CHECK_ARG(dev_state && n_valid_dev && median_dev && (mode == 1 || mode == 2));
+  k_scales_finalize<<<1, 1, 0, S(stream)>>>(dev_state, n_valid_dev, median_dev, mode, scale_structure);
+  return check_launch("mrf_scales_finalize");
+}
+int mrf_parallax_to_structure_dev(const double* parallax, int rows, int w, int y0, const double* q_host,
+                                  const double* dev_state, int frame, double* structure, mrf_stream_t stream) {
+  MRF_CHECK_ARG(parallax && structure && rows > 0 && w > 0 && q_host && dev_state && (frame == 0 || frame == 1));
+  k_parallax_to_structure<<<grid_for((long long)rows * w), 256, 0, S(stream)>>>(parallax, rows, w, y0, pt2(q_host), 0.0, 0.0,
+                                                                               structure, dev_state, frame);
+  return check_launch("mrf_parallax_to_structure_dev");
+}
+int mrf_rigidity_structure_dev(const double* S0, const double* S1, const double* p_dir, const double* p_cnn,
+                               const uint8_t* occ0, const uint8_t* occ1, int rows, int w, const double* dev_state,
+                               double sigma_structure, double weight_cnn, double* unaries_f64, int32_t* unaries_i32,
+                               mrf_stream_t stream) {
+  MRF_CHECK_ARG(S0 && S1 && p_dir && p_cnn && rows > 0 && w > 0 && dev_state && (unaries_f64 || unaries_i32));
+  const long long n = (long long)rows * w;
+  k_rigidity_structure<<<grid_for(n), 256, 0, S(stream)>>>(S0, S1, p_dir, p_cnn, occ0, occ1, n, 0.0, 0.0, sigma_structure,
+                                                          weight_cnn, unaries_f64, unaries_i32, dev_state);
+  return check_launch("mrf_rigidity_structure_dev");
 }
 
 int mrf_abs_deviation_f64(const double* x, size_t n, double c, double* out, mrf_stream_t stream) {
   MRF_CHECK_ARG(x && out);
   if (n == 0) return 0;
-  k_abs_dev<<<grid_for((long long)n), 256, 0, S(stream)>>>(x, n, c, out);
+  k_abs_dev<<<grid_for((long long)n), 256, 0, S(stream)>>>(x, n, c, out, nullptr, nullptr);
   return check_launch("mrf_abs_deviation_f64");
 }
 

@@ -201,6 +201,73 @@ def erode3x3(mask_u8):
     return out
 
 
+# ------------------------------------------------------------------------------------ a4 with device-resident scalars
+class StructureBuffers:
+    """Reusable HBM buffers of the device-resident compute_structure stage for one frame size."""
+
+    def __init__(self, rows, w, dev="cuda"):
+        L = _lib.lib()
+        n = rows * w
+        self.state = torch.zeros(_lib.STATE_WORDS, dtype=F64, device=dev)
+        self.cand = torch.empty(n, dtype=F64, device=dev)
+        self.dev_abs = torch.empty(n, dtype=F64, device=dev)
+        self.count1 = torch.zeros(1, dtype=I32, device=dev)
+        self.count2 = torch.zeros(1, dtype=I32, device=dev)
+        self.med = torch.zeros(3, dtype=F64, device=dev)
+        self.scratch = torch.empty(L.mrf_front_scratch_bytes(), dtype=U8, device=dev)
+        self.sel = torch.empty(L.mrf_select_scratch_bytes(n), dtype=U8, device=dev)
+
+
+def structure_scales_dev(par0, par1, p_thr, q0, q1, frame_h, buf, scale_structure=1):
+    """pipeline/compute_structure.py:84,172-223 with nothing coming back to the host: mu of both frames, the
+    valid mask, B_fwd = 1.426 * MAD of the forward structure at B = 1 (or 1.0), B_b = the median ratio (or
+    -B_fwd) -- all written to ``buf.state``.  Returns the valid mask ``pv`` (uint8).  ``scale_structure`` 1 (MAD)
+    or anything but 2 (-> 1.0); the std variant (2) is not offered here."""
+    L = _lib.lib()
+    rows, w = par0.shape
+    p = _lib.FrontParams()
+    p.rows, p.w, p.y0, p.frame_h = rows, w, 0, int(frame_h)
+    p.q0 = _pt(q0); p.q1 = _pt(q1)
+    st = _stream()
+    check(L.mrf_front_mu_whole(C.byref(p), _p(buf.state), _p(buf.scratch), st), "mrf_front_mu_whole")            # :84
+    pv = torch.empty((rows, w), dtype=U8, device=par0.device)
+    cap = rows * w
+    # B_fwd (:183-198): MAD of parallax2normedstructure(par1, q1, 1.0, mu1) over the valid pixels
+    check(L.mrf_structure_candidates_dev(_p(par0), _p(par1), _p(p_thr), rows, w, 0, _pt(q0), _pt(q1), _p(buf.state), 1, _p(pv),
+                                         _p(buf.cand), _p(buf.count1), st), "mrf_structure_candidates_dev")
+    check(L.mrf_select_median_dev(_p(buf.cand), _p(buf.count1), cap, _p(buf.med[0:1]), _p(buf.sel), st), "mrf_select_median_dev")
+    check(L.mrf_abs_deviation_dev(_p(buf.cand), _p(buf.count1), cap, _p(buf.med[0:1]), _p(buf.dev_abs), st), "mrf_abs_deviation_dev")
+    check(L.mrf_select_median_dev(_p(buf.dev_abs), _p(buf.count1), cap, _p(buf.med[1:2]), _p(buf.sel), st), "mrf_select_median_dev")
+    check(L.mrf_scales_finalize(_p(buf.state), _p(buf.count1), _p(buf.med[1:2]), 1, int(scale_structure), st), "mrf_scales_finalize")
+    # B_b (:204-221): median of template / target with that B_fwd
+    check(L.mrf_structure_candidates_dev(_p(par0), _p(par1), _p(p_thr), rows, w, 0, _pt(q0), _pt(q1), _p(buf.state), 2, None,
+                                         _p(buf.cand), _p(buf.count2), st), "mrf_structure_candidates_dev")
+    check(L.mrf_select_median_dev(_p(buf.cand), _p(buf.count2), cap, _p(buf.med[2:3]), _p(buf.sel), st), "mrf_select_median_dev")
+    check(L.mrf_scales_finalize(_p(buf.state), _p(buf.count1), _p(buf.med[2:3]), 2, int(scale_structure), st), "mrf_scales_finalize")
+    return pv
+
+
+def parallax_to_structure_dev(parallax, q, state, frame):
+    """pipeline/compute_structure.py:25-33 with B and mu of ``frame`` read from the device state."""
+    _chk(parallax, F64, "parallax"); _chk(state, F64, "state")
+    rows, w = parallax.shape
+    out = torch.empty_like(parallax)
+    check(_lib.lib().mrf_parallax_to_structure_dev(_p(parallax), rows, w, 0, _pt(q), _p(state), int(frame), _p(out), _stream()),
+          "mrf_parallax_to_structure_dev")
+    return out
+
+
+def rigidity_structure_dev(S0, S1, p_dir, p_cnn, occ0, occ1, state, sigma_structure, weight_cnn, want_i32=False):
+    """pipeline/compute_structure.py:374-394 with mu of both frames read from the device state."""
+    rows, w = S0.shape
+    un = torch.empty((rows, w, 2), dtype=F64, device=S0.device)
+    ui = torch.empty((rows, w, 2), dtype=I32, device=S0.device) if want_i32 else None
+    check(_lib.lib().mrf_rigidity_structure_dev(_p(S0), _p(S1), _p(p_dir), _p(p_cnn), _p(occ0), _p(occ1), rows, w, _p(state),
+                                                float(sigma_structure), float(weight_cnn), _p(un), _p(ui), _stream()),
+          "mrf_rigidity_structure_dev")
+    return un, ui
+
+
 # ------------------------------------------------------------------------------------ statistics
 def select_kth(keys, k, n=None):
     """k-th smallest (0-based) of the first ``n`` fp64 keys, its successor and the NaN count, as a
@@ -345,6 +412,42 @@ def cost_volume(ref_ch, nb_texels, labels, H, q, mu, B, label_scale=1.0, nonrigi
     dst = C.c_void_p(int(out_ptr)) if out_ptr is not None else _p(cost)
     check(_lib.lib().mrf_cost_volume(C.byref(p), _p(ref_ch), _p(nb_texels), _p(labels), _p(nonrigid), _p(occluded),
                                      dst, _p(mn), _p(am), _p(halo_miss), _p(state), _stream()), "mrf_cost_volume")
+    return cost, mn, am
+
+
+def cost_volume_auto(ref_ch, nb_texels, labels, H, q, mu, B, label_scale=1.0, nonrigid=None, occluded=None,
+                     cw=(0.01, 1.0, 1.0), interp="cubic", want_cost=True, halo_miss=None, state=None, frame=1, n_labels=None):
+    """The cost volume of one neighbour frame with the reference's AUTO-SIGMA Lorentzian
+    (utils/robust_functions.py:55-58, what generate_lorentzian() without an argument gives): per label plane,
+    sigma = max(1e-6, 1.4826 * median |Iz|) over the whole plane and cost = sigma * log(1 + 0.5 Iz^2 / sigma^2).
+    Whole frames only (the median is over the plane).  Three launches per label (fp64 residual, exact median,
+    rho); nothing comes back to the host.  Returns (cost fp32 [L,h,w] or None, min_cost, argmin)."""
+    _chk(ref_ch, F64, "ref_ch"); _chk(nb_texels, F32, "nb_texels"); _chk(labels, F64, "labels")
+    _chk(nonrigid, U8, "nonrigid"); _chk(occluded, U8, "occluded"); _chk(state, F64, "state")
+    L = _lib.lib()
+    rows, w = ref_ch.shape[:2]
+    if nb_texels.shape[0] != rows:
+        raise ValueError("the auto-sigma mode needs whole frames (sigma is a median over the whole label plane)")
+    Ln = labels.numel() if labels is not None else int(n_labels)
+    dev = ref_ch.device
+    n = rows * w
+    p = _cv_params(rows, w, rows, H, q, mu, B, label_scale, Ln, "lorentzian_auto", 1.0, cw, interp, "LHW_F32", 1000.0, "gather", 0,
+                   rows, 0, 0, frame)
+    cost = torch.empty((Ln, rows, w), dtype=F32, device=dev) if want_cost else None
+    mn = torch.empty((rows, w), dtype=F32, device=dev)
+    am = torch.empty((rows, w), dtype=I32, device=dev)
+    Iz = torch.empty((rows, w), dtype=F64, device=dev)
+    aIz = torch.empty((rows, w), dtype=F64, device=dev)
+    med = torch.empty(1, dtype=F64, device=dev)
+    cnt = torch.full((1,), n, dtype=I32, device=dev)
+    scratch = torch.empty(L.mrf_select_scratch_bytes(n), dtype=U8, device=dev)
+    st = _stream()
+    for l in range(Ln):
+        check(L.mrf_cost_residual_plane(C.byref(p), _p(ref_ch), _p(nb_texels), _p(labels), _p(nonrigid), _p(occluded), l, _p(Iz),
+                                        _p(aIz), _p(halo_miss), _p(state), st), "mrf_cost_residual_plane")
+        check(L.mrf_select_median_dev(_p(aIz), _p(cnt), n, _p(med), _p(scratch), st), "mrf_select_median_dev")
+        check(L.mrf_cost_auto_rho_plane(_p(Iz), n, _p(med), l, _p(cost[l]) if cost is not None else None, _p(mn), _p(am), st),
+              "mrf_cost_auto_rho_plane")
     return cost, mn, am
 
 

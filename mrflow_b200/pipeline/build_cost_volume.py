@@ -29,7 +29,9 @@ def build_cost_volume(images, flow, rigidity, homographies, epipoles, params=Non
     cost volumes fp32 [51,h,w] (or int32 [h,w,51] = int(cost*1000) with ``layout='HWL_I32'``, the layout
     extern/eff_trws/image.cpp:80 reads), structures fp64 [h,w], ``B_array = [B_b, 1.0]`` (:131).
 
-    ``rho``/``sigma``: robust function of utils/robust_functions.py (fixed-parameter forms);
+    ``rho``/``sigma``: robust function of utils/robust_functions.py; ``rho='lorentzian', sigma=None`` (or
+    ``rho='lorentzian_auto'``) is the reference's auto-sigma form (:55-58: sigma = 1.4826 * median |Iz| of each
+    label plane) -- a second mode, three launches per label;
     ``interp``: 'cubic' is what the reference samples with (interpolation.py:76-80), 'linear' the
     bilinear variant; ``range_mask``: 'as_written' zeroes the pixels with rigidity > 0 before taking
     the label range (:159, sic), 'rigid_only' the others.  ``return_device=True`` keeps everything in HBM
@@ -38,7 +40,11 @@ def build_cost_volume(images, flow, rigidity, homographies, epipoles, params=Non
     require_cuda()
     stats = stats or pp.LocalStats()
     rigidity = np.asarray(rigidity)
-    if isinstance(stats, pp.LocalStats) and not return_device:
+    if rho == "lorentzian" and sigma is None:
+        rho = "lorentzian_auto"
+    if rho == "lorentzian_auto":
+        sigma = 1.0                                   # unused: sigma comes from each plane's median
+    if isinstance(stats, pp.LocalStats) and not return_device and rho != "lorentzian_auto":
         return _host_call(images, flow, rigidity, homographies, epipoles, rho, sigma, interp, range_mask, layout, variant)
     band = pp.Band.from_host(images, flow, rigidity, None)
     if isinstance(stats, pp.LocalStats):

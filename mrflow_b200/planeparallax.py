@@ -86,7 +86,8 @@ class Band:
 
     @classmethod
     def from_host(cls, images, flow, rigidity, occlusions=None, device_name="cuda", rows=None, halo=0):
-        """Upload a whole frame, or rows ``rows=(y0, y1)`` of it with ``halo`` extra neighbour rows.
+        """Upload a whole frame, or rows ``rows=(y0, y1)`` of it with ``halo`` extra neighbour rows
+        (``images=None``: a stage that does not sample the frames, e.g. compute_structure, skips their 32 MB).
         Images are uploaded with 2 more rows on each cut side so that the gradient + 3x3 blur of the
         channel construction is exact on every row that is kept."""
         h, w = np.asarray(rigidity).shape
@@ -98,7 +99,7 @@ class Band:
             a = np.ascontiguousarray(np.asarray(a)[lo:hi], dtype=dtype)
             return torch.from_numpy(a).to(device_name, non_blocking=True)
 
-        imgs = [up(images[i], np.float64, m0, m1) for i in range(3)]
+        imgs = [up(images[i], np.float64, m0, m1) for i in range(3)] if images is not None else None
         fl = [[up(flow[f][0], np.float32, y0, y1), up(flow[f][1], np.float32, y0, y1)] for f in range(2)]
         rg = up(rigidity, np.float64, y0, y1)
         oc = None
@@ -282,6 +283,20 @@ def cost_volumes(band, ref64, tex, labels_dev, homographies, q_ar, mu_ar, B_ar, 
     if state is not None:                      # whole-frame scalars stay on the device
         mu_ar, B_ar = (0.0, 1.0), (0.0, 0.0)
     scales = ((mu_ar[0] / mu_ar[1]), 1.0)
+    if rho == "lorentzian_auto":
+        # the reference's auto-sigma Lorentzian: sigma is a median over each whole label plane
+        # (utils/robust_functions.py:55-58) -- a second mode with three launches per label, whole frames only
+        if band.rows != band.frame_h or layout != "LHW_F32" or out_ptr[0] is not None or out_ptr[1] is not None:
+            raise NotImplementedError("the auto-sigma cost volume needs a whole frame on one GPU and the LHW_F32 layout")
+        for f in frames:
+            c, mn, am = device.cost_volume_auto(ref64, tex[f], labels_dev, homographies[f], q_ar[f], mu_ar[f], B_ar[f],
+                                                label_scale=scales[f], nonrigid=nonrigid, occluded=occluded[f], cw=CHANNEL_WEIGHTS,
+                                                interp=interp, want_cost=want_cost, halo_miss=halo_miss, state=state, frame=f,
+                                                n_labels=n_labels)
+            if out[f] is not None and c is not None:
+                out[f].copy_(c); c = out[f]
+            res[f] = (c, mn, am)
+        return res
     if pair and tuple(frames) == (0, 1) and tex[0].shape == tex[1].shape:
         if events is not None:
             ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))

@@ -24,8 +24,10 @@ def get_residual_flow(x, y, u, v, H):
     require_cuda()
     _grid_offsets(x, y)
     Hinv = np.linalg.inv(np.asarray(H, dtype=np.float64))
-    ur, vr, _, _ = device.flow_to_parallax(up(u, np.float32), up(v, np.float32), Hinv, (0.0, 0.0),
-                                           want_parallax=False, want_dists=False)
+    # (x + u) is formed in the flow's own precision promoted to fp64 (int64 + fp32/fp64 -> fp64, :9-10), rounded to
+    # fp32 ONCE (:11), sent through inv(H) and reduced by the fp32 grid (:15-16) -- the arithmetic of get_full_flow
+    # with inv(H), so fp64 flows are not rounded twice
+    ur, vr = device.full_flow(up(u, np.float64), up(v, np.float64), Hinv)
     return down(ur), down(vr)
 
 

@@ -332,5 +332,77 @@ def main():
         print(tag, "written:", len(out), "arrays")
 
 
+FULL_KEYS = ("S0", "S1", "mu", "B", "q", "rigidity", "merged", "u", "v")
+CROP = (slice(200, 232), slice(480, 544))          # 32 x 64
+
+
+def full_example_inputs(images_u8, occ_bits):
+    """The inputs of the full-size configs[0] chain, rebuilt identically by the generator and by the tests: the
+    reference's example frames (uint8 RGB from the fixture, /255 as load_data.py:52), synthetic flows /
+    homographies / epipoles of a seeded Sintel-shape triplet, the uniform 0.6 rigidity prior of --no_init
+    (load_data.py:153-155) and the stored occlusion maps."""
+    from mrflow_b200 import synth
+    t = synth.make_triplet("sintel", seed=1005, flow_noise=0.03)
+    h, w = t["shape"]
+    t["images"] = [images_u8[i].astype(np.float64) / 255.0 for i in range(3)]
+    t["rigidity"] = np.full((h, w), 0.6)
+    t["occlusions"] = [np.unpackbits(occ_bits[i])[:h * w].reshape(h, w).astype(bool) for i in range(2)]
+    return t
+
+
+def main_full():
+    """BASELINE.json configs[0] at FULL size: example/frame1-3.png (1024x436) with synthetic precomputed flows, uniform
+    rigidity, --override_optimization 1 -- the reference's own chain of mrflow.py:98-140 (compute_structure with its
+    C++ MRF solver -> optimize -> combine_flow).  Stored: the frames (uint8), the occlusion maps (bit-packed), and of
+    every output its sha256 and a 32x64 crop."""
+    sys.path.insert(0, ROOT)
+    import argparse
+    import contextlib
+    import io
+    import cv2
+    from mrflow_b200 import synth
+    ref = import_reference()
+    cs, s2f, inf = ref["cs"], ref["s2f"], ref["inf"]
+    from oracle import trws
+    assert trws.available(), "build oracle/_ref first (python -m oracle.build_ref)"
+    inf.eff_trws = trws._ext()
+    inf.HAVE_TRWS = True
+    from rigidity import occlusions as occmod
+    from pipeline import optimize_variational_refinement as ovr
+    images_u8 = np.stack([cv2.imread(REF + "/example/frame%d.png" % i)[:, :, ::-1] for i in (1, 2, 3)])   # BGR -> RGB, load_data.py:52
+    t0 = synth.make_triplet("sintel", seed=1005, flow_noise=0.03)
+    h, w = t0["shape"]
+    rs = np.random.RandomState(321)
+
+    def smooth(scale):
+        return (cv2.GaussianBlur(rs.standard_normal((h, w)).astype(np.float32), (0, 0), 6.0) * scale).astype(np.float32)
+    backflow = [[(-t0["flow"][f][0] + smooth(9.0)).astype(np.float32), (-t0["flow"][f][1] + smooth(9.0)).astype(np.float32)]
+                for f in range(2)]
+    ob, of, _ = occmod.computeOcclusionsFromConsistency(t0["flow"], backflow, threshold=3.0)
+    occ_bits = np.stack([np.packbits(np.asarray(o).astype(np.uint8).ravel()) for o in (ob, of)])
+    t = full_example_inputs(images_u8, occ_bits)
+    p = argparse.Namespace(debug_use_rigidity_gt=0, debug_save_frames=0, debug_compute_figure=0, rigidity_sigma_direction=1.0,
+                           rigidity_weight_cnn=0.0, rigidity_sigma_structure=1.0, rigidity_use_structure=1, scale_structure=1,
+                           nonlinear_structure_initialization=0, occlusion_reasoning=1, tempdir=".", override_optimization=1)
+    with contextlib.redirect_stdout(io.StringIO()):
+        full = cs.compute_structure(t["images"], t["flow"], t["rigidity"], t["occlusions"], [H.copy() for H in t["homographies"]],
+                                    t["epipoles"], p)
+        merged = ovr.optimize(t["images"], full[0], full[5], full[4], full[1], full[3], full[2], t["occlusions"], p)[0]
+        _, u, v = s2f.combine_flow(merged, t["flow"][1], full[5], full[4], full[2], full[1], full[3], t["images"], p)
+    vals = dict(S0=full[0][0], S1=full[0][1], mu=np.array(full[2]), B=np.array(full[3]), q=np.array(full[4]),
+                rigidity=np.asarray(full[5]), merged=merged, u=u, v=v)
+    out = {"images_u8": images_u8, "occ_bits": occ_bits, "weight_cnn": np.array(0.0)}
+    for k in FULL_KEYS:
+        a = np.ascontiguousarray(vals[k])
+        out["sha_" + k] = np.array(sha(a))
+        out["crop_" + k] = a[CROP].copy() if a.shape == (h, w) else a.copy()
+    out["occluded_fraction"] = np.array([float(np.mean(o)) for o in t["occlusions"]])
+    out["rigid_fraction"] = np.array(float(np.mean(full[5])))
+    np.savez_compressed(os.path.join(HERE, "ref_example_full.npz"), **out)
+    print("example_full written:", len(out), "arrays; rigid fraction %.3f, occluded %s" % (out["rigid_fraction"], out["occluded_fraction"]))
+
+
 if __name__ == "__main__":
-    main()
+    if "--full-only" not in sys.argv:
+        main()
+    main_full()

@@ -308,6 +308,28 @@ def test_cost_volume_vs_oracle(dev, trip, mode, variant):
         _check_argmin(am.cpu().numpy(), want[f])
 
 
+def test_cost_volume_auto_sigma(dev, trip):
+    """The reference's auto-sigma Lorentzian (utils/robust_functions.py:55-58) per label plane: sigma from the
+    exact median of |Iz| over the plane.  Against the oracle (same rho with sigma=0 -> auto)."""
+    from oracle import hotpath as hp
+    t = trip
+    ch, mu, rig, occ = _cv_setup(t)
+    B = [-0.37, 0.41]
+    labels = np.linspace(-3.0, 4.5, 9)
+    want, wmin, wam = hp.cost_volume(ch, rig, occ, t["homographies"], B, mu, t["epipoles"], labels, kind="lorentzian", sigma=0.0)
+    nr = cu((rig == 0).astype(np.uint8))
+    ref_ch = cu(ch[1])
+    for f, nbi in ((0, 0), (1, 2)):
+        tex = cu(np.concatenate([ch[nbi].astype(np.float32), np.zeros(ch[nbi].shape[:2] + (1,), np.float32)], axis=2))
+        cost, mn, am = dev.cost_volume_auto(ref_ch, tex, cu(labels), t["homographies"][f], t["epipoles"][f], mu[f], B[f],
+                                            label_scale=(mu[0] / mu[1] if f == 0 else 1.0), nonrigid=nr,
+                                            occluded=cu(occ[f].astype(np.uint8)), frame=f)
+        exact = _check_costs(cost.cpu().numpy(), want[f], "auto-sigma frame %d" % f)
+        assert exact > 0.99
+        assert eq(mn.cpu(), cost.min(dim=0).values.cpu()) and eq(am.cpu(), cost.cpu().numpy().argmin(axis=0))
+        _check_argmin(am.cpu().numpy(), want[f])
+
+
 def test_cost_volume_golden_planes(dev, golden):
     """Against planes produced by the reference's own sampler + rho (tests/golden/make_golden.py)."""
     from oracle import hotpath as hp

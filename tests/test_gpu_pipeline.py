@@ -452,3 +452,52 @@ def test_full_chain_sintel_size():
     # and the chain reproduces the input flow on rigid pixels (SURVEY.md section 4 identity)
     rigid = rig & (~occ[0]) & (~occ[1])
     assert np.median(np.abs(u - t["flow"][1][0])[rigid]) < 0.05
+
+
+def test_config1_full_size_against_reference():
+    """BASELINE.json configs[0] at full size through the drop-in modules: the reference's example frames
+    (1024x436), synthetic flows, uniform rigidity, override_optimization=1 -- compute_structure (reference MRF
+    solver as the unchanged consumer) -> optimize -> combine_flow against the REFERENCE's own outputs
+    (tests/golden/ref_example_full.npz: crops, and the hash of the rigidity map)."""
+    from mrflow_b200.pipeline import compute_structure as cs, optimize_variational_refinement as ovr, structure2flow as s2f
+    from oracle import trws
+    from test_oracle_golden import _full_example
+    if not trws.available():
+        pytest.skip("oracle/_ref not built")
+    mg, g, t = _full_example()
+    params = _params(override_optimization=1, rigidity_weight_cnn=float(g["weight_cnn"]))
+    S, Hs, mu, B, q, rig, oc = cs.compute_structure(t["images"], t["flow"], t["rigidity"], t["occlusions"],
+                                                    [H.copy() for H in t["homographies"]], t["epipoles"], params,
+                                                    infer_mrf=trws.infer_mrf)
+    merged = ovr.optimize(t["images"], S, rig, q, Hs, B, mu, oc, params)[0]
+    _, u, v = s2f.combine_flow(merged, t["flow"][1], rig, q, mu, Hs, B, t["images"], params)
+    np.testing.assert_allclose(mu, g["crop_mu"], rtol=1e-14)
+    np.testing.assert_allclose(B, g["crop_B"], rtol=1e-11)
+    assert np.array_equal(np.array(q), g["crop_q"])
+    assert mg.sha(np.ascontiguousarray(np.asarray(rig))) == str(g["sha_rigidity"])      # the MRF labelling is identical
+    c = mg.CROP
+    for name, got in (("S0", S[0]), ("S1", S[1]), ("merged", merged)):
+        want = g["crop_" + name]
+        fin = np.isfinite(want)
+        np.testing.assert_allclose(got[c][fin], want[fin], rtol=1e-10)
+    assert np.abs(u[c] - g["crop_u"]).max() <= 1e-4 and np.abs(v[c] - g["crop_v"]).max() <= 1e-4   # north_star: 1e-4 px
+    assert u.dtype == np.float32 and u.shape == (436, 1024)
+
+
+def test_build_cost_volume_auto_sigma(trip):
+    """build_cost_volume with the reference's auto-sigma Lorentzian (sigma=None; utils/robust_functions.py:55-58)
+    against the oracle's same mode, at the GPU's own scalars (see test_build_cost_volume)."""
+    from mrflow_b200.pipeline.build_cost_volume import build_cost_volume
+    from oracle import hotpath as hp
+    from test_gpu_kernels import _check_costs
+    t = trip
+    h, w = t["shape"]
+    got = build_cost_volume(t["images"], t["flow"], t["rigidity"], t["homographies"], t["epipoles"], _params(), rho="lorentzian",
+                            sigma=None, range_mask="rigid_only")
+    ch = [hp.prepare_channels(I) for I in t["images"]]
+    noocc = [np.zeros((h, w), bool)] * 2
+    want, _, _ = hp.cost_volume(ch, t["rigidity"], noocc, t["homographies"], got[3], got[2], got[4], got[5], kind="lorentzian",
+                                sigma=0.0, labels=[0, 13, 25, 38, 50])
+    for f in range(2):
+        assert got[0][f].shape == (51, h, w)
+        _check_costs(got[0][f][[0, 13, 25, 38, 50]], want[f], "auto-sigma frame %d" % f)

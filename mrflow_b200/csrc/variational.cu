@@ -786,11 +786,16 @@ int mrf_vec_scale(const double* y, size_t n, double s, double* out, mrf_stream_t
 }
 
 static int persistent_grid(int* blocks_out) {
-  static int cached = 0;
+  // the co-resident grid is a property of the CURRENT device: cached per device, not per process
+  static int cached_by_dev[64] = {0};
+  int dev = 0;
+  cudaError_t e0 = cudaGetDevice(&dev);
+  if (e0 != cudaSuccess) return fail((int)e0, "mrf_minres: %s", cudaGetErrorString(e0));
+  int scratch_slot = 0;
+  int& cached = (dev >= 0 && dev < 64) ? cached_by_dev[dev] : scratch_slot;
   if (!cached) {
-    int dev = 0, sms = 0, per_sm = 0;
-    cudaError_t e = cudaGetDevice(&dev);
-    if (e == cudaSuccess) e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    int sms = 0, per_sm = 0;
+    cudaError_t e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_minres_persistent, 256, 0);
     if (e != cudaSuccess) return fail((int)e, "mrf_minres: occupancy query: %s", cudaGetErrorString(e));
     if (per_sm < 1 || sms < 1) return fail(MRF_E_BADARG, "mrf_minres: kernel does not fit an SM");

@@ -32,7 +32,7 @@ KEEP = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum
 def main():
     rep, tag = sys.argv[1], sys.argv[2]
     workload = sys.argv[3] if len(sys.argv) > 3 else "sintel_1024x436_L51_F2_cubic"
-    units = float(sys.argv[4]) if len(sys.argv) > 4 else 446464 * 51 / 32.0
+    units = float(sys.argv[4]) if len(sys.argv) > 4 else 2 * 446464 * 51 / 32.0      # one launch = both neighbour frames
     out = os.path.join(ROOT, "profiles")
     os.makedirs(out, exist_ok=True)
     raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
@@ -55,6 +55,10 @@ def main():
     d[workload] = traffic
     d["_source"] = d.get("_source", {})
     d["_source"][workload] = "%s (ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum, mean of %d launches)" % (tag, len(rows) - 2)
+    d["_capture"] = "profiles/%s_costvol_metrics.csv (ncu --set full --clock-control none, round 2 final kernel: one launch = both neighbour frames)" % tag
+    ie = hdr.index("smsp__inst_executed.sum")
+    d["_inst_executed"] = d.get("_inst_executed", {})
+    d["_inst_executed"][workload] = sum(float(r[ie].replace(",", "")) for r in rows[2:]) / (len(rows) - 2)
     json.dump(d, open(tj, "w"), indent=1, sort_keys=True)
 
     src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "sass"], capture_output=True, text=True).stdout
@@ -80,6 +84,15 @@ def main():
         f.write("%s\nexecuted warp instructions per warp-sample (32 pixel*labels): %.1f\n" % (sec["name"], tot / units))
         for k, v in hist.most_common():
             f.write("%-12s %8.2f %5.1f%%\n" % (k, v / units, 100.0 * v / tot))
+    # the hot loop: the SASS lines executed at least half as often as the most executed one, in address order
+    mx = max(int(r[ia]) for r in sec["rows"])
+    with open(os.path.join(out, "%s_costvol_hotloop.sass" % tag), "w") as f:
+        f.write("// %s\n// SASS of the label loop (lines executed >= 50%% as often as the hottest line), from the ncu source page;\n"
+                "// columns: address, warp-level executions, instruction\n" % sec["name"])
+        iaddr = sec["hdr"].index("Address")
+        for r in sec["rows"]:
+            if int(r[ia]) * 2 >= mx:
+                f.write("%s %10d  %s\n" % (r[iaddr], int(r[ia]), r[isrc]))
     print("traffic per launch: %.1f MB" % (traffic / 1e6))
 
 

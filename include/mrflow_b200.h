@@ -357,9 +357,9 @@ int mrf_cost_volume_front(const mrf_front_params* p_host, const float* u0, const
  * and the next kernel polls its own flags -- one one-way NVLink latency per exchange.  Every rank owns a context
  * of mrf_peer_sync_bytes() bytes from mrf_peer_alloc, zeroed once, opened by all peers (ctx[r] = this process's
  * pointer to rank r's context, its own at [rank]).  Call sequence per step, all ranks alike:
- *   mrf_peer_sync_begin; mrf_front_mu_whole / parallax_band; candidates_band(peer); mrf_select13_hist_dev(pass
- *   1..4, peer); mrf_select13_successor_dev(peer); mrf_front_structures_band(gathered NULL, peer);
- *   mrf_label_range_dev(gathered NULL, peer).  A rank that never shows up sets the context's error word (second
+ *   mrf_peer_sync_begin; mrf_front_mu_whole / parallax_band; candidates_band(peer); mrf_peer_push_hist(0);
+ *   4 x { mrf_select13_hist_dev(pass p, peer); mrf_peer_push_hist(p) }; mrf_select13_successor_dev(peer);
+ *   mrf_front_structures_band(gathered NULL, peer); mrf_label_range_dev(gathered NULL, peer).  A rank that never shows up sets the context's error word (second
  * 8-byte word) after 20 s of wall clock; check it before trusting results. */
 typedef struct {
   void* ctx[8];
@@ -367,6 +367,9 @@ typedef struct {
 } mrf_peer_sync;
 size_t mrf_peer_sync_bytes(void);
 int mrf_peer_sync_begin(const mrf_peer_sync* peer_host, mrf_stream_t stream);
+/* after the kernel that produced this rank's local histogram of `pass` (candidates_band: 0; hist_dev: 1..4):
+ * add it into every rank's histogram over NVLink and publish the phase (32 blocks) */
+int mrf_peer_push_hist(const mrf_peer_sync* peer_host, const void* select_scratch, int pass, mrf_stream_t stream);
 int mrf_front_mu_whole(const mrf_front_params* p_host, double* dev_state, void* scratch, mrf_stream_t stream);
 int mrf_front_parallax_band(const mrf_front_params* p_host, const float* u0, const float* v0,
                             const float* u1, const float* v1, double* par0, double* par1,

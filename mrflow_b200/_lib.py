@@ -107,6 +107,7 @@ SIGNATURES = {
     "mrf_front_structures_band": (_I, [C.POINTER(FrontParams), _P, _P, _P, _P, _P, _P, _P, _P, _I, _P, _P, _P]),
     "mrf_peer_sync_bytes": (_Z, []),
     "mrf_peer_sync_begin": (_I, [_P, _P]),
+    "mrf_peer_push_hist": (_I, [_P, _P, _I, _P]),
     "mrf_select13_begin": (_I, [_P, _P]),
     "mrf_select13_hist_dev": (_I, [_P, _P, _Z, _I, _P, _P, _P]),
     "mrf_select13_successor_dev": (_I, [_P, _P, _Z, _P, _P, _P]),

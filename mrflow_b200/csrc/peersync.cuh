@@ -3,8 +3,8 @@
 //
 // Every rank owns one PeerCtx in its HBM, exported over CUDA IPC (mrf_peer_alloc / mrf_peer_open) and mapped
 // by all ranks.  A kernel that produces a partial result
-//   * adds (at the start of the consuming kernel, spread over its blocks) the rank's finished histogram into the
-//     histogram of EVERY rank (remote red.add over NVLink, 32 KB per peer), or
+//   * is followed by a 32-block kernel that adds the rank's finished histogram into the histogram of EVERY rank
+//     (remote red.add over NVLink, 32 KB per peer), or
 //   * has its last block write a few words into its slot of every rank's gather area,
 // then publishes "phase ph of step e done" by storing the step's epoch into its flag on every rank.  The
 // consumer kernel -- the next launch on each rank's stream -- starts by polling its OWN flags until all ranks
@@ -121,24 +121,25 @@ __device__ __forceinline__ unsigned long long peer_phase_wait(const PeerArg& pa,
   return e;
 }
 
-// Sum of a histogram over the ranks, at the START of the kernel that consumes it: the blocks of this grid add
-// slices of this rank's finished LOCAL histogram (pass `ph`, in the select scratch) into the pass's histogram in
-// EVERY rank's context -- remote reductions over NVLink, 8192 bins spread over the first blocks of the grid --
-// the last block to finish publishes the phase, and every block then waits until all ranks have published.
-// Returns the epoch; the summed histogram is pa.p[rank]->hist[epoch & 1][ph].
-__device__ __forceinline__ unsigned long long peer_hist_exchange(const PeerArg& pa, int ph, const unsigned int* local_hist) {
+// Sum of a histogram over the ranks: a small kernel of its own (kS13Bins / 256 blocks, always co-resident) between
+// the kernel that produced this rank's LOCAL histogram of pass `ph` (in the select scratch) and the kernel that
+// consumes the sum.  Every thread adds one bin into the pass's histogram in EVERY rank's context -- remote
+// reductions over NVLink for the peers -- and the last block publishes the phase.  The consumer starts with
+// peer_phase_wait(ph) and reads pa.p[rank]->hist[epoch & 1][ph].  (The wait must not sit in the same grid as the
+// push: a grid larger than the GPU can hold at once would have its resident blocks spin for a flag that needs
+// the not-yet-scheduled ones.)
+static __global__ void __launch_bounds__(256)
+k_peer_push_hist(const PeerArg pa, const unsigned int* __restrict__ local_hist, int ph) {
   PeerCtx* me = pa.p[pa.rank];
-  const unsigned long long e = me->epoch;
-  const int set = (int)(e & 1ull);
-  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < (size_t)kS13Bins; i += (size_t)gridDim.x * blockDim.x) {
-    const unsigned int c = __ldcg(local_hist + i);
+  const int set = (int)(me->epoch & 1ull);
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < kS13Bins) {
+    const unsigned int c = local_hist[i];
     if (c) {
       for (int r = 0; r < pa.world; ++r) atomicAdd(&pa.p[r]->hist[set][ph][i], c);
     }
   }
   peer_phase_done(pa, ph, nullptr, 0, 0);
-  peer_phase_wait(pa, ph);
-  return e;
 }
 
 }  // namespace mrf

@@ -163,8 +163,9 @@ k_s13_hist(const double* __restrict__ keys, const int* __restrict__ n_dev, int p
   const unsigned int* h_prev = (pass >= 1) ? s13_hist(scratch, pass - 1) : nullptr;
   if (pa.world > 0) {
     PeerCtx* me = pa.p[pa.rank];
-    // sum the previous pass's histogram over the ranks (peersync.cuh)
-    epoch = (pass >= 1) ? peer_hist_exchange(pa, pass - 1, s13_hist(scratch, pass - 1)) : me->epoch;
+    // the previous pass's histogram, summed over the ranks by mrf_peer_push_hist, is complete once every rank has
+    // published that phase (peersync.cuh)
+    epoch = (pass >= 1) ? peer_phase_wait(pa, pass - 1) : me->epoch;
     if (pass >= 1) h_prev = me->hist[epoch & 1ull][pass - 1];
     if (pass == 1) {
       // zero the histogram set of the NEXT step: every rank is past the previous step (its last user), and this
@@ -213,7 +214,7 @@ k_s13_successor(const double* __restrict__ keys, const int* __restrict__ n_dev, 
   unsigned long long kth, k_rem, n_total;
   const unsigned int* h_last = s13_hist(scratch, kS13Passes - 1);
   if (pa.world > 0) {
-    const unsigned long long epoch = peer_hist_exchange(pa, kS13Passes - 1, s13_hist(scratch, kS13Passes - 1));
+    const unsigned long long epoch = peer_phase_wait(pa, kS13Passes - 1);
     h_last = pa.p[pa.rank]->hist[epoch & 1ull][kS13Passes - 1];
   }
   s13_resolve_from(h_last, scratch, kS13Passes, kth, k_rem, n_total, s_tmp);
@@ -507,6 +508,15 @@ int mrf_select13_successor_dev(const double* keys, const int* n_local_dev, size_
   if (peer_arg(peer, &pa)) return MRF_E_BADARG;
   k_s13_successor<<<s13_blocks(capacity), 256, 0, S(stream)>>>(keys, n_local_dev, scratch, pa);
   return check_launch("mrf_select13_successor_dev");
+}
+
+int mrf_peer_push_hist(const mrf_peer_sync* peer, const void* select_scratch, int pass, mrf_stream_t stream) {
+  MRF_CHECK_ARG(peer && select_scratch && pass >= 0 && pass < kS13Passes);
+  PeerArg pa;
+  if (peer_arg(peer, &pa) || pa.world == 0) return fail(MRF_E_BADARG, "mrf_peer_push_hist: bad peer context");
+  const unsigned int* h = (const unsigned int*)((const char*)select_scratch + kS13HistOffset) + (size_t)pass * kS13Bins;
+  k_peer_push_hist<<<kS13Bins / 256, 256, 0, S(stream)>>>(pa, h, pass);
+  return check_launch("mrf_peer_push_hist");
 }
 
 // ---- peer-memory synchronisation context of the row-band pre-pass (peersync.cuh)

@@ -521,6 +521,8 @@ def banded_front(band, homographies, q_ar, rigid_mask, zero_mask, buf, group=Non
     for ps in range(_lib.SELECT13_PASSES):
         if peer is None:
             dist.all_reduce(buf.sel_hist[ps], op=dist.ReduceOp.SUM, group=group)
+        else:
+            check(L.mrf_peer_push_hist(pr, P(buf.sel), ps, st), "mrf_peer_push_hist")
         if ps + 1 < _lib.SELECT13_PASSES:
             check(L.mrf_select13_hist_dev(P(buf.cand), P(buf.count), cap, ps + 1, P(buf.sel), pr, st), "mrf_select13_hist_dev")
         else:

@@ -126,6 +126,63 @@ def _worker(rank, world, port, queue):
     os._exit(0)                             # no collective teardown: a failed rank must not hang the other
 
 
+def _worker_large(rank, world, port, queue):
+    import torch
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    out = {}
+    try:
+        import traceback
+        from mrflow_b200 import sharding
+        # 2.65 M pixels per band: the select kernels then run at their largest grid (4 blocks per SM), more blocks
+        # than fit beside the concurrent channel kernels -- the peer-memory exchange must not depend on a whole
+        # grid being resident (a wait inside the pushing grid once dead-locked exactly here)
+        rec = sharding.bench_bands((1728, 3072), 3, 1, n_waves=4)
+        out["rec"] = rec
+    except Exception:                       # noqa: BLE001
+        out["error"] = traceback.format_exc()
+    queue.put((rank, out))
+    queue.close(); queue.join_thread()
+    os._exit(0)
+
+
+def test_large_bands_peer_memory_exchange():
+    import torch
+    import torch.multiprocessing as mp
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker_large, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    import queue as _queue
+    res = {}
+    try:
+        for _ in procs:
+            try:
+                k, v = q.get(timeout=150 if not res else 30)
+                res[k] = v
+            except _queue.Empty:
+                break
+    finally:
+        for p in procs:
+            p.join(timeout=5)
+            if p.is_alive():
+                p.kill()
+    for r in res.values():
+        assert "error" not in r, r["error"]
+    assert len(res) == 2, "a rank did not report: got %s" % sorted(res)
+    rec = res[0]["rec"]
+    assert rec["bands_bit_exact"] is True and rec["n_miss"] == 0
+    # no wait ran into its time-out: a step takes milliseconds, not 20 s
+    assert rec["compute_only"]["ms_per_step"] < 50 and rec["compute_only_nccl_collectives"]["ms_per_step"] < 50
+
+
 def test_two_band_volume_equals_whole_frame():
     import torch
     import torch.multiprocessing as mp

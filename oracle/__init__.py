@@ -28,14 +28,22 @@ Parity status
 * a11 (``computeDataTerm``): PINNED the same way -- the energy, and the complete linear system
   (diag(A_data), b_data) of the reference function with its auto-sigma Lorentzian; a9
   (``compute_derivs_through_H``), ``computeOcclusionsFromConsistency`` and ``get_image_weights`` likewise.
+* a5 (``correct_epipole``, pipeline/compute_structure.py:453-511): PINNED.  The generator runs the reference's
+  own function -- objective, BFGS call, acceptance rule untouched -- with a small ``chumpy.ch`` stand-in whose
+  derivative comes from torch autograd (tests/golden/make_golden.py::_Ch); the restatement here with the
+  analytic gradient lands within 1.6e-9 px of it (bar 1e-6; one epipole of the 'inside' fixture moves 1.7 px,
+  the other is kept).
 * a4 end to end: the reference's ``compute_structure`` run with its own solver (oracle/_ref) is stored
-  for the three fixtures whose epipole lies outside the frame (one with moving objects, 14 % non-rigid after
-  the MRF); the oracle reproduces all seven outputs
-  bit for bit.  (With the epipole inside, the reference needs chumpy for ``correct_epipole``: unpinned.)
+  for all four fixtures (one with moving objects, 14 % non-rigid after the MRF; one with the epipole inside the
+  frame, where the reference's own q_new is fed to both sides so that everything downstream is compared bit for
+  bit); the oracle reproduces all seven outputs bit for bit.
+* configs[0] at FULL size: example/frame1-3.png (1024x436), synthetic flows, uniform rigidity,
+  override_optimization=1 through the reference's chain of mrflow.py:98-140; the oracle reproduces the sha256
+  of every output (tests/golden/ref_example_full.npz, test_config1_full_size_chain_pinned).
 * stage 5 (``oracle/variational.py``): the variational refinement ``optimizeStructureSingleScale``
   (optimize_structure_single_scale.py:310-652) and the reference's whole default stage 5
   (``optimize`` -> ``optimizeStructureMultiScale`` -> ...): PINNED -- bit-identical structure and energies
-  on the three outside-epipole fixtures, plus a case with a carved non-rigid block (same scipy / OpenCV calls; the explicit stencil matrices are asserted
+  on all four fixtures, plus a case with a carved non-rigid block (same scipy / OpenCV calls; the explicit stencil matrices are asserted
   equal to construct_matrices.py's when the goldens are generated).
 * a12 (the per-label cost volume): the reference's arithmetic for this step lived in a compiled
   extension that is NOT shipped (``pipeline/build_cost_volume.py:26-27``).  The oracle composes

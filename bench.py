@@ -49,6 +49,7 @@ def parse():
     ap.add_argument("--variant", default="staged", choices=["staged", "gather", "staged_occ2", "gather_occ2"])
     ap.add_argument("--batch", type=int, default=16, help="triplets per step (a step = one pass of the path over one batch)")
     ap.add_argument("--no-bands", action="store_true", help="skip the 4K row-band record (bands_4k)")
+    ap.add_argument("--bands-timeout", type=int, default=240, help="seconds after which the line is printed without bands_4k")
     ap.add_argument("--no-pair", action="store_true", help="one cost-volume launch per neighbour frame instead of one per triplet")
     ap.add_argument("--no-priority", action="store_true", help="pre-pass on a normal-priority stream")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -466,23 +467,13 @@ def run_ours(args):
         else:
             parity, _, _ = parity_against_oracle(t, stepper.cost, state_g, [0, 25, 50], args.interp)
 
-    # ---- BASELINE.json configs[3]: one 4K frame in row bands over the N GPUs (strong scaling); at N = 1 the base
-    bands = None
-    if not args.no_bands:
-        for st, _ in slots:
-            del st
-        slots.clear()
-        stepper_launches = stepper.launches_in_graph
-        cuda_graph = stepper.graph is not None
-        stepper = None
-        torch.cuda.empty_cache()
-        from mrflow_b200 import sharding
-        bands = sharding.bench_bands(synth.SHAPES["4k"], max(5, min(steps, 20)), 3, interp=args.interp, variant=args.variant)
-    else:
-        stepper_launches = stepper.launches_in_graph
-        cuda_graph = stepper.graph is not None
+    stepper_launches = stepper.launches_in_graph
+    cuda_graph = stepper.graph is not None
 
-    if rank == 0:
+    printed = []
+
+    def emit(bands_rec):
+        printed.append(1)
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": warm,
                 "ms_per_step": total_ms_max / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "f64 geometry / f32 sampling", "data": "synthetic",
@@ -497,10 +488,37 @@ def run_ours(args):
                                    "value": world * units_per_triplet * n_single / (single_ms_max * 1e-3),
                                    "note": "one triplet at a time, L2 flushed before every step (path latency)"},
                 "clocks": clocks.summary(), "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
-                "cpu_baseline": cpu_baseline, "parity": parity, "bands_4k": bands}
-        print(json.dumps(line))
+                "cpu_baseline": cpu_baseline, "parity": parity, "bands_4k": bands_rec}
+        print(json.dumps(line), flush=True)
+
+    # ---- BASELINE.json configs[3]: one 4K frame in row bands over the N GPUs (strong scaling); at N = 1 the base
+    bands, dog = None, None
+    if not args.no_bands:
+        slots.clear()
+        stepper = None
+        torch.cuda.empty_cache()
+        from mrflow_b200 import sharding
+        # The headline line must come out whatever happens in this add-on record: an exception becomes an "error"
+        # entry, and a watchdog prints the line without the record if the banded run does not return in time (a
+        # lost rank would otherwise leave the others in a collective).
+        def _bail():
+            if rank == 0 and not printed:
+                emit({"error": "bands_4k did not finish within %d s" % args.bands_timeout})
+            os._exit(0)
+        dog = threading.Timer(args.bands_timeout, _bail)
+        dog.daemon = True
+        dog.start()
+        try:
+            bands = sharding.bench_bands(synth.SHAPES["4k"], max(5, min(steps, 20)), 3, interp=args.interp, variant=args.variant)
+        except Exception as e:                              # noqa: BLE001
+            bands = {"error": "%s: %s" % (type(e).__name__, e)}
+
+    if rank == 0:
+        emit(bands)
     if world > 1:
-        dist.destroy_process_group()
+        dist.destroy_process_group()          # still under the watchdog: a rank that failed above may not join
+    if dog is not None:
+        dog.cancel()
 
 
 if __name__ == "__main__":

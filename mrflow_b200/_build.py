@@ -31,9 +31,13 @@ def _stale(target, deps):
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force=False, verbose=False):
-    """Compile every CUDA translation unit and link the shared library.  Returns its path."""
-    objdir = os.path.join(HERE, "build")
+def build(force=False, verbose=False, extra=(), lib=None, objdir_name="build"):
+    """Compile every CUDA translation unit and link the shared library.  Returns its path.  ``extra`` (nvcc
+    flags), ``lib`` and ``objdir_name`` build an experimental copy beside the product library
+    (tools/bench_kernel.py --lib)."""
+    global LIB
+    lib_path = lib or LIB
+    objdir = os.path.join(HERE, objdir_name)
     os.makedirs(objdir, exist_ok=True)
     headers = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))]
     headers.append(os.path.join(os.path.dirname(HERE), "include", "mrflow_b200.h"))
@@ -43,7 +47,7 @@ def build(force=False, verbose=False):
         obj = os.path.join(objdir, src[:-3] + ".o")
         path = os.path.join(CSRC, src)
         if force or _stale(obj, [path] + headers):
-            cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", path, "-o", obj]
+            cmd = [nvcc] + NVCC_FLAGS + list(extra) + (["-Xptxas", "-v"] if verbose else []) + ["-c", path, "-o", obj]
             r = subprocess.run(cmd, capture_output=True, text=True)
             if verbose:
                 sys.stderr.write(r.stderr)
@@ -53,12 +57,12 @@ def build(force=False, verbose=False):
 
     with ThreadPoolExecutor(max_workers=4) as ex:
         objs = list(ex.map(compile_one, SOURCES))
-    if force or _stale(LIB, objs):
-        cmd = [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB] + objs + ["-lcudart"]
+    if force or _stale(lib_path, objs):
+        cmd = [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", lib_path] + objs + ["-lcudart"]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError("link failed:\n%s\n%s" % (r.stdout, r.stderr))
-    return LIB
+    return lib_path
 
 
 if __name__ == "__main__":

@@ -7,7 +7,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libmrflow_b200.so")
+LIB_PATH = os.environ.get("MRF_LIB_PATH") or os.path.join(HERE, "libmrflow_b200.so")    # MRF_LIB_PATH: an experimental build
 
 INTERP = {"cubic": 0, "linear": 1}
 RHO = {"lorentzian": 0, "charbonnier": 1, "geman_mcclure": 2, "quadratic": 3, "lorentzian_auto": 4, "none": 5}

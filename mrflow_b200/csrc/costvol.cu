@@ -31,7 +31,10 @@
 
 namespace mrf {
 
-constexpr int kTX = 32, kTY = 8, kThreads = kTX * kTY;
+#ifndef MRF_TY
+#define MRF_TY 8          // tile rows (warps per block); experiments: -DMRF_TY=7 with MRF_VARIANT_OCC4
+#endif
+constexpr int kTX = 32, kTY = MRF_TY, kThreads = kTX * kTY;
 constexpr int kMaxLabels = 256;
 constexpr int kWinCap = 3072;      // staged window capacity in texels (48 KB)
 constexpr int kWinCap4 = 2560;     // ... with four blocks per SM (40 KB)

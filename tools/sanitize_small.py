@@ -25,5 +25,24 @@ device.data_term(torch.from_numpy(t["A_true"]).cuda(), ch[0], ch[0].clone(), (ma
 fl = [[torch.from_numpy(t["flow"][f][k]).cuda() for k in range(2)] for f in range(2)]
 device.flow_consistency(fl, fl, 2.0)
 device.image_weights(torch.from_numpy(t["images"][1]).cuda())
+# round 2: both forms of the pre-pass, the auto-sigma cost volume, the device-resident structure stage, the
+# pipelined host call, the five-pass select on its own
+rigid = mask
+nonrigid = (mask == 0).to(torch.uint8)
+for fused in (False, True):
+    buf = device.FrontBuffers(72, 96)
+    device.cost_volume_front(band.flow, rigid, nonrigid, t["homographies"], t["epipoles"], 72, buf, fused=fused)
+bcv.build_cost_volume(t["images"], t["flow"], t["rigidity"], t["homographies"], t["epipoles"], None, rho="lorentzian", sigma=None,
+                      range_mask="rigid_only")
+bcv.build_cost_volume(t["images"], t["flow"], t["rigidity"], t["homographies"], t["epipoles"], None, range_mask="rigid_only")
+bcv.build_cost_volume(t["images"], t["flow"], t["rigidity"], t["homographies"], t["epipoles"], None, range_mask="rigid_only",
+                      layout="HWL_I32")
+from mrflow_b200.pipeline import compute_structure as cs
+import argparse
+cs.compute_structure(t["images"], t["flow"], t["rigidity"], [np.zeros((72, 96), bool)] * 2, [H.copy() for H in t["homographies"]],
+                     t["epipoles"], argparse.Namespace(nonlinear_structure_initialization=0),
+                     infer_mrf=lambda I, un, lam: (un[:, :, 1] > un[:, :, 0]).astype(np.int32))
+for n in (0, 1, 5000):
+    device.median(torch.randn(max(n, 1) + 3, dtype=torch.float64, device="cuda"), n)
 torch.cuda.synchronize()
 print("sanitize_small ok, halo misses:", int(miss.cpu()[0]))

@@ -44,3 +44,25 @@ def test_product_never_imports_the_oracle():
             if f.endswith(".py"):
                 txt = open(os.path.join(dirpath, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", txt, flags=re.M), f
+
+
+def test_bench_reference_arm_contract():
+    """bench.py --impl reference (the CPU arm, the one leg that runs without a GPU) prints one JSON line with
+    the contract's keys and the same `config` keys as the GPU arm uses."""
+    import json
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--shape", "48x64", "--steps", "1",
+                        "--warmup", "0"], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [l for l in r.stdout.splitlines() if l.startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["metric"] == "cost_volume_pixel_labels_per_s" and d["higher_is_better"] is True
+    assert sorted(d["config"]) == ["frames", "interp", "labels", "workload"]
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["value"] == d["value"] == d["e2e"]["value"]
+    assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
+    src = open(os.path.join(root, "bench.py")).read()
+    assert '"config": {"workload": workload_name(args, hw), "labels": N_LABELS, "frames": 2, "interp": args.interp}' in src
+    assert src.count('"config": {"workload": workload_name(args, hw), "labels": N_LABELS, "frames": 2, "interp": args.interp}') == 2

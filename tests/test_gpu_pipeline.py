@@ -501,3 +501,20 @@ def test_build_cost_volume_auto_sigma(trip):
     for f in range(2):
         assert got[0][f].shape == (51, h, w)
         _check_costs(got[0][f][[0, 13, 25, 38, 50]], want[f], "auto-sigma frame %d" % f)
+
+
+@pytest.mark.parametrize("layout", ["LHW_F32", "HWL_I32"])
+def test_pipelined_host_call_equals_resident_pass(trip, layout):
+    """The plain build_cost_volume call (uploads, row-chunked kernels and pitched downloads overlapped over
+    PCIe) returns exactly what the device-resident pass leaves in HBM, in both volume layouts."""
+    from mrflow_b200.pipeline.build_cost_volume import build_cost_volume
+    t = trip
+    host = build_cost_volume(t["images"], t["flow"], t["rigidity"], t["homographies"], t["epipoles"], _params(), layout=layout,
+                             range_mask="rigid_only")
+    dev = build_cost_volume(t["images"], t["flow"], t["rigidity"], t["homographies"], t["epipoles"], _params(), layout=layout,
+                            range_mask="rigid_only", return_device=True)
+    for f in range(2):
+        assert np.array_equal(host[0][f], dev[0][f].cpu().numpy())
+        assert np.array_equal(host[1][f], dev[1][f].cpu().numpy(), equal_nan=True)
+    assert host[2] == dev[2] and host[3] == dev[3] and np.array_equal(host[5], dev[5])
+    assert all(np.array_equal(a, b) for a, b in zip(host[4], dev[4]))

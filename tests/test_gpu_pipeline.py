@@ -185,6 +185,8 @@ def test_build_cost_volume(trip, mask_mode):
         np.testing.assert_allclose(got[1][f][fin], want[1][f][fin], rtol=1e-10)
     # and against the oracle's own volume: all but a vanishing fraction of samples agree
     close = np.isclose(np.stack(got[0]), np.stack(want[0]), rtol=1e-5, atol=1e-7)
+    print("build_cost_volume[%s]: %.6f of the samples within 1e-5 of the oracle's own volume (own mu / B / labels)"
+          % (mask_mode, close.mean()))
     assert close.mean() > 0.9999
 
     dev = build_cost_volume(t["images"], t["flow"], rig, t["homographies"], t["epipoles"], _params(),

@@ -1145,9 +1145,10 @@ int mrf_cost_volume_front(const mrf_front_params* p, const float* u0, const floa
 }
 
 
-// ---- the same pre-pass in pieces for row bands: the caller all-reduces (NCCL, on the stream) between
-// the pieces -- the two sums behind mu, the candidate count, the 256-bin histograms of the distributed
-// median, and the range min / max -- so there is no host round trip either.
+// ---- the same pre-pass in pieces for row bands: between the pieces the five 8192-bin
+// histograms of the exact median, its three successor words and the six range words are exchanged -- by NCCL
+// collectives the caller enqueues on the stream, or, with a peer context, by the kernels themselves over NVLink
+// peer memory (peersync.cuh).  mu needs no exchange (mrf_front_mu_whole).  No host round trip either way.
 int mrf_front_mu_whole(const mrf_front_params* p, double* dev_state, void* scratch, mrf_stream_t stream) {
   MRF_CHECK_ARG(p && dev_state && scratch && p->frame_h > 0 && p->w > 0);
   double* partial = (double*)scratch;

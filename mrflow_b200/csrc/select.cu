@@ -6,7 +6,10 @@
 //   * label range of pipeline/build_cost_volume.py:154-169,190-192: min / max with the reference's
 //     zeroing rules applied on the fly.
 //
-// Selection is an 8-pass MSD radix select over order-preserving 64-bit keys: each pass histograms one
+// Two selections live here.  The device-resident one (k_s13_*, select13.cuh) takes five passes over 13-bit digits
+// and resolves each digit inside the next pass's kernel; the pre-pass, the variational refinement and the
+// row-band protocol use it.  The host-driven one below is an 8-pass MSD radix select over order-preserving
+// 64-bit keys: each pass histograms one
 // byte of the keys that still match the prefix found so far (shared-memory privatised histogram,
 // one global atomic per bin per block), and a one-thread step picks the byte.  The histogram and the
 // pick are separate entry points so that a multi-GPU caller can all-reduce the 256-bin histogram

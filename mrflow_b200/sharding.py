@@ -1,14 +1,17 @@
 """Row-band sharding of one triplet over the GPUs of a box.
 
-One process per GPU (``torch.distributed``, NCCL).  Rank r owns rows ``[y0_r, y1_r)`` of the reference
-frame for all labels; per-pixel work is independent given a handful of whole-frame scalars, so the
+One process per GPU (``torch.distributed``, NCCL for the plumbing).  Rank r owns rows ``[y0_r, y1_r)`` of the
+reference frame for all labels; per-pixel work is independent given a handful of whole-frame scalars, so the
 only exchange steps are
 
-* tiny all-reduces: the sum behind ``mu`` (pipeline/compute_structure.py:84), the counts of the
-  gates (:164, :183), the label range min/max (pipeline/build_cost_volume.py:190-191);
-* exact distributed medians (compute_structure.py:190, :221): an 8-pass radix select whose 256-bin
-  histogram (2 KB) is all-reduced per pass -- ``DistSelect`` below, a host-side protocol around two
-  per-shard device steps, so the protocol itself is testable on CPU with gloo;
+* nothing at all for ``mu`` (pipeline/compute_structure.py:84): the sum of ||p - q|| over the whole frame depends
+  only on (q, h, w), so every rank evaluates it itself in the one-GPU summation tree (``banded_mu``);
+* the exact median behind B_b (compute_structure.py:221): five radix passes over 13-bit digits whose 8192-bin
+  histograms are summed over the ranks, one gather of the three successor words, one gather of the six words of
+  the label range (pipeline/build_cost_volume.py:190-191) -- in ``banded_front`` either as seven small NCCL
+  collectives enqueued on the stream, or, with a ``PeerSync``, with NO collective launch: the kernels exchange
+  over NVLink peer memory themselves (csrc/peersync.cuh).  ``DistSelect13`` is the host twin of that protocol and
+  ``DistSelect`` / ``BandStats`` the host-driven 8-bit protocol, both testable on CPU with gloo;
 * the gather of the label-major cost-volume slices to the rank that runs TRW-S: the root exports a
   whole-frame ``[L][h][w]`` buffer as peer memory and every rank's cost-volume kernel stores its
   rows straight into it over NVLink (``PeerVolume``) -- the transfer is the kernel's own output

@@ -50,6 +50,7 @@ def parse():
     ap.add_argument("--batch", type=int, default=16, help="triplets per step (a step = one pass of the path over one batch)")
     ap.add_argument("--no-bands", action="store_true", help="skip the 4K row-band record (bands_4k)")
     ap.add_argument("--bands-timeout", type=int, default=240, help="seconds after which the line is printed without bands_4k")
+    ap.add_argument("--ref-labels", type=int, default=None, help="--impl reference: labels per step (default: all 51)")
     ap.add_argument("--no-pair", action="store_true", help="one cost-volume launch per neighbour frame instead of one per triplet")
     ap.add_argument("--no-priority", action="store_true", help="pre-pass on a normal-priority stream")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -189,18 +190,23 @@ def run_reference(args):
     warm = 1 if args.warmup is None else args.warmup
     t = synth.make_triplet(hw, seed=1001)
     t_rest, state, ch = cpu_front_and_tail(t)
-    idx = [0, 17, 34, 50]
+    # every step is the WHOLE workload of one triplet on the host: all 51 labels of both neighbour frames (about 3 s
+    # on 16 cores) plus the pre-pass / channels / structure->flow part (timed once, identical every step); nothing is
+    # pro-rated.  --ref-labels N bounds the sample to N evenly spaced labels (then the rest is scaled by N/51).
+    n_lab = N_LABELS if args.ref_labels is None else max(1, min(N_LABELS, args.ref_labels))
+    idx = sorted(set(int(round(v)) for v in np.linspace(0, N_LABELS - 1, n_lab)))
     for _ in range(warm):
         cpu_reference_step(t, ch, state, idx, args.interp)
     tot_s, tot_u = 0.0, 0
     for _ in range(steps):
         dt, units = cpu_reference_step(t, ch, state, idx, args.interp)
-        tot_s += dt + t_rest * len(idx) / N_LABELS       # pro-rated share of the non-cost-volume work
+        tot_s += dt + t_rest * len(idx) / N_LABELS
         tot_u += units
     value = tot_u / tot_s
     cores = host_threads()
     sample = "%d of %d labels x 2 frames per step on the full %dx%d triplet; structure pre-pass / channels / " \
-             "structure->flow timed once (%.3f s) and pro-rated" % (len(idx), N_LABELS, hw[1], hw[0], t_rest)
+             "structure->flow timed once (%.3f s) and added to every step%s" % (
+                 len(idx), N_LABELS, hw[1], hw[0], t_rest, "" if len(idx) == N_LABELS else " in proportion")
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
             "warmup": warm, "ms_per_step": 1e3 * tot_s / max(steps, 1), "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",

@@ -72,6 +72,15 @@ def workload_name(args, hw):
     return "%s_%dx%d_L%d_F2_%s" % (args.shape, hw[1], hw[0], N_LABELS, args.interp)
 
 
+def bench_config(args, hw):
+    """the same dict in both arms (the driver compares them)"""
+    vol_mb = 2 * N_LABELS * hw[0] * hw[1] * 4 / 1e6
+    l2 = ("GPU arm: L2 flushed (256 MiB fill) before the timed region and before every single-triplet step; a step cycles "
+          "over %d resident triplets and writes %d x %.0f MB (> 126 MB L2).  CPU arm: not applicable"
+          % (max(1, args.pipeline), max(1, args.batch), vol_mb))
+    return {"workload": workload_name(args, hw), "labels": N_LABELS, "frames": 2, "interp": args.interp, "l2": l2}
+
+
 def algorithmic_bytes_per_launch(h, w, L=N_LABELS):
     """one launch computes BOTH neighbour frames of a triplet; every input read once and
     every output written once: per frame the cost store L*4, min/argmin 4, neighbour channels 3*4, masks 2, plus
@@ -210,7 +219,7 @@ def run_reference(args):
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
             "warmup": warm, "ms_per_step": 1e3 * tot_s / max(steps, 1), "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": workload_name(args, hw), "labels": N_LABELS, "frames": 2, "interp": args.interp},
+            "config": bench_config(args, hw),
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
                              "host_cpus": os.cpu_count()},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
@@ -484,13 +493,12 @@ def run_ours(args):
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": warm,
                 "ms_per_step": total_ms_max / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "f64 geometry / f32 sampling", "data": "synthetic",
-                "config": {"workload": workload_name(args, hw), "labels": N_LABELS, "frames": 2, "interp": args.interp},
+                "config": bench_config(args, hw),
                 "details": {"triplets_per_step": T, "ms_per_triplet": ms_per_triplet, "variant": args.variant,
                             "range_mask": RANGE_MASK,
                             "cuda_graph": "pre-pass + channels (%d launches) replayed as one graph" % stepper_launches
                             if cuda_graph else "off", "triplets_in_flight": P, "parallelism": "triplets x%d" % world,
-                            "l2": "flushed before the timed region; the batch cycles over %d resident triplets and each "
-                                  "writes 182 MB (> 126 MB L2)" % P},
+                            },
                 "single_triplet": {"ms_per_step": single_ms_max / n_single, "steps": n_single,
                                    "value": world * units_per_triplet * n_single / (single_ms_max * 1e-3),
                                    "note": "one triplet at a time, L2 flushed before every step (path latency)"},

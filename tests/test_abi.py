@@ -60,9 +60,8 @@ def test_bench_reference_arm_contract():
     assert len(lines) == 1
     d = json.loads(lines[0])
     assert d["impl"] == "reference" and d["metric"] == "cost_volume_pixel_labels_per_s" and d["higher_is_better"] is True
-    assert sorted(d["config"]) == ["frames", "interp", "labels", "workload"]
+    assert sorted(d["config"]) == ["frames", "interp", "l2", "labels", "workload"]
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["value"] == d["value"] == d["e2e"]["value"]
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
     src = open(os.path.join(root, "bench.py")).read()
-    assert '"config": {"workload": workload_name(args, hw), "labels": N_LABELS, "frames": 2, "interp": args.interp}' in src
-    assert src.count('"config": {"workload": workload_name(args, hw), "labels": N_LABELS, "frames": 2, "interp": args.interp}') == 2
+    assert src.count('"config": bench_config(args, hw)') == 2          # both arms build it with the same function

@@ -266,9 +266,11 @@ typedef struct {
 #define MRF_VARIANT_OCC2   16 /* OR-able tuning flag: compile for 2 resident blocks / SM (128
                                  registers per thread) instead of 3 */
 #define MRF_VARIANT_OCC4   32 /* OR-able: 4 resident blocks / SM (64 registers, 40 KB staged window) */
-#define MRF_VARIANT_WARPFAST 64 /* OR-able, bicubic only: a warp-uniform straight-line fast path round the
-                                   gather instead of per-lane branches (same arithmetic; measured 7 % slower
-                                   at 80 registers, profiles/r2d_kernel_variants_sintel.jsonl; kept for comparison) */
+#define MRF_VARIANT_GROUPED 128 /* OR-able, staged only: the label loop handles two labels per iteration, each phase (fp64
+                                   geometry, taps, fp64 residual / rho) one branch-free straight line over both.  Same
+                                   arithmetic.  Default for bilinear sampling (8 % faster); opt-in for bicubic (measured
+                                   10 % slower: the kernel is bound by shared-memory wavefronts there) */
+#define MRF_VARIANT_SINGLE  256 /* OR-able: bilinear sampling with the one-label-per-iteration loop (for comparison) */
 
 /* ref_ch: fp64 [rows,w,3] channels of the reference frame band; nb_texels as described;
  * labels: fp64 [n_labels] structure_range (device); nonrigid/occluded: uint8 [rows,w], !=0

@@ -13,7 +13,7 @@ INTERP = {"cubic": 0, "linear": 1}
 RHO = {"lorentzian": 0, "charbonnier": 1, "geman_mcclure": 2, "quadratic": 3, "lorentzian_auto": 4, "none": 5}
 LAYOUT = {"LHW_F32": 0, "HWL_I32": 1}
 VARIANT = {"staged": 0, "gather": 1, "staged_occ2": 16, "gather_occ2": 17, "staged_occ4": 32, "gather_occ4": 33,
-           "staged_warpfast": 64, "gather_warpfast": 65, "staged_occ4_warpfast": 96, "staged_occ2_warpfast": 80}
+           "staged_grouped": 128, "staged_occ2_grouped": 144, "staged_occ4_grouped": 160, "staged_single": 256}
 SELECT_HIST_OFFSET = 64
 SELECT13_BINS, SELECT13_HIST_OFFSET, SELECT13_SUCC_OFFSET, SELECT13_PASSES = 8192, 256, 24, 5
 

@@ -34,6 +34,9 @@ namespace mrf {
 #ifndef MRF_TY
 #define MRF_TY 8          // tile rows (warps per block); experiments: -DMRF_TY=7 with MRF_VARIANT_OCC4
 #endif
+#ifndef MRF_GROUP_LINEAR
+#define MRF_GROUP_LINEAR 2   // labels per iteration of the grouped loop, bilinear sampling (experiments: 3, 4)
+#endif
 constexpr int kTX = 32, kTY = MRF_TY, kThreads = kTX * kTY;
 constexpr int kMaxLabels = 256;
 constexpr int kWinCap = 3072;      // staged window capacity in texels (48 KB)
@@ -167,7 +170,7 @@ __constant__ double kThird = 1.0 / 3.0;
 __device__ __forceinline__ double log_ge1(double u) {
   int hi = __double2hiint(u);
   const int lo = __double2loint(u);
-  if (hi >= 0x7ff00000) return u;                       // inf / NaN
+  const bool special = hi >= 0x7ff00000;                // inf / NaN: returned as they are
   int e = (hi >> 20) - 1023;
   hi = (hi & 0x000fffff) | 0x3ff00000;
   if (hi >= 0x3ff6a09e) { hi -= 0x00100000; e += 1; }   // m >= sqrt(2): halve
@@ -190,7 +193,8 @@ __device__ __forceinline__ double log_ge1(double u) {
   pl = fma(s2, pl, kAtanhC[0]);
   pl = pl * s2;
   const double two_s = sv + sv;
-  return fma((double)e, kLn2, fma(two_s, pl, two_s));
+  const double res = fma((double)e, kLn2, fma(two_s, pl, two_s));
+  return special ? u : res;
 }
 
 // Reciprocal of a tame double, correctly rounded: hardware seed (MUFU.RCP64H, ~2^-23) and three
@@ -273,15 +277,115 @@ __device__ __noinline__ float band_sample_cost(const CVArgs& a, float xf, float 
   return (float)cst;
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// Pieces of the grouped label loop (FORM 2): the loop handles the labels in pairs, and each phase of
+// the pair -- fp64 geometry, the tap gathers, the fp64 residual / rho tail -- is one branch-free
+// straight line over both labels, so that the two dependent fp64 chains of a phase interleave
+// (the single-label forms leave the fp64 pipe's latency exposed: `wait` was the top stall reason).
+// Every operation and its order are those of the other forms; results are bit-identical.
+struct SampleCode {
+  uint32_t p0;      // shared-memory address of the footprint's first texel (a harmless address when !fast)
+  uint32_t wx, wy;  // addresses of the two weight vectors in the 1/32-px table
+  bool fast;        // exact sequences proven, inside the frame, footprint inside the staged window, pixel alive
+  bool cold;        // alive, not fast, and the sample counts (inexact operands, or inside the frame)
+};
+struct WinGeom { int fx_lo, fy_lo, fx_span, fy_span; uint32_t win_s, win_base, pitch, wt_s; };
+
+template <int INTERP>
+__device__ __forceinline__ void sample_code(const CVArgs& a, uint32_t lab_addr, double n_fast, double xk, double yk,
+                                            double t1, double t2, const WinGeom& g, bool dead, SampleCode& s) {
+  constexpr int kOff = (INTERP == MRF_INTERP_CUBIC) ? 1 : 0;
+  double ab, dl, rdl;
+  asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(ab), "=d"(dl) : "r"(lab_addr));
+  asm volatile("ld.shared.f64 %0, [%1];" : "=d"(rdl) : "r"(lab_addr + 16u));
+  const double r = div_rc(ab * n_fast, dl, rdl);             // r = A*B*n / (B*A/mu - 1)  :221
+  const double xn = xk + r * t1, yn = yk + r * t2;           // :224-235
+  const double den = (xn * a.H.m[6] + yn * a.H.m[7]) + a.H.m[8];   // interpolate_through_H.py:31-35
+  const double Xn = (xn * a.H.m[0] + yn * a.H.m[1]) + a.H.m[2];
+  const double Yn = (xn * a.H.m[3] + yn * a.H.m[4]) + a.H.m[5];
+  const double rd = rcp_rn_tame(den);
+  const double X = div_rc(Xn, den, rd);
+  const double Y = div_rc(Yn, den, rd);
+  const bool exact = tame_divisor(den);                      // else: NaN / wild operands somewhere above
+  const bool inside = (X >= 0.0) && (X <= a.wm1) && (Y >= 0.0) && (Y <= a.hm1);   // :39
+  const float xf = (float)X, yf = (float)Y;                  // interpolation.py:77-78
+  const int sx = __float2int_rn(xf * 32.0f), sy = __float2int_rn(yf * 32.0f);      // cv2.remap's 1/32-px bins
+  const int ix0 = (sx >> 5) - kOff, iy0 = (sy >> 5) - kOff;
+  const bool inwin = (unsigned)(ix0 - g.fx_lo) <= (unsigned)g.fx_span && (unsigned)(iy0 - g.fy_lo) <= (unsigned)g.fy_span;
+  s.fast = exact && inside && inwin && !dead;
+  s.cold = !dead && !s.fast && (!exact || inside);
+  s.p0 = s.fast ? (g.win_s + (uint32_t)iy0 * g.pitch + (uint32_t)ix0 * 16u) : g.win_base;
+  s.wx = g.wt_s + (uint32_t)(sx & 31) * 16u;
+  s.wy = g.wt_s + (uint32_t)(sy & 31) * 16u;
+}
+
+// the taps of one sample out of the staged window: OpenCV's order (bicubic: row sums left to right, then the
+// rows; bilinear: one running sum), every product and sum rounded separately
+template <int INTERP>
+__device__ __forceinline__ F3 window_taps(const SampleCode& s, uint32_t pitch) {
+  constexpr int kTaps = (INTERP == MRF_INTERP_CUBIC) ? 4 : 2;
+  float wxa[4], wya[4];
+  lds128(s.wx, wxa[0], wxa[1], wxa[2], wxa[3]);
+  lds128(s.wy, wya[0], wya[1], wya[2], wya[3]);
+  F3 J;
+#pragma unroll
+  for (int j = 0; j < kTaps; ++j) {
+    F3 row;
+#pragma unroll
+    for (int i = 0; i < kTaps; ++i) {
+      const float wgt = wya[j] * wxa[i];
+      float tx, ty, tz, tw;
+      lds128(s.p0 + (uint32_t)j * pitch + (uint32_t)i * 16u, tx, ty, tz, tw);
+      const float px = tx * wgt, py = ty * wgt, pz = tz * wgt;
+      if (INTERP == MRF_INTERP_CUBIC) {
+        if (i == 0) { row.x = px; row.y = py; row.z = pz; }
+        else        { row.x = row.x + px; row.y = row.y + py; row.z = row.z + pz; }
+      } else {
+        if (i == 0 && j == 0) { J.x = px; J.y = py; J.z = pz; }
+        else { J.x = J.x + px; J.y = J.y + py; J.z = J.z + pz; }
+      }
+    }
+    if (INTERP == MRF_INTERP_CUBIC) {
+      if (j == 0) J = row;
+      else { J.x = J.x + row.x; J.y = J.y + row.y; J.z = J.z + row.z; }
+    }
+  }
+  return J;
+}
+
+// A sample the grouped loop could not take from the window: geometry again with the same sequences (same
+// bits), then the plain-division path or the global-memory gather.  Cold.
+template <int INTERP>
+__device__ __noinline__ float cold_cost(const CVArgs& a, uint32_t lab_addr, double n, double xk, double yk, double t1,
+                                        double t2, uint32_t ref_s, float cost_dead) {
+  double ab, dl, rdl, r0, r1, r2;
+  asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(ab), "=d"(dl) : "r"(lab_addr));
+  asm volatile("ld.shared.f64 %0, [%1];" : "=d"(rdl) : "r"(lab_addr + 16u));
+  asm volatile("ld.shared.f64 %0, [%1];" : "=d"(r0) : "r"(ref_s));
+  asm volatile("ld.shared.f64 %0, [%1];" : "=d"(r1) : "r"(ref_s + (uint32_t)(kThreads * 8)));
+  asm volatile("ld.shared.f64 %0, [%1];" : "=d"(r2) : "r"(ref_s + (uint32_t)(kThreads * 16)));
+  const double n_fast = ((n == 0.0) || tame(n)) ? n : __longlong_as_double(0x7FF8000000000000ll);
+  const double r = div_rc(ab * n_fast, dl, rdl);
+  const double xn = xk + r * t1, yn = yk + r * t2;
+  const double den = (xn * a.H.m[6] + yn * a.H.m[7]) + a.H.m[8];
+  if (!tame_divisor(den)) return slow_sample_cost<INTERP>(a, ab, dl, n, xk, yk, t1, t2, r0, r1, r2);
+  const double Xn = (xn * a.H.m[0] + yn * a.H.m[1]) + a.H.m[2];
+  const double Yn = (xn * a.H.m[3] + yn * a.H.m[4]) + a.H.m[5];
+  const double rd = rcp_rn_tame(den);
+  const double X = div_rc(Xn, den, rd);
+  const double Y = div_rc(Yn, den, rd);
+  const bool inside = (X >= 0.0) && (X <= a.wm1) && (Y >= 0.0) && (Y <= a.hm1);
+  if (!inside) return cost_dead;
+  return band_sample_cost<INTERP>(a, (float)X, (float)Y, r0, r1, r2);
+}
+
+template <int N> struct IntC { static constexpr int value = N; };
+
 struct __align__(16) LabelRec { double ab, den, rden, safe; };   // safe: 1.0 / 0.0
 
-template <int INTERP, bool STAGED, int OCC, int LAYOUT, bool WF>
-__global__ void __launch_bounds__(kThreads, OCC)
-k_cost_volume(const __grid_constant__ CVArgs a0, const __grid_constant__ CVArgs a1) {
-  // blockIdx.z selects the neighbour frame: both frames of a triplet share one grid, so the tail of one
-  // frame's blocks overlaps the head of the other's (grid.z = 1: a0 only)
-  const CVArgs& a = (blockIdx.z == 0) ? a0 : a1;
-  extern __shared__ __align__(128) unsigned char dyn_smem[];
+template <int INTERP, bool STAGED, int LAYOUT, int FORM>
+__device__ __forceinline__ void cost_volume_block(const CVArgs& a, unsigned char* dyn_smem) {
   __shared__ LabelRec s_lab[kMaxLabels];    // A*B, B*A/mu - 1, RN(1/that), exact-sequence-safe flag
   __shared__ __align__(16) float4 s_wt[32]; // OpenCV's interpolation table: weights at frac/32
   __shared__ double s_c[2];                 // min / max over labels of A*B / (B*A/mu - 1)
@@ -441,6 +545,7 @@ k_cost_volume(const __grid_constant__ CVArgs a0, const __grid_constant__ CVArgs 
   asm volatile("" : "+d"(xk), "+d"(yk));
   const float cost_dead = (float)rho_eval(a.rho, 0.0, a.rho_param);
   const bool lor_fast = (a.rho == MRF_RHO_LORENTZIAN) && tame(a.s2);
+  const bool lor_unit = lor_fast && (a.s2 == 1.0);          // sigma = 1 (the default)
   // a pixel whose n is not tame poisons its own fast path the same way
   const double n_fast = ((n == 0.0) || tame(n)) ? n : __longlong_as_double(0x7FF8000000000000ll);
   float best = 0.f; int best_l = 0;
@@ -453,174 +558,80 @@ k_cost_volume(const __grid_constant__ CVArgs a0, const __grid_constant__ CVArgs 
   else { cost_p = a.min_cost ? (char*)(a.min_cost + pix) : (char*)(a.argmin + pix); cost_step = 0; }
   uint32_t cost_off = 0;                                    // host side guarantees L * step < 4 GiB
 
-  // Two forms of the label loop with identical arithmetic.  Bilinear (4 taps): one straight line --
-  // geometry, window test, taps, residual, rho computed for every label and selected at the end, so the
-  // compiler overlaps the fp64 chains with the gathers (measured 0.233 -> 0.203 ms).  Bicubic (16 taps):
-  // branches round the sampling keep the live register set inside the 80-register budget of 3 blocks / SM
-  // (the straight-line form measured 0.329 -> 0.350 ms there).
-  if constexpr (INTERP == MRF_INTERP_LINEAR) {
-    // The loop body is one straight line: geometry, window test, 16 taps, residual, rho -- computed for
-    // every label whether or not the sample will be used (an unused sample reads a harmless address),
-    // and selected at the end; the rare cases (pole / degenerate operands, footprints at the image border
-    // or outside the staged window) are patched up afterwards in one cold branch.  No branch inside the
-    // hot code means the compiler can overlap the fp64 chains with the shared-memory gathers.
-    const double inside_hi_x = a.wm1, inside_hi_y = a.hm1;
-    const bool warp_dead = __all_sync(__activemask(), dead);  // e.g. inside a non-rigid region: nothing to sample
-    for (int l = 0; l < L; ++l, cost_off += cost_step) {
-      if (warp_dead) {                                        // warp-uniform
-        if (LAYOUT == MRF_LAYOUT_LHW_F32) __stcs((float*)(cost_p + cost_off), cost_dead);
-        else *(int32_t*)(cost_p + cost_off) = (int32_t)(cost_dead * a.i32_scale);
-        if (l == 0) { best = cost_dead; best_l = 0; }
-        continue;
-      }
-      double ab, dl, rdl;
-      asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(ab), "=d"(dl) : "r"(lab_s + (uint32_t)l * 32u));
-      asm volatile("ld.shared.f64 %0, [%1];" : "=d"(rdl) : "r"(lab_s + (uint32_t)l * 32u + 16u));
-      // r = A*B*n / (B*A/mu - 1)  :221
-      const double r = div_rc(ab * n_fast, dl, rdl);
-      const double xn = xk + r * t1, yn = yk + r * t2;        // :224-235
-      // interpolate_through_H.py:31-35
-      const double den = (xn * a.H.m[6] + yn * a.H.m[7]) + a.H.m[8];
-      const double Xn = (xn * a.H.m[0] + yn * a.H.m[1]) + a.H.m[2];
-      const double Yn = (xn * a.H.m[3] + yn * a.H.m[4]) + a.H.m[5];
-      const double rd = rcp_rn_tame(den);
-      const double X = div_rc(Xn, den, rd);
-      const double Y = div_rc(Yn, den, rd);
-      // every condition under which the sequences above are not proven exact ends in a NaN or wild den
-      const bool exact = tame_divisor(den);
-      const bool inside = (X >= 0.0) && (X <= inside_hi_x) && (Y >= 0.0) && (Y <= inside_hi_y);   // :39
-      const float xf = (float)X, yf = (float)Y;               // interpolation.py:77-78
-      // cv2.remap's quantisation; inside the frame |coord*32| < 2^31 and the int16 saturation cannot
-      // trigger for any position the window test below accepts (garbage otherwise, never used)
-      const int sx = __float2int_rn(xf * 32.0f), sy = __float2int_rn(yf * 32.0f);
-      const int ix0 = (sx >> 5) - kOff, iy0 = (sy >> 5) - kOff;
-      const bool inwin = (unsigned)(ix0 - fx_lo) <= (unsigned)fx_span && (unsigned)(iy0 - fy_lo) <= (unsigned)fy_span;
-      const bool fast = exact && inside && inwin && !dead;
-      const uint32_t p0 = fast ? (win_s + (uint32_t)iy0 * pitch + (uint32_t)ix0 * 16u) : win_base;
-      float wxa[4], wya[4];
-      lds128(wt_s + (uint32_t)(sx & 31) * 16u, wxa[0], wxa[1], wxa[2], wxa[3]);
-      lds128(wt_s + (uint32_t)(sy & 31) * 16u, wya[0], wya[1], wya[2], wya[3]);
-      F3 J;
-  #pragma unroll
-      for (int j = 0; j < kTaps; ++j) {
-        F3 row;
-  #pragma unroll
-        for (int i = 0; i < kTaps; ++i) {
-          const float wgt = wya[j] * wxa[i];
-          float tx, ty, tz, tw;
-          lds128(p0 + (uint32_t)j * pitch + (uint32_t)i * 16u, tx, ty, tz, tw);
-          const float px = tx * wgt, py = ty * wgt, pz = tz * wgt;
-          if (INTERP == MRF_INTERP_CUBIC) {                   // row sums, then rows
-            if (i == 0) { row.x = px; row.y = py; row.z = pz; }
-            else        { row.x = row.x + px; row.y = row.y + py; row.z = row.z + pz; }
-          } else {                                            // linear: one running sum
-            if (i == 0 && j == 0) { J.x = px; J.y = py; J.z = pz; }
-            else { J.x = J.x + px; J.y = J.y + py; J.z = J.z + pz; }
-          }
-        }
-        if (INTERP == MRF_INTERP_CUBIC) {
-          if (j == 0) J = row;
-          else { J.x = J.x + row.x; J.y = J.y + row.y; J.z = J.z + row.z; }
-        }
-      }
+  // Two forms of the label loop with identical arithmetic.  Grouped (FORM 2; bilinear): labels two at a time,
+  // every phase one branch-free straight line over both, so the compiler overlaps the fp64 chains with each
+  // other and with the gathers (bilinear, 4 taps: 0.207 -> 0.190 ms per frame at Sintel size).  Branching
+  // (FORM 0; bicubic): one label at a time, branches round the sampling.  The bicubic kernel is co-limited by
+  // instruction issue and shared-memory wavefronts (16 x LDS.128 per sample); the grouped form executes 6 %
+  // fewer instructions there and halves the `wait` stalls, but its back-to-back gathers of two labels raise
+  // the shared-memory stalls by more: 0.363 against 0.330 ms (profiles/r4a_kernel_forms.jsonl, r4b_*).
+  if constexpr (FORM == 2) {
+    // Grouped form: labels two at a time, three branch-free phases per pair (see sample_code above).
+    const unsigned full = __activemask();
+    const bool warp_dead = __all_sync(full, dead);            // e.g. inside a non-rigid region: nothing to sample
+    WinGeom wg;
+    wg.fx_lo = fx_lo; wg.fy_lo = fy_lo; wg.fx_span = fx_span; wg.fy_span = fy_span;
+    wg.win_s = win_s; wg.win_base = win_base; wg.pitch = pitch; wg.wt_s = wt_s;
+    auto body = [&](auto gc, int l) {
+      constexpr int G = decltype(gc)::value;
+      SampleCode sc[G];
+#pragma unroll
+      for (int g = 0; g < G; ++g)
+        sample_code<INTERP>(a, lab_s + (uint32_t)(l + g) * 32u, n_fast, xk, yk, t1, t2, wg, dead, sc[g]);
+      F3 J[G];
+#pragma unroll
+      for (int g = 0; g < G; ++g) J[g] = window_taps<INTERP>(sc[g], pitch);
       double r0, r1, r2;                                      // reference-frame channels of this pixel
       asm volatile("ld.shared.f64 %0, [%1];" : "=d"(r0) : "r"(ref_s));
       asm volatile("ld.shared.f64 %0, [%1];" : "=d"(r1) : "r"(ref_s + (uint32_t)(kThreads * 8)));
       asm volatile("ld.shared.f64 %0, [%1];" : "=d"(r2) : "r"(ref_s + (uint32_t)(kThreads * 16)));
-      const double e0 = ((double)J.x - r0) * a.cw0;           // :274
-      const double e1 = ((double)J.y - r1) * a.cw1;
-      const double e2 = ((double)J.z - r2) * a.cw2;
-      const double Iz = div_rc((e0 + e1) + e2, 3.0, kThird);  // .mean(axis=2): sum / 3.0, exact
-      double cst;
-      if (lor_fast) {
-        const double z = div_rc(Iz * Iz, a.s2, a.rs2);        // x / sigma**2  :52
-        cst = log_ge1(1.0 + z);
+      double Iz[G], cst[G];
+#pragma unroll
+      for (int g = 0; g < G; ++g) {
+        const double e0 = ((double)J[g].x - r0) * a.cw0;      // :274
+        const double e1 = ((double)J[g].y - r1) * a.cw1;
+        const double e2 = ((double)J[g].z - r2) * a.cw2;
+        Iz[g] = div_rc((e0 + e1) + e2, 3.0, kThird);          // .mean(axis=2): sum / 3.0, exact
+      }
+      if (lor_unit) {
+#pragma unroll
+        for (int g = 0; g < G; ++g) cst[g] = log_ge1(1.0 + Iz[g] * Iz[g]);                        // :52, sigma = 1
+      } else if (lor_fast) {
+#pragma unroll
+        for (int g = 0; g < G; ++g) cst[g] = log_ge1(1.0 + div_rc(Iz[g] * Iz[g], a.s2, a.rs2));   // :52
       } else {
-        cst = (a.rho == MRF_RHO_NONE) ? Iz : rho_eval(a.rho, Iz * Iz, a.rho_param);   // :302
+#pragma unroll
+        for (int g = 0; g < G; ++g)
+          cst[g] = (a.rho == MRF_RHO_NONE) ? Iz[g] : rho_eval(a.rho, Iz[g] * Iz[g], a.rho_param);  // :302
       }
-      float cf = fast ? (float)cst : cost_dead;
-      if (!fast && !dead && (!exact || inside)) {
-        // cold: inexact-sequence operands, or a footprint at the image border / outside the window
-        cf = exact ? band_sample_cost<INTERP>(a, xf, yf, r0, r1, r2)
-                   : slow_sample_cost<INTERP>(a, ab, dl, n, xk, yk, t1, t2, r0, r1, r2);
+      float cf[G];
+      bool any_cold = false;
+#pragma unroll
+      for (int g = 0; g < G; ++g) { cf[g] = sc[g].fast ? (float)cst[g] : cost_dead; any_cold = any_cold || sc[g].cold; }
+      if (any_cold) {                                         // rare: pole / degenerate operands, window or border miss
+#pragma unroll
+        for (int g = 0; g < G; ++g)
+          if (sc[g].cold) cf[g] = cold_cost<INTERP>(a, lab_s + (uint32_t)(l + g) * 32u, n, xk, yk, t1, t2, ref_s, cost_dead);
       }
-      if (LAYOUT == MRF_LAYOUT_LHW_F32) __stcs((float*)(cost_p + cost_off), cf);
-      else *(int32_t*)(cost_p + cost_off) = (int32_t)(cf * a.i32_scale);
-      if (l == 0 || cf < best) { best = cf; best_l = l; }     // np.argmin: first minimum
-    }
-  } else if constexpr (WF) {
-    // Bicubic, warp-uniform form.  Geometry for every lane (a dead lane -- non-rigid / occluded pixel -- computes
-    // along and is discarded at the end); if EVERY lane of the warp is either dead or has an exact, in-frame,
-    // in-window sample -- the overwhelmingly common case -- the 16-tap gather, residual and rho run as one
-    // straight line under a warp-uniform branch: no divergence bookkeeping, and the compiler is free to overlap
-    // the gathers of this label with the fp64 tail.  Otherwise the warp takes the general per-lane form for this
-    // label.  Same operations in the same order on every path.
-    const unsigned full = __activemask();
-    const bool warp_dead = __all_sync(full, dead);            // nothing to sample (and, unstaged, no window to read)
-    for (int l = 0; l < L; ++l, cost_off += cost_step) {
-      double ab, dl, rdl;
-      asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(ab), "=d"(dl) : "r"(lab_s + (uint32_t)l * 32u));
-      asm volatile("ld.shared.f64 %0, [%1];" : "=d"(rdl) : "r"(lab_s + (uint32_t)l * 32u + 16u));
-      const double r = div_rc(ab * n_fast, dl, rdl);          // r = A*B*n / (B*A/mu - 1)  :221
-      const double xn = xk + r * t1, yn = yk + r * t2;        // :224-235
-      const double den = (xn * a.H.m[6] + yn * a.H.m[7]) + a.H.m[8];   // interpolate_through_H.py:31-35
-      const double Xn = (xn * a.H.m[0] + yn * a.H.m[1]) + a.H.m[2];
-      const double Yn = (xn * a.H.m[3] + yn * a.H.m[4]) + a.H.m[5];
-      const double rd = rcp_rn_tame(den);
-      const double X = div_rc(Xn, den, rd);
-      const double Y = div_rc(Yn, den, rd);
-      const bool exact = tame_divisor(den);
-      const bool inside = (X >= 0.0) && (X <= a.wm1) && (Y >= 0.0) && (Y <= a.hm1);   // :39
-      const float xf = (float)X, yf = (float)Y;               // interpolation.py:77-78
-      const int sx = __float2int_rn(xf * 32.0f), sy = __float2int_rn(yf * 32.0f);
-      const int ix0 = (sx >> 5) - kOff, iy0 = (sy >> 5) - kOff;
-      const bool inwin = (unsigned)(ix0 - fx_lo) <= (unsigned)fx_span && (unsigned)(iy0 - fy_lo) <= (unsigned)fy_span;
-      const bool ok = exact && inside && inwin;
-      float cf;
-      if (!warp_dead && __all_sync(full, ok || dead)) {
-        const uint32_t p0 = ok ? (win_s + (uint32_t)iy0 * pitch + (uint32_t)ix0 * 16u) : win_base;
-        float wxa[4], wya[4];
-        lds128(wt_s + (uint32_t)(sx & 31) * 16u, wxa[0], wxa[1], wxa[2], wxa[3]);
-        lds128(wt_s + (uint32_t)(sy & 31) * 16u, wya[0], wya[1], wya[2], wya[3]);
-        F3 J;
-  #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          F3 row;
-  #pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const float wgt = wya[j] * wxa[i];
-            float tx, ty, tz, tw;
-            lds128(p0 + (uint32_t)j * pitch + (uint32_t)i * 16u, tx, ty, tz, tw);
-            const float px = tx * wgt, py = ty * wgt, pz = tz * wgt;
-            if (i == 0) { row.x = px; row.y = py; row.z = pz; }
-            else        { row.x = row.x + px; row.y = row.y + py; row.z = row.z + pz; }
-          }
-          if (j == 0) J = row;
-          else { J.x = J.x + row.x; J.y = J.y + row.y; J.z = J.z + row.z; }
-        }
-        double r0, r1, r2;                                    // reference-frame channels of this pixel
-        asm volatile("ld.shared.f64 %0, [%1];" : "=d"(r0) : "r"(ref_s));
-        asm volatile("ld.shared.f64 %0, [%1];" : "=d"(r1) : "r"(ref_s + (uint32_t)(kThreads * 8)));
-        asm volatile("ld.shared.f64 %0, [%1];" : "=d"(r2) : "r"(ref_s + (uint32_t)(kThreads * 16)));
-        const double e0 = ((double)J.x - r0) * a.cw0;         // :274
-        const double e1 = ((double)J.y - r1) * a.cw1;
-        const double e2 = ((double)J.z - r2) * a.cw2;
-        const double Iz = div_rc((e0 + e1) + e2, 3.0, kThird);
-        double cst;
-        if (lor_fast) cst = log_ge1(1.0 + div_rc(Iz * Iz, a.s2, a.rs2));
-        else cst = (a.rho == MRF_RHO_NONE) ? Iz : rho_eval(a.rho, Iz * Iz, a.rho_param);
-        cf = dead ? cost_dead : (float)cst;
-      } else {
-        cf = cost_dead;
-        if (!dead) {
-          const double r0 = s_ref[0][threadIdx.x], r1 = s_ref[1][threadIdx.x], r2 = s_ref[2][threadIdx.x];
-          if (!exact) cf = slow_sample_cost<INTERP>(a, ab, dl, n, xk, yk, t1, t2, r0, r1, r2);
-          else if (inside) cf = band_sample_cost<INTERP>(a, xf, yf, r0, r1, r2);   // global gather (window or border miss)
-        }
+#pragma unroll
+      for (int g = 0; g < G; ++g) {
+        if (LAYOUT == MRF_LAYOUT_LHW_F32) __stcs((float*)(cost_p + cost_off), cf[g]);
+        else *(int32_t*)(cost_p + cost_off) = (int32_t)(cf[g] * a.i32_scale);
+        cost_off += cost_step;
+        if ((g == 0 && l == 0) || cf[g] < best) { best = cf[g]; best_l = l + g; }   // np.argmin: first minimum
       }
-      if (LAYOUT == MRF_LAYOUT_LHW_F32) __stcs((float*)(cost_p + cost_off), cf);
-      else *(int32_t*)(cost_p + cost_off) = (int32_t)(cf * a.i32_scale);
-      if (l == 0 || cf < best) { best = cf; best_l = l; }     // np.argmin: first minimum
+    };
+    if (warp_dead) {
+      for (int l = 0; l < L; ++l, cost_off += cost_step) {
+        if (LAYOUT == MRF_LAYOUT_LHW_F32) __stcs((float*)(cost_p + cost_off), cost_dead);
+        else *(int32_t*)(cost_p + cost_off) = (int32_t)(cost_dead * a.i32_scale);
+      }
+      best = cost_dead; best_l = 0;
+    } else {
+      constexpr int G = (INTERP == MRF_INTERP_LINEAR) ? MRF_GROUP_LINEAR : 2;
+      int l = 0;
+      for (; l + G <= L; l += G) body(IntC<G>{}, l);
+      for (; l < L; ++l) body(IntC<1>{}, l);
     }
   } else {
     for (int l = 0; l < L; ++l, cost_off += cost_step) {
@@ -700,7 +711,9 @@ k_cost_volume(const __grid_constant__ CVArgs a0, const __grid_constant__ CVArgs 
           const double e2 = ((double)J.z - r2) * a.cw2;
           const double Iz = div_rc((e0 + e1) + e2, 3.0, kThird);   // .mean(axis=2): sum / 3.0, exact
           double cst;
-          if (lor_fast) {
+          if (lor_unit) {
+            cst = log_ge1(1.0 + Iz * Iz);                     // sigma = 1: x / sigma**2 == x exactly  :52
+          } else if (lor_fast) {
             const double z = div_rc(Iz * Iz, a.s2, a.rs2);    // x / sigma**2  :52
             cst = log_ge1(1.0 + z);
           } else {
@@ -716,6 +729,22 @@ k_cost_volume(const __grid_constant__ CVArgs a0, const __grid_constant__ CVArgs 
   }
   if (a.min_cost) a.min_cost[pix] = best;
   if (a.argmin) a.argmin[pix] = best_l;
+}
+
+template <int INTERP, bool STAGED, int OCC, int LAYOUT, int FORM>
+__global__ void __launch_bounds__(kThreads, OCC)
+k_cost_volume(const __grid_constant__ CVArgs a0, const __grid_constant__ CVArgs a1) {
+  // blockIdx.z selects the neighbour frame: both frames of a triplet share one grid, so the tail of one
+  // frame's blocks overlaps the head of the other's (grid.z = 1: a0 only)
+  extern __shared__ __align__(128) unsigned char dyn_smem[];
+  if constexpr (FORM == 2) {
+    // one copy of the body per argument block: every per-frame scalar (H, the frame bounds, the channel
+    // weights) is then a constant-bank operand of the instruction that uses it -- no loads, no registers
+    if (blockIdx.z == 0) cost_volume_block<INTERP, STAGED, LAYOUT, FORM>(a0, dyn_smem);
+    else cost_volume_block<INTERP, STAGED, LAYOUT, FORM>(a1, dyn_smem);
+  } else {
+    cost_volume_block<INTERP, STAGED, LAYOUT, FORM>((blockIdx.z == 0) ? a0 : a1, dyn_smem);
+  }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -841,7 +870,10 @@ static int cv_launch(const mrf_costvol_params* p, const CVArgs& a, const CVArgs&
   const dim3 grid(cdiv(p->w, kTX), cdiv(p->rows, kTY), (unsigned)nz);
   const bool staged = ((p->variant & 1) != MRF_VARIANT_GATHER);
   const int occ = (p->variant & MRF_VARIANT_OCC2) ? 2 : ((p->variant & MRF_VARIANT_OCC4) ? 4 : 3);
-  const bool wf = (p->variant & MRF_VARIANT_WARPFAST) != 0;
+  // the grouped form takes its samples from the staged window; it is the default for bilinear sampling
+  // (MRF_VARIANT_SINGLE selects the one-label form) and opt-in for bicubic (MRF_VARIANT_GROUPED)
+  const bool grouped = (p->interp == MRF_INTERP_LINEAR) ? !(p->variant & MRF_VARIANT_SINGLE) : (p->variant & MRF_VARIANT_GROUPED) != 0;
+  const int form = (grouped && staged) ? 2 : 0;
   const size_t smem = staged ? (size_t)a.win_cap * 16 : 0;
   cudaError_t e = cudaSuccess;
 #define MRF_LAUNCH(I, ST, OC, LY, WFv)                                                                         \
@@ -860,8 +892,13 @@ static int cv_launch(const mrf_costvol_params* p, const CVArgs& a, const CVArgs&
 #define MRF_LAUNCH_LY(I, ST, OC, WFv) do { if (p->layout == MRF_LAYOUT_LHW_F32) MRF_LAUNCH(I, ST, OC, MRF_LAYOUT_LHW_F32, WFv); else MRF_LAUNCH(I, ST, OC, MRF_LAYOUT_HWL_I32, WFv); } while (0)
 #define MRF_LAUNCH_ST(I, OC, WFv) do { if (staged) MRF_LAUNCH_LY(I, true, OC, WFv); else MRF_LAUNCH_LY(I, false, OC, WFv); } while (0)
 #define MRF_LAUNCH_OC(I, WFv) do { if (occ == 2) MRF_LAUNCH_ST(I, 2, WFv); else if (occ == 4) MRF_LAUNCH_ST(I, 4, WFv); else MRF_LAUNCH_ST(I, 3, WFv); } while (0)
-  if (p->interp == MRF_INTERP_CUBIC) { if (wf) MRF_LAUNCH_OC(MRF_INTERP_CUBIC, true); else MRF_LAUNCH_OC(MRF_INTERP_CUBIC, false); }
-  else MRF_LAUNCH_OC(MRF_INTERP_LINEAR, false);
+#define MRF_LAUNCH_G(I) do { if (occ == 2) MRF_LAUNCH_LY(I, true, 2, 2); else if (occ == 4) MRF_LAUNCH_LY(I, true, 4, 2); else MRF_LAUNCH_LY(I, true, 3, 2); } while (0)
+  if (p->interp == MRF_INTERP_CUBIC) {
+    if (form == 2) MRF_LAUNCH_G(MRF_INTERP_CUBIC); else MRF_LAUNCH_OC(MRF_INTERP_CUBIC, 0);
+  } else {
+    if (form == 2) MRF_LAUNCH_G(MRF_INTERP_LINEAR); else MRF_LAUNCH_OC(MRF_INTERP_LINEAR, 0);
+  }
+#undef MRF_LAUNCH_G
 #undef MRF_LAUNCH_LY
 #undef MRF_LAUNCH_OC
 #undef MRF_LAUNCH_ST

@@ -49,8 +49,6 @@ def main():
         for variant in sorted(_lib.VARIANT, key=lambda k: _lib.VARIANT[k]):
             if names and variant not in names:
                 continue
-            if interp == "linear" and "warpfast" in variant:
-                continue
             for f in (1,):
                 def run():
                     return device.cost_volume(ref64, tex[f], None, H_ar[f], q_ar[f], 0.0, 0.0, nonrigid=nonrigid, interp=interp,

@@ -90,14 +90,6 @@ struct FetchBand {   // neighbour texels in global memory, band rows nb_y0 .. nb
     F3 r; r.x = t.x; r.y = t.y; r.z = t.z; return r;
   }
 };
-struct FetchWin {    // staged window in shared memory
-  const float4* win; int ww; int wx0; int wy0;
-  __device__ __forceinline__ F3 operator()(int yy, int xx) const {
-    const float4 t = win[(yy - wy0) * ww + (xx - wx0)];
-    F3 r; r.x = t.x; r.y = t.y; r.z = t.z; return r;
-  }
-};
-
 template <int INTERP, class Fetch>
 __device__ __forceinline__ F3 sample(const Fetch& f, int h, int w, float xf, float yf) {
   if (INTERP == MRF_INTERP_CUBIC) return sample_cubic(f, h, w, xf, yf);

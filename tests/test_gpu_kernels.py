@@ -522,6 +522,55 @@ def test_device_side_median_and_label_range(dev, n):
     assert np.isnan(state[_lib.STATE_LABELS:_lib.STATE_LABELS + 51].cpu().numpy()).all()
 
 
+@pytest.mark.parametrize("n", [0, 1, 2, 3, 255, 256, 257, 4097, 300001, 446464])
+@pytest.mark.parametrize("kind", ["normal", "dups", "alldup", "zeros", "nan", "wide", "binade", "binade_big", "inf"])
+def test_median_adversarial(dev, n, kind):
+    """The exact device-side median against numpy.median on inputs that stress a radix select: one repeated value,
+    mostly exact zeros (a masked residual plane), a few thousand or all keys sharing 25 leading bits (every digit is
+    needed), wide dynamic range, signed zeros, NaNs, infinities; and the state words the row-band protocol exchanges."""
+    import ctypes as C
+    import torch
+    from mrflow_b200 import _lib
+    L = _lib.lib()
+    rs = np.random.RandomState(11 * n + len(kind))
+    x = rs.standard_normal(n) * (10.0 ** rs.randint(-8, 9, n) if kind == "wide" else 3.0)
+    if kind == "dups" and n > 2:
+        x[rs.randint(0, n, n // 2)] = 1.25
+        x[:2] = [0.0, -0.0]
+    if kind == "alldup":
+        x[:] = -7.5
+    if kind == "zeros" and n > 2:                 # the |Iz| planes of the auto-sigma mode: mostly exact zeros
+        x = np.abs(x); x[rs.rand(n) < 0.7] = 0.0
+    if kind == "nan" and n > 2:
+        x[n // 2] = np.nan
+    if kind == "binade" and n > 8:                # the median's class: <= 2000 keys sharing 25 bits -> radix over the list
+        d = min(n // 2, 2000)
+        lo = (n - d) // 2
+        x = np.concatenate([-1.0 - np.abs(x[:lo]), 1.0 + rs.rand(d) * 1e-9, 5.0 + np.abs(x[lo + d:])])
+        rs.shuffle(x)
+    if kind == "binade_big":                      # ... for all keys: the class cannot be gathered
+        x = 1.0 + rs.rand(n) * 1e-9
+    if kind == "inf" and n > 3:
+        x[0] = np.inf; x[1] = -np.inf; x[2] = np.inf
+    cap = n + 7
+    keys = cu(np.concatenate([x, np.full(7, 123.0)]))
+    cnt = torch.tensor([n], dtype=torch.int32, device="cuda")
+    P = lambda t: C.c_void_p(t.data_ptr())
+    st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    out = torch.zeros(1, dtype=torch.float64, device="cuda")
+    scr = torch.zeros(L.mrf_select_scratch_bytes(0), dtype=torch.uint8, device="cuda")
+    _lib.check(L.mrf_select_median_dev(P(keys), P(cnt), cap, P(out), P(scr), st), "median_dev")
+    got = float(out.cpu()[0])
+    with np.errstate(invalid="ignore"):
+        want = np.median(x) if n else np.nan
+    assert (np.isnan(got) and np.isnan(want)) or got == want, (got, want)
+    if n and not np.isnan(want):
+        w = scr.view(torch.int64)[:8].cpu().numpy()
+        xs = np.sort(x)
+        k = (n - 1) // 2
+        assert int(w[6]) == n and int(w[3]) == 0 and int(w[4]) == int((x <= xs[k]).sum())
+
+
 @pytest.mark.parametrize("n", [0, 1, 2, 3, 4097, 300001])
 @pytest.mark.parametrize("kind", ["normal", "dups", "nan", "wide"])
 def test_select13_sharded_steps(dev, n, kind):

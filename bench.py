@@ -376,7 +376,7 @@ def run_ours(args):
     try:
         tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
         traffic = tj.get(workload_name(args, hw))
-        traffic_src = tj.get("_capture")
+        traffic_src = tj.get("_captures", {}).get(workload_name(args, hw)) or tj.get("_capture")
         inst = tj.get("_inst_executed", {}).get(workload_name(args, hw))
     except Exception:   # noqa: BLE001
         pass

@@ -56,6 +56,8 @@ def main():
     d["_source"] = d.get("_source", {})
     d["_source"][workload] = "%s (ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum, mean of %d launches)" % (tag, len(rows) - 2)
     d["_capture"] = "profiles/%s_costvol_metrics.csv (ncu --set full --clock-control none, round 2 final kernel: one launch = both neighbour frames)" % tag
+    d["_captures"] = d.get("_captures", {})
+    d["_captures"][workload] = d["_capture"]
     ie = hdr.index("smsp__inst_executed.sum")
     d["_inst_executed"] = d.get("_inst_executed", {})
     d["_inst_executed"][workload] = sum(float(r[ie].replace(",", "")) for r in rows[2:]) / (len(rows) - 2)

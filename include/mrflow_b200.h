@@ -429,6 +429,11 @@ int mrf_flow_consistency(const float* uf0, const float* vf0, const float* ub0, c
                          const float* uf1, const float* vf1, const float* ub1, const float* vb1,
                          int h, int w, double threshold, uint8_t* occ_backward, uint8_t* occ_forward,
                          uint8_t* occ_both, mrf_stream_t stream);
+/* utils/flow_io.py:33-48 (flow_read), the payload half: file_dev = the WHOLE .flo file as it lies on disk, copied to
+ * device memory (4-byte aligned): 12-byte header (fp32 tag 202021.25, int32 width, int32 height -- validate it on the
+ * host, as mrflow_b200.utils.flow_io.flow_read does), then height*width interleaved (u, v) fp32 pairs.  u, v: fp32
+ * [h,w] planes, bit copies of the payload. */
+int mrf_flo_decode(const void* file_dev, size_t file_bytes, int h, int w, float* u, float* v, mrf_stream_t stream);
 /* rigidity/inference.py:140-167 (get_image_weights): I fp64 [h,w,c]; four fp32 [h,w] planes in the
  * reference's return order (horizontal, vertical, ne, se), ready for Eff_TRWS.solve
  * (extern/eff_trws/eff_trws.pyx:25-53).  scratch: mrf_image_weights_scratch_bytes() bytes. */

@@ -115,6 +115,7 @@ SIGNATURES = {
     "mrf_select_median_dev": (_I, [_P, _P, _Z, _P, _P, _P]),
     "mrf_label_range_dev": (_I, [_P, _I, _P, _I, _P, _P]),
     "mrf_flow_consistency": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _D, _P, _P, _P, _P]),
+    "mrf_flo_decode": (_I, [_P, _Z, _I, _I, _P, _P, _P]),
     "mrf_image_weights_scratch_bytes": (_Z, []),
     "mrf_image_weights": (_I, [_P, _I, _I, _I, _P, _P, _P, _P, _P, _P]),
     "mrf_derivs_through_H": (_I, [_P, _I, _I, _I, _DP, _DP, _I, _P, _P, _P]),

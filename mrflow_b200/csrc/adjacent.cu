@@ -3,7 +3,9 @@
 //     `occlusions` input: two bilinear cv2.remap calls (default BORDER_CONSTANT) per direction, an
 //     fp32 consistency error, threshold, and the invalid-region bookkeeping;
 //   * rigidity/inference.py:140-167 get_image_weights -- the contrast-sensitive 8-neighbourhood
-//     weights the MRF consumer (extern/eff_trws) takes next to the int32 unaries.
+//     weights the MRF consumer (extern/eff_trws) takes next to the int32 unaries;
+//   * utils/flow_io.py:33-48 flow_read -- the .flo payload (interleaved u, v) split into the two fp32 planes the
+//     path takes, so a flow file goes host -> HBM as it lies on disk.
 // Streaming kernels, one thread per pixel, coalesced along x.
 #include "sampling.cuh"
 
@@ -149,6 +151,18 @@ k_image_weights(const double* __restrict__ I, int h, int w, int c, const double*
   w_se[i] = (float)exp(-(d[3] * d[3]) * beta[3]);
 }
 
+
+// utils/flow_io.py:44-46: tmp = payload.reshape(h, 2 w); u = tmp[:, 0::2]; v = tmp[:, 1::2].  The payload starts 12 bytes
+// into the file, so it is only 4-byte aligned: one fp32 pair per thread as two 4-byte loads (the pair's 8 bytes are
+// contiguous, a warp reads 256 contiguous bytes), planes written coalesced.
+__global__ void __launch_bounds__(256)
+k_flo_decode(const float* __restrict__ payload, long long n, float* __restrict__ u, float* __restrict__ v) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    u[i] = payload[2 * i];
+    v[i] = payload[2 * i + 1];
+  }
+}
+
 }  // namespace mrf
 
 using namespace mrf;
@@ -181,6 +195,17 @@ int mrf_image_weights(const double* I, int h, int w, int c, float* w_horizontal,
   dim3 grid(cdiv(w, 32), cdiv(h, 8));
   k_image_weights<<<grid, 256, 0, S(stream)>>>(I, h, w, c, beta, w_horizontal, w_vertical, w_ne, w_se);
   return check_launch("mrf_image_weights/exp");
+}
+
+int mrf_flo_decode(const void* file_dev, size_t file_bytes, int h, int w, float* u, float* v, mrf_stream_t stream) {
+  MRF_CHECK_ARG(file_dev && u && v && h > 0 && w > 0);
+  MRF_CHECK_ARG(((uintptr_t)file_dev & 3) == 0);
+  const long long n = (long long)h * w;
+  MRF_CHECK_ARG(file_bytes >= 12 + (size_t)n * 8);                       /* header + h*w (u, v) pairs */
+  const float* payload = reinterpret_cast<const float*>(static_cast<const char*>(file_dev) + 12);
+  const long long b = (n + 255) / 256;
+  k_flo_decode<<<(unsigned)(b < (long long)kSMs * 8 ? b : (long long)kSMs * 8), 256, 0, S(stream)>>>(payload, n, u, v);
+  return check_launch("mrf_flo_decode");
 }
 
 }  // extern "C"

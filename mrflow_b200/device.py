@@ -504,6 +504,16 @@ def flow_consistency(flow, backflow, threshold):
     return tuple(outs)
 
 
+def flo_decode(file_bytes_dev, h, w):
+    """utils/flow_io.py:44-46 on the device: the whole .flo file as a uint8 CUDA tensor -> (u, v) fp32 [h,w]."""
+    _chk(file_bytes_dev, U8, "file")
+    u = torch.empty((h, w), dtype=F32, device=file_bytes_dev.device)
+    v = torch.empty((h, w), dtype=F32, device=file_bytes_dev.device)
+    check(_lib.lib().mrf_flo_decode(_p(file_bytes_dev), file_bytes_dev.numel(), int(h), int(w), _p(u), _p(v), _stream()),
+          "mrf_flo_decode")
+    return u, v
+
+
 def image_weights(I):
     """rigidity/inference.py:140-167.  I fp64 [h,w,c] (or [h,w]).  Returns (w_horizontal, w_vertical, w_ne,
     w_se) fp32 [h,w]."""

@@ -556,3 +556,17 @@ def compute_data_term(A, I1, I2, rigidity, occlusions, H, B, mu, q, kind="lorent
     if return_intermediates:
         return diag_m, b_m, E, dict(Iz=Iz, dphi=dphi, dr_da=dr_da, psi=psi, diag=diag, b=b)
     return diag_m, b_m, E
+
+
+def flow_read(filename):
+    """utils/flow_io.py:33-48 (flow_read): tag, width, height, then height x (2 width) fp32 with u in the even and v
+    in the odd columns.  Same assertions."""
+    with open(filename, "rb") as f:
+        check = np.fromfile(f, dtype=np.float32, count=1)[0]
+        assert check == 202021.25, " flow_read:: Wrong tag in flow file"                        # :38-39
+        width = np.fromfile(f, dtype=np.int32, count=1)[0]
+        height = np.fromfile(f, dtype=np.int32, count=1)[0]
+        size = int(width) * int(height)
+        assert width > 0 and height > 0 and size > 1 and size < 100000000                       # :43
+        tmp = np.fromfile(f, dtype=np.float32, count=-1).reshape((height, width * 2))           # :44
+    return tmp[:, np.arange(width) * 2], tmp[:, np.arange(width) * 2 + 1]                       # :45-46

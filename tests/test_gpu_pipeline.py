@@ -520,3 +520,40 @@ def test_pipelined_host_call_equals_resident_pass(trip, layout):
         assert np.array_equal(host[1][f], dev[1][f].cpu().numpy(), equal_nan=True)
     assert host[2] == dev[2] and host[3] == dev[3] and np.array_equal(host[5], dev[5])
     assert all(np.array_equal(a, b) for a, b in zip(host[4], dev[4]))
+
+
+@pytest.mark.gpu
+def test_flo_decode_against_reference(tmp_path):
+    """utils/flow_io.py:33-48: mrflow_b200.utils.flow_io.flow_read (the file goes to HBM as it lies on disk, the planes
+    are split by mrf_flo_decode) against what the reference's own flow_read returned for the stored file, bit for bit;
+    a round trip through flow_write at the Sintel size; the reference's two assertions."""
+    import os
+    import torch
+    from conftest import GOLDEN
+    from mrflow_b200.utils import flow_io
+    g = np.load(os.path.join(GOLDEN, "ref_flo.npz"))
+    name = str(tmp_path / "a.flo")
+    g["flo"].tofile(name)
+    u, v = flow_io.flow_read(name)
+    assert u.dtype == np.float32 and u.shape == g["u"].shape
+    assert np.array_equal(u.view(np.uint32), g["u"].view(np.uint32)) and np.array_equal(v.view(np.uint32), g["v"].view(np.uint32))
+    ud, vd = flow_io.flow_read(name, device_out=True)
+    assert ud.is_cuda and vd.is_cuda
+    assert np.array_equal(ud.cpu().numpy().view(np.uint32), g["u"].view(np.uint32))
+    rs = np.random.RandomState(5)
+    U, V = rs.standard_normal((436, 1024)).astype(np.float32), rs.standard_normal((436, 1024)).astype(np.float32)
+    big = str(tmp_path / "b.flo")
+    flow_io.flow_write(big, U, V)
+    u2, v2 = flow_io.flow_read(big)
+    assert np.array_equal(u2, U) and np.array_equal(v2, V)
+    from oracle import hotpath as hp
+    u3, v3 = hp.flow_read(big)                                  # the writer's file is one the reference layout reads
+    assert np.array_equal(u3, U) and np.array_equal(v3, V)
+    bad = g["flo"].copy(); bad[0] ^= 1
+    bad.tofile(name)
+    with pytest.raises(AssertionError):
+        flow_io.flow_read(name)
+    short = g["flo"][:-8]
+    short.tofile(name)
+    with pytest.raises(AssertionError):
+        flow_io.flow_read(name)

@@ -246,13 +246,22 @@ __device__ __noinline__ float slow_sample_cost(const CVArgs& a, double ab, doubl
 
 // A sample with exact coordinates whose footprint touches the image border or leaves the staged
 // window: global-memory gather (for row-band inputs with the halo check), then the same residual / rho.
+struct WinRef { const int* s_win; uint32_t win_s, pitch, wt_s; };   // the staged window (s_win = nullptr: none)
+template <int INTERP> __device__ F3 sample_window_border(uint32_t win_s, uint32_t pitch, uint32_t wt_s, int w, int frame_h, int sx, int sy);
+template <int INTERP> __device__ __forceinline__ bool border_in_window(const int* s_win, int w, int frame_h, int sx, int sy);
+
 template <int INTERP>
-__device__ __noinline__ float band_sample_cost(const CVArgs& a, float xf, float yf, double c0, double c1, double c2) {
+__device__ __noinline__ float band_sample_cost(const CVArgs& a, float xf, float yf, double c0, double c1, double c2,
+                                               const WinRef wr = WinRef{nullptr, 0u, 0u, 0u}) {
   int iy, fy; cv_quantise(yf, iy, fy);
   const int lo = (INTERP == MRF_INTERP_CUBIC) ? -1 : 0, hi = (INTERP == MRF_INTERP_CUBIC) ? 2 : 1;
   const int ya = max(0, min(a.frame_h - 1, iy + lo)), yb = max(0, min(a.frame_h - 1, iy + hi));
   F3 J;
-  if (ya < a.nb_y0 || yb > a.nb_y0 + a.nb_rows - 1) {
+  // an in-frame sample (the only kind that comes here): |coord * 32| < 2^31, the quantisation cannot saturate
+  const int sx = __float2int_rn(xf * 32.0f), sy = __float2int_rn(yf * 32.0f);
+  if (wr.s_win && border_in_window<INTERP>(wr.s_win, a.w, a.frame_h, sx, sy)) {
+    J = sample_window_border<INTERP>(wr.win_s, wr.pitch, wr.wt_s, a.w, a.frame_h, sx, sy);   // image border, staged taps
+  } else if (ya < a.nb_y0 || yb > a.nb_y0 + a.nb_rows - 1) {
     if (a.halo_miss) atomicAdd(a.halo_miss, 1);
     J.x = J.y = J.z = 0.f;
   } else {
@@ -350,7 +359,7 @@ __device__ __forceinline__ F3 window_taps(const SampleCode& s, uint32_t pitch) {
 // bits), then the plain-division path or the global-memory gather.  Cold.
 template <int INTERP>
 __device__ __noinline__ float cold_cost(const CVArgs& a, uint32_t lab_addr, double n, double xk, double yk, double t1,
-                                        double t2, uint32_t ref_s, float cost_dead) {
+                                        double t2, uint32_t ref_s, float cost_dead, const WinRef wr) {
   double ab, dl, rdl, r0, r1, r2;
   asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(ab), "=d"(dl) : "r"(lab_addr));
   asm volatile("ld.shared.f64 %0, [%1];" : "=d"(rdl) : "r"(lab_addr + 16u));
@@ -369,10 +378,54 @@ __device__ __noinline__ float cold_cost(const CVArgs& a, uint32_t lab_addr, doub
   const double Y = div_rc(Yn, den, rd);
   const bool inside = (X >= 0.0) && (X <= a.wm1) && (Y >= 0.0) && (Y <= a.hm1);
   if (!inside) return cost_dead;
-  return band_sample_cost<INTERP>(a, (float)X, (float)Y, r0, r1, r2);
+  return band_sample_cost<INTERP>(a, (float)X, (float)Y, r0, r1, r2, wr);
 }
 
 template <int N> struct IntC { static constexpr int value = N; };
+
+// A sample whose footprint touches the image border (cv2.remap's BORDER_REPLICATE path: taps clamped to the frame, ONE
+// running sum over the taps in row-major order -- not the row sums of an interior footprint) taken from the staged
+// window: the clamped taps of such a sample lie inside the window whenever the sample itself does.  The pixels of
+// the frame's outermost columns and rows produce these for most labels (0.4 % of the samples, but one lane is enough
+// to send its warp here: 4.5 % of the warp-samples at Sintel size), and the global-memory gather they used to take
+// cost 12 % of the kernel (profiles/r4n_ablation_study.jsonl).  win_s: shared address of texel (0, 0).
+template <int INTERP>
+__device__ __noinline__ F3 sample_window_border(uint32_t win_s, uint32_t pitch, uint32_t wt_s, int w, int frame_h, int sx, int sy) {
+  constexpr int kTaps = (INTERP == MRF_INTERP_CUBIC) ? 4 : 2;
+  constexpr int kOff = (INTERP == MRF_INTERP_CUBIC) ? 1 : 0;
+  const int ix0 = (sx >> 5) - kOff, iy0 = (sy >> 5) - kOff;
+  float wxa[4], wya[4];
+  lds128(wt_s + (uint32_t)(sx & 31) * 16u, wxa[0], wxa[1], wxa[2], wxa[3]);
+  lds128(wt_s + (uint32_t)(sy & 31) * 16u, wya[0], wya[1], wya[2], wya[3]);
+  F3 acc;
+#pragma unroll
+  for (int j = 0; j < kTaps; ++j) {
+    const int yy = max(0, min(frame_h - 1, iy0 + j));
+    const uint32_t row = win_s + (uint32_t)yy * pitch;
+#pragma unroll
+    for (int i = 0; i < kTaps; ++i) {
+      const int xx = max(0, min(w - 1, ix0 + i));
+      const float wgt = wya[j] * wxa[i];
+      float tx, ty, tz, tw;
+      lds128(row + (uint32_t)xx * 16u, tx, ty, tz, tw);
+      const float px = tx * wgt, py = ty * wgt, pz = tz * wgt;
+      if (i == 0 && j == 0) { acc.x = px; acc.y = py; acc.z = pz; }
+      else { acc.x = acc.x + px; acc.y = acc.y + py; acc.z = acc.z + pz; }
+    }
+  }
+  return acc;
+}
+// the clamped footprint of (sx, sy) lies inside the staged window s_win = (wx0, wy0, ww, wh)
+template <int INTERP>
+__device__ __forceinline__ bool border_in_window(const int* s_win, int w, int frame_h, int sx, int sy) {
+  constexpr int kTaps = (INTERP == MRF_INTERP_CUBIC) ? 4 : 2;
+  constexpr int kOff = (INTERP == MRF_INTERP_CUBIC) ? 1 : 0;
+  const int ix0 = (sx >> 5) - kOff, iy0 = (sy >> 5) - kOff;
+  const int cx0 = max(0, min(w - 1, ix0)), cx1 = max(0, min(w - 1, ix0 + kTaps - 1));
+  const int cy0 = max(0, min(frame_h - 1, iy0)), cy1 = max(0, min(frame_h - 1, iy0 + kTaps - 1));
+  const int wx0 = s_win[0], wy0 = s_win[1], ww = s_win[2], wh = s_win[3];
+  return cx0 >= wx0 && cx1 < wx0 + ww && cy0 >= wy0 && cy1 < wy0 + wh;
+}
 
 struct __align__(16) LabelRec { double ab, den, rden, safe; };   // safe: 1.0 / 0.0
 
@@ -603,7 +656,8 @@ __device__ __forceinline__ void cost_volume_block(const CVArgs& a, unsigned char
       if (any_cold) {                                         // rare: pole / degenerate operands, window or border miss
 #pragma unroll
         for (int g = 0; g < G; ++g)
-          if (sc[g].cold) cf[g] = cold_cost<INTERP>(a, lab_s + (uint32_t)(l + g) * 32u, n, xk, yk, t1, t2, ref_s, cost_dead);
+          if (sc[g].cold) cf[g] = cold_cost<INTERP>(a, lab_s + (uint32_t)(l + g) * 32u, n, xk, yk, t1, t2, ref_s, cost_dead,
+                                                    WinRef{STAGED ? s_win : nullptr, win_s, pitch, wt_s});
       }
 #pragma unroll
       for (int g = 0; g < G; ++g) {
@@ -682,8 +736,11 @@ __device__ __forceinline__ void cost_volume_block(const CVArgs& a, unsigned char
                 else { J.x = J.x + row.x; J.y = J.y + row.y; J.z = J.z + row.z; }
               }
             }
+          } else if (STAGED && border_in_window<INTERP>(s_win, a.w, a.frame_h, sx, sy)) {
+            // footprint at the image border, clamped taps inside the staged window
+            J = sample_window_border<INTERP>(win_s, pitch, wt_s, a.w, a.frame_h, sx, sy);
           } else {
-            // footprint touches the image border or leaves the staged window: gather from global
+            // footprint leaves the staged window: gather from global
             // memory; for row-band inputs check the halo (taps of an in-frame sample: rows iy-1..iy+2)
             const int iy = sy >> 5;
             const int ya = max(0, min(a.frame_h - 1, iy - 1)), yb = max(0, min(a.frame_h - 1, iy + 2));

@@ -22,6 +22,7 @@ def main():
     ap.add_argument("--shape", default="sintel")
     ap.add_argument("--reps", type=int, default=20)
     ap.add_argument("--variants", default="")
+    ap.add_argument("--labels", type=int, default=51, help="labels evaluated per launch (the first n of the triplet's 51)")
     args = ap.parse_args()
     hw = synth.SHAPES[args.shape]
     h, w = hw
@@ -52,7 +53,7 @@ def main():
             for f in (1,):
                 def run():
                     return device.cost_volume(ref64, tex[f], None, H_ar[f], q_ar[f], 0.0, 0.0, nonrigid=nonrigid, interp=interp,
-                                              variant=variant, out=out, state=buf.state, frame=f, n_labels=51)
+                                              variant=variant, out=out, state=buf.state, frame=f, n_labels=args.labels)
                 for _ in range(3):
                     _, mn, am = run()
                 torch.cuda.synchronize()
@@ -66,7 +67,7 @@ def main():
                     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                     e0.record(); run(); e1.record(); e1.synchronize()
                     ts.append(e0.elapsed_time(e1))
-                res.append(dict(shape=args.shape, interp=interp, variant=variant, frame=f, ms_median=float(np.median(ts)),
+                res.append(dict(shape=args.shape, interp=interp, variant=variant, frame=f, labels=args.labels, ms_median=float(np.median(ts)),
                                 ms_min=float(min(ts)), same_bits_as_first=same))
                 print(json.dumps(res[-1]), flush=True)
 

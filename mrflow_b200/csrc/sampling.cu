@@ -6,26 +6,11 @@
 //    oracle/cvemul.py (rgb2gray32, gaussian_blur3); the kernels below follow that specification.
 //  * mrf_warp_sample: structure_refinement/interpolate_through_H.py:7-51 (compute_derivs=False).
 //
-// Both are streaming kernels (one thread per output element, coalesced along x); the gray plane
-// and the gradient stencil are served from L1/L2, so HBM traffic is the compulsory
-// read-RGB / write-channels.
+// One thread per output element, coalesced along x; the channel kernel stages its tile in shared memory, so HBM
+// traffic is the compulsory read-RGB / write-channels.
 #include "sampling.cuh"
 
 namespace mrf {
-
-// cv2.cvtColor(fp32, COLOR_RGB2GRAY): fma(B, 0.114f, fma(R, 0.299f, G*0.587f)); then
-// .astype('float64') * 255.0  (optimize_structure_single_scale.py:352)
-template <typename T>
-__global__ void __launch_bounds__(256)
-k_gray(const T* __restrict__ rgb, long long n, double* __restrict__ gray) {
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n;
-       i += (long long)gridDim.x * blockDim.x) {
-    // I.astype('float32') when T = double
-    const float r = (float)rgb[3 * i], g = (float)rgb[3 * i + 1], b = (float)rgb[3 * i + 2];
-    const float y = fmaf(b, 0.114f, fmaf(r, 0.299f, g * 0.587f));
-    gray[i] = (double)y * 255.0;
-  }
-}
 
 __device__ __forceinline__ int reflect101(int i, int n) {
   if (i < 0) i = -i;
@@ -33,46 +18,65 @@ __device__ __forceinline__ int reflect101(int i, int n) {
   return i;
 }
 
-// np.gradient along one axis, unit spacing, edge_order=1.
-__device__ __forceinline__ double grad_y(const double* __restrict__ g, int h, int w, int y, int x) {
-  if (y == 0) return g[(long long)w + x] - g[x];
-  if (y == h - 1) return g[(long long)(h - 1) * w + x] - g[(long long)(h - 2) * w + x];
-  return (g[(long long)(y + 1) * w + x] - g[(long long)(y - 1) * w + x]) / 2.0;
-}
-__device__ __forceinline__ double grad_x(const double* __restrict__ g, int h, int w, int y, int x) {
-  const double* row = g + (long long)y * w;
-  if (x == 0) return row[1] - row[0];
-  if (x == w - 1) return row[w - 1] - row[w - 2];
-  return (row[x + 1] - row[x - 1]) / 2.0;
-}
-
-// cv2.GaussianBlur(fp64, (3,3), sigmaX=-1): separable [1/4,1/2,1/4], BORDER_REFLECT_101; row pass
-// (p[x-1]*.25 + p[x]*.5) + p[x+1]*.25, column pass r[y]*.5 + (r[y-1] + r[y+1])*.25.
-template <bool DY>
-__device__ __forceinline__ double blur3_of_grad(const double* __restrict__ g, int h, int w, int y, int x) {
-  double r[3];
+// gray, gradients and blur of one 32 x 8 tile in ONE kernel: the tile's gray values (2-pixel halo) are formed from
+// RGB in shared memory -- cv2.cvtColor(fp32, COLOR_RGB2GRAY) = fma(B, 0.114f, fma(R, 0.299f, G*0.587f)), then
+// .astype('float64') * 255.0 (:352) --, the two np.gradient planes (1-pixel halo) from those, and the 3x3 Gaussian
+// (cv2.GaussianBlur(fp64, (3,3), sigmaX=-1): row pass (p[x-1]*.25 + p[x]*.5) + p[x+1]*.25, column pass
+// r[y]*.5 + (r[y-1] + r[y+1])*.25, BORDER_REFLECT_101) from those.  The reflected blur taps of a tile at the frame
+// border fall inside the tile's own gradient halo.  One launch per frame, no gray plane in HBM; the operations and
+// their order are oracle/cvemul.py's, so the result is bit-identical to OpenCV's.
+constexpr int kChTX = 32, kChTY = 8;
+template <typename T>
+__global__ void __launch_bounds__(kChTX * kChTY)
+k_channels(const T* __restrict__ rgb, int h, int w, double* __restrict__ ch64, float4* __restrict__ texels) {
+  __shared__ double s_gray[kChTY + 4][kChTX + 4];
+  __shared__ double s_gy[kChTY + 2][kChTX + 2];
+  __shared__ double s_gx[kChTY + 2][kChTX + 2];
+  const int x0 = blockIdx.x * kChTX, y0 = blockIdx.y * kChTY;
+  for (int k = threadIdx.x; k < (kChTY + 4) * (kChTX + 4); k += kChTX * kChTY) {
+    const int r = k / (kChTX + 4), c = k - r * (kChTX + 4);
+    const int Y = y0 - 2 + r, X = x0 - 2 + c;
+    if (Y >= 0 && Y < h && X >= 0 && X < w) {
+      const long long i = (long long)Y * w + X;
+      // I.astype('float32') when T = double; cv2.cvtColor(fp32, COLOR_RGB2GRAY); .astype('float64') * 255.0
+      const float rr = (float)rgb[3 * i], gg = (float)rgb[3 * i + 1], bb = (float)rgb[3 * i + 2];
+      const float yv = fmaf(bb, 0.114f, fmaf(rr, 0.299f, gg * 0.587f));
+      s_gray[r][c] = (double)yv * 255.0;
+    }
+  }
+  __syncthreads();
+  for (int k = threadIdx.x; k < (kChTY + 2) * (kChTX + 2); k += kChTX * kChTY) {
+    const int r = k / (kChTX + 2), c = k - r * (kChTX + 2);
+    const int Y = y0 - 1 + r, X = x0 - 1 + c;
+    if (Y >= 0 && Y < h && X >= 0 && X < w) {
+      const int gr = r + 1, gc = c + 1;                                  // the same pixel in s_gray
+      // np.gradient, unit spacing, edge_order = 1
+      double dy, dx;
+      if (Y == 0) dy = s_gray[gr + 1][gc] - s_gray[gr][gc];
+      else if (Y == h - 1) dy = s_gray[gr][gc] - s_gray[gr - 1][gc];
+      else dy = (s_gray[gr + 1][gc] - s_gray[gr - 1][gc]) / 2.0;
+      if (X == 0) dx = s_gray[gr][gc + 1] - s_gray[gr][gc];
+      else if (X == w - 1) dx = s_gray[gr][gc] - s_gray[gr][gc - 1];
+      else dx = (s_gray[gr][gc + 1] - s_gray[gr][gc - 1]) / 2.0;
+      s_gy[r][c] = dy; s_gx[r][c] = dx;
+    }
+  }
+  __syncthreads();
+  const int x = x0 + (threadIdx.x & 31), y = y0 + (threadIdx.x >> 5);
+  if (x >= w || y >= h) return;
+  // cv2.GaussianBlur(fp64, (3,3), sigmaX=-1): [1/4,1/2,1/4] separable, BORDER_REFLECT_101
+  const int ca = reflect101(x - 1, w) - (x0 - 1), cb = x - (x0 - 1), cc = reflect101(x + 1, w) - (x0 - 1);
+  double ry[3], rx[3];
 #pragma unroll
   for (int j = 0; j < 3; ++j) {
-    const int yy = reflect101(y + j - 1, h);
-    const int xa = reflect101(x - 1, w), xc = reflect101(x + 1, w);
-    const double a = DY ? grad_y(g, h, w, yy, xa) : grad_x(g, h, w, yy, xa);
-    const double b = DY ? grad_y(g, h, w, yy, x) : grad_x(g, h, w, yy, x);
-    const double c = DY ? grad_y(g, h, w, yy, xc) : grad_x(g, h, w, yy, xc);
-    r[j] = (a * 0.25 + b * 0.5) + c * 0.25;
+    const int rj = reflect101(y + j - 1, h) - (y0 - 1);
+    ry[j] = (s_gy[rj][ca] * 0.25 + s_gy[rj][cb] * 0.5) + s_gy[rj][cc] * 0.25;
+    rx[j] = (s_gx[rj][ca] * 0.25 + s_gx[rj][cb] * 0.5) + s_gx[rj][cc] * 0.25;
   }
-  return r[1] * 0.5 + (r[0] + r[2]) * 0.25;
-}
-
-__global__ void __launch_bounds__(256)
-k_channels(const double* __restrict__ gray, int h, int w, double* __restrict__ ch64,
-           float4* __restrict__ texels) {
-  const int x = blockIdx.x * 32 + (threadIdx.x & 31);
-  const int y = blockIdx.y * 8 + (threadIdx.x >> 5);
-  if (x >= w || y >= h) return;
+  const double gy = ry[1] * 0.5 + (ry[0] + ry[2]) * 0.25;
+  const double gx = rx[1] * 0.5 + (rx[0] + rx[2]) * 0.25;
   const long long i = (long long)y * w + x;
-  const double g = gray[i];
-  const double gy = blur3_of_grad<true>(gray, h, w, y, x);
-  const double gx = blur3_of_grad<false>(gray, h, w, y, x);
+  const double g = s_gray[(threadIdx.x >> 5) + 2][(threadIdx.x & 31) + 2];
   if (ch64) { ch64[3 * i] = g; ch64[3 * i + 1] = gy; ch64[3 * i + 2] = gx; }
   if (texels) texels[i] = make_float4((float)g, (float)gy, (float)gx, 0.0f);
 }
@@ -143,14 +147,11 @@ extern "C" {
 
 int mrf_prepare_channels(const void* rgb, int rgb_is_f64, int h, int w, double* ch64, float* texels,
                          double* gray_scratch, mrf_stream_t stream) {
-  MRF_CHECK_ARG(rgb && gray_scratch && h >= 2 && w >= 2 && (ch64 || texels));
-  const long long n = (long long)h * w;
-  if (rgb_is_f64) k_gray<double><<<grid_for(n), 256, 0, S(stream)>>>((const double*)rgb, n, gray_scratch);
-  else            k_gray<float><<<grid_for(n), 256, 0, S(stream)>>>((const float*)rgb, n, gray_scratch);
-  int rc = check_launch("mrf_prepare_channels/gray");
-  if (rc) return rc;
-  dim3 grid(cdiv(w, 32), cdiv(h, 8));
-  k_channels<<<grid, 256, 0, S(stream)>>>(gray_scratch, h, w, ch64, (float4*)texels);
+  MRF_CHECK_ARG(rgb && h >= 2 && w >= 2 && (ch64 || texels));
+  (void)gray_scratch;   /* kept in the signature; the gray plane now lives in shared memory only */
+  dim3 grid(cdiv(w, kChTX), cdiv(h, kChTY));
+  if (rgb_is_f64) k_channels<double><<<grid, kChTX * kChTY, 0, S(stream)>>>((const double*)rgb, h, w, ch64, (float4*)texels);
+  else            k_channels<float><<<grid, kChTX * kChTY, 0, S(stream)>>>((const float*)rgb, h, w, ch64, (float4*)texels);
   return check_launch("mrf_prepare_channels/channels");
 }
 

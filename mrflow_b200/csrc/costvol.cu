@@ -150,16 +150,17 @@ __device__ __forceinline__ bool tame(double v) {
   return (ex - 923u) <= 200u;
 }
 
-// log(u) for u >= 1 (u = 1 + z of the Lorentzian, utils/robust_functions.py:52,58).  Argument
+// The bicubic kernel's log(u), u >= 1 (the kernel is bound by shared-memory wavefronts there, and the table form's
+// scattered load costs more than its fp64 instructions save: 0.310 against 0.301 ms per frame).  Argument
 // reduction u = m*2^e with m in [sqrt(1/2), sqrt(2)), s = (m-1)/(m+1), log m = 2 atanh(s) as an
 // odd polynomial through s^15; relative error < 2^-43, i.e. the fp32 cost the kernel stores is the
 // correctly rounded one except for about one sample in 2^19 (then off by one fp32 ulp, 6e-8
 // relative, against the 1e-5 bar).  numpy's own log is only specified to < 1 ulp of fp64 either.
-__constant__ double kAtanhC[7] = {1.0 / 3.0, 1.0 / 5.0, 1.0 / 7.0, 1.0 / 9.0, 1.0 / 11.0, 1.0 / 13.0, 1.0 / 15.0};
 __constant__ double kLn2 = 0.6931471805599453094;
 __constant__ double kThird = 1.0 / 3.0;
+__constant__ double kAtanhC[7] = {1.0 / 3.0, 1.0 / 5.0, 1.0 / 7.0, 1.0 / 9.0, 1.0 / 11.0, 1.0 / 13.0, 1.0 / 15.0};
 
-__device__ __forceinline__ double log_ge1(double u) {
+__device__ __forceinline__ double log_ge1_series(double u) {
   int hi = __double2hiint(u);
   const int lo = __double2loint(u);
   const bool special = hi >= 0x7ff00000;                // inf / NaN: returned as they are
@@ -187,6 +188,46 @@ __device__ __forceinline__ double log_ge1(double u) {
   const double two_s = sv + sv;
   const double res = fma((double)e, kLn2, fma(two_s, pl, two_s));
   return special ? u : res;
+}
+
+
+// The bilinear kernel's log(u), u >= 1 (that kernel is bound by the fp64 pipe: -5 % with this form;
+// utils/robust_functions.py:52,58).  u = m * 2^e with m in [1, 2);
+// the top seven mantissa bits pick (RN(1/c), RN(log c)) for the midpoint c of m's 1/128-wide interval from a 2 KB table
+// in shared memory (log_table.inc; the first interval uses c = 1, so that r = m - 1 is exact and the relative
+// accuracy holds as u -> 1); r = m/c - 1 as one fma, |r| < 2^-7; log m = log c + log1p(r), log1p as its Taylor
+// polynomial through r^6 (next term < 2^-44.8 of the result).  Relative error < 2^-44, i.e. the fp32 cost the kernel
+// stores is the correctly rounded one except for about one sample in 2^20 (then off by one fp32 ulp, 6e-8 relative,
+// against the 1e-5 bar).  numpy's own log is only specified to < 1 ulp of fp64 either.  Nine fp64 instructions and
+// one shared-memory load; the argument-reduced atanh series it replaces took 21 and a reciprocal.
+__device__ const double kLogTab[128][2] = {
+#include "log_table.inc"
+};
+__constant__ double kLog1pC[4] = {-1.0 / 6.0, 1.0 / 5.0, -1.0 / 4.0, 1.0 / 3.0};
+
+__device__ __forceinline__ double log_ge1_table(double u, uint32_t tab_s) {
+  const int hi = __double2hiint(u);
+  const int lo = __double2loint(u);
+  const bool special = hi >= 0x7ff00000;                // inf / NaN: returned as they are
+  const int e = (hi >> 20) - 1023;
+  const double m = __hiloint2double((hi & 0x000fffff) | 0x3ff00000, lo);
+  double rc, lc;
+  asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(rc), "=d"(lc) : "r"(tab_s + (((uint32_t)hi >> 13) & 127u) * 16u));
+  const double r = fma(m, rc, -1.0);
+  double q = fma(r, kLog1pC[0], kLog1pC[1]);
+  q = fma(r, q, kLog1pC[2]);
+  q = fma(r, q, kLog1pC[3]);
+  q = fma(r, q, -0.5);
+  const double t = fma(r * r, q, r);                    // log1p(r)
+  const double res = fma((double)e, kLn2, lc + t);
+  return special ? u : res;
+}
+
+// one log per sampler: every variant of a sampler (staged, gather, the cold paths) uses the same one
+template <int INTERP>
+__device__ __forceinline__ double log_ge1(double u, uint32_t tab_s) {
+  if constexpr (INTERP == MRF_INTERP_LINEAR) return log_ge1_table(u, tab_s);
+  else return log_ge1_series(u);
 }
 
 // Reciprocal of a tame double, correctly rounded: hardware seed (MUFU.RCP64H, ~2^-23) and three
@@ -246,13 +287,13 @@ __device__ __noinline__ float slow_sample_cost(const CVArgs& a, double ab, doubl
 
 // A sample with exact coordinates whose footprint touches the image border or leaves the staged
 // window: global-memory gather (for row-band inputs with the halo check), then the same residual / rho.
-struct WinRef { const int* s_win; uint32_t win_s, pitch, wt_s; };   // the staged window (s_win = nullptr: none)
-template <int INTERP> __device__ F3 sample_window_border(uint32_t win_s, uint32_t pitch, uint32_t wt_s, int w, int frame_h, int sx, int sy);
+struct WinRef { const int* s_win; uint32_t win_s, pitch, wt_s, log_s; };   // the staged window (s_win = nullptr: none), the log table
+template <int INTERP> __device__ __noinline__ F3 sample_window_border(uint32_t win_s, uint32_t pitch, uint32_t wt_s, int w, int frame_h, int sx, int sy);
 template <int INTERP> __device__ __forceinline__ bool border_in_window(const int* s_win, int w, int frame_h, int sx, int sy);
 
 template <int INTERP>
 __device__ __noinline__ float band_sample_cost(const CVArgs& a, float xf, float yf, double c0, double c1, double c2,
-                                               const WinRef wr = WinRef{nullptr, 0u, 0u, 0u}) {
+                                               const WinRef wr) {
   int iy, fy; cv_quantise(yf, iy, fy);
   const int lo = (INTERP == MRF_INTERP_CUBIC) ? -1 : 0, hi = (INTERP == MRF_INTERP_CUBIC) ? 2 : 1;
   const int ya = max(0, min(a.frame_h - 1, iy + lo)), yb = max(0, min(a.frame_h - 1, iy + hi));
@@ -273,7 +314,7 @@ __device__ __noinline__ float band_sample_cost(const CVArgs& a, float xf, float 
   const double e2 = ((double)J.z - c2) * a.cw2;
   const double Iz = div_rc((e0 + e1) + e2, 3.0, kThird);
   double cst;
-  if (a.rho == MRF_RHO_LORENTZIAN && tame(a.s2)) cst = log_ge1(1.0 + div_rc(Iz * Iz, a.s2, a.rs2));
+  if (a.rho == MRF_RHO_LORENTZIAN && tame(a.s2)) cst = log_ge1<INTERP>(1.0 + div_rc(Iz * Iz, a.s2, a.rs2), wr.log_s);
   else cst = (a.rho == MRF_RHO_NONE) ? Iz : rho_eval(a.rho, Iz * Iz, a.rho_param);
   return (float)cst;
 }
@@ -433,6 +474,7 @@ template <int INTERP, bool STAGED, int LAYOUT, int FORM>
 __device__ __forceinline__ void cost_volume_block(const CVArgs& a, unsigned char* dyn_smem) {
   __shared__ LabelRec s_lab[kMaxLabels];    // A*B, B*A/mu - 1, RN(1/that), exact-sequence-safe flag
   __shared__ __align__(16) float4 s_wt[32]; // OpenCV's interpolation table: weights at frac/32
+  __shared__ __align__(16) double s_log[INTERP == MRF_INTERP_LINEAR ? 128 : 1][2];   // log_ge1_table's table (bilinear only)
   __shared__ double s_c[2];                 // min / max over labels of A*B / (B*A/mu - 1)
   __shared__ double s_ref[3][kThreads];     // this thread's reference-frame channels (register relief)
   __shared__ float s_red[kTY][4];
@@ -469,6 +511,10 @@ __device__ __forceinline__ void cost_volume_block(const CVArgs& a, unsigned char
     rec.rden = safe ? 1.0 / den : __longlong_as_double(0x7FF8000000000000ll);
     rec.safe = safe ? 1.0 : 0.0;
     s_lab[l] = rec;
+  }
+  if (INTERP == MRF_INTERP_LINEAR && threadIdx.x >= 64 && threadIdx.x < 192) {
+    const int k = threadIdx.x - 64;
+    s_log[k][0] = kLogTab[k][0]; s_log[k][1] = kLogTab[k][1];
   }
   if (threadIdx.x >= 32 && threadIdx.x < 64) {
     const int fr = threadIdx.x - 32;
@@ -580,6 +626,7 @@ __device__ __forceinline__ void cost_volume_block(const CVArgs& a, unsigned char
   uint32_t win_base = smem_u32(dyn_smem);                    // any valid footprint address for unused samples
   uint32_t win_s = win_base - (uint32_t)(wy0 * ww + wx0) * 16u;             // address of texel (0, 0)
   uint32_t wt_s = smem_u32(s_wt);
+  const uint32_t log_s = smem_u32(s_log);
   uint32_t lab_s = smem_u32(s_lab);
   uint32_t ref_s = smem_u32(&s_ref[0][threadIdx.x]);
   const uint32_t pitch = (uint32_t)ww * 16u;
@@ -640,10 +687,10 @@ __device__ __forceinline__ void cost_volume_block(const CVArgs& a, unsigned char
       }
       if (lor_unit) {
 #pragma unroll
-        for (int g = 0; g < G; ++g) cst[g] = log_ge1(1.0 + Iz[g] * Iz[g]);                        // :52, sigma = 1
+        for (int g = 0; g < G; ++g) cst[g] = log_ge1<INTERP>(1.0 + Iz[g] * Iz[g], log_s);                        // :52, sigma = 1
       } else if (lor_fast) {
 #pragma unroll
-        for (int g = 0; g < G; ++g) cst[g] = log_ge1(1.0 + div_rc(Iz[g] * Iz[g], a.s2, a.rs2));   // :52
+        for (int g = 0; g < G; ++g) cst[g] = log_ge1<INTERP>(1.0 + div_rc(Iz[g] * Iz[g], a.s2, a.rs2), log_s);   // :52
       } else {
 #pragma unroll
         for (int g = 0; g < G; ++g)
@@ -657,7 +704,7 @@ __device__ __forceinline__ void cost_volume_block(const CVArgs& a, unsigned char
 #pragma unroll
         for (int g = 0; g < G; ++g)
           if (sc[g].cold) cf[g] = cold_cost<INTERP>(a, lab_s + (uint32_t)(l + g) * 32u, n, xk, yk, t1, t2, ref_s, cost_dead,
-                                                    WinRef{STAGED ? s_win : nullptr, win_s, pitch, wt_s});
+                                                    WinRef{STAGED ? s_win : nullptr, win_s, pitch, wt_s, log_s});
       }
 #pragma unroll
       for (int g = 0; g < G; ++g) {
@@ -761,10 +808,10 @@ __device__ __forceinline__ void cost_volume_block(const CVArgs& a, unsigned char
           const double Iz = div_rc((e0 + e1) + e2, 3.0, kThird);   // .mean(axis=2): sum / 3.0, exact
           double cst;
           if (lor_unit) {
-            cst = log_ge1(1.0 + Iz * Iz);                     // sigma = 1: x / sigma**2 == x exactly  :52
+            cst = log_ge1<INTERP>(1.0 + Iz * Iz, log_s);                     // sigma = 1: x / sigma**2 == x exactly  :52
           } else if (lor_fast) {
             const double z = div_rc(Iz * Iz, a.s2, a.rs2);    // x / sigma**2  :52
-            cst = log_ge1(1.0 + z);
+            cst = log_ge1<INTERP>(1.0 + z, log_s);
           } else {
             cst = (a.rho == MRF_RHO_NONE) ? Iz : rho_eval(a.rho, Iz * Iz, a.rho_param);   // :302
           }

@@ -17,14 +17,16 @@
 // image of its epipolar segment under H), copies that window of the neighbour frame's packed
 // texels (gray, d/dy, d/dx, 0) into shared memory with one TMA bulk copy per window row
 // (cp.async.bulk global->shared completing on an mbarrier), and gathers the 16 bicubic taps with
-// LDS.128.  Samples whose footprint leaves the staged window (labels near the pole of the
-// parallax formula, very large parallax) take the global-memory gather path, which is also the
-// whole kernel in the unstaged variant -- results are bit-identical either way.
+// LDS.128.  A sample whose footprint touches the image border (cv2.remap's clamped, running-sum
+// order) takes its taps from the window too (sample_window_border); one whose footprint leaves the
+// staged window (labels near the pole of the parallax formula, very large parallax) takes the
+// global-memory gather path, which is also the whole kernel in the unstaged variant -- results are
+// bit-identical either way.
 //
 // Arithmetic is written operation by operation in the reference's order and compiled with
 // -fmad=false, so the fp64 coordinates, the 1/32-px bins, the fp32 tap sums and the fp64 residual
-// are the oracle's bit for bit; only log() (relative error < 2^-43 before the fp32 rounding) can
-// differ.  Divisions by per-label / per-launch constants and the two projective divisions that share
+// are the oracle's bit for bit; only log() (relative error < 2^-43 before the fp32 rounding; one
+// implementation per sampler, log_ge1) can differ.  Divisions by per-label / per-launch constants and the two projective divisions that share
 // a divisor are evaluated with a reciprocal and exact FMA remainder corrections (div_rc), which
 // returns the correctly rounded quotient -- the same bits as a division -- at a fifth of the cost.
 #include "sampling.cuh"
@@ -632,7 +634,8 @@ __device__ __forceinline__ void cost_volume_block(const CVArgs& a, unsigned char
   const uint32_t pitch = (uint32_t)ww * 16u;
   // keep the shared-window addresses in registers (the compiler would otherwise rebuild them from
   // the CTA id on every iteration)
-  asm volatile("" : "+r"(win_s), "+r"(wt_s), "+r"(lab_s), "+r"(ref_s), "+r"(win_base));
+  if constexpr (FORM == 2) asm volatile("" : "+r"(win_s), "+r"(wt_s), "+r"(lab_s), "+r"(ref_s), "+r"(win_base));
+  else asm volatile("" : "+r"(win_s), "+r"(wt_s), "+r"(lab_s), "+r"(ref_s));      // win_base: only the grouped form's stand-in address
   double xk = xd, yk = yd;                                  // pinned copies: not rebuilt from the thread id
   asm volatile("" : "+d"(xk), "+d"(yk));
   const float cost_dead = (float)rho_eval(a.rho, 0.0, a.rho_param);

@@ -218,7 +218,8 @@ int mrf_masked_minmax_f64(const double* S, const uint8_t* zero_mask, int rows, i
  * produces it; fp64 input is rounded to fp32 first, the reference's I.astype('float32').
  * Outputs (either may be NULL): ch64 fp64 [h,w,3] interleaved = dstack(gray, gy, gx);
  * texels fp32 [h,w,4] = (gray, gy, gx, 0) each rounded to fp32 -- the sampler's input
- * (interpolation.py:76 casts the image to fp32).  gray_scratch: h*w doubles. */
+ * (interpolation.py:76 casts the image to fp32).  One launch per frame: gray, gradients and blur of a tile are
+ * formed in shared memory.  gray_scratch: unused since then (kept in the signature; may be NULL). */
 int mrf_prepare_channels(const void* rgb, int rgb_is_f64, int h, int w, double* ch64, float* texels,
                          double* gray_scratch, mrf_stream_t stream);
 

@@ -347,8 +347,7 @@ def prepare_channels(rgb, want_ch64=True, want_texels=True):
     dev = rgb.device
     ch64 = torch.empty((h, w, 3), dtype=F64, device=dev) if want_ch64 else None
     tex = torch.empty((h, w, 4), dtype=F32, device=dev) if want_texels else None
-    gray = torch.empty((h, w), dtype=F64, device=dev)
-    check(_lib.lib().mrf_prepare_channels(_p(rgb), int(rgb.dtype == F64), h, w, _p(ch64), _p(tex), _p(gray), _stream()),
+    check(_lib.lib().mrf_prepare_channels(_p(rgb), int(rgb.dtype == F64), h, w, _p(ch64), _p(tex), None, _stream()),
           "mrf_prepare_channels")
     return ch64, tex
 

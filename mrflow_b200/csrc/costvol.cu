@@ -145,6 +145,16 @@ __device__ __forceinline__ double div_rc(double a, double d, double rd) {
   r = fma(-d, q, a);
   return fma(r, rd, q);
 }
+// a / 3 (the channel mean, `.mean(axis=2)`), correctly rounded with ONE correction.  With c = RN(1/3) = (1/3)(1 - 2^-54):
+// q0 = RN(a c) is within 1.5 ulp of q* = a/3, the remainder r = a - 3 q0 is exact (a small multiple of ulp(q0)), and
+// q0 + r c = q* - (q* - q0) 2^-54, i.e. q* displaced by less than 2^-54 ulp.  a/3 is never closer than ulp/6 to a rounding
+// boundary (3 x a 54-bit midpoint is odd in a bit position below ulp(a)), so the final rounding returns RN(a/3).
+// tests/test_exact_division.py replays the sequence in rational arithmetic.
+__device__ __forceinline__ double div3(double a, double third) {
+  const double q = a * third;
+  const double r = fma(-3.0, q, a);
+  return fma(r, third, q);
+}
 // exponent of a double within [2^-100, 2^100] (and finite, non-zero): the range in which the
 // sequences above cannot over/underflow for this kernel's operands
 __device__ __forceinline__ bool tame(double v) {
@@ -314,7 +324,7 @@ __device__ __noinline__ float band_sample_cost(const CVArgs& a, float xf, float 
   const double e0 = ((double)J.x - c0) * a.cw0;
   const double e1 = ((double)J.y - c1) * a.cw1;
   const double e2 = ((double)J.z - c2) * a.cw2;
-  const double Iz = div_rc((e0 + e1) + e2, 3.0, kThird);
+  const double Iz = div3((e0 + e1) + e2, kThird);
   double cst;
   if (a.rho == MRF_RHO_LORENTZIAN && tame(a.s2)) cst = log_ge1<INTERP>(1.0 + div_rc(Iz * Iz, a.s2, a.rs2), wr.log_s);
   else cst = (a.rho == MRF_RHO_NONE) ? Iz : rho_eval(a.rho, Iz * Iz, a.rho_param);
@@ -641,6 +651,7 @@ __device__ __forceinline__ void cost_volume_block(const CVArgs& a, unsigned char
   const float cost_dead = (float)rho_eval(a.rho, 0.0, a.rho_param);
   const bool lor_fast = (a.rho == MRF_RHO_LORENTZIAN) && tame(a.s2);
   const bool lor_unit = lor_fast && (a.s2 == 1.0);          // sigma = 1 (the default)
+  const bool unit_w12 = (a.cw1 == 1.0) && (a.cw2 == 1.0);   // the gradient channels' weights (:371)
   // a pixel whose n is not tame poisons its own fast path the same way
   const double n_fast = ((n == 0.0) || tame(n)) ? n : __longlong_as_double(0x7FF8000000000000ll);
   float best = 0.f; int best_l = 0;
@@ -684,9 +695,9 @@ __device__ __forceinline__ void cost_volume_block(const CVArgs& a, unsigned char
 #pragma unroll
       for (int g = 0; g < G; ++g) {
         const double e0 = ((double)J[g].x - r0) * a.cw0;      // :274
-        const double e1 = ((double)J[g].y - r1) * a.cw1;
-        const double e2 = ((double)J[g].z - r2) * a.cw2;
-        Iz[g] = div_rc((e0 + e1) + e2, 3.0, kThird);          // .mean(axis=2): sum / 3.0, exact
+        double e1 = (double)J[g].y - r1, e2 = (double)J[g].z - r2;
+        if (!unit_w12) { e1 = e1 * a.cw1; e2 = e2 * a.cw2; }  // x * 1.0 == x: the default weights (0.01, 1, 1) skip two products
+        Iz[g] = div3((e0 + e1) + e2, kThird);          // .mean(axis=2): sum / 3.0, exact
       }
       if (lor_unit) {
 #pragma unroll
@@ -806,9 +817,9 @@ __device__ __forceinline__ void cost_volume_block(const CVArgs& a, unsigned char
           asm volatile("ld.shared.f64 %0, [%1];" : "=d"(r1) : "r"(ref_s + (uint32_t)(kThreads * 8)));
           asm volatile("ld.shared.f64 %0, [%1];" : "=d"(r2) : "r"(ref_s + (uint32_t)(kThreads * 16)));
           const double e0 = ((double)J.x - r0) * a.cw0;       // :274
-          const double e1 = ((double)J.y - r1) * a.cw1;
-          const double e2 = ((double)J.z - r2) * a.cw2;
-          const double Iz = div_rc((e0 + e1) + e2, 3.0, kThird);   // .mean(axis=2): sum / 3.0, exact
+          double e1 = (double)J.y - r1, e2 = (double)J.z - r2;
+          if (!unit_w12) { e1 = e1 * a.cw1; e2 = e2 * a.cw2; } // x * 1.0 == x: the default weights (0.01, 1, 1) skip two products
+          const double Iz = div3((e0 + e1) + e2, kThird);   // .mean(axis=2): sum / 3.0, exact
           double cst;
           if (lor_unit) {
             cst = log_ge1<INTERP>(1.0 + Iz * Iz, log_s);                     // sigma = 1: x / sigma**2 == x exactly  :52
